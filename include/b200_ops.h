@@ -1,0 +1,223 @@
+/* b200_ops.h -- C ABI of the B200-native op-kernel layer (libb200tf.so).
+ *
+ * This is the drop-in boundary described in SURVEY.md section 8(b): plain pointers, sizes and
+ * ints only; no C++ or torch types cross it.  Every entry point sits where the reference's GPU
+ * op kernels call into StreamExecutor (tensorflow/stream_executor/stream.h: ThenBlasGemm :1154,
+ * ThenConvolveWithAlgorithm, ThenMemcpy :1482-1529, ThenMemZero :1531, ThenRecordEvent :214,
+ * BlockHostUntilDone :1591) or launch their own CUDA kernels; each declaration cites the
+ * reference code it replaces.  The thin OpKernel wrappers in
+ * simple_tensorflow_b200/csrc/tensorflow/core/kernels/ are the only intended callers.
+ *
+ * Conventions
+ *   - All data pointers are DEVICE pointers unless the name ends in _host.
+ *   - `stream` is a cudaStream_t / CUstream passed as void* (NULL = legacy default stream).
+ *     Every op only ENQUEUES work and returns (gpu_device.cc:337-399 contract); nothing in an op
+ *     entry point synchronises the device.
+ *   - Return value: 0 on success, otherwise a tensorflow::error::Code value
+ *     (tensorflow/core/lib/core/error_codes.proto): 3 INVALID_ARGUMENT, 8 RESOURCE_EXHAUSTED,
+ *     12 UNIMPLEMENTED, 13 INTERNAL.  b200_last_error() returns the message for the calling
+ *     thread; the wrapper turns both into a tensorflow::Status.
+ *   - dtype arguments use tensorflow::DataType numbering (framework/types.proto).
+ *   - Tensors are dense row-major (framework/tensor_types.h:25-28); images are NHWC, filters HWIO.
+ *   - There is NO CPU fallback: without a CUDA device every compute entry point returns
+ *     13 INTERNAL.
+ */
+#ifndef B200_OPS_H_
+#define B200_OPS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_API __attribute__((visibility("default")))
+
+/* tensorflow::error::Code subset */
+enum {
+  B200_OK = 0,
+  B200_INVALID_ARGUMENT = 3,
+  B200_RESOURCE_EXHAUSTED = 8,
+  B200_FAILED_PRECONDITION = 9,
+  B200_UNIMPLEMENTED = 12,
+  B200_INTERNAL = 13
+};
+
+/* tensorflow::DataType subset (framework/types.proto:13-40) */
+enum {
+  B200_DT_FLOAT = 1,
+  B200_DT_INT32 = 3,
+  B200_DT_INT64 = 9,
+  B200_DT_BFLOAT16 = 14
+};
+
+/* ------------------------------------------------------------------ library / device */
+B200_API const char* b200_version(void);
+B200_API const char* b200_last_error(void);
+/* Number of CUDA devices visible (0 without a GPU; never fails). */
+B200_API int b200_device_count(void);
+B200_API int b200_set_device(int ordinal);
+/* Kernels launched by this library in the calling process since load (all threads). */
+B200_API uint64_t b200_launch_count(void);
+/* MatMul/Conv precision for DT_FLOAT: 0 = single-pass TF32 tensor cores (default; inputs are
+ * truncated to 10 mantissa bits by the MMA, fp32 accumulate), 1 = SIMT fp32 FMA (IEEE fp32
+ * products, the reference Eigen path's arithmetic).  Shapes the TMA path cannot address
+ * (leading dimension not a multiple of 16 bytes) always use the SIMT kernel. */
+B200_API int b200_set_matmul_precision(int mode);
+B200_API int b200_get_matmul_precision(void);
+
+/* ------------------------------------------------------------------ StreamExecutor-level shim
+ * Mirrors Stream / StreamExecutor members the reference's GPU device uses
+ * (stream_executor/stream.h:116,189,214,1482-1531,1591; stream_executor_pimpl.h:110,191). */
+B200_API int b200_stream_create(void** stream);
+B200_API int b200_stream_destroy(void* stream);
+B200_API int b200_stream_synchronize(void* stream);          /* BlockHostUntilDone */
+B200_API int b200_stream_wait_event(void* stream, void* event); /* ThenWaitFor */
+B200_API int b200_event_create(void** event);
+B200_API int b200_event_destroy(void* event);
+B200_API int b200_event_record(void* event, void* stream);   /* ThenRecordEvent */
+B200_API int b200_event_synchronize(void* event);
+B200_API int b200_event_query(void* event);                  /* 0 done, 1 pending, <0 error */
+B200_API int b200_event_elapsed_ms(void* start, void* stop, float* ms);
+B200_API int b200_malloc(void** dptr, size_t bytes);         /* AllocateArray */
+B200_API int b200_free(void* dptr);
+B200_API int b200_host_malloc(void** hptr, size_t bytes);    /* HostMemoryAllocate (pinned) */
+B200_API int b200_host_free(void* hptr);
+B200_API int b200_memcpy_h2d_async(void* dst, const void* src_host, size_t bytes, void* stream);
+B200_API int b200_memcpy_d2h_async(void* dst_host, const void* src, size_t bytes, void* stream);
+B200_API int b200_memcpy_d2d_async(void* dst, const void* src, size_t bytes, void* stream);
+B200_API int b200_memset_async(void* dst, int byte_value, size_t bytes, void* stream); /* ThenMemZero */
+B200_API int b200_mem_info(size_t* free_bytes, size_t* total_bytes);
+
+/* ------------------------------------------------------------------ MatMul / BatchMatMul
+ * Replaces LaunchMatMul<GPUDevice,T,true>::launch -> ThenBlasGemm (core/kernels/matmul_op.cc:162-203).
+ * a is [m,k] (or [k,m] when transpose_a), b is [k,n] (or [n,k] when transpose_b), c is [m,n];
+ * same argument meaning as the op attrs (core/ops/math_ops.cc:1033-1040).  m,n,k > 0: the
+ * zero-size rules of MatMulOp::Compute (matmul_op.cc:240-253) stay in the OpKernel wrapper.
+ * dtype: DT_FLOAT (tf32 tensor cores, fp32 accumulate) or DT_BFLOAT16 (fp32 accumulate). */
+B200_API int b200_matmul(int dtype, const void* a, const void* b, void* c, int64_t m, int64_t n,
+                         int64_t k, int transpose_a, int transpose_b, void* stream);
+/* Replaces LaunchBatchMatMul<GPUDevice,Scalar>::Launch -> ThenBlasGemmBatchedWithScratch
+ * (core/kernels/batch_matmul_op_impl.h:297-363).  x is [batch,m,k] (or [batch,k,m] when adj_x),
+ * y is [batch,k,n] (or [batch,n,k] when adj_y); strided, no pointer arrays, no scratch. */
+B200_API int b200_batch_matmul(int dtype, const void* x, const void* y, void* out, int64_t batch,
+                               int64_t m, int64_t n, int64_t k, int adj_x, int adj_y,
+                               void* stream);
+
+/* ------------------------------------------------------------------ BiasAdd / BiasAddGrad
+ * BiasGPU<T>::compute, NHWC (core/kernels/bias_op_gpu.cu.cc:69-88; op bias_op.cc:43-117):
+ * out[r, c] = in[r, c] + bias[c], rows = prod(leading dims); out may alias in. */
+B200_API int b200_bias_add(int dtype, const void* in, const void* bias, void* out, int64_t rows,
+                           int64_t channels, void* stream);
+/* BiasGradGPU<T>::compute, NHWC (bias_op_gpu.cu.cc:189-242; op bias_op.cc:171-227):
+ * out[c] = sum_r out_backprop[r, c]; fp32 accumulation, deterministic two-stage reduction
+ * (no atomics).  workspace: b200_bias_add_grad_workspace_bytes() bytes of device scratch. */
+B200_API size_t b200_bias_add_grad_workspace_bytes(int dtype, int64_t rows, int64_t channels);
+B200_API int b200_bias_add_grad(int dtype, const void* out_backprop, void* out, int64_t rows,
+                                int64_t channels, void* workspace, size_t workspace_bytes,
+                                void* stream);
+
+/* ------------------------------------------------------------------ Relu / ReluGrad
+ * functor::Relu / functor::ReluGrad (core/kernels/relu_op_functor.h:28-60):
+ * y = max(x, 0);  dx = g * (f > 0) with f the Relu input or output.  In-place allowed. */
+B200_API int b200_relu(int dtype, const void* features, void* activations, int64_t n,
+                       void* stream);
+B200_API int b200_relu_grad(int dtype, const void* gradients, const void* features,
+                            void* backprops, int64_t n, void* stream);
+
+/* ------------------------------------------------------------------ Softmax / LogSoftmax
+ * SoftmaxEigenImpl (core/kernels/softmax_op_functor.h:43-99): rank-2 [rows, cols];
+ * softmax = exp(x - max) * (1 / sum);  log variant = x - max - log(sum exp(x - max)). */
+B200_API int b200_softmax(int dtype, const void* logits, void* out, int64_t rows, int64_t cols,
+                          int log_softmax, void* stream);
+/* XentEigenImpl (core/kernels/xent_op.h:47-113): loss[r] = sum_c labels*(log sum exp - (x-max)),
+ * backprop = softmax - labels. */
+B200_API int b200_softmax_xent(int dtype, const void* logits, const void* labels, void* loss,
+                               void* backprop, int64_t rows, int64_t cols, void* stream);
+
+/* ------------------------------------------------------------------ MaxPool / MaxPoolGrad (NHWC)
+ * MaxPoolForwardNHWC (core/kernels/maxpooling_op_gpu.cu.cc:93-129) with the CPU kernel's
+ * semantics (pooling_ops_common.h:204-238): padded cells never participate.
+ * pad_top/pad_left are the "before" paddings from GetWindowedOutputSize. */
+B200_API int b200_max_pool(int dtype, const void* in, void* out, int64_t batch, int64_t in_h,
+                           int64_t in_w, int64_t channels, int64_t out_h, int64_t out_w,
+                           int window_h, int window_w, int stride_h, int stride_w, int pad_top,
+                           int pad_left, void* stream);
+/* MaxPoolingGradOp (core/kernels/maxpooling_op.cc:230-306,117-178): gradient goes to the first
+ * maximum of each window in row-major scan order; gather formulation, no atomics. */
+B200_API int b200_max_pool_grad(int dtype, const void* orig_in, const void* orig_out,
+                                const void* grad, void* in_backprop, int64_t batch, int64_t in_h,
+                                int64_t in_w, int64_t channels, int64_t out_h, int64_t out_w,
+                                int window_h, int window_w, int stride_h, int stride_w,
+                                int pad_top, int pad_left, void* stream);
+
+/* ------------------------------------------------------------------ Cast / ArgMax (bit-exact)
+ * CastOp (core/kernels/cast_op.cc, cast_op.h:93-141): float->bfloat16 TRUNCATES the low 16 bits
+ * (framework/bfloat16.cc:20-31), bfloat16->float shifts; int32/int64/float conversions follow
+ * C++ static_cast. */
+B200_API int b200_cast(int src_dtype, int dst_dtype, const void* in, void* out, int64_t n,
+                       void* stream);
+/* ArgOp<..., ArgMax> (core/kernels/argmax_op.cc:44-98): input viewed as [outer, axis, inner],
+ * output int64 [outer, inner]; lowest index wins ties. */
+B200_API int b200_argmax(int dtype, const void* in, int64_t* out, int64_t outer, int64_t axis_size,
+                         int64_t inner, void* stream);
+
+/* ------------------------------------------------------------------ Conv2D family (NHWC, HWIO)
+ * Geometry is what Conv2DOp::Compute / ConvBackpropComputeDimensions derive
+ * (core/kernels/conv_ops.cc:267-380, conv_grad_ops.cc:37-126): out size and the "before"
+ * paddings come from GetWindowedOutputSizeVerbose (framework/common_shape_fns.cc:19-56). */
+typedef struct b200_conv2d_geometry {
+  int64_t batch, in_h, in_w, in_c;      /* input  [batch, in_h, in_w, in_c]        */
+  int64_t filter_h, filter_w, out_c;    /* filter [filter_h, filter_w, in_c, out_c] */
+  int64_t out_h, out_w;                 /* output [batch, out_h, out_w, out_c]      */
+  int32_t stride_h, stride_w;
+  int32_t pad_top, pad_left;
+} b200_conv2d_geometry;
+
+/* Scratch needed by any of the three conv entry points for this geometry (may be 0). */
+B200_API size_t b200_conv2d_workspace_bytes(int dtype, const b200_conv2d_geometry* g, int which);
+/* which: 0 forward, 1 backprop-input, 2 backprop-filter */
+
+/* Replaces LaunchConv2DOp<GPUDevice,T>::launch (core/kernels/conv_ops.cc:433-720). */
+B200_API int b200_conv2d(int dtype, const void* input, const void* filter, void* output,
+                         const b200_conv2d_geometry* g, void* workspace, size_t workspace_bytes,
+                         void* stream);
+/* Replaces Conv2DSlowBackpropInputOp<GPUDevice,T> (core/kernels/conv_grad_input_ops.cc:533-917). */
+B200_API int b200_conv2d_backprop_input(int dtype, const void* filter, const void* out_backprop,
+                                        void* in_backprop, const b200_conv2d_geometry* g,
+                                        void* workspace, size_t workspace_bytes, void* stream);
+/* Replaces Conv2DSlowBackpropFilterOp<GPUDevice,T> (core/kernels/conv_grad_filter_ops.cc:361-738). */
+B200_API int b200_conv2d_backprop_filter(int dtype, const void* input, const void* out_backprop,
+                                         void* filter_backprop, const b200_conv2d_geometry* g,
+                                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------ graph glue
+ * ApplyGradientDescent (core/kernels/training_ops.cc:410-412): var -= alpha * delta. */
+B200_API int b200_apply_gradient_descent(int dtype, void* var, float alpha, const void* delta,
+                                         int64_t n, void* stream);
+/* AddN (core/kernels/aggregate_ops.cc:153-176) for n_inputs <= 8. */
+B200_API int b200_add_n(int dtype, const void* const* inputs_host, int n_inputs, void* out,
+                        int64_t n, void* stream);
+/* out = in * scale (used for the mean-loss gradient and the 1/p replica average). */
+B200_API int b200_scale(int dtype, const void* in, float scale, void* out, int64_t n,
+                        void* stream);
+/* out[0] = sum(in[0..n)) * scale; fp32, deterministic (loss reduction: Mean/Sum glue). */
+B200_API int b200_reduce_sum(int dtype, const void* in, float scale, void* out, int64_t n,
+                             void* stream);
+
+/* ------------------------------------------------------------------ replica data-parallel
+ * One NCCL all-reduce (sum) over a contiguous gradient arena on the compute stream
+ * (SURVEY.md 8e).  The reference has no collective op (third_party/nccl.BUILD has no call
+ * sites); this replaces its tower pattern _Send/_Recv + AddN (aggregate_ops.cc:153-176).
+ * libnccl is dlopen()ed on first use; unique-id exchange is the host's job. */
+B200_API int b200_nccl_unique_id(void* id128_host);  /* writes 128 bytes */
+B200_API int b200_nccl_comm_init_rank(void** comm, int nranks, const void* id128_host, int rank);
+B200_API int b200_nccl_comm_destroy(void* comm);
+B200_API int b200_nccl_all_reduce_sum(int dtype, const void* sendbuf, void* recvbuf,
+                                      int64_t count, void* comm, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_OPS_H_ */

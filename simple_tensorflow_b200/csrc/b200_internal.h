@@ -1,0 +1,50 @@
+// Internal (non-ABI) declarations shared by the .cu translation units of libb200tf.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200_ops.h"
+
+namespace b200 {
+
+// printf-style; stores a thread-local message returned by b200_last_error().
+void set_last_error(const char* fmt, ...) __attribute__((format(printf, 1, 2)));
+
+// Driver entry points resolved at run time through cudaGetDriverEntryPoint so that the library
+// loads (and exports its symbols) on a machine without libcuda.so.
+struct DriverApi {
+  CUresult (*cuTensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+};
+const DriverApi& driver();
+
+int sm_count();                       // SMs of the current device (cached per device)
+void note_launch(int n = 1);          // bump the library-wide launch counter
+int check_launch(const char* what);   // cudaGetLastError -> B200_INTERNAL + message
+int require_device(const char* what); // B200_INTERNAL when no CUDA device is usable
+
+inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+
+// ------------------------------------------------------------------ GEMM plumbing
+struct GemmArgs {
+  int dtype;                 // B200_DT_FLOAT or B200_DT_BFLOAT16
+  const void* a;             // logical A[M,K]
+  const void* b;             // logical B[K,N]
+  void* c;                   // C[M,N] row-major
+  long long M, N, K, batch;
+  long long lda, ldb, ldc;   // leading dimensions of the STORED row-major matrices (elements)
+  long long strideA, strideB, strideC;  // batch strides (elements)
+  bool a_mn_major;           // A stored as [K,M] (transpose_a)
+  bool b_mn_major;           // B stored as [K,N] (i.e. NOT transpose_b)
+  int force_bn;              // 0 = auto
+};
+bool gemm_tcgen05_supported(const GemmArgs& g);
+int gemm_tcgen05(const GemmArgs& g, cudaStream_t stream);
+int gemm_simt(const GemmArgs& g, cudaStream_t stream);
+// Precision-aware front door used by matmul / batch_matmul / conv.
+int gemm_dispatch(const GemmArgs& g, cudaStream_t stream);
+
+}  // namespace b200

@@ -1,0 +1,454 @@
+// Streaming (HBM-bound) element-wise op kernels: BiasAdd, Relu, ReluGrad, Cast,
+// ApplyGradientDescent, AddN, Scale.  Every kernel moves 16 bytes per thread per access
+// (float4 / 8 x bf16), issues kUnroll independent loads before the first use, and falls back to
+// a scalar kernel when a pointer or the channel count breaks 16-byte alignment.
+//
+// Reference kernels replaced (all relative to tensorflow/core/kernels/):
+//   BiasAdd   bias_op_gpu.cu.cc:48-88 (BiasNHWCKernel, scalar ldg, grid capped at #SMs)
+//   Relu/Grad relu_op_gpu.cu.cc:32-40 (Eigen GpuDevice expression of relu_op_functor.h:28-60)
+//   Cast      cast_op_gpu.cu.cc (Eigen scalar_cast_op; bfloat16 = truncation, cast_op.h:119-141)
+//   ApplyGradientDescent training_ops_gpu.cu.cc / training_ops.cc:410-412
+//   AddN      aggregate_ops_gpu.cu.cc / aggregate_ops.cc:153-176
+#include <cuda_bf16.h>
+
+#include "b200_internal.h"
+
+namespace b200 {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+template <typename T>
+struct Vec16 {
+  static constexpr int kN = 16 / sizeof(T);
+};
+
+__device__ __forceinline__ uint4 ld16(const void* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ void st16(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+
+// ---- per-16-byte math on fp32 x4 / bf16 x8, all arithmetic in fp32
+template <typename T>
+struct Lanes;
+template <>
+struct Lanes<float> {
+  static constexpr int kN = 4;
+  __device__ static void unpack(uint4 v, float (&f)[4]) {
+    f[0] = __uint_as_float(v.x);
+    f[1] = __uint_as_float(v.y);
+    f[2] = __uint_as_float(v.z);
+    f[3] = __uint_as_float(v.w);
+  }
+  __device__ static uint4 pack(const float (&f)[4]) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                      __float_as_uint(f[3]));
+  }
+  __device__ static float load1(const float* p) { return *p; }
+  __device__ static void store1(float* p, float v) { *p = v; }
+};
+template <>
+struct Lanes<__nv_bfloat16> {
+  static constexpr int kN = 8;
+  __device__ static void unpack(uint4 v, float (&f)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      f[2 * i] = __uint_as_float(w[i] << 16);
+      f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+    }
+  }
+  __device__ static uint4 pack(const float (&f)[8]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+      w[i] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __device__ static float load1(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+  __device__ static void store1(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline unsigned blocks_for(long long items, int per_block) {
+  long long b = (items + per_block - 1) / per_block;
+  return (unsigned)(b < 1 ? 1 : b);
+}
+
+// ------------------------------------------------------------------ generic n-ary map
+// out[i] = f(in0[i], in1[i], ...) ; NIN inputs, one output, same dtype.
+template <typename T, int NIN, typename F>
+__global__ void __launch_bounds__(kThreads)
+map_vec_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
+               long long nvec, F f) {
+  constexpr int N = Lanes<T>::kN;
+  const long long base = ((long long)blockIdx.x * kThreads * kUnroll) + threadIdx.x;
+  uint4 va[kUnroll], vb[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const long long i = base + (long long)u * kThreads;
+    if (i < nvec) {
+      va[u] = ld16(a + i * N);
+      if (NIN > 1) vb[u] = ld16(b + i * N);
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const long long i = base + (long long)u * kThreads;
+    if (i < nvec) {
+      float x[N], y[N], r[N];
+      Lanes<T>::unpack(va[u], x);
+      if (NIN > 1) Lanes<T>::unpack(vb[u], y);
+#pragma unroll
+      for (int j = 0; j < N; ++j) r[j] = f(x[j], NIN > 1 ? y[j] : 0.f);
+      st16(out + i * N, Lanes<T>::pack(r));
+    }
+  }
+}
+template <typename T, int NIN, typename F>
+__global__ void __launch_bounds__(kThreads)
+map_scalar_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
+                  long long start, long long n, F f) {
+  const long long i = start + (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i < n) {
+    const float x = Lanes<T>::load1(a + i);
+    const float y = NIN > 1 ? Lanes<T>::load1(b + i) : 0.f;
+    Lanes<T>::store1(out + i, f(x, y));
+  }
+}
+
+template <typename T, int NIN, typename F>
+static int launch_map(const char* what, const void* a, const void* b, void* out, long long n, F f,
+                      cudaStream_t stream) {
+  if (n <= 0) return B200_OK;
+  constexpr int N = Lanes<T>::kN;
+  const T* pa = static_cast<const T*>(a);
+  const T* pb = static_cast<const T*>(b);
+  T* po = static_cast<T*>(out);
+  const bool vec = aligned16(a) && aligned16(out) && (NIN < 2 || aligned16(b));
+  long long nvec = vec ? n / N : 0;
+  if (nvec > 0) {
+    map_vec_kernel<T, NIN, F><<<blocks_for(nvec, kThreads * kUnroll), kThreads, 0, stream>>>(
+        pa, pb, po, nvec, f);
+    note_launch();
+  }
+  const long long done = nvec * N;
+  if (done < n) {
+    map_scalar_kernel<T, NIN, F><<<blocks_for(n - done, kThreads), kThreads, 0, stream>>>(
+        pa, pb, po, done, n, f);
+    note_launch();
+  }
+  return check_launch(what);
+}
+
+struct ReluF {
+  // cwiseMax(0): relu_op_functor.h:35
+  __device__ float operator()(float x, float) const { return x > 0.f ? x : 0.f; }
+};
+struct ReluGradF {
+  // gradients * (features > 0): relu_op_functor.h:54-55
+  __device__ float operator()(float g, float f) const { return f > 0.f ? g : g * 0.f; }
+};
+struct ScaleF {
+  float s;
+  __device__ float operator()(float x, float) const { return x * s; }
+};
+struct SgdF {
+  float alpha;
+  // var -= alpha * delta: training_ops.cc:410-412
+  __device__ float operator()(float var, float delta) const { return var - alpha * delta; }
+};
+
+// ------------------------------------------------------------------ BiasAdd
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bias_add_vec_kernel(const T* __restrict__ in, const T* __restrict__ bias, T* __restrict__ out,
+                    long long nvec, int cvec /* channels / N */) {
+  constexpr int N = Lanes<T>::kN;
+  const long long base = ((long long)blockIdx.x * kThreads * kUnroll) + threadIdx.x;
+  uint4 vi[kUnroll], vb[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const long long i = base + (long long)u * kThreads;
+    if (i < nvec) {
+      vi[u] = ld16(in + i * N);
+      vb[u] = ld16(bias + (i % cvec) * N);  // bias row stays in L1/L2
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const long long i = base + (long long)u * kThreads;
+    if (i < nvec) {
+      float x[N], b[N], r[N];
+      Lanes<T>::unpack(vi[u], x);
+      Lanes<T>::unpack(vb[u], b);
+#pragma unroll
+      for (int j = 0; j < N; ++j) r[j] = x[j] + b[j];
+      st16(out + i * N, Lanes<T>::pack(r));
+    }
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+bias_add_scalar_kernel(const T* __restrict__ in, const T* __restrict__ bias, T* __restrict__ out,
+                       long long n, long long channels) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i < n)
+    Lanes<T>::store1(out + i, Lanes<T>::load1(in + i) + Lanes<T>::load1(bias + i % channels));
+}
+
+template <typename T>
+static int launch_bias_add(const void* in, const void* bias, void* out, long long rows,
+                           long long channels, cudaStream_t stream) {
+  constexpr int N = Lanes<T>::kN;
+  const long long n = rows * channels;
+  if (n == 0) return B200_OK;
+  if (channels % N == 0 && aligned16(in) && aligned16(out) && aligned16(bias)) {
+    const long long nvec = n / N;
+    bias_add_vec_kernel<T><<<blocks_for(nvec, kThreads * kUnroll), kThreads, 0, stream>>>(
+        static_cast<const T*>(in), static_cast<const T*>(bias), static_cast<T*>(out), nvec,
+        (int)(channels / N));
+  } else {
+    bias_add_scalar_kernel<T><<<blocks_for(n, kThreads), kThreads, 0, stream>>>(
+        static_cast<const T*>(in), static_cast<const T*>(bias), static_cast<T*>(out), n, channels);
+  }
+  note_launch();
+  return check_launch("b200_bias_add");
+}
+
+// ------------------------------------------------------------------ Cast
+// One generic scalar-converting kernel (4 elements per thread); float<->bfloat16 are bit moves.
+template <typename S, typename D>
+struct CastOne;
+template <>
+struct CastOne<float, uint16_t> {  // float -> bfloat16: keep the upper 16 bits (bfloat16.cc:20-31)
+  __device__ static uint16_t run(float v) { return (uint16_t)(__float_as_uint(v) >> 16); }
+};
+template <>
+struct CastOne<uint16_t, float> {  // bfloat16 -> float (bfloat16.cc:33-50)
+  __device__ static float run(uint16_t v) { return __uint_as_float(((uint32_t)v) << 16); }
+};
+template <typename S, typename D>
+struct CastOne {
+  __device__ static D run(S v) { return static_cast<D>(v); }
+};
+
+template <typename S, typename D>
+__global__ void __launch_bounds__(kThreads)
+cast_kernel(const S* __restrict__ in, D* __restrict__ out, long long n) {
+  const long long base = ((long long)blockIdx.x * kThreads * kUnroll) + threadIdx.x;
+  S v[kUnroll];
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const long long i = base + (long long)u * kThreads;
+    if (i < n) v[u] = in[i];
+  }
+#pragma unroll
+  for (int u = 0; u < kUnroll; ++u) {
+    const long long i = base + (long long)u * kThreads;
+    if (i < n) out[i] = CastOne<S, D>::run(v[u]);
+  }
+}
+// float -> bfloat16, 8 elements per thread: 2 x 16-byte loads, 1 x 16-byte store.
+__global__ void __launch_bounds__(kThreads)
+cast_f32_bf16_vec_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, long long nvec) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= nvec) return;
+  const uint4 a = ld16(in + i * 8), b = ld16(in + i * 8 + 4);
+  uint4 r;
+  r.x = (a.x >> 16) | (a.y & 0xFFFF0000u);
+  r.y = (a.z >> 16) | (a.w & 0xFFFF0000u);
+  r.z = (b.x >> 16) | (b.y & 0xFFFF0000u);
+  r.w = (b.z >> 16) | (b.w & 0xFFFF0000u);
+  st16(out + i * 8, r);
+}
+__global__ void __launch_bounds__(kThreads)
+cast_bf16_f32_vec_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, long long nvec) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= nvec) return;
+  const uint4 a = ld16(in + i * 8);
+  st16(out + i * 8, make_uint4(a.x << 16, a.x & 0xFFFF0000u, a.y << 16, a.y & 0xFFFF0000u));
+  st16(out + i * 8 + 4, make_uint4(a.z << 16, a.z & 0xFFFF0000u, a.w << 16, a.w & 0xFFFF0000u));
+}
+
+template <typename S, typename D>
+static int launch_cast(const void* in, void* out, long long n, cudaStream_t stream) {
+  cast_kernel<S, D><<<blocks_for(n, kThreads * kUnroll), kThreads, 0, stream>>>(
+      static_cast<const S*>(in), static_cast<D*>(out), n);
+  note_launch();
+  return check_launch("b200_cast");
+}
+
+// ------------------------------------------------------------------ AddN
+template <typename T>
+struct AddNPtrs {
+  const T* p[8];
+  int n;
+};
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+add_n_kernel(AddNPtrs<T> ins, T* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  if (i >= n) return;
+  // ((in0 + in1) + in2) + ... : aggregate_ops.cc:153-176 sums left to right
+  float acc = Lanes<T>::load1(ins.p[0] + i);
+  for (int k = 1; k < ins.n; ++k) acc += Lanes<T>::load1(ins.p[k] + i);
+  Lanes<T>::store1(out + i, acc);
+}
+
+static int bad_dtype(const char* what, int dtype) {
+  set_last_error("%s: unsupported dtype %d (DT_FLOAT=1, DT_BFLOAT16=14)", what, dtype);
+  return B200_UNIMPLEMENTED;
+}
+static int bad_n(const char* what, long long n) {
+  set_last_error("%s: negative element count %lld", what, n);
+  return B200_INVALID_ARGUMENT;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_bias_add(int dtype, const void* in, const void* bias, void* out, int64_t rows,
+                  int64_t channels, void* stream) {
+  if (rows < 0 || channels < 0) return bad_n("b200_bias_add", rows < 0 ? rows : channels);
+  if (rows * channels == 0) return B200_OK;
+  int rc = require_device("b200_bias_add");
+  if (rc) return rc;
+  if (dtype == B200_DT_FLOAT) return launch_bias_add<float>(in, bias, out, rows, channels, as_stream(stream));
+  if (dtype == B200_DT_BFLOAT16)
+    return launch_bias_add<__nv_bfloat16>(in, bias, out, rows, channels, as_stream(stream));
+  return bad_dtype("b200_bias_add", dtype);
+}
+
+int b200_relu(int dtype, const void* features, void* activations, int64_t n, void* stream) {
+  if (n < 0) return bad_n("b200_relu", n);
+  if (n == 0) return B200_OK;
+  int rc = require_device("b200_relu");
+  if (rc) return rc;
+  if (dtype == B200_DT_FLOAT)
+    return launch_map<float, 1>("b200_relu", features, nullptr, activations, n, ReluF{}, as_stream(stream));
+  if (dtype == B200_DT_BFLOAT16)
+    return launch_map<__nv_bfloat16, 1>("b200_relu", features, nullptr, activations, n, ReluF{},
+                                        as_stream(stream));
+  return bad_dtype("b200_relu", dtype);
+}
+
+int b200_relu_grad(int dtype, const void* gradients, const void* features, void* backprops,
+                   int64_t n, void* stream) {
+  if (n < 0) return bad_n("b200_relu_grad", n);
+  if (n == 0) return B200_OK;
+  int rc = require_device("b200_relu_grad");
+  if (rc) return rc;
+  if (dtype == B200_DT_FLOAT)
+    return launch_map<float, 2>("b200_relu_grad", gradients, features, backprops, n, ReluGradF{},
+                                as_stream(stream));
+  if (dtype == B200_DT_BFLOAT16)
+    return launch_map<__nv_bfloat16, 2>("b200_relu_grad", gradients, features, backprops, n,
+                                        ReluGradF{}, as_stream(stream));
+  return bad_dtype("b200_relu_grad", dtype);
+}
+
+int b200_scale(int dtype, const void* in, float scale, void* out, int64_t n, void* stream) {
+  if (n < 0) return bad_n("b200_scale", n);
+  if (n == 0) return B200_OK;
+  int rc = require_device("b200_scale");
+  if (rc) return rc;
+  if (dtype == B200_DT_FLOAT)
+    return launch_map<float, 1>("b200_scale", in, nullptr, out, n, ScaleF{scale}, as_stream(stream));
+  if (dtype == B200_DT_BFLOAT16)
+    return launch_map<__nv_bfloat16, 1>("b200_scale", in, nullptr, out, n, ScaleF{scale},
+                                        as_stream(stream));
+  return bad_dtype("b200_scale", dtype);
+}
+
+int b200_apply_gradient_descent(int dtype, void* var, float alpha, const void* delta, int64_t n,
+                                void* stream) {
+  if (n < 0) return bad_n("b200_apply_gradient_descent", n);
+  if (n == 0) return B200_OK;
+  int rc = require_device("b200_apply_gradient_descent");
+  if (rc) return rc;
+  if (dtype == B200_DT_FLOAT)
+    return launch_map<float, 2>("b200_apply_gradient_descent", var, delta, var, n, SgdF{alpha},
+                                as_stream(stream));
+  if (dtype == B200_DT_BFLOAT16)
+    return launch_map<__nv_bfloat16, 2>("b200_apply_gradient_descent", var, delta, var, n,
+                                        SgdF{alpha}, as_stream(stream));
+  return bad_dtype("b200_apply_gradient_descent", dtype);
+}
+
+int b200_add_n(int dtype, const void* const* inputs_host, int n_inputs, void* out, int64_t n,
+               void* stream) {
+  if (n < 0) return bad_n("b200_add_n", n);
+  if (n_inputs < 1 || n_inputs > 8) {
+    set_last_error("b200_add_n: n_inputs must be in [1, 8], got %d", n_inputs);
+    return B200_INVALID_ARGUMENT;
+  }
+  if (n == 0) return B200_OK;
+  int rc = require_device("b200_add_n");
+  if (rc) return rc;
+  if (dtype == B200_DT_FLOAT) {
+    AddNPtrs<float> p{};
+    p.n = n_inputs;
+    for (int i = 0; i < n_inputs; ++i) p.p[i] = static_cast<const float*>(inputs_host[i]);
+    add_n_kernel<float><<<blocks_for(n, kThreads), kThreads, 0, as_stream(stream)>>>(
+        p, static_cast<float*>(out), n);
+  } else if (dtype == B200_DT_BFLOAT16) {
+    AddNPtrs<__nv_bfloat16> p{};
+    p.n = n_inputs;
+    for (int i = 0; i < n_inputs; ++i) p.p[i] = static_cast<const __nv_bfloat16*>(inputs_host[i]);
+    add_n_kernel<__nv_bfloat16><<<blocks_for(n, kThreads), kThreads, 0, as_stream(stream)>>>(
+        p, static_cast<__nv_bfloat16*>(out), n);
+  } else {
+    return bad_dtype("b200_add_n", dtype);
+  }
+  note_launch();
+  return check_launch("b200_add_n");
+}
+
+int b200_cast(int src_dtype, int dst_dtype, const void* in, void* out, int64_t n, void* stream) {
+  if (n < 0) return bad_n("b200_cast", n);
+  if (n == 0) return B200_OK;
+  int rc = require_device("b200_cast");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  if (src_dtype == dst_dtype) {  // CastOpBase::Compute aliases the input (cast_op.cc:63-66)
+    size_t es = src_dtype == B200_DT_BFLOAT16 ? 2 : (src_dtype == B200_DT_INT64 ? 8 : 4);
+    if (in != out) return b200_memcpy_d2d_async(out, in, (size_t)n * es, stream);
+    return B200_OK;
+  }
+#define PAIR(a, b) (src_dtype == (a) && dst_dtype == (b))
+  if (PAIR(B200_DT_FLOAT, B200_DT_BFLOAT16)) {
+    if (n % 8 == 0 && aligned16(in) && aligned16(out)) {
+      cast_f32_bf16_vec_kernel<<<blocks_for(n / 8, kThreads), kThreads, 0, s>>>(
+          static_cast<const float*>(in), static_cast<uint16_t*>(out), n / 8);
+      note_launch();
+      return check_launch("b200_cast");
+    }
+    return launch_cast<float, uint16_t>(in, out, n, s);
+  }
+  if (PAIR(B200_DT_BFLOAT16, B200_DT_FLOAT)) {
+    if (n % 8 == 0 && aligned16(in) && aligned16(out)) {
+      cast_bf16_f32_vec_kernel<<<blocks_for(n / 8, kThreads), kThreads, 0, s>>>(
+          static_cast<const uint16_t*>(in), static_cast<float*>(out), n / 8);
+      note_launch();
+      return check_launch("b200_cast");
+    }
+    return launch_cast<uint16_t, float>(in, out, n, s);
+  }
+  if (PAIR(B200_DT_FLOAT, B200_DT_INT32)) return launch_cast<float, int32_t>(in, out, n, s);
+  if (PAIR(B200_DT_FLOAT, B200_DT_INT64)) return launch_cast<float, int64_t>(in, out, n, s);
+  if (PAIR(B200_DT_INT32, B200_DT_FLOAT)) return launch_cast<int32_t, float>(in, out, n, s);
+  if (PAIR(B200_DT_INT64, B200_DT_FLOAT)) return launch_cast<int64_t, float>(in, out, n, s);
+  if (PAIR(B200_DT_INT32, B200_DT_INT64)) return launch_cast<int32_t, int64_t>(in, out, n, s);
+  if (PAIR(B200_DT_INT64, B200_DT_INT32)) return launch_cast<int64_t, int32_t>(in, out, n, s);
+#undef PAIR
+  set_last_error("b200_cast: unsupported dtype pair %d -> %d", src_dtype, dst_dtype);
+  return B200_UNIMPLEMENTED;
+}
+
+}  // extern "C"

@@ -1,0 +1,223 @@
+// MatMul / BatchMatMul entry points of the C ABI, the precision/shape dispatch in front of the
+// tcgen05 GEMM, and the SIMT fp32 GEMM that serves shapes TMA cannot address (leading dimension
+// not a multiple of 16 bytes, e.g. the 3x5 matrices of the reference's matmul_op_test.py) and
+// the "exact fp32" precision mode.
+//
+// Reference semantics: MatMulOp::Compute (tensorflow/core/kernels/matmul_op.cc:215-256) and
+// BatchMatMul::Compute (tensorflow/core/kernels/batch_matmul_op_impl.h:367-434).
+#include <cuda_bf16.h>
+
+#include "b200_internal.h"
+
+namespace b200 {
+
+template <typename T>
+__device__ __forceinline__ float to_f32(T v);
+template <>
+__device__ __forceinline__ float to_f32<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) {
+  return __bfloat162float(v);
+}
+template <typename T>
+__device__ __forceinline__ T from_f32(float v);
+template <>
+__device__ __forceinline__ float from_f32<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+// 64x64 output tile, 16x16 threads, 4x4 micro-tile per thread, K step 16.  Any strides/major.
+constexpr int kSimtTile = 64;
+constexpr int kSimtK = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int M, int N,
+                 int K, long long lda, long long ldb, long long ldc, long long sA, long long sB,
+                 long long sC, bool a_mn, bool b_mn) {
+  __shared__ float As[kSimtK][kSimtTile + 1];
+  __shared__ float Bs[kSimtK][kSimtTile + 1];
+  const int batch = blockIdx.z;
+  A += batch * sA;
+  B += batch * sB;
+  C += batch * sC;
+  const int m0 = blockIdx.y * kSimtTile;
+  const int n0 = blockIdx.x * kSimtTile;
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < K; k0 += kSimtK) {
+    // cooperative load: 64x16 elements of A and of B, 4 per thread each
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = threadIdx.x + i * 256;
+      int mm, kk;
+      if (a_mn) {  // stored [K, M]: contiguous along M
+        mm = idx & 63;
+        kk = idx >> 6;
+      } else {  // stored [M, K]: contiguous along K
+        kk = idx & 15;
+        mm = idx >> 4;
+      }
+      const int gm = m0 + mm, gk = k0 + kk;
+      float v = 0.f;
+      if (gm < M && gk < K) v = to_f32<T>(a_mn ? A[(long long)gk * lda + gm] : A[(long long)gm * lda + gk]);
+      As[kk][mm] = v;
+      int nn;
+      if (b_mn) {  // stored [K, N]
+        nn = idx & 63;
+        kk = idx >> 6;
+      } else {  // stored [N, K]
+        kk = idx & 15;
+        nn = idx >> 4;
+      }
+      const int gn = n0 + nn;
+      const int gk2 = k0 + kk;
+      v = 0.f;
+      if (gn < N && gk2 < K) v = to_f32<T>(b_mn ? B[(long long)gk2 * ldb + gn] : B[(long long)gn * ldb + gk2]);
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kSimtK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int gm = m0 + ty * 4 + i;
+    if (gm >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gn = n0 + tx * 4 + j;
+      if (gn < N) C[(long long)gm * ldc + gn] = from_f32<T>(acc[i][j]);
+    }
+  }
+}
+
+int gemm_simt(const GemmArgs& g, cudaStream_t stream) {
+  if (g.batch > 65535) {
+    set_last_error("gemm_simt: batch %lld exceeds grid.z limit", g.batch);
+    return B200_UNIMPLEMENTED;
+  }
+  dim3 grid((unsigned)((g.N + kSimtTile - 1) / kSimtTile),
+            (unsigned)((g.M + kSimtTile - 1) / kSimtTile), (unsigned)g.batch);
+  if (g.dtype == B200_DT_FLOAT) {
+    gemm_simt_kernel<float><<<grid, 256, 0, stream>>>(
+        static_cast<const float*>(g.a), static_cast<const float*>(g.b), static_cast<float*>(g.c),
+        (int)g.M, (int)g.N, (int)g.K, g.lda, g.ldb, g.ldc, g.strideA, g.strideB, g.strideC,
+        g.a_mn_major, g.b_mn_major);
+  } else if (g.dtype == B200_DT_BFLOAT16) {
+    gemm_simt_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+        static_cast<const __nv_bfloat16*>(g.a), static_cast<const __nv_bfloat16*>(g.b),
+        static_cast<__nv_bfloat16*>(g.c), (int)g.M, (int)g.N, (int)g.K, g.lda, g.ldb, g.ldc,
+        g.strideA, g.strideB, g.strideC, g.a_mn_major, g.b_mn_major);
+  } else {
+    set_last_error("gemm_simt: unsupported dtype %d", g.dtype);
+    return B200_UNIMPLEMENTED;
+  }
+  note_launch();
+  return check_launch("gemm_simt");
+}
+
+int gemm_dispatch(const GemmArgs& g, cudaStream_t stream) {
+  const bool want_exact = g.dtype == B200_DT_FLOAT && b200_get_matmul_precision() == 1;
+  // Tiny problems: a 128-row MMA tile would be mostly padding and launch-bound anyway.
+  const bool tiny = g.M * g.N * g.K < 32LL * 32 * 32;
+  if (!want_exact && !tiny && gemm_tcgen05_supported(g) && driver().cuTensorMapEncodeTiled)
+    return gemm_tcgen05(g, stream);
+  return gemm_simt(g, stream);
+}
+
+static int validate_gemm(const char* what, int dtype, const void* a, const void* b, void* c,
+                         int64_t m, int64_t n, int64_t k, int64_t batch) {
+  if (dtype != B200_DT_FLOAT && dtype != B200_DT_BFLOAT16) {
+    set_last_error("%s: unsupported dtype %d (DT_FLOAT=1, DT_BFLOAT16=14)", what, dtype);
+    return B200_UNIMPLEMENTED;
+  }
+  if (m <= 0 || n <= 0 || k <= 0 || batch <= 0) {
+    set_last_error("%s: m, n, k, batch must be positive (m=%lld n=%lld k=%lld batch=%lld); the "
+                   "zero-size rules of matmul_op.cc:240-253 belong to the OpKernel wrapper",
+                   what, (long long)m, (long long)n, (long long)k, (long long)batch);
+    return B200_INVALID_ARGUMENT;
+  }
+  if (!a || !b || !c) {
+    set_last_error("%s: null pointer argument", what);
+    return B200_INVALID_ARGUMENT;
+  }
+  if (m > INT32_MAX || n > INT32_MAX || k > INT32_MAX) {
+    set_last_error("%s: dimension exceeds int32", what);
+    return B200_INVALID_ARGUMENT;
+  }
+  return require_device(what);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200_matmul(int dtype, const void* a, const void* b, void* c, int64_t m, int64_t n, int64_t k,
+                int transpose_a, int transpose_b, void* stream) {
+  int rc = validate_gemm("b200_matmul", dtype, a, b, c, m, n, k, 1);
+  if (rc) return rc;
+  GemmArgs g{};
+  g.dtype = dtype;
+  g.a = a;
+  g.b = b;
+  g.c = c;
+  g.M = m;
+  g.N = n;
+  g.K = k;
+  g.batch = 1;
+  g.lda = transpose_a ? m : k;
+  g.ldb = transpose_b ? k : n;
+  g.ldc = n;
+  g.strideA = m * k;
+  g.strideB = k * n;
+  g.strideC = m * n;
+  g.a_mn_major = transpose_a != 0;
+  g.b_mn_major = transpose_b == 0;
+  return gemm_dispatch(g, as_stream(stream));
+}
+
+int b200_batch_matmul(int dtype, const void* x, const void* y, void* out, int64_t batch, int64_t m,
+                      int64_t n, int64_t k, int adj_x, int adj_y, void* stream) {
+  int rc = validate_gemm("b200_batch_matmul", dtype, x, y, out, m, n, k, batch);
+  if (rc) return rc;
+  GemmArgs g{};
+  g.dtype = dtype;
+  g.a = x;
+  g.b = y;
+  g.c = out;
+  g.M = m;
+  g.N = n;
+  g.K = k;
+  g.batch = batch;
+  g.lda = adj_x ? m : k;
+  g.ldb = adj_y ? k : n;
+  g.ldc = n;
+  g.strideA = m * k;
+  g.strideB = k * n;
+  g.strideC = m * n;
+  g.a_mn_major = adj_x != 0;
+  g.b_mn_major = adj_y == 0;
+  return gemm_dispatch(g, as_stream(stream));
+}
+
+}  // extern "C"

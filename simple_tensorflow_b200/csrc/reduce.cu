@@ -1,0 +1,643 @@
+// Reduction-style HBM-bound op kernels: BiasAddGrad, Softmax / LogSoftmax,
+// SoftmaxCrossEntropyWithLogits, ArgMax, and a deterministic sum (loss glue).
+//
+// Reference kernels replaced (relative to tensorflow/core/kernels/):
+//   BiasAddGrad  bias_op_gpu.cu.cc:93-242 (ThenMemZero + shared/global atomicAdd, order varies)
+//                -> two-stage ordered column reduction, no atomics, bit-reproducible
+//   Softmax      softmax_op_gpu.cu.cc:32-44 (SoftmaxEigenImpl = 4 Eigen kernels + 2 temporaries)
+//                -> one kernel, one read + one write of the matrix
+//   Xent         xent_op_gpu.cu.cc (XentEigenImpl, xent_op.h:47-113) -> one kernel
+//   ArgMax       argmax_op_gpu.cu.cc (Eigen argmax reducer, argmax_op.h:29-42)
+#include <cfloat>
+#include <cuda_bf16.h>
+
+#include "b200_internal.h"
+
+namespace b200 {
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ float ldf(const T* p);
+template <>
+__device__ __forceinline__ float ldf<float>(const float* p) {
+  return __ldg(p);
+}
+template <>
+__device__ __forceinline__ float ldf<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+template <typename T>
+__device__ __forceinline__ void stf(T* p, float v);
+template <>
+__device__ __forceinline__ void stf<float>(float* p, float v) {
+  *p = v;
+}
+template <>
+__device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+  *p = __float2bfloat16_rn(v);
+}
+
+// ================================================================== BiasAddGrad
+// Stage 1: block (32, 8).  Columns are processed in vectors of VEC elements (16 bytes when the
+// channel count allows).  W = channels / VEC vector-columns.  If W >= 32 a CTA owns 32
+// vector-columns; if W < 32 the spare lanes fold extra rows (fold = 32 / W) so small channel
+// counts (LeNet: 32, 64, 10) still use every lane.  Each CTA reduces a contiguous chunk of rows
+// and writes one partial row; stage 2 adds the partial rows in chunk order.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256)
+bias_grad_stage1(const T* __restrict__ g, float* __restrict__ partial, long long rows,
+                 int channels, int rows_per_chunk) {
+  const int W = channels / VEC;
+  const int wt = W < 32 ? W : 32;        // vector-columns handled per CTA
+  const int fold = W < 32 ? 32 / W : 1;  // rows covered by one warp-row
+  const int x = threadIdx.x, y = threadIdx.y;
+  const int cv = blockIdx.x * 32 + (x % wt);
+  const int sub = x / wt;
+  const bool active = sub < fold && cv < W;
+  const long long r0 = (long long)blockIdx.y * rows_per_chunk;
+  long long r1 = r0 + rows_per_chunk;
+  if (r1 > rows) r1 = rows;
+  float acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  if (active) {
+    for (long long r = r0 + y * fold + sub; r < r1; r += 8 * fold) {
+      const T* p = g + r * channels + (long long)cv * VEC;
+      if (VEC == 1) {
+        acc[0] += ldf<T>(p);
+      } else if (sizeof(T) == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+        acc[0] += v.x;
+        acc[1] += v.y;
+        acc[2] += v.z;
+        acc[3] += v.w;
+      } else {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          acc[2 * i] += __uint_as_float(w[i] << 16);
+          acc[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+        }
+      }
+    }
+  }
+  __shared__ float sm[8][32][VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) sm[y][x][j] = active ? acc[j] : 0.f;
+  __syncthreads();
+  if (y == 0 && sub == 0 && cv < W) {
+    float tot[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) tot[j] = 0.f;
+    for (int yy = 0; yy < 8; ++yy)
+      for (int s = 0; s < fold; ++s)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) tot[j] += sm[yy][x + s * wt][j];
+    float* dst = partial + (long long)blockIdx.y * channels + (long long)cv * VEC;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) dst[j] = tot[j];
+  }
+}
+// Stage 2: out[c] = sum over chunks (ascending); block (32, 8), 8-way strided then ordered merge.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_grad_stage2(const float* __restrict__ partial, T* __restrict__ out, int nchunks,
+                 int channels) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.f;
+  if (c < channels)
+    for (int k = threadIdx.y; k < nchunks; k += 8) acc += partial[(long long)k * channels + c];
+  __shared__ float sm[8][33];
+  sm[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < channels) {
+    float t = 0.f;
+    for (int yy = 0; yy < 8; ++yy) t += sm[yy][threadIdx.x];
+    stf<T>(out + c, t);
+  }
+}
+
+struct BiasGradPlan {
+  int vec, col_tiles, nchunks, rows_per_chunk;
+};
+static BiasGradPlan plan_bias_grad(int dtype, long long rows, long long channels, bool aligned) {
+  BiasGradPlan p;
+  const int v16 = dtype == B200_DT_FLOAT ? 4 : 8;
+  p.vec = (aligned && channels % v16 == 0) ? v16 : 1;
+  const long long W = channels / p.vec;
+  p.col_tiles = (int)((W + 31) / 32);
+  const int fold = W < 32 ? (int)(32 / W) : 1;
+  long long want = (4LL * 148 + p.col_tiles - 1) / p.col_tiles;  // ~4 CTAs per SM in total
+  long long max_chunks = (rows + 8LL * fold * 4 - 1) / (8LL * fold * 4);  // >= 4 rows per thread
+  if (max_chunks < 1) max_chunks = 1;
+  if (want > max_chunks) want = max_chunks;
+  if (want > 4096) want = 4096;
+  if (want < 1) want = 1;
+  p.rows_per_chunk = (int)((rows + want - 1) / want);
+  p.nchunks = (int)((rows + p.rows_per_chunk - 1) / p.rows_per_chunk);
+  return p;
+}
+
+// ================================================================== Softmax family
+// Row-per-warp, whole row held in registers: NV float4 (or 8 x bf16) per lane => cols <= 128*NV
+// (or 256*NV).  One HBM read and one write of the matrix.
+template <typename T, int NV, bool kLog>
+__global__ void __launch_bounds__(256)
+softmax_warp_kernel(const T* __restrict__ logits, T* __restrict__ out, long long rows, int cols) {
+  constexpr int E = 16 / sizeof(T);  // elements per 16-byte vector
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* x = logits + row * cols;
+  float v[NV][E];
+  float mx = -FLT_MAX;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c0 = (lane + 32 * j) * E;
+    if (c0 < cols) {
+      const uint4 q = __ldg(reinterpret_cast<const uint4*>(x + c0));
+      if (sizeof(T) == 4) {
+        v[j][0] = __uint_as_float(q.x);
+        v[j][1] = __uint_as_float(q.y);
+        v[j][2 % E] = __uint_as_float(q.z);
+        v[j][3 % E] = __uint_as_float(q.w);
+      } else {
+        const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          v[j][(2 * i) % E] = __uint_as_float(w[i] << 16);
+          v[j][(2 * i + 1) % E] = __uint_as_float(w[i] & 0xFFFF0000u);
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < E; ++e) mx = fmaxf(mx, v[j][e]);
+    }
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c0 = (lane + 32 * j) * E;
+    if (c0 < cols) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        v[j][e] -= mx;  // shifted logits
+        const float ex = expf(v[j][e]);
+        sum += ex;
+        if (!kLog) v[j][e] = ex;
+      }
+    }
+  }
+  sum = warp_sum(sum);
+  const float k = kLog ? logf(sum) : 1.f / sum;
+  T* y = out + row * cols;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c0 = (lane + 32 * j) * E;
+    if (c0 < cols) {
+      float r[E];
+#pragma unroll
+      for (int e = 0; e < E; ++e) r[e] = kLog ? v[j][e] - k : v[j][e] * k;
+      uint4 q;
+      if (sizeof(T) == 4) {
+        q = make_uint4(__float_as_uint(r[0]), __float_as_uint(r[1]), __float_as_uint(r[2 % E]),
+                       __float_as_uint(r[3 % E]));
+      } else {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          __nv_bfloat162 h = __floats2bfloat162_rn(r[(2 * i) % E], r[(2 * i + 1) % E]);
+          w[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+        q = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      *reinterpret_cast<uint4*>(y + c0) = q;
+    }
+  }
+}
+
+// Generic fallback: one CTA (256 threads) per row, three passes over the row (L1/L2 resident),
+// any column count / alignment.  Also carries the xent variant.
+__device__ __forceinline__ float block_reduce(float v, bool is_max, float* sm) {
+  v = is_max ? warp_max(v) : warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sm[w] = v;
+  __syncthreads();
+  float r = is_max ? -FLT_MAX : 0.f;
+  for (int i = 0; i < 8; ++i) r = is_max ? fmaxf(r, sm[i]) : r + sm[i];
+  return r;
+}
+template <typename T, bool kLog>
+__global__ void __launch_bounds__(256)
+softmax_block_kernel(const T* __restrict__ logits, T* __restrict__ out, int cols) {
+  __shared__ float sm[8];
+  const T* x = logits + (long long)blockIdx.x * cols;
+  T* y = out + (long long)blockIdx.x * cols;
+  float mx = -FLT_MAX;
+  for (int c = threadIdx.x; c < cols; c += 256) mx = fmaxf(mx, ldf<T>(x + c));
+  mx = block_reduce(mx, true, sm);
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) sum += expf(ldf<T>(x + c) - mx);
+  sum = block_reduce(sum, false, sm);
+  const float k = kLog ? logf(sum) : 1.f / sum;
+  for (int c = threadIdx.x; c < cols; c += 256) {
+    const float s = ldf<T>(x + c) - mx;
+    stf<T>(y + c, kLog ? s - k : expf(s) * k);
+  }
+}
+// loss[r] = sum_c labels * (log(sum) - shifted); backprop = exp(shifted) / sum - labels
+template <typename T>
+__global__ void __launch_bounds__(256)
+xent_block_kernel(const T* __restrict__ logits, const T* __restrict__ labels, T* __restrict__ loss,
+                  T* __restrict__ backprop, int cols) {
+  __shared__ float sm[8];
+  const T* x = logits + (long long)blockIdx.x * cols;
+  const T* l = labels + (long long)blockIdx.x * cols;
+  T* bp = backprop + (long long)blockIdx.x * cols;
+  float mx = -FLT_MAX;
+  for (int c = threadIdx.x; c < cols; c += 256) mx = fmaxf(mx, ldf<T>(x + c));
+  mx = block_reduce(mx, true, sm);
+  float sum = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) sum += expf(ldf<T>(x + c) - mx);
+  sum = block_reduce(sum, false, sm);
+  const float ls = logf(sum);
+  float acc = 0.f;
+  for (int c = threadIdx.x; c < cols; c += 256) {
+    const float s = ldf<T>(x + c) - mx;
+    const float lab = ldf<T>(l + c);
+    acc += lab * (ls - s);
+    stf<T>(bp + c, expf(s) / sum - lab);
+  }
+  acc = block_reduce(acc, false, sm);
+  if (threadIdx.x == 0) stf<T>(loss + blockIdx.x, acc);
+}
+// Row-per-warp xent for cols <= 1024 (the MLP's 1024-class logits, LeNet's 10 classes).
+template <typename T>
+__global__ void __launch_bounds__(256)
+xent_warp_kernel(const T* __restrict__ logits, const T* __restrict__ labels, T* __restrict__ loss,
+                 T* __restrict__ backprop, long long rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const T* x = logits + row * cols;
+  const T* l = labels + row * cols;
+  T* bp = backprop + row * cols;
+  float v[32], lab[32];
+  float mx = -FLT_MAX;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int c = lane + 32 * j;
+    if (c < cols) {
+      v[j] = ldf<T>(x + c);
+      lab[j] = ldf<T>(l + c);
+      mx = fmaxf(mx, v[j]);
+    }
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j)
+    if (lane + 32 * j < cols) {
+      v[j] -= mx;
+      sum += expf(v[j]);
+    }
+  sum = warp_sum(sum);
+  const float ls = logf(sum);
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int c = lane + 32 * j;
+    if (c < cols) {
+      acc += lab[j] * (ls - v[j]);
+      stf<T>(bp + c, expf(v[j]) / sum - lab[j]);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) stf<T>(loss + row, acc);
+}
+
+// ================================================================== ArgMax
+template <typename T>
+__device__ __forceinline__ T arg_lowest();
+template <>
+__device__ __forceinline__ float arg_lowest<float>() {
+  return -FLT_MAX;
+}
+template <>
+__device__ __forceinline__ int32_t arg_lowest<int32_t>() {
+  return INT32_MIN;
+}
+template <>
+__device__ __forceinline__ int64_t arg_lowest<int64_t>() {
+  return INT64_MIN;
+}
+// inner == 1: one warp per row; (value, index) butterfly, lower index wins ties.
+template <typename T>
+__global__ void __launch_bounds__(256)
+argmax_last_axis_kernel(const T* __restrict__ in, int64_t* __restrict__ out, long long outer,
+                        long long axis) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= outer) return;
+  const T* x = in + row * axis;
+  T bv = arg_lowest<T>();
+  long long bi = 0;  // Eigen's reducer starts at (index 0, lowest) and needs strict > to move
+  for (long long a = lane; a < axis; a += 32) {
+    const T v = x[a];
+    if (v > bv) {
+      bv = v;
+      bi = a;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const T ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const long long oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) {
+      bv = ov;
+      bi = oi;
+    }
+  }
+  // a lane that saw no element > lowest keeps index 0; with ties on lowest the smallest lane
+  // index wins, and index 0 is the smallest possible
+  if (lane == 0) out[row] = bi;
+}
+// general: one thread per (outer, inner) walks the axis; coalesced across inner.
+template <typename T>
+__global__ void __launch_bounds__(256)
+argmax_strided_kernel(const T* __restrict__ in, int64_t* __restrict__ out, long long outer,
+                      long long axis, long long inner) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= outer * inner) return;
+  const long long o = i / inner, k = i - o * inner;
+  const T* x = in + o * axis * inner + k;
+  T bv = arg_lowest<T>();
+  long long bi = 0;
+  for (long long a = 0; a < axis; ++a) {
+    const T v = x[a * inner];
+    if (v > bv) {
+      bv = v;
+      bi = a;
+    }
+  }
+  out[i] = bi;
+}
+
+// ================================================================== deterministic sum
+__global__ void __launch_bounds__(256)
+sum_stage1(const float* __restrict__ in, float* __restrict__ partial, long long n) {
+  __shared__ float sm[8];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += 256LL * gridDim.x)
+    acc += in[i];
+  acc = block_reduce(acc, false, sm);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+__global__ void __launch_bounds__(256)
+sum_stage2(const float* __restrict__ partial, float* __restrict__ out, int n, float scale) {
+  __shared__ float sm[8];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += 256) acc += partial[i];
+  acc = block_reduce(acc, false, sm);
+  if (threadIdx.x == 0) out[0] = acc * scale;
+}
+// single CTA variant when n is small: no scratch needed
+__global__ void __launch_bounds__(256)
+sum_single(const float* __restrict__ in, float* __restrict__ out, long long n, float scale) {
+  __shared__ float sm[8];
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < n; i += 256) acc += in[i];
+  acc = block_reduce(acc, false, sm);
+  if (threadIdx.x == 0) out[0] = acc * scale;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+template <typename T>
+static int launch_softmax(const void* logits, void* out, long long rows, int cols, bool log_sm,
+                          cudaStream_t s) {
+  constexpr int E = 16 / sizeof(T);
+  const T* x = static_cast<const T*>(logits);
+  T* y = static_cast<T*>(out);
+  const bool vec = cols % E == 0 && aligned16(logits) && aligned16(out);
+  const int nv = (cols + 32 * E - 1) / (32 * E);  // 16-byte vectors per lane
+  const unsigned wgrid = (unsigned)((rows + 7) / 8);
+#define SM_LAUNCH(NV)                                                                   \
+  do {                                                                                  \
+    if (log_sm)                                                                         \
+      softmax_warp_kernel<T, NV, true><<<wgrid, 256, 0, s>>>(x, y, rows, cols);         \
+    else                                                                                \
+      softmax_warp_kernel<T, NV, false><<<wgrid, 256, 0, s>>>(x, y, rows, cols);        \
+  } while (0)
+  if (vec && nv <= 8) {
+    if (nv <= 1)
+      SM_LAUNCH(1);
+    else if (nv <= 2)
+      SM_LAUNCH(2);
+    else if (nv <= 4)
+      SM_LAUNCH(4);
+    else
+      SM_LAUNCH(8);
+  } else {
+    if (log_sm)
+      softmax_block_kernel<T, true><<<(unsigned)rows, 256, 0, s>>>(x, y, cols);
+    else
+      softmax_block_kernel<T, false><<<(unsigned)rows, 256, 0, s>>>(x, y, cols);
+  }
+#undef SM_LAUNCH
+  note_launch();
+  return check_launch("b200_softmax");
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+size_t b200_bias_add_grad_workspace_bytes(int dtype, int64_t rows, int64_t channels) {
+  if (rows <= 0 || channels <= 0) return 0;
+  // alignment-independent upper bound: the scalar plan never needs more chunks than the vector one
+  BiasGradPlan a = plan_bias_grad(dtype, rows, channels, true);
+  BiasGradPlan b = plan_bias_grad(dtype, rows, channels, false);
+  const int n = a.nchunks > b.nchunks ? a.nchunks : b.nchunks;
+  return (size_t)n * (size_t)channels * sizeof(float);
+}
+
+int b200_bias_add_grad(int dtype, const void* out_backprop, void* out, int64_t rows,
+                       int64_t channels, void* workspace, size_t workspace_bytes, void* stream) {
+  if (rows < 0 || channels < 0) {
+    set_last_error("b200_bias_add_grad: negative size");
+    return B200_INVALID_ARGUMENT;
+  }
+  if (dtype != B200_DT_FLOAT && dtype != B200_DT_BFLOAT16) {
+    set_last_error("b200_bias_add_grad: unsupported dtype %d", dtype);
+    return B200_UNIMPLEMENTED;
+  }
+  if (channels == 0) return B200_OK;
+  int rc = require_device("b200_bias_add_grad");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  if (rows == 0)  // sum over nothing = 0 (bias_op.cc:206-209 zero-fills)
+    return b200_memset_async(out, 0, (size_t)channels * (dtype == B200_DT_FLOAT ? 4 : 2), stream);
+  if (channels > INT32_MAX) {
+    set_last_error("b200_bias_add_grad: channels exceeds int32");
+    return B200_INVALID_ARGUMENT;
+  }
+  const BiasGradPlan p = plan_bias_grad(dtype, rows, channels, aligned16(out_backprop));
+  const size_t need = (size_t)p.nchunks * (size_t)channels * sizeof(float);
+  if (!workspace || workspace_bytes < need) {
+    set_last_error("b200_bias_add_grad: workspace too small (%zu < %zu bytes)", workspace_bytes,
+                   need);
+    return B200_INVALID_ARGUMENT;
+  }
+  float* partial = static_cast<float*>(workspace);
+  dim3 grid(p.col_tiles, p.nchunks), block(32, 8);
+  if (dtype == B200_DT_FLOAT) {
+    if (p.vec == 4)
+      bias_grad_stage1<float, 4><<<grid, block, 0, s>>>(static_cast<const float*>(out_backprop),
+                                                        partial, rows, (int)channels,
+                                                        p.rows_per_chunk);
+    else
+      bias_grad_stage1<float, 1><<<grid, block, 0, s>>>(static_cast<const float*>(out_backprop),
+                                                        partial, rows, (int)channels,
+                                                        p.rows_per_chunk);
+    bias_grad_stage2<float><<<(unsigned)((channels + 31) / 32), block, 0, s>>>(
+        partial, static_cast<float*>(out), p.nchunks, (int)channels);
+  } else {
+    if (p.vec == 8)
+      bias_grad_stage1<__nv_bfloat16, 8><<<grid, block, 0, s>>>(
+          static_cast<const __nv_bfloat16*>(out_backprop), partial, rows, (int)channels,
+          p.rows_per_chunk);
+    else
+      bias_grad_stage1<__nv_bfloat16, 1><<<grid, block, 0, s>>>(
+          static_cast<const __nv_bfloat16*>(out_backprop), partial, rows, (int)channels,
+          p.rows_per_chunk);
+    bias_grad_stage2<__nv_bfloat16><<<(unsigned)((channels + 31) / 32), block, 0, s>>>(
+        partial, static_cast<__nv_bfloat16*>(out), p.nchunks, (int)channels);
+  }
+  note_launch(2);
+  return check_launch("b200_bias_add_grad");
+}
+
+int b200_softmax(int dtype, const void* logits, void* out, int64_t rows, int64_t cols,
+                 int log_softmax, void* stream) {
+  if (rows < 0 || cols < 0 || cols > INT32_MAX) {
+    set_last_error("b200_softmax: bad shape [%lld, %lld]", (long long)rows, (long long)cols);
+    return B200_INVALID_ARGUMENT;
+  }
+  if (rows * cols == 0) return B200_OK;
+  int rc = require_device("b200_softmax");
+  if (rc) return rc;
+  if (dtype == B200_DT_FLOAT)
+    return launch_softmax<float>(logits, out, rows, (int)cols, log_softmax != 0, as_stream(stream));
+  if (dtype == B200_DT_BFLOAT16)
+    return launch_softmax<__nv_bfloat16>(logits, out, rows, (int)cols, log_softmax != 0,
+                                         as_stream(stream));
+  set_last_error("b200_softmax: unsupported dtype %d", dtype);
+  return B200_UNIMPLEMENTED;
+}
+
+int b200_softmax_xent(int dtype, const void* logits, const void* labels, void* loss,
+                      void* backprop, int64_t rows, int64_t cols, void* stream) {
+  if (rows < 0 || cols < 0 || cols > INT32_MAX) {
+    set_last_error("b200_softmax_xent: bad shape [%lld, %lld]", (long long)rows, (long long)cols);
+    return B200_INVALID_ARGUMENT;
+  }
+  if (rows == 0) return B200_OK;
+  int rc = require_device("b200_softmax_xent");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  if (cols == 0) return b200_memset_async(loss, 0, (size_t)rows * (dtype == B200_DT_FLOAT ? 4 : 2), stream);
+  if (dtype == B200_DT_FLOAT) {
+    if (cols <= 1024)
+      xent_warp_kernel<float><<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(
+          static_cast<const float*>(logits), static_cast<const float*>(labels),
+          static_cast<float*>(loss), static_cast<float*>(backprop), rows, (int)cols);
+    else
+      xent_block_kernel<float><<<(unsigned)rows, 256, 0, s>>>(
+          static_cast<const float*>(logits), static_cast<const float*>(labels),
+          static_cast<float*>(loss), static_cast<float*>(backprop), (int)cols);
+  } else if (dtype == B200_DT_BFLOAT16) {
+    if (cols <= 1024)
+      xent_warp_kernel<__nv_bfloat16><<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(
+          static_cast<const __nv_bfloat16*>(logits), static_cast<const __nv_bfloat16*>(labels),
+          static_cast<__nv_bfloat16*>(loss), static_cast<__nv_bfloat16*>(backprop), rows,
+          (int)cols);
+    else
+      xent_block_kernel<__nv_bfloat16><<<(unsigned)rows, 256, 0, s>>>(
+          static_cast<const __nv_bfloat16*>(logits), static_cast<const __nv_bfloat16*>(labels),
+          static_cast<__nv_bfloat16*>(loss), static_cast<__nv_bfloat16*>(backprop), (int)cols);
+  } else {
+    set_last_error("b200_softmax_xent: unsupported dtype %d", dtype);
+    return B200_UNIMPLEMENTED;
+  }
+  note_launch();
+  return check_launch("b200_softmax_xent");
+}
+
+int b200_argmax(int dtype, const void* in, int64_t* out, int64_t outer, int64_t axis_size,
+                int64_t inner, void* stream) {
+  if (outer < 0 || inner < 0 || axis_size <= 0) {
+    set_last_error("b200_argmax: bad shape [%lld, %lld, %lld] (axis must be non-empty)",
+                   (long long)outer, (long long)axis_size, (long long)inner);
+    return B200_INVALID_ARGUMENT;
+  }
+  if (outer * inner == 0) return B200_OK;
+  int rc = require_device("b200_argmax");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+#define ARG_LAUNCH(T)                                                                          \
+  do {                                                                                         \
+    if (inner == 1 && axis_size >= 64)                                                         \
+      argmax_last_axis_kernel<T><<<(unsigned)((outer + 7) / 8), 256, 0, s>>>(                  \
+          static_cast<const T*>(in), out, outer, axis_size);                                   \
+    else                                                                                       \
+      argmax_strided_kernel<T><<<(unsigned)((outer * inner + 255) / 256), 256, 0, s>>>(        \
+          static_cast<const T*>(in), out, outer, axis_size, inner);                            \
+  } while (0)
+  if (dtype == B200_DT_FLOAT)
+    ARG_LAUNCH(float);
+  else if (dtype == B200_DT_INT32)
+    ARG_LAUNCH(int32_t);
+  else if (dtype == B200_DT_INT64)
+    ARG_LAUNCH(int64_t);
+  else {
+    set_last_error("b200_argmax: unsupported dtype %d", dtype);
+    return B200_UNIMPLEMENTED;
+  }
+#undef ARG_LAUNCH
+  note_launch();
+  return check_launch("b200_argmax");
+}
+
+int b200_reduce_sum(int dtype, const void* in, float scale, void* out, int64_t n, void* stream) {
+  if (dtype != B200_DT_FLOAT) {
+    set_last_error("b200_reduce_sum: only DT_FLOAT is supported (got %d)", dtype);
+    return B200_UNIMPLEMENTED;
+  }
+  if (n < 0) {
+    set_last_error("b200_reduce_sum: negative n");
+    return B200_INVALID_ARGUMENT;
+  }
+  int rc = require_device("b200_reduce_sum");
+  if (rc) return rc;
+  sum_single<<<1, 256, 0, as_stream(stream)>>>(static_cast<const float*>(in),
+                                                static_cast<float*>(out), n, scale);
+  note_launch();
+  return check_launch("b200_reduce_sum");
+}
+
+}  // extern "C"

@@ -1,0 +1,312 @@
+// StreamExecutor-level shim of libb200tf.so: streams, events, device/pinned memory, copies,
+// plus library-wide helpers (error string, launch counter, driver entry points, NCCL loader).
+// Mirrors the members of perftools::gputools::Stream / StreamExecutor that the reference's GPU
+// device and kernels use (tensorflow/stream_executor/stream.h:116,189,214,1482-1531,1591;
+// stream_executor_pimpl.h:110,191,226-268).
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <mutex>
+
+#include "b200_internal.h"
+
+namespace b200 {
+
+static thread_local char g_err[1024] = "";
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_matmul_precision{0};
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+void note_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("%s: kernel launch failed: %s", what, cudaGetErrorString(e));
+    return B200_INTERNAL;
+  }
+  return B200_OK;
+}
+
+int require_device(const char* what) {
+  static int cached = -1;  // device count; racy init is benign
+  if (cached < 0) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+      n = 0;
+      cudaGetLastError();
+    }
+    cached = n;
+  }
+  if (cached == 0) {
+    set_last_error("%s: no CUDA device available (libb200tf has no CPU fallback)", what);
+    return B200_INTERNAL;
+  }
+  return B200_OK;
+}
+
+int sm_count() {
+  static int cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
+const DriverApi& driver() {
+  static DriverApi api;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      api.cuTensorMapEncodeTiled = reinterpret_cast<decltype(api.cuTensorMapEncodeTiled)>(fn);
+    } else {
+      api.cuTensorMapEncodeTiled = nullptr;
+      cudaGetLastError();
+    }
+  });
+  return api;
+}
+
+// ------------------------------------------------------------------ NCCL (dlopen'ed)
+struct Id128 {
+  char bytes[128];
+};
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /*ncclUniqueId by value: 128 bytes*/ Id128, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+static std::once_flag g_nccl_once;
+
+static bool load_nccl() {
+  std::call_once(g_nccl_once, [] {
+    const char* names[] = {"libnccl.so.2", "libnccl.so", nullptr};
+    const char* env = getenv("B200TF_NCCL_LIB");
+    void* h = env ? dlopen(env, RTLD_NOW | RTLD_GLOBAL) : nullptr;
+    for (int i = 0; !h && names[i]; ++i) h = dlopen(names[i], RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+    g_nccl.handle = h;
+    g_nccl.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclGetUniqueId"));
+    g_nccl.CommInitRank =
+        reinterpret_cast<int (*)(void**, int, Id128, int)>(dlsym(h, "ncclCommInitRank"));
+    g_nccl.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+    g_nccl.AllReduce =
+        reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(
+            dlsym(h, "ncclAllReduce"));
+    g_nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+  });
+  if (!g_nccl.handle || !g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) {
+    set_last_error("NCCL: libnccl.so.2 could not be loaded (set B200TF_NCCL_LIB)");
+    return false;
+  }
+  return true;
+}
+static int nccl_rc(int r, const char* what) {
+  if (r == 0) return B200_OK;
+  set_last_error("%s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "nccl error");
+  return B200_INTERNAL;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+#define CUDA_RC(expr, what)                                               \
+  do {                                                                    \
+    cudaError_t _e = (expr);                                              \
+    if (_e != cudaSuccess) {                                              \
+      set_last_error("%s: %s", what, cudaGetErrorString(_e));             \
+      cudaGetLastError();                                                 \
+      return _e == cudaErrorMemoryAllocation ? B200_RESOURCE_EXHAUSTED    \
+                                             : B200_INTERNAL;             \
+    }                                                                     \
+  } while (0)
+
+extern "C" {
+
+const char* b200_version(void) { return "b200tf 0.1 (sm_100a)"; }
+const char* b200_last_error(void) { return g_err; }
+
+int b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+int b200_set_device(int ordinal) {
+  CUDA_RC(cudaSetDevice(ordinal), "b200_set_device");
+  return B200_OK;
+}
+uint64_t b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int b200_set_matmul_precision(int mode) {
+  if (mode < 0 || mode > 1) {
+    set_last_error("b200_set_matmul_precision: mode must be 0 or 1 (got %d)", mode);
+    return B200_INVALID_ARGUMENT;
+  }
+  g_matmul_precision.store(mode);
+  return B200_OK;
+}
+int b200_get_matmul_precision(void) { return g_matmul_precision.load(); }
+
+int b200_stream_create(void** stream) {
+  cudaStream_t s;
+  CUDA_RC(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "b200_stream_create");
+  *stream = s;
+  return B200_OK;
+}
+int b200_stream_destroy(void* stream) {
+  CUDA_RC(cudaStreamDestroy(as_stream(stream)), "b200_stream_destroy");
+  return B200_OK;
+}
+int b200_stream_synchronize(void* stream) {
+  CUDA_RC(cudaStreamSynchronize(as_stream(stream)), "b200_stream_synchronize");
+  return B200_OK;
+}
+int b200_stream_wait_event(void* stream, void* event) {
+  CUDA_RC(cudaStreamWaitEvent(as_stream(stream), static_cast<cudaEvent_t>(event), 0),
+          "b200_stream_wait_event");
+  return B200_OK;
+}
+int b200_event_create(void** event) {
+  cudaEvent_t e;
+  CUDA_RC(cudaEventCreate(&e), "b200_event_create");
+  *event = e;
+  return B200_OK;
+}
+int b200_event_destroy(void* event) {
+  CUDA_RC(cudaEventDestroy(static_cast<cudaEvent_t>(event)), "b200_event_destroy");
+  return B200_OK;
+}
+int b200_event_record(void* event, void* stream) {
+  CUDA_RC(cudaEventRecord(static_cast<cudaEvent_t>(event), as_stream(stream)),
+          "b200_event_record");
+  return B200_OK;
+}
+int b200_event_synchronize(void* event) {
+  CUDA_RC(cudaEventSynchronize(static_cast<cudaEvent_t>(event)), "b200_event_synchronize");
+  return B200_OK;
+}
+int b200_event_query(void* event) {
+  cudaError_t e = cudaEventQuery(static_cast<cudaEvent_t>(event));
+  if (e == cudaSuccess) return 0;
+  if (e == cudaErrorNotReady) {
+    cudaGetLastError();
+    return 1;
+  }
+  set_last_error("b200_event_query: %s", cudaGetErrorString(e));
+  return -B200_INTERNAL;
+}
+int b200_event_elapsed_ms(void* start, void* stop, float* ms) {
+  CUDA_RC(cudaEventElapsedTime(ms, static_cast<cudaEvent_t>(start), static_cast<cudaEvent_t>(stop)),
+          "b200_event_elapsed_ms");
+  return B200_OK;
+}
+int b200_malloc(void** dptr, size_t bytes) {
+  *dptr = nullptr;
+  if (bytes == 0) return B200_OK;
+  CUDA_RC(cudaMalloc(dptr, bytes), "b200_malloc");
+  return B200_OK;
+}
+int b200_free(void* dptr) {
+  if (!dptr) return B200_OK;
+  CUDA_RC(cudaFree(dptr), "b200_free");
+  return B200_OK;
+}
+int b200_host_malloc(void** hptr, size_t bytes) {
+  *hptr = nullptr;
+  if (bytes == 0) return B200_OK;
+  CUDA_RC(cudaHostAlloc(hptr, bytes, cudaHostAllocDefault), "b200_host_malloc");
+  return B200_OK;
+}
+int b200_host_free(void* hptr) {
+  if (!hptr) return B200_OK;
+  CUDA_RC(cudaFreeHost(hptr), "b200_host_free");
+  return B200_OK;
+}
+int b200_memcpy_h2d_async(void* dst, const void* src_host, size_t bytes, void* stream) {
+  if (bytes == 0) return B200_OK;
+  CUDA_RC(cudaMemcpyAsync(dst, src_host, bytes, cudaMemcpyHostToDevice, as_stream(stream)),
+          "b200_memcpy_h2d_async");
+  return B200_OK;
+}
+int b200_memcpy_d2h_async(void* dst_host, const void* src, size_t bytes, void* stream) {
+  if (bytes == 0) return B200_OK;
+  CUDA_RC(cudaMemcpyAsync(dst_host, src, bytes, cudaMemcpyDeviceToHost, as_stream(stream)),
+          "b200_memcpy_d2h_async");
+  return B200_OK;
+}
+int b200_memcpy_d2d_async(void* dst, const void* src, size_t bytes, void* stream) {
+  if (bytes == 0) return B200_OK;
+  CUDA_RC(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, as_stream(stream)),
+          "b200_memcpy_d2d_async");
+  return B200_OK;
+}
+int b200_memset_async(void* dst, int byte_value, size_t bytes, void* stream) {
+  if (bytes == 0) return B200_OK;
+  CUDA_RC(cudaMemsetAsync(dst, byte_value, bytes, as_stream(stream)), "b200_memset_async");
+  return B200_OK;
+}
+int b200_mem_info(size_t* free_bytes, size_t* total_bytes) {
+  CUDA_RC(cudaMemGetInfo(free_bytes, total_bytes), "b200_mem_info");
+  return B200_OK;
+}
+
+// ------------------------------------------------------------------ NCCL
+int b200_nccl_unique_id(void* id128_host) {
+  if (!load_nccl()) return B200_FAILED_PRECONDITION;
+  return nccl_rc(g_nccl.GetUniqueId(id128_host), "ncclGetUniqueId");
+}
+int b200_nccl_comm_init_rank(void** comm, int nranks, const void* id128_host, int rank) {
+  if (!load_nccl()) return B200_FAILED_PRECONDITION;
+  Id128 id;
+  memcpy(&id, id128_host, sizeof(id));
+  return nccl_rc(g_nccl.CommInitRank(comm, nranks, id, rank), "ncclCommInitRank");
+}
+int b200_nccl_comm_destroy(void* comm) {
+  if (!load_nccl()) return B200_FAILED_PRECONDITION;
+  return nccl_rc(g_nccl.CommDestroy(comm), "ncclCommDestroy");
+}
+int b200_nccl_all_reduce_sum(int dtype, const void* sendbuf, void* recvbuf, int64_t count,
+                             void* comm, void* stream) {
+  if (!load_nccl()) return B200_FAILED_PRECONDITION;
+  int nccl_type;
+  if (dtype == B200_DT_FLOAT)
+    nccl_type = 7;  // ncclFloat32
+  else if (dtype == B200_DT_BFLOAT16)
+    nccl_type = 9;  // ncclBfloat16
+  else {
+    set_last_error("b200_nccl_all_reduce_sum: unsupported dtype %d", dtype);
+    return B200_UNIMPLEMENTED;
+  }
+  if (count == 0) return B200_OK;
+  return nccl_rc(g_nccl.AllReduce(sendbuf, recvbuf, (size_t)count, nccl_type, /*ncclSum*/ 0, comm,
+                                  as_stream(stream)),
+                 "ncclAllReduce");
+}
+
+}  // extern "C"
