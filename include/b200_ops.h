@@ -95,9 +95,15 @@ B200_API int b200_mem_info(size_t* free_bytes, size_t* total_bytes);
  * a is [m,k] (or [k,m] when transpose_a), b is [k,n] (or [n,k] when transpose_b), c is [m,n];
  * same argument meaning as the op attrs (core/ops/math_ops.cc:1033-1040).  m,n,k > 0: the
  * zero-size rules of MatMulOp::Compute (matmul_op.cc:240-253) stay in the OpKernel wrapper.
- * dtype: DT_FLOAT (tf32 tensor cores, fp32 accumulate) or DT_BFLOAT16 (fp32 accumulate). */
+ * dtype: DT_FLOAT (tf32 tensor cores, fp32 accumulate) or DT_BFLOAT16 (fp32 accumulate).
+ * workspace (optional, may be NULL/0): b200_matmul_workspace_bytes() bytes of device scratch let
+ * shapes with few output tiles (e.g. dW = X^T dY, 1024x1024 output, K = 4096) split K across
+ * SMs; partial sums are added in a fixed order, so results do not depend on scheduling.  The
+ * OpKernel wrapper obtains it with allocate_temp, as the reference's GPU conv kernels do. */
+B200_API size_t b200_matmul_workspace_bytes(int dtype, int64_t m, int64_t n, int64_t k);
 B200_API int b200_matmul(int dtype, const void* a, const void* b, void* c, int64_t m, int64_t n,
-                         int64_t k, int transpose_a, int transpose_b, void* stream);
+                         int64_t k, int transpose_a, int transpose_b, void* workspace,
+                         size_t workspace_bytes, void* stream);
 /* Replaces LaunchBatchMatMul<GPUDevice,Scalar>::Launch -> ThenBlasGemmBatchedWithScratch
  * (core/kernels/batch_matmul_op_impl.h:297-363).  x is [batch,m,k] (or [batch,k,m] when adj_x),
  * y is [batch,k,n] (or [batch,n,k] when adj_y); strided, no pointer arrays, no scratch. */

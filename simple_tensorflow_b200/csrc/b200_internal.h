@@ -40,11 +40,15 @@ struct GemmArgs {
   bool a_mn_major;           // A stored as [K,M] (transpose_a)
   bool b_mn_major;           // B stored as [K,N] (i.e. NOT transpose_b)
   int force_bn;              // 0 = auto
+  void* workspace;           // optional device scratch enabling split-K (may be null)
+  size_t workspace_bytes;
 };
 bool gemm_tcgen05_supported(const GemmArgs& g);
 int gemm_tcgen05(const GemmArgs& g, cudaStream_t stream);
 int gemm_simt(const GemmArgs& g, cudaStream_t stream);
 // Precision-aware front door used by matmul / batch_matmul / conv.
 int gemm_dispatch(const GemmArgs& g, cudaStream_t stream);
+// Scratch that lets gemm_dispatch use split-K for this shape (0 when it would not split).
+size_t gemm_workspace_bytes(int dtype, long long M, long long N, long long K, long long batch);
 
 }  // namespace b200

@@ -1,0 +1,373 @@
+// Conv2D / Conv2DBackpropInput / Conv2DBackpropFilter, NHWC x HWIO -> NHWC.
+//
+// Replaces LaunchConv2DOp<GPUDevice,T>::launch (tensorflow/core/kernels/conv_ops.cc:433-720),
+// Conv2DSlowBackpropInputOp<GPUDevice,T> (conv_grad_input_ops.cc:533-917) and
+// Conv2DSlowBackpropFilterOp<GPUDevice,T> (conv_grad_filter_ops.cc:361-738): cuDNN calls wrapped
+// in NHWC<->NCHW and HWIO->OIHW shuffles (conv_ops_gpu_3.cu.cc).  Here everything stays NHWC:
+//
+//   forward   out[N*OH*OW, K]  = patches[N*OH*OW, R*S*C] . filter[R*S*C, K]
+//   dFilter   dW [R*S*C, K]    = patches^T               . dY[N*OH*OW, K]      (split-K, ordered)
+//   dInput    cols[N*OH*OW, R*S*C] = dY . filter^T,  then a GATHER col2im (no atomics)
+//
+// i.e. the im2col-GEMM formulation of the reference's CPU kernels
+// (eigen_spatial_convolutions.h:1050-1067, conv_grad_filter_ops.cc:55-82,
+// conv_grad_input_ops.cc:57-87) with the GEMMs on the tcgen05 kernel (gemm_tcgen05.cu).  The
+// filter needs no reshuffle: HWIO is already the row-major [R*S*C, K] GEMM operand.  1x1/stride-1
+// convolutions skip the patch matrix entirely (same shortcut as conv_ops.cc:454-480).
+// Round-1 data path: the patch matrix is materialised in the caller-provided workspace; the
+// implicit-GEMM (TMA im2col) variant that removes this traffic is the next optimisation step.
+#include <cuda_bf16.h>
+
+#include "b200_internal.h"
+
+namespace b200 {
+
+struct ConvG {
+  int N, H, W, C, R, S, K, OH, OW, sh, sw, pt, pl;
+  int ldk;  // leading dimension of the patch matrix (R*S*C rounded up to 16 bytes)
+};
+
+// One thread copies one 16-byte (or scalar) piece of one patch row.
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+im2col_kernel(const T* __restrict__ in, T* __restrict__ col, ConvG g, long long total) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int per_row = g.ldk / V;  // vectors per patch row (incl. zero padding)
+  const int j = (int)(idx % per_row) * V;
+  const long long p = idx / per_row;  // output pixel index n*OH*OW + oh*OW + ow
+  T* dst = col + p * g.ldk + j;
+  const int rsc = g.R * g.S * g.C;
+  if (j >= rsc) {
+#pragma unroll
+    for (int e = 0; e < V; ++e) dst[e] = T(0.f);
+    return;
+  }
+  const int c = j % g.C;
+  const int tap = j / g.C;
+  const int s = tap % g.S, r = tap / g.S;
+  const int ow = (int)(p % g.OW);
+  const long long q = p / g.OW;
+  const int oh = (int)(q % g.OH);
+  const int n = (int)(q / g.OH);
+  const int ih = oh * g.sh - g.pt + r, iw = ow * g.sw - g.pl + s;
+  if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
+    const T* src = in + (((long long)n * g.H + ih) * g.W + iw) * g.C + c;
+    if (V * sizeof(T) == 16) {
+      *reinterpret_cast<uint4*>(dst) = __ldg(reinterpret_cast<const uint4*>(src));
+    } else {
+#pragma unroll
+      for (int e = 0; e < V; ++e) dst[e] = src[e];
+    }
+  } else {
+    if (V * sizeof(T) == 16) {
+      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
+    } else {
+#pragma unroll
+      for (int e = 0; e < V; ++e) dst[e] = T(0.f);
+    }
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ float cvt_in(T v);
+template <>
+__device__ __forceinline__ float cvt_in<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ float cvt_in<__nv_bfloat16>(__nv_bfloat16 v) {
+  return __bfloat162float(v);
+}
+template <typename T>
+__device__ __forceinline__ T cvt_out(float v);
+template <>
+__device__ __forceinline__ float cvt_out<float>(float v) {
+  return v;
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) {
+  return __float2bfloat16_rn(v);
+}
+
+// Gather col2im: thread per input element (n, h, w, c); sums the patch-matrix entries that map
+// to it, visiting output pixels in ascending (oh, ow) order like Col2im
+// (conv_grad_input_ops.cc:57-87) does.
+template <typename T>
+__global__ void __launch_bounds__(256)
+col2im_gather_kernel(const T* __restrict__ col, T* __restrict__ dx, ConvG g, long long total) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % g.C);
+  long long q = idx / g.C;
+  const int w = (int)(q % g.W);
+  q /= g.W;
+  const int h = (int)(q % g.H);
+  const int n = (int)(q / g.H);
+  float acc = 0.f;
+  // oh * sh - pt + r == h  with 0 <= r < R
+  const int hp = h + g.pt, wp = w + g.pl;
+  int oh_lo = hp - (g.R - 1);
+  oh_lo = oh_lo <= 0 ? 0 : (oh_lo + g.sh - 1) / g.sh;
+  const int oh_hi = min(hp / g.sh, g.OH - 1);
+  int ow_lo = wp - (g.S - 1);
+  ow_lo = ow_lo <= 0 ? 0 : (ow_lo + g.sw - 1) / g.sw;
+  const int ow_hi = min(wp / g.sw, g.OW - 1);
+  for (int oh = oh_lo; oh <= oh_hi; ++oh) {
+    const int r = hp - oh * g.sh;
+    for (int ow = ow_lo; ow <= ow_hi; ++ow) {
+      const int s = wp - ow * g.sw;
+      const long long p = ((long long)n * g.OH + oh) * g.OW + ow;
+      acc += cvt_in<T>(col[p * g.ldk + (r * g.S + s) * g.C + c]);
+    }
+  }
+  dx[idx] = cvt_out<T>(acc);
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline size_t esize_of(int dtype) { return dtype == B200_DT_FLOAT ? 4 : 2; }
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static int to_geom(const char* what, int dtype, const b200_conv2d_geometry* in, ConvG* g) {
+  if (dtype != B200_DT_FLOAT && dtype != B200_DT_BFLOAT16) {
+    set_last_error("%s: unsupported dtype %d", what, dtype);
+    return B200_UNIMPLEMENTED;
+  }
+  if (!in) {
+    set_last_error("%s: null geometry", what);
+    return B200_INVALID_ARGUMENT;
+  }
+  if (in->batch < 0 || in->in_h < 0 || in->in_w < 0 || in->in_c < 0 || in->filter_h <= 0 ||
+      in->filter_w <= 0 || in->out_c < 0 || in->out_h < 0 || in->out_w < 0 || in->stride_h <= 0 ||
+      in->stride_w <= 0 || in->pad_top < 0 || in->pad_left < 0) {
+    set_last_error("%s: invalid geometry", what);
+    return B200_INVALID_ARGUMENT;
+  }
+  const int64_t lim = INT32_MAX;
+  if (in->batch > lim || in->in_h > lim || in->in_w > lim || in->in_c > lim || in->out_c > lim ||
+      in->filter_h * in->filter_w * in->in_c > lim) {
+    set_last_error("%s: dimension exceeds int32", what);
+    return B200_INVALID_ARGUMENT;
+  }
+  g->N = (int)in->batch;
+  g->H = (int)in->in_h;
+  g->W = (int)in->in_w;
+  g->C = (int)in->in_c;
+  g->R = (int)in->filter_h;
+  g->S = (int)in->filter_w;
+  g->K = (int)in->out_c;
+  g->OH = (int)in->out_h;
+  g->OW = (int)in->out_w;
+  g->sh = in->stride_h;
+  g->sw = in->stride_w;
+  g->pt = in->pad_top;
+  g->pl = in->pad_left;
+  const int a = (int)(16 / esize_of(dtype));
+  const int rsc = g->R * g->S * g->C;
+  g->ldk = (rsc + a - 1) / a * a;
+  return B200_OK;
+}
+
+static bool is_pointwise(const ConvG& g) {
+  return g.R == 1 && g.S == 1 && g.sh == 1 && g.sw == 1 && g.pt == 0 && g.pl == 0 &&
+         g.OH == g.H && g.OW == g.W;
+}
+
+template <typename T>
+static int run_im2col(const void* in, void* col, const ConvG& g, cudaStream_t s) {
+  constexpr int V16 = 16 / sizeof(T);
+  const long long rows = (long long)g.N * g.OH * g.OW;
+  if (g.C % V16 == 0 && aligned16(in) && aligned16(col)) {
+    const long long total = rows * (g.ldk / V16);
+    im2col_kernel<T, V16><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        static_cast<const T*>(in), static_cast<T*>(col), g, total);
+  } else {
+    const long long total = rows * g.ldk;
+    im2col_kernel<T, 1><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
+        static_cast<const T*>(in), static_cast<T*>(col), g, total);
+  }
+  note_launch();
+  return check_launch("im2col");
+}
+
+static GemmArgs base_gemm(int dtype) {
+  GemmArgs a{};
+  a.dtype = dtype;
+  a.batch = 1;
+  return a;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+size_t b200_conv2d_workspace_bytes(int dtype, const b200_conv2d_geometry* geom, int which) {
+  ConvG g;
+  if (to_geom("b200_conv2d_workspace_bytes", dtype, geom, &g) != B200_OK) return 0;
+  const size_t es = esize_of(dtype);
+  const long long rows = (long long)g.N * g.OH * g.OW;
+  const long long rsc = (long long)g.R * g.S * g.C;
+  const size_t col = is_pointwise(g) ? 0 : align256((size_t)rows * g.ldk * es);
+  if (which == 0) return col + align256(gemm_workspace_bytes(dtype, rows, g.K, rsc, 1));
+  if (which == 1) return col + align256(gemm_workspace_bytes(dtype, rows, rsc, g.K, 1));
+  if (which == 2) return col + align256(gemm_workspace_bytes(dtype, rsc, g.K, rows, 1));
+  return 0;
+}
+
+int b200_conv2d(int dtype, const void* input, const void* filter, void* output,
+                const b200_conv2d_geometry* geom, void* workspace, size_t workspace_bytes,
+                void* stream) {
+  ConvG g;
+  int rc = to_geom("b200_conv2d", dtype, geom, &g);
+  if (rc) return rc;
+  const long long rows = (long long)g.N * g.OH * g.OW;
+  if (rows == 0 || g.K == 0) return B200_OK;  // conv_ops.cc:357-359
+  rc = require_device("b200_conv2d");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  const size_t es = esize_of(dtype);
+  const long long rsc = (long long)g.R * g.S * g.C;
+  if (rsc == 0) return b200_memset_async(output, 0, (size_t)rows * g.K * es, stream);
+  const size_t need = b200_conv2d_workspace_bytes(dtype, geom, 0);
+  if (need > 0 && (!workspace || workspace_bytes < need)) {
+    set_last_error("b200_conv2d: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
+    return B200_INVALID_ARGUMENT;
+  }
+  GemmArgs a = base_gemm(dtype);
+  a.b = filter;  // [R*S*C, K] row-major == HWIO
+  a.c = output;
+  a.M = rows;
+  a.N = g.K;
+  a.K = rsc;
+  a.ldb = g.K;
+  a.ldc = g.K;
+  a.a_mn_major = false;
+  a.b_mn_major = true;
+  if (is_pointwise(g)) {
+    a.a = input;
+    a.lda = g.C;
+    a.workspace = workspace;
+    a.workspace_bytes = workspace ? workspace_bytes : 0;
+  } else {
+    const size_t col_bytes = align256((size_t)rows * g.ldk * es);
+    rc = dtype == B200_DT_FLOAT ? run_im2col<float>(input, workspace, g, s)
+                                : run_im2col<__nv_bfloat16>(input, workspace, g, s);
+    if (rc) return rc;
+    a.a = workspace;
+    a.lda = g.ldk;
+    a.workspace = static_cast<char*>(workspace) + col_bytes;
+    a.workspace_bytes = workspace_bytes - col_bytes;
+    if (a.workspace_bytes == 0) a.workspace = nullptr;
+  }
+  return gemm_dispatch(a, s);
+}
+
+int b200_conv2d_backprop_filter(int dtype, const void* input, const void* out_backprop,
+                                void* filter_backprop, const b200_conv2d_geometry* geom,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  ConvG g;
+  int rc = to_geom("b200_conv2d_backprop_filter", dtype, geom, &g);
+  if (rc) return rc;
+  const long long rows = (long long)g.N * g.OH * g.OW;
+  const long long rsc = (long long)g.R * g.S * g.C;
+  if (rsc == 0 || g.K == 0) return B200_OK;
+  rc = require_device("b200_conv2d_backprop_filter");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  const size_t es = esize_of(dtype);
+  if (rows == 0) return b200_memset_async(filter_backprop, 0, (size_t)rsc * g.K * es, stream);
+  const size_t need = b200_conv2d_workspace_bytes(dtype, geom, 2);
+  if (need > 0 && (!workspace || workspace_bytes < need)) {
+    set_last_error("b200_conv2d_backprop_filter: workspace too small (%zu < %zu bytes)",
+                   workspace_bytes, need);
+    return B200_INVALID_ARGUMENT;
+  }
+  GemmArgs a = base_gemm(dtype);
+  a.b = out_backprop;  // [rows, K]
+  a.c = filter_backprop;
+  a.M = rsc;
+  a.N = g.K;
+  a.K = rows;
+  a.ldb = g.K;
+  a.ldc = g.K;
+  a.a_mn_major = true;  // A^T is stored: patches [rows, R*S*C]
+  a.b_mn_major = true;
+  if (is_pointwise(g)) {
+    a.a = input;
+    a.lda = g.C;
+    a.workspace = workspace;
+    a.workspace_bytes = workspace ? workspace_bytes : 0;
+  } else {
+    const size_t col_bytes = align256((size_t)rows * g.ldk * es);
+    rc = dtype == B200_DT_FLOAT ? run_im2col<float>(input, workspace, g, s)
+                                : run_im2col<__nv_bfloat16>(input, workspace, g, s);
+    if (rc) return rc;
+    a.a = workspace;
+    a.lda = g.ldk;
+    a.workspace = static_cast<char*>(workspace) + col_bytes;
+    a.workspace_bytes = workspace_bytes - col_bytes;
+    if (a.workspace_bytes == 0) a.workspace = nullptr;
+  }
+  return gemm_dispatch(a, s);
+}
+
+int b200_conv2d_backprop_input(int dtype, const void* filter, const void* out_backprop,
+                               void* in_backprop, const b200_conv2d_geometry* geom,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+  ConvG g;
+  int rc = to_geom("b200_conv2d_backprop_input", dtype, geom, &g);
+  if (rc) return rc;
+  const long long rows = (long long)g.N * g.OH * g.OW;
+  const long long rsc = (long long)g.R * g.S * g.C;
+  const long long nin = (long long)g.N * g.H * g.W * g.C;
+  if (nin == 0) return B200_OK;
+  rc = require_device("b200_conv2d_backprop_input");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  const size_t es = esize_of(dtype);
+  if (rows == 0 || g.K == 0) return b200_memset_async(in_backprop, 0, (size_t)nin * es, stream);
+  const size_t need = b200_conv2d_workspace_bytes(dtype, geom, 1);
+  if (need > 0 && (!workspace || workspace_bytes < need)) {
+    set_last_error("b200_conv2d_backprop_input: workspace too small (%zu < %zu bytes)",
+                   workspace_bytes, need);
+    return B200_INVALID_ARGUMENT;
+  }
+  GemmArgs a = base_gemm(dtype);
+  a.a = out_backprop;  // [rows, K]
+  a.lda = g.K;
+  a.b = filter;        // [R*S*C, K]: logical B[K, R*S*C] stored transposed => K-major
+  a.ldb = g.K;
+  a.M = rows;
+  a.N = rsc;
+  a.K = g.K;
+  a.a_mn_major = false;
+  a.b_mn_major = false;
+  if (is_pointwise(g)) {
+    a.c = in_backprop;
+    a.ldc = g.C;
+    a.workspace = workspace;
+    a.workspace_bytes = workspace ? workspace_bytes : 0;
+    return gemm_dispatch(a, s);
+  }
+  const size_t col_bytes = align256((size_t)rows * g.ldk * es);
+  a.c = workspace;
+  a.ldc = g.ldk;
+  a.workspace = static_cast<char*>(workspace) + col_bytes;
+  a.workspace_bytes = workspace_bytes - col_bytes;
+  if (a.workspace_bytes == 0) a.workspace = nullptr;
+  rc = gemm_dispatch(a, s);
+  if (rc) return rc;
+  if (dtype == B200_DT_FLOAT)
+    col2im_gather_kernel<float><<<(unsigned)((nin + 255) / 256), 256, 0, s>>>(
+        static_cast<const float*>(workspace), static_cast<float*>(in_backprop), g, nin);
+  else
+    col2im_gather_kernel<__nv_bfloat16><<<(unsigned)((nin + 255) / 256), 256, 0, s>>>(
+        static_cast<const __nv_bfloat16*>(workspace), static_cast<__nv_bfloat16*>(in_backprop), g,
+        nin);
+  note_launch();
+  return check_launch("col2im_gather");
+}
+
+}  // extern "C"

@@ -55,10 +55,15 @@ constexpr size_t gemm_smem_bytes() {
          1024 + 256;
 }
 
+static int plan_splits(long long tiles, int num_kb);
+
 struct GemmShape {
   int M, N, K, batch;
   int ldc;            // elements
   long long strideC;  // elements between batches
+  int splits;         // split-K factor (1 = none)
+  int kb_per_split;   // K blocks per split
+  float* partial;     // [splits][batch][M][N] fp32 partial sums when splits > 1
 };
 
 __device__ __forceinline__ void store_row32(float* dst, const uint32_t (&v)[32], int ncols,
@@ -136,6 +141,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
   const int tiles_per_batch = tiles_m * tiles_n;
   const int num_tiles = tiles_per_batch * s.batch;
   const int num_kb = (s.K + BK - 1) / BK;
+  // Work item = (split, tile): consecutive CTAs take different tiles of the same K split.
+  const int num_work = num_tiles * s.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmapA);
@@ -165,12 +172,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int split = work / num_tiles;
+        const int tile = work - split * num_tiles;
         const int b = tile / tiles_per_batch;
         const int t = tile - b * tiles_per_batch;
         const int m0 = (t % tiles_m) * kBM;
         const int n0 = (t / tiles_m) * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int kb0 = split * s.kb_per_split;
+        const int kb1 = min(kb0 + s.kb_per_split, num_kb);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           mbar_expect_tx(&full_bar[stage], kABytes + kBBytes);
           const int k0 = kb * BK;
@@ -204,11 +215,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       uint32_t acc = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const int split = work / num_tiles;
+        const int kb0 = split * s.kb_per_split;
+        const int kb1 = min(kb0 + s.kb_per_split, num_kb);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smA + stage * kABytes);
@@ -229,9 +243,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
                                                                kMn32 ? 512 : 1024, kMn32 ? 1 : 2)
                                         : make_smem_desc_sw128(b_addr + b_off, 16, 1024);
             if (sizeof(TIn) == 4)
-              umma_tf32(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0);
+              umma_tf32(d_tmem, adesc, bdesc, kIdesc, ((kb - kb0) | k) != 0);
             else
-              umma_f16(d_tmem, adesc, bdesc, kIdesc, (kb | k) != 0);
+              umma_f16(d_tmem, adesc, bdesc, kIdesc, ((kb - kb0) | k) != 0);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == kStages) {
@@ -253,7 +267,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
     const bool vec_ok = (s.ldc % (16 / (int)sizeof(TOut)) == 0) &&
                         (s.strideC % (16 / (int)sizeof(TOut)) == 0) &&
                         ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const int split = work / num_tiles;
+      const int tile = work - split * num_tiles;
       const int b = tile / tiles_per_batch;
       const int t = tile - b * tiles_per_batch;
       const int m0 = (t % tiles_m) * kBM;
@@ -262,6 +278,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
       tc_fence_after();
       const int row = m0 + quad * 32 + lane;
       TOut* crow = C + (long long)b * s.strideC + (long long)row * s.ldc;
+      // split-K: fp32 partial tile, dense [split][batch][M][N]
+      float* prow = s.partial + (((long long)split * s.batch + b) * s.M + row) * (long long)s.N;
+      const bool pvec = (s.N & 3) == 0;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
@@ -270,7 +289,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
         const int col = n0 + c * 32;
         int ncols = s.N - col;
         ncols = ncols > 32 ? 32 : ncols;
-        if (row < s.M && ncols > 0) store_row32(crow + col, v, ncols, vec_ok);
+        if (row < s.M && ncols > 0) {
+          if (s.splits > 1)
+            store_row32(prow + col, v, ncols, pvec);
+          else
+            store_row32(crow + col, v, ncols, vec_ok);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -287,6 +311,43 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc<kTmemCols>(tmem_base);
+  }
+}
+
+// Split-K reduction: out = sum over splits (ascending, deterministic) of the fp32 partials.
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, TOut* __restrict__ C, int splits,
+                     long long batch, int M, int N, int ldc, long long strideC) {
+  const long long per_split = batch * (long long)M * N;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;  // index of a 4-column group
+  const int n4 = (N + 3) / 4;
+  if (i >= batch * (long long)M * n4) return;
+  const int c4 = (int)(i % n4);
+  const long long r = i / n4;  // b * M + row
+  const long long b = r / M;
+  const int row = (int)(r - b * M);
+  const int col = c4 * 4;
+  const int nc = min(4, N - col);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* p = partial + r * N + col;
+  for (int s = 0; s < splits; ++s) {
+    if (nc == 4 && (N & 3) == 0) {
+      const float4 v = *reinterpret_cast<const float4*>(p + s * per_split);
+      acc[0] += v.x;
+      acc[1] += v.y;
+      acc[2] += v.z;
+      acc[3] += v.w;
+    } else {
+      for (int j = 0; j < nc; ++j) acc[j] += p[s * per_split + j];
+    }
+  }
+  TOut* dst = C + b * strideC + (long long)row * ldc + col;
+  for (int j = 0; j < nc; ++j) {
+    if (sizeof(TOut) == 4)
+      reinterpret_cast<float*>(dst)[j] = acc[j];
+    else
+      reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16_rn(acc[j]);
   }
 }
 
@@ -361,9 +422,30 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   s.ldc = (int)g.ldc;
   s.strideC = g.strideC;
   const long long tiles = ((g.M + kBM - 1) / kBM) * ((g.N + BN - 1) / BN) * g.batch;
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  // split-K when the output tiles alone cannot fill the SMs and scratch was provided
+  const int num_kb = (int)((g.K + Tr::kBK - 1) / Tr::kBK);
+  int splits = 1;
+  if (g.workspace) {
+    splits = plan_splits(tiles, num_kb);
+    while (splits > 1 &&
+           (size_t)splits * g.batch * g.M * g.N * sizeof(float) > g.workspace_bytes)
+      --splits;
+    if (splits < 1) splits = 1;
+  }
+  s.kb_per_split = (num_kb + splits - 1) / splits;
+  splits = (num_kb + s.kb_per_split - 1) / s.kb_per_split;  // no empty split
+  s.splits = splits;
+  s.partial = static_cast<float*>(g.workspace);
+  const long long work = tiles * splits;
+  const int grid = (int)(work < sm_count() ? work : sm_count());
   kern<<<grid, kGemmThreads, smem, stream>>>(ma, mb, static_cast<TOut*>(g.c), s);
   note_launch();
+  if (splits > 1) {
+    const long long groups = g.batch * g.M * ((g.N + 3) / 4);
+    splitk_reduce_kernel<TOut><<<(unsigned)((groups + 255) / 256), 256, 0, stream>>>(
+        s.partial, static_cast<TOut*>(g.c), splits, g.batch, s.M, s.N, s.ldc, s.strideC);
+    note_launch();
+  }
   return check_launch("gemm_tcgen05");
 }
 
@@ -375,14 +457,36 @@ static int dispatch_major(const GemmArgs& g, cudaStream_t stream) {
   return launch_gemm<TIn, TOut, true, true, BN>(g, stream);
 }
 
-// Tile-N choice: fill the 148 SMs.  128x128 tiles unless that leaves < 1 wave while 128x64 helps.
+// Split-K plan shared by the launcher and gemm_workspace_bytes(): how many K splits a 128-wide
+// tiling would use for this shape (1 = none).
+static int plan_splits(long long tiles, int num_kb) {
+  if (tiles * 2 > sm_count() || num_kb < 8) return 1;
+  long long splits = sm_count() / tiles;
+  if (splits > num_kb / 4) splits = num_kb / 4;  // >= 4 K blocks per split
+  if (splits > 16) splits = 16;
+  return splits < 1 ? 1 : (int)splits;
+}
+
+size_t gemm_workspace_bytes(int dtype, long long M, long long N, long long K, long long batch) {
+  if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return 0;
+  const int bk = dtype == B200_DT_FLOAT ? GemmTraits<float>::kBK : GemmTraits<__nv_bfloat16>::kBK;
+  const int bn = N <= 64 ? 64 : 128;
+  const long long tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn) * batch;
+  const int splits = plan_splits(tiles, (int)((K + bk - 1) / bk));
+  return splits > 1 ? (size_t)splits * batch * M * N * sizeof(float) : 0;
+}
+
+// Tile-N choice: fill the 148 SMs.  128x128 tiles; when those cannot fill the machine either
+// split K (scratch available) or fall back to 128x64 tiles.
 static int choose_bn(const GemmArgs& g) {
   if (g.force_bn == 64 || g.force_bn == 128 || g.force_bn == 256) return g.force_bn;
+  if (g.N <= 64) return 64;
   const long long tm = (g.M + kBM - 1) / kBM;
   const long long t128 = tm * ((g.N + 127) / 128) * g.batch;
-  if (g.N <= 64) return 64;
-  if (t128 < sm_count()) return 64;
-  return 128;
+  if (t128 >= sm_count()) return 128;
+  const int bk = g.dtype == B200_DT_FLOAT ? GemmTraits<float>::kBK : GemmTraits<__nv_bfloat16>::kBK;
+  if (g.workspace && plan_splits(t128, (int)((g.K + bk - 1) / bk)) > 1) return 128;
+  return 64;
 }
 
 bool gemm_tcgen05_supported(const GemmArgs& g) {

@@ -172,8 +172,13 @@ using namespace b200;
 
 extern "C" {
 
+size_t b200_matmul_workspace_bytes(int dtype, int64_t m, int64_t n, int64_t k) {
+  return gemm_workspace_bytes(dtype, m, n, k, 1);
+}
+
 int b200_matmul(int dtype, const void* a, const void* b, void* c, int64_t m, int64_t n, int64_t k,
-                int transpose_a, int transpose_b, void* stream) {
+                int transpose_a, int transpose_b, void* workspace, size_t workspace_bytes,
+                void* stream) {
   int rc = validate_gemm("b200_matmul", dtype, a, b, c, m, n, k, 1);
   if (rc) return rc;
   GemmArgs g{};
@@ -193,6 +198,8 @@ int b200_matmul(int dtype, const void* a, const void* b, void* c, int64_t m, int
   g.strideC = m * n;
   g.a_mn_major = transpose_a != 0;
   g.b_mn_major = transpose_b == 0;
+  g.workspace = workspace;
+  g.workspace_bytes = workspace ? workspace_bytes : 0;
   return gemm_dispatch(g, as_stream(stream));
 }
 
