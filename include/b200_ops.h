@@ -60,6 +60,12 @@ B200_API int b200_device_count(void);
 B200_API int b200_set_device(int ordinal);
 /* Kernels launched by this library in the calling process since load (all threads). */
 B200_API uint64_t b200_launch_count(void);
+/* Measurement hook for bench.py's roofline: between begin and end every tensor-core GEMM launch
+ * (MatMul, BatchMatMul, the conv GEMMs) is bracketed by CUDA events on its own stream;
+ * end() waits for them and returns the summed device time, launch count and 2*M*N*K FLOPs. */
+B200_API int b200_profile_begin(void);
+B200_API int b200_profile_end(double* gemm_ms_total, uint64_t* gemm_launches,
+                              double* gemm_flops_total);
 /* MatMul/Conv precision for DT_FLOAT: 0 = single-pass TF32 tensor cores (default; inputs are
  * truncated to 10 mantissa bits by the MMA, fp32 accumulate), 1 = SIMT fp32 FMA (IEEE fp32
  * products, the reference Eigen path's arithmetic).  Shapes the TMA path cannot address
@@ -199,9 +205,14 @@ B200_API int b200_conv2d_backprop_filter(int dtype, const void* input, const voi
                                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ graph glue
- * ApplyGradientDescent (core/kernels/training_ops.cc:410-412): var -= alpha * delta. */
-B200_API int b200_apply_gradient_descent(int dtype, void* var, float alpha, const void* delta,
-                                         int64_t n, void* stream);
+ * ApplyGradientDescent (core/kernels/training_ops.cc:410-412): var -= alpha * delta; alpha is a
+ * DEVICE scalar of the same dtype, as in the reference's GPU functor (training_ops_gpu.cu.cc). */
+B200_API int b200_apply_gradient_descent(int dtype, void* var, const void* alpha,
+                                         const void* delta, int64_t n, void* stream);
+/* Mul (core/kernels/cwise_op_mul_1.cc) for the two shapes gradient graphs need: same-shape, or
+ * y a DEVICE scalar broadcast over x (y_is_scalar != 0). */
+B200_API int b200_mul(int dtype, const void* x, const void* y, void* out, int64_t n,
+                      int y_is_scalar, void* stream);
 /* AddN (core/kernels/aggregate_ops.cc:153-176) for n_inputs <= 8. */
 B200_API int b200_add_n(int dtype, const void* const* inputs_host, int n_inputs, void* out,
                         int64_t n, void* stream);

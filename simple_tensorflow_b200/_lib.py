@@ -35,6 +35,9 @@ SIGNATURES = {
     "b200_device_count": (c_int, []),
     "b200_set_device": (c_int, [c_int]),
     "b200_launch_count": (ctypes.c_uint64, []),
+    "b200_profile_begin": (c_int, []),
+    "b200_profile_end": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64),
+                                 ctypes.POINTER(ctypes.c_double)]),
     "b200_set_matmul_precision": (c_int, [c_int]),
     "b200_get_matmul_precision": (c_int, []),
     "b200_stream_create": (c_int, [ctypes.POINTER(c_void_p)]),
@@ -85,8 +88,9 @@ SIGNATURES = {
     "b200_conv2d_backprop_filter": (c_int, [c_int, c_void_p, c_void_p, c_void_p,
                                             ctypes.POINTER(ConvGeometry), c_void_p, c_size_t,
                                             c_void_p]),
-    "b200_apply_gradient_descent": (c_int, [c_int, c_void_p, c_float, c_void_p, c_int64,
+    "b200_apply_gradient_descent": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                             c_void_p]),
+    "b200_mul": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "b200_add_n": (c_int, [c_int, ctypes.POINTER(c_void_p), c_int, c_void_p, c_int64, c_void_p]),
     "b200_scale": (c_int, [c_int, c_void_p, c_float, c_void_p, c_int64, c_void_p]),
     "b200_reduce_sum": (c_int, [c_int, c_void_p, c_float, c_void_p, c_int64, c_void_p]),

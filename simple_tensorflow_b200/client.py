@@ -1,0 +1,397 @@
+"""Graph / Operation / Session on top of the C API (libb200tf_framework.so).
+
+The role of the reference's tensorflow/python/framework/ops.py (Graph, Operation, Tensor) and
+tensorflow/python/client/session.py (BaseSession.run :660-1012) -- reduced to what driving the
+hot path needs, and talking to the same C entry points (TF_NewOperation / TF_FinishOperation /
+TF_SessionRun, tensorflow/c/c_api.h) the reference reaches through SWIG
+(python/client/tf_session_helper.cc:462,575).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+from . import _lib
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+FRAMEWORK_PATH = os.path.join(_HERE, "lib", "libb200tf_framework.so")
+
+# TF_DataType <-> numpy.  bfloat16 has no numpy dtype: it travels as uint16 bit patterns.
+TF_FLOAT, TF_INT32, TF_INT64, TF_BFLOAT16 = 1, 3, 9, 14
+_NP_OF = {TF_FLOAT: np.float32, TF_INT32: np.int32, TF_INT64: np.int64, TF_BFLOAT16: np.uint16}
+_TF_OF = {np.dtype(np.float32): TF_FLOAT, np.dtype(np.int32): TF_INT32,
+          np.dtype(np.int64): TF_INT64}
+float32, int32, int64, bfloat16 = TF_FLOAT, TF_INT32, TF_INT64, TF_BFLOAT16
+
+c_void_p, c_int, c_int64, c_size_t, c_char_p = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
+                                                 ctypes.c_size_t, ctypes.c_char_p)
+
+
+class TF_Output(ctypes.Structure):
+    _fields_ = [("oper", c_void_p), ("index", c_int)]
+
+
+class RunStats(ctypes.Structure):
+    _fields_ = [("nodes_executed", c_int64), ("kernels_launched", c_int64),
+                ("h2d_bytes", c_int64), ("d2h_bytes", c_int64)]
+
+
+_SIGS = {
+    "TF_Version": (c_char_p, []),
+    "TF_NewStatus": (c_void_p, []), "TF_DeleteStatus": (None, [c_void_p]),
+    "TF_GetCode": (c_int, [c_void_p]), "TF_Message": (c_char_p, [c_void_p]),
+    "TF_AllocateTensor": (c_void_p, [c_int, ctypes.POINTER(c_int64), c_int, c_size_t]),
+    "TF_DeleteTensor": (None, [c_void_p]), "TF_TensorType": (c_int, [c_void_p]),
+    "TF_NumDims": (c_int, [c_void_p]), "TF_Dim": (c_int64, [c_void_p, c_int]),
+    "TF_TensorByteSize": (c_size_t, [c_void_p]), "TF_TensorData": (c_void_p, [c_void_p]),
+    "TF_NewSessionOptions": (c_void_p, []), "TF_DeleteSessionOptions": (None, [c_void_p]),
+    "TF_SetTarget": (None, [c_void_p, c_char_p]),
+    "B200TF_SetGpuDevice": (None, [c_void_p, c_int]),
+    "B200TF_SetGpuMemoryLimit": (None, [c_void_p, c_size_t]),
+    "B200TF_SetCollective": (None, [c_void_p, c_void_p, c_int]),
+    "TF_NewGraph": (c_void_p, []), "TF_DeleteGraph": (None, [c_void_p]),
+    "TF_NewOperation": (c_void_p, [c_void_p, c_char_p, c_char_p]),
+    "TF_SetDevice": (None, [c_void_p, c_char_p]),
+    "TF_AddInput": (None, [c_void_p, TF_Output]),
+    "TF_AddInputList": (None, [c_void_p, ctypes.POINTER(TF_Output), c_int]),
+    "TF_AddControlInput": (None, [c_void_p, c_void_p]),
+    "TF_SetAttrString": (None, [c_void_p, c_char_p, c_char_p, c_size_t]),
+    "TF_SetAttrInt": (None, [c_void_p, c_char_p, c_int64]),
+    "TF_SetAttrIntList": (None, [c_void_p, c_char_p, ctypes.POINTER(c_int64), c_int]),
+    "TF_SetAttrFloat": (None, [c_void_p, c_char_p, ctypes.c_float]),
+    "TF_SetAttrBool": (None, [c_void_p, c_char_p, ctypes.c_ubyte]),
+    "TF_SetAttrType": (None, [c_void_p, c_char_p, c_int]),
+    "TF_SetAttrShape": (None, [c_void_p, c_char_p, ctypes.POINTER(c_int64), c_int]),
+    "TF_SetAttrTensor": (None, [c_void_p, c_char_p, c_void_p, c_void_p]),
+    "TF_FinishOperation": (c_void_p, [c_void_p, c_void_p]),
+    "TF_OperationName": (c_char_p, [c_void_p]), "TF_OperationOpType": (c_char_p, [c_void_p]),
+    "TF_OperationNumOutputs": (c_int, [c_void_p]),
+    "TF_OperationOutputType": (c_int, [TF_Output]),
+    "TF_OperationNumInputs": (c_int, [c_void_p]),
+    "TF_GraphOperationByName": (c_void_p, [c_void_p, c_char_p]),
+    "TF_NewSession": (c_void_p, [c_void_p, c_void_p, c_void_p]),
+    "TF_CloseSession": (None, [c_void_p, c_void_p]),
+    "TF_DeleteSession": (None, [c_void_p, c_void_p]),
+    "TF_SessionRun": (None, [c_void_p, c_void_p, ctypes.POINTER(TF_Output),
+                             ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(TF_Output),
+                             ctypes.POINTER(c_void_p), c_int, ctypes.POINTER(c_void_p), c_int,
+                             c_void_p, c_void_p]),
+    "B200TF_SessionLastRunStats": (None, [c_void_p, ctypes.POINTER(RunStats)]),
+    "B200TF_SessionStream": (c_void_p, [c_void_p]),
+    "B200TF_ListRegisteredOps": (c_void_p, []),
+    "B200TF_ListRegisteredKernels": (c_void_p, []),
+    "TF_LoadLibrary": (c_void_p, [c_char_p, c_void_p]),
+    "TF_DeleteLibraryHandle": (None, [c_void_p]),
+}
+
+_fw = None
+
+
+def framework():
+    """dlopen libb200tf_framework.so (after libb200tf.so) and attach prototypes."""
+    global _fw
+    if _fw is None:
+        _lib.load()  # the kernel library first: the framework links against it
+        if not os.path.exists(FRAMEWORK_PATH):
+            raise ImportError(FRAMEWORK_PATH + " is missing: run __graft_entry__.build()")
+        fw = ctypes.CDLL(FRAMEWORK_PATH, mode=ctypes.RTLD_GLOBAL)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(fw, name)
+            fn.restype = res
+            fn.argtypes = args
+        _fw = fw
+    return _fw
+
+
+class OpError(RuntimeError):
+    """A non-OK tensorflow::Status (python/framework/errors_impl.py OpError)."""
+
+    def __init__(self, code, message):
+        super().__init__(message)
+        self.error_code = code
+        self.message = message
+
+
+class _Status:
+    def __init__(self):
+        self.fw = framework()
+        self.ptr = self.fw.TF_NewStatus()
+
+    def check(self):
+        code = self.fw.TF_GetCode(self.ptr)
+        if code != 0:
+            raise OpError(code, self.fw.TF_Message(self.ptr).decode("utf-8", "replace"))
+
+    def __del__(self):
+        try:
+            self.fw.TF_DeleteStatus(self.ptr)
+        except Exception:
+            pass
+
+
+def _free_cstr_list(ptr):
+    s = ctypes.cast(ptr, c_char_p).value.decode()
+    ctypes.CDLL(None).free(c_void_p(ptr))
+    return [l for l in s.split("\n") if l]
+
+
+def registered_ops():
+    return _free_cstr_list(framework().B200TF_ListRegisteredOps())
+
+
+def registered_kernels():
+    return _free_cstr_list(framework().B200TF_ListRegisteredKernels())
+
+
+# ------------------------------------------------------------------ tensors
+class HostTensor:
+    """Owns a TF_Tensor (pinned host memory when a GPU is present) and views it as numpy."""
+
+    def __init__(self, ptr, owned=True):
+        self.fw = framework()
+        self.ptr = ptr
+        self.owned = owned
+
+    @classmethod
+    def allocate(cls, dtype, shape):
+        fw = framework()
+        dims = (c_int64 * max(len(shape), 1))(*shape)
+        n = int(np.prod(shape, dtype=np.int64)) if len(shape) else 1
+        ptr = fw.TF_AllocateTensor(dtype, dims, len(shape), n * np.dtype(_NP_OF[dtype]).itemsize)
+        if not ptr:
+            raise MemoryError("TF_AllocateTensor failed")
+        return cls(ptr)
+
+    @classmethod
+    def from_numpy(cls, array, dtype=None):
+        array = np.asarray(array)
+        if array.ndim:  # (ascontiguousarray would turn a 0-d scalar into shape [1])
+            array = np.ascontiguousarray(array)
+        if dtype is None:
+            dtype = _TF_OF[array.dtype]
+        t = cls.allocate(dtype, array.shape)
+        t.numpy()[...] = array.astype(_NP_OF[dtype], copy=False)
+        return t
+
+    @property
+    def dtype(self):
+        return self.fw.TF_TensorType(self.ptr)
+
+    @property
+    def shape(self):
+        return tuple(self.fw.TF_Dim(self.ptr, i) for i in range(self.fw.TF_NumDims(self.ptr)))
+
+    def numpy(self):
+        """A numpy view on the tensor's own storage (no copy; keep `self` alive)."""
+        nbytes = self.fw.TF_TensorByteSize(self.ptr)
+        np_dtype = np.dtype(_NP_OF[self.dtype])
+        if nbytes == 0:
+            return np.zeros(self.shape, np_dtype)
+        buf = (ctypes.c_char * nbytes).from_address(self.fw.TF_TensorData(self.ptr))
+        return np.frombuffer(buf, dtype=np_dtype).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            if self.owned and self.ptr:
+                self.fw.TF_DeleteTensor(self.ptr)
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------ graph
+class Output:
+    """One output of an Operation (python/framework/ops.py Tensor)."""
+
+    def __init__(self, op, index):
+        self.op = op
+        self.index = index
+
+    @property
+    def name(self):
+        return "%s:%d" % (self.op.name, self.index)
+
+    @property
+    def dtype(self):
+        return framework().TF_OperationOutputType(self._c())
+
+    @property
+    def graph(self):
+        return self.op.graph
+
+    def _c(self):
+        return TF_Output(self.op.ptr, self.index)
+
+    def __repr__(self):
+        return "<Output %s dtype=%d>" % (self.name, self.dtype)
+
+
+class Operation:
+    def __init__(self, graph, ptr, inputs, control_inputs, attrs):
+        self.graph = graph
+        self.ptr = ptr
+        self.inputs = list(inputs)
+        self.control_inputs = list(control_inputs)
+        self.attrs = dict(attrs)
+        fw = framework()
+        self.name = fw.TF_OperationName(ptr).decode()
+        self.type = fw.TF_OperationOpType(ptr).decode()
+        self.outputs = [Output(self, i) for i in range(fw.TF_OperationNumOutputs(ptr))]
+
+    def get_attr(self, name):
+        return self.attrs[name]
+
+    def __repr__(self):
+        return "<Operation %s type=%s>" % (self.name, self.type)
+
+
+class Graph:
+    def __init__(self):
+        self.fw = framework()
+        self.ptr = self.fw.TF_NewGraph()
+        self.operations = []
+        self._names = {}
+        self.variables = []       # (variable_output, initial_value_output)
+        self.shapes = {}          # static shapes recorded by the op constructors (Output.name -> tuple)
+
+    def unique_name(self, base):
+        n = self._names.get(base, 0)
+        self._names[base] = n + 1
+        return base if n == 0 else "%s_%d" % (base, n)
+
+    def create_op(self, op_type, inputs, attrs=None, name=None, control_inputs=(),
+                  input_lists=()):
+        """ops.py Graph.create_op: inputs are Outputs; attrs maps name -> python value using
+        the tagged forms ('type', dt), ('shape', dims), ('tensor', HostTensor), ('ints', [...])."""
+        fw = self.fw
+        name = self.unique_name(name or op_type)
+        desc = fw.TF_NewOperation(self.ptr, op_type.encode(), name.encode())
+        for inp in inputs:
+            if isinstance(inp, (list, tuple)):
+                arr = (TF_Output * len(inp))(*[i._c() for i in inp])
+                fw.TF_AddInputList(desc, arr, len(inp))
+            else:
+                fw.TF_AddInput(desc, inp._c())
+        for c in control_inputs:
+            fw.TF_AddControlInput(desc, c.ptr)
+        status = _Status()
+        for k, v in (attrs or {}).items():
+            kb = k.encode()
+            if isinstance(v, tuple) and v[0] == "type":
+                fw.TF_SetAttrType(desc, kb, v[1])
+            elif isinstance(v, tuple) and v[0] == "shape":
+                dims = (c_int64 * max(len(v[1]), 1))(*v[1])
+                fw.TF_SetAttrShape(desc, kb, dims, len(v[1]))
+            elif isinstance(v, tuple) and v[0] == "tensor":
+                fw.TF_SetAttrTensor(desc, kb, v[1].ptr, status.ptr)
+                status.check()
+            elif isinstance(v, tuple) and v[0] == "ints":
+                arr = (c_int64 * max(len(v[1]), 1))(*v[1])
+                fw.TF_SetAttrIntList(desc, kb, arr, len(v[1]))
+            elif isinstance(v, bool):
+                fw.TF_SetAttrBool(desc, kb, 1 if v else 0)
+            elif isinstance(v, int):
+                fw.TF_SetAttrInt(desc, kb, v)
+            elif isinstance(v, float):
+                fw.TF_SetAttrFloat(desc, kb, v)
+            elif isinstance(v, str):
+                b = v.encode()
+                fw.TF_SetAttrString(desc, kb, b, len(b))
+            else:
+                raise TypeError("unsupported attr %s=%r" % (k, v))
+        ptr = fw.TF_FinishOperation(desc, status.ptr)
+        status.check()
+        flat_inputs = []
+        for inp in inputs:
+            flat_inputs.extend(inp if isinstance(inp, (list, tuple)) else [inp])
+        op = Operation(self, ptr, flat_inputs, control_inputs, attrs or {})
+        self.operations.append(op)
+        return op
+
+    def __del__(self):
+        try:
+            self.fw.TF_DeleteGraph(self.ptr)
+        except Exception:
+            pass
+
+
+# ------------------------------------------------------------------ session
+class Session:
+    """session.py BaseSession: run(fetches, feed_dict).  Feeds are host arrays, fetches come back
+    as numpy arrays; one device sync per run."""
+
+    def __init__(self, graph, gpu=0, memory_limit_bytes=0, collective_comm=None, num_replicas=1):
+        self.fw = framework()
+        self.graph = graph
+        opts = self.fw.TF_NewSessionOptions()
+        self.fw.B200TF_SetGpuDevice(opts, gpu)
+        if memory_limit_bytes:
+            self.fw.B200TF_SetGpuMemoryLimit(opts, memory_limit_bytes)
+        if collective_comm:
+            self.fw.B200TF_SetCollective(opts, collective_comm, num_replicas)
+        status = _Status()
+        self.ptr = self.fw.TF_NewSession(graph.ptr, opts, status.ptr)
+        self.fw.TF_DeleteSessionOptions(opts)
+        status.check()
+        self._status = _Status()
+
+    def run(self, fetches, feed_dict=None, as_host_tensors=False):
+        single = not isinstance(fetches, (list, tuple))
+        fetch_list = [fetches] if single else list(fetches)
+        outs = [f for f in fetch_list if isinstance(f, Output)]
+        targets = [f for f in fetch_list if isinstance(f, Operation)]
+        feed_dict = feed_dict or {}
+        keep = []
+        feed_outputs, feed_ptrs = [], []
+        for k, v in feed_dict.items():
+            if not isinstance(v, HostTensor):
+                v = HostTensor.from_numpy(np.asarray(v), k.dtype)
+            keep.append(v)
+            feed_outputs.append(k._c())
+            feed_ptrs.append(v.ptr)
+        n_in, n_out, n_t = len(feed_outputs), len(outs), len(targets)
+        c_in = (TF_Output * max(n_in, 1))(*feed_outputs)
+        c_in_vals = (c_void_p * max(n_in, 1))(*feed_ptrs)
+        c_out = (TF_Output * max(n_out, 1))(*[o._c() for o in outs])
+        c_out_vals = (c_void_p * max(n_out, 1))()
+        c_targets = (c_void_p * max(n_t, 1))(*[t.ptr for t in targets])
+        self.fw.TF_SessionRun(self.ptr, None, c_in, c_in_vals, n_in, c_out, c_out_vals, n_out,
+                              c_targets, n_t, None, self._status.ptr)
+        self._status.check()
+        results = []
+        it = iter(range(n_out))
+        for f in fetch_list:
+            if isinstance(f, Output):
+                t = HostTensor(c_out_vals[next(it)])
+                results.append(t if as_host_tensors else np.array(t.numpy()))
+            else:
+                results.append(None)
+        return results[0] if single else results
+
+    def stream(self):
+        """The CUstream handle (int) all kernels of this session run on."""
+        return self.fw.B200TF_SessionStream(self.ptr)
+
+    def last_run_stats(self):
+        s = RunStats()
+        self.fw.B200TF_SessionLastRunStats(self.ptr, ctypes.byref(s))
+        return {"nodes_executed": s.nodes_executed, "kernels_launched": s.kernels_launched,
+                "h2d_bytes": s.h2d_bytes, "d2h_bytes": s.d2h_bytes}
+
+    def close(self):
+        if self.ptr:
+            st = _Status()
+            self.fw.TF_CloseSession(self.ptr, st.ptr)
+            self.fw.TF_DeleteSession(self.ptr, st.ptr)
+            self.ptr = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -48,6 +48,11 @@ int gemm_tcgen05(const GemmArgs& g, cudaStream_t stream);
 int gemm_simt(const GemmArgs& g, cudaStream_t stream);
 // Precision-aware front door used by matmul / batch_matmul / conv.
 int gemm_dispatch(const GemmArgs& g, cudaStream_t stream);
+// Optional per-launch timing of the tensor-core GEMM (b200_profile_begin/end): brackets the
+// launch with CUDA events on the launching stream.
+bool profile_enabled();
+void profile_gemm_launch_begin(cudaStream_t stream);
+void profile_gemm_launch_end(cudaStream_t stream, double flops);
 // Scratch that lets gemm_dispatch use split-K for this shape (0 when it would not split).
 size_t gemm_workspace_bytes(int dtype, long long M, long long N, long long K, long long batch);
 

@@ -26,6 +26,11 @@ struct Vec16 {
 __device__ __forceinline__ uint4 ld16(const void* p) {
   return __ldg(reinterpret_cast<const uint4*>(p));
 }
+// Plain (coherent) 16-byte load for operands that may alias the output (in-place Relu, BiasAdd,
+// ApplyGradientDescent): ld.global.nc would be illegal on memory the kernel also writes.
+__device__ __forceinline__ uint4 ld16_rw(const void* p) {
+  return *reinterpret_cast<const uint4*>(p);
+}
 __device__ __forceinline__ void st16(void* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
 
 // ---- per-16-byte math on fp32 x4 / bf16 x8, all arithmetic in fp32
@@ -81,8 +86,7 @@ static inline unsigned blocks_for(long long items, int per_block) {
 // out[i] = f(in0[i], in1[i], ...) ; NIN inputs, one output, same dtype.
 template <typename T, int NIN, typename F>
 __global__ void __launch_bounds__(kThreads)
-map_vec_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
-               long long nvec, F f) {
+map_vec_kernel(const T* a, const T* b, T* out, long long nvec, F f) {
   constexpr int N = Lanes<T>::kN;
   const long long base = ((long long)blockIdx.x * kThreads * kUnroll) + threadIdx.x;
   uint4 va[kUnroll], vb[kUnroll];
@@ -90,8 +94,8 @@ map_vec_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__
   for (int u = 0; u < kUnroll; ++u) {
     const long long i = base + (long long)u * kThreads;
     if (i < nvec) {
-      va[u] = ld16(a + i * N);
-      if (NIN > 1) vb[u] = ld16(b + i * N);
+      va[u] = ld16_rw(a + i * N);
+      if (NIN > 1) vb[u] = ld16_rw(b + i * N);
     }
   }
 #pragma unroll
@@ -109,8 +113,7 @@ map_vec_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__
 }
 template <typename T, int NIN, typename F>
 __global__ void __launch_bounds__(kThreads)
-map_scalar_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ out,
-                  long long start, long long n, F f) {
+map_scalar_kernel(const T* a, const T* b, T* out, long long start, long long n, F f) {
   const long long i = start + (long long)blockIdx.x * kThreads + threadIdx.x;
   if (i < n) {
     const float x = Lanes<T>::load1(a + i);
@@ -155,17 +158,28 @@ struct ScaleF {
   float s;
   __device__ float operator()(float x, float) const { return x * s; }
 };
+template <typename T>
 struct SgdF {
-  float alpha;
+  const T* alpha;  // device scalar, like the lr() of the reference's GPU functor
   // var -= alpha * delta: training_ops.cc:410-412
-  __device__ float operator()(float var, float delta) const { return var - alpha * delta; }
+  __device__ float operator()(float var, float delta) const {
+    return var - Lanes<T>::load1(alpha) * delta;
+  }
+};
+struct MulF {
+  __device__ float operator()(float x, float y) const { return x * y; }
+};
+template <typename T>
+struct MulScalarF {
+  const T* y;  // device scalar broadcast over x
+  __device__ float operator()(float x, float) const { return x * Lanes<T>::load1(y); }
 };
 
 // ------------------------------------------------------------------ BiasAdd
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-bias_add_vec_kernel(const T* __restrict__ in, const T* __restrict__ bias, T* __restrict__ out,
-                    long long nvec, int cvec /* channels / N */) {
+bias_add_vec_kernel(const T* in, const T* __restrict__ bias, T* out, long long nvec,
+                    int cvec /* channels / N */) {
   constexpr int N = Lanes<T>::kN;
   const long long base = ((long long)blockIdx.x * kThreads * kUnroll) + threadIdx.x;
   uint4 vi[kUnroll], vb[kUnroll];
@@ -173,7 +187,7 @@ bias_add_vec_kernel(const T* __restrict__ in, const T* __restrict__ bias, T* __r
   for (int u = 0; u < kUnroll; ++u) {
     const long long i = base + (long long)u * kThreads;
     if (i < nvec) {
-      vi[u] = ld16(in + i * N);
+      vi[u] = ld16_rw(in + i * N);
       vb[u] = ld16(bias + (i % cvec) * N);  // bias row stays in L1/L2
     }
   }
@@ -192,8 +206,8 @@ bias_add_vec_kernel(const T* __restrict__ in, const T* __restrict__ bias, T* __r
 }
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-bias_add_scalar_kernel(const T* __restrict__ in, const T* __restrict__ bias, T* __restrict__ out,
-                       long long n, long long channels) {
+bias_add_scalar_kernel(const T* in, const T* __restrict__ bias, T* out, long long n,
+                       long long channels) {
   const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
   if (i < n)
     Lanes<T>::store1(out + i, Lanes<T>::load1(in + i) + Lanes<T>::load1(bias + i % channels));
@@ -366,18 +380,42 @@ int b200_scale(int dtype, const void* in, float scale, void* out, int64_t n, voi
   return bad_dtype("b200_scale", dtype);
 }
 
-int b200_apply_gradient_descent(int dtype, void* var, float alpha, const void* delta, int64_t n,
-                                void* stream) {
+int b200_mul(int dtype, const void* x, const void* y, void* out, int64_t n, int y_is_scalar,
+             void* stream) {
+  if (n < 0) return bad_n("b200_mul", n);
+  if (n == 0) return B200_OK;
+  int rc = require_device("b200_mul");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  if (dtype == B200_DT_FLOAT) {
+    if (y_is_scalar)
+      return launch_map<float, 1>("b200_mul", x, nullptr, out, n,
+                                  MulScalarF<float>{static_cast<const float*>(y)}, s);
+    return launch_map<float, 2>("b200_mul", x, y, out, n, MulF{}, s);
+  }
+  if (dtype == B200_DT_BFLOAT16) {
+    if (y_is_scalar)
+      return launch_map<__nv_bfloat16, 1>(
+          "b200_mul", x, nullptr, out, n,
+          MulScalarF<__nv_bfloat16>{static_cast<const __nv_bfloat16*>(y)}, s);
+    return launch_map<__nv_bfloat16, 2>("b200_mul", x, y, out, n, MulF{}, s);
+  }
+  return bad_dtype("b200_mul", dtype);
+}
+
+int b200_apply_gradient_descent(int dtype, void* var, const void* alpha, const void* delta,
+                                int64_t n, void* stream) {
   if (n < 0) return bad_n("b200_apply_gradient_descent", n);
   if (n == 0) return B200_OK;
   int rc = require_device("b200_apply_gradient_descent");
   if (rc) return rc;
   if (dtype == B200_DT_FLOAT)
-    return launch_map<float, 2>("b200_apply_gradient_descent", var, delta, var, n, SgdF{alpha},
-                                as_stream(stream));
+    return launch_map<float, 2>("b200_apply_gradient_descent", var, delta, var, n,
+                                SgdF<float>{static_cast<const float*>(alpha)}, as_stream(stream));
   if (dtype == B200_DT_BFLOAT16)
-    return launch_map<__nv_bfloat16, 2>("b200_apply_gradient_descent", var, delta, var, n,
-                                        SgdF{alpha}, as_stream(stream));
+    return launch_map<__nv_bfloat16, 2>(
+        "b200_apply_gradient_descent", var, delta, var, n,
+        SgdF<__nv_bfloat16>{static_cast<const __nv_bfloat16*>(alpha)}, as_stream(stream));
   return bad_dtype("b200_apply_gradient_descent", dtype);
 }
 

@@ -438,7 +438,10 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   s.partial = static_cast<float*>(g.workspace);
   const long long work = tiles * splits;
   const int grid = (int)(work < sm_count() ? work : sm_count());
+  const bool prof = profile_enabled();
+  if (prof) profile_gemm_launch_begin(stream);
   kern<<<grid, kGemmThreads, smem, stream>>>(ma, mb, static_cast<TOut*>(g.c), s);
+  if (prof) profile_gemm_launch_end(stream, 2.0 * (double)g.M * (double)g.N * (double)g.K * g.batch);
   note_launch();
   if (splits > 1) {
     const long long groups = g.batch * g.M * ((g.N + 3) / 4);

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <dlfcn.h>
 #include <mutex>
+#include <vector>
 
 #include "b200_internal.h"
 
@@ -83,6 +84,43 @@ const DriverApi& driver() {
     }
   });
   return api;
+}
+
+// ------------------------------------------------------------------ GEMM launch profiling
+struct ProfileState {
+  std::mutex mu;
+  bool enabled = false;
+  std::vector<cudaEvent_t> starts, stops;
+  std::vector<double> flops;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t pending_start = nullptr;
+};
+static ProfileState g_prof;
+static std::atomic<bool> g_prof_on{false};
+bool profile_enabled() { return g_prof_on.load(std::memory_order_relaxed); }
+static cudaEvent_t prof_event() {
+  if (!g_prof.pool.empty()) {
+    cudaEvent_t e = g_prof.pool.back();
+    g_prof.pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+void profile_gemm_launch_begin(cudaStream_t stream) {
+  std::lock_guard<std::mutex> l(g_prof.mu);
+  g_prof.pending_start = prof_event();
+  cudaEventRecord(g_prof.pending_start, stream);
+}
+void profile_gemm_launch_end(cudaStream_t stream, double flops) {
+  std::lock_guard<std::mutex> l(g_prof.mu);
+  cudaEvent_t e = prof_event();
+  cudaEventRecord(e, stream);
+  g_prof.starts.push_back(g_prof.pending_start);
+  g_prof.stops.push_back(e);
+  g_prof.flops.push_back(flops);
+  g_prof.pending_start = nullptr;
 }
 
 // ------------------------------------------------------------------ NCCL (dlopen'ed)
@@ -172,6 +210,38 @@ int b200_set_matmul_precision(int mode) {
   return B200_OK;
 }
 int b200_get_matmul_precision(void) { return g_matmul_precision.load(); }
+
+int b200_profile_begin(void) {
+  std::lock_guard<std::mutex> l(g_prof.mu);
+  g_prof.starts.clear();
+  g_prof.stops.clear();
+  g_prof.flops.clear();
+  g_prof.enabled = true;
+  g_prof_on.store(true);
+  return B200_OK;
+}
+int b200_profile_end(double* gemm_ms_total, uint64_t* gemm_launches, double* gemm_flops_total) {
+  g_prof_on.store(false);
+  std::lock_guard<std::mutex> l(g_prof.mu);
+  g_prof.enabled = false;
+  double ms = 0.0, fl = 0.0;
+  for (size_t i = 0; i < g_prof.starts.size(); ++i) {
+    cudaEventSynchronize(g_prof.stops[i]);
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, g_prof.starts[i], g_prof.stops[i]) == cudaSuccess) ms += t;
+    fl += g_prof.flops[i];
+    g_prof.pool.push_back(g_prof.starts[i]);
+    g_prof.pool.push_back(g_prof.stops[i]);
+  }
+  if (gemm_ms_total) *gemm_ms_total = ms;
+  if (gemm_launches) *gemm_launches = g_prof.starts.size();
+  if (gemm_flops_total) *gemm_flops_total = fl;
+  g_prof.starts.clear();
+  g_prof.stops.clear();
+  g_prof.flops.clear();
+  cudaGetLastError();
+  return B200_OK;
+}
 
 int b200_stream_create(void** stream) {
   cudaStream_t s;

@@ -1,0 +1,428 @@
+#include "tensorflow/core/common_runtime/direct_session.h"
+
+#include <algorithm>
+#include <functional>
+#include <set>
+
+namespace tensorflow {
+
+Status NewSession(const SessionOptions& options, Session** out_session) {
+  if (!options.target.empty())
+    return errors::Unimplemented("Only the in-process DirectSession (target \"\") is available; "
+                                 "the gRPC runtime is outside the B200 hot path");
+  std::unique_ptr<DirectSession> s(new DirectSession(options));
+  TF_RETURN_IF_ERROR(s->Init());
+  *out_session = s.release();
+  return Status::OK();
+}
+
+DirectSession::DirectSession(const SessionOptions& options) : options_(options) {}
+
+DirectSession::~DirectSession() {
+  if (device_) device_->Sync();
+  executors_.clear();
+  nodes_.clear();  // kernels (and the variables they own) go before the device's allocator
+}
+
+Status DirectSession::Init() {
+  TF_RETURN_IF_ERROR(
+      BaseGPUDevice::Create(options_.gpu_device_id, options_.gpu_memory_limit_bytes, &device_));
+  device_->set_collective_comm(options_.collective_comm, options_.num_replicas);
+  return Status::OK();
+}
+
+Status DirectSession::ParseTensorName(const std::string& name, std::string* node, int* slot) {
+  const size_t colon = name.rfind(':');
+  if (colon == std::string::npos) {
+    *node = name;
+    *slot = 0;
+    return Status::OK();
+  }
+  *node = name.substr(0, colon);
+  const std::string idx = name.substr(colon + 1);
+  if (idx.empty() || idx.find_first_not_of("0123456789") != std::string::npos)
+    return errors::InvalidArgument("Malformed tensor name '", name, "'");
+  *slot = atoi(idx.c_str());
+  return Status::OK();
+}
+
+Status DirectSession::AddNodes(const GraphDef& graph) {
+  const size_t first_new = nodes_.size();
+  for (const NodeDef& nd : graph.node) {
+    if (node_index_.count(nd.name))
+      return errors::InvalidArgument("Node '", nd.name, "' is not unique");
+    const OpDef* op_def = OpRegistry::Global()->LookUp(nd.op);
+    if (op_def == nullptr)
+      return errors::NotFound("Op type not registered '", nd.op, "' (node '", nd.name, "')");
+    std::unique_ptr<NodeItem> item(new NodeItem);
+    item->def = nd;
+    TF_RETURN_IF_ERROR(ValidateNodeDef(&item->def, *op_def));
+    if (!nd.device.empty() && nd.device.find("CPU") != std::string::npos &&
+        nd.device.find("cpu") != std::string::npos)
+      return errors::InvalidArgument("Node '", nd.name, "' requests device '", nd.device,
+                                     "' but this runtime places every node on the GPU");
+    node_index_[nd.name] = static_cast<int>(nodes_.size());
+    nodes_.push_back(std::move(item));
+  }
+  // resolve inputs after all nodes of this batch are known (GraphDefs need not be sorted)
+  for (size_t i = first_new; i < nodes_.size(); ++i) {
+    NodeItem* item = nodes_[i].get();
+    for (const std::string& in : item->def.input) {
+      if (!in.empty() && in[0] == '^') {
+        auto it = node_index_.find(in.substr(1));
+        if (it == node_index_.end())
+          return errors::InvalidArgument("Node '", item->def.name, "': Unknown control input '", in, "'");
+        item->control_inputs.push_back(it->second);
+        continue;
+      }
+      std::string src;
+      int slot;
+      TF_RETURN_IF_ERROR(ParseTensorName(in, &src, &slot));
+      auto it = node_index_.find(src);
+      if (it == node_index_.end())
+        return errors::InvalidArgument("Node '", item->def.name, "': Unknown input node '", in, "'");
+      item->inputs.push_back(TensorId{it->second, slot});
+    }
+    const OpDef* op_def = OpRegistry::Global()->LookUp(item->def.op);
+    DataTypeVector in_types, out_types;
+    TF_RETURN_IF_ERROR(InOutTypesForNode(item->def, *op_def, &in_types, &out_types));
+    if (in_types.size() != item->inputs.size())
+      return errors::InvalidArgument("Node '", item->def.name, "' of type ", item->def.op,
+                                     " expects ", in_types.size(), " inputs but has ",
+                                     item->inputs.size());
+  }
+  return Status::OK();
+}
+
+Status DirectSession::Create(const GraphDef& graph) {
+  std::lock_guard<std::mutex> l(mu_);
+  if (!nodes_.empty())
+    return errors::AlreadyExists("A Graph has already been created for this session.");
+  return AddNodes(graph);
+}
+
+Status DirectSession::Extend(const GraphDef& graph) {
+  std::lock_guard<std::mutex> l(mu_);
+  if (closed_) return errors::Cancelled("Session has been closed.");
+  return AddNodes(graph);
+}
+
+Status DirectSession::Close() {
+  std::lock_guard<std::mutex> l(mu_);
+  closed_ = true;
+  if (device_) return device_->Sync();
+  return Status::OK();
+}
+
+Status DirectSession::EnsureKernel(NodeItem* item) {
+  if (item->kernel) return Status::OK();
+  return CreateOpKernel(DeviceType(DEVICE_GPU), device_.get(),
+                        device_->GetAllocator(AllocatorAttributes()), item->def, &item->kernel);
+}
+
+Status DirectSession::GetOrCreateExecutors(const std::vector<std::string>& feeds,
+                                           const std::vector<std::string>& fetches,
+                                           const std::vector<std::string>& targets,
+                                           ExecutorsAndKeys** out) {
+  // Same key construction idea as direct_session.cc:918-936 (sorted names joined).
+  std::vector<std::string> fs(feeds), ts(targets);
+  std::sort(ts.begin(), ts.end());
+  std::string key;
+  for (const auto& f : fs) key += f + ",";
+  key += "->";
+  for (const auto& f : fetches) key += f + ",";
+  key += "/";
+  for (const auto& t : ts) key += t + ",";
+  auto it = executors_.find(key);
+  if (it != executors_.end()) {
+    *out = it->second.get();
+    return Status::OK();
+  }
+
+  std::unique_ptr<ExecutorsAndKeys> ek(new ExecutorsAndKeys);
+  // feeds: (node, slot) -> feed index
+  std::map<std::pair<int, int>, int> feed_of;
+  for (size_t i = 0; i < feeds.size(); ++i) {
+    std::string node;
+    int slot;
+    TF_RETURN_IF_ERROR(ParseTensorName(feeds[i], &node, &slot));
+    auto n = node_index_.find(node);
+    if (n == node_index_.end())
+      return errors::NotFound("FeedInputs: unable to find feed output ", feeds[i]);
+    feed_of[{n->second, slot}] = static_cast<int>(i);
+  }
+  // prune: reverse reachability from fetches + targets, not expanding through fed tensors
+  std::vector<int> state(nodes_.size(), 0);  // 0 unvisited, 1 in progress, 2 done
+  std::vector<int> order;
+  std::function<Status(int)> visit = [&](int n) -> Status {
+    if (state[n] == 2) return Status::OK();
+    if (state[n] == 1)
+      return errors::InvalidArgument("Graph has a cycle through node '", nodes_[n]->def.name,
+                                     "' (control-flow loops are outside the hot path)");
+    state[n] = 1;
+    for (const TensorId& in : nodes_[n]->inputs)
+      if (!feed_of.count({in.node, in.slot})) TF_RETURN_IF_ERROR(visit(in.node));
+    for (int c : nodes_[n]->control_inputs) TF_RETURN_IF_ERROR(visit(c));
+    state[n] = 2;
+    order.push_back(n);
+    return Status::OK();
+  };
+  std::vector<TensorId> fetch_ids;
+  for (const std::string& f : fetches) {
+    std::string node;
+    int slot;
+    TF_RETURN_IF_ERROR(ParseTensorName(f, &node, &slot));
+    auto n = node_index_.find(node);
+    if (n == node_index_.end())
+      return errors::NotFound("FetchOutputs node ", f, ": not found");
+    fetch_ids.push_back(TensorId{n->second, slot});
+    if (!feed_of.count({n->second, slot})) TF_RETURN_IF_ERROR(visit(n->second));
+  }
+  for (const std::string& t : targets) {
+    auto n = node_index_.find(t);
+    if (n == node_index_.end()) return errors::NotFound("Target node ", t, ": not found");
+    TF_RETURN_IF_ERROR(visit(n->second));
+  }
+  // entry table + plan
+  std::vector<int> first_entry(nodes_.size(), -1);
+  for (int n : order) {
+    TF_RETURN_IF_ERROR(EnsureKernel(nodes_[n].get()));
+    first_entry[n] = ek->num_entries;
+    ek->num_entries += std::max(1, nodes_[n]->kernel->num_outputs());
+  }
+  ek->entry_consumers.assign(ek->num_entries, 0);
+  ek->entry_is_fetch.assign(ek->num_entries, false);
+  ek->feed_needs_device.assign(feeds.size(), false);
+  ek->feed_needs_host.assign(feeds.size(), false);
+  for (int n : order) {
+    PlanNode pn;
+    pn.node = n;
+    pn.first_entry = first_entry[n];
+    const OpKernel* k = nodes_[n]->kernel.get();
+    for (size_t i = 0; i < nodes_[n]->inputs.size(); ++i) {
+      const TensorId& in = nodes_[n]->inputs[i];
+      InputSource src;
+      auto f = feed_of.find({in.node, in.slot});
+      if (f != feed_of.end()) {
+        src.feed = f->second;
+        if (k->input_memory_types()[i] == HOST_MEMORY)
+          ek->feed_needs_host[src.feed] = true;
+        else
+          ek->feed_needs_device[src.feed] = true;
+      } else {
+        src.id = in;
+        const int producer_outputs = nodes_[in.node]->kernel->num_outputs();
+        if (in.slot >= producer_outputs)
+          return errors::InvalidArgument("Node '", nodes_[n]->def.name, "' reads output ", in.slot,
+                                         " of '", nodes_[in.node]->def.name, "' which has only ",
+                                         producer_outputs, " outputs");
+        // dtype agreement (graph_constructor's edge type check)
+        const DataType produced = nodes_[in.node]->kernel->output_type(in.slot);
+        if (produced != k->input_type(i))
+          return errors::InvalidArgument("Input ", i, " of node ", nodes_[n]->def.name,
+                                         " was passed ", DataTypeString(produced), " from ",
+                                         nodes_[in.node]->def.name, ":", in.slot,
+                                         " incompatible with expected ",
+                                         DataTypeString(k->input_type(i)), ".");
+        ek->entry_consumers[first_entry[in.node] + in.slot]++;
+      }
+      pn.inputs.push_back(src);
+    }
+    ek->order.push_back(std::move(pn));
+  }
+  for (const TensorId& id : fetch_ids) {
+    InputSource src;
+    auto f = feed_of.find({id.node, id.slot});
+    if (f != feed_of.end()) {
+      src.feed = f->second;
+      ek->feed_needs_host[src.feed] = true;
+    } else {
+      if (id.slot >= nodes_[id.node]->kernel->num_outputs())
+        return errors::InvalidArgument("Fetch ", nodes_[id.node]->def.name, ":", id.slot,
+                                       " is out of range");
+      src.id = id;
+      ek->entry_is_fetch[first_entry[id.node] + id.slot] = true;
+    }
+    ek->fetches.push_back(src);
+  }
+  ek->node_first_entry = first_entry;
+  *out = ek.get();
+  executors_[key] = std::move(ek);
+  return Status::OK();
+}
+
+Status DirectSession::Run(const std::vector<std::pair<std::string, Tensor>>& inputs,
+                          const std::vector<std::string>& output_tensor_names,
+                          const std::vector<std::string>& target_node_names,
+                          std::vector<Tensor>* outputs) {
+  std::lock_guard<std::mutex> l(mu_);
+  if (closed_) return errors::Cancelled("Session has been closed.");
+  if (nodes_.empty())
+    return errors::FailedPrecondition("Session was not created with a graph before Run()!");
+  std::vector<std::string> feed_names;
+  for (const auto& kv : inputs) feed_names.push_back(kv.first);
+  ExecutorsAndKeys* ek = nullptr;
+  TF_RETURN_IF_ERROR(
+      GetOrCreateExecutors(feed_names, output_tensor_names, target_node_names, &ek));
+  ++step_id_;
+  const unsigned long long launches_before = b200_launch_count();
+  stats_ = RunStats();
+  Status s = RunPlan(ek, inputs, outputs);
+  if (!s.ok()) device_->Sync();  // drain whatever was enqueued before reporting
+  stats_.kernels_launched = static_cast<long long>(b200_launch_count() - launches_before);
+  return s;
+}
+
+Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
+                              const std::vector<std::pair<std::string, Tensor>>& inputs,
+                              std::vector<Tensor>* outputs) {
+  // ---- SendInputs: stage feeds where their consumers need them
+  std::vector<Tensor> feed_dev(inputs.size()), feed_host(inputs.size());
+  for (size_t i = 0; i < inputs.size(); ++i) {
+    if (ek->feed_needs_host[i]) feed_host[i] = inputs[i].second;
+    if (ek->feed_needs_device[i]) {
+      TF_RETURN_IF_ERROR(device_->MakeTensorFromHost(inputs[i].second, &feed_dev[i]));
+      stats_.h2d_bytes += static_cast<long long>(inputs[i].second.TotalBytes());
+    }
+  }
+  std::vector<Entry> entries(ek->num_entries);
+  std::vector<int> pending(ek->entry_consumers);
+  std::vector<Tensor> deref_storage;     // Tensor handles for ref->value conversions
+  std::vector<TensorValue> input_values;
+  std::vector<Tensor> converted;         // memory-space conversions for this node
+  DeviceContext* dc = device_->device_context();
+
+  for (const PlanNode& pn : ek->order) {
+    NodeItem* item = nodes_[pn.node].get();
+    OpKernel* kernel = item->kernel.get();
+    input_values.clear();
+    deref_storage.clear();
+    converted.clear();
+    deref_storage.reserve(pn.inputs.size());
+    converted.reserve(pn.inputs.size());
+    for (size_t i = 0; i < pn.inputs.size(); ++i) {
+      const InputSource& src = pn.inputs[i];
+      const bool want_host = kernel->input_memory_types()[i] == HOST_MEMORY;
+      if (src.feed >= 0) {
+        if (kernel->input_is_ref(i))
+          return errors::InvalidArgument("Node '", item->def.name, "': input ", i,
+                                         " is a reference and cannot be fed");
+        input_values.push_back(TensorValue(want_host ? &feed_host[src.feed] : &feed_dev[src.feed]));
+        continue;
+      }
+      Entry& en = entries[entry_index_of(ek, src.id)];
+      if (!en.has_value)
+        return errors::Internal("Node '", item->def.name, "': input ", i, " from '",
+                                nodes_[src.id.node]->def.name, ":", src.id.slot,
+                                "' was never produced");
+      if (kernel->input_is_ref(i)) {
+        if (en.ref == nullptr)
+          return errors::InvalidArgument("Node '", item->def.name, "': input ", i,
+                                         " expects a reference (variable) but got a value");
+        input_values.push_back(TensorValue(en.ref_mu, en.ref));
+        continue;
+      }
+      Tensor* t = &en.val;
+      if (en.ref != nullptr) {  // dereference a variable for a by-value consumer
+        std::lock_guard<std::mutex> rl(*en.ref_mu);
+        deref_storage.push_back(*en.ref);
+        t = &deref_storage.back();
+        if (!t->IsInitialized() || t->NumElements() == 0)
+          return errors::FailedPrecondition("Attempting to use uninitialized value ",
+                                            nodes_[src.id.node]->def.name);
+      }
+      if (want_host != en.on_host && t->NumElements() > 0) {
+        Tensor c;
+        if (want_host) {  // device -> host needs the data now: sync (rare: shape-like operands)
+          TF_RETURN_IF_ERROR(device_->CopyTensorToHost(*t, &c));
+          TF_RETURN_IF_ERROR(device_->Sync());
+          stats_.d2h_bytes += static_cast<long long>(t->TotalBytes());
+        } else {
+          TF_RETURN_IF_ERROR(device_->MakeTensorFromHost(*t, &c));
+          stats_.h2d_bytes += static_cast<long long>(t->TotalBytes());
+        }
+        converted.push_back(std::move(c));
+        t = &converted.back();
+      }
+      input_values.push_back(TensorValue(t));
+    }
+
+    OpKernelContext::Params params;
+    params.step_id = step_id_;
+    params.op_kernel = kernel;
+    params.device = device_.get();
+    params.inputs = &input_values;
+    params.op_device_context = dc;
+    std::vector<AllocatorAttributes> out_attrs(kernel->num_outputs());
+    for (int o = 0; o < kernel->num_outputs(); ++o)
+      out_attrs[o].set_on_host(kernel->output_memory_types()[o] == HOST_MEMORY);
+    params.output_attr_array = out_attrs.data();
+    {
+      OpKernelContext ctx(&params);
+      device_->Compute(kernel, &ctx);
+      ++stats_.nodes_executed;
+      if (!ctx.status().ok()) {
+        const Status& s = ctx.status();
+        return Status(s.code(), strings::StrCat(s.error_message(), "\n\t [[Node: ",
+                                                SummarizeNodeDef(item->def), "]]"));
+      }
+      for (int o = 0; o < kernel->num_outputs(); ++o) {
+        TensorValue v = ctx.release_output(o);
+        Entry& out = entries[pn.first_entry + o];
+        if (v.tensor == nullptr) {
+          if (ek->entry_consumers[pn.first_entry + o] > 0 || ek->entry_is_fetch[pn.first_entry + o])
+            return errors::Internal("Missing ", o, "-th output from ", SummarizeNodeDef(item->def));
+          continue;
+        }
+        out.has_value = true;
+        out.on_host = kernel->output_memory_types()[o] == HOST_MEMORY;
+        if (v.is_ref()) {
+          out.ref = v.tensor;
+          out.ref_mu = v.mutex_if_ref;
+        } else {
+          out.val = std::move(*v.tensor);
+          delete v.tensor;
+        }
+      }
+    }
+    // release inputs whose last consumer just ran (buffers go back to the arena; reuse is
+    // stream-ordered, see gpu_bfc_allocator.h)
+    for (const InputSource& src : pn.inputs) {
+      if (src.feed >= 0) continue;
+      const int eidx = entry_index_of(ek, src.id);
+      if (--pending[eidx] == 0 && !ek->entry_is_fetch[eidx]) entries[eidx].val = Tensor();
+    }
+  }
+
+  // ---- RecvOutputs: device -> pinned host, then the single sync of the step
+  outputs->clear();
+  outputs->resize(ek->fetches.size());
+  for (size_t i = 0; i < ek->fetches.size(); ++i) {
+    const InputSource& src = ek->fetches[i];
+    if (src.feed >= 0) {
+      (*outputs)[i] = inputs[src.feed].second;
+      continue;
+    }
+    Entry& en = entries[entry_index_of(ek, src.id)];
+    if (!en.has_value)
+      return errors::Internal("Fetch ", nodes_[src.id.node]->def.name, ":", src.id.slot,
+                              " was never produced");
+    Tensor t = en.val;
+    if (en.ref != nullptr) {
+      std::lock_guard<std::mutex> rl(*en.ref_mu);
+      t = *en.ref;
+      if (!t.IsInitialized() || t.NumElements() == 0)
+        return errors::FailedPrecondition("Attempting to use uninitialized value ",
+                                          nodes_[src.id.node]->def.name);
+    }
+    if (en.on_host) {
+      (*outputs)[i] = t;
+    } else {
+      TF_RETURN_IF_ERROR(device_->CopyTensorToHost(t, &(*outputs)[i]));
+      stats_.d2h_bytes += static_cast<long long>(t.TotalBytes());
+    }
+  }
+  return device_->Sync();  // sync_on_finish
+}
+
+}  // namespace tensorflow

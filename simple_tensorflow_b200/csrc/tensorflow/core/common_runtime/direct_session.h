@@ -1,0 +1,110 @@
+// DirectSession for one B200 graph copy.
+//
+// BASELINE.json keeps the reference's DirectSession/executor "as-is"; those sources cannot be
+// compiled here (no bazel/protoc/Eigen), so this class reproduces the CALL CONTRACT the kernels
+// see from them and nothing more:
+//   * Run() prunes the graph to the fetches/targets, stopping at feeds
+//     (direct_session.cc:1098-1233), caches the result under a feeds/fetches/targets key
+//     (GetOrCreateExecutors :904-1096) and creates each kernel once with CreateOpKernel
+//     (:1028-1042; stateful kernels such as VariableV2 therefore keep their state);
+//   * the executor walks the partition in a topological order on ONE host thread -- what
+//     ExecutorState::Process does for a GPU partition, whose kernels are all "inexpensive"
+//     (executor.cc:1487-1691, op_kernel.cc:97-99) -- filling OpKernelContext::Params
+//     (:1575-1649), calling Device::Compute (:1651) and propagating outputs (:1654-1673);
+//   * feeds are copied host->device and fetches device->host through the device context
+//     (the job of _Send/_Recv + GPUUtil), and the device is synced exactly once per step
+//     (sync_on_finish, direct_session.cc:451, executor.cc:2211-2217).
+// Everything is placed on DEVICE_GPU: the named ops have no CPU fallback by design.
+#ifndef B200TF_CORE_COMMON_RUNTIME_DIRECT_SESSION_H_
+#define B200TF_CORE_COMMON_RUNTIME_DIRECT_SESSION_H_
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "tensorflow/core/common_runtime/gpu/gpu_device.h"
+#include "tensorflow/core/framework/op_kernel.h"
+#include "tensorflow/core/public/session.h"
+
+namespace tensorflow {
+
+class DirectSession : public Session {
+ public:
+  explicit DirectSession(const SessionOptions& options);
+  ~DirectSession() override;
+  Status Init();
+  Status Create(const GraphDef& graph) override;
+  Status Extend(const GraphDef& graph) override;
+  Status Run(const std::vector<std::pair<std::string, Tensor>>& inputs,
+             const std::vector<std::string>& output_tensor_names,
+             const std::vector<std::string>& target_node_names,
+             std::vector<Tensor>* outputs) override;
+  Status Close() override;
+  const RunStats& last_run_stats() const override { return stats_; }
+  BaseGPUDevice* device() const { return device_.get(); }
+
+ private:
+  struct TensorId {
+    int node = -1;
+    int slot = 0;
+  };
+  struct NodeItem {
+    NodeDef def;
+    std::vector<TensorId> inputs;       // data inputs, in op-signature order
+    std::vector<int> control_inputs;    // node indices
+    std::unique_ptr<OpKernel> kernel;   // created on first use
+  };
+  struct InputSource {
+    int feed = -1;  // >= 0: index into the step's feeds
+    TensorId id;    // otherwise: produced by this (node, slot)
+  };
+  struct PlanNode {
+    int node;
+    std::vector<InputSource> inputs;
+    int first_entry;  // index of output slot 0 in the entry table
+  };
+  struct ExecutorsAndKeys {
+    std::vector<PlanNode> order;
+    std::vector<InputSource> fetches;
+    std::vector<int> node_first_entry;  // per graph node: entry index of its output 0 (-1: pruned)
+    std::vector<int> entry_consumers;   // per entry: how many plan inputs read it
+    std::vector<bool> entry_is_fetch;
+    std::vector<bool> feed_needs_device, feed_needs_host;
+    int num_entries = 0;
+  };
+  struct Entry {
+    Tensor val;
+    Tensor* ref = nullptr;
+    std::mutex* ref_mu = nullptr;
+    bool has_value = false;
+    bool on_host = false;
+  };
+
+  static int entry_index_of(const ExecutorsAndKeys* ek, const TensorId& id) {
+    return ek->node_first_entry[id.node] + id.slot;
+  }
+  static Status ParseTensorName(const std::string& name, std::string* node, int* slot);
+  Status AddNodes(const GraphDef& graph);
+  Status GetOrCreateExecutors(const std::vector<std::string>& feeds,
+                              const std::vector<std::string>& fetches,
+                              const std::vector<std::string>& targets, ExecutorsAndKeys** out);
+  Status EnsureKernel(NodeItem* item);
+  Status RunPlan(ExecutorsAndKeys* ek, const std::vector<std::pair<std::string, Tensor>>& inputs,
+                 std::vector<Tensor>* outputs);
+
+  const SessionOptions options_;
+  std::unique_ptr<BaseGPUDevice> device_;
+  std::mutex mu_;
+  std::vector<std::unique_ptr<NodeItem>> nodes_;
+  std::unordered_map<std::string, int> node_index_;
+  std::map<std::string, std::unique_ptr<ExecutorsAndKeys>> executors_;
+  RunStats stats_;
+  long long step_id_ = 0;
+  bool closed_ = false;
+};
+
+}  // namespace tensorflow
+#endif

@@ -1,0 +1,118 @@
+#include "tensorflow/core/common_runtime/gpu/gpu_device.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace tensorflow {
+
+static Status AbiStatus(int rc, const char* what) {
+  if (rc == 0) return Status::OK();
+  return Status(static_cast<error::Code>(rc), strings::StrCat(what, ": ", b200_last_error()));
+}
+
+void GPUDeviceContext::CopyCPUTensorToDevice(const Tensor* cpu_tensor, Device* device,
+                                             Tensor* device_tensor, StatusCallback done) const {
+  const size_t bytes = cpu_tensor->TotalBytes();
+  if (bytes > 0) {
+    gpu::DeviceMemoryBase dst(device_tensor->raw_data(), bytes);
+    stream_->ThenMemcpyH2D(&dst, cpu_tensor->raw_data(), bytes);
+    if (!stream_->ok()) {
+      done(errors::Internal("CPU->GPU Memcpy failed: ", b200_last_error()));
+      return;
+    }
+  }
+  done(Status::OK());
+}
+
+void GPUDeviceContext::CopyDeviceTensorToCPU(const Tensor* device_tensor, const std::string&,
+                                             Device* device, Tensor* cpu_tensor,
+                                             StatusCallback done) {
+  const size_t bytes = device_tensor->TotalBytes();
+  if (bytes > 0) {
+    gpu::DeviceMemoryBase src(device_tensor->raw_data(), bytes);
+    stream_->ThenMemcpyD2H(cpu_tensor->raw_data(), src, bytes);
+    if (!stream_->ok()) {
+      done(errors::Internal("GPU->CPU Memcpy failed: ", b200_last_error()));
+      return;
+    }
+  }
+  done(Status::OK());
+}
+
+BaseGPUDevice::BaseGPUDevice(int gpu_id, const std::string& name)
+    : Device(name, DEVICE_GPU), gpu_id_(gpu_id) {}
+
+BaseGPUDevice::~BaseGPUDevice() {
+  if (stream_) stream_->BlockHostUntilDone();
+}
+
+Status BaseGPUDevice::Create(int gpu_id, size_t memory_limit_bytes,
+                             std::unique_ptr<BaseGPUDevice>* out) {
+  const int n = b200_device_count();
+  if (gpu_id < 0 || gpu_id >= n)
+    return errors::NotFound("GPU device ", gpu_id, " not found (", n,
+                            " CUDA devices visible; the B200 kernels have no CPU fallback)");
+  TF_RETURN_IF_ERROR(AbiStatus(b200_set_device(gpu_id), "b200_set_device"));
+  std::unique_ptr<BaseGPUDevice> d(
+      new BaseGPUDevice(gpu_id, strings::StrCat("/job:localhost/replica:0/task:0/gpu:", gpu_id)));
+  d->stream_.reset(new gpu::Stream());
+  d->stream_->Init();
+  if (!d->stream_->ok()) return errors::Internal("Failed to create the compute stream");
+  if (memory_limit_bytes == 0) {
+    size_t free_b = 0, total_b = 0;
+    TF_RETURN_IF_ERROR(AbiStatus(b200_mem_info(&free_b, &total_b), "b200_mem_info"));
+    const size_t reserve = std::max<size_t>(300u << 20, static_cast<size_t>(free_b * 0.05));
+    memory_limit_bytes = free_b > reserve ? free_b - reserve : free_b;
+  }
+  d->gpu_allocator_.reset(new GPUBFCAllocator(gpu_id, memory_limit_bytes,
+                                              strings::StrCat("GPU_", gpu_id, "_bfc")));
+  d->host_allocator_.reset(new GPUHostAllocator());
+  d->context_.reset(new GPUDeviceContext(d->stream_.get(), d->host_allocator_.get()));
+  d->gpu_device_info_.stream = d->stream_.get();
+  d->gpu_device_info_.default_context = d->context_.get();
+  d->gpu_device_info_.gpu_id = gpu_id;
+  d->set_tensorflow_gpu_device_info(&d->gpu_device_info_);
+  *out = std::move(d);
+  return Status::OK();
+}
+
+void BaseGPUDevice::Compute(OpKernel* op_kernel, OpKernelContext* context) {
+  // One process may drive several devices (replicas): make ours current, then enqueue.
+  b200_set_device(gpu_id_);
+  op_kernel->Compute(context);
+  if (context->status().ok() && !stream_->ok())
+    context->SetStatus(errors::Internal("GPU stream failed while running ", op_kernel->name()));
+}
+
+Status BaseGPUDevice::Sync() {
+  b200_set_device(gpu_id_);
+  if (!stream_->BlockHostUntilDone())
+    return errors::Internal("GPU sync failed: ", b200_last_error());
+  return Status::OK();
+}
+
+Status BaseGPUDevice::MakeTensorFromHost(const Tensor& host, Tensor* device_tensor) {
+  b200_set_device(gpu_id_);
+  Tensor t(gpu_allocator_.get(), host.dtype(), host.shape());
+  if (!t.IsInitialized())
+    return errors::ResourceExhausted("OOM when allocating feed tensor ", host.shape().DebugString());
+  Status s;
+  context_->CopyCPUTensorToDevice(&host, this, &t, [&s](const Status& r) { s = r; });
+  TF_RETURN_IF_ERROR(s);
+  *device_tensor = std::move(t);
+  return Status::OK();
+}
+
+Status BaseGPUDevice::CopyTensorToHost(const Tensor& device_tensor, Tensor* host) {
+  b200_set_device(gpu_id_);
+  Tensor t(host_allocator_.get(), device_tensor.dtype(), device_tensor.shape());
+  if (!t.IsInitialized())
+    return errors::ResourceExhausted("OOM when allocating pinned fetch buffer");
+  Status s;
+  context_->CopyDeviceTensorToCPU(&device_tensor, "", this, &t, [&s](const Status& r) { s = r; });
+  TF_RETURN_IF_ERROR(s);
+  *host = std::move(t);
+  return Status::OK();
+}
+
+}  // namespace tensorflow

@@ -1,0 +1,78 @@
+// BaseGPUDevice for B200 -- the "new tensorflow/core/common_runtime/gpu device" of the
+// north star.  Same roles as the reference's core/common_runtime/gpu/gpu_device.{h,cc}:
+//   * one compute stream per device (BaseGPUDevice::Init, gpu_device.cc:194-264)
+//   * BFC arena for device memory, pinned-host allocator for feeds/fetches
+//   * GPUDeviceContext carrying the stream to kernels (gpu_device_context.h) and doing the
+//     H2D / D2H tensor copies of GPUUtil (gpu_util.cc)
+//   * Compute() only enqueues (gpu_device.cc:337-399); Sync() is the one blocking call per step
+//     (gpu_device.cc:413)
+// All CUDA access goes through the C ABI shim (tensorflow/stream_executor/stream.h).
+#ifndef B200TF_CORE_COMMON_RUNTIME_GPU_GPU_DEVICE_H_
+#define B200TF_CORE_COMMON_RUNTIME_GPU_GPU_DEVICE_H_
+
+#include <memory>
+#include <string>
+
+#include "tensorflow/core/common_runtime/device.h"
+#include "tensorflow/core/common_runtime/gpu/gpu_bfc_allocator.h"
+
+namespace tensorflow {
+
+class GPUDeviceContext : public DeviceContext {
+ public:
+  GPUDeviceContext(gpu::Stream* stream, Allocator* host_allocator)
+      : stream_(stream), host_allocator_(host_allocator) {}
+  gpu::Stream* stream() const override { return stream_; }
+  void CopyCPUTensorToDevice(const Tensor* cpu_tensor, Device* device, Tensor* device_tensor,
+                             StatusCallback done) const override;
+  void CopyDeviceTensorToCPU(const Tensor* device_tensor, const std::string& tensor_name,
+                             Device* device, Tensor* cpu_tensor, StatusCallback done) override;
+
+ private:
+  gpu::Stream* stream_;
+  Allocator* host_allocator_;
+};
+
+class BaseGPUDevice : public Device {
+ public:
+  // memory_limit_bytes == 0: free memory minus max(300 MiB, 5 %) like gpu_device.cc:546-561.
+  static Status Create(int gpu_id, size_t memory_limit_bytes, std::unique_ptr<BaseGPUDevice>* out);
+  ~BaseGPUDevice() override;
+
+  Allocator* GetAllocator(AllocatorAttributes attr) override {
+    return attr.on_host() ? static_cast<Allocator*>(host_allocator_.get())
+                          : static_cast<Allocator*>(gpu_allocator_.get());
+  }
+  void Compute(OpKernel* op_kernel, OpKernelContext* context) override;
+  Status Sync() override;
+  Status MakeTensorFromHost(const Tensor& host, Tensor* device_tensor) override;
+  Status CopyTensorToHost(const Tensor& device_tensor, Tensor* host) override;
+
+  // Replica data-parallel: the NCCL communicator this device's B200AllReduce kernels use
+  // (created by the host with b200_nccl_comm_init_rank; not owned).
+  void set_collective_comm(void* comm, int num_replicas) {
+    collective_comm_ = comm;
+    num_replicas_ = num_replicas;
+  }
+  void* collective_comm() const { return collective_comm_; }
+  int num_replicas() const { return num_replicas_; }
+
+  int gpu_id() const { return gpu_id_; }
+  gpu::Stream* compute_stream() const { return stream_.get(); }
+  GPUDeviceContext* device_context() const { return context_.get(); }
+  Allocator* host_allocator() const { return host_allocator_.get(); }
+
+ private:
+  BaseGPUDevice(int gpu_id, const std::string& name);
+  const int gpu_id_;
+  std::unique_ptr<gpu::Stream> stream_;
+  std::unique_ptr<GPUBFCAllocator> gpu_allocator_;
+  std::unique_ptr<GPUHostAllocator> host_allocator_;
+  std::unique_ptr<GPUDeviceContext> context_;
+  GpuDeviceInfo gpu_device_info_;
+  void* collective_comm_ = nullptr;
+  int num_replicas_ = 1;
+};
+
+}  // namespace tensorflow
+#endif

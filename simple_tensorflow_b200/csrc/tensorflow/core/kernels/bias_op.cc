@@ -1,0 +1,80 @@
+// BiasAdd / BiasAddGrad for DEVICE_GPU on B200 (NHWC).
+// Validation follows BiasOp::Compute (core/kernels/bias_op.cc:62-117) and BiasGradOp::Compute
+// (:185-227); launches replace BiasGPU / BiasGradGPU (bias_op_gpu.cu.cc:69-88,189-242).
+#include "tensorflow/core/kernels/gpu_kernel_util.h"
+#include "tensorflow/core/util/padding.h"
+
+namespace tensorflow {
+
+static Status RequireNHWC(OpKernelConstruction* ctx, const char* op) {
+  std::string data_format;
+  if (ctx->GetAttr("data_format", &data_format).ok() && data_format != "NHWC")
+    return errors::Unimplemented(op, " on B200 supports only the NHWC data_format (the CPU "
+                                 "kernel the oracle follows is NHWC-only too, bias_op.cc:54-55)");
+  return Status::OK();
+}
+
+template <typename T>
+class BiasOp : public OpKernel {
+ public:
+  explicit BiasOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, RequireNHWC(ctx, "BiasAdd"));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& input = ctx->input(0);
+    const Tensor& bias = ctx->input(1);
+    OP_REQUIRES(ctx, TensorShapeUtils::IsMatrixOrHigher(input.shape()),
+                errors::InvalidArgument("Input tensor must be at least 2D: ",
+                                        input.shape().DebugString()));
+    OP_REQUIRES(ctx, TensorShapeUtils::IsVector(bias.shape()),
+                errors::InvalidArgument("Biases must be 1D: ", bias.shape().DebugString()));
+    const int64 channels = input.dim_size(input.dims() - 1);
+    OP_REQUIRES(ctx, bias.dim_size(0) == channels,
+                errors::InvalidArgument("Must provide as many biases as the last dimension of the "
+                                        "input tensor: ", bias.shape().DebugString(), " vs. ",
+                                        input.shape().DebugString()));
+    Tensor* output = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->forward_input_or_allocate_output({0}, 0, input.shape(), &output));
+    if (input.NumElements() == 0) return;
+    OP_REQUIRES_OK(ctx, FromAbi(b200_bias_add(AbiType<T>::v, input.raw_data(), bias.raw_data(),
+                                              output->raw_data(), input.NumElements() / channels,
+                                              channels, GetCudaStream(ctx)),
+                                "BiasAdd"));
+  }
+};
+
+template <typename T>
+class BiasGradOp : public OpKernel {
+ public:
+  explicit BiasGradOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, RequireNHWC(ctx, "BiasAddGrad"));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& g = ctx->input(0);
+    OP_REQUIRES(ctx, TensorShapeUtils::IsMatrixOrHigher(g.shape()),
+                errors::InvalidArgument("Input tensor must be at least 2D: ",
+                                        g.shape().DebugString()));
+    const int64 channels = g.dim_size(g.dims() - 1);
+    Tensor* output = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({channels}), &output));
+    if (channels == 0) return;
+    const int64 rows = g.NumElements() / channels;
+    const size_t ws = b200_bias_add_grad_workspace_bytes(AbiType<T>::v, rows, channels);
+    Tensor scratch;
+    if (ws > 0) OP_REQUIRES_OK(ctx, ctx->allocate_temp(DT_UINT8, TensorShape({(int64)ws}), &scratch));
+    OP_REQUIRES_OK(ctx, FromAbi(b200_bias_add_grad(AbiType<T>::v, g.raw_data(), output->raw_data(),
+                                                   rows, channels, ws ? scratch.raw_data() : nullptr,
+                                                   ws, GetCudaStream(ctx)),
+                                "BiasAddGrad"));
+  }
+};
+
+#define REGISTER_GPU(T)                                                                     \
+  REGISTER_KERNEL_BUILDER(Name("BiasAdd").Device(DEVICE_GPU).TypeConstraint<T>("T"),        \
+                          BiasOp<T>);                                                       \
+  REGISTER_KERNEL_BUILDER(Name("BiasAddGrad").Device(DEVICE_GPU).TypeConstraint<T>("T"),    \
+                          BiasGradOp<T>);
+REGISTER_B200_FLOAT_TYPES(REGISTER_GPU)
+#undef REGISTER_GPU
+
+}  // namespace tensorflow

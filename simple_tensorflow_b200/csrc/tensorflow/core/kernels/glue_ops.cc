@@ -1,0 +1,406 @@
+// Graph-glue kernels that keep a whole training step on the device:
+// Const, Placeholder, Identity, Reshape, Shape, NoOp, VariableV2, Assign, AddN, Mul, Mean,
+// ApplyGradientDescent, and the additive B200AllReduce.  Semantics follow the reference's
+// core/kernels/{constant_op,identity_op,reshape_op,shape_ops,no_op,variable_ops,assign_op,
+// aggregate_ops,cwise_op_mul_1,reduction_ops_mean,training_ops}.cc for the cases training
+// graphs of the hot path produce.
+#include <memory>
+
+#include "tensorflow/core/common_runtime/device.h"
+#include "tensorflow/core/common_runtime/gpu/gpu_device.h"
+#include "tensorflow/core/kernels/gpu_kernel_util.h"
+
+namespace tensorflow {
+
+// ---------------------------------------------------------------- Const
+// constant_op.cc: the tensor attr is materialised once, at kernel construction.  int32 outputs
+// live in host memory like the reference's HostConstantOp registration (shape operands).
+class ConstantOp : public OpKernel {
+ public:
+  explicit ConstantOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+    Tensor host;
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("value", &host));
+    DataType dtype;
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("dtype", &dtype));
+    OP_REQUIRES(ctx, dtype == host.dtype(),
+                errors::InvalidArgument("Type mismatch between value (", DataTypeString(host.dtype()),
+                                        ") and dtype (", DataTypeString(dtype), ")"));
+    if (ctx->output_memory_types()[0] == HOST_MEMORY) {
+      tensor_ = host;
+      return;
+    }
+    Device* device = dynamic_cast<Device*>(ctx->device());
+    OP_REQUIRES(ctx, device != nullptr, errors::Internal("Const: no device"));
+    OP_REQUIRES_OK(ctx, device->MakeTensorFromHost(host, &tensor_));
+  }
+  void Compute(OpKernelContext* ctx) override { ctx->set_output(0, tensor_); }
+
+ private:
+  Tensor tensor_;
+};
+REGISTER_KERNEL_BUILDER(Name("Const").Device(DEVICE_GPU).TypeConstraint<float>("dtype"), ConstantOp);
+REGISTER_KERNEL_BUILDER(Name("Const").Device(DEVICE_GPU).TypeConstraint<bfloat16>("dtype"),
+                        ConstantOp);
+REGISTER_KERNEL_BUILDER(Name("Const").Device(DEVICE_GPU).TypeConstraint<int64>("dtype"), ConstantOp);
+REGISTER_KERNEL_BUILDER(
+    Name("Const").Device(DEVICE_GPU).HostMemory("output").TypeConstraint<int32>("dtype"),
+    ConstantOp);
+
+// ---------------------------------------------------------------- Placeholder / NoOp / Identity
+class PlaceholderOp : public OpKernel {
+ public:
+  explicit PlaceholderOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
+  void Compute(OpKernelContext* ctx) override {
+    // array_ops / constant_op.cc PlaceholderOp::Compute
+    ctx->SetStatus(errors::InvalidArgument("You must feed a value for placeholder tensor '",
+                                           name(), "' with dtype ",
+                                           DataTypeString(output_type(0))));
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("Placeholder").Device(DEVICE_GPU), PlaceholderOp);
+
+class NoOp : public OpKernel {
+ public:
+  explicit NoOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
+  void Compute(OpKernelContext*) override {}
+};
+REGISTER_KERNEL_BUILDER(Name("NoOp").Device(DEVICE_GPU), NoOp);
+
+class IdentityOp : public OpKernel {
+ public:
+  explicit IdentityOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
+  void Compute(OpKernelContext* ctx) override { ctx->set_output(0, ctx->input(0)); }
+};
+REGISTER_KERNEL_BUILDER(Name("Identity").Device(DEVICE_GPU), IdentityOp);
+
+// ---------------------------------------------------------------- Reshape / Shape
+// reshape_op.h: `shape` is a host-memory vector, one -1 entry is inferred, the buffer is shared.
+class ReshapeOp : public OpKernel {
+ public:
+  explicit ReshapeOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& input = ctx->input(0);
+    const Tensor& sizes = ctx->input(1);
+    OP_REQUIRES(ctx, TensorShapeUtils::IsVector(sizes.shape()),
+                errors::InvalidArgument("sizes input must be 1-D, not shape ",
+                                        sizes.shape().DebugString()));
+    TensorShape shape;
+    int64 product = 1;
+    int unknown_index = -1;
+    for (int d = 0; d < sizes.NumElements(); ++d) {
+      const int64 size = sizes.dtype() == DT_INT64 ? sizes.data<int64>()[d]
+                                                   : sizes.data<int32>()[d];
+      if (size == -1) {
+        OP_REQUIRES(ctx, unknown_index == -1,
+                    errors::InvalidArgument("only one input size may be -1, not both ",
+                                            unknown_index, " and ", d));
+        unknown_index = d;
+        shape.AddDim(1);
+      } else {
+        OP_REQUIRES(ctx, size >= 0, errors::InvalidArgument("size ", d, " must be non-negative, not ", size));
+        shape.AddDim(size);
+        product *= size;
+      }
+    }
+    if (unknown_index != -1) {
+      OP_REQUIRES(ctx, product > 0,
+                  errors::InvalidArgument("Reshape cannot infer the missing input size for an "
+                                          "empty tensor unless all specified input sizes are non-zero"));
+      const int64 missing = input.NumElements() / product;
+      OP_REQUIRES(ctx, product * missing == input.NumElements(),
+                  errors::InvalidArgument("Input to reshape is a tensor with ", input.NumElements(),
+                                          " values, but the requested shape requires a multiple of ",
+                                          product));
+      shape.set_dim(unknown_index, missing);
+    }
+    OP_REQUIRES(ctx, shape.num_elements() == input.NumElements(),
+                errors::InvalidArgument("Input to reshape is a tensor with ", input.NumElements(),
+                                        " values, but the requested shape has ",
+                                        shape.num_elements()));
+    Tensor output;
+    OP_REQUIRES(ctx, output.CopyFrom(input, shape), errors::Internal("Reshape CopyFrom failed"));
+    ctx->set_output(0, output);
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("Reshape").Device(DEVICE_GPU).HostMemory("shape"), ReshapeOp);
+
+class ShapeOp : public OpKernel {
+ public:
+  explicit ShapeOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& inp = ctx->input(0);
+    Tensor* out = nullptr;
+    AllocatorAttributes host;
+    host.set_on_host(true);
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({inp.dims()}), &out, host));
+    for (int i = 0; i < inp.dims(); ++i) {
+      if (output_type(0) == DT_INT64)
+        out->data<int64>()[i] = inp.dim_size(i);
+      else
+        out->data<int32>()[i] = static_cast<int32>(inp.dim_size(i));
+    }
+  }
+};
+REGISTER_KERNEL_BUILDER(Name("Shape").Device(DEVICE_GPU).HostMemory("output"), ShapeOp);
+
+// ---------------------------------------------------------------- VariableV2 / Assign
+// variable_ops.h: the tensor lives with the (stateful) kernel, guarded by a mutex; the output is
+// a reference to it.  It starts unallocated; Assign gives it storage (assign_op.h).
+class VariableOp : public OpKernel {
+ public:
+  explicit VariableOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("shape", &shape_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("dtype", &dtype_));
+    var_ = Tensor(dtype_, TensorShape({0}));
+  }
+  void Compute(OpKernelContext* ctx) override { ctx->set_output_ref(0, &mu_, &var_); }
+
+ private:
+  TensorShape shape_;
+  DataType dtype_;
+  std::mutex mu_;
+  Tensor var_;
+};
+REGISTER_KERNEL_BUILDER(Name("VariableV2").Device(DEVICE_GPU), VariableOp);
+
+class AssignOp : public OpKernel {
+ public:
+  explicit AssignOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("validate_shape", &validate_shape_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& rhs = ctx->input(1);
+    ctx->forward_ref_input_to_ref_output(0, 0);
+    std::mutex* mu = ctx->input_ref_mutex(0);
+    std::lock_guard<std::mutex> l(*mu);
+    Tensor old_lhs = ctx->mutable_input(0, /*lock_held=*/true);
+    if (validate_shape_ && old_lhs.IsInitialized() && old_lhs.NumElements() > 0)
+      OP_REQUIRES(ctx, old_lhs.shape().IsSameSize(rhs.shape()),
+                  errors::InvalidArgument("Assign requires shapes of both tensors to match. "
+                                          "lhs shape= ", old_lhs.shape().DebugString(),
+                                          " rhs shape= ", rhs.shape().DebugString()));
+    // assign_op.h: reuse the lhs buffer when the sizes agree, otherwise take a fresh copy.
+    Tensor* lhs = (*params_inputs(ctx))[0].tensor;
+    if (old_lhs.IsInitialized() && old_lhs.NumElements() == rhs.NumElements() &&
+        old_lhs.NumElements() > 0) {
+      lhs->CopyFrom(old_lhs, rhs.shape());
+    } else {
+      Tensor fresh(ctx->get_allocator(AllocatorAttributes()), rhs.dtype(), rhs.shape());
+      OP_REQUIRES(ctx, fresh.IsInitialized(),
+                  errors::ResourceExhausted("OOM when allocating variable ", name()));
+      *lhs = fresh;
+    }
+    OP_REQUIRES_OK(ctx, FromAbi(b200_memcpy_d2d_async(lhs->raw_data(), rhs.raw_data(),
+                                                      rhs.TotalBytes(), GetCudaStream(ctx)),
+                                "Assign"));
+  }
+
+ private:
+  // The ref input's Tensor object is the variable itself (TensorValue::tensor).
+  static const std::vector<TensorValue>* params_inputs(OpKernelContext* ctx) {
+    return ctx->ref_inputs_for_assign();
+  }
+  bool validate_shape_;
+};
+REGISTER_KERNEL_BUILDER(Name("Assign").Device(DEVICE_GPU), AssignOp);
+
+// ---------------------------------------------------------------- AddN / Mul / Mean
+template <typename T>
+class AddNOp : public OpKernel {
+ public:
+  explicit AddNOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
+  void Compute(OpKernelContext* ctx) override {
+    const int num = ctx->num_inputs();
+    const Tensor& input0 = ctx->input(0);
+    for (int i = 1; i < num; ++i)
+      OP_REQUIRES(ctx, ctx->input(i).shape() == input0.shape(),
+                  errors::InvalidArgument("Inputs to operation ", name(), " of type ",
+                                          type_string(), " must have the same size and shape.  "
+                                          "Input 0: ", input0.shape().DebugString(), " != input ",
+                                          i, ": ", ctx->input(i).shape().DebugString()));
+    OP_REQUIRES(ctx, num <= 8, errors::Unimplemented("AddN with more than 8 inputs"));
+    Tensor* output = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, input0.shape(), &output));
+    const void* ptrs[8];
+    for (int i = 0; i < num; ++i) ptrs[i] = ctx->input(i).raw_data();
+    OP_REQUIRES_OK(ctx, FromAbi(b200_add_n(AbiType<T>::v, ptrs, num, output->raw_data(),
+                                           input0.NumElements(), GetCudaStream(ctx)),
+                                "AddN"));
+  }
+};
+
+template <typename T>
+class MulOp : public OpKernel {
+ public:
+  explicit MulOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor* x = &ctx->input(0);
+    const Tensor* y = &ctx->input(1);
+    if (x->NumElements() == 1 && y->NumElements() != 1) std::swap(x, y);  // commutative
+    const bool scalar = y->NumElements() == 1 && x->NumElements() != 1;
+    OP_REQUIRES(ctx, scalar || x->shape() == y->shape(),
+                errors::Unimplemented("Mul on B200 supports equal shapes or a scalar operand; got ",
+                                      x->shape().DebugString(), " vs ", y->shape().DebugString()));
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, x->shape(), &out));
+    OP_REQUIRES_OK(ctx, FromAbi(b200_mul(AbiType<T>::v, x->raw_data(), y->raw_data(),
+                                         out->raw_data(), x->NumElements(), scalar,
+                                         GetCudaStream(ctx)),
+                                "Mul"));
+  }
+};
+
+// Mean over ALL elements (the loss reduction); reduction_indices is a host-memory vector.
+class MeanOp : public OpKernel {
+ public:
+  explicit MeanOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("keep_dims", &keep_dims_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& data = ctx->input(0);
+    const Tensor& axes = ctx->input(1);
+    OP_REQUIRES(ctx, axes.NumElements() == data.dims(),
+                errors::Unimplemented("Mean on B200 reduces over all dimensions only (got ",
+                                      axes.NumElements(), " axes for rank ", data.dims(), ")"));
+    TensorShape out_shape;
+    if (keep_dims_)
+      for (int i = 0; i < data.dims(); ++i) out_shape.AddDim(1);
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, out_shape, &out));
+    const int64 n = data.NumElements();
+    OP_REQUIRES_OK(ctx, FromAbi(b200_reduce_sum(B200_DT_FLOAT, data.raw_data(),
+                                                n ? 1.0f / static_cast<float>(n) : 0.f,
+                                                out->raw_data(), n, GetCudaStream(ctx)),
+                                "Mean"));
+  }
+
+ private:
+  bool keep_dims_;
+};
+REGISTER_KERNEL_BUILDER(
+    Name("Mean").Device(DEVICE_GPU).TypeConstraint<float>("T").HostMemory("reduction_indices"),
+    MeanOp);
+
+// ---------------------------------------------------------------- ApplyGradientDescent
+// training_ops.cc:369-412: var -= alpha * delta on the variable's own buffer; out = ref(var).
+template <typename T>
+class ApplyGradientDescentOp : public OpKernel {
+ public:
+  explicit ApplyGradientDescentOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
+  void Compute(OpKernelContext* ctx) override {
+    Tensor var = ctx->mutable_input(0, false);
+    OP_REQUIRES(ctx, var.IsInitialized() && var.NumElements() > 0,
+                errors::FailedPrecondition("Attempting to use uninitialized variables: ",
+                                           def().input.empty() ? name() : def().input[0]));
+    const Tensor& alpha = ctx->input(1);
+    OP_REQUIRES(ctx, TensorShapeUtils::IsScalar(alpha.shape()),
+                errors::InvalidArgument("alpha is not a scalar: ", alpha.shape().DebugString()));
+    const Tensor& delta = ctx->input(2);
+    OP_REQUIRES(ctx, var.shape().IsSameSize(delta.shape()),
+                errors::InvalidArgument("var and delta do not have the same shape",
+                                        var.shape().DebugString(), " ",
+                                        delta.shape().DebugString()));
+    OP_REQUIRES_OK(ctx, FromAbi(b200_apply_gradient_descent(AbiType<T>::v, var.raw_data(),
+                                                            alpha.raw_data(), delta.raw_data(),
+                                                            var.NumElements(), GetCudaStream(ctx)),
+                                "ApplyGradientDescent"));
+    ctx->forward_ref_input_to_ref_output(0, 0);
+  }
+};
+
+// ---------------------------------------------------------------- B200AllReduce (additive)
+// One ncclAllReduce(sum) on the compute stream over the referenced buffer, in place, followed by
+// an optional scale (1/replicas for a gradient average).  No host synchronisation.
+template <typename T>
+class B200AllReduceOp : public OpKernel {
+ public:
+  explicit B200AllReduceOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("scale", &scale_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    Tensor data = ctx->mutable_input(0, false);
+    ctx->forward_ref_input_to_ref_output(0, 0);
+    BaseGPUDevice* dev = dynamic_cast<BaseGPUDevice*>(ctx->device());
+    OP_REQUIRES(ctx, dev != nullptr, errors::Internal("B200AllReduce needs a GPU device"));
+    if (dev->num_replicas() <= 1 || dev->collective_comm() == nullptr) {
+      if (scale_ != 1.0f)
+        OP_REQUIRES_OK(ctx, FromAbi(b200_scale(AbiType<T>::v, data.raw_data(), scale_,
+                                               data.raw_data(), data.NumElements(),
+                                               GetCudaStream(ctx)),
+                                    "B200AllReduce scale"));
+      return;
+    }
+    OP_REQUIRES_OK(ctx, FromAbi(b200_nccl_all_reduce_sum(AbiType<T>::v, data.raw_data(),
+                                                         data.raw_data(), data.NumElements(),
+                                                         dev->collective_comm(),
+                                                         GetCudaStream(ctx)),
+                                "ncclAllReduce"));
+    if (scale_ != 1.0f)
+      OP_REQUIRES_OK(ctx, FromAbi(b200_scale(AbiType<T>::v, data.raw_data(), scale_,
+                                             data.raw_data(), data.NumElements(),
+                                             GetCudaStream(ctx)),
+                                  "B200AllReduce scale"));
+  }
+
+ private:
+  float scale_;
+};
+
+template <typename T>
+class B200AllReduceNOp : public OpKernel {
+ public:
+  explicit B200AllReduceNOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("scale", &scale_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    BaseGPUDevice* dev = dynamic_cast<BaseGPUDevice*>(ctx->device());
+    OP_REQUIRES(ctx, dev != nullptr, errors::Internal("B200AllReduceN needs a GPU device"));
+    const int n = ctx->num_inputs();
+    void* stream = GetCudaStream(ctx);
+    // 256-byte aligned slices so every slice keeps 16-byte vector alignment
+    std::vector<int64> offset(n + 1, 0);
+    for (int i = 0; i < n; ++i)
+      offset[i + 1] = offset[i] + (ctx->input(i).NumElements() + 127) / 128 * 128;
+    Tensor arena;
+    OP_REQUIRES_OK(ctx, ctx->allocate_temp(DataTypeToEnum<T>::v(), TensorShape({offset[n]}), &arena));
+    char* base = static_cast<char*>(arena.raw_data());
+    OP_REQUIRES_OK(ctx, FromAbi(b200_memset_async(base, 0, arena.TotalBytes(), stream), "arena"));
+    for (int i = 0; i < n; ++i)
+      OP_REQUIRES_OK(ctx, FromAbi(b200_memcpy_d2d_async(base + offset[i] * sizeof(T),
+                                                        ctx->input(i).raw_data(),
+                                                        ctx->input(i).TotalBytes(), stream),
+                                  "pack"));
+    if (dev->num_replicas() > 1 && dev->collective_comm() != nullptr)
+      OP_REQUIRES_OK(ctx, FromAbi(b200_nccl_all_reduce_sum(AbiType<T>::v, base, base, offset[n],
+                                                           dev->collective_comm(), stream),
+                                  "ncclAllReduce"));
+    if (scale_ != 1.0f)
+      OP_REQUIRES_OK(ctx, FromAbi(b200_scale(AbiType<T>::v, base, scale_, base, offset[n], stream),
+                                  "scale"));
+    for (int i = 0; i < n; ++i) {
+      Tensor* out = nullptr;
+      OP_REQUIRES_OK(ctx, ctx->allocate_output(i, ctx->input(i).shape(), &out));
+      OP_REQUIRES_OK(ctx, FromAbi(b200_memcpy_d2d_async(out->raw_data(),
+                                                        base + offset[i] * sizeof(T),
+                                                        out->TotalBytes(), stream),
+                                  "unpack"));
+    }
+  }
+
+ private:
+  float scale_;
+};
+
+#define REGISTER_GPU(T)                                                                          \
+  REGISTER_KERNEL_BUILDER(Name("B200AllReduceN").Device(DEVICE_GPU).TypeConstraint<T>("T"),      \
+                          B200AllReduceNOp<T>);                                                  \
+  REGISTER_KERNEL_BUILDER(Name("AddN").Device(DEVICE_GPU).TypeConstraint<T>("T"), AddNOp<T>);    \
+  REGISTER_KERNEL_BUILDER(Name("Mul").Device(DEVICE_GPU).TypeConstraint<T>("T"), MulOp<T>);      \
+  REGISTER_KERNEL_BUILDER(Name("ApplyGradientDescent").Device(DEVICE_GPU).TypeConstraint<T>("T"),\
+                          ApplyGradientDescentOp<T>);                                            \
+  REGISTER_KERNEL_BUILDER(Name("B200AllReduce").Device(DEVICE_GPU).TypeConstraint<T>("T"),       \
+                          B200AllReduceOp<T>);
+REGISTER_B200_FLOAT_TYPES(REGISTER_GPU)
+#undef REGISTER_GPU
+
+}  // namespace tensorflow

@@ -1,0 +1,124 @@
+// MaxPool / MaxPoolGrad for DEVICE_GPU on B200 (NHWC, spatial pooling).
+// Parameter checks follow MaxPoolingOp / PoolParameters (core/kernels/pooling_ops_common.h:73-130,
+// pooling_ops_common.cc:31-90) and MaxPoolingGradOp (core/kernels/maxpooling_op.cc:230-306).
+#include "tensorflow/core/kernels/gpu_kernel_util.h"
+#include "tensorflow/core/util/padding.h"
+
+namespace tensorflow {
+namespace {
+
+struct PoolAttrs {
+  std::vector<int32> ksize, stride;
+  Padding padding;
+  Status Init(OpKernelConstruction* context) {
+    std::string data_format;
+    if (context->GetAttr("data_format", &data_format).ok() && data_format != "NHWC")
+      return errors::InvalidArgument("Default MaxPoolingOp only supports NHWC.");
+    TF_RETURN_IF_ERROR(context->GetAttr("ksize", &ksize));
+    if (ksize.size() != 4)
+      return errors::InvalidArgument("Sliding window ksize field must specify 4 dimensions");
+    TF_RETURN_IF_ERROR(context->GetAttr("strides", &stride));
+    if (stride.size() != 4)
+      return errors::InvalidArgument("Sliding window stride field must specify 4 dimensions");
+    TF_RETURN_IF_ERROR(context->GetAttr("padding", &padding));
+    if (ksize[0] != 1 || stride[0] != 1)
+      return errors::Unimplemented("Pooling is not yet supported on the batch dimension.");
+    if (ksize[3] != 1 || stride[3] != 1)
+      return errors::Unimplemented("Depthwise max pooling is outside the B200 hot path "
+                                   "(pooling_ops_common.cc:54-57 allows spatial OR depth pooling)");
+    return Status::OK();
+  }
+};
+
+struct PoolDims {
+  int64 batch, rows, cols, depth, out_rows, out_cols, pad_rows, pad_cols;
+};
+Status ComputePoolDims(const TensorShape& in, const PoolAttrs& a, PoolDims* d) {
+  if (in.dims() != 4) return errors::InvalidArgument("tensor_in must be 4-dimensional");
+  d->batch = in.dim_size(0);
+  d->rows = in.dim_size(1);
+  d->cols = in.dim_size(2);
+  d->depth = in.dim_size(3);
+  TF_RETURN_IF_ERROR(GetWindowedOutputSize(d->rows, a.ksize[1], a.stride[1], a.padding,
+                                           &d->out_rows, &d->pad_rows));
+  return GetWindowedOutputSize(d->cols, a.ksize[2], a.stride[2], a.padding, &d->out_cols,
+                               &d->pad_cols);
+}
+
+}  // namespace
+
+template <typename T>
+class MaxPoolingOp : public OpKernel {
+ public:
+  explicit MaxPoolingOp(OpKernelConstruction* context) : OpKernel(context) {
+    OP_REQUIRES_OK(context, attrs_.Init(context));
+  }
+  void Compute(OpKernelContext* context) override {
+    const Tensor& tensor_in = context->input(0);
+    PoolDims d;
+    OP_REQUIRES_OK(context, ComputePoolDims(tensor_in.shape(), attrs_, &d));
+    Tensor* output = nullptr;
+    OP_REQUIRES_OK(context, context->allocate_output(
+                                0, TensorShape({d.batch, d.out_rows, d.out_cols, d.depth}), &output));
+    if (output->NumElements() == 0) return;
+    OP_REQUIRES_OK(context,
+                   FromAbi(b200_max_pool(AbiType<T>::v, tensor_in.raw_data(), output->raw_data(),
+                                         d.batch, d.rows, d.cols, d.depth, d.out_rows, d.out_cols,
+                                         attrs_.ksize[1], attrs_.ksize[2], attrs_.stride[1],
+                                         attrs_.stride[2], (int)d.pad_rows, (int)d.pad_cols,
+                                         GetCudaStream(context)),
+                           "MaxPool"));
+  }
+
+ private:
+  PoolAttrs attrs_;
+};
+
+template <typename T>
+class MaxPoolingGradOp : public OpKernel {
+ public:
+  explicit MaxPoolingGradOp(OpKernelConstruction* context) : OpKernel(context) {
+    OP_REQUIRES_OK(context, attrs_.Init(context));
+  }
+  void Compute(OpKernelContext* context) override {
+    const Tensor& tensor_in = context->input(0);
+    const Tensor& tensor_out = context->input(1);
+    const Tensor& out_backprop = context->input(2);
+    OP_REQUIRES(context, tensor_in.dims() == 4,
+                errors::InvalidArgument("tensor_in must be 4-dimensional"));
+    OP_REQUIRES(context, tensor_out.dims() == 4,
+                errors::InvalidArgument("tensor_out must be 4-dimensional"));
+    OP_REQUIRES(context, out_backprop.dims() == 4,
+                errors::InvalidArgument("out_backprop must be 4-dimensional"));
+    PoolDims d;
+    OP_REQUIRES_OK(context, ComputePoolDims(tensor_in.shape(), attrs_, &d));
+    const TensorShape expect({d.batch, d.out_rows, d.out_cols, d.depth});
+    OP_REQUIRES(context, out_backprop.shape() == expect,
+                errors::InvalidArgument("out_backprop shape ", out_backprop.shape().DebugString(),
+                                        " does not match the pooled shape ", expect.DebugString()));
+    Tensor* output = nullptr;
+    OP_REQUIRES_OK(context, context->allocate_output(0, tensor_in.shape(), &output));
+    if (output->NumElements() == 0) return;
+    OP_REQUIRES_OK(context, FromAbi(b200_max_pool_grad(
+                                        AbiType<T>::v, tensor_in.raw_data(), tensor_out.raw_data(),
+                                        out_backprop.raw_data(), output->raw_data(), d.batch,
+                                        d.rows, d.cols, d.depth, d.out_rows, d.out_cols,
+                                        attrs_.ksize[1], attrs_.ksize[2], attrs_.stride[1],
+                                        attrs_.stride[2], (int)d.pad_rows, (int)d.pad_cols,
+                                        GetCudaStream(context)),
+                                    "MaxPoolGrad"));
+  }
+
+ private:
+  PoolAttrs attrs_;
+};
+
+#define REGISTER_GPU(T)                                                                      \
+  REGISTER_KERNEL_BUILDER(Name("MaxPool").Device(DEVICE_GPU).TypeConstraint<T>("T"),         \
+                          MaxPoolingOp<T>);                                                  \
+  REGISTER_KERNEL_BUILDER(Name("MaxPoolGrad").Device(DEVICE_GPU).TypeConstraint<T>("T"),     \
+                          MaxPoolingGradOp<T>);
+REGISTER_B200_FLOAT_TYPES(REGISTER_GPU)
+#undef REGISTER_GPU
+
+}  // namespace tensorflow

@@ -1,0 +1,46 @@
+// Relu / ReluGrad for DEVICE_GPU on B200.  Checks follow ReluOp / ReluGradOp
+// (core/kernels/relu_op.h:34-94, numeric_op.h:52-111): same-shape inputs, in-place allowed.
+#include "tensorflow/core/kernels/gpu_kernel_util.h"
+
+namespace tensorflow {
+
+template <typename T>
+class ReluOp : public OpKernel {
+ public:
+  explicit ReluOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& features = ctx->input(0);
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->forward_input_or_allocate_output({0}, 0, features.shape(), &out));
+    OP_REQUIRES_OK(ctx, FromAbi(b200_relu(AbiType<T>::v, features.raw_data(), out->raw_data(),
+                                          features.NumElements(), GetCudaStream(ctx)),
+                                "Relu"));
+  }
+};
+
+template <typename T>
+class ReluGradOp : public OpKernel {
+ public:
+  explicit ReluGradOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& g = ctx->input(0);
+    const Tensor& a = ctx->input(1);
+    OP_REQUIRES(ctx, a.IsSameSize(g),
+                errors::InvalidArgument("Inputs must have the same size"));  // relu_op.h:48-60
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->forward_input_or_allocate_output({0, 1}, 0, g.shape(), &out));
+    OP_REQUIRES_OK(ctx, FromAbi(b200_relu_grad(AbiType<T>::v, g.raw_data(), a.raw_data(),
+                                               out->raw_data(), g.NumElements(),
+                                               GetCudaStream(ctx)),
+                                "ReluGrad"));
+  }
+};
+
+#define REGISTER_GPU(T)                                                                      \
+  REGISTER_KERNEL_BUILDER(Name("Relu").Device(DEVICE_GPU).TypeConstraint<T>("T"), ReluOp<T>); \
+  REGISTER_KERNEL_BUILDER(Name("ReluGrad").Device(DEVICE_GPU).TypeConstraint<T>("T"),        \
+                          ReluGradOp<T>);
+REGISTER_B200_FLOAT_TYPES(REGISTER_GPU)
+#undef REGISTER_GPU
+
+}  // namespace tensorflow

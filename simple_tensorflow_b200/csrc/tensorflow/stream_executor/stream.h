@@ -1,0 +1,103 @@
+// perftools::gputools::Stream / Event / DeviceMemoryBase -- the slice of the reference's
+// StreamExecutor surface that its GPU device and kernels use (stream_executor/stream.h:116,189,
+// 214,1482-1531,1591; device_memory.h:47), implemented as a thin veneer over the C ABI of
+// libb200tf.so (include/b200_ops.h).  No CUDA headers are needed above this line.
+#ifndef B200TF_STREAM_EXECUTOR_STREAM_H_
+#define B200TF_STREAM_EXECUTOR_STREAM_H_
+
+#include <cstddef>
+#include <cstdint>
+
+#include "b200_ops.h"
+
+namespace perftools {
+namespace gputools {
+
+class DeviceMemoryBase {
+ public:
+  explicit DeviceMemoryBase(void* opaque = nullptr, uint64_t size = 0)
+      : opaque_(opaque), size_(size) {}
+  void* opaque() { return opaque_; }
+  const void* opaque() const { return opaque_; }
+  uint64_t size() const { return size_; }
+  bool is_null() const { return opaque_ == nullptr; }
+
+ private:
+  void* opaque_;
+  uint64_t size_;
+};
+
+class Event {
+ public:
+  Event() : handle_(nullptr) {}
+  ~Event() {
+    if (handle_) b200_event_destroy(handle_);
+  }
+  bool Init() { return b200_event_create(&handle_) == 0; }
+  // Event::PollForStatus: kComplete / kPending / kError
+  enum class Status { kComplete, kPending, kError };
+  Status PollForStatus() {
+    const int r = b200_event_query(handle_);
+    return r == 0 ? Status::kComplete : (r == 1 ? Status::kPending : Status::kError);
+  }
+  void* handle() const { return handle_; }
+
+ private:
+  void* handle_;
+};
+
+// Error convention of the reference: Then* return *this and latch failure in ok()
+// (kernels then map !ok() to errors::Internal, e.g. core/kernels/matmul_op.cc:196-201).
+class Stream {
+ public:
+  Stream() : handle_(nullptr), ok_(false), owned_(false) {}
+  // Wrap an existing CUstream (e.g. the framework embedding us already owns one).
+  explicit Stream(void* existing) : handle_(existing), ok_(true), owned_(false) {}
+  ~Stream() {
+    if (owned_ && handle_) b200_stream_destroy(handle_);
+  }
+  Stream& Init() {
+    ok_ = b200_stream_create(&handle_) == 0;
+    owned_ = ok_;
+    return *this;
+  }
+  bool ok() const { return ok_; }
+  void* cuda_stream() const { return handle_; }  // what kernels pass to the b200_* ops
+
+  Stream& ThenMemcpyH2D(DeviceMemoryBase* gpu_dst, const void* host_src, uint64_t size) {
+    return Latch(b200_memcpy_h2d_async(gpu_dst->opaque(), host_src, size, handle_));
+  }
+  Stream& ThenMemcpyD2H(void* host_dst, const DeviceMemoryBase& gpu_src, uint64_t size) {
+    return Latch(b200_memcpy_d2h_async(host_dst, gpu_src.opaque(), size, handle_));
+  }
+  Stream& ThenMemcpyD2D(DeviceMemoryBase* gpu_dst, const DeviceMemoryBase& gpu_src,
+                        uint64_t size) {
+    return Latch(b200_memcpy_d2d_async(gpu_dst->opaque(), gpu_src.opaque(), size, handle_));
+  }
+  Stream& ThenMemZero(DeviceMemoryBase* location, uint64_t size) {
+    return Latch(b200_memset_async(location->opaque(), 0, size, handle_));
+  }
+  Stream& ThenRecordEvent(Event* event) {
+    return Latch(b200_event_record(event->handle(), handle_));
+  }
+  Stream& ThenWaitFor(Event* event) {
+    return Latch(b200_stream_wait_event(handle_, event->handle()));
+  }
+  bool BlockHostUntilDone() {
+    Latch(b200_stream_synchronize(handle_));
+    return ok_;
+  }
+
+ private:
+  Stream& Latch(int rc) {
+    if (rc != 0) ok_ = false;
+    return *this;
+  }
+  void* handle_;
+  bool ok_;
+  bool owned_;
+};
+
+}  // namespace gputools
+}  // namespace perftools
+#endif

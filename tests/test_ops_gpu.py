@@ -400,7 +400,14 @@ def test_apply_gradient_descent_add_n_scale_sum(oracle, rng):
     var = rng.randn(n).astype(np.float32)
     delta = rng.randn(n).astype(np.float32)
     dv, dd = au.dev(var), au.dev(delta)
-    au.call(L.b200_apply_gradient_descent, 1, dv.data_ptr(), 0.01, dd.data_ptr(), n, au.stream())
+    alpha = au.dev(np.array([0.01], np.float32))
+    au.call(L.b200_apply_gradient_descent, 1, dv.data_ptr(), alpha.data_ptr(), dd.data_ptr(), n,
+            au.stream())
+    prod = au.empty((n,))
+    au.call(L.b200_mul, 1, dd.data_ptr(), alpha.data_ptr(), prod.data_ptr(), n, 1, au.stream())
+    np.testing.assert_array_equal(au.host(prod), delta * np.float32(0.01))
+    au.call(L.b200_mul, 1, dd.data_ptr(), dd.data_ptr(), prod.data_ptr(), n, 0, au.stream())
+    np.testing.assert_array_equal(au.host(prod), delta * delta)
     np.testing.assert_allclose(au.host(dv), oracle.apply_gradient_descent(var, 0.01, delta),
                                rtol=1e-6, atol=1e-7)
     import ctypes

@@ -1,0 +1,185 @@
+"""GPU: graphs built through the Python front-end -> C API -> DirectSession-contract executor ->
+OpKernel wrappers -> C ABI kernels, checked against the oracle chained on the CPU.
+Covers BASELINE configs 1-3 at reduced batch (full sizes run in bench.py and in the
+property tests of test_ops_gpu.py)."""
+import numpy as np
+import pytest
+
+from simple_tensorflow_b200 import client, ops as tf
+
+pytestmark = pytest.mark.gpu
+
+
+def test_direct_session_minus_ax_known_answers():
+    # core/common_runtime/direct_session_test.cc:54-137: a=[[3,2],[-1,0]], x=[[1],[1]]; y=a*x=5,-1;
+    # y_neg... we run y = a*x and z = a*y (17, ... uses a*(a*x)): a*[5,-1] = [13,-5]
+    tf.reset_default_graph()
+    a = tf.constant(np.array([[3, 2], [-1, 0]], np.float32))
+    x = tf.placeholder(tf.float32, [2, 1], "x")
+    y = tf.matmul(a, x, name="y")
+    z = tf.matmul(a, y, name="z")
+    with client.Session(tf.get_default_graph()) as sess:
+        yv, zv = sess.run([y, z], {x: np.array([[1], [1]], np.float32)})
+        np.testing.assert_array_equal(yv.ravel(), [5.0, -1.0])
+        np.testing.assert_array_equal(zv.ravel(), [13.0, -5.0])
+        # feeding an intermediate tensor prunes its producer (direct_session_test.cc TestFeed)
+        zv2 = sess.run(z, {y: np.array([[1], [2]], np.float32)})
+        np.testing.assert_array_equal(zv2.ravel(), [7.0, -1.0])
+        st = sess.last_run_stats()
+        assert st["kernels_launched"] >= 1 and st["h2d_bytes"] == 8
+
+
+def test_single_matmul_128_config1(oracle, rng):
+    # BASELINE config 1: single MatMul 128x128 fp32 through the session
+    a = rng.randn(128, 128).astype(np.float32)
+    b = rng.randn(128, 128).astype(np.float32)
+    tf.reset_default_graph()
+    pa, pb = tf.placeholder(tf.float32, [128, 128]), tf.placeholder(tf.float32, [128, 128])
+    c = tf.matmul(pa, pb)
+    with client.Session(tf.get_default_graph()) as sess:
+        got = sess.run(c, {pa: a, pb: b})
+    ref = oracle.matmul(a, b)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-3
+
+
+def _mlp_reference(oracle, x, labels, ws, bs, lr):
+    acts, pres = [x], []
+    for i, (w, b) in enumerate(zip(ws, bs)):
+        pre = oracle.bias_add(oracle.matmul(acts[-1], w), b)
+        pres.append(pre)
+        acts.append(oracle.relu(pre) if i < len(ws) - 1 else pre)
+    lvec, bp = oracle.softmax_xent(acts[-1], labels)
+    g = bp / np.float32(x.shape[0])
+    new_ws, new_bs = [None] * len(ws), [None] * len(ws)
+    for i in reversed(range(len(ws))):
+        new_bs[i] = oracle.apply_gradient_descent(bs[i], lr, oracle.bias_add_grad(g))
+        new_ws[i] = oracle.apply_gradient_descent(ws[i], lr, oracle.matmul(acts[i], g, True, False))
+        if i > 0:
+            g = oracle.relu_grad(oracle.matmul(g, ws[i], False, True), acts[i])
+    return float(lvec.mean()), new_ws, new_bs
+
+
+def test_mlp_training_step_config2_reduced(oracle, rng):
+    B, D = 512, 256
+    x = rng.uniform(-1, 1, (B, D)).astype(np.float32)
+    labels = np.eye(D, dtype=np.float32)[rng.randint(0, D, B)]
+    ws = [(rng.randn(D, D) / np.sqrt(D)).astype(np.float32) for _ in range(3)]
+    bs = [np.full(D, 0.1, np.float32) for _ in range(3)]
+    tf.reset_default_graph()
+    xp, lp = tf.placeholder(tf.float32, [B, D]), tf.placeholder(tf.float32, [B, D])
+    Ws = [tf.Variable(w, name="W%d" % i) for i, w in enumerate(ws)]
+    Bs = [tf.Variable(b, name="b%d" % i) for i, b in enumerate(bs)]
+    h = xp
+    for i in range(3):
+        h = tf.bias_add(tf.matmul(h, Ws[i]), Bs[i])
+        if i < 2:
+            h = tf.relu(h)
+    loss = tf.reduce_mean(tf.softmax_cross_entropy_with_logits(h, lp))
+    train = tf.GradientDescentOptimizer(0.5).minimize(loss)
+    with client.Session(tf.get_default_graph()) as sess:
+        sess.run(tf.global_variables_initializer())
+        got_loss, _ = sess.run([loss, train], {xp: x, lp: labels})
+        got_ws = sess.run([v.ref for v in Ws])
+        got_bs = sess.run([v.ref for v in Bs])
+        loss2 = sess.run(loss, {xp: x, lp: labels})
+    ref_loss, ref_ws, ref_bs = _mlp_reference(oracle, x, labels, ws, bs, 0.5)
+    assert abs(got_loss - ref_loss) < 1e-2 * abs(ref_loss)
+    for g, r in zip(got_ws + got_bs, ref_ws + ref_bs):
+        assert np.abs(g - r).max() / np.abs(r).max() < 1e-2
+    assert loss2 < got_loss  # one SGD step on the same batch reduces the loss
+
+
+def test_lenet_training_step_config3_reduced(oracle, rng):
+    B = 8
+    x = rng.uniform(0, 1, (B, 28, 28, 1)).astype(np.float32)
+    labels = np.eye(10, dtype=np.float32)[rng.randint(0, 10, B)]
+    w1 = (rng.randn(5, 5, 1, 32) * 0.1).astype(np.float32)
+    w2 = (rng.randn(5, 5, 32, 64) * 0.05).astype(np.float32)
+    w3 = (rng.randn(7 * 7 * 64, 128) * 0.02).astype(np.float32)
+    w4 = (rng.randn(128, 10) * 0.1).astype(np.float32)
+    b1, b2 = np.full(32, 0.1, np.float32), np.full(64, 0.1, np.float32)
+    b3, b4 = np.full(128, 0.1, np.float32), np.full(10, 0.1, np.float32)
+    lr = 0.1
+    tf.reset_default_graph()
+    xp, lp = tf.placeholder(tf.float32, [B, 28, 28, 1]), tf.placeholder(tf.float32, [B, 10])
+    V = {n: tf.Variable(v, name=n) for n, v in dict(w1=w1, w2=w2, w3=w3, w4=w4, b1=b1, b2=b2,
+                                                    b3=b3, b4=b4).items()}
+    c1 = tf.relu(tf.bias_add(tf.conv2d(xp, V["w1"], [1, 1, 1, 1], "SAME"), V["b1"]))
+    p1 = tf.max_pool(c1, [1, 2, 2, 1], [1, 2, 2, 1], "SAME")
+    c2 = tf.relu(tf.bias_add(tf.conv2d(p1, V["w2"], [1, 1, 1, 1], "SAME"), V["b2"]))
+    p2 = tf.max_pool(c2, [1, 2, 2, 1], [1, 2, 2, 1], "SAME")
+    flat = tf.reshape(p2, [B, 7 * 7 * 64])
+    f1 = tf.relu(tf.bias_add(tf.matmul(flat, V["w3"]), V["b3"]))
+    logits = tf.bias_add(tf.matmul(f1, V["w4"]), V["b4"])
+    loss = tf.reduce_mean(tf.softmax_cross_entropy_with_logits(logits, lp))
+    train = tf.GradientDescentOptimizer(lr).minimize(loss)
+    with client.Session(tf.get_default_graph()) as sess:
+        sess.run(tf.global_variables_initializer())
+        got_loss, _ = sess.run([loss, train], {xp: x, lp: labels})
+        got = dict(zip(V, sess.run([V[n].ref for n in V])))
+        pred = sess.run(tf.argmax(logits, 1), {xp: x, lp: labels})
+
+    o = oracle
+    a1 = o.relu(o.bias_add(o.conv2d(x, w1, (1, 1), "SAME"), b1))
+    q1 = o.max_pool(a1, (2, 2), (2, 2), "SAME")
+    a2 = o.relu(o.bias_add(o.conv2d(q1, w2, (1, 1), "SAME"), b2))
+    q2 = o.max_pool(a2, (2, 2), (2, 2), "SAME")
+    fl = q2.reshape(B, -1)
+    g1 = o.relu(o.bias_add(o.matmul(fl, w3), b3))
+    lg = o.bias_add(o.matmul(g1, w4), b4)
+    lvec, bp = o.softmax_xent(lg, labels)
+    d = bp / np.float32(B)
+    ref = {"b4": o.apply_gradient_descent(b4, lr, o.bias_add_grad(d)),
+           "w4": o.apply_gradient_descent(w4, lr, o.matmul(g1, d, True, False))}
+    d = o.relu_grad(o.matmul(d, w4, False, True), g1)
+    ref["b3"] = o.apply_gradient_descent(b3, lr, o.bias_add_grad(d))
+    ref["w3"] = o.apply_gradient_descent(w3, lr, o.matmul(fl, d, True, False))
+    d = o.matmul(d, w3, False, True).reshape(q2.shape)
+    d = o.relu_grad(o.max_pool_grad(a2, d, (2, 2), (2, 2), "SAME"), a2)
+    ref["b2"] = o.apply_gradient_descent(b2, lr, o.bias_add_grad(d))
+    ref["w2"] = o.apply_gradient_descent(w2, lr, o.conv2d_backprop_filter(q1, w2.shape, d, (1, 1), "SAME"))
+    d = o.conv2d_backprop_input(q1.shape, w2, d, (1, 1), "SAME")
+    d = o.relu_grad(o.max_pool_grad(a1, d, (2, 2), (2, 2), "SAME"), a1)
+    ref["b1"] = o.apply_gradient_descent(b1, lr, o.bias_add_grad(d))
+    ref["w1"] = o.apply_gradient_descent(w1, lr, o.conv2d_backprop_filter(x, w1.shape, d, (1, 1), "SAME"))
+    assert abs(got_loss - lvec.mean()) < 1e-2 * abs(lvec.mean())
+    for n in V:
+        assert np.abs(got[n] - ref[n]).max() / np.abs(ref[n]).max() < 1e-2, n
+    assert pred.dtype == np.int64 and pred.shape == (B,)
+
+
+def test_session_error_behaviour(rng):
+    tf.reset_default_graph()
+    x = tf.placeholder(tf.float32, [4, 3], "x")
+    w = tf.Variable(np.ones((5, 2), np.float32), name="w")
+    y = tf.matmul(x, w, name="bad_matmul")
+    with client.Session(tf.get_default_graph()) as sess:
+        with pytest.raises(client.OpError) as e:  # placeholder not fed (constant_op.cc)
+            sess.run(y)
+        assert e.value.error_code in (3, 9)
+        with pytest.raises(client.OpError) as e:  # variable read before its initializer ran
+            sess.run(y, {x: np.ones((4, 3), np.float32)})
+        assert e.value.error_code == 9 and "uninitialized" in e.value.message
+        sess.run(tf.global_variables_initializer())
+        with pytest.raises(client.OpError) as e:  # matmul_op.cc:228-232
+            sess.run(y, {x: np.ones((4, 3), np.float32)})
+        assert e.value.error_code == 3 and "Matrix size-incompatible" in e.value.message
+        assert "bad_matmul" in e.value.message
+        # the session stays usable after a failed step
+        w2 = sess.run(w.ref)
+        np.testing.assert_array_equal(w2, np.ones((5, 2), np.float32))
+
+
+def test_bf16_graph_additive_dtype(oracle, rng):
+    # BASELINE config 4's dtype: bf16 storage, fp32 accumulate (additive T extension)
+    B, D = 256, 128
+    x = oracle.truncate_to_bf16(rng.uniform(-1, 1, (B, D)).astype(np.float32))
+    w = oracle.truncate_to_bf16((rng.randn(D, D) / np.sqrt(D)).astype(np.float32))
+    tf.reset_default_graph()
+    xp = tf.placeholder(tf.float32, [B, D])
+    h = tf.relu(tf.matmul(tf.cast(xp, tf.bfloat16), tf.constant(w, tf.bfloat16)))
+    out = tf.cast(h, tf.float32)
+    with client.Session(tf.get_default_graph()) as sess:
+        got = sess.run(out, {xp: x})
+    ref = oracle.relu(oracle.matmul(x, w))
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-2
