@@ -110,6 +110,19 @@ B200_API size_t b200_matmul_workspace_bytes(int dtype, int64_t m, int64_t n, int
 B200_API int b200_matmul(int dtype, const void* a, const void* b, void* c, int64_t m, int64_t n,
                          int64_t k, int transpose_a, int transpose_b, void* workspace,
                          size_t workspace_bytes, void* stream);
+/* MatMul with the element-wise op that follows it in the graph applied in the GEMM epilogue
+ * (accumulator still in registers, one HBM write instead of three round trips):
+ *   bias != NULL                -> BiasAdd   (bias [n], bias_op.cc:62-117 semantics)
+ *   relu != 0                   -> Relu      (relu_op_functor.h:28-38), after the bias
+ *   relu_grad_features != NULL  -> ReluGrad  c = (a.b) * (features > 0), features [m, n]
+ *                                  (relu_op_functor.h:44-57); exclusive with relu
+ * Used by the executor's MatMul+BiasAdd(+Relu) / MatMul+ReluGrad rewrite (the role the
+ * reference gives its GraphOptimizer, direct_session.cc:1051); op boundaries in the user's graph
+ * are unchanged and results are identical to running the ops one by one. */
+B200_API int b200_fused_matmul(int dtype, const void* a, const void* b, void* c, int64_t m,
+                               int64_t n, int64_t k, int transpose_a, int transpose_b,
+                               const void* bias, int relu, const void* relu_grad_features,
+                               void* stream);
 /* Replaces LaunchBatchMatMul<GPUDevice,Scalar>::Launch -> ThenBlasGemmBatchedWithScratch
  * (core/kernels/batch_matmul_op_impl.h:297-363).  x is [batch,m,k] (or [batch,k,m] when adj_x),
  * y is [batch,k,n] (or [batch,n,k] when adj_y); strided, no pointer arrays, no scratch. */

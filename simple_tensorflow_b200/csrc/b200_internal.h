@@ -42,6 +42,11 @@ struct GemmArgs {
   int force_bn;              // 0 = auto
   void* workspace;           // optional device scratch enabling split-K (may be null)
   size_t workspace_bytes;
+  // fused epilogue (tcgen05 path only; all optional)
+  const void* bias;                // + bias[col]
+  bool relu;                       // max(x, 0)
+  const void* relu_grad_features;  // x * (features[row, col] > 0), features [M, N]
+  long long ld_features;
 };
 bool gemm_tcgen05_supported(const GemmArgs& g);
 int gemm_tcgen05(const GemmArgs& g, cudaStream_t stream);

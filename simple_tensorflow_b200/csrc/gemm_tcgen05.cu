@@ -20,12 +20,18 @@
 #include "b200_internal.h"
 
 #include <cuda_bf16.h>
+#include <cstdlib>
+#include <cstring>
 
 namespace b200 {
 
 constexpr int kBM = 128;          // tile rows  (UMMA M, cta_group::1)
 constexpr int kSwizzleBytes = 128;
 constexpr int kGemmThreads = 192;
+// Epilogue staging: 4 warps x 2 buffers x (32 rows x 128 B), 128B-swizzled, drained by TMA stores.
+constexpr int kEpiBufBytes = 32 * kSwizzleBytes;
+constexpr int kEpiStageBytes = 4 * 2 * kEpiBufBytes;  // store staging
+constexpr int kEpiFeatBytes = 4 * 2 * kEpiBufBytes;   // ReluGrad-features staging (TMA loads)
 
 template <typename T>
 struct GemmTraits;
@@ -44,18 +50,24 @@ struct GemmTraits<__nv_bfloat16> {
   static constexpr CUtensorMapDataType kTmaType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
 };
 
-template <int BN>
+// kCtas = 1: one CTA computes a 128 x BN tile (tcgen05 cta_group::1).
+// kCtas = 2: a CTA PAIR (cluster of 2, the two SMs of a TPC) computes a 256 x BN tile with
+//            cta_group::2 MMAs: each CTA stages its own 128 rows of A and its own BN/2 columns of
+//            B, so the per-SM L2->smem operand traffic per FLOP halves compared with kCtas = 1
+//            (the main loop is L2-fabric bound, see profiles/).
+template <int BN, int kCtas>
 constexpr int gemm_stages() {
-  return BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  // stage = A (16 KiB) + B (BN / kCtas rows of 128 B)
+  return (BN / kCtas) >= 256 ? 3 : ((BN / kCtas) >= 128 ? 5 : 6);
 }
-template <int BN>
+template <int BN, int kCtas>
 constexpr size_t gemm_smem_bytes() {
-  // A stage + B stage, + 1 KiB alignment slack + barriers.
-  return static_cast<size_t>(gemm_stages<BN>()) * (kBM * kSwizzleBytes + BN * kSwizzleBytes) +
-         1024 + 256;
+  return static_cast<size_t>(gemm_stages<BN, kCtas>()) *
+             (kBM * kSwizzleBytes + (BN / kCtas) * kSwizzleBytes) +
+         kEpiStageBytes + kEpiFeatBytes + 1024 + 256;
 }
 
-static int plan_splits(long long tiles, int num_kb);
+static int plan_splits(long long tiles, int num_kb, int units);
 
 struct GemmShape {
   int M, N, K, batch;
@@ -64,6 +76,15 @@ struct GemmShape {
   int splits;         // split-K factor (1 = none)
   int kb_per_split;   // K blocks per split
   float* partial;     // [splits][batch][M][N] fp32 partial sums when splits > 1
+  int a_map4d, b_map4d;  // MN-major operand described by a 4-D map: one TMA per stage
+  // epilogue
+  int tma_store;         // 1: stage through smem and TMA-store via tmapC (C or the partial buffer)
+  const void* bias;      // optional fused BiasAdd: + bias[col]      (element type TOut)
+  int relu;              // optional fused Relu:     max(x, 0)
+  const void* relu_grad_features;  // optional fused ReluGrad: x * (features[row, col] > 0)
+  int ld_features;       // leading dimension of features (elements)
+  int feat_tma;          // 1: features are fetched by TMA through tmapF (prefetched, coalesced)
+  int bias_vec;          // 1: bias pointer is 16-byte aligned (vector loads)
 };
 
 __device__ __forceinline__ void store_row32(float* dst, const uint32_t (&v)[32], int ncols,
@@ -105,103 +126,159 @@ __device__ __forceinline__ void store_row32(__nv_bfloat16* dst, const uint32_t (
   }
 }
 
+__device__ __forceinline__ float ld_as_float(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld_as_float(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+template <typename TOut>
+__host__ __device__ constexpr int nvals_max() {
+  return kSwizzleBytes / (int)sizeof(TOut);
+}
+template <typename TOut, int BN>
+__host__ __device__ constexpr int partial_out_iters() {
+  return BN / 32;
+}
+
 // TIn: operand element type (float -> tf32 MMA, bf16 -> f16-kind MMA); TOut: stored type.
-template <typename TIn, typename TOut, bool kAMN, bool kBMN, int BN>
+template <typename TIn, typename TOut, bool kAMN, bool kBMN, int BN, int kCtas>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
-                    const __grid_constant__ CUtensorMap tmapB, TOut* __restrict__ C,
+                    const __grid_constant__ CUtensorMap tmapB,
+                    const __grid_constant__ CUtensorMap tmapC,
+                    const __grid_constant__ CUtensorMap tmapF, TOut* __restrict__ C,
                     GemmShape s) {
   using Tr = GemmTraits<TIn>;
   constexpr int BK = Tr::kBK;
-  constexpr int kStages = gemm_stages<BN>();
+  constexpr int kStages = gemm_stages<BN, kCtas>();
+  constexpr int kTileM = kBM * kCtas;           // rows of the (pair's) output tile
+  constexpr int kBNLocal = BN / kCtas;          // B rows (output columns) staged by this CTA
   constexpr int kABytes = kBM * kSwizzleBytes;  // 16 KiB
-  constexpr int kBBytes = BN * kSwizzleBytes;
+  constexpr int kBBytes = kBNLocal * kSwizzleBytes;
   constexpr int kChunk = kSwizzleBytes / sizeof(TIn);  // MN elements per 128-B swizzle row
   constexpr int kTmemCols = 2 * BN;                    // double-buffered fp32 accumulator
   static_assert(kTmemCols <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM cols");
-  constexpr uint32_t kIdesc = make_idesc(Tr::kFormat, kAMN, kBMN, kBM, BN);
+  constexpr uint32_t kIdesc = make_idesc(Tr::kFormat, kAMN, kBMN, kTileM, BN);
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   uint8_t* smA = smem;
   uint8_t* smB = smem + kStages * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kABytes + kBBytes));
-  uint64_t* full_bar = bars;                    // [kStages]
+  uint8_t* smEpi = smem + kStages * (kABytes + kBBytes);  // 1 KiB aligned (stages are KiB multiples)
+  uint8_t* smFeat = smEpi + kEpiStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (kABytes + kBBytes) +
+                                               kEpiStageBytes + kEpiFeatBytes);
+  uint64_t* full_bar = bars;                    // [kStages]  (kCtas = 2: the leader's is used)
   uint64_t* empty_bar = bars + kStages;         // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;     // [2]
-  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]  (kCtas = 2: the leader's is used)
+  uint64_t* feat_bar = bars + 2 * kStages + 4;    // [4 warps][2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 12);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0;
+  const bool leader = cta_rank == 0;
+  const int unit = blockIdx.x / kCtas;        // tile scheduler unit: a CTA or a CTA pair
+  const int num_units = gridDim.x / kCtas;
 
-  const int tiles_m = (s.M + kBM - 1) / kBM;
+  const int tiles_m = (s.M + kTileM - 1) / kTileM;
   const int tiles_n = (s.N + BN - 1) / BN;
   const int tiles_per_batch = tiles_m * tiles_n;
   const int num_tiles = tiles_per_batch * s.batch;
   const int num_kb = (s.K + BK - 1) / BK;
-  // Work item = (split, tile): consecutive CTAs take different tiles of the same K split.
+  // Work item = (split, tile): consecutive units take different tiles of the same K split.
   const int num_work = num_tiles * s.splits;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmapA);
     tma_prefetch_desc(&tmapB);
+    if (s.tma_store) tma_prefetch_desc(&tmapC);
+    if (s.feat_tma) tma_prefetch_desc(&tmapF);
   }
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < kStages; ++i) {
-        mbar_init(&full_bar[i], 1);
+        mbar_init(&full_bar[i], kCtas);  // one producer arrive per CTA of the pair
         mbar_init(&empty_bar[i], 1);
       }
       for (int i = 0; i < 2; ++i) {
         mbar_init(&tfull_bar[i], 1);
-        mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+        mbar_init(&tempty_bar[i], 4 * kCtas);  // one arrive per epilogue warp (of both CTAs)
       }
+      for (int i = 0; i < 8; ++i) mbar_init(&feat_bar[i], 1);
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc<kTmemCols>(tmem_slot);
+    if (kCtas == 2)
+      tmem_alloc_2cta<kTmemCols>(tmem_slot);
+    else
+      tmem_alloc<kTmemCols>(tmem_slot);
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2)
+    cluster_sync_all();  // peer barriers must be initialised before any remote arrive / TMA credit
+  else
+    __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
+    // ===================== TMA producer (one per CTA) =====================
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      for (int work = unit; work < num_work; work += num_units) {
         const int split = work / num_tiles;
         const int tile = work - split * num_tiles;
         const int b = tile / tiles_per_batch;
         const int t = tile - b * tiles_per_batch;
-        const int m0 = (t % tiles_m) * kBM;
-        const int n0 = (t / tiles_m) * BN;
+        const int m0 = (t % tiles_m) * kTileM + (int)cta_rank * kBM;
+        const int n0 = (t / tiles_m) * BN + (int)cta_rank * kBNLocal;
         const int kb0 = split * s.kb_per_split;
         const int kb1 = min(kb0 + s.kb_per_split, num_kb);
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_expect_tx(&full_bar[stage], kABytes + kBBytes);
+          if (kCtas == 1) {
+            mbar_expect_tx(&full_bar[stage], kABytes + kBBytes);
+          } else if (leader) {
+            mbar_expect_tx(&full_bar[stage], 2 * (kABytes + kBBytes));  // both CTAs' bytes
+          } else {
+            mbar_arrive_remote(&full_bar[stage], 0);
+          }
           const int k0 = kb * BK;
           uint8_t* a_dst = smA + stage * kABytes;
           uint8_t* b_dst = smB + stage * kBBytes;
+          auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
+            if (kCtas == 2)
+              tma_load_3d_2cta(dst, map, &full_bar[stage], c0, c1, b);
+            else
+              tma_load_3d(dst, map, &full_bar[stage], c0, c1, b);
+          };
+          // MN-major tile = [chunks][BK rows][128 B]; a 4-D map (128B, K, chunk, batch) fetches
+          // all chunks with ONE instruction (TMA issue rate matters: 8 loads/stage cost ~30%).
+          auto load4 = [&](void* dst, const CUtensorMap* map, int mn0) {
+            if (kCtas == 2)
+              tma_load_4d_2cta(dst, map, &full_bar[stage], 0, k0, mn0 / kChunk, b);
+            else
+              tma_load_4d(dst, map, &full_bar[stage], 0, k0, mn0 / kChunk, b);
+          };
           if (!kAMN) {
-            tma_load_3d(a_dst, &tmapA, &full_bar[stage], k0, m0, b);
+            load(a_dst, &tmapA, k0, m0);
+          } else if (s.a_map4d) {
+            load4(a_dst, &tmapA, m0);
           } else {
 #pragma unroll
             for (int c = 0; c < kBM / kChunk; ++c)
-              tma_load_3d(a_dst + c * (BK * kSwizzleBytes), &tmapA, &full_bar[stage],
-                          m0 + c * kChunk, k0, b);
+              load(a_dst + c * (BK * kSwizzleBytes), &tmapA, m0 + c * kChunk, k0);
           }
           if (!kBMN) {
-            tma_load_3d(b_dst, &tmapB, &full_bar[stage], k0, n0, b);
+            load(b_dst, &tmapB, k0, n0);
+          } else if (s.b_map4d) {
+            load4(b_dst, &tmapB, n0);
           } else {
 #pragma unroll
-            for (int c = 0; c < BN / kChunk; ++c)
-              tma_load_3d(b_dst + c * (BK * kSwizzleBytes), &tmapB, &full_bar[stage],
-                          n0 + c * kChunk, k0, b);
+            for (int c = 0; c < kBNLocal / kChunk; ++c)
+              load(b_dst + c * (BK * kSwizzleBytes), &tmapB, n0 + c * kChunk, k0);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -211,11 +288,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (leader CTA only when paired) =====================
+    if (lane == 0 && leader) {
       uint32_t stage = 0, phase = 0;
       uint32_t acc = 0, acc_phase = 0;
-      for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+      for (int work = unit; work < num_work; work += num_units) {
         const int split = work / num_tiles;
         const int kb0 = split * s.kb_per_split;
         const int kb1 = min(kb0 + s.kb_per_split, num_kb);
@@ -242,18 +319,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
             const uint64_t bdesc = kBMN ? make_smem_desc_sw128(b_addr + b_off, BK * kSwizzleBytes,
                                                                kMn32 ? 512 : 1024, kMn32 ? 1 : 2)
                                         : make_smem_desc_sw128(b_addr + b_off, 16, 1024);
-            if (sizeof(TIn) == 4)
-              umma_tf32(d_tmem, adesc, bdesc, kIdesc, ((kb - kb0) | k) != 0);
-            else
-              umma_f16(d_tmem, adesc, bdesc, kIdesc, ((kb - kb0) | k) != 0);
+            const uint32_t accum = ((kb - kb0) | k) != 0;
+            if (kCtas == 2) {
+              if (sizeof(TIn) == 4)
+                umma_tf32_2cta(d_tmem, adesc, bdesc, kIdesc, accum);
+              else
+                umma_f16_2cta(d_tmem, adesc, bdesc, kIdesc, accum);
+            } else {
+              if (sizeof(TIn) == 4)
+                umma_tf32(d_tmem, adesc, bdesc, kIdesc, accum);
+              else
+                umma_f16(d_tmem, adesc, bdesc, kIdesc, accum);
+            }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          // frees the smem slot (in both CTAs) once these MMAs retire
+          if (kCtas == 2)
+            umma_commit_2cta(&empty_bar[stage]);
+          else
+            umma_commit(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue warps (of both CTAs)
+        if (kCtas == 2)
+          umma_commit_2cta(&tfull_bar[acc]);
+        else
+          umma_commit(&tfull_bar[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -262,55 +355,235 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
     }
   } else {
     // ===================== epilogue warps =====================
+    // TMEM -> registers (thread = output row) -> [bias / relu / relu-grad] -> 128B-swizzled smem
+    // staging -> TMA store (coalesced, clips ragged edges).  Direct global stores remain as the
+    // fallback for outputs TMA cannot address.
+    constexpr int kEpiCols = kSwizzleBytes / (int)sizeof(TOut);  // columns per 128-B staged row
+    constexpr int kLdPerIter = kEpiCols / 32;                    // tcgen05.ld x32 per iteration
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
     uint32_t acc = 0, acc_phase = 0;
+    uint32_t ebuf = 0, stores_in_flight = 0;
+    uint8_t* my_stage = smEpi + quad * 2 * kEpiBufBytes;
+    uint8_t* my_feat = smFeat + quad * 2 * kEpiBufBytes;
+    uint64_t* my_fbar = feat_bar + quad * 2;
+    uint32_t feat_issued = 0, feat_used = 0;  // running chunk counters (buffer = n & 1)
+    const bool feat_on = s.relu_grad_features != nullptr && s.feat_tma && s.splits == 1;
+    // ReluGrad features do not depend on the MMA: fetch them (coalesced, via TMA) ahead of use.
+    auto issue_feat = [&](int col, int row0f, int bidx) {
+      if (lane == 0) {
+        uint64_t* fb = &my_fbar[feat_issued & 1];
+        mbar_expect_tx(fb, kEpiBufBytes);
+        tma_load_3d(my_feat + (feat_issued & 1) * kEpiBufBytes, &tmapF, fb, col, row0f, bidx);
+      }
+      ++feat_issued;
+    };
     const bool vec_ok = (s.ldc % (16 / (int)sizeof(TOut)) == 0) &&
                         (s.strideC % (16 / (int)sizeof(TOut)) == 0) &&
                         ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
-    for (int work = blockIdx.x; work < num_work; work += gridDim.x) {
+    for (int work = unit; work < num_work; work += num_units) {
       const int split = work / num_tiles;
       const int tile = work - split * num_tiles;
       const int b = tile / tiles_per_batch;
       const int t = tile - b * tiles_per_batch;
-      const int m0 = (t % tiles_m) * kBM;
+      const int m0 = (t % tiles_m) * kTileM + (int)cta_rank * kBM;
       const int n0 = (t / tiles_m) * BN;
+      const int row0 = m0 + quad * 32;
+      if (feat_on) {  // chunks 0 and 1 of this tile, before waiting for the accumulator
+        issue_feat(n0, row0, b);
+        if (n0 + kEpiCols < s.N && BN > kEpiCols) issue_feat(n0 + kEpiCols, row0, b);
+      }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const int row = m0 + quad * 32 + lane;
+      const int row = row0 + lane;
+      const bool partial_out = s.splits > 1;
       TOut* crow = C + (long long)b * s.strideC + (long long)row * s.ldc;
       // split-K: fp32 partial tile, dense [split][batch][M][N]
       float* prow = s.partial + (((long long)split * s.batch + b) * s.M + row) * (long long)s.N;
       const bool pvec = (s.N & 3) == 0;
+      constexpr int kIters = partial_out_iters<TOut, BN>();
+      (void)kIters;
+      const int cols_per_iter = partial_out ? 32 : kEpiCols;
+      const int iters = BN / cols_per_iter;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * 32, v);
-        tmem_ld_wait();
-        const int col = n0 + c * 32;
-        int ncols = s.N - col;
-        ncols = ncols > 32 ? 32 : ncols;
-        if (row < s.M && ncols > 0) {
-          if (s.splits > 1)
-            store_row32(prow + col, v, ncols, pvec);
-          else
-            store_row32(crow + col, v, ncols, vec_ok);
+      for (int c = 0; c < iters; ++c) {
+        const int col = n0 + c * cols_per_iter;
+        if (col >= s.N) break;  // warp-uniform
+        uint32_t v[32 * kLdPerIter];
+        {
+          uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+          tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * cols_per_iter,
+                        v0);
+          if (kLdPerIter == 2 && !partial_out) {
+            uint32_t(&v1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32 * (kLdPerIter - 1)]);
+            tmem_ld_32x32(
+                tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN + c * cols_per_iter + 32, v1);
+          }
+          tmem_ld_wait();
+        }
+        const int nvals = partial_out ? 32 : kEpiCols;
+        // ---- fused element-wise tail (full-precision, before any rounding)
+        if (!partial_out) {
+          if (s.bias != nullptr) {
+            const TOut* bp = static_cast<const TOut*>(s.bias) + col;
+            if (s.bias_vec && col + kEpiCols <= s.N) {
+              // every lane reads the same 128 bytes: 8 broadcast 16-byte loads
+#pragma unroll
+              for (int q4 = 0; q4 < 8; ++q4) {
+                const uint4 bw = __ldg(reinterpret_cast<const uint4*>(bp) + q4);
+                const uint32_t bwv[4] = {bw.x, bw.y, bw.z, bw.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  if (sizeof(TOut) == 4) {
+                    const int j = q4 * 4 + e;
+                    v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(bwv[e]));
+                  } else {
+                    const int j = (q4 * 4 + e) * 2;
+                    v[j % (32 * kLdPerIter)] = __float_as_uint(
+                        __uint_as_float(v[j % (32 * kLdPerIter)]) + __uint_as_float(bwv[e] << 16));
+                    v[(j + 1) % (32 * kLdPerIter)] =
+                        __float_as_uint(__uint_as_float(v[(j + 1) % (32 * kLdPerIter)]) +
+                                        __uint_as_float(bwv[e] & 0xFFFF0000u));
+                  }
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < kEpiCols; ++j)
+                if (col + j < s.N)
+                  v[j] = __float_as_uint(__uint_as_float(v[j]) + ld_as_float(bp + j));
+            }
+          }
+          if (s.relu) {
+#pragma unroll
+            for (int j = 0; j < kEpiCols; ++j) {
+              const float f = __uint_as_float(v[j]);
+              v[j] = __float_as_uint(f > 0.f ? f : 0.f);
+            }
+          }
+          if (feat_on) {
+            // this chunk's features were staged by TMA as [32 rows][128 B], 128B-swizzled
+            mbar_wait(&my_fbar[feat_used & 1], (feat_used >> 1) & 1);
+            const uint32_t fbase =
+                smem_u32(my_feat + (feat_used & 1) * kEpiBufBytes) + lane * kSwizzleBytes;
+#pragma unroll
+            for (int q4 = 0; q4 < 8; ++q4) {
+              uint32_t f0, f1, f2, f3;
+              asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(f0), "=r"(f1), "=r"(f2), "=r"(f3)
+                           : "r"(fbase + (uint32_t)((q4 ^ (lane & 7)) << 4)));
+              const uint32_t fw[4] = {f0, f1, f2, f3};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                if (sizeof(TOut) == 4) {
+                  const int j = q4 * 4 + e;
+                  const float g = __uint_as_float(v[j]);
+                  v[j] = __float_as_uint(__uint_as_float(fw[e]) > 0.f ? g : g * 0.f);
+                } else {
+                  const int j0 = ((q4 * 4 + e) * 2) % (32 * kLdPerIter);
+                  const int j1 = ((q4 * 4 + e) * 2 + 1) % (32 * kLdPerIter);
+                  const float g0 = __uint_as_float(v[j0]), g1 = __uint_as_float(v[j1]);
+                  v[j0] = __float_as_uint(__uint_as_float(fw[e] << 16) > 0.f ? g0 : g0 * 0.f);
+                  v[j1] = __float_as_uint(__uint_as_float(fw[e] & 0xFFFF0000u) > 0.f ? g1
+                                                                                      : g1 * 0.f);
+                }
+              }
+            }
+            ++feat_used;
+            __syncwarp();  // every lane has read the buffer: it may be refilled
+            const int next_col = col + 2 * kEpiCols;
+            if (c + 2 < iters && next_col < s.N) issue_feat(next_col, row0, b);
+          } else if (s.relu_grad_features != nullptr && row < s.M) {
+            const TOut* fp = static_cast<const TOut*>(s.relu_grad_features) +
+                             (long long)row * s.ld_features + col;
+#pragma unroll
+            for (int j = 0; j < kEpiCols; ++j)
+              if (col + j < s.N) {
+                const float g = __uint_as_float(v[j]);
+                v[j] = __float_as_uint(ld_as_float(fp + j) > 0.f ? g : g * 0.f);
+              }
+          }
+        }
+        if (s.tma_store) {
+          // pack to the output type: 32 x 32-bit words = one 128-byte staged row per thread
+          uint32_t w[32];
+          if (sizeof(TOut) == 4 || partial_out) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j] = v[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              __nv_bfloat162 h = __floats2bfloat162_rn(__uint_as_float(v[(2 * j) % nvals_max<TOut>()]),
+                                                       __uint_as_float(v[(2 * j + 1) % nvals_max<TOut>()]));
+              w[j] = *reinterpret_cast<uint32_t*>(&h);
+            }
+          }
+          // the staging buffer we are about to overwrite must have been read by its TMA store
+          if (stores_in_flight >= 2) {
+            if (lane == 0) tma_store_wait_read<1>();
+            __syncwarp();
+          }
+          uint8_t* buf = my_stage + ebuf * kEpiBufBytes;
+          const uint32_t rbase = smem_u32(buf) + lane * kSwizzleBytes;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const uint32_t addr = rbase + (uint32_t)((j ^ (lane & 7)) << 4);  // 128B swizzle
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w[4 * j]),
+                         "r"(w[4 * j + 1]), "r"(w[4 * j + 2]), "r"(w[4 * j + 3])
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&tmapC, buf, col, row0, partial_out ? split * s.batch + b : b);
+            tma_store_commit();
+          }
+          ++stores_in_flight;
+          ebuf ^= 1;
+        } else {
+          int ncols = s.N - col;
+          ncols = ncols > nvals ? nvals : ncols;
+          if (row < s.M) {
+            if (partial_out) {
+              uint32_t(&v0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[0]);
+              store_row32(prow + col, v0, ncols, pvec);
+            } else {
+#pragma unroll
+              for (int h = 0; h < kLdPerIter; ++h) {
+                uint32_t(&vh)[32] = *reinterpret_cast<uint32_t(*)[32]>(&v[32 * h]);
+                const int nc = ncols - 32 * h;
+                if (nc > 0) store_row32(crow + col + 32 * h, vh, nc > 32 ? 32 : nc, vec_ok);
+              }
+            }
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (kCtas == 2 && !leader)
+          mbar_arrive_remote(&tempty_bar[acc], 0);  // the leader's MMA thread waits on it
+        else
+          mbar_arrive(&tempty_bar[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
+    if (s.tma_store && lane == 0) tma_store_wait<0>();  // global writes done before exit
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kCtas == 2)
+    cluster_sync_all();  // no CTA may exit (or free TMEM) while its peer can still signal it
+  else
+    __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<kTmemCols>(tmem_base);
+    if (kCtas == 2)
+      tmem_dealloc_2cta<kTmemCols>(tmem_base);
+    else
+      tmem_dealloc<kTmemCols>(tmem_base);
   }
 }
 
@@ -379,32 +652,82 @@ static int encode_operand_map(CUtensorMap* map, CUtensorMapDataType dt, size_t e
   return B200_OK;
 }
 
-template <typename TIn, typename TOut, bool kAMN, bool kBMN, int BN>
+// MN-major operand stored [K, MN] (ld elements per row), MN % chunk == 0: 4-D view
+// (chunk, K, MN / chunk, batch) so that one box {chunk, BK, nchunks, 1} lands in smem as
+// [nchunks][BK][128 B] -- the UMMA MN-major tile layout.
+static bool encode_mn_major_map4d(CUtensorMap* map, CUtensorMapDataType dt, size_t esize,
+                                  const void* ptr, long long K, long long MN, long long ld,
+                                  long long batch, long long batch_stride, int chunk, int bk,
+                                  int nchunks) {
+  if (MN % chunk != 0) return false;
+  cuuint64_t gdim[4] = {(cuuint64_t)chunk, (cuuint64_t)K, (cuuint64_t)(MN / chunk),
+                        (cuuint64_t)batch};
+  cuuint64_t gstride[3] = {(cuuint64_t)(ld * esize), (cuuint64_t)(chunk * esize),
+                           (cuuint64_t)((batch > 1 ? batch_stride : K * ld) * esize)};
+  cuuint32_t box[4] = {(cuuint32_t)chunk, (cuuint32_t)bk, (cuuint32_t)nchunks, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return driver().cuTensorMapEncodeTiled(
+             map, dt, 4, const_cast<void*>(ptr), gdim, gstride, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE,
+             esize == 4 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// Output (or split-K partial) tensor map for the epilogue's TMA stores: box = 128 B x 32 rows.
+static bool encode_store_map(CUtensorMap* map, CUtensorMapDataType dt, size_t esize, void* ptr,
+                             long long rows, long long cols, long long ld, long long batches,
+                             long long batch_stride) {
+  if ((ld * esize) % 16 || (batch_stride * esize) % 16 || (reinterpret_cast<uintptr_t>(ptr) & 15))
+    return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batches};
+  cuuint64_t gstride[2] = {(cuuint64_t)(ld * esize),
+                           (cuuint64_t)((batches > 1 ? batch_stride : rows * ld) * esize)};
+  cuuint32_t box[3] = {(cuuint32_t)(kSwizzleBytes / esize), 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return driver().cuTensorMapEncodeTiled(map, dt, 3, ptr, gdim, gstride, box, estr,
+                                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                         CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <typename TIn, typename TOut, bool kAMN, bool kBMN, int BN, int kCtas>
 static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   using Tr = GemmTraits<TIn>;
   constexpr int kChunk = kSwizzleBytes / sizeof(TIn);
+  constexpr int kTileM = kBM * kCtas;
+  constexpr int kBNLocal = BN / kCtas;
   CUtensorMap ma, mb;
   int rc;
-  // A: logical [M,K]; stored [M,K] (K-major) or [K,M] (MN-major).
+  // A: logical [M,K]; stored [M,K] (K-major) or [K,M] (MN-major).  Box = one CTA's 128 rows.
+  static const bool no_map4d = getenv("B200TF_GEMM_NO_MAP4D") != nullptr;
+  bool a4 = false, b4 = false;
   if (!kAMN)
     rc = encode_operand_map(&ma, Tr::kTmaType, sizeof(TIn), g.a, g.M, g.K, g.lda, g.batch,
                             g.strideA, Tr::kBK, kBM, false);
+  else if (!no_map4d &&
+           (a4 = encode_mn_major_map4d(&ma, Tr::kTmaType, sizeof(TIn), g.a, g.K, g.M, g.lda,
+                                       g.batch, g.strideA, kChunk, Tr::kBK, kBM / kChunk)))
+    rc = B200_OK;
   else
     rc = encode_operand_map(&ma, Tr::kTmaType, sizeof(TIn), g.a, g.K, g.M, g.lda, g.batch,
                             g.strideA, kChunk, Tr::kBK, true);
   if (rc) return rc;
-  // B: logical [K,N]; stored [K,N] (MN-major) or [N,K] (K-major).
+  // B: logical [K,N]; stored [K,N] (MN-major) or [N,K] (K-major).  Box = one CTA's BN/kCtas cols.
   if (!kBMN)
     rc = encode_operand_map(&mb, Tr::kTmaType, sizeof(TIn), g.b, g.N, g.K, g.ldb, g.batch,
-                            g.strideB, Tr::kBK, BN, false);
+                            g.strideB, Tr::kBK, kBNLocal, false);
+  else if (!no_map4d &&
+           (b4 = encode_mn_major_map4d(&mb, Tr::kTmaType, sizeof(TIn), g.b, g.K, g.N, g.ldb,
+                                       g.batch, g.strideB, kChunk, Tr::kBK, kBNLocal / kChunk)))
+    rc = B200_OK;
   else
     rc = encode_operand_map(&mb, Tr::kTmaType, sizeof(TIn), g.b, g.K, g.N, g.ldb, g.batch,
                             g.strideB, kChunk, Tr::kBK, true);
   if (rc) return rc;
 
-  auto kern = gemm_tcgen05_kernel<TIn, TOut, kAMN, kBMN, BN>;
+  auto kern = gemm_tcgen05_kernel<TIn, TOut, kAMN, kBMN, BN, kCtas>;
   static bool attr_set = false;  // per template instantiation
-  constexpr size_t smem = gemm_smem_bytes<BN>();
+  constexpr size_t smem = gemm_smem_bytes<BN, kCtas>();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
@@ -421,12 +744,14 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   s.batch = (int)g.batch;
   s.ldc = (int)g.ldc;
   s.strideC = g.strideC;
-  const long long tiles = ((g.M + kBM - 1) / kBM) * ((g.N + BN - 1) / BN) * g.batch;
+  const long long tiles = ((g.M + kTileM - 1) / kTileM) * ((g.N + BN - 1) / BN) * g.batch;
+  const int units = sm_count() / kCtas;  // schedulable CTAs or CTA pairs
   // split-K when the output tiles alone cannot fill the SMs and scratch was provided
   const int num_kb = (int)((g.K + Tr::kBK - 1) / Tr::kBK);
   int splits = 1;
-  if (g.workspace) {
-    splits = plan_splits(tiles, num_kb);
+  const bool fused = g.bias || g.relu || g.relu_grad_features;
+  if (g.workspace && !fused) {  // a fused tail needs the complete sum in one epilogue
+    splits = plan_splits(tiles, num_kb, units);
     while (splits > 1 &&
            (size_t)splits * g.batch * g.M * g.N * sizeof(float) > g.workspace_bytes)
       --splits;
@@ -436,11 +761,59 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   splits = (num_kb + s.kb_per_split - 1) / s.kb_per_split;  // no empty split
   s.splits = splits;
   s.partial = static_cast<float*>(g.workspace);
+  s.a_map4d = a4 ? 1 : 0;
+  s.b_map4d = b4 ? 1 : 0;
+  s.bias = g.bias;
+  s.relu = g.relu ? 1 : 0;
+  s.relu_grad_features = g.relu_grad_features;
+  s.ld_features = (int)g.ld_features;
+  CUtensorMap mc;
+  memset(&mc, 0, sizeof(mc));
+  static const bool no_tma_store = getenv("B200TF_GEMM_DIRECT_STORE") != nullptr;
+  if (no_tma_store)
+    s.tma_store = 0;
+  else if (splits > 1)
+    s.tma_store = encode_store_map(&mc, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, g.workspace, g.M, g.N,
+                                   g.N, (long long)splits * g.batch, g.M * g.N);
+  else
+    s.tma_store = encode_store_map(&mc, sizeof(TOut) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                          : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                                   sizeof(TOut), g.c, g.M, g.N, g.ldc, g.batch, g.strideC);
+  CUtensorMap mf;
+  memset(&mf, 0, sizeof(mf));
+  s.feat_tma = 0;
+  if (g.relu_grad_features && splits == 1)
+    s.feat_tma = encode_store_map(&mf, sizeof(TOut) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                          : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                                  sizeof(TOut), const_cast<void*>(g.relu_grad_features), g.M, g.N,
+                                  g.ld_features, 1, g.M * g.ld_features);
+  s.bias_vec = g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0;
   const long long work = tiles * splits;
-  const int grid = (int)(work < sm_count() ? work : sm_count());
+  const int grid_units = (int)(work < units ? work : units);
   const bool prof = profile_enabled();
   if (prof) profile_gemm_launch_begin(stream);
-  kern<<<grid, kGemmThreads, smem, stream>>>(ma, mb, static_cast<TOut*>(g.c), s);
+  if (kCtas == 1) {
+    kern<<<grid_units, kGemmThreads, smem, stream>>>(ma, mb, mc, mf, static_cast<TOut*>(g.c), s);
+  } else {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid_units * kCtas);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mf, static_cast<TOut*>(g.c), s);
+    if (e != cudaSuccess) {
+      set_last_error("gemm_tcgen05 (cta pair) launch: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return B200_INTERNAL;
+    }
+  }
   if (prof) profile_gemm_launch_end(stream, 2.0 * (double)g.M * (double)g.N * (double)g.K * g.batch);
   note_launch();
   if (splits > 1) {
@@ -452,44 +825,63 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   return check_launch("gemm_tcgen05");
 }
 
-template <typename TIn, typename TOut, int BN>
+template <typename TIn, typename TOut, int BN, int kCtas>
 static int dispatch_major(const GemmArgs& g, cudaStream_t stream) {
-  if (!g.a_mn_major && !g.b_mn_major) return launch_gemm<TIn, TOut, false, false, BN>(g, stream);
-  if (!g.a_mn_major && g.b_mn_major) return launch_gemm<TIn, TOut, false, true, BN>(g, stream);
-  if (g.a_mn_major && !g.b_mn_major) return launch_gemm<TIn, TOut, true, false, BN>(g, stream);
-  return launch_gemm<TIn, TOut, true, true, BN>(g, stream);
+  if (!g.a_mn_major && !g.b_mn_major)
+    return launch_gemm<TIn, TOut, false, false, BN, kCtas>(g, stream);
+  if (!g.a_mn_major && g.b_mn_major)
+    return launch_gemm<TIn, TOut, false, true, BN, kCtas>(g, stream);
+  if (g.a_mn_major && !g.b_mn_major)
+    return launch_gemm<TIn, TOut, true, false, BN, kCtas>(g, stream);
+  return launch_gemm<TIn, TOut, true, true, BN, kCtas>(g, stream);
 }
 
-// Split-K plan shared by the launcher and gemm_workspace_bytes(): how many K splits a 128-wide
-// tiling would use for this shape (1 = none).
-static int plan_splits(long long tiles, int num_kb) {
-  if (tiles * 2 > sm_count() || num_kb < 8) return 1;
-  long long splits = sm_count() / tiles;
+// Split-K plan shared by the launcher and gemm_workspace_bytes(): how many K splits a tiling
+// with `tiles` output tiles would use on `units` schedulable CTAs / CTA pairs (1 = none).
+static int plan_splits(long long tiles, int num_kb, int units) {
+  if (tiles * 2 > units || num_kb < 8) return 1;
+  long long splits = units / tiles;
   if (splits > num_kb / 4) splits = num_kb / 4;  // >= 4 K blocks per split
   if (splits > 16) splits = 16;
   return splits < 1 ? 1 : (int)splits;
 }
 
-size_t gemm_workspace_bytes(int dtype, long long M, long long N, long long K, long long batch) {
-  if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return 0;
-  const int bk = dtype == B200_DT_FLOAT ? GemmTraits<float>::kBK : GemmTraits<__nv_bfloat16>::kBK;
-  const int bn = N <= 64 ? 64 : 128;
-  const long long tiles = ((M + kBM - 1) / kBM) * ((N + bn - 1) / bn) * batch;
-  const int splits = plan_splits(tiles, (int)((K + bk - 1) / bk));
-  return splits > 1 ? (size_t)splits * batch * M * N * sizeof(float) : 0;
+// Tile configuration.  CTA pairs (256 x BN tiles, cta_group::2) whenever the problem has at least
+// one full pair tile of rows: they halve the L2->smem operand traffic per FLOP, which is what
+// bounds the main loop.  Otherwise single CTAs with 128 x {128, 64} tiles.
+struct TileConfig {
+  int ctas, bn;
+};
+static TileConfig choose_config(const GemmArgs& g) {
+  if (g.force_bn == 64) return {1, 64};
+  if (g.force_bn == 128) return {1, 128};
+  if (g.force_bn == 2128) return {2, 128};
+  if (g.force_bn == 2256) return {2, 256};
+  const char* env = getenv("B200TF_GEMM_CTAS");
+  const bool allow_pairs = !(env && env[0] == '1');
+  if (allow_pairs && g.M >= 256 && g.N >= 128) return {2, g.N >= 256 ? 256 : 128};
+  if (g.N <= 64) return {1, 64};
+  const long long t128 = ((g.M + kBM - 1) / kBM) * ((g.N + 127) / 128) * g.batch;
+  if (t128 >= sm_count()) return {1, 128};
+  const int bk = g.dtype == B200_DT_FLOAT ? GemmTraits<float>::kBK : GemmTraits<__nv_bfloat16>::kBK;
+  if (g.workspace && plan_splits(t128, (int)((g.K + bk - 1) / bk), sm_count()) > 1) return {1, 128};
+  return {1, 64};
 }
 
-// Tile-N choice: fill the 148 SMs.  128x128 tiles; when those cannot fill the machine either
-// split K (scratch available) or fall back to 128x64 tiles.
-static int choose_bn(const GemmArgs& g) {
-  if (g.force_bn == 64 || g.force_bn == 128 || g.force_bn == 256) return g.force_bn;
-  if (g.N <= 64) return 64;
-  const long long tm = (g.M + kBM - 1) / kBM;
-  const long long t128 = tm * ((g.N + 127) / 128) * g.batch;
-  if (t128 >= sm_count()) return 128;
-  const int bk = g.dtype == B200_DT_FLOAT ? GemmTraits<float>::kBK : GemmTraits<__nv_bfloat16>::kBK;
-  if (g.workspace && plan_splits(t128, (int)((g.K + bk - 1) / bk)) > 1) return 128;
-  return 64;
+size_t gemm_workspace_bytes(int dtype, long long M, long long N, long long K, long long batch) {
+  if (M <= 0 || N <= 0 || K <= 0 || batch <= 0) return 0;
+  GemmArgs g{};
+  g.dtype = dtype;
+  g.M = M;
+  g.N = N;
+  g.K = K;
+  g.batch = batch;
+  g.workspace = reinterpret_cast<void*>(1);  // "scratch will be available"
+  const TileConfig c = choose_config(g);
+  const int bk = dtype == B200_DT_FLOAT ? GemmTraits<float>::kBK : GemmTraits<__nv_bfloat16>::kBK;
+  const long long tiles = ((M + kBM * c.ctas - 1) / (kBM * c.ctas)) * ((N + c.bn - 1) / c.bn) * batch;
+  const int splits = plan_splits(tiles, (int)((K + bk - 1) / bk), sm_count() / c.ctas);
+  return splits > 1 ? (size_t)splits * batch * M * N * sizeof(float) : 0;
 }
 
 bool gemm_tcgen05_supported(const GemmArgs& g) {
@@ -504,17 +896,21 @@ bool gemm_tcgen05_supported(const GemmArgs& g) {
   return true;
 }
 
-int gemm_tcgen05(const GemmArgs& g, cudaStream_t stream) {
-  const int bn = choose_bn(g);
-  if (g.dtype == B200_DT_FLOAT) {
-    if (bn == 64) return dispatch_major<float, float, 64>(g, stream);
-    if (bn == 256) return dispatch_major<float, float, 256>(g, stream);
-    return dispatch_major<float, float, 128>(g, stream);
-  } else if (g.dtype == B200_DT_BFLOAT16) {
-    if (bn == 64) return dispatch_major<__nv_bfloat16, __nv_bfloat16, 64>(g, stream);
-    if (bn == 256) return dispatch_major<__nv_bfloat16, __nv_bfloat16, 256>(g, stream);
-    return dispatch_major<__nv_bfloat16, __nv_bfloat16, 128>(g, stream);
+template <typename TIn, typename TOut>
+static int dispatch_config(const GemmArgs& g, const TileConfig& c, cudaStream_t stream) {
+  if (c.ctas == 2) {
+    if (c.bn == 256) return dispatch_major<TIn, TOut, 256, 2>(g, stream);
+    return dispatch_major<TIn, TOut, 128, 2>(g, stream);
   }
+  if (c.bn == 64) return dispatch_major<TIn, TOut, 64, 1>(g, stream);
+  return dispatch_major<TIn, TOut, 128, 1>(g, stream);
+}
+
+int gemm_tcgen05(const GemmArgs& g, cudaStream_t stream) {
+  const TileConfig c = choose_config(g);
+  if (g.dtype == B200_DT_FLOAT) return dispatch_config<float, float>(g, c, stream);
+  if (g.dtype == B200_DT_BFLOAT16)
+    return dispatch_config<__nv_bfloat16, __nv_bfloat16>(g, c, stream);
   set_last_error("gemm_tcgen05: unsupported dtype %d", g.dtype);
   return B200_UNIMPLEMENTED;
 }

@@ -203,6 +203,48 @@ int b200_matmul(int dtype, const void* a, const void* b, void* c, int64_t m, int
   return gemm_dispatch(g, as_stream(stream));
 }
 
+int b200_fused_matmul(int dtype, const void* a, const void* b, void* c, int64_t m, int64_t n,
+                      int64_t k, int transpose_a, int transpose_b, const void* bias, int relu,
+                      const void* relu_grad_features, void* stream) {
+  int rc = validate_gemm("b200_fused_matmul", dtype, a, b, c, m, n, k, 1);
+  if (rc) return rc;
+  if (relu && relu_grad_features) {
+    set_last_error("b200_fused_matmul: relu and relu_grad_features are mutually exclusive");
+    return B200_INVALID_ARGUMENT;
+  }
+  GemmArgs g{};
+  g.dtype = dtype;
+  g.a = a;
+  g.b = b;
+  g.c = c;
+  g.M = m;
+  g.N = n;
+  g.K = k;
+  g.batch = 1;
+  g.lda = transpose_a ? m : k;
+  g.ldb = transpose_b ? k : n;
+  g.ldc = n;
+  g.strideA = m * k;
+  g.strideB = k * n;
+  g.strideC = m * n;
+  g.a_mn_major = transpose_a != 0;
+  g.b_mn_major = transpose_b == 0;
+  g.bias = bias;
+  g.relu = relu != 0;
+  g.relu_grad_features = relu_grad_features;
+  g.ld_features = n;
+  const bool want_exact = dtype == B200_DT_FLOAT && b200_get_matmul_precision() == 1;
+  if (!want_exact && gemm_tcgen05_supported(g) && driver().cuTensorMapEncodeTiled)
+    return gemm_tcgen05(g, as_stream(stream));
+  // Shapes TMA cannot address / exact mode: GEMM, then the element-wise tail as separate kernels.
+  rc = gemm_simt(g, as_stream(stream));
+  if (rc) return rc;
+  if (bias) rc = b200_bias_add(dtype, c, bias, c, m, n, stream);
+  if (!rc && relu) rc = b200_relu(dtype, c, c, m * n, stream);
+  if (!rc && relu_grad_features) rc = b200_relu_grad(dtype, c, relu_grad_features, c, m * n, stream);
+  return rc;
+}
+
 int b200_batch_matmul(int dtype, const void* x, const void* y, void* out, int64_t batch, int64_t m,
                       int64_t n, int64_t k, int adj_x, int adj_y, void* stream) {
   int rc = validate_gemm("b200_batch_matmul", dtype, x, y, out, m, n, k, batch);

@@ -71,16 +71,35 @@ bias_grad_stage1(const T* __restrict__ g, float* __restrict__ partial, long long
 #pragma unroll
   for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
   if (active) {
-    for (long long r = r0 + y * fold + sub; r < r1; r += 8 * fold) {
+    long long r = r0 + y * fold + sub;
+    const long long step = 8 * fold;
+    if (VEC == 4 && sizeof(T) == 4) {
+      // four independent 16-byte row loads in flight per thread (rows r, r+step, r+2step, r+3step)
+      for (; r + 3 * step < r1; r += 4 * step) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          v[u] = __ldg(reinterpret_cast<const float4*>(g + (r + u * step) * channels +
+                                                       (long long)cv * VEC));
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // same summation order as the scalar tail below
+          acc[0] += v[u].x;
+          acc[1 % VEC] += v[u].y;
+          acc[2 % VEC] += v[u].z;
+          acc[3 % VEC] += v[u].w;
+        }
+      }
+    }
+    for (; r < r1; r += step) {
       const T* p = g + r * channels + (long long)cv * VEC;
       if (VEC == 1) {
         acc[0] += ldf<T>(p);
       } else if (sizeof(T) == 4) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(p));
         acc[0] += v.x;
-        acc[1] += v.y;
-        acc[2] += v.z;
-        acc[3] += v.w;
+        acc[1 % VEC] += v.y;
+        acc[2 % VEC] += v.z;
+        acc[3 % VEC] += v.w;
       } else {
         const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -138,8 +157,8 @@ static BiasGradPlan plan_bias_grad(int dtype, long long rows, long long channels
   const long long W = channels / p.vec;
   p.col_tiles = (int)((W + 31) / 32);
   const int fold = W < 32 ? (int)(32 / W) : 1;
-  long long want = (4LL * 148 + p.col_tiles - 1) / p.col_tiles;  // ~4 CTAs per SM in total
-  long long max_chunks = (rows + 8LL * fold * 4 - 1) / (8LL * fold * 4);  // >= 4 rows per thread
+  long long want = (2LL * 148 + p.col_tiles - 1) / p.col_tiles;  // ~2 CTAs per SM in total
+  long long max_chunks = (rows + 8LL * fold * 16 - 1) / (8LL * fold * 16);  // >= 16 rows per thread
   if (max_chunks < 1) max_chunks = 1;
   if (want > max_chunks) want = max_chunks;
   if (want > 4096) want = 4096;
@@ -326,6 +345,62 @@ xent_warp_kernel(const T* __restrict__ logits, const T* __restrict__ labels, T* 
   }
   acc = warp_sum(acc);
   if (lane == 0) stf<T>(loss + row, acc);
+}
+
+// fp32, cols % 4 == 0, cols <= 128 * NV: 16-byte loads, whole row of logits and labels in registers.
+template <int NV>
+__global__ void __launch_bounds__(256)
+xent_warp_vec_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
+                     float* __restrict__ loss, float* __restrict__ backprop, long long rows,
+                     int cols) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float4* x = reinterpret_cast<const float4*>(logits + row * cols);
+  const float4* l = reinterpret_cast<const float4*>(labels + row * cols);
+  float4* bp = reinterpret_cast<float4*>(backprop + row * cols);
+  const int nvec = cols >> 2;
+  float4 v[NV], lab[NV];
+  float mx = -FLT_MAX;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nvec) {
+      v[j] = __ldg(x + i);
+      lab[j] = __ldg(l + i);
+      mx = fmaxf(mx, fmaxf(fmaxf(v[j].x, v[j].y), fmaxf(v[j].z, v[j].w)));
+    }
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+    if (lane + 32 * j < nvec) {
+      v[j].x -= mx;
+      v[j].y -= mx;
+      v[j].z -= mx;
+      v[j].w -= mx;
+      sum += expf(v[j].x) + expf(v[j].y) + expf(v[j].z) + expf(v[j].w);
+    }
+  sum = warp_sum(sum);
+  const float ls = logf(sum);
+  float acc = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int i = lane + 32 * j;
+    if (i < nvec) {
+      acc += lab[j].x * (ls - v[j].x) + lab[j].y * (ls - v[j].y) + lab[j].z * (ls - v[j].z) +
+             lab[j].w * (ls - v[j].w);
+      float4 o;
+      o.x = expf(v[j].x) / sum - lab[j].x;
+      o.y = expf(v[j].y) / sum - lab[j].y;
+      o.z = expf(v[j].z) / sum - lab[j].z;
+      o.w = expf(v[j].w) / sum - lab[j].w;
+      bp[i] = o;
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) loss[row] = acc;
 }
 
 // ================================================================== ArgMax
@@ -562,7 +637,22 @@ int b200_softmax_xent(int dtype, const void* logits, const void* labels, void* l
   cudaStream_t s = as_stream(stream);
   if (cols == 0) return b200_memset_async(loss, 0, (size_t)rows * (dtype == B200_DT_FLOAT ? 4 : 2), stream);
   if (dtype == B200_DT_FLOAT) {
-    if (cols <= 1024)
+    const bool vec = cols % 4 == 0 && cols <= 1024 && aligned16(logits) && aligned16(labels) &&
+                     aligned16(backprop);
+    const float* xl = static_cast<const float*>(logits);
+    const float* ll = static_cast<const float*>(labels);
+    float* lo = static_cast<float*>(loss);
+    float* bo = static_cast<float*>(backprop);
+    const unsigned wg = (unsigned)((rows + 7) / 8);
+    if (vec && cols <= 128)
+      xent_warp_vec_kernel<1><<<wg, 256, 0, s>>>(xl, ll, lo, bo, rows, (int)cols);
+    else if (vec && cols <= 256)
+      xent_warp_vec_kernel<2><<<wg, 256, 0, s>>>(xl, ll, lo, bo, rows, (int)cols);
+    else if (vec && cols <= 512)
+      xent_warp_vec_kernel<4><<<wg, 256, 0, s>>>(xl, ll, lo, bo, rows, (int)cols);
+    else if (vec)
+      xent_warp_vec_kernel<8><<<wg, 256, 0, s>>>(xl, ll, lo, bo, rows, (int)cols);
+    else if (cols <= 1024)
       xent_warp_kernel<float><<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(
           static_cast<const float*>(logits), static_cast<const float*>(labels),
           static_cast<float*>(loss), static_cast<float*>(backprop), rows, (int)cols);

@@ -197,6 +197,7 @@ Status DirectSession::GetOrCreateExecutors(const std::vector<std::string>& feeds
   for (int n : order) {
     PlanNode pn;
     pn.node = n;
+    pn.item = nodes_[n].get();
     pn.first_entry = first_entry[n];
     const OpKernel* k = nodes_[n]->kernel.get();
     for (size_t i = 0; i < nodes_[n]->inputs.size(); ++i) {
@@ -246,8 +247,87 @@ Status DirectSession::GetOrCreateExecutors(const std::vector<std::string>& feeds
     ek->fetches.push_back(src);
   }
   ek->node_first_entry = first_entry;
+  if (getenv("B200TF_DISABLE_FUSION") == nullptr) TF_RETURN_IF_ERROR(FuseMatMulChains(ek.get()));
   *out = ek.get();
   executors_[key] = std::move(ek);
+  return Status::OK();
+}
+
+Status DirectSession::FuseMatMulChains(ExecutorsAndKeys* ek) {
+  auto entry_of = [&](const PlanNode& pn, int slot) { return pn.first_entry + slot; };
+  auto single_use = [&](int entry) {
+    return ek->entry_consumers[entry] == 1 && !ek->entry_is_fetch[entry];
+  };
+  // the unique plan node (after position `from`) reading (node, 0) as its input `want_input`
+  auto consumer_of = [&](size_t from, int node, int want_input) -> int {
+    for (size_t j = from + 1; j < ek->order.size(); ++j) {
+      const PlanNode& c = ek->order[j];
+      if (c.dead) continue;
+      for (size_t i = 0; i < c.inputs.size(); ++i)
+        if (c.inputs[i].feed < 0 && c.inputs[i].id.node == node && c.inputs[i].id.slot == 0)
+          return static_cast<int>(i) == want_input ? static_cast<int>(j) : -1;
+    }
+    return -1;
+  };
+  for (size_t i = 0; i < ek->order.size(); ++i) {
+    PlanNode& mm = ek->order[i];
+    if (mm.dead || mm.node < 0 || mm.item->def.op != "MatMul") continue;
+    const DataType dt = mm.item->kernel->input_type(0);
+    if (dt != DT_FLOAT && dt != DT_BFLOAT16) continue;
+    if (!single_use(entry_of(mm, 0))) continue;
+    const int j = consumer_of(i, mm.node, 0);
+    if (j < 0) continue;
+    PlanNode& next = ek->order[j];
+    if (next.node < 0) continue;
+    std::vector<std::string> fused_ops;
+    int last = j;
+    InputSource extra;
+    if (next.item->def.op == "BiasAdd") {
+      std::string fmt = "NHWC";
+      GetNodeAttr(next.item->def, "data_format", &fmt);
+      if (fmt != "NHWC") continue;
+      fused_ops = {"BiasAdd"};
+      extra = next.inputs[1];
+      if (single_use(entry_of(next, 0))) {
+        const int k = consumer_of(j, next.node, 0);
+        if (k >= 0 && ek->order[k].node >= 0 && ek->order[k].item->def.op == "Relu") {
+          fused_ops.push_back("Relu");
+          last = k;
+        }
+      }
+    } else if (next.item->def.op == "ReluGrad") {
+      fused_ops = {"ReluGrad"};
+      extra = next.inputs[1];
+      // features must not be the matmul output itself
+      if (extra.feed < 0 && extra.id.node == mm.node) continue;
+    } else {
+      continue;
+    }
+    std::unique_ptr<NodeItem> fused(new NodeItem);
+    PlanNode& tail = ek->order[last];
+    fused->def.name = tail.item->def.name + "/_fused_matmul";
+    fused->def.op = "_FusedMatMul";
+    fused->def.attr["T"] = AttrValue::Type(dt);
+    fused->def.attr["num_args"] = AttrValue::I(1);
+    fused->def.attr["transpose_a"] = mm.item->def.attr.at("transpose_a");
+    fused->def.attr["transpose_b"] = mm.item->def.attr.at("transpose_b");
+    fused->def.attr["fused_ops"] = AttrValue::ListS(fused_ops);
+    fused->def.input = {mm.item->def.input[0], mm.item->def.input[1], "<fused>"};
+    TF_RETURN_IF_ERROR(EnsureKernel(fused.get()));
+    PlanNode repl;
+    repl.node = -1;
+    repl.item = fused.get();
+    repl.first_entry = tail.first_entry;  // consumers of the chain's result are unchanged
+    repl.inputs = {mm.inputs[0], mm.inputs[1], extra};
+    mm.dead = true;
+    if (last != j) next.dead = true;
+    ek->order[last] = repl;
+    ek->rewritten.push_back(std::move(fused));
+  }
+  std::vector<PlanNode> alive;
+  for (PlanNode& pn : ek->order)
+    if (!pn.dead) alive.push_back(std::move(pn));
+  ek->order.swap(alive);
   return Status::OK();
 }
 
@@ -293,7 +373,7 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
   DeviceContext* dc = device_->device_context();
 
   for (const PlanNode& pn : ek->order) {
-    NodeItem* item = nodes_[pn.node].get();
+    NodeItem* item = pn.item;
     OpKernel* kernel = item->kernel.get();
     input_values.clear();
     deref_storage.clear();

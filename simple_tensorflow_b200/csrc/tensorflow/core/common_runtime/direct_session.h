@@ -62,12 +62,15 @@ class DirectSession : public Session {
     TensorId id;    // otherwise: produced by this (node, slot)
   };
   struct PlanNode {
-    int node;
+    int node;            // index into nodes_ (-1 for a node synthesised by a rewrite)
+    NodeItem* item;      // the node to execute (owned by nodes_ or by ExecutorsAndKeys::rewritten)
+    bool dead = false;   // folded into a fused node by a rewrite
     std::vector<InputSource> inputs;
     int first_entry;  // index of output slot 0 in the entry table
   };
   struct ExecutorsAndKeys {
     std::vector<PlanNode> order;
+    std::vector<std::unique_ptr<NodeItem>> rewritten;  // fused nodes created for this plan
     std::vector<InputSource> fetches;
     std::vector<int> node_first_entry;  // per graph node: entry index of its output 0 (-1: pruned)
     std::vector<int> entry_consumers;   // per entry: how many plan inputs read it
@@ -92,6 +95,9 @@ class DirectSession : public Session {
                               const std::vector<std::string>& fetches,
                               const std::vector<std::string>& targets, ExecutorsAndKeys** out);
   Status EnsureKernel(NodeItem* item);
+  // GraphOptimizer-stage rewrite (direct_session.cc:1051 role): MatMul+BiasAdd(+Relu) and
+  // MatMul+ReluGrad chains whose intermediates have a single consumer run as one _FusedMatMul.
+  Status FuseMatMulChains(ExecutorsAndKeys* ek);
   Status RunPlan(ExecutorsAndKeys* ek, const std::vector<std::pair<std::string, Tensor>>& inputs,
                  std::vector<Tensor>* outputs);
 

@@ -36,6 +36,7 @@ struct AttrValue {
   static AttrValue Shape(const TensorShape& v) { AttrValue a; a.kind = kShape; a.shape = v; return a; }
   static AttrValue TensorV(const Tensor& v) { AttrValue a; a.kind = kTensor; a.tensor = v; return a; }
   static AttrValue ListI(const std::vector<int64>& v) { AttrValue a; a.kind = kListI; a.list_i = v; return a; }
+  static AttrValue ListS(const std::vector<std::string>& v) { AttrValue a; a.kind = kListS; a.list_s = v; return a; }
 };
 
 struct NodeDef {
@@ -61,6 +62,7 @@ Status GetNodeAttr(const NodeDef& n, const std::string& name, TensorShape* v);
 Status GetNodeAttr(const NodeDef& n, const std::string& name, Tensor* v);
 Status GetNodeAttr(const NodeDef& n, const std::string& name, std::vector<int32>* v);
 Status GetNodeAttr(const NodeDef& n, const std::string& name, std::vector<int64>* v);
+Status GetNodeAttr(const NodeDef& n, const std::string& name, std::vector<std::string>* v);
 std::string SummarizeNodeDef(const NodeDef& n);
 
 }  // namespace tensorflow

@@ -317,6 +317,7 @@ B200TF_GET_ATTR(DataType, kType, "type", a->type)
 B200TF_GET_ATTR(TensorShape, kShape, "shape", a->shape)
 B200TF_GET_ATTR(Tensor, kTensor, "tensor", a->tensor)
 B200TF_GET_ATTR(std::vector<int64>, kListI, "list(int)", a->list_i)
+B200TF_GET_ATTR(std::vector<std::string>, kListS, "list(string)", a->list_s)
 #undef B200TF_GET_ATTR
 Status GetNodeAttr(const NodeDef& n, const std::string& name, std::vector<int32>* v) {
   std::vector<int64> tmp;

@@ -113,11 +113,89 @@ class BatchMatMulOp : public OpKernel {
   bool adj_y_;
 };
 
+// _FusedMatMul: MatMul whose epilogue applies the BiasAdd / Relu / ReluGrad that followed it.
+template <typename T>
+class FusedMatMulOp : public OpKernel {
+ public:
+  explicit FusedMatMulOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("transpose_a", &transpose_a_));
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("transpose_b", &transpose_b_));
+    std::vector<std::string> fused;
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("fused_ops", &fused));
+    if (fused == std::vector<std::string>{"BiasAdd"}) mode_ = kBias;
+    else if (fused == std::vector<std::string>{"BiasAdd", "Relu"}) mode_ = kBiasRelu;
+    else if (fused == std::vector<std::string>{"ReluGrad"}) mode_ = kReluGrad;
+    else
+      OP_REQUIRES(ctx, false, errors::InvalidArgument("Unsupported fused_ops for _FusedMatMul"));
+    OP_REQUIRES(ctx, ctx->num_inputs() == 3,
+                errors::InvalidArgument("_FusedMatMul expects exactly one extra argument"));
+  }
+
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& a = ctx->input(0);
+    const Tensor& b = ctx->input(1);
+    const Tensor& arg = ctx->input(2);
+    OP_REQUIRES(ctx, TensorShapeUtils::IsMatrix(a.shape()),
+                errors::InvalidArgument("In[0] is not a matrix"));
+    OP_REQUIRES(ctx, TensorShapeUtils::IsMatrix(b.shape()),
+                errors::InvalidArgument("In[1] is not a matrix"));
+    const int a_contract = transpose_a_ ? 0 : 1;
+    const int b_contract = transpose_b_ ? 1 : 0;
+    OP_REQUIRES(ctx, a.dim_size(a_contract) == b.dim_size(b_contract),
+                errors::InvalidArgument("Matrix size-incompatible: In[0]: ",
+                                        a.shape().DebugString(), ", In[1]: ",
+                                        b.shape().DebugString()));
+    const int64 m = a.dim_size(1 - a_contract), k = a.dim_size(a_contract);
+    const int64 n = b.dim_size(1 - b_contract);
+    if (mode_ == kReluGrad) {
+      OP_REQUIRES(ctx, arg.shape() == TensorShape({m, n}),
+                  errors::InvalidArgument("Inputs must have the same size"));  // relu_op.h:48-60
+    } else {
+      OP_REQUIRES(ctx, TensorShapeUtils::IsVector(arg.shape()),
+                  errors::InvalidArgument("Biases must be 1D: ", arg.shape().DebugString()));
+      OP_REQUIRES(ctx, arg.dim_size(0) == n,
+                  errors::InvalidArgument("Must provide as many biases as the last dimension of "
+                                          "the input tensor: ", arg.shape().DebugString(),
+                                          " vs. ", TensorShape({m, n}).DebugString()));
+    }
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({m, n}), &out));
+    if (out->NumElements() == 0) return;
+    void* stream = GetCudaStream(ctx);
+    if (k == 0) {  // product is zero: run the tail on a zero matrix, op by op
+      OP_REQUIRES_OK(ctx, FromAbi(b200_memset_async(out->raw_data(), 0, out->TotalBytes(), stream),
+                                  "_FusedMatMul zero fill"));
+      if (mode_ != kReluGrad)
+        OP_REQUIRES_OK(ctx, FromAbi(b200_bias_add(AbiType<T>::v, out->raw_data(), arg.raw_data(),
+                                                  out->raw_data(), m, n, stream), "BiasAdd"));
+      if (mode_ == kBiasRelu)
+        OP_REQUIRES_OK(ctx, FromAbi(b200_relu(AbiType<T>::v, out->raw_data(), out->raw_data(),
+                                              m * n, stream), "Relu"));
+      return;
+    }
+    OP_REQUIRES_OK(ctx, FromAbi(b200_fused_matmul(
+                                    AbiType<T>::v, a.raw_data(), b.raw_data(), out->raw_data(), m,
+                                    n, k, transpose_a_, transpose_b_,
+                                    mode_ == kReluGrad ? nullptr : arg.raw_data(),
+                                    mode_ == kBiasRelu, mode_ == kReluGrad ? arg.raw_data() : nullptr,
+                                    stream),
+                                "Blas GEMM launch failed"));
+  }
+
+ private:
+  enum Mode { kBias, kBiasRelu, kReluGrad };
+  bool transpose_a_;
+  bool transpose_b_;
+  Mode mode_ = kBias;
+};
+
 #define REGISTER_GPU(T)                                                                        \
   REGISTER_KERNEL_BUILDER(Name("MatMul").Device(DEVICE_GPU).TypeConstraint<T>("T"),            \
                           MatMulOp<T>);                                                        \
   REGISTER_KERNEL_BUILDER(Name("BatchMatMul").Device(DEVICE_GPU).TypeConstraint<T>("T"),       \
-                          BatchMatMulOp<T>);
+                          BatchMatMulOp<T>);                                                   \
+  REGISTER_KERNEL_BUILDER(Name("_FusedMatMul").Device(DEVICE_GPU).TypeConstraint<T>("T"),      \
+                          FusedMatMulOp<T>);
 REGISTER_B200_FLOAT_TYPES(REGISTER_GPU)
 #undef REGISTER_GPU
 

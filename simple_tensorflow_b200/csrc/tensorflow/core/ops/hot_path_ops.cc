@@ -17,6 +17,15 @@ REGISTER_OP("MatMul")
     .Attr("transpose_a: bool = false").Attr("transpose_b: bool = false")
     .Attr("T: {half, float, double, int32, complex64, complex128, bfloat16}");
 
+// Produced only by the executor's rewrite of MatMul+BiasAdd(+Relu) / MatMul+ReluGrad chains (the
+// shape later TensorFlow's grappler remapper gives the same fusion): args[0] is the bias or the
+// ReluGrad features; fused_ops is one of {BiasAdd}, {BiasAdd, Relu}, {ReluGrad}.
+REGISTER_OP("_FusedMatMul")
+    .Input("a: T").Input("b: T").Input("args: num_args * T").Output("product: T")
+    .Attr("T: {float, bfloat16}").Attr("num_args: int >= 0")
+    .Attr("transpose_a: bool = false").Attr("transpose_b: bool = false")
+    .Attr("fused_ops: list(string)");
+
 REGISTER_OP("BatchMatMul")
     .Input("x: T").Input("y: T").Output("output: T")
     .Attr("T: {half, float, double, int32, complex64, complex128, bfloat16}")

@@ -79,6 +79,21 @@ def matmul(a, b, ta=False, tb=False, bf16=False, use_workspace=True):
     return host(out)
 
 
+def fused_matmul(a, b, ta=False, tb=False, bias=None, relu=False, features=None, bf16=False):
+    L = lib()
+    m = a.shape[1] if ta else a.shape[0]
+    k = a.shape[0] if ta else a.shape[1]
+    n = b.shape[0] if tb else b.shape[1]
+    da, db = dev(a, bf16), dev(b, bf16)
+    dbias = dev(bias, bf16) if bias is not None else None
+    dfeat = dev(features, bf16) if features is not None else None
+    out = empty((m, n), tdt(bf16), fill=float("nan"))
+    call(L.b200_fused_matmul, cdt(bf16), da.data_ptr(), db.data_ptr(), out.data_ptr(), m, n, k,
+         int(ta), int(tb), dbias.data_ptr() if dbias is not None else None, int(relu),
+         dfeat.data_ptr() if dfeat is not None else None, stream())
+    return host(out)
+
+
 def batch_matmul(x, y, adj_x=False, adj_y=False, bf16=False):
     L = lib()
     batch = x.shape[0]

@@ -89,7 +89,21 @@ def test_mlp_training_step_config2_reduced(oracle, rng):
     assert loss2 < got_loss  # one SGD step on the same batch reduces the loss
 
 
-def test_lenet_training_step_config3_reduced(oracle, rng):
+@pytest.mark.parametrize("exact_fp32", [False, True])
+def test_lenet_training_step_config3_reduced(oracle, rng, exact_fp32):
+    # exact_fp32=True runs the GEMMs on the IEEE-fp32 SIMT kernel: element-wise comparison.
+    # Default TF32 mode: a pre-activation within TF32 rounding of zero may flip its ReLU mask
+    # relative to the fp32 oracle, which moves single entries of a small-batch weight gradient by
+    # O(1) of their size; the comparison there is in Frobenius norm (still <= 1e-2 relative).
+    from simple_tensorflow_b200 import _lib
+    assert _lib.load().b200_set_matmul_precision(1 if exact_fp32 else 0) == 0
+    try:
+        _lenet_step(oracle, rng, exact_fp32)
+    finally:
+        _lib.load().b200_set_matmul_precision(0)
+
+
+def _lenet_step(oracle, rng, exact_fp32):
     B = 8
     x = rng.uniform(0, 1, (B, 28, 28, 1)).astype(np.float32)
     labels = np.eye(10, dtype=np.float32)[rng.randint(0, 10, B)]
@@ -143,9 +157,54 @@ def test_lenet_training_step_config3_reduced(oracle, rng):
     ref["b1"] = o.apply_gradient_descent(b1, lr, o.bias_add_grad(d))
     ref["w1"] = o.apply_gradient_descent(w1, lr, o.conv2d_backprop_filter(x, w1.shape, d, (1, 1), "SAME"))
     assert abs(got_loss - lvec.mean()) < 1e-2 * abs(lvec.mean())
-    for n in V:
-        assert np.abs(got[n] - ref[n]).max() / np.abs(ref[n]).max() < 1e-2, n
+    if exact_fp32:
+        errs = {n: float(np.abs(got[n] - ref[n]).max() / np.abs(ref[n]).max()) for n in V}
+        assert all(e < 1e-3 for e in errs.values()), errs
+    else:
+        errs = {n: float(np.linalg.norm((got[n] - ref[n]).ravel()) / np.linalg.norm(ref[n].ravel()))
+                for n in V}
+        assert all(e < 1e-2 for e in errs.values()), errs
     assert pred.dtype == np.int64 and pred.shape == (B,)
+
+
+def test_fusion_rewrite_matches_unfused(oracle, rng, monkeypatch):
+    # MatMul+BiasAdd+Relu and MatMul+ReluGrad chains run as _FusedMatMul (fewer launches), with
+    # results identical (same GEMM, same fp32 tail) to the op-by-op execution.
+    B, D = 512, 256
+    x = rng.uniform(-1, 1, (B, D)).astype(np.float32)
+    labels = np.eye(D, dtype=np.float32)[rng.randint(0, D, B)]
+    ws = [(rng.randn(D, D) / np.sqrt(D)).astype(np.float32) for _ in range(3)]
+
+    def run(disable):
+        if disable:
+            monkeypatch.setenv("B200TF_DISABLE_FUSION", "1")
+        else:
+            monkeypatch.delenv("B200TF_DISABLE_FUSION", raising=False)
+        tf.reset_default_graph()
+        xp, lp = tf.placeholder(tf.float32, [B, D]), tf.placeholder(tf.float32, [B, D])
+        Ws = [tf.Variable(w, name="W%d" % i) for i, w in enumerate(ws)]
+        Bs = [tf.Variable(np.full(D, 0.1, np.float32), name="b%d" % i) for i in range(3)]
+        h = xp
+        for i in range(3):
+            h = tf.bias_add(tf.matmul(h, Ws[i]), Bs[i])
+            if i < 2:
+                h = tf.relu(h)
+        loss = tf.reduce_mean(tf.softmax_cross_entropy_with_logits(h, lp))
+        train = tf.GradientDescentOptimizer(0.5).minimize(loss)
+        with client.Session(tf.get_default_graph()) as sess:
+            sess.run(tf.global_variables_initializer())
+            lv, _ = sess.run([loss, train], {xp: x, lp: labels})
+            stats = sess.last_run_stats()
+            return lv, sess.run([v.ref for v in Ws + Bs]), stats
+
+    l0, v0, s0 = run(disable=True)
+    l1, v1, s1 = run(disable=False)
+    assert s1["nodes_executed"] < s0["nodes_executed"]
+    assert s1["kernels_launched"] < s0["kernels_launched"]
+    # same arithmetic; only the split-K choice (hence fp32 summation order) of small GEMMs differs
+    assert abs(l0 - l1) <= 1e-5 * abs(l0)
+    for a, b in zip(v0, v1):
+        np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-5)
 
 
 def test_session_error_behaviour(rng):

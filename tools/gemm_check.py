@@ -16,7 +16,10 @@ def run(dtype, m, n, k, ta, tb, batch=1, iters=0):
     c = torch.full((batch, m, n), float("nan"), device=dev, dtype=tdt)
     st = torch.cuda.current_stream().cuda_stream
     if batch == 1:
-        rc = lib.b200_matmul(dtype, a.data_ptr(), b.data_ptr(), c.data_ptr(), m, n, k, int(ta), int(tb), st)
+        nb = lib.b200_matmul_workspace_bytes(dtype, m, n, k)
+        ws = torch.empty(max(nb, 1), dtype=torch.uint8, device=dev)
+        wsp = ws.data_ptr() if nb else None
+        rc = lib.b200_matmul(dtype, a.data_ptr(), b.data_ptr(), c.data_ptr(), m, n, k, int(ta), int(tb), wsp, nb, st)
     else:
         rc = lib.b200_batch_matmul(dtype, a.data_ptr(), b.data_ptr(), c.data_ptr(), batch, m, n, k, int(ta), int(tb), st)
     if rc:
@@ -32,10 +35,10 @@ def run(dtype, m, n, k, ta, tb, batch=1, iters=0):
     if iters:
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         for _ in range(3):
-            lib.b200_matmul(dtype, a.data_ptr(), b.data_ptr(), c.data_ptr(), m, n, k, int(ta), int(tb), st)
+            lib.b200_matmul(dtype, a.data_ptr(), b.data_ptr(), c.data_ptr(), m, n, k, int(ta), int(tb), wsp, nb, st)
         e0.record()
         for _ in range(iters):
-            lib.b200_matmul(dtype, a.data_ptr(), b.data_ptr(), c.data_ptr(), m, n, k, int(ta), int(tb), st)
+            lib.b200_matmul(dtype, a.data_ptr(), b.data_ptr(), c.data_ptr(), m, n, k, int(ta), int(tb), wsp, nb, st)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / iters
         msg += f"  {ms*1e3:.1f} us  {2*m*n*k/ms/1e9:.1f} TFLOP/s"
@@ -49,6 +52,8 @@ for dtype in (_lib.DT_FLOAT, _lib.DT_BFLOAT16):
     run(dtype, 128, 128, 128, False, True)
     run(dtype, 200, 136, 72, False, False)      # ragged tiles, aligned strides
     run(dtype, 200, 136, 72, True, True)
+    run(dtype, 512, 384, 200, False, False)
+    run(dtype, 300, 130, 64, True, False)
     run(dtype, 4096, 1024, 1024, False, False, iters=20)
     run(dtype, 4096, 1024, 1024, False, True, iters=20)
     run(dtype, 1024, 1024, 4096, True, False, iters=20)
