@@ -230,12 +230,15 @@ def run_b200(args):
 
     def timed(fetches, feed, steps):
         """-> (device ms between events on the session stream, launches, last loss)."""
-        launches, loss = 0, None
+        launches, loss, enq = 0, None, 0
         barrier()
         _lib.check(L.b200_event_record(ev0, stream))
         for _ in range(steps):
             loss = sess.run(fetches, feed)[0]
-            launches += sess.last_run_stats()["kernels_launched"]
+            st = sess.last_run_stats()
+            launches += st["kernels_launched"]
+            enq += st["host_enqueue_us"]
+        timed.host_enqueue_us = enq / max(steps, 1)
         _lib.check(L.b200_event_record(ev1, stream))
         barrier()
         ms = ctypes.c_float()
@@ -259,6 +262,7 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     ms_res, launches, loss_res = timed(res_fetch, None, args.steps)
+    host_enqueue_us = timed.host_enqueue_us
     ms_e2e, _, loss_e2e = timed(fed_fetch, feed, args.steps)
     clocks = sampler.summary() if rank == 0 else None
     h2d = sess.last_run_stats()["h2d_bytes"]
@@ -308,7 +312,8 @@ def run_b200(args):
                                "(BASELINE configs[1]); Session.Run([loss, train_op])",
                    "global_batch": BATCH * world, "parallelism": "dp%d" % world,
                    "l2": "no flush: per-step working set ~%.0f MB > 126 MB L2" % working_set_mb,
-                   "loss_resident": loss_res, "loss_e2e": loss_e2e},
+                   "loss_resident": loss_res, "loss_e2e": loss_e2e,
+                   "host_enqueue_us_per_step": host_enqueue_us},
         "clocks": clocks,
         "e2e": {"value": n_samples / (ms_e2e / 1e3), "unit": "samples/s",
                 "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,

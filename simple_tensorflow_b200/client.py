@@ -33,7 +33,8 @@ class TF_Output(ctypes.Structure):
 
 class RunStats(ctypes.Structure):
     _fields_ = [("nodes_executed", c_int64), ("kernels_launched", c_int64),
-                ("h2d_bytes", c_int64), ("d2h_bytes", c_int64)]
+                ("h2d_bytes", c_int64), ("d2h_bytes", c_int64),
+                ("host_enqueue_us", c_int64), ("host_total_us", c_int64)]
 
 
 _SIGS = {
@@ -375,7 +376,8 @@ class Session:
         s = RunStats()
         self.fw.B200TF_SessionLastRunStats(self.ptr, ctypes.byref(s))
         return {"nodes_executed": s.nodes_executed, "kernels_launched": s.kernels_launched,
-                "h2d_bytes": s.h2d_bytes, "d2h_bytes": s.d2h_bytes}
+                "h2d_bytes": s.h2d_bytes, "d2h_bytes": s.d2h_bytes,
+                "host_enqueue_us": s.host_enqueue_us, "host_total_us": s.host_total_us}
 
     def close(self):
         if self.ptr:

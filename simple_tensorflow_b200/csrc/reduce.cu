@@ -157,8 +157,10 @@ static BiasGradPlan plan_bias_grad(int dtype, long long rows, long long channels
   const long long W = channels / p.vec;
   p.col_tiles = (int)((W + 31) / 32);
   const int fold = W < 32 ? (int)(32 / W) : 1;
-  long long want = (2LL * 148 + p.col_tiles - 1) / p.col_tiles;  // ~2 CTAs per SM in total
-  long long max_chunks = (rows + 8LL * fold * 16 - 1) / (8LL * fold * 16);  // >= 16 rows per thread
+  // Enough CTAs to keep ~5 MB of loads in flight (HBM latency x bandwidth): ~8 CTAs per SM, each
+  // thread issuing one batch of four independent 16-byte loads.
+  long long want = (8LL * 148 + p.col_tiles - 1) / p.col_tiles;
+  long long max_chunks = (rows + 8LL * fold * 4 - 1) / (8LL * fold * 4);  // >= 4 rows per thread
   if (max_chunks < 1) max_chunks = 1;
   if (want > max_chunks) want = max_chunks;
   if (want > 4096) want = 4096;

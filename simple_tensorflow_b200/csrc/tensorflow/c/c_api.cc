@@ -321,6 +321,8 @@ void B200TF_SessionLastRunStats(TF_Session* s, B200TF_RunStats* out) {
   out->kernels_launched = r.kernels_launched;
   out->h2d_bytes = r.h2d_bytes;
   out->d2h_bytes = r.d2h_bytes;
+  out->host_enqueue_us = r.host_enqueue_us;
+  out->host_total_us = r.host_total_us;
 }
 
 void* B200TF_SessionStream(TF_Session* s) {

@@ -127,7 +127,7 @@ TF_CAPI_EXPORT extern void TF_SessionRun(TF_Session* session, const void* run_op
 /* Additive introspection: step statistics of the last TF_SessionRun on this session
  * (what StepStats/RunMetadata would carry). */
 typedef struct B200TF_RunStats {
-  int64_t nodes_executed, kernels_launched, h2d_bytes, d2h_bytes;
+  int64_t nodes_executed, kernels_launched, h2d_bytes, d2h_bytes, host_enqueue_us, host_total_us;
 } B200TF_RunStats;
 TF_CAPI_EXPORT extern void B200TF_SessionLastRunStats(TF_Session*, B200TF_RunStats* out);
 /* The CUstream every kernel of this session is enqueued on (for CUDA-event timing). */

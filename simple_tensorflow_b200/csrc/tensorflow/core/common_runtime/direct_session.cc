@@ -1,6 +1,7 @@
 #include "tensorflow/core/common_runtime/direct_session.h"
 
 #include <algorithm>
+#include <chrono>
 #include <functional>
 #include <set>
 
@@ -347,7 +348,11 @@ Status DirectSession::Run(const std::vector<std::pair<std::string, Tensor>>& inp
   ++step_id_;
   const unsigned long long launches_before = b200_launch_count();
   stats_ = RunStats();
+  const auto t0 = std::chrono::steady_clock::now();
+  run_start_ = t0;
   Status s = RunPlan(ek, inputs, outputs);
+  stats_.host_total_us = std::chrono::duration_cast<std::chrono::microseconds>(
+                             std::chrono::steady_clock::now() - t0).count();
   if (!s.ok()) device_->Sync();  // drain whatever was enqueued before reporting
   stats_.kernels_launched = static_cast<long long>(b200_launch_count() - launches_before);
   return s;
@@ -502,6 +507,8 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
       stats_.d2h_bytes += static_cast<long long>(t.TotalBytes());
     }
   }
+  stats_.host_enqueue_us = std::chrono::duration_cast<std::chrono::microseconds>(
+                               std::chrono::steady_clock::now() - run_start_).count();
   return device_->Sync();  // sync_on_finish
 }
 

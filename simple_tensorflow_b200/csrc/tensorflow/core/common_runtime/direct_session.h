@@ -18,6 +18,7 @@
 #ifndef B200TF_CORE_COMMON_RUNTIME_DIRECT_SESSION_H_
 #define B200TF_CORE_COMMON_RUNTIME_DIRECT_SESSION_H_
 
+#include <chrono>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -108,6 +109,7 @@ class DirectSession : public Session {
   std::unordered_map<std::string, int> node_index_;
   std::map<std::string, std::unique_ptr<ExecutorsAndKeys>> executors_;
   RunStats stats_;
+  std::chrono::steady_clock::time_point run_start_;
   long long step_id_ = 0;
   bool closed_ = false;
 };

@@ -25,6 +25,8 @@ struct RunStats {
   long long kernels_launched = 0;  // libb200tf launch-counter delta over the step
   long long h2d_bytes = 0;
   long long d2h_bytes = 0;
+  long long host_enqueue_us = 0;   // host time from Run() entry until every kernel was enqueued
+  long long host_total_us = 0;     // host time of the whole Run() including the final device sync
 };
 
 class Session {
