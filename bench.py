@@ -161,6 +161,49 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+LENET_BATCH = 512
+
+
+def build_lenet_graph(num_replicas, seed):
+    """BASELINE configs[2] / SURVEY 8d C3: conv5x5x1x32 SAME -> relu -> pool2 -> conv5x5x32x64 SAME
+    -> relu -> pool2 -> fc 3136x1024 + relu -> fc 1024x10 -> xent; batch 512, NHWC fp32."""
+    from simple_tensorflow_b200 import ops as tf
+    rng = np.random.RandomState(seed)
+    B = LENET_BATCH
+    x = rng.uniform(-1, 1, (B, 28, 28, 1)).astype(np.float32)
+    labels = np.zeros((B, 10), np.float32)
+    labels[np.arange(B), rng.randint(0, 10, B)] = 1.0
+    shapes = dict(w1=(5, 5, 1, 32), w2=(5, 5, 32, 64), w3=(3136, 1024), w4=(1024, 10))
+    tf.reset_default_graph()
+    V = {}
+    for n, shp in shapes.items():
+        fan_in = int(np.prod(shp[:-1]))
+        V[n] = tf.Variable((rng.randn(*shp) / np.sqrt(fan_in)).astype(np.float32), name=n)
+        V["b" + n[1]] = tf.Variable(np.full(shp[-1], 0.1, np.float32), name="b" + n[1])
+    train_vars = list(V.values())
+
+    def tower(inp, lab, tag):
+        c1 = tf.relu(tf.bias_add(tf.conv2d(inp, V["w1"], [1, 1, 1, 1], "SAME"), V["b1"]))
+        p1 = tf.max_pool(c1, [1, 2, 2, 1], [1, 2, 2, 1], "SAME")
+        c2 = tf.relu(tf.bias_add(tf.conv2d(p1, V["w2"], [1, 1, 1, 1], "SAME"), V["b2"]))
+        p2 = tf.max_pool(c2, [1, 2, 2, 1], [1, 2, 2, 1], "SAME")
+        flat = tf.reshape(p2, [B, 3136])
+        f1 = tf.relu(tf.bias_add(tf.matmul(flat, V["w3"]), V["b3"]))
+        logits = tf.bias_add(tf.matmul(f1, V["w4"]), V["b4"])
+        loss = tf.reduce_mean(tf.softmax_cross_entropy_with_logits(logits, lab), name=tag + "/loss")
+        train = tf.GradientDescentOptimizer(LR).minimize(loss, train_vars, name=tag + "/train",
+                                                         num_replicas=num_replicas)
+        return loss, train
+
+    x_res = tf.Variable(x, name="x_resident")
+    l_res = tf.Variable(labels, name="labels_resident")
+    res = tower(x_res.ref, l_res.ref, "resident")
+    xp = tf.placeholder(tf.float32, [B, 28, 28, 1], "x")
+    lp = tf.placeholder(tf.float32, [B, 10], "labels")
+    fed = tower(xp, lp, "fed")
+    return tf, dict(x=x, labels=labels, xp=xp, lp=lp, resident=res, fed=fed)
+
+
 def build_graph(num_replicas, seed):
     from simple_tensorflow_b200 import ops as tf
     x, labels, ws, bs = synthetic(seed)
@@ -210,7 +253,9 @@ def run_b200(args):
         from simple_tensorflow_b200 import replica
         comm = replica.init_nccl_comm(L, rank, world, local_rank)
 
-    tf, G = build_graph(world, seed=1234 + rank)
+    lenet = args.workload == "lenet"
+    batch = LENET_BATCH if lenet else BATCH
+    tf, G = (build_lenet_graph if lenet else build_graph)(world, seed=1234 + rank)
     sess = client.Session(tf.get_default_graph(), gpu=local_rank, collective_comm=comm,
                           num_replicas=world)
     sess.run(tf.global_variables_initializer())
@@ -278,6 +323,9 @@ def run_b200(args):
 
     if rank != 0:
         sess.close()
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
         return
     peaks = {}
     try:
@@ -298,8 +346,8 @@ def run_b200(args):
             "dram_bytes_per_launch"]
     except Exception:
         pass
-    base = cpu_baseline() if world == 1 and not args.no_cpu_baseline else None
-    n_samples = BATCH * world * args.steps
+    base = cpu_baseline() if world == 1 and not args.no_cpu_baseline and not lenet else None
+    n_samples = batch * world * args.steps
     working_set_mb = (2 * BATCH * WIDTH * 4 + LAYERS * WIDTH * WIDTH * 4 * 2 +
                       8 * BATCH * WIDTH * 4) / 1e6
     line = {
@@ -308,10 +356,14 @@ def run_b200(args):
         "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32 graph; GEMMs on TF32 tensor cores, fp32 accumulate",
         "data": "synthetic",
-        "config": {"workload": "mlp-3x1024 batch 4096/replica fp32 fwd+bwd+sgd "
-                               "(BASELINE configs[1]); Session.Run([loss, train_op])",
-                   "global_batch": BATCH * world, "parallelism": "dp%d" % world,
-                   "l2": "no flush: per-step working set ~%.0f MB > 126 MB L2" % working_set_mb,
+        "config": {"workload": ("lenet-5 batch 512/replica NHWC fp32 fwd+bwd+sgd (BASELINE "
+                                "configs[2]); Session.Run([loss, train_op])") if lenet else
+                               ("mlp-3x1024 batch 4096/replica fp32 fwd+bwd+sgd "
+                                "(BASELINE configs[1]); Session.Run([loss, train_op])"),
+                   "global_batch": batch * world, "parallelism": "dp%d" % world,
+                   "l2": ("no flush: per-step working set > 126 MB L2 (conv2 patch matrix alone is "
+                          "321 MB)") if lenet else
+                         ("no flush: per-step working set ~%.0f MB > 126 MB L2" % working_set_mb),
                    "loss_resident": loss_res, "loss_e2e": loss_e2e,
                    "host_enqueue_us_per_step": host_enqueue_us},
         "clocks": clocks,
@@ -324,12 +376,16 @@ def run_b200(args):
                      "frac": achieved / peak if peak else None, "traffic": traffic,
                      "peak_source": peak_src, "launches_timed": int(gemm_n.value),
                      "us_per_launch": 1e3 * gemm_ms.value / max(1, gemm_n.value),
-                     "flops_per_launch": GEMM_FLOPS,
+                     "flops_per_launch": (gemm_fl.value / max(1, gemm_n.value)),
                      "gemm_share_of_step": (gemm_ms.value / prof_steps) / (ms_res / args.steps)},
         "cpu_baseline": base,
     }
     print(json.dumps(line))
     sess.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 def main():
@@ -339,6 +395,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="mlp", choices=["mlp", "lenet"],
+                    help="mlp = BASELINE configs[1] (default, the metric's config); lenet = configs[2]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -244,6 +244,13 @@ B200_API int b200_reduce_sum(int dtype, const void* in, float scale, void* out, 
 B200_API int b200_nccl_unique_id(void* id128_host);  /* writes 128 bytes */
 B200_API int b200_nccl_comm_init_rank(void** comm, int nranks, const void* id128_host, int rank);
 B200_API int b200_nccl_comm_destroy(void* comm);
+/* average != 0 -> ncclAvg (sum / ranks) so a gradient mean needs no separate scale kernel.
+ * Calls between group_start / group_end are aggregated by NCCL into ONE collective launch, so a
+ * set of gradient tensors is reduced without packing them into a staging buffer. */
+B200_API int b200_nccl_group_start(void);
+B200_API int b200_nccl_group_end(void);
+B200_API int b200_nccl_all_reduce(int dtype, const void* sendbuf, void* recvbuf, int64_t count,
+                                  int average, void* comm, void* stream);
 B200_API int b200_nccl_all_reduce_sum(int dtype, const void* sendbuf, void* recvbuf,
                                       int64_t count, void* comm, void* stream);
 

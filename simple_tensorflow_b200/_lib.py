@@ -99,6 +99,9 @@ SIGNATURES = {
     "b200_nccl_unique_id": (c_int, [c_void_p]),
     "b200_nccl_comm_init_rank": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_int]),
     "b200_nccl_comm_destroy": (c_int, [c_void_p]),
+    "b200_nccl_group_start": (c_int, []),
+    "b200_nccl_group_end": (c_int, []),
+    "b200_nccl_all_reduce": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "b200_nccl_all_reduce_sum": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
 }
 

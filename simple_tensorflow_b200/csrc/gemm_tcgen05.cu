@@ -842,7 +842,7 @@ static int plan_splits(long long tiles, int num_kb, int units) {
   if (tiles * 2 > units || num_kb < 8) return 1;
   long long splits = units / tiles;
   if (splits > num_kb / 4) splits = num_kb / 4;  // >= 4 K blocks per split
-  if (splits > 16) splits = 16;
+  if (splits > 64) splits = 64;  // scratch = splits * M * N * 4 bytes; callers size it from this plan
   return splits < 1 ? 1 : (int)splits;
 }
 

@@ -134,6 +134,8 @@ struct NcclApi {
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
 };
 static NcclApi g_nccl;
 static std::once_flag g_nccl_once;
@@ -154,6 +156,8 @@ static bool load_nccl() {
         reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(
             dlsym(h, "ncclAllReduce"));
     g_nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+    g_nccl.GroupStart = reinterpret_cast<int (*)()>(dlsym(h, "ncclGroupStart"));
+    g_nccl.GroupEnd = reinterpret_cast<int (*)()>(dlsym(h, "ncclGroupEnd"));
   });
   if (!g_nccl.handle || !g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllReduce) {
     set_last_error("NCCL: libnccl.so.2 could not be loaded (set B200TF_NCCL_LIB)");
@@ -360,6 +364,31 @@ int b200_nccl_comm_init_rank(void** comm, int nranks, const void* id128_host, in
 int b200_nccl_comm_destroy(void* comm) {
   if (!load_nccl()) return B200_FAILED_PRECONDITION;
   return nccl_rc(g_nccl.CommDestroy(comm), "ncclCommDestroy");
+}
+int b200_nccl_group_start(void) {
+  if (!load_nccl() || !g_nccl.GroupStart) return B200_FAILED_PRECONDITION;
+  return nccl_rc(g_nccl.GroupStart(), "ncclGroupStart");
+}
+int b200_nccl_group_end(void) {
+  if (!load_nccl() || !g_nccl.GroupEnd) return B200_FAILED_PRECONDITION;
+  return nccl_rc(g_nccl.GroupEnd(), "ncclGroupEnd");
+}
+int b200_nccl_all_reduce(int dtype, const void* sendbuf, void* recvbuf, int64_t count, int average,
+                         void* comm, void* stream) {
+  if (!load_nccl()) return B200_FAILED_PRECONDITION;
+  int nccl_type;
+  if (dtype == B200_DT_FLOAT)
+    nccl_type = 7;
+  else if (dtype == B200_DT_BFLOAT16)
+    nccl_type = 9;
+  else {
+    set_last_error("b200_nccl_all_reduce: unsupported dtype %d", dtype);
+    return B200_UNIMPLEMENTED;
+  }
+  if (count == 0) return B200_OK;
+  return nccl_rc(g_nccl.AllReduce(sendbuf, recvbuf, (size_t)count, nccl_type,
+                                  average ? /*ncclAvg*/ 4 : /*ncclSum*/ 0, comm, as_stream(stream)),
+                 "ncclAllReduce");
 }
 int b200_nccl_all_reduce_sum(int dtype, const void* sendbuf, void* recvbuf, int64_t count,
                              void* comm, void* stream) {

@@ -4,6 +4,7 @@
 // core/kernels/{constant_op,identity_op,reshape_op,shape_ops,no_op,variable_ops,assign_op,
 // aggregate_ops,cwise_op_mul_1,reduction_ops_mean,training_ops}.cc for the cases training
 // graphs of the hot path produce.
+#include <cmath>
 #include <memory>
 
 #include "tensorflow/core/common_runtime/device.h"
@@ -346,6 +347,10 @@ class B200AllReduceOp : public OpKernel {
   float scale_;
 };
 
+// N gradient tensors reduced across replicas by ONE NCCL launch: the per-tensor ncclAllReduce
+// calls sit inside ncclGroupStart/End, which NCCL aggregates into a single collective kernel on
+// the compute stream -- no packing copies, no host synchronisation.  scale == 1/replicas maps to
+// ncclAvg; any other scale runs as ncclSum followed by a scale kernel per tensor.
 template <typename T>
 class B200AllReduceNOp : public OpKernel {
  public:
@@ -357,34 +362,37 @@ class B200AllReduceNOp : public OpKernel {
     OP_REQUIRES(ctx, dev != nullptr, errors::Internal("B200AllReduceN needs a GPU device"));
     const int n = ctx->num_inputs();
     void* stream = GetCudaStream(ctx);
-    // 256-byte aligned slices so every slice keeps 16-byte vector alignment
-    std::vector<int64> offset(n + 1, 0);
-    for (int i = 0; i < n; ++i)
-      offset[i + 1] = offset[i] + (ctx->input(i).NumElements() + 127) / 128 * 128;
-    Tensor arena;
-    OP_REQUIRES_OK(ctx, ctx->allocate_temp(DataTypeToEnum<T>::v(), TensorShape({offset[n]}), &arena));
-    char* base = static_cast<char*>(arena.raw_data());
-    OP_REQUIRES_OK(ctx, FromAbi(b200_memset_async(base, 0, arena.TotalBytes(), stream), "arena"));
-    for (int i = 0; i < n; ++i)
-      OP_REQUIRES_OK(ctx, FromAbi(b200_memcpy_d2d_async(base + offset[i] * sizeof(T),
-                                                        ctx->input(i).raw_data(),
-                                                        ctx->input(i).TotalBytes(), stream),
-                                  "pack"));
-    if (dev->num_replicas() > 1 && dev->collective_comm() != nullptr)
-      OP_REQUIRES_OK(ctx, FromAbi(b200_nccl_all_reduce_sum(AbiType<T>::v, base, base, offset[n],
-                                                           dev->collective_comm(), stream),
-                                  "ncclAllReduce"));
-    if (scale_ != 1.0f)
-      OP_REQUIRES_OK(ctx, FromAbi(b200_scale(AbiType<T>::v, base, scale_, base, offset[n], stream),
-                                  "scale"));
-    for (int i = 0; i < n; ++i) {
-      Tensor* out = nullptr;
-      OP_REQUIRES_OK(ctx, ctx->allocate_output(i, ctx->input(i).shape(), &out));
-      OP_REQUIRES_OK(ctx, FromAbi(b200_memcpy_d2d_async(out->raw_data(),
-                                                        base + offset[i] * sizeof(T),
-                                                        out->TotalBytes(), stream),
-                                  "unpack"));
+    const bool collective = dev->num_replicas() > 1 && dev->collective_comm() != nullptr;
+    const bool average =
+        collective && std::fabs(scale_ * dev->num_replicas() - 1.0f) < 1e-6f;
+    std::vector<Tensor*> outs(n, nullptr);
+    for (int i = 0; i < n; ++i)  // reduce in place when this op is the buffer's only user
+      OP_REQUIRES_OK(ctx, ctx->forward_input_or_allocate_output({i}, i, ctx->input(i).shape(),
+                                                                &outs[i]));
+    if (collective) {
+      OP_REQUIRES_OK(ctx, FromAbi(b200_nccl_group_start(), "ncclGroupStart"));
+      Status s;
+      for (int i = 0; i < n; ++i)
+        s.Update(FromAbi(b200_nccl_all_reduce(AbiType<T>::v, ctx->input(i).raw_data(),
+                                              outs[i]->raw_data(), ctx->input(i).NumElements(),
+                                              average, dev->collective_comm(), stream),
+                         "ncclAllReduce"));
+      Status e = FromAbi(b200_nccl_group_end(), "ncclGroupEnd");
+      OP_REQUIRES_OK(ctx, s);
+      OP_REQUIRES_OK(ctx, e);
+    } else {
+      for (int i = 0; i < n; ++i)
+        if (outs[i]->raw_data() != ctx->input(i).raw_data())
+          OP_REQUIRES_OK(ctx, FromAbi(b200_memcpy_d2d_async(outs[i]->raw_data(),
+                                                            ctx->input(i).raw_data(),
+                                                            outs[i]->TotalBytes(), stream),
+                                      "copy"));
     }
+    if (!average && scale_ != 1.0f)
+      for (int i = 0; i < n; ++i)
+        OP_REQUIRES_OK(ctx, FromAbi(b200_scale(AbiType<T>::v, outs[i]->raw_data(), scale_,
+                                               outs[i]->raw_data(), outs[i]->NumElements(), stream),
+                                    "scale"));
   }
 
  private:

@@ -127,8 +127,8 @@ REGISTER_OP("B200AllReduce")
     .Input("data: Ref(T)").Output("out: Ref(T)").Attr("T: {float, bfloat16}")
     .Attr("scale: float = 1.0").SetIsStateful();
 
-// Fused form for gradient sets: packs the N tensors into one contiguous scratch arena, issues
-// exactly ONE ncclAllReduce on the compute stream, scales by `scale` and unpacks.
+// Fused form for gradient sets: the N per-tensor all-reduces are grouped (ncclGroupStart/End)
+// into ONE NCCL launch on the compute stream; `scale` = 1/replicas maps to ncclAvg.
 REGISTER_OP("B200AllReduceN")
     .Input("inputs: N * T").Output("outputs: N * T").Attr("N: int >= 1")
     .Attr("T: {float, bfloat16}").Attr("scale: float = 1.0").SetIsStateful();

@@ -207,6 +207,19 @@ def test_fusion_rewrite_matches_unfused(oracle, rng, monkeypatch):
         np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-5)
 
 
+def test_all_reduce_n_single_replica(rng):
+    # without a communicator the op is an identity (times scale): the N>1 path runs in bench.py
+    a = rng.randn(1000).astype(np.float32)
+    b = rng.randn(33, 7).astype(np.float32)
+    tf.reset_default_graph()
+    pa, pb = tf.placeholder(tf.float32, [1000]), tf.placeholder(tf.float32, [33, 7])
+    ra, rb = tf.all_reduce_n([tf.identity(pa), tf.identity(pb)], scale=0.5)
+    with client.Session(tf.get_default_graph()) as sess:
+        ga, gb = sess.run([ra, rb], {pa: a, pb: b})
+    np.testing.assert_array_equal(ga, a * np.float32(0.5))
+    np.testing.assert_array_equal(gb, b * np.float32(0.5))
+
+
 def test_session_error_behaviour(rng):
     tf.reset_default_graph()
     x = tf.placeholder(tf.float32, [4, 3], "x")
