@@ -27,44 +27,56 @@ struct ConvG {
   int ldk;  // leading dimension of the patch matrix (R*S*C rounded up to 16 bytes)
 };
 
-// One thread copies one 16-byte (or scalar) piece of one patch row.
+// Patch-matrix builder.  Thread (lane-in-row) owns ONE vector slot j of the patch row, so its filter
+// tap (r, s, c) is decoded once; the CTA then walks `rows_per_cta` output pixels, decoding each
+// pixel's (n, oh, ow) once per row-group instead of once per element (the first version spent its
+// time in ~10 integer divisions per 16 bytes).  Rows are written fully coalesced.
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
-im2col_kernel(const T* __restrict__ in, T* __restrict__ col, ConvG g, long long total) {
-  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
-  if (idx >= total) return;
-  const int per_row = g.ldk / V;  // vectors per patch row (incl. zero padding)
-  const int j = (int)(idx % per_row) * V;
-  const long long p = idx / per_row;  // output pixel index n*OH*OW + oh*OW + ow
-  T* dst = col + p * g.ldk + j;
+im2col_kernel(const T* __restrict__ in, T* __restrict__ col, ConvG g, long long rows,
+              int threads_per_row, int rows_per_cta) {
+  const int lane_in_row = threadIdx.x % threads_per_row;
+  const int row_in_group = threadIdx.x / threads_per_row;
+  const int groups = 256 / threads_per_row;  // pixel rows handled concurrently by the CTA
+  const int vecs_per_row = g.ldk / V;
   const int rsc = g.R * g.S * g.C;
-  if (j >= rsc) {
+  const long long row_begin = (long long)blockIdx.x * rows_per_cta;
+  long long row_end = row_begin + rows_per_cta;
+  if (row_end > rows) row_end = rows;
+  for (int jv = lane_in_row; jv < vecs_per_row; jv += threads_per_row) {
+    const int j = jv * V;
+    const bool pad_slot = j >= rsc;
+    const int c = pad_slot ? 0 : j % g.C;
+    const int tap = pad_slot ? 0 : j / g.C;
+    const int fs = tap % g.S, fr = tap / g.S;
+    // (n, oh, ow) of the first pixel by division once, then advanced incrementally
+    long long p = row_begin + row_in_group;
+    int ow = (int)(p % g.OW);
+    int oh = (int)((p / g.OW) % g.OH);
+    int n = (int)(p / ((long long)g.OW * g.OH));
+    for (; p < row_end; p += groups) {
+      const int ih = oh * g.sh - g.pt + fr, iw = ow * g.sw - g.pl + fs;
+      T* dst = col + p * g.ldk + j;
+      const bool inside = !pad_slot && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
+      if (V * sizeof(T) == 16) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (inside)
+          v = __ldg(reinterpret_cast<const uint4*>(
+              in + (((long long)n * g.H + ih) * g.W + iw) * g.C + c));
+        *reinterpret_cast<uint4*>(dst) = v;
+      } else {
+        const T* src = in + (((long long)n * g.H + ih) * g.W + iw) * g.C + c;
 #pragma unroll
-    for (int e = 0; e < V; ++e) dst[e] = T(0.f);
-    return;
-  }
-  const int c = j % g.C;
-  const int tap = j / g.C;
-  const int s = tap % g.S, r = tap / g.S;
-  const int ow = (int)(p % g.OW);
-  const long long q = p / g.OW;
-  const int oh = (int)(q % g.OH);
-  const int n = (int)(q / g.OH);
-  const int ih = oh * g.sh - g.pt + r, iw = ow * g.sw - g.pl + s;
-  if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) {
-    const T* src = in + (((long long)n * g.H + ih) * g.W + iw) * g.C + c;
-    if (V * sizeof(T) == 16) {
-      *reinterpret_cast<uint4*>(dst) = __ldg(reinterpret_cast<const uint4*>(src));
-    } else {
-#pragma unroll
-      for (int e = 0; e < V; ++e) dst[e] = src[e];
-    }
-  } else {
-    if (V * sizeof(T) == 16) {
-      *reinterpret_cast<uint4*>(dst) = make_uint4(0, 0, 0, 0);
-    } else {
-#pragma unroll
-      for (int e = 0; e < V; ++e) dst[e] = T(0.f);
+        for (int e = 0; e < V; ++e) dst[e] = inside ? src[e] : T(0.f);
+      }
+      ow += groups;
+      while (ow >= g.OW) {
+        ow -= g.OW;
+        if (++oh == g.OH) {
+          oh = 0;
+          ++n;
+        }
+      }
     }
   }
 }
@@ -177,14 +189,26 @@ template <typename T>
 static int run_im2col(const void* in, void* col, const ConvG& g, cudaStream_t s) {
   constexpr int V16 = 16 / sizeof(T);
   const long long rows = (long long)g.N * g.OH * g.OW;
+  auto plan = [&](int vecs_per_row, int* tpr, int* rpc) {
+    int t = 32;  // threads per patch row: power of two in [32, 256]
+    while (t < vecs_per_row && t < 256) t <<= 1;
+    *tpr = t;
+    const int groups = 256 / t;
+    // ~4 waves of CTAs over the SMs, at least one row per group
+    long long r = (rows + 4LL * sm_count() - 1) / (4LL * sm_count());
+    r = (r + groups - 1) / groups * groups;
+    if (r < groups) r = groups;
+    *rpc = (int)r;
+  };
+  int tpr, rpc;
   if (g.C % V16 == 0 && aligned16(in) && aligned16(col)) {
-    const long long total = rows * (g.ldk / V16);
-    im2col_kernel<T, V16><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-        static_cast<const T*>(in), static_cast<T*>(col), g, total);
+    plan(g.ldk / V16, &tpr, &rpc);
+    im2col_kernel<T, V16><<<(unsigned)((rows + rpc - 1) / rpc), 256, 0, s>>>(
+        static_cast<const T*>(in), static_cast<T*>(col), g, rows, tpr, rpc);
   } else {
-    const long long total = rows * g.ldk;
-    im2col_kernel<T, 1><<<(unsigned)((total + 255) / 256), 256, 0, s>>>(
-        static_cast<const T*>(in), static_cast<T*>(col), g, total);
+    plan(g.ldk, &tpr, &rpc);
+    im2col_kernel<T, 1><<<(unsigned)((rows + rpc - 1) / rpc), 256, 0, s>>>(
+        static_cast<const T*>(in), static_cast<T*>(col), g, rows, tpr, rpc);
   }
   note_launch();
   return check_launch("im2col");

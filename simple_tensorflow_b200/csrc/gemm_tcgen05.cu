@@ -31,7 +31,8 @@ constexpr int kGemmThreads = 192;
 // Epilogue staging: 4 warps x 2 buffers x (32 rows x 128 B), 128B-swizzled, drained by TMA stores.
 constexpr int kEpiBufBytes = 32 * kSwizzleBytes;
 constexpr int kEpiStageBytes = 4 * 2 * kEpiBufBytes;  // store staging
-constexpr int kEpiFeatBytes = 4 * 2 * kEpiBufBytes;   // ReluGrad-features staging (TMA loads)
+constexpr int kFeatBufs = 4;                          // feature tiles in flight per epilogue warp
+constexpr int kEpiFeatBytes = 4 * kFeatBufs * kEpiBufBytes;  // ReluGrad-features / bias staging
 
 template <typename T>
 struct GemmTraits;
@@ -58,7 +59,9 @@ struct GemmTraits<__nv_bfloat16> {
 template <int BN, int kCtas>
 constexpr int gemm_stages() {
   // stage = A (16 KiB) + B (BN / kCtas rows of 128 B)
-  return (BN / kCtas) >= 256 ? 3 : ((BN / kCtas) >= 128 ? 5 : 6);
+  // The main loop is L2-bandwidth bound (~54 GB/s per SM x ~1 us latency = 54 KB in flight), so
+  // 4 stages of 32 KiB are plenty; the smem saved feeds the epilogue's prefetch buffers.
+  return (BN / kCtas) >= 256 ? 2 : ((BN / kCtas) >= 128 ? 4 : 5);
 }
 template <int BN, int kCtas>
 constexpr size_t gemm_smem_bytes() {
@@ -86,6 +89,8 @@ struct GemmShape {
   int feat_tma;          // 1: features are fetched by TMA through tmapF (prefetched, coalesced)
   int bias_vec;          // 1: bias pointer is 16-byte aligned (vector loads)
 };
+
+__device__ __forceinline__ bool partial_out_tile(const GemmShape& s) { return s.splits > 1; }
 
 __device__ __forceinline__ void store_row32(float* dst, const uint32_t (&v)[32], int ncols,
                                             bool vec_ok) {
@@ -138,6 +143,8 @@ template <typename TOut, int BN>
 __host__ __device__ constexpr int partial_out_iters() {
   return BN / 32;
 }
+struct GemmShape;
+__device__ __forceinline__ bool partial_out_tile(const GemmShape& s);
 
 // TIn: operand element type (float -> tf32 MMA, bf16 -> f16-kind MMA); TOut: stored type.
 template <typename TIn, typename TOut, bool kAMN, bool kBMN, int BN, int kCtas>
@@ -172,8 +179,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
   uint64_t* empty_bar = bars + kStages;         // [kStages]
   uint64_t* tfull_bar = bars + 2 * kStages;     // [2]
   uint64_t* tempty_bar = bars + 2 * kStages + 2;  // [2]  (kCtas = 2: the leader's is used)
-  uint64_t* feat_bar = bars + 2 * kStages + 4;    // [4 warps][2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 12);
+  uint64_t* feat_bar = bars + 2 * kStages + 4;    // [4 warps][kFeatBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + 4 * kFeatBufs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -206,7 +213,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
         mbar_init(&tfull_bar[i], 1);
         mbar_init(&tempty_bar[i], 4 * kCtas);  // one arrive per epilogue warp (of both CTAs)
       }
-      for (int i = 0; i < 8; ++i) mbar_init(&feat_bar[i], 1);
+      for (int i = 0; i < 4 * kFeatBufs; ++i) mbar_init(&feat_bar[i], 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -364,16 +371,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
     uint32_t acc = 0, acc_phase = 0;
     uint32_t ebuf = 0, stores_in_flight = 0;
     uint8_t* my_stage = smEpi + quad * 2 * kEpiBufBytes;
-    uint8_t* my_feat = smFeat + quad * 2 * kEpiBufBytes;
-    uint64_t* my_fbar = feat_bar + quad * 2;
-    uint32_t feat_issued = 0, feat_used = 0;  // running chunk counters (buffer = n & 1)
+    uint8_t* my_feat = smFeat + quad * kFeatBufs * kEpiBufBytes;
+    uint64_t* my_fbar = feat_bar + quad * kFeatBufs;
+    uint32_t feat_issued = 0, feat_used = 0;  // running chunk counters (buffer = n % kFeatBufs)
     const bool feat_on = s.relu_grad_features != nullptr && s.feat_tma && s.splits == 1;
     // ReluGrad features do not depend on the MMA: fetch them (coalesced, via TMA) ahead of use.
     auto issue_feat = [&](int col, int row0f, int bidx) {
       if (lane == 0) {
-        uint64_t* fb = &my_fbar[feat_issued & 1];
+        uint64_t* fb = &my_fbar[feat_issued % kFeatBufs];
         mbar_expect_tx(fb, kEpiBufBytes);
-        tma_load_3d(my_feat + (feat_issued & 1) * kEpiBufBytes, &tmapF, fb, col, row0f, bidx);
+        tma_load_3d(my_feat + (feat_issued % kFeatBufs) * kEpiBufBytes, &tmapF, fb, col, row0f,
+                    bidx);
       }
       ++feat_issued;
     };
@@ -388,9 +396,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
       const int m0 = (t % tiles_m) * kTileM + (int)cta_rank * kBM;
       const int n0 = (t / tiles_m) * BN;
       const int row0 = m0 + quad * 32;
-      if (feat_on) {  // chunks 0 and 1 of this tile, before waiting for the accumulator
-        issue_feat(n0, row0, b);
-        if (n0 + kEpiCols < s.N && BN > kEpiCols) issue_feat(n0 + kEpiCols, row0, b);
+      if (feat_on) {  // the first kFeatBufs chunks of this tile, while the MMAs are still running
+#pragma unroll
+        for (int pc = 0; pc < kFeatBufs; ++pc)
+          if (pc * kEpiCols < BN && n0 + pc * kEpiCols < s.N) issue_feat(n0 + pc * kEpiCols, row0, b);
+      }
+      // Bias slice of this tile -> this warp's (otherwise unused) feature staging, also ahead of
+      // the accumulator: the per-chunk broadcast reads then hit smem instead of exposing an L2
+      // round trip per chunk.
+      const bool bias_smem = s.bias != nullptr && s.bias_vec && !partial_out_tile(s) &&
+                             !feat_on && n0 + BN <= s.N;
+      if (bias_smem) {
+        const uint4* bsrc = reinterpret_cast<const uint4*>(static_cast<const TOut*>(s.bias) + n0);
+        uint4* bdst = reinterpret_cast<uint4*>(my_feat);
+        constexpr int kVecs = BN * (int)sizeof(TOut) / 16;
+        for (int i = lane; i < kVecs; i += 32) bdst[i] = __ldg(bsrc + i);
+        __syncwarp();
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
@@ -427,9 +448,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
             const TOut* bp = static_cast<const TOut*>(s.bias) + col;
             if (s.bias_vec && col + kEpiCols <= s.N) {
               // every lane reads the same 128 bytes: 8 broadcast 16-byte loads
+              const uint4* bsm = reinterpret_cast<const uint4*>(my_feat) + c * 8;
 #pragma unroll
               for (int q4 = 0; q4 < 8; ++q4) {
-                const uint4 bw = __ldg(reinterpret_cast<const uint4*>(bp) + q4);
+                const uint4 bw = bias_smem ? bsm[q4] : __ldg(reinterpret_cast<const uint4*>(bp) + q4);
                 const uint32_t bwv[4] = {bw.x, bw.y, bw.z, bw.w};
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
@@ -462,9 +484,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
           }
           if (feat_on) {
             // this chunk's features were staged by TMA as [32 rows][128 B], 128B-swizzled
-            mbar_wait(&my_fbar[feat_used & 1], (feat_used >> 1) & 1);
+            mbar_wait(&my_fbar[feat_used % kFeatBufs], (feat_used / kFeatBufs) & 1);
             const uint32_t fbase =
-                smem_u32(my_feat + (feat_used & 1) * kEpiBufBytes) + lane * kSwizzleBytes;
+                smem_u32(my_feat + (feat_used % kFeatBufs) * kEpiBufBytes) + lane * kSwizzleBytes;
 #pragma unroll
             for (int q4 = 0; q4 < 8; ++q4) {
               uint32_t f0, f1, f2, f3;
@@ -490,8 +512,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
             }
             ++feat_used;
             __syncwarp();  // every lane has read the buffer: it may be refilled
-            const int next_col = col + 2 * kEpiCols;
-            if (c + 2 < iters && next_col < s.N) issue_feat(next_col, row0, b);
+            const int next_col = col + kFeatBufs * kEpiCols;
+            if (c + kFeatBufs < iters && next_col < s.N) issue_feat(next_col, row0, b);
           } else if (s.relu_grad_features != nullptr && row < s.M) {
             const TOut* fp = static_cast<const TOut*>(s.relu_grad_features) +
                              (long long)row * s.ld_features + col;

@@ -109,7 +109,55 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict
   }
 }
 
+// Skinny GEMM for N <= 32 (e.g. the 10-class logits layer and its weight gradient): one warp per
+// output row, lanes stride over K, N accumulators per lane, shuffle reduction at the end.  The
+// 64x64-tile kernel above would put such a problem on a handful of CTAs.
+template <typename T, int NMAX>
+__global__ void __launch_bounds__(256)
+gemm_skinny_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int M, int N,
+                   int K, long long lda, long long ldb, long long ldc, bool a_mn, bool b_mn) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= M) return;
+  float acc[NMAX];
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) acc[j] = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float a = to_f32<T>(a_mn ? A[(long long)k * lda + row] : A[(long long)row * lda + k]);
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j)
+      if (j < N)
+        acc[j] = fmaf(a, to_f32<T>(b_mn ? B[(long long)k * ldb + j] : B[(long long)j * ldb + k]),
+                      acc[j]);
+  }
+#pragma unroll
+  for (int j = 0; j < NMAX; ++j) {
+    float v = acc[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0 && j < N) C[(long long)row * ldc + j] = from_f32<T>(v);
+  }
+}
+
 int gemm_simt(const GemmArgs& g, cudaStream_t stream) {
+  if (g.batch == 1 && g.N <= 32 && g.K >= 64 && g.M >= 64) {
+    const unsigned grid = (unsigned)((g.M + 7) / 8);
+#define SKINNY(T, NMAX)                                                                      \
+  gemm_skinny_kernel<T, NMAX><<<grid, 256, 0, stream>>>(                                     \
+      static_cast<const T*>(g.a), static_cast<const T*>(g.b), static_cast<T*>(g.c), (int)g.M, \
+      (int)g.N, (int)g.K, g.lda, g.ldb, g.ldc, g.a_mn_major, g.b_mn_major)
+    if (g.dtype == B200_DT_FLOAT) {
+      if (g.N <= 16) SKINNY(float, 16); else SKINNY(float, 32);
+    } else if (g.dtype == B200_DT_BFLOAT16) {
+      if (g.N <= 16) SKINNY(__nv_bfloat16, 16); else SKINNY(__nv_bfloat16, 32);
+    } else {
+      set_last_error("gemm_simt: unsupported dtype %d", g.dtype);
+      return B200_UNIMPLEMENTED;
+    }
+#undef SKINNY
+    note_launch();
+    return check_launch("gemm_skinny");
+  }
   if (g.batch > 65535) {
     set_last_error("gemm_simt: batch %lld exceeds grid.z limit", g.batch);
     return B200_UNIMPLEMENTED;

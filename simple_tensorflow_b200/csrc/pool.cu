@@ -164,6 +164,57 @@ max_pool_grad_kernel(const T* __restrict__ in, const T* __restrict__ grad, T* __
   PoolVec<T, V>::store(dx + idx * V, acc);
 }
 
+// Non-overlapping windows (stride >= window, the LeNet 2x2/2 case): every input cell belongs to at
+// most one window, so one thread per OUTPUT cell reads its window once, finds the first maximum and
+// writes the whole window's gradients (winner = grad, others = 0).  Each input is read exactly
+// once and nothing is recomputed; cells covered by no window are zeroed by a memset beforehand
+// (only needed when the windows do not tile the input).
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+max_pool_grad_disjoint_kernel(const T* __restrict__ in, const T* __restrict__ grad,
+                              T* __restrict__ dx, PoolGeom g, long long total) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int CV = g.C / V;
+  const int cv = (int)(idx % CV);
+  long long r = idx / CV;
+  const int ow = (int)(r % g.OW);
+  r /= g.OW;
+  const int oh = (int)(r % g.OH);
+  const int n = (int)(r / g.OH);
+  int h0 = oh * g.sh - g.pt, w0 = ow * g.sw - g.pl;
+  const int h1 = min(h0 + g.wh, g.H), w1 = min(w0 + g.ww, g.W);
+  h0 = max(h0, 0);
+  w0 = max(w0, 0);
+  const long long ibase = ((long long)n * g.H * g.W) * g.C + (long long)cv * V;
+  float best[V], gv[V];
+  int arg[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    best[j] = -FLT_MAX;
+    arg[j] = -1;
+  }
+  for (int h = h0; h < h1; ++h)
+    for (int w = w0; w < w1; ++w) {
+      float v[V];
+      PoolVec<T, V>::load(in + ibase + ((long long)h * g.W + w) * g.C, v);
+#pragma unroll
+      for (int j = 0; j < V; ++j)
+        if (best[j] < v[j] || arg[j] == -1) {  // maxpooling_op.cc:139-144: first maximum wins
+          best[j] = v[j];
+          arg[j] = h * g.W + w;
+        }
+    }
+  PoolVec<T, V>::load(grad + idx * V, gv);
+  for (int h = h0; h < h1; ++h)
+    for (int w = w0; w < w1; ++w) {
+      float o[V];
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = (arg[j] == h * g.W + w) ? gv[j] : 0.f;
+      PoolVec<T, V>::store(dx + ibase + ((long long)h * g.W + w) * g.C, o);
+    }
+}
+
 static int check_pool_args(const char* what, int dtype, int64_t batch, int64_t in_h, int64_t in_w,
                            int64_t channels, int64_t out_h, int64_t out_w, int window_h,
                            int window_w, int stride_h, int stride_w, int pad_top, int pad_left,
@@ -255,6 +306,32 @@ int b200_max_pool_grad(int dtype, const void* orig_in, const void* orig_out, con
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
   const bool al = aligned16(orig_in) && aligned16(grad) && aligned16(in_backprop);
+  if (stride_h >= window_h && stride_w >= window_w && out_h > 0 && out_w > 0) {
+    // disjoint windows: do they tile the whole input?
+    const bool tiles = stride_h == window_h && stride_w == window_w && pad_top == 0 &&
+                       pad_left == 0 && out_h * stride_h >= in_h && out_w * stride_w >= in_w;
+    const size_t es = dtype == B200_DT_FLOAT ? 4 : 2;
+    if (!tiles) {
+      rc = b200_memset_async(in_backprop, 0, (size_t)nin * es, stream);
+      if (rc) return rc;
+    }
+    const long long nout = (long long)batch * out_h * out_w * channels;
+#define POOLG(T, V)                                                                            \
+  do {                                                                                         \
+    const long long t = nout / V;                                                              \
+    max_pool_grad_disjoint_kernel<T, V><<<(unsigned)((t + 255) / 256), 256, 0, s>>>(           \
+        static_cast<const T*>(orig_in), static_cast<const T*>(grad), static_cast<T*>(in_backprop), \
+        g, t);                                                                                 \
+  } while (0)
+    if (dtype == B200_DT_FLOAT) {
+      if (al && channels % 4 == 0) POOLG(float, 4); else POOLG(float, 1);
+    } else {
+      if (al && channels % 8 == 0) POOLG(__nv_bfloat16, 8); else POOLG(__nv_bfloat16, 1);
+    }
+#undef POOLG
+    note_launch();
+    return check_launch("b200_max_pool_grad");
+  }
   if (dtype == B200_DT_FLOAT) {
     if (al && channels % 4 == 0) {
       const long long t = nin / 4;
