@@ -18,6 +18,11 @@ struct DriverApi {
                                      const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  CUresult (*cuTensorMapEncodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                      const cuuint64_t*, const cuuint64_t*, const int*, const int*,
+                                      cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                      CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 };
 const DriverApi& driver();
 
@@ -29,6 +34,12 @@ int require_device(const char* what); // B200_INTERNAL when no CUDA device is us
 inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 
 // ------------------------------------------------------------------ GEMM plumbing
+// Implicit-GEMM convolution: the A operand [N*OH*OW, R*S*C] is never materialised; the GEMM's TMA
+// producer gathers it from the NHWC activation tensor with im2col-mode loads.
+struct ConvAOperand {
+  const void* input;  // NHWC
+  int N, H, W, C, R, S, OH, OW, sh, sw, pt, pl;
+};
 struct GemmArgs {
   int dtype;                 // B200_DT_FLOAT or B200_DT_BFLOAT16
   const void* a;             // logical A[M,K]
@@ -47,8 +58,11 @@ struct GemmArgs {
   bool relu;                       // max(x, 0)
   const void* relu_grad_features;  // x * (features[row, col] > 0), features [M, N]
   long long ld_features;
+  const ConvAOperand* conv_a;      // non-null: A is gathered on the fly (a / lda unused)
 };
 bool gemm_tcgen05_supported(const GemmArgs& g);
+// Can this convolution's patch operand be fetched by TMA im2col (channel / padding limits)?
+bool conv_a_supported(int dtype, const ConvAOperand& c);
 int gemm_tcgen05(const GemmArgs& g, cudaStream_t stream);
 int gemm_simt(const GemmArgs& g, cudaStream_t stream);
 // Precision-aware front door used by matmul / batch_matmul / conv.

@@ -75,6 +75,19 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+// im2col-mode load of an NHWC activation tensor (map dims C, W, H, N): `pixelsPerColumn` output
+// pixels starting at input-space base (w, h, n), `channelsPerPixel` channels from c, filter tap
+// offset (off_w, off_h).  Padding and image/batch wrap-around are resolved by the TMA unit.
+__device__ __forceinline__ void tma_load_im2col_4d(void* smem_dst, const CUtensorMap* m,
+                                                   uint64_t* bar, int c, int w, int h, int n,
+                                                   uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c), "r"(w), "r"(h), "r"(n),
+      "h"(off_w), "h"(off_h)
+      : "memory");
+}
 // 3-D tiled store shared -> global (bulk group completion).
 __device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* smem_src, int c0,
                                              int c1, int c2) {
@@ -198,6 +211,17 @@ __device__ __forceinline__ void tma_load_4d_2cta(void* smem_dst, const CUtensorM
           smem_u32(smem_dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1),
       "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_2cta(void* smem_dst, const CUtensorMap* m,
+                                                        uint64_t* bar, int c, int w, int h, int n,
+                                                        uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global"
+      ".mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & kPeerBitMask), "r"(c), "r"(w),
+      "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
 template <int kCols>

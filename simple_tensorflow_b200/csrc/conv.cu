@@ -17,6 +17,7 @@
 // Round-1 data path: the patch matrix is materialised in the caller-provided workspace; the
 // implicit-GEMM (TMA im2col) variant that removes this traffic is the next optimisation step.
 #include <cuda_bf16.h>
+#include <cstdlib>
 
 #include "b200_internal.h"
 
@@ -136,6 +137,21 @@ col2im_gather_kernel(const T* __restrict__ col, T* __restrict__ dx, ConvG g, lon
   dx[idx] = cvt_out<T>(acc);
 }
 
+// dInput as a forward convolution of dY: filter'[r', s', k, c] = filter[R-1-r', S-1-s', c, k]
+// (spatially flipped, in/out channels swapped).  R*S*C*K elements: negligible next to the conv.
+template <typename T>
+__global__ void __launch_bounds__(256)
+flip_filter_kernel(const T* __restrict__ w, T* __restrict__ wt, int R, int S, int C, int K) {
+  const int i = blockIdx.x * 256 + threadIdx.x;  // index into wt [R, S, K, C]
+  if (i >= R * S * C * K) return;
+  const int c = i % C;
+  int t = i / C;
+  const int k = t % K;
+  t /= K;
+  const int s2 = t % S, r2 = t / S;
+  wt[i] = w[(((R - 1 - r2) * S + (S - 1 - s2)) * C + c) * K + k];
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static inline size_t esize_of(int dtype) { return dtype == B200_DT_FLOAT ? 4 : 2; }
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -234,9 +250,35 @@ size_t b200_conv2d_workspace_bytes(int dtype, const b200_conv2d_geometry* geom, 
   const long long rows = (long long)g.N * g.OH * g.OW;
   const long long rsc = (long long)g.R * g.S * g.C;
   const size_t col = is_pointwise(g) ? 0 : align256((size_t)rows * g.ldk * es);
-  if (which == 0) return col + align256(gemm_workspace_bytes(dtype, rows, g.K, rsc, 1));
-  if (which == 1) return col + align256(gemm_workspace_bytes(dtype, rows, rsc, g.K, 1));
-  if (which == 2) return col + align256(gemm_workspace_bytes(dtype, rsc, g.K, rows, 1));
+  if (which == 0) {
+    // implicit GEMM needs no patch matrix (decided again at launch from the real pointers)
+    ConvAOperand ca{reinterpret_cast<const void*>(16), g.N, g.H, g.W, g.C, g.R, g.S, g.OH, g.OW,
+                    g.sh, g.sw, g.pt, g.pl};
+    if (!is_pointwise(g) && getenv("B200TF_CONV_EXPLICIT") == nullptr &&
+        b200_get_matmul_precision() == 0 && (g.K % (16 / (int)es)) == 0 &&
+        conv_a_supported(dtype, ca))
+      return 0;
+    return col + align256(gemm_workspace_bytes(dtype, rows, g.K, rsc, 1));
+  }
+  if (which == 1) {
+    // stride-1 dInput = implicit forward conv of dY with the flipped filter: scratch = that filter
+    ConvAOperand cd{reinterpret_cast<const void*>(16), g.N, g.OH, g.OW, g.K, g.R, g.S, g.H, g.W,
+                    1, 1, g.R - 1 - g.pt, g.S - 1 - g.pl};
+    if (!is_pointwise(g) && g.sh == 1 && g.sw == 1 && getenv("B200TF_CONV_EXPLICIT") == nullptr &&
+        b200_get_matmul_precision() == 0 && (g.C % (16 / (int)es)) == 0 &&
+        g.R - 1 - g.pt >= 0 && g.S - 1 - g.pl >= 0 && conv_a_supported(dtype, cd))
+      return align256((size_t)rsc * g.K * es);
+    return col + align256(gemm_workspace_bytes(dtype, rows, rsc, g.K, 1));
+  }
+  if (which == 2) {
+    ConvAOperand ca{reinterpret_cast<const void*>(16), g.N, g.H, g.W, g.C, g.R, g.S, g.OH, g.OW,
+                    g.sh, g.sw, g.pt, g.pl};
+    if (!is_pointwise(g) && getenv("B200TF_CONV_EXPLICIT") == nullptr &&
+        b200_get_matmul_precision() == 0 && (g.K % (16 / (int)es)) == 0 &&
+        conv_a_supported(dtype, ca))
+      return align256(gemm_workspace_bytes(dtype, rsc, g.K, rows, 1));  // split-K partials only
+    return col + align256(gemm_workspace_bytes(dtype, rsc, g.K, rows, 1));
+  }
   return 0;
 }
 
@@ -269,13 +311,29 @@ int b200_conv2d(int dtype, const void* input, const void* filter, void* output,
   a.ldc = g.K;
   a.a_mn_major = false;
   a.b_mn_major = true;
+  ConvAOperand ca{input, g.N, g.H, g.W, g.C, g.R, g.S, g.OH, g.OW, g.sh, g.sw, g.pt, g.pl};
+  static const bool no_implicit = getenv("B200TF_CONV_EXPLICIT") != nullptr;
   if (is_pointwise(g)) {
     a.a = input;
     a.lda = g.C;
     a.workspace = workspace;
     a.workspace_bytes = workspace ? workspace_bytes : 0;
+  } else if (!no_implicit && b200_get_matmul_precision() == 0 && (g.K % (16 / (int)es)) == 0 &&
+             aligned16(filter) && conv_a_supported(dtype, ca)) {
+    // implicit GEMM: the TMA producer gathers patch rows straight from the NHWC input
+    a.a = input;  // unused by the kernel, kept non-null for validation
+    a.lda = g.C;
+    a.conv_a = &ca;
+    a.workspace = nullptr;
+    a.workspace_bytes = 0;
+    return gemm_tcgen05(a, s);
   } else {
     const size_t col_bytes = align256((size_t)rows * g.ldk * es);
+    if (!workspace || workspace_bytes < col_bytes) {  // e.g. unaligned pointers ruled out TMA im2col
+      set_last_error("b200_conv2d: the patch-matrix path needs %zu bytes of workspace, got %zu",
+                     col_bytes, workspace_bytes);
+      return B200_INVALID_ARGUMENT;
+    }
     rc = dtype == B200_DT_FLOAT ? run_im2col<float>(input, workspace, g, s)
                                 : run_im2col<__nv_bfloat16>(input, workspace, g, s);
     if (rc) return rc;
@@ -318,6 +376,18 @@ int b200_conv2d_backprop_filter(int dtype, const void* input, const void* out_ba
   a.ldc = g.K;
   a.a_mn_major = true;  // A^T is stored: patches [rows, R*S*C]
   a.b_mn_major = true;
+  ConvAOperand ca{input, g.N, g.H, g.W, g.C, g.R, g.S, g.OH, g.OW, g.sh, g.sw, g.pt, g.pl};
+  static const bool no_implicit = getenv("B200TF_CONV_EXPLICIT") != nullptr;
+  if (!is_pointwise(g) && !no_implicit && b200_get_matmul_precision() == 0 &&
+      (g.K % (16 / (int)es)) == 0 && aligned16(out_backprop) && conv_a_supported(dtype, ca)) {
+    // implicit GEMM: im2col boxes feed the MN-major A operand directly (no patch matrix)
+    a.a = input;
+    a.lda = g.C;
+    a.conv_a = &ca;
+    a.workspace = workspace;
+    a.workspace_bytes = workspace ? workspace_bytes : 0;
+    return gemm_tcgen05(a, s);
+  }
   if (is_pointwise(g)) {
     a.a = input;
     a.lda = g.C;
@@ -325,6 +395,11 @@ int b200_conv2d_backprop_filter(int dtype, const void* input, const void* out_ba
     a.workspace_bytes = workspace ? workspace_bytes : 0;
   } else {
     const size_t col_bytes = align256((size_t)rows * g.ldk * es);
+    if (!workspace || workspace_bytes < col_bytes) {
+      set_last_error("b200_conv2d_backprop_filter: the patch-matrix path needs %zu bytes of "
+                     "workspace, got %zu", col_bytes, workspace_bytes);
+      return B200_INVALID_ARGUMENT;
+    }
     rc = dtype == B200_DT_FLOAT ? run_im2col<float>(input, workspace, g, s)
                                 : run_im2col<__nv_bfloat16>(input, workspace, g, s);
     if (rc) return rc;
@@ -358,6 +433,38 @@ int b200_conv2d_backprop_input(int dtype, const void* filter, const void* out_ba
                    workspace_bytes, need);
     return B200_INVALID_ARGUMENT;
   }
+  {
+    ConvAOperand cd{out_backprop, g.N, g.OH, g.OW, g.K, g.R, g.S, g.H, g.W,
+                    1, 1, g.R - 1 - g.pt, g.S - 1 - g.pl};
+    static const bool no_implicit = getenv("B200TF_CONV_EXPLICIT") != nullptr;
+    if (!is_pointwise(g) && g.sh == 1 && g.sw == 1 && !no_implicit &&
+        b200_get_matmul_precision() == 0 && (g.C % (16 / (int)es)) == 0 && cd.pt >= 0 &&
+        cd.pl >= 0 && aligned16(in_backprop) && conv_a_supported(dtype, cd)) {
+      const int nflt = g.R * g.S * g.C * g.K;
+      if (dtype == B200_DT_FLOAT)
+        flip_filter_kernel<float><<<(nflt + 255) / 256, 256, 0, s>>>(
+            static_cast<const float*>(filter), static_cast<float*>(workspace), g.R, g.S, g.C, g.K);
+      else
+        flip_filter_kernel<__nv_bfloat16><<<(nflt + 255) / 256, 256, 0, s>>>(
+            static_cast<const __nv_bfloat16*>(filter), static_cast<__nv_bfloat16*>(workspace), g.R,
+            g.S, g.C, g.K);
+      note_launch();
+      GemmArgs d = base_gemm(dtype);
+      d.a = out_backprop;
+      d.lda = g.K;
+      d.conv_a = &cd;
+      d.b = workspace;  // [R*S*K, C] row-major
+      d.ldb = g.C;
+      d.b_mn_major = true;
+      d.a_mn_major = false;
+      d.c = in_backprop;
+      d.ldc = g.C;
+      d.M = (long long)g.N * g.H * g.W;
+      d.N = g.C;
+      d.K = (long long)g.R * g.S * g.K;
+      return gemm_tcgen05(d, s);
+    }
+  }
   GemmArgs a = base_gemm(dtype);
   a.a = out_backprop;  // [rows, K]
   a.lda = g.K;
@@ -376,6 +483,11 @@ int b200_conv2d_backprop_input(int dtype, const void* filter, const void* out_ba
     return gemm_dispatch(a, s);
   }
   const size_t col_bytes = align256((size_t)rows * g.ldk * es);
+  if (!workspace || workspace_bytes < col_bytes) {
+    set_last_error("b200_conv2d_backprop_input: the patch-matrix path needs %zu bytes of "
+                   "workspace, got %zu", col_bytes, workspace_bytes);
+    return B200_INVALID_ARGUMENT;
+  }
   a.c = workspace;
   a.ldc = g.ldk;
   a.workspace = static_cast<char*>(workspace) + col_bytes;

@@ -81,6 +81,13 @@ static inline unsigned blocks_for(long long items, int per_block) {
   long long b = (items + per_block - 1) / per_block;
   return (unsigned)(b < 1 ? 1 : b);
 }
+// grid for the persistent (grid-stride) kernels: at most 8 resident CTAs of 256 threads per SM
+static inline unsigned persistent_blocks(long long items, int per_block) {
+  const long long cap = 8LL * sm_count();
+  long long b = (items + per_block - 1) / per_block;
+  if (b > cap) b = cap;
+  return (unsigned)(b < 1 ? 1 : b);
+}
 
 // ------------------------------------------------------------------ generic n-ary map
 // out[i] = f(in0[i], in1[i], ...) ; NIN inputs, one output, same dtype.
@@ -88,26 +95,30 @@ template <typename T, int NIN, typename F>
 __global__ void __launch_bounds__(kThreads)
 map_vec_kernel(const T* a, const T* b, T* out, long long nvec, F f) {
   constexpr int N = Lanes<T>::kN;
-  const long long base = ((long long)blockIdx.x * kThreads * kUnroll) + threadIdx.x;
-  uint4 va[kUnroll], vb[kUnroll];
+  // Persistent grid-stride loop: the grid is capped at ~8 CTAs per SM so a 16-64 MB tensor is
+  // covered without CTA wave transitions (each costs ~1 us, B300_MICROARCH "T_wave_trans").
+  for (long long base = ((long long)blockIdx.x * kThreads * kUnroll) + threadIdx.x; base < nvec;
+       base += (long long)gridDim.x * kThreads * kUnroll) {
+    uint4 va[kUnroll], vb[kUnroll];
 #pragma unroll
-  for (int u = 0; u < kUnroll; ++u) {
-    const long long i = base + (long long)u * kThreads;
-    if (i < nvec) {
-      va[u] = ld16_rw(a + i * N);
-      if (NIN > 1) vb[u] = ld16_rw(b + i * N);
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = base + (long long)u * kThreads;
+      if (i < nvec) {
+        va[u] = ld16_rw(a + i * N);
+        if (NIN > 1) vb[u] = ld16_rw(b + i * N);
+      }
     }
-  }
 #pragma unroll
-  for (int u = 0; u < kUnroll; ++u) {
-    const long long i = base + (long long)u * kThreads;
-    if (i < nvec) {
-      float x[N], y[N], r[N];
-      Lanes<T>::unpack(va[u], x);
-      if (NIN > 1) Lanes<T>::unpack(vb[u], y);
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = base + (long long)u * kThreads;
+      if (i < nvec) {
+        float x[N], y[N], r[N];
+        Lanes<T>::unpack(va[u], x);
+        if (NIN > 1) Lanes<T>::unpack(vb[u], y);
 #pragma unroll
-      for (int j = 0; j < N; ++j) r[j] = f(x[j], NIN > 1 ? y[j] : 0.f);
-      st16(out + i * N, Lanes<T>::pack(r));
+        for (int j = 0; j < N; ++j) r[j] = f(x[j], NIN > 1 ? y[j] : 0.f);
+        st16(out + i * N, Lanes<T>::pack(r));
+      }
     }
   }
 }
@@ -133,7 +144,7 @@ static int launch_map(const char* what, const void* a, const void* b, void* out,
   const bool vec = aligned16(a) && aligned16(out) && (NIN < 2 || aligned16(b));
   long long nvec = vec ? n / N : 0;
   if (nvec > 0) {
-    map_vec_kernel<T, NIN, F><<<blocks_for(nvec, kThreads * kUnroll), kThreads, 0, stream>>>(
+    map_vec_kernel<T, NIN, F><<<persistent_blocks(nvec, kThreads * kUnroll), kThreads, 0, stream>>>(
         pa, pb, po, nvec, f);
     note_launch();
   }
@@ -181,26 +192,28 @@ __global__ void __launch_bounds__(kThreads)
 bias_add_vec_kernel(const T* in, const T* __restrict__ bias, T* out, long long nvec,
                     int cvec /* channels / N */) {
   constexpr int N = Lanes<T>::kN;
-  const long long base = ((long long)blockIdx.x * kThreads * kUnroll) + threadIdx.x;
-  uint4 vi[kUnroll], vb[kUnroll];
+  for (long long base = ((long long)blockIdx.x * kThreads * kUnroll) + threadIdx.x; base < nvec;
+       base += (long long)gridDim.x * kThreads * kUnroll) {
+    uint4 vi[kUnroll], vb[kUnroll];
 #pragma unroll
-  for (int u = 0; u < kUnroll; ++u) {
-    const long long i = base + (long long)u * kThreads;
-    if (i < nvec) {
-      vi[u] = ld16_rw(in + i * N);
-      vb[u] = ld16(bias + (i % cvec) * N);  // bias row stays in L1/L2
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = base + (long long)u * kThreads;
+      if (i < nvec) {
+        vi[u] = ld16_rw(in + i * N);
+        vb[u] = ld16(bias + (i % cvec) * N);  // bias row stays in L1/L2
+      }
     }
-  }
 #pragma unroll
-  for (int u = 0; u < kUnroll; ++u) {
-    const long long i = base + (long long)u * kThreads;
-    if (i < nvec) {
-      float x[N], b[N], r[N];
-      Lanes<T>::unpack(vi[u], x);
-      Lanes<T>::unpack(vb[u], b);
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = base + (long long)u * kThreads;
+      if (i < nvec) {
+        float x[N], b[N], r[N];
+        Lanes<T>::unpack(vi[u], x);
+        Lanes<T>::unpack(vb[u], b);
 #pragma unroll
-      for (int j = 0; j < N; ++j) r[j] = x[j] + b[j];
-      st16(out + i * N, Lanes<T>::pack(r));
+        for (int j = 0; j < N; ++j) r[j] = x[j] + b[j];
+        st16(out + i * N, Lanes<T>::pack(r));
+      }
     }
   }
 }
@@ -221,7 +234,7 @@ static int launch_bias_add(const void* in, const void* bias, void* out, long lon
   if (n == 0) return B200_OK;
   if (channels % N == 0 && aligned16(in) && aligned16(out) && aligned16(bias)) {
     const long long nvec = n / N;
-    bias_add_vec_kernel<T><<<blocks_for(nvec, kThreads * kUnroll), kThreads, 0, stream>>>(
+    bias_add_vec_kernel<T><<<persistent_blocks(nvec, kThreads * kUnroll), kThreads, 0, stream>>>(
         static_cast<const T*>(in), static_cast<const T*>(bias), static_cast<T*>(out), nvec,
         (int)(channels / N));
   } else {
@@ -268,23 +281,25 @@ cast_kernel(const S* __restrict__ in, D* __restrict__ out, long long n) {
 // float -> bfloat16, 8 elements per thread: 2 x 16-byte loads, 1 x 16-byte store.
 __global__ void __launch_bounds__(kThreads)
 cast_f32_bf16_vec_kernel(const float* __restrict__ in, uint16_t* __restrict__ out, long long nvec) {
-  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= nvec) return;
-  const uint4 a = ld16(in + i * 8), b = ld16(in + i * 8 + 4);
-  uint4 r;
-  r.x = (a.x >> 16) | (a.y & 0xFFFF0000u);
-  r.y = (a.z >> 16) | (a.w & 0xFFFF0000u);
-  r.z = (b.x >> 16) | (b.y & 0xFFFF0000u);
-  r.w = (b.z >> 16) | (b.w & 0xFFFF0000u);
-  st16(out + i * 8, r);
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * kThreads) {
+    const uint4 a = ld16(in + i * 8), b = ld16(in + i * 8 + 4);
+    uint4 r;
+    r.x = (a.x >> 16) | (a.y & 0xFFFF0000u);
+    r.y = (a.z >> 16) | (a.w & 0xFFFF0000u);
+    r.z = (b.x >> 16) | (b.y & 0xFFFF0000u);
+    r.w = (b.z >> 16) | (b.w & 0xFFFF0000u);
+    st16(out + i * 8, r);
+  }
 }
 __global__ void __launch_bounds__(kThreads)
 cast_bf16_f32_vec_kernel(const uint16_t* __restrict__ in, float* __restrict__ out, long long nvec) {
-  const long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
-  if (i >= nvec) return;
-  const uint4 a = ld16(in + i * 8);
-  st16(out + i * 8, make_uint4(a.x << 16, a.x & 0xFFFF0000u, a.y << 16, a.y & 0xFFFF0000u));
-  st16(out + i * 8 + 4, make_uint4(a.z << 16, a.z & 0xFFFF0000u, a.w << 16, a.w & 0xFFFF0000u));
+  for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * kThreads) {
+    const uint4 a = ld16(in + i * 8);
+    st16(out + i * 8, make_uint4(a.x << 16, a.x & 0xFFFF0000u, a.y << 16, a.y & 0xFFFF0000u));
+    st16(out + i * 8 + 4, make_uint4(a.z << 16, a.z & 0xFFFF0000u, a.w << 16, a.w & 0xFFFF0000u));
+  }
 }
 
 template <typename S, typename D>
@@ -462,7 +477,7 @@ int b200_cast(int src_dtype, int dst_dtype, const void* in, void* out, int64_t n
 #define PAIR(a, b) (src_dtype == (a) && dst_dtype == (b))
   if (PAIR(B200_DT_FLOAT, B200_DT_BFLOAT16)) {
     if (n % 8 == 0 && aligned16(in) && aligned16(out)) {
-      cast_f32_bf16_vec_kernel<<<blocks_for(n / 8, kThreads), kThreads, 0, s>>>(
+      cast_f32_bf16_vec_kernel<<<persistent_blocks(n / 8, kThreads), kThreads, 0, s>>>(
           static_cast<const float*>(in), static_cast<uint16_t*>(out), n / 8);
       note_launch();
       return check_launch("b200_cast");
@@ -471,7 +486,7 @@ int b200_cast(int src_dtype, int dst_dtype, const void* in, void* out, int64_t n
   }
   if (PAIR(B200_DT_BFLOAT16, B200_DT_FLOAT)) {
     if (n % 8 == 0 && aligned16(in) && aligned16(out)) {
-      cast_bf16_f32_vec_kernel<<<blocks_for(n / 8, kThreads), kThreads, 0, s>>>(
+      cast_bf16_f32_vec_kernel<<<persistent_blocks(n / 8, kThreads), kThreads, 0, s>>>(
           static_cast<const uint16_t*>(in), static_cast<float*>(out), n / 8);
       note_launch();
       return check_launch("b200_cast");

@@ -20,6 +20,7 @@
 #include "b200_internal.h"
 
 #include <cuda_bf16.h>
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 
@@ -80,6 +81,8 @@ struct GemmShape {
   int kb_per_split;   // K blocks per split
   float* partial;     // [splits][batch][M][N] fp32 partial sums when splits > 1
   int a_map4d, b_map4d;  // MN-major operand described by a 4-D map: one TMA per stage
+  // implicit-GEMM convolution A operand (conv_a != 0): K blocks enumerate (filter tap, channel block)
+  int conv_a, cv_OW, cv_OH, cv_sh, cv_sw, cv_pt, cv_pl, cv_S, cv_C, cv_cblocks, cv_taps;
   // epilogue
   int tma_store;         // 1: stage through smem and TMA-store via tmapC (C or the partial buffer)
   const void* bias;      // optional fused BiasAdd: + bias[col]      (element type TOut)
@@ -252,7 +255,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
           } else {
             mbar_arrive_remote(&full_bar[stage], 0);
           }
-          const int k0 = kb * BK;
+          int k0 = kb * BK;
+          int cv_c0 = 0, cv_r = 0, cv_s = 0;
+          if (s.conv_a && !kAMN) {  // kb -> (tap, channel block); B rows follow HWIO: (tap * C + c0)
+            const int tap = kb / s.cv_cblocks;
+            cv_c0 = (kb - tap * s.cv_cblocks) * BK;
+            cv_r = tap / s.cv_S;
+            cv_s = tap - cv_r * s.cv_S;
+            k0 = tap * s.cv_C + cv_c0;
+          }
           uint8_t* a_dst = smA + stage * kABytes;
           uint8_t* b_dst = smB + stage * kBBytes;
           auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
@@ -269,8 +280,45 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
             else
               tma_load_4d(dst, map, &full_bar[stage], 0, k0, mn0 / kChunk, b);
           };
-          if (!kAMN) {
+          if (!kAMN && s.conv_a) {
+            // first output pixel of this CTA's 128-row slab -> input-space base coordinates
+            const int ow = m0 % s.cv_OW;
+            const int t2 = m0 / s.cv_OW;
+            const int oh = t2 % s.cv_OH;
+            const int img = t2 / s.cv_OH;
+            const int bw = ow * s.cv_sw - s.cv_pl, bh = oh * s.cv_sh - s.cv_pt;
+            if (kCtas == 2)
+              tma_load_im2col_4d_2cta(a_dst, &tmapA, &full_bar[stage], cv_c0, bw, bh, img,
+                                      (uint16_t)cv_s, (uint16_t)cv_r);
+            else
+              tma_load_im2col_4d(a_dst, &tmapA, &full_bar[stage], cv_c0, bw, bh, img,
+                                 (uint16_t)cv_s, (uint16_t)cv_r);
+          } else if (!kAMN) {
             load(a_dst, &tmapA, k0, m0);
+          } else if (s.conv_a) {
+            // Filter gradient: GEMM-K runs over output pixels, GEMM-M over (tap, channel).  Each
+            // 128-byte chunk of M is one (tap, channel block): an im2col box of BK pixels x chunk
+            // channels lands in smem as [BK rows][128 B] -- the MN-major chunk layout.
+            const int p0 = kb * BK;
+            const int ow = p0 % s.cv_OW;
+            const int t2 = p0 / s.cv_OW;
+            const int oh = t2 % s.cv_OH;
+            const int img = t2 / s.cv_OH;
+            const int bw = ow * s.cv_sw - s.cv_pl, bh = oh * s.cv_sh - s.cv_pt;
+#pragma unroll
+            for (int c = 0; c < kBM / kChunk; ++c) {
+              const int mi = m0 + c * kChunk;
+              int tap = mi / s.cv_C;
+              const int c0 = mi - tap * s.cv_C;
+              if (tap >= s.cv_taps) tap = s.cv_taps - 1;  // rows beyond R*S*C are never stored
+              const int fr = tap / s.cv_S, fs = tap - fr * s.cv_S;
+              if (kCtas == 2)
+                tma_load_im2col_4d_2cta(a_dst + c * (BK * kSwizzleBytes), &tmapA, &full_bar[stage],
+                                        c0, bw, bh, img, (uint16_t)fs, (uint16_t)fr);
+              else
+                tma_load_im2col_4d(a_dst + c * (BK * kSwizzleBytes), &tmapA, &full_bar[stage], c0,
+                                   bw, bh, img, (uint16_t)fs, (uint16_t)fr);
+            }
           } else if (s.a_map4d) {
             load4(a_dst, &tmapA, m0);
           } else {
@@ -615,9 +663,11 @@ __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, TOut* __restrict__ C, int splits,
                      long long batch, int M, int N, int ldc, long long strideC) {
   const long long per_split = batch * (long long)M * N;
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;  // index of a 4-column group
   const int n4 = (N + 3) / 4;
-  if (i >= batch * (long long)M * n4) return;
+  const long long total = batch * (long long)M * n4;
+  // persistent grid-stride over 4-column groups
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total;
+       i += (long long)gridDim.x * 256) {
   const int c4 = (int)(i % n4);
   const long long r = i / n4;  // b * M + row
   const long long b = r / M;
@@ -644,6 +694,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, TOut* __restrict__ C, in
     else
       reinterpret_cast<__nv_bfloat16*>(dst)[j] = __float2bfloat16_rn(acc[j]);
   }
+  }  // group loop
 }
 
 // ------------------------------------------------------------------ host side
@@ -695,6 +746,46 @@ static bool encode_mn_major_map4d(CUtensorMap* map, CUtensorMapDataType dt, size
              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+bool conv_a_supported(int dtype, const ConvAOperand& c) {
+  const int es = dtype == B200_DT_FLOAT ? 4 : 2;
+  const int bk = kSwizzleBytes / es;
+  if (!driver().cuTensorMapEncodeIm2col) return false;
+  if (c.C % bk != 0) return false;                      // whole 128-byte channel blocks per tap
+  if ((reinterpret_cast<uintptr_t>(c.input) & 15) != 0) return false;
+  const int pad_r = std::max(0, (c.OW - 1) * c.sw + c.S - c.W) - c.pl;
+  const int pad_b = std::max(0, (c.OH - 1) * c.sh + c.R - c.H) - c.pt;
+  const int lo_w = -c.pl, lo_h = -c.pt, up_w = pad_r - (c.S - 1), up_h = pad_b - (c.R - 1);
+  for (int v : {lo_w, lo_h, up_w, up_h})
+    if (v < -128 || v > 127) return false;              // rank-4 corner range
+  if (c.S > 256 || c.R > 256 || c.sw > 8 || c.sh > 8) return false;
+  if ((long long)c.N * c.OH * c.OW > 0x7fffffffLL) return false;
+  return true;
+}
+
+static int encode_im2col_map(CUtensorMap* map, CUtensorMapDataType dt, size_t esize,
+                             const ConvAOperand& c, int channels_per_pixel, int pixels,
+                             bool mn_major = false) {
+  cuuint64_t gdim[4] = {(cuuint64_t)c.C, (cuuint64_t)c.W, (cuuint64_t)c.H, (cuuint64_t)c.N};
+  cuuint64_t gstride[3] = {(cuuint64_t)c.C * esize, (cuuint64_t)c.W * c.C * esize,
+                           (cuuint64_t)c.H * c.W * c.C * esize};
+  const int pad_r = std::max(0, (c.OW - 1) * c.sw + c.S - c.W) - c.pl;
+  const int pad_b = std::max(0, (c.OH - 1) * c.sh + c.R - c.H) - c.pt;
+  int lower[2] = {-c.pl, -c.pt};                         // {W, H}
+  int upper[2] = {pad_r - (c.S - 1), pad_b - (c.R - 1)};
+  cuuint32_t estr[4] = {1, (cuuint32_t)c.sw, (cuuint32_t)c.sh, 1};
+  CUresult r = driver().cuTensorMapEncodeIm2col(
+      map, dt, 4, const_cast<void*>(c.input), gdim, gstride, lower, upper,
+      (cuuint32_t)channels_per_pixel, (cuuint32_t)pixels, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+      (mn_major && esize == 4) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+      CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeIm2col failed with CUresult %d", (int)r);
+    return B200_INTERNAL;
+  }
+  return B200_OK;
+}
+
 // Output (or split-K partial) tensor map for the epilogue's TMA stores: box = 128 B x 32 rows.
 static bool encode_store_map(CUtensorMap* map, CUtensorMapDataType dt, size_t esize, void* ptr,
                              long long rows, long long cols, long long ld, long long batches,
@@ -723,7 +814,12 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   // A: logical [M,K]; stored [M,K] (K-major) or [K,M] (MN-major).  Box = one CTA's 128 rows.
   static const bool no_map4d = getenv("B200TF_GEMM_NO_MAP4D") != nullptr;
   bool a4 = false, b4 = false;
-  if (!kAMN)
+  if (g.conv_a) {
+    if (kAMN)  // filter gradient: boxes of BK pixels x one 128-byte channel chunk
+      rc = encode_im2col_map(&ma, Tr::kTmaType, sizeof(TIn), *g.conv_a, kChunk, Tr::kBK, true);
+    else       // forward / input gradient: boxes of 128 pixels x BK channels
+      rc = encode_im2col_map(&ma, Tr::kTmaType, sizeof(TIn), *g.conv_a, Tr::kBK, kBM);
+  } else if (!kAMN)
     rc = encode_operand_map(&ma, Tr::kTmaType, sizeof(TIn), g.a, g.M, g.K, g.lda, g.batch,
                             g.strideA, Tr::kBK, kBM, false);
   else if (!no_map4d &&
@@ -784,6 +880,12 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   s.splits = splits;
   s.partial = static_cast<float*>(g.workspace);
   s.a_map4d = a4 ? 1 : 0;
+  s.conv_a = g.conv_a ? 1 : 0;
+  if (g.conv_a) {
+    const ConvAOperand& c = *g.conv_a;
+    s.cv_OW = c.OW; s.cv_OH = c.OH; s.cv_sh = c.sh; s.cv_sw = c.sw; s.cv_pt = c.pt; s.cv_pl = c.pl;
+    s.cv_S = c.S; s.cv_C = c.C; s.cv_cblocks = c.C / Tr::kBK; s.cv_taps = c.R * c.S;
+  }
   s.b_map4d = b4 ? 1 : 0;
   s.bias = g.bias;
   s.relu = g.relu ? 1 : 0;
@@ -840,7 +942,9 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   note_launch();
   if (splits > 1) {
     const long long groups = g.batch * g.M * ((g.N + 3) / 4);
-    splitk_reduce_kernel<TOut><<<(unsigned)((groups + 255) / 256), 256, 0, stream>>>(
+    long long rblocks = (groups + 255) / 256;
+    if (rblocks > 8LL * sm_count()) rblocks = 8LL * sm_count();
+    splitk_reduce_kernel<TOut><<<(unsigned)rblocks, 256, 0, stream>>>(
         s.partial, static_cast<TOut*>(g.c), splits, g.batch, s.M, s.N, s.ldc, s.strideC);
     note_launch();
   }
@@ -910,6 +1014,10 @@ bool gemm_tcgen05_supported(const GemmArgs& g) {
   const int e = g.dtype == B200_DT_FLOAT ? 4 : 2;
   const int align = 16 / e;
   if (g.M <= 0 || g.N <= 0 || g.K <= 0 || g.batch <= 0) return false;
+  if (g.conv_a) {
+    if (g.ldb % align || (reinterpret_cast<uintptr_t>(g.b) & 15)) return false;
+    return g.batch == 1 && conv_a_supported(g.dtype, *g.conv_a);
+  }
   if (g.lda % align || g.ldb % align) return false;
   if (g.batch > 1 && (g.strideA % align || g.strideB % align)) return false;
   if ((reinterpret_cast<uintptr_t>(g.a) & 15) || (reinterpret_cast<uintptr_t>(g.b) & 15))

@@ -178,8 +178,9 @@ __global__ void __launch_bounds__(256)
 softmax_warp_kernel(const T* __restrict__ logits, T* __restrict__ out, long long rows, int cols) {
   constexpr int E = 16 / sizeof(T);  // elements per 16-byte vector
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  // persistent: warps stride over rows (grid capped at ~8 CTAs/SM, no CTA wave transitions)
+  for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows;
+       row += (long long)gridDim.x * 8) {
   const T* x = logits + row * cols;
   float v[NV][E];
   float mx = -FLT_MAX;
@@ -246,6 +247,7 @@ softmax_warp_kernel(const T* __restrict__ logits, T* __restrict__ out, long long
       *reinterpret_cast<uint4*>(y + c0) = q;
     }
   }
+  }  // row loop
 }
 
 // Generic fallback: one CTA (256 threads) per row, three passes over the row (L1/L2 resident),
@@ -356,8 +358,8 @@ xent_warp_vec_kernel(const float* __restrict__ logits, const float* __restrict__
                      float* __restrict__ loss, float* __restrict__ backprop, long long rows,
                      int cols) {
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows;
+       row += (long long)gridDim.x * 8) {
   const float4* x = reinterpret_cast<const float4*>(logits + row * cols);
   const float4* l = reinterpret_cast<const float4*>(labels + row * cols);
   float4* bp = reinterpret_cast<float4*>(backprop + row * cols);
@@ -403,6 +405,7 @@ xent_warp_vec_kernel(const float* __restrict__ logits, const float* __restrict__
   }
   acc = warp_sum(acc);
   if (lane == 0) loss[row] = acc;
+  }  // row loop
 }
 
 // ================================================================== ArgMax
@@ -510,7 +513,8 @@ static int launch_softmax(const void* logits, void* out, long long rows, int col
   T* y = static_cast<T*>(out);
   const bool vec = cols % E == 0 && aligned16(logits) && aligned16(out);
   const int nv = (cols + 32 * E - 1) / (32 * E);  // 16-byte vectors per lane
-  const unsigned wgrid = (unsigned)((rows + 7) / 8);
+  unsigned wgrid = (unsigned)((rows + 7) / 8);
+  if (wgrid > 8u * (unsigned)sm_count()) wgrid = 8u * (unsigned)sm_count();
 #define SM_LAUNCH(NV)                                                                   \
   do {                                                                                  \
     if (log_sm)                                                                         \
@@ -645,7 +649,8 @@ int b200_softmax_xent(int dtype, const void* logits, const void* labels, void* l
     const float* ll = static_cast<const float*>(labels);
     float* lo = static_cast<float*>(loss);
     float* bo = static_cast<float*>(backprop);
-    const unsigned wg = (unsigned)((rows + 7) / 8);
+    unsigned wg = (unsigned)((rows + 7) / 8);
+    if (wg > 8u * (unsigned)sm_count()) wg = 8u * (unsigned)sm_count();
     if (vec && cols <= 128)
       xent_warp_vec_kernel<1><<<wg, 256, 0, s>>>(xl, ll, lo, bo, rows, (int)cols);
     else if (vec && cols <= 256)

@@ -82,6 +82,15 @@ const DriverApi& driver() {
       api.cuTensorMapEncodeTiled = nullptr;
       cudaGetLastError();
     }
+    fn = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess) {
+      api.cuTensorMapEncodeIm2col = reinterpret_cast<decltype(api.cuTensorMapEncodeIm2col)>(fn);
+    } else {
+      api.cuTensorMapEncodeIm2col = nullptr;
+      cudaGetLastError();
+    }
   });
   return api;
 }
