@@ -7,6 +7,7 @@ TF_SessionRun, tensorflow/c/c_api.h) the reference reaches through SWIG
 (python/client/tf_session_helper.cc:462,575).
 """
 import ctypes
+import weakref
 import os
 
 import numpy as np
@@ -79,6 +80,7 @@ _SIGS = {
                              c_void_p, c_void_p]),
     "B200TF_SessionLastRunStats": (None, [c_void_p, ctypes.POINTER(RunStats)]),
     "B200TF_SessionStream": (c_void_p, [c_void_p]),
+    "B200TF_SessionStageTensor": (c_void_p, [c_void_p, c_void_p, c_void_p]),
     "B200TF_ListRegisteredOps": (c_void_p, []),
     "B200TF_ListRegisteredKernels": (c_void_p, []),
     "TF_LoadLibrary": (c_void_p, [c_char_p, c_void_p]),
@@ -195,6 +197,30 @@ class HostTensor:
         try:
             if self.owned and self.ptr:
                 self.fw.TF_DeleteTensor(self.ptr)
+        except Exception:
+            pass
+
+
+class StagedTensor:
+    """A feed value already on its way to (or in) device memory: see Session.stage()."""
+
+    def __init__(self, ptr, dtype, shape, nbytes):
+        self.fw = framework()
+        self.ptr = ptr
+        self.dtype = dtype
+        self.shape = shape
+        self.nbytes = nbytes
+
+    def release(self):
+        """Give the device memory back (it belongs to the session's arena, so Session.close()
+        releases every staged tensor that is still alive before the device goes away)."""
+        if self.ptr:
+            self.fw.TF_DeleteTensor(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.release()
         except Exception:
             pass
 
@@ -334,6 +360,7 @@ class Session:
         self.fw.TF_DeleteSessionOptions(opts)
         status.check()
         self._status = _Status()
+        self._staged = weakref.WeakSet()
 
     def run(self, fetches, feed_dict=None, as_host_tensors=False):
         single = not isinstance(fetches, (list, tuple))
@@ -344,7 +371,9 @@ class Session:
         keep = []
         feed_outputs, feed_ptrs = [], []
         for k, v in feed_dict.items():
-            if not isinstance(v, HostTensor):
+            if isinstance(v, StagedTensor) and not v.ptr:
+                raise ValueError("staged tensor fed to %s was already released" % k.name)
+            if not isinstance(v, (HostTensor, StagedTensor)):
                 v = HostTensor.from_numpy(np.asarray(v), k.dtype)
             keep.append(v)
             feed_outputs.append(k._c())
@@ -368,6 +397,22 @@ class Session:
                 results.append(None)
         return results[0] if single else results
 
+    def stage(self, value, dtype=None):
+        """Start copying a feed value to the device and return at once (input prefetch).
+
+        `value` is a HostTensor (pinned; its buffer must not be rewritten until the run that
+        consumes the staged tensor has returned) or anything numpy can convert.  The returned
+        StagedTensor is accepted by run() as a feed value and is used without another copy, so
+        staging step i+1 before running step i hides the PCIe transfer behind the kernels.
+        """
+        if not isinstance(value, HostTensor):
+            value = HostTensor.from_numpy(np.asarray(value), dtype)
+        ptr = self.fw.B200TF_SessionStageTensor(self.ptr, value.ptr, self._status.ptr)
+        self._status.check()
+        st = StagedTensor(ptr, value.dtype, value.shape, self.fw.TF_TensorByteSize(value.ptr))
+        self._staged.add(st)
+        return st
+
     def stream(self):
         """The CUstream handle (int) all kernels of this session run on."""
         return self.fw.B200TF_SessionStream(self.ptr)
@@ -381,6 +426,8 @@ class Session:
 
     def close(self):
         if self.ptr:
+            for staged in list(self._staged):
+                staged.release()
             st = _Status()
             self.fw.TF_CloseSession(self.ptr, st.ptr)
             self.fw.TF_DeleteSession(self.ptr, st.ptr)

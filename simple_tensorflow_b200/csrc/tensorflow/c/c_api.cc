@@ -325,6 +325,13 @@ void B200TF_SessionLastRunStats(TF_Session* s, B200TF_RunStats* out) {
   out->host_total_us = r.host_total_us;
 }
 
+TF_Tensor* B200TF_SessionStageTensor(TF_Session* s, TF_Tensor* host, TF_Status* status) {
+  tensorflow::Tensor staged;
+  status->status = s->session->StageFeed(host->tensor, &staged);
+  if (!status->status.ok()) return nullptr;
+  return new TF_Tensor{staged};
+}
+
 void* B200TF_SessionStream(TF_Session* s) {
   auto* ds = dynamic_cast<tensorflow::DirectSession*>(s->session);
   return ds ? ds->device()->compute_stream()->cuda_stream() : nullptr;

@@ -132,6 +132,16 @@ typedef struct B200TF_RunStats {
 TF_CAPI_EXPORT extern void B200TF_SessionLastRunStats(TF_Session*, B200TF_RunStats* out);
 /* The CUstream every kernel of this session is enqueued on (for CUDA-event timing). */
 TF_CAPI_EXPORT extern void* B200TF_SessionStream(TF_Session*);
+/* Input staging (prefetch to device): starts the host->device copy of a pinned host tensor on
+ * the session's host_to_device stream and returns at once.  The returned TF_Tensor is
+ * DEVICE-RESIDENT (TF_TensorData is a device pointer: do not dereference it on the host); pass it
+ * as an input value of TF_SessionRun, which then uses it without another copy, ordered behind the
+ * staging copy.  Staging step i+1 before running step i overlaps the copy with the kernels.
+ * The host tensor may be deleted right away (the session keeps its buffer until the copy has
+ * been consumed).  Delete the staged tensor with TF_DeleteTensor after the Run that used it,
+ * and in any case BEFORE TF_DeleteSession: its memory belongs to the session's device arena. */
+TF_CAPI_EXPORT extern TF_Tensor* B200TF_SessionStageTensor(TF_Session*, TF_Tensor* host,
+                                                           TF_Status* status);
 /* Registered ops / kernels ("Op:DEVICE:label"), newline-separated; caller frees with free(). */
 TF_CAPI_EXPORT extern char* B200TF_ListRegisteredOps(void);
 TF_CAPI_EXPORT extern char* B200TF_ListRegisteredKernels(void);

@@ -2,10 +2,19 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
+#include <cstring>
 #include <functional>
+#include <queue>
 #include <set>
 
 namespace tensorflow {
+
+// Environment switch that defaults to ON: only an explicit "0" turns it off.
+static bool EnvFlagOff(const char* name) {
+  const char* v = getenv(name);
+  return v != nullptr && std::strcmp(v, "0") == 0;
+}
 
 Status NewSession(const SessionOptions& options, Session** out_session) {
   if (!options.target.empty())
@@ -184,6 +193,48 @@ Status DirectSession::GetOrCreateExecutors(const std::vector<std::string>& feeds
     if (n == node_index_.end()) return errors::NotFound("Target node ", t, ": not found");
     TF_RETURN_IF_ERROR(visit(n->second));
   }
+  // Schedule.  The DFS above pruned and checked for cycles; the execution order is a list
+  // schedule of the pruned set: collectives (own stream) as soon as their inputs exist, every
+  // other node in graph-construction order (the order a front-end emits backprop in: last layer
+  // first), so a layer's gradient exchange runs under the remaining backward kernels.
+  const bool overlap_collectives = device_->num_replicas() > 1 &&
+                                   device_->collective_comm() != nullptr &&
+                                   !EnvFlagOff("B200TF_COLLECTIVE_OVERLAP");
+  auto is_collective = [&](int n) {
+    return overlap_collectives && nodes_[n]->def.op.rfind("B200AllReduce", 0) == 0 &&
+           nodes_[n]->def.op != "B200AllReduce";  // the ref-variable form stays on compute
+  };
+  {
+    std::vector<int> indeg(nodes_.size(), 0);
+    std::vector<std::vector<int>> consumers(nodes_.size());
+    for (int n : order) {
+      for (const TensorId& in : nodes_[n]->inputs)
+        if (!feed_of.count({in.node, in.slot})) {
+          consumers[in.node].push_back(n);
+          ++indeg[n];
+        }
+      for (int c : nodes_[n]->control_inputs) {
+        consumers[c].push_back(n);
+        ++indeg[n];
+      }
+    }
+    typedef std::pair<int, int> Key;  // (class, node id)
+    std::priority_queue<Key, std::vector<Key>, std::greater<Key>> ready;
+    for (int n : order)
+      if (indeg[n] == 0) ready.push(Key(is_collective(n) ? 0 : 1, n));
+    std::vector<int> scheduled;
+    scheduled.reserve(order.size());
+    while (!ready.empty()) {
+      const int n = ready.top().second;
+      ready.pop();
+      scheduled.push_back(n);
+      for (int c : consumers[n])
+        if (--indeg[c] == 0) ready.push(Key(is_collective(c) ? 0 : 1, c));
+    }
+    if (scheduled.size() != order.size())
+      return errors::Internal("scheduler dropped nodes (", scheduled.size(), " of ", order.size(), ")");
+    order.swap(scheduled);
+  }
   // entry table + plan
   std::vector<int> first_entry(nodes_.size(), -1);
   for (int n : order) {
@@ -200,6 +251,14 @@ Status DirectSession::GetOrCreateExecutors(const std::vector<std::string>& feeds
     pn.node = n;
     pn.item = nodes_[n].get();
     pn.first_entry = first_entry[n];
+    if (is_collective(n)) {
+      pn.collective = static_cast<int>(ek->collective_events.size() / 2);
+      for (int e = 0; e < 2; ++e) {
+        ek->collective_events.emplace_back(new gpu::Event());
+        if (!ek->collective_events.back()->Init())
+          return errors::Internal("could not create an event for ", nodes_[n]->def.name);
+      }
+    }
     const OpKernel* k = nodes_[n]->kernel.get();
     for (size_t i = 0; i < nodes_[n]->inputs.size(); ++i) {
       const TensorId& in = nodes_[n]->inputs[i];
@@ -249,9 +308,48 @@ Status DirectSession::GetOrCreateExecutors(const std::vector<std::string>& feeds
   }
   ek->node_first_entry = first_entry;
   if (getenv("B200TF_DISABLE_FUSION") == nullptr) TF_RETURN_IF_ERROR(FuseMatMulChains(ek.get()));
+  if (!EnvFlagOff("B200TF_GRADIENT_ARENA")) PlanGradientArenas(ek.get());
   *out = ek.get();
   executors_[key] = std::move(ek);
   return Status::OK();
+}
+
+void DirectSession::PlanGradientArenas(ExecutorsAndKeys* ek) {
+  std::vector<std::pair<int, int>> producer_of(ek->num_entries, {-1, -1});  // entry -> (plan idx, slot)
+  for (size_t p = 0; p < ek->order.size(); ++p) {
+    const PlanNode& pn = ek->order[p];
+    for (int o = 0; o < pn.item->kernel->num_outputs(); ++o)
+      producer_of[pn.first_entry + o] = {static_cast<int>(p), o};
+  }
+  for (PlanNode& pn : ek->order) {
+    if (pn.item->def.op != "B200AllReduceN" || pn.inputs.size() < 2) continue;
+    bool eligible = true;
+    for (const InputSource& src : pn.inputs) {
+      if (src.feed >= 0) {
+        eligible = false;
+        break;
+      }
+      const int e = entry_index_of(ek, src.id);
+      const std::pair<int, int> prod = producer_of[e];
+      // sole consumer, not fetched, and not already claimed by another arena
+      if (ek->entry_consumers[e] != 1 || ek->entry_is_fetch[e] || prod.first < 0 ||
+          (!ek->order[prod.first].arena_slots.empty() &&
+           ek->order[prod.first].arena_slots[prod.second].first >= 0))
+        eligible = false;
+    }
+    if (!eligible) continue;
+    const int a = static_cast<int>(ek->arenas.size());
+    ek->arenas.emplace_back();
+    ek->arenas.back().dtype = pn.item->kernel->input_type(0);
+    pn.arena = a;
+    for (size_t i = 0; i < pn.inputs.size(); ++i) {
+      const std::pair<int, int> prod = producer_of[entry_index_of(ek, pn.inputs[i].id)];
+      PlanNode& producer = ek->order[prod.first];
+      if (producer.arena_slots.empty())
+        producer.arena_slots.assign(producer.item->kernel->num_outputs(), {-1, -1});
+      producer.arena_slots[prod.second] = {a, static_cast<int>(i)};
+    }
+  }
 }
 
 Status DirectSession::FuseMatMulChains(ExecutorsAndKeys* ek) {
@@ -363,13 +461,35 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
                               std::vector<Tensor>* outputs) {
   // ---- SendInputs: stage feeds where their consumers need them
   std::vector<Tensor> feed_dev(inputs.size()), feed_host(inputs.size());
+  std::vector<StagedFeed> consumed_stages;  // released after the step's sync
+  std::vector<Tensor> keepalive;            // tensors touched by collective-stream nodes
+  gpu::Stream* compute = device_->compute_stream();
+  gpu::Stream* collective = device_->collective_stream();
+  Allocator* device_allocator = device_->GetAllocator(AllocatorAttributes());
   for (size_t i = 0; i < inputs.size(); ++i) {
+    const Tensor& fed = inputs[i].second;
+    if (fed.buffer() != nullptr && fed.buffer()->allocator() == device_allocator) {
+      // a staged (device-resident) feed: no copy, only the ordering edge
+      if (ek->feed_needs_host[i])
+        return errors::InvalidArgument("Feed '", inputs[i].first, "' is device-resident but a ",
+                                       "consumer needs it in host memory");
+      auto st = staged_.find(fed.buffer());
+      if (st != staged_.end()) {
+        compute->ThenWaitFor(st->second.ready.get());
+        consumed_stages.push_back(std::move(st->second));
+        staged_.erase(st);
+      }
+      feed_dev[i] = fed;
+      continue;
+    }
     if (ek->feed_needs_host[i]) feed_host[i] = inputs[i].second;
     if (ek->feed_needs_device[i]) {
       TF_RETURN_IF_ERROR(device_->MakeTensorFromHost(inputs[i].second, &feed_dev[i]));
       stats_.h2d_bytes += static_cast<long long>(inputs[i].second.TotalBytes());
     }
   }
+  std::vector<Tensor> arena_root(ek->arenas.size());  // this step's gradient arenas
+  std::vector<Tensor> preallocated;
   std::vector<Entry> entries(ek->num_entries);
   std::vector<int> pending(ek->entry_consumers);
   std::vector<Tensor> deref_storage;     // Tensor handles for ref->value conversions
@@ -407,6 +527,10 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
         input_values.push_back(TensorValue(en.ref_mu, en.ref));
         continue;
       }
+      if (en.pending != nullptr && pn.collective < 0) {
+        compute->ThenWaitFor(en.pending);  // produced on the collective stream
+        en.pending = nullptr;
+      }
       Tensor* t = &en.val;
       if (en.ref != nullptr) {  // dereference a variable for a by-value consumer
         std::lock_guard<std::mutex> rl(*en.ref_mu);
@@ -438,6 +562,56 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
     params.device = device_.get();
     params.inputs = &input_values;
     params.op_device_context = dc;
+    preallocated.clear();
+    if (!pn.arena_slots.empty()) {  // hand the kernel its windows of the gradient arenas
+      preallocated.resize(kernel->num_outputs());
+      for (int o = 0; o < kernel->num_outputs(); ++o) {
+        const int a = pn.arena_slots[o].first, pos = pn.arena_slots[o].second;
+        if (a < 0 || !ek->arenas[a].learned) continue;
+        const GradientArena& ga = ek->arenas[a];
+        const size_t esize = DataTypeSize(ga.dtype);
+        if (arena_root[a].buffer() == nullptr)
+          arena_root[a] = Tensor(device_allocator, ga.dtype,
+                                 TensorShape({static_cast<int64>(ga.total / esize)}));
+        if (arena_root[a].buffer() == nullptr || ga.bytes[pos] == 0) continue;
+        TensorBuffer* window = new TensorBuffer(arena_root[a].buffer(), ga.offsets[pos], ga.bytes[pos]);
+        preallocated[o] = Tensor(ga.dtype, TensorShape({static_cast<int64>(ga.bytes[pos] / esize)}),
+                                 window);
+        window->Unref();
+      }
+      params.preallocated_outputs = &preallocated;
+    }
+    if (pn.arena >= 0) {  // (re)learn the layout from what the producers actually delivered
+      GradientArena& ga = ek->arenas[pn.arena];
+      bool same = ga.learned && ga.bytes.size() == input_values.size();
+      for (size_t i = 0; same && i < input_values.size(); ++i)
+        same = ga.bytes[i] == input_values[i].tensor->TotalBytes();
+      if (!same) {
+        ga.bytes.resize(input_values.size());
+        ga.offsets.resize(input_values.size());
+        size_t at = 0;
+        for (size_t i = 0; i < input_values.size(); ++i) {
+          ga.bytes[i] = input_values[i].tensor->TotalBytes();
+          ga.offsets[i] = at;
+          at += (ga.bytes[i] + 255) / 256 * 256;
+        }
+        ga.total = at;
+        ga.learned = at > 0;
+      }
+    }
+    gpu::Event* done = nullptr;
+    if (pn.collective >= 0) {
+      // everything enqueued so far (the producers of the inputs, the last users of any chunk
+      // the arena hands this node) precedes the node on its own stream
+      gpu::Event* inputs_ready = ek->collective_events[2 * pn.collective].get();
+      done = ek->collective_events[2 * pn.collective + 1].get();
+      compute->ThenRecordEvent(inputs_ready);
+      collective->ThenWaitFor(inputs_ready);
+      params.op_device_context = device_->collective_context();
+      params.record_tensor_accesses = true;
+      for (const TensorValue& v : input_values)
+        if (!v.is_ref() && v.tensor != nullptr) keepalive.push_back(*v.tensor);
+    }
     std::vector<AllocatorAttributes> out_attrs(kernel->num_outputs());
     for (int o = 0; o < kernel->num_outputs(); ++o)
       out_attrs[o].set_on_host(kernel->output_memory_types()[o] == HOST_MEMORY);
@@ -451,6 +625,14 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
         return Status(s.code(), strings::StrCat(s.error_message(), "\n\t [[Node: ",
                                                 SummarizeNodeDef(item->def), "]]"));
       }
+      if (done != nullptr) {
+        collective->ThenRecordEvent(done);
+        std::vector<Tensor> temps;
+        ctx.retrieve_accessed_tensors(&temps);
+        for (Tensor& t : temps) keepalive.push_back(std::move(t));
+        if (!collective->ok())
+          return errors::Internal("collective stream failed at node ", item->def.name);
+      }
       for (int o = 0; o < kernel->num_outputs(); ++o) {
         TensorValue v = ctx.release_output(o);
         Entry& out = entries[pn.first_entry + o];
@@ -461,6 +643,8 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
         }
         out.has_value = true;
         out.on_host = kernel->output_memory_types()[o] == HOST_MEMORY;
+        out.pending = done;
+        if (done != nullptr && !v.is_ref()) keepalive.push_back(*v.tensor);
         if (v.is_ref()) {
           out.ref = v.tensor;
           out.ref_mu = v.mutex_if_ref;
@@ -478,6 +662,13 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
       if (--pending[eidx] == 0 && !ek->entry_is_fetch[eidx]) entries[eidx].val = Tensor();
     }
   }
+
+  // the compute stream joins every collective nobody waited for, so one sync covers the step
+  for (Entry& en : entries)
+    if (en.pending != nullptr) {
+      compute->ThenWaitFor(en.pending);
+      en.pending = nullptr;
+    }
 
   // ---- RecvOutputs: device -> pinned host, then the single sync of the step
   outputs->clear();
@@ -509,7 +700,22 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
   }
   stats_.host_enqueue_us = std::chrono::duration_cast<std::chrono::microseconds>(
                                std::chrono::steady_clock::now() - run_start_).count();
-  return device_->Sync();  // sync_on_finish
+  return device_->Sync();  // sync_on_finish (keepalive / consumed_stages die after it)
+}
+
+Status DirectSession::StageFeed(const Tensor& host, Tensor* staged) {
+  std::lock_guard<std::mutex> l(mu_);
+  if (closed_) return errors::Cancelled("Session has been closed.");
+  if (host.NumElements() == 0) return errors::InvalidArgument("cannot stage an empty tensor");
+  StagedFeed st;
+  st.ready.reset(new gpu::Event());
+  if (!st.ready->Init()) return errors::Internal("could not create the staging event");
+  st.host = host;
+  Tensor dev;
+  TF_RETURN_IF_ERROR(device_->StageTensorFromHost(host, &dev, st.ready.get()));
+  staged_[dev.buffer()] = std::move(st);  // a stale entry for a recycled buffer is replaced
+  *staged = std::move(dev);
+  return Status::OK();
 }
 
 }  // namespace tensorflow

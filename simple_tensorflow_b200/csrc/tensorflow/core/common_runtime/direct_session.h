@@ -11,6 +11,11 @@
 //     ExecutorState::Process does for a GPU partition, whose kernels are all "inexpensive"
 //     (executor.cc:1487-1691, op_kernel.cc:97-99) -- filling OpKernelContext::Params
 //     (:1575-1649), calling Device::Compute (:1651) and propagating outputs (:1654-1673);
+//   * kernels whose op is a collective (B200AllReduce*) are placed on the device's collective
+//     stream when replicas > 1 (the reference's per-node DeviceContext / stream assignment,
+//     gpu_device.cc:337-399, executor.cc:1575-1649): the executor orders the two streams with
+//     events, keeps every tensor such a node touched alive until the step's sync, and schedules
+//     collectives as soon as their inputs exist so they overlap the rest of the backward pass;
 //   * feeds are copied host->device and fetches device->host through the device context
 //     (the job of _Send/_Recv + GPUUtil), and the device is synced exactly once per step
 //     (sync_on_finish, direct_session.cc:451, executor.cc:2211-2217).
@@ -45,6 +50,7 @@ class DirectSession : public Session {
              std::vector<Tensor>* outputs) override;
   Status Close() override;
   const RunStats& last_run_stats() const override { return stats_; }
+  Status StageFeed(const Tensor& host, Tensor* staged) override;
   BaseGPUDevice* device() const { return device_.get(); }
 
  private:
@@ -66,11 +72,27 @@ class DirectSession : public Session {
     int node;            // index into nodes_ (-1 for a node synthesised by a rewrite)
     NodeItem* item;      // the node to execute (owned by nodes_ or by ExecutorsAndKeys::rewritten)
     bool dead = false;   // folded into a fused node by a rewrite
+    int collective = -1; // >= 0: runs on the collective stream; index of its event pair
+    int arena = -1;      // >= 0: a B200AllReduceN whose inputs are laid out in this gradient arena
+    // per output: (arena, position) when the output is one of an arena's gradients, else (-1, -1)
+    std::vector<std::pair<int, int>> arena_slots;
     std::vector<InputSource> inputs;
     int first_entry;  // index of output slot 0 in the entry table
   };
+  // Gradient arena (the job of later TensorFlow's ScopedAllocator): the tensors one
+  // B200AllReduceN reduces are produced directly into consecutive 256-byte-aligned windows of
+  // one buffer, so the bucket is ONE in-place ncclAllReduce with no gather/scatter copies.
+  // Sizes are learned from the first step that runs the plan; a producer whose request does not
+  // match its window simply allocates normally and the collective falls back to its copying path.
+  struct GradientArena {
+    std::vector<size_t> bytes, offsets;
+    size_t total = 0;
+    DataType dtype = DT_FLOAT;
+    bool learned = false;
+  };
   struct ExecutorsAndKeys {
     std::vector<PlanNode> order;
+    std::vector<GradientArena> arenas;
     std::vector<std::unique_ptr<NodeItem>> rewritten;  // fused nodes created for this plan
     std::vector<InputSource> fetches;
     std::vector<int> node_first_entry;  // per graph node: entry index of its output 0 (-1: pruned)
@@ -78,6 +100,8 @@ class DirectSession : public Session {
     std::vector<bool> entry_is_fetch;
     std::vector<bool> feed_needs_device, feed_needs_host;
     int num_entries = 0;
+    // per collective-stream node: [2k] inputs-ready (recorded on compute), [2k+1] done
+    std::vector<std::unique_ptr<gpu::Event>> collective_events;
   };
   struct Entry {
     Tensor val;
@@ -85,6 +109,11 @@ class DirectSession : public Session {
     std::mutex* ref_mu = nullptr;
     bool has_value = false;
     bool on_host = false;
+    gpu::Event* pending = nullptr;  // produced on another stream: wait for this before reading
+  };
+  struct StagedFeed {
+    std::unique_ptr<gpu::Event> ready;
+    Tensor host;  // keeps the pinned source alive until the copy has been consumed
   };
 
   static int entry_index_of(const ExecutorsAndKeys* ek, const TensorId& id) {
@@ -99,6 +128,7 @@ class DirectSession : public Session {
   // GraphOptimizer-stage rewrite (direct_session.cc:1051 role): MatMul+BiasAdd(+Relu) and
   // MatMul+ReluGrad chains whose intermediates have a single consumer run as one _FusedMatMul.
   Status FuseMatMulChains(ExecutorsAndKeys* ek);
+  void PlanGradientArenas(ExecutorsAndKeys* ek);
   Status RunPlan(ExecutorsAndKeys* ek, const std::vector<std::pair<std::string, Tensor>>& inputs,
                  std::vector<Tensor>* outputs);
 
@@ -109,6 +139,7 @@ class DirectSession : public Session {
   std::unordered_map<std::string, int> node_index_;
   std::map<std::string, std::unique_ptr<ExecutorsAndKeys>> executors_;
   RunStats stats_;
+  std::unordered_map<const TensorBuffer*, StagedFeed> staged_;  // copies still in flight
   std::chrono::steady_clock::time_point run_start_;
   long long step_id_ = 0;
   bool closed_ = false;

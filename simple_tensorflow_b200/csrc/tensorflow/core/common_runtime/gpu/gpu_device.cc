@@ -43,6 +43,8 @@ BaseGPUDevice::BaseGPUDevice(int gpu_id, const std::string& name)
     : Device(name, DEVICE_GPU), gpu_id_(gpu_id) {}
 
 BaseGPUDevice::~BaseGPUDevice() {
+  if (h2d_stream_) h2d_stream_->BlockHostUntilDone();
+  if (collective_stream_) collective_stream_->BlockHostUntilDone();
   if (stream_) stream_->BlockHostUntilDone();
 }
 
@@ -57,7 +59,14 @@ Status BaseGPUDevice::Create(int gpu_id, size_t memory_limit_bytes,
       new BaseGPUDevice(gpu_id, strings::StrCat("/job:localhost/replica:0/task:0/gpu:", gpu_id)));
   d->stream_.reset(new gpu::Stream());
   d->stream_->Init();
-  if (!d->stream_->ok()) return errors::Internal("Failed to create the compute stream");
+  d->h2d_stream_.reset(new gpu::Stream());
+  d->h2d_stream_->Init();
+  d->collective_stream_.reset(new gpu::Stream());
+  d->collective_stream_->Init();
+  d->h2d_fence_.reset(new gpu::Event());
+  if (!d->stream_->ok() || !d->h2d_stream_->ok() || !d->collective_stream_->ok() ||
+      !d->h2d_fence_->Init())
+    return errors::Internal("Failed to create the device's stream group");
   if (memory_limit_bytes == 0) {
     size_t free_b = 0, total_b = 0;
     TF_RETURN_IF_ERROR(AbiStatus(b200_mem_info(&free_b, &total_b), "b200_mem_info"));
@@ -68,6 +77,8 @@ Status BaseGPUDevice::Create(int gpu_id, size_t memory_limit_bytes,
                                               strings::StrCat("GPU_", gpu_id, "_bfc")));
   d->host_allocator_.reset(new GPUHostAllocator());
   d->context_.reset(new GPUDeviceContext(d->stream_.get(), d->host_allocator_.get()));
+  d->collective_context_.reset(
+      new GPUDeviceContext(d->collective_stream_.get(), d->host_allocator_.get()));
   d->gpu_device_info_.stream = d->stream_.get();
   d->gpu_device_info_.default_context = d->context_.get();
   d->gpu_device_info_.gpu_id = gpu_id;
@@ -99,6 +110,27 @@ Status BaseGPUDevice::MakeTensorFromHost(const Tensor& host, Tensor* device_tens
   Status s;
   context_->CopyCPUTensorToDevice(&host, this, &t, [&s](const Status& r) { s = r; });
   TF_RETURN_IF_ERROR(s);
+  *device_tensor = std::move(t);
+  return Status::OK();
+}
+
+Status BaseGPUDevice::StageTensorFromHost(const Tensor& host, Tensor* device_tensor,
+                                          gpu::Event* ready) {
+  b200_set_device(gpu_id_);
+  Tensor t(gpu_allocator_.get(), host.dtype(), host.shape());
+  if (!t.IsInitialized())
+    return errors::ResourceExhausted("OOM when allocating staged feed ", host.shape().DebugString());
+  // The arena hands out chunks whose last use may still be queued on the compute stream.
+  stream_->ThenRecordEvent(h2d_fence_.get());
+  h2d_stream_->ThenWaitFor(h2d_fence_.get());
+  const size_t bytes = host.TotalBytes();
+  if (bytes > 0) {
+    gpu::DeviceMemoryBase dst(t.raw_data(), bytes);
+    h2d_stream_->ThenMemcpyH2D(&dst, host.raw_data(), bytes);
+  }
+  h2d_stream_->ThenRecordEvent(ready);
+  if (!h2d_stream_->ok() || !stream_->ok())
+    return errors::Internal("CPU->GPU staged Memcpy failed: ", b200_last_error());
   *device_tensor = std::move(t);
   return Status::OK();
 }

@@ -1,6 +1,8 @@
 // BaseGPUDevice for B200 -- the "new tensorflow/core/common_runtime/gpu device" of the
 // north star.  Same roles as the reference's core/common_runtime/gpu/gpu_device.{h,cc}:
-//   * one compute stream per device (BaseGPUDevice::Init, gpu_device.cc:194-264)
+//   * a stream group per device (BaseGPUDevice::Init, gpu_device.cc:194-264): ONE compute stream
+//     that every kernel runs on, a host_to_device stream for staged feeds, and (additive) a
+//     collective stream so gradient all-reduces overlap the rest of the backward pass
 //   * BFC arena for device memory, pinned-host allocator for feeds/fetches
 //   * GPUDeviceContext carrying the stream to kernels (gpu_device_context.h) and doing the
 //     H2D / D2H tensor copies of GPUUtil (gpu_util.cc)
@@ -59,16 +61,27 @@ class BaseGPUDevice : public Device {
 
   int gpu_id() const { return gpu_id_; }
   gpu::Stream* compute_stream() const { return stream_.get(); }
+  gpu::Stream* host_to_device_stream() const { return h2d_stream_.get(); }
+  gpu::Stream* collective_stream() const { return collective_stream_.get(); }
   GPUDeviceContext* device_context() const { return context_.get(); }
+  // The DeviceContext handed to kernels the executor places on the collective stream.
+  GPUDeviceContext* collective_context() const { return collective_context_.get(); }
+
+  // Starts the host->device copy of `host` on the host_to_device stream (after everything the
+  // compute stream has been given so far, like GPUUtil::CopyCPUTensorToGPU's
+  // ThenWaitFor(compute), gpu_util.cc:300-306) and returns at once; `ready` is recorded behind
+  // the copy.  The caller makes the consuming stream wait for `ready`.
+  Status StageTensorFromHost(const Tensor& host, Tensor* device_tensor, gpu::Event* ready);
   Allocator* host_allocator() const { return host_allocator_.get(); }
 
  private:
   BaseGPUDevice(int gpu_id, const std::string& name);
   const int gpu_id_;
-  std::unique_ptr<gpu::Stream> stream_;
+  std::unique_ptr<gpu::Stream> stream_, h2d_stream_, collective_stream_;
+  std::unique_ptr<gpu::Event> h2d_fence_;
   std::unique_ptr<GPUBFCAllocator> gpu_allocator_;
   std::unique_ptr<GPUHostAllocator> host_allocator_;
-  std::unique_ptr<GPUDeviceContext> context_;
+  std::unique_ptr<GPUDeviceContext> context_, collective_context_;
   GpuDeviceInfo gpu_device_info_;
   void* collective_comm_ = nullptr;
   int num_replicas_ = 1;

@@ -87,10 +87,16 @@ Status OpKernelContext::allocate_output(int index, const TensorShape& shape, Ten
   if (index < 0 || index >= num_outputs())
     return errors::Internal("allocate_output: bad output index ", index);
   Tensor* t = new Tensor();
-  Status s = allocate_tensor(params_->op_kernel->output_type(index), shape, t, attr);
-  if (!s.ok()) {
-    delete t;
-    return s;
+  const Tensor* pre = preallocated_output(index);
+  if (pre != nullptr && pre->dtype() == params_->op_kernel->output_type(index) &&
+      pre->NumElements() == shape.num_elements() && shape.num_elements() > 0) {
+    t->CopyFrom(*pre, shape);
+  } else {
+    Status s = allocate_tensor(params_->op_kernel->output_type(index), shape, t, attr);
+    if (!s.ok()) {
+      delete t;
+      return s;
+    }
   }
   if (output_owned_[index] && outputs_[index].tensor) delete outputs_[index].tensor;
   outputs_[index] = TensorValue(t);
@@ -102,6 +108,8 @@ Status OpKernelContext::allocate_output(int index, const TensorShape& shape, Ten
 Status OpKernelContext::forward_input_or_allocate_output(
     const std::vector<int>& candidate_input_indices, int output_index,
     const TensorShape& output_shape, Tensor** output) {
+  if (preallocated_output(output_index) != nullptr)  // the executor chose this output's home
+    return allocate_output(output_index, output_shape, output);
   for (int input_index : candidate_input_indices) {
     const TensorValue& v = (*params_->inputs)[input_index];
     if (v.is_ref() || v.tensor == nullptr) continue;
@@ -126,9 +134,13 @@ Status OpKernelContext::forward_input_or_allocate_output(
 
 Status OpKernelContext::allocate_temp(DataType type, const TensorShape& shape, Tensor* out_temp,
                                       AllocatorAttributes attr) {
-  // With a single compute stream the arena's stream-ordered reuse keeps the scratch valid
-  // until the enqueued kernels have consumed it (gpu_device.cc:266-271).
-  return allocate_tensor(type, shape, out_temp, attr);
+  // On the compute stream the arena's stream-ordered reuse keeps the scratch valid until the
+  // enqueued kernels have consumed it (gpu_device.cc:266-271).  A kernel running on another
+  // stream has its scratch recorded so the executor can hold it until that stream has finished
+  // (the reference's record_tensor_accesses / EventMgr::ThenDeleteTensors, gpu_device.cc:372-385).
+  Status s = allocate_tensor(type, shape, out_temp, attr);
+  if (s.ok() && params_->record_tensor_accesses) referenced_tensors_.push_back(*out_temp);
+  return s;
 }
 
 void OpKernelContext::set_output(int index, const Tensor& tensor) {

@@ -174,6 +174,13 @@ class OpKernelContext {
     const std::vector<AllocatorAttributes>* input_alloc_attrs = nullptr;
     const AllocatorAttributes* output_attr_array = nullptr;
     DeviceContext* op_device_context = nullptr;
+    // op_kernel.h:508: a kernel that runs on a stream other than the compute stream has the
+    // tensors it touched recorded, so the executor can keep them alive until that stream is done.
+    bool record_tensor_accesses = false;
+    // Per output: a buffer the executor wants the kernel's allocate_output() to use (a slice of
+    // a gradient arena, the job of later TensorFlow's ScopedAllocator).  Used when dtype and
+    // element count match the request; otherwise allocation proceeds as usual.
+    const std::vector<Tensor>* preallocated_outputs = nullptr;
   };
   explicit OpKernelContext(Params* params);
   ~OpKernelContext();
@@ -209,6 +216,11 @@ class OpKernelContext {
   }
   Status allocate_temp(DataType type, const TensorShape& shape, Tensor* out_temp,
                        AllocatorAttributes allocator_attr);
+  // op_kernel.h:989: the tensors recorded under Params::record_tensor_accesses.
+  void retrieve_accessed_tensors(std::vector<Tensor>* out_vector) {
+    out_vector->swap(referenced_tensors_);
+    referenced_tensors_.clear();
+  }
   void set_output(int index, const Tensor& tensor);
   void set_output_ref(int index, std::mutex* mu, Tensor* tensor_for_ref);
   Tensor* mutable_output(int index) { return outputs_[index].tensor; }
@@ -235,10 +247,16 @@ class OpKernelContext {
  private:
   Status allocate_tensor(DataType type, const TensorShape& shape, Tensor* out_tensor,
                          AllocatorAttributes attr);
+  const Tensor* preallocated_output(int index) const {
+    const std::vector<Tensor>* p = params_->preallocated_outputs;
+    if (p == nullptr || index >= static_cast<int>(p->size())) return nullptr;
+    return (*p)[index].buffer() != nullptr ? &(*p)[index] : nullptr;
+  }
   Params* params_;
   Status status_;
   std::vector<TensorValue> outputs_;
   std::vector<bool> output_owned_;
+  std::vector<Tensor> referenced_tensors_;  // only filled under record_tensor_accesses
 };
 
 // ------------------------------------------------------------------ registration

@@ -21,9 +21,18 @@ class TensorBuffer {
       : alloc_(a), data_(a->AllocateRaw(Allocator::kAllocatorAlignment, bytes)), size_(bytes) {}
   // Wraps memory owned elsewhere (e.g. TF_NewTensor with a deallocator handled by the caller).
   TensorBuffer(void* data, size_t bytes) : alloc_(nullptr), data_(data), size_(bytes) {}
+  // A window [offset, offset + bytes) of `root` (tensor.cc SubBuffer): keeps the root alive and
+  // never frees memory itself.  Used for slices of a gradient arena (direct_session.cc).
+  TensorBuffer(TensorBuffer* root, size_t offset, size_t bytes)
+      : alloc_(nullptr), data_(static_cast<char*>(root->data()) + offset), size_(bytes),
+        root_(root->root_buffer()) {
+    root_->Ref();
+  }
   void* data() const { return data_; }
   size_t size() const { return size_; }
-  Allocator* allocator() const { return alloc_; }
+  // The allocator the memory came from (a window reports its root's).
+  Allocator* allocator() const { return root_ ? root_->alloc_ : alloc_; }
+  TensorBuffer* root_buffer() { return root_ ? root_ : this; }
   void Ref() { ref_.fetch_add(1, std::memory_order_relaxed); }
   bool Unref() {
     if (ref_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
@@ -36,11 +45,15 @@ class TensorBuffer {
 
  private:
   ~TensorBuffer() {
-    if (alloc_ && data_) alloc_->DeallocateRaw(data_);
+    if (root_)
+      root_->Unref();
+    else if (alloc_ && data_)
+      alloc_->DeallocateRaw(data_);
   }
   Allocator* alloc_;
   void* data_;
   size_t size_;
+  TensorBuffer* root_ = nullptr;
   std::atomic<int> ref_{1};
 };
 

@@ -5,6 +5,8 @@
 // aggregate_ops,cwise_op_mul_1,reduction_ops_mean,training_ops}.cc for the cases training
 // graphs of the hot path produce.
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 #include <memory>
 
 #include "tensorflow/core/common_runtime/device.h"
@@ -347,10 +349,14 @@ class B200AllReduceOp : public OpKernel {
   float scale_;
 };
 
-// N gradient tensors reduced across replicas by ONE NCCL launch: the per-tensor ncclAllReduce
-// calls sit inside ncclGroupStart/End, which NCCL aggregates into a single collective kernel on
-// the compute stream -- no packing copies, no host synchronisation.  scale == 1/replicas maps to
-// ncclAvg; any other scale runs as ncclSum followed by a scale kernel per tensor.
+// N gradient tensors (one bucket) reduced across replicas by ONE collective: the tensors are
+// gathered into a contiguous scratch arena, reduced by a single ncclAllReduce and scattered
+// back (4 MB + 4 KB buckets: the two extra copies cost ~3 us each at HBM speed, a second
+// collective costs its full NVLink latency).  B200TF_ALLREDUCE_PACK=0 keeps the tensors in place
+// and issues one ncclAllReduce per tensor inside ncclGroupStart/End instead.  scale == 1/replicas
+// maps to ncclAvg; any other scale runs as ncclSum followed by a scale kernel.  The kernel uses
+// whatever stream its DeviceContext carries: the executor places it on the device's collective
+// stream so the exchange overlaps the remaining backward kernels.  No host synchronisation.
 template <typename T>
 class B200AllReduceNOp : public OpKernel {
  public:
@@ -369,7 +375,61 @@ class B200AllReduceNOp : public OpKernel {
     for (int i = 0; i < n; ++i)  // reduce in place when this op is the buffer's only user
       OP_REQUIRES_OK(ctx, ctx->forward_input_or_allocate_output({i}, i, ctx->input(i).shape(),
                                                                 &outs[i]));
-    if (collective) {
+    // Inputs produced into one gradient arena (direct_session.cc PlanGradientArenas): consecutive
+    // 256-byte-aligned windows of one root buffer -> ONE in-place collective, no copies.
+    bool contiguous = collective && n > 1 && ctx->input(0).buffer() != nullptr;
+    size_t span = 0;
+    for (int i = 0; contiguous && i < n; ++i) {
+      const Tensor& t = ctx->input(i);
+      contiguous = t.buffer() != nullptr &&
+                   t.buffer()->root_buffer() == ctx->input(0).buffer()->root_buffer() &&
+                   static_cast<char*>(t.raw_data()) ==
+                       static_cast<char*>(ctx->input(0).raw_data()) + span;
+      span += (t.TotalBytes() + 255) / 256 * 256;
+    }
+    static const bool pack_enabled = [] {
+      const char* v = getenv("B200TF_ALLREDUCE_PACK");
+      return v == nullptr || std::strcmp(v, "0") != 0;
+    }();
+    if (contiguous) {
+      void* base = ctx->input(0).raw_data();
+      const int64 total = static_cast<int64>(span / sizeof(T));  // padding included: inside the arena
+      OP_REQUIRES_OK(ctx, FromAbi(b200_nccl_all_reduce(AbiType<T>::v, base, base, total, average,
+                                                       dev->collective_comm(), stream),
+                                  "ncclAllReduce"));
+      for (int i = 0; i < n; ++i)  // an input that could not be forwarded gets its copy
+        if (outs[i]->raw_data() != ctx->input(i).raw_data())
+          OP_REQUIRES_OK(ctx, FromAbi(b200_memcpy_d2d_async(outs[i]->raw_data(),
+                                                            ctx->input(i).raw_data(),
+                                                            outs[i]->TotalBytes(), stream),
+                                      "copy"));
+    } else if (collective && n > 1 && pack_enabled) {
+      int64 total = 0;
+      std::vector<int64> offset(n);
+      for (int i = 0; i < n; ++i) {  // 256-byte aligned slots (in elements)
+        offset[i] = total;
+        const int64 per = 256 / static_cast<int64>(sizeof(T));
+        total += (ctx->input(i).NumElements() + per - 1) / per * per;
+      }
+      Tensor arena;
+      OP_REQUIRES_OK(ctx, ctx->allocate_temp(DataTypeToEnum<T>::value, TensorShape({total}), &arena));
+      char* base = static_cast<char*>(arena.raw_data());
+      for (int i = 0; i < n; ++i)
+        if (ctx->input(i).NumElements() > 0)
+          OP_REQUIRES_OK(ctx, FromAbi(b200_memcpy_d2d_async(base + offset[i] * sizeof(T),
+                                                            ctx->input(i).raw_data(),
+                                                            ctx->input(i).TotalBytes(), stream),
+                                      "gather"));
+      OP_REQUIRES_OK(ctx, FromAbi(b200_nccl_all_reduce(AbiType<T>::v, base, base, total, average,
+                                                       dev->collective_comm(), stream),
+                                  "ncclAllReduce"));
+      for (int i = 0; i < n; ++i)
+        if (outs[i]->NumElements() > 0)
+          OP_REQUIRES_OK(ctx, FromAbi(b200_memcpy_d2d_async(outs[i]->raw_data(),
+                                                            base + offset[i] * sizeof(T),
+                                                            outs[i]->TotalBytes(), stream),
+                                      "scatter"));
+    } else if (collective) {
       OP_REQUIRES_OK(ctx, FromAbi(b200_nccl_group_start(), "ncclGroupStart"));
       Status s;
       for (int i = 0; i < n; ++i)

@@ -40,6 +40,13 @@ class Session {
                      const std::vector<std::string>& target_node_names,
                      std::vector<Tensor>* outputs) = 0;
   virtual Status Close() = 0;
+  // Additive (the role tf.contrib's StagingArea / prefetch-to-device plays for input pipelines):
+  // starts copying a pinned host tensor to the session's device on the host_to_device stream
+  // and returns immediately with a device-resident Tensor that Run() accepts as a feed value
+  // without another copy -- the copy of step i+1 overlaps the kernels of step i.
+  virtual Status StageFeed(const Tensor& host, Tensor* staged) {
+    return errors::Unimplemented("StageFeed is not supported by this session");
+  }
   virtual const RunStats& last_run_stats() const = 0;
 };
 

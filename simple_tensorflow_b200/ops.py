@@ -447,13 +447,36 @@ class GradientDescentOptimizer:
         grads = gradients(loss, var_list)
         return list(zip(grads, var_list))
 
-    def apply_gradients(self, grads_and_vars, name=None, num_replicas=1):
+    def apply_gradients(self, grads_and_vars, name=None, num_replicas=1, bucket_bytes=1 << 20):
         g = get_default_graph()
         updates = []
         grads_and_vars = [(gr, v) for gr, v in grads_and_vars if gr is not None]
-        if num_replicas > 1:  # replica data-parallel: one fused all-reduce, averaged
-            reduced = all_reduce_n([gr for gr, _ in grads_and_vars], 1.0 / num_replicas)
-            grads_and_vars = list(zip(reduced, [v for _, v in grads_and_vars]))
+        if num_replicas > 1:
+            # Replica data-parallel: gradients are averaged across replicas in buckets, filled
+            # in the order backprop emits them (graph-construction order) and closed once they
+            # hold `bucket_bytes`; each bucket is one collective that the executor starts as
+            # soon as its gradients exist, under the rest of the backward pass.
+            # bucket_bytes=None: a single all-reduce after the whole backward pass.
+            reduced = {}
+            bucket, held = [], 0
+            position = {id(op): i for i, op in enumerate(g.operations)}
+            todo = sorted(grads_and_vars, key=lambda gv: position.get(id(gv[0].op), 0))
+            for i, (gr, v) in enumerate(todo):
+                if bucket and bucket[0][0].dtype != gr.dtype:
+                    for (g0, v0), r in zip(bucket, all_reduce_n([b[0] for b in bucket], 1.0 / num_replicas)):
+                        reduced[id(v0)] = r
+                    bucket, held = [], 0
+                bucket.append((gr, v))
+                shape = _shape(gr)
+                if shape is None:
+                    shape = getattr(v, "shape", None) or ()
+                held += int(np.prod(shape, dtype=np.int64)) * np.dtype(client._NP_OF[gr.dtype]).itemsize
+                last = i == len(todo) - 1
+                if last or (bucket_bytes is not None and held >= bucket_bytes):
+                    for (g0, v0), r in zip(bucket, all_reduce_n([b[0] for b in bucket], 1.0 / num_replicas)):
+                        reduced[id(v0)] = r
+                    bucket, held = [], 0
+            grads_and_vars = [(reduced[id(v)], v) for _, v in grads_and_vars]
         for grad, var in grads_and_vars:
             if grad is None:
                 continue
@@ -463,5 +486,6 @@ class GradientDescentOptimizer:
                                        "GradientDescent/update_" + var.op.name))
         return group(*updates, name=name or "GradientDescent")
 
-    def minimize(self, loss, var_list=None, name=None, num_replicas=1):
-        return self.apply_gradients(self.compute_gradients(loss, var_list), name, num_replicas)
+    def minimize(self, loss, var_list=None, name=None, num_replicas=1, bucket_bytes=1 << 20):
+        return self.apply_gradients(self.compute_gradients(loss, var_list), name, num_replicas,
+                                    bucket_bytes)

@@ -220,6 +220,53 @@ def test_all_reduce_n_single_replica(rng):
     np.testing.assert_array_equal(gb, b * np.float32(0.5))
 
 
+def test_staged_feeds_match_host_feeds(oracle, rng):
+    # Session.stage(): the copy runs on the host_to_device stream, Run() only orders behind it
+    a = rng.uniform(-1, 1, (300, 128)).astype(np.float32)
+    b = rng.uniform(-1, 1, (128, 64)).astype(np.float32)
+    tf.reset_default_graph()
+    pa, pb = tf.placeholder(tf.float32, [300, 128]), tf.placeholder(tf.float32, [128, 64])
+    c = tf.relu(tf.matmul(pa, pb))
+    axis = tf.placeholder(tf.int32, [])
+    am = tf.get_default_graph().create_op("ArgMax", [c, axis], {"T": ("type", tf.float32)},
+                                          "am").outputs[0]
+    with client.Session(tf.get_default_graph()) as sess:
+        host = sess.run(c, {pa: a, pb: b})
+        sa, sb = sess.stage(a), sess.stage(client.HostTensor.from_numpy(b))
+        assert sa.shape == (300, 128) and sa.nbytes == a.nbytes
+        staged = sess.run(c, {pa: sa, pb: sb})
+        np.testing.assert_array_equal(host, staged)
+        # a staged tensor stays valid device memory: feed it again, mixed with a host feed
+        again = sess.run(c, {pa: sa, pb: b})
+        np.testing.assert_array_equal(host, again)
+        assert sess.last_run_stats()["h2d_bytes"] == b.nbytes
+        # pipelined use: stage the next input before running the current one
+        nxt = sess.stage(a * 2)
+        cur = sess.run(c, {pa: sa, pb: sb})
+        np.testing.assert_array_equal(host, cur)
+        np.testing.assert_array_equal(sess.run(c, {pa: nxt, pb: sb}),
+                                      sess.run(c, {pa: a * 2, pb: b}))
+        # HostMemory consumers (ArgMax's `dimension`) cannot take a device-resident feed
+        with pytest.raises(client.OpError) as e:
+            sess.run(am, {pa: sa, pb: sb, axis: sess.stage(np.int32(1))})
+        assert e.value.error_code == 3 and "host memory" in e.value.message
+    ref = oracle.relu(oracle.matmul(a, b))
+    assert np.abs(host - ref).max() / np.abs(ref).max() < 3e-3
+
+
+def test_schedule_is_a_valid_order_for_out_of_order_graphs(rng):
+    # the list scheduler must respect data AND control edges whatever the construction order
+    tf.reset_default_graph()
+    v = tf.Variable(np.zeros(4, np.float32), name="v")
+    one = tf.constant(np.ones(4, np.float32))
+    with_init = tf.get_default_graph().create_op(
+        "Identity", [v.ref], {"T": ("type", tf.float32)}, "read_after_init",
+        control_inputs=[v.initializer])
+    out = tf.add_n([with_init.outputs[0], one])
+    with client.Session(tf.get_default_graph()) as sess:
+        np.testing.assert_array_equal(sess.run(out), np.ones(4, np.float32))
+
+
 def test_session_error_behaviour(rng):
     tf.reset_default_graph()
     x = tf.placeholder(tf.float32, [4, 3], "x")

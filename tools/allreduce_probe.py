@@ -1,0 +1,68 @@
+"""NCCL all-reduce latency probe through the C ABI (b200_nccl_all_reduce), one rank per GPU.
+
+  python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/allreduce_probe.py
+
+Prints per message size the device time of one in-place fp32 ncclAvg all-reduce (CUDA events on
+the launching stream, max over ranks) and the bus bandwidth 2(N-1)/N * bytes / t.  Not part of the
+product or the test-suite; the numbers explain bench.py's N>1 step time.
+"""
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from simple_tensorflow_b200 import _lib, replica  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = _lib.load()
+    comm = replica.init_nccl_comm(L, rank, world, local)
+    stream = ctypes.c_void_p()
+    _lib.check(L.b200_stream_create(ctypes.byref(stream)))
+    e0, e1 = ctypes.c_void_p(), ctypes.c_void_p()
+    _lib.check(L.b200_event_create(ctypes.byref(e0)))
+    _lib.check(L.b200_event_create(ctypes.byref(e1)))
+    rows = []
+    for nbytes in (4 << 10, 256 << 10, 1 << 20, 4 << 20, 12599296, 64 << 20):
+        n = nbytes // 4
+        buf = torch.ones(n, device="cuda", dtype=torch.float32)
+        iters = 50
+
+        def once():
+            _lib.check(L.b200_nccl_all_reduce(_lib.DT_FLOAT, buf.data_ptr(), buf.data_ptr(), n, 1,
+                                              comm, stream))
+        for _ in range(5):
+            once()
+        _lib.check(L.b200_stream_synchronize(stream))
+        dist.barrier()
+        _lib.check(L.b200_event_record(e0, stream))
+        for _ in range(iters):
+            once()
+        _lib.check(L.b200_event_record(e1, stream))
+        _lib.check(L.b200_stream_synchronize(stream))
+        ms = ctypes.c_float()
+        _lib.check(L.b200_event_elapsed_ms(e0, e1, ctypes.byref(ms)))
+        us = replica.max_over_ranks(ms.value * 1e3 / iters)
+        assert abs(float(buf[0].item()) - 1.0) < 1e-6
+        rows.append({"bytes": nbytes, "us": us,
+                     "busbw_gbs": 2.0 * (world - 1) / world * nbytes / (us * 1e-6) / 1e9})
+        if rank == 0:
+            print("%10d B  %8.1f us  busbw %7.1f GB/s" % (nbytes, us, rows[-1]["busbw_gbs"]), flush=True)
+    if rank == 0 and len(sys.argv) > 1:
+        json.dump({"world": world, "rows": rows}, open(sys.argv[1], "w"), indent=1)
+    dist.barrier()
+    _lib.check(L.b200_nccl_comm_destroy(comm))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
