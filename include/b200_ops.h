@@ -77,6 +77,9 @@ B200_API int b200_get_matmul_precision(void);
  * Mirrors Stream / StreamExecutor members the reference's GPU device uses
  * (stream_executor/stream.h:116,189,214,1482-1531,1591; stream_executor_pimpl.h:110,191). */
 B200_API int b200_stream_create(void** stream);
+/* high_priority != 0: the device's highest stream priority (the reference creates all streams at
+ * default priority; the collective stream wants its few CTAs scheduled ahead of queued GEMMs). */
+B200_API int b200_stream_create_with_priority(void** stream, int high_priority);
 B200_API int b200_stream_destroy(void* stream);
 B200_API int b200_stream_synchronize(void* stream);          /* BlockHostUntilDone */
 B200_API int b200_stream_wait_event(void* stream, void* event); /* ThenWaitFor */

@@ -41,6 +41,7 @@ SIGNATURES = {
     "b200_set_matmul_precision": (c_int, [c_int]),
     "b200_get_matmul_precision": (c_int, []),
     "b200_stream_create": (c_int, [ctypes.POINTER(c_void_p)]),
+    "b200_stream_create_with_priority": (c_int, [ctypes.POINTER(c_void_p), c_int]),
     "b200_stream_destroy": (c_int, [c_void_p]),
     "b200_stream_synchronize": (c_int, [c_void_p]),
     "b200_stream_wait_event": (c_int, [c_void_p, c_void_p]),

@@ -262,6 +262,15 @@ int b200_stream_create(void** stream) {
   *stream = s;
   return B200_OK;
 }
+int b200_stream_create_with_priority(void** stream, int high_priority) {
+  int least = 0, greatest = 0;
+  CUDA_RC(cudaDeviceGetStreamPriorityRange(&least, &greatest), "b200_stream_create_with_priority");
+  cudaStream_t s;
+  CUDA_RC(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? greatest : least),
+          "b200_stream_create_with_priority");
+  *stream = s;
+  return B200_OK;
+}
 int b200_stream_destroy(void* stream) {
   CUDA_RC(cudaStreamDestroy(as_stream(stream)), "b200_stream_destroy");
   return B200_OK;

@@ -194,12 +194,17 @@ Status DirectSession::GetOrCreateExecutors(const std::vector<std::string>& feeds
     TF_RETURN_IF_ERROR(visit(n->second));
   }
   // Schedule.  The DFS above pruned and checked for cycles; the execution order is a list
-  // schedule of the pruned set: collectives (own stream) as soon as their inputs exist, every
-  // other node in graph-construction order (the order a front-end emits backprop in: last layer
-  // first), so a layer's gradient exchange runs under the remaining backward kernels.
+  // schedule of the pruned set: nodes in graph-construction order (the order a front-end emits
+  // backprop in: last layer first); when collectives run on their own stream they are taken as
+  // soon as their inputs exist, so a bucket's exchange runs under the remaining backward kernels.
+  // Measured on 4 and 8 B200 (profiles/r01_notes.md): NCCL's 24-32 CTAs land on as many TPCs
+  // and break up the CTA pairs of the persistent GEMMs running beside them, so the side-stream
+  // exchange costs more than it hides; the default is one in-place all-reduce of the whole
+  // gradient arena on the compute stream.  B200TF_COLLECTIVE_OVERLAP=1 turns the overlap on.
+  const char* ov = getenv("B200TF_COLLECTIVE_OVERLAP");
   const bool overlap_collectives = device_->num_replicas() > 1 &&
-                                   device_->collective_comm() != nullptr &&
-                                   !EnvFlagOff("B200TF_COLLECTIVE_OVERLAP");
+                                   device_->collective_comm() != nullptr && ov != nullptr &&
+                                   std::strcmp(ov, "1") == 0;
   auto is_collective = [&](int n) {
     return overlap_collectives && nodes_[n]->def.op.rfind("B200AllReduce", 0) == 0 &&
            nodes_[n]->def.op != "B200AllReduce";  // the ref-variable form stays on compute

@@ -1,6 +1,7 @@
 #include "tensorflow/core/common_runtime/gpu/gpu_device.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace tensorflow {
@@ -62,7 +63,10 @@ Status BaseGPUDevice::Create(int gpu_id, size_t memory_limit_bytes,
   d->h2d_stream_.reset(new gpu::Stream());
   d->h2d_stream_->Init();
   d->collective_stream_.reset(new gpu::Stream());
-  d->collective_stream_->Init();
+  {
+    const char* pr = getenv("B200TF_COLLECTIVE_PRIORITY");  // default: high
+    d->collective_stream_->Init(pr == nullptr || std::strcmp(pr, "0") != 0);
+  }
   d->h2d_fence_.reset(new gpu::Event());
   if (!d->stream_->ok() || !d->h2d_stream_->ok() || !d->collective_stream_->ok() ||
       !d->h2d_fence_->Init())

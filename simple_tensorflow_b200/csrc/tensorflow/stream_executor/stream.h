@@ -56,8 +56,9 @@ class Stream {
   ~Stream() {
     if (owned_ && handle_) b200_stream_destroy(handle_);
   }
-  Stream& Init() {
-    ok_ = b200_stream_create(&handle_) == 0;
+  Stream& Init(bool high_priority = false) {
+    ok_ = (high_priority ? b200_stream_create_with_priority(&handle_, 1)
+                         : b200_stream_create(&handle_)) == 0;
     owned_ = ok_;
     return *this;
   }

@@ -447,7 +447,7 @@ class GradientDescentOptimizer:
         grads = gradients(loss, var_list)
         return list(zip(grads, var_list))
 
-    def apply_gradients(self, grads_and_vars, name=None, num_replicas=1, bucket_bytes=1 << 20):
+    def apply_gradients(self, grads_and_vars, name=None, num_replicas=1, bucket_bytes=None):
         g = get_default_graph()
         updates = []
         grads_and_vars = [(gr, v) for gr, v in grads_and_vars if gr is not None]
@@ -455,8 +455,10 @@ class GradientDescentOptimizer:
             # Replica data-parallel: gradients are averaged across replicas in buckets, filled
             # in the order backprop emits them (graph-construction order) and closed once they
             # hold `bucket_bytes`; each bucket is one collective that the executor starts as
-            # soon as its gradients exist, under the rest of the backward pass.
-            # bucket_bytes=None: a single all-reduce after the whole backward pass.
+            # soon as its gradients exist (under the rest of the backward pass when the session
+            # runs collectives on their own stream, B200TF_COLLECTIVE_OVERLAP=1).
+            # bucket_bytes=None (default, fastest measured on 2-8 B200): a single all-reduce of
+            # one contiguous gradient arena after the whole backward pass.
             reduced = {}
             bucket, held = [], 0
             position = {id(op): i for i, op in enumerate(g.operations)}
@@ -486,6 +488,6 @@ class GradientDescentOptimizer:
                                        "GradientDescent/update_" + var.op.name))
         return group(*updates, name=name or "GradientDescent")
 
-    def minimize(self, loss, var_list=None, name=None, num_replicas=1, bucket_bytes=1 << 20):
+    def minimize(self, loss, var_list=None, name=None, num_replicas=1, bucket_bytes=None):
         return self.apply_gradients(self.compute_gradients(loss, var_list), name, num_replicas,
                                     bucket_bytes)

@@ -18,10 +18,10 @@ def _gpu_count():
 
 
 @pytest.mark.parametrize("bucket,overlap,pack", [
-    ("default", "1", "1"),   # per-layer buckets on the collective stream, packed arena
-    ("default", "1", "0"),   # ... grouped in-place collectives
-    ("default", "0", "1"),   # same buckets on the compute stream
-    ("none", "1", "1"),      # one all-reduce after the whole backward pass
+    ("default", "0", "1"),   # one all-reduce of the gradient arena after the backward pass
+    ("1048576", "1", "1"),   # per-layer buckets on the collective stream
+    ("1048576", "1", "0"),   # ... grouped in-place collectives on the first (unlearned) step
+    ("1048576", "0", "1"),   # same buckets on the compute stream
     ("2048", "1", "1"),      # tiny buckets: every gradient its own collective
 ])
 def test_two_replica_training_matches_full_batch_oracle(bucket, overlap, pack):

@@ -57,6 +57,45 @@ def main():
                      "busbw_gbs": 2.0 * (world - 1) / world * nbytes / (us * 1e-6) / 1e9})
         if rank == 0:
             print("%10d B  %8.1f us  busbw %7.1f GB/s" % (nbytes, us, rows[-1]["busbw_gbs"]), flush=True)
+    # ---- same sizes on NCCL symmetric windows (ncclMemAlloc + ncclCommWindowRegister, 2.27+)
+    try:
+        nccl = ctypes.CDLL("libnccl.so.2")
+        nccl.ncclMemAlloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
+        nccl.ncclCommWindowRegister.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
+        nccl.ncclAllReduce.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                                       ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        for nbytes in (4 << 10, 1 << 20, 4 << 20, 12599296):
+            n = nbytes // 4
+            size = (nbytes + 4095) // 4096 * 4096
+            ptr, win = ctypes.c_void_p(), ctypes.c_void_p()
+            rc = nccl.ncclMemAlloc(ctypes.byref(ptr), size)
+            assert rc == 0, "ncclMemAlloc rc=%d" % rc
+            rc = nccl.ncclCommWindowRegister(comm, ptr, size, ctypes.byref(win), 1)
+            assert rc == 0, "ncclCommWindowRegister rc=%d" % rc
+            _lib.check(L.b200_memset_async(ptr, 0, size, stream))
+
+            def once_sym():
+                rc = nccl.ncclAllReduce(ptr, ptr, n, 7, 4, comm, stream)
+                assert rc == 0, rc
+            for _ in range(5):
+                once_sym()
+            _lib.check(L.b200_stream_synchronize(stream))
+            dist.barrier()
+            _lib.check(L.b200_event_record(e0, stream))
+            for _ in range(50):
+                once_sym()
+            _lib.check(L.b200_event_record(e1, stream))
+            _lib.check(L.b200_stream_synchronize(stream))
+            ms = ctypes.c_float()
+            _lib.check(L.b200_event_elapsed_ms(e0, e1, ctypes.byref(ms)))
+            us = replica.max_over_ranks(ms.value * 1e3 / 50)
+            rows.append({"bytes": nbytes, "us": us, "symmetric_window": True})
+            if rank == 0:
+                print("%10d B  %8.1f us  (symmetric window)" % (nbytes, us), flush=True)
+    except Exception as e:  # noqa: BLE001
+        if rank == 0:
+            print("symmetric-window probe failed:", repr(e), flush=True)
     if rank == 0 and len(sys.argv) > 1:
         json.dump({"world": world, "rows": rows}, open(sys.argv[1], "w"), indent=1)
     dist.barrier()
