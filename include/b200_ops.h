@@ -163,6 +163,12 @@ B200_API int b200_softmax(int dtype, const void* logits, void* out, int64_t rows
  * backprop = softmax - labels. */
 B200_API int b200_softmax_xent(int dtype, const void* logits, const void* labels, void* loss,
                                void* backprop, int64_t rows, int64_t cols, void* stream);
+/* Same, with the backprop output multiplied by a DEVICE scalar before it is stored (the
+ * `backprop * grad_loss` Mul that nn_grad.py:323-333 emits right behind the op, folded in by the
+ * executor when grad_loss is a scalar constant).  fp32 only; NULL scale == b200_softmax_xent. */
+B200_API int b200_softmax_xent_scaled(int dtype, const void* logits, const void* labels, void* loss,
+                                      void* backprop, int64_t rows, int64_t cols,
+                                      const float* backprop_scale, void* stream);
 
 /* ------------------------------------------------------------------ MaxPool / MaxPoolGrad (NHWC)
  * MaxPoolForwardNHWC (core/kernels/maxpooling_op_gpu.cu.cc:93-129) with the CPU kernel's

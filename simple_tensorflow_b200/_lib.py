@@ -76,6 +76,8 @@ SIGNATURES = {
     "b200_softmax": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "b200_softmax_xent": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_int64, c_void_p]),
+    "b200_softmax_xent_scaled": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                  c_int64, c_void_p, c_void_p]),
     "b200_max_pool": (c_int, [c_int, c_void_p, c_void_p] + [c_int64] * 6 + [c_int] * 6
                       + [c_void_p]),
     "b200_max_pool_grad": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 6

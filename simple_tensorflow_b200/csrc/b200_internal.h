@@ -75,4 +75,43 @@ void profile_gemm_launch_end(cudaStream_t stream, double flops);
 // Scratch that lets gemm_dispatch use split-K for this shape (0 when it would not split).
 size_t gemm_workspace_bytes(int dtype, long long M, long long N, long long K, long long batch);
 
+#ifdef __CUDACC__
+// Programmatic dependent launch (sm_90+).  Every kernel of the library executes the trigger first
+// thing, so a kernel launched behind it WITH cudaLaunchAttributeProgrammaticStreamSerialization
+// (only the tcgen05 GEMM and its split-K reduce) may have its CTAs scheduled while this grid is
+// still draining: launch latency and prologue (barrier init, TMEM allocation, cluster sync)
+// disappear under the predecessor's tail.  Such a kernel must execute pdl_wait() -- which
+// returns once every prerequisite grid has completed and its memory is visible -- before it
+// touches global memory.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// First statement of every kernel but the GEMM (which overlaps its prologue first): let the
+// successor be scheduled, then wait for the predecessors' memory.
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+bool pdl_enabled();  // runtime.cu: on unless B200TF_NO_PDL is set
+// kernel<<<grid, block, smem, stream>>>(args...) with programmatic stream serialization allowed:
+// the grid may be scheduled while its predecessor in the stream drains (every kernel begins with
+// pdl_prologue(), so nothing is read or written before the predecessor has completed).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 }  // namespace b200

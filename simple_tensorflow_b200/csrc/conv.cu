@@ -36,6 +36,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256)
 im2col_kernel(const T* __restrict__ in, T* __restrict__ col, ConvG g, long long rows,
               int threads_per_row, int rows_per_cta) {
+  pdl_prologue();
   const int lane_in_row = threadIdx.x % threads_per_row;
   const int row_in_group = threadIdx.x / threads_per_row;
   const int groups = 256 / threads_per_row;  // pixel rows handled concurrently by the CTA
@@ -109,6 +110,7 @@ __device__ __forceinline__ __nv_bfloat16 cvt_out<__nv_bfloat16>(float v) {
 template <typename T>
 __global__ void __launch_bounds__(256)
 col2im_gather_kernel(const T* __restrict__ col, T* __restrict__ dx, ConvG g, long long total) {
+  pdl_prologue();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
   const int c = (int)(idx % g.C);
@@ -142,6 +144,7 @@ col2im_gather_kernel(const T* __restrict__ col, T* __restrict__ dx, ConvG g, lon
 template <typename T>
 __global__ void __launch_bounds__(256)
 flip_filter_kernel(const T* __restrict__ w, T* __restrict__ wt, int R, int S, int C, int K) {
+  pdl_prologue();
   const int i = blockIdx.x * 256 + threadIdx.x;  // index into wt [R, S, K, C]
   if (i >= R * S * C * K) return;
   const int c = i % C;
@@ -219,11 +222,11 @@ static int run_im2col(const void* in, void* col, const ConvG& g, cudaStream_t s)
   int tpr, rpc;
   if (g.C % V16 == 0 && aligned16(in) && aligned16(col)) {
     plan(g.ldk / V16, &tpr, &rpc);
-    im2col_kernel<T, V16><<<(unsigned)((rows + rpc - 1) / rpc), 256, 0, s>>>(
+    launch_pdl(im2col_kernel<T, V16>, dim3((unsigned)((rows + rpc - 1) / rpc)), dim3(256), 0, s, 
         static_cast<const T*>(in), static_cast<T*>(col), g, rows, tpr, rpc);
   } else {
     plan(g.ldk, &tpr, &rpc);
-    im2col_kernel<T, 1><<<(unsigned)((rows + rpc - 1) / rpc), 256, 0, s>>>(
+    launch_pdl(im2col_kernel<T, 1>, dim3((unsigned)((rows + rpc - 1) / rpc)), dim3(256), 0, s, 
         static_cast<const T*>(in), static_cast<T*>(col), g, rows, tpr, rpc);
   }
   note_launch();
@@ -442,10 +445,10 @@ int b200_conv2d_backprop_input(int dtype, const void* filter, const void* out_ba
         cd.pl >= 0 && aligned16(in_backprop) && conv_a_supported(dtype, cd)) {
       const int nflt = g.R * g.S * g.C * g.K;
       if (dtype == B200_DT_FLOAT)
-        flip_filter_kernel<float><<<(nflt + 255) / 256, 256, 0, s>>>(
+        launch_pdl(flip_filter_kernel<float>, dim3((nflt + 255) / 256), dim3(256), 0, s, 
             static_cast<const float*>(filter), static_cast<float*>(workspace), g.R, g.S, g.C, g.K);
       else
-        flip_filter_kernel<__nv_bfloat16><<<(nflt + 255) / 256, 256, 0, s>>>(
+        launch_pdl(flip_filter_kernel<__nv_bfloat16>, dim3((nflt + 255) / 256), dim3(256), 0, s, 
             static_cast<const __nv_bfloat16*>(filter), static_cast<__nv_bfloat16*>(workspace), g.R,
             g.S, g.C, g.K);
       note_launch();
@@ -496,10 +499,10 @@ int b200_conv2d_backprop_input(int dtype, const void* filter, const void* out_ba
   rc = gemm_dispatch(a, s);
   if (rc) return rc;
   if (dtype == B200_DT_FLOAT)
-    col2im_gather_kernel<float><<<(unsigned)((nin + 255) / 256), 256, 0, s>>>(
+    launch_pdl(col2im_gather_kernel<float>, dim3((unsigned)((nin + 255) / 256)), dim3(256), 0, s, 
         static_cast<const float*>(workspace), static_cast<float*>(in_backprop), g, nin);
   else
-    col2im_gather_kernel<__nv_bfloat16><<<(unsigned)((nin + 255) / 256), 256, 0, s>>>(
+    launch_pdl(col2im_gather_kernel<__nv_bfloat16>, dim3((unsigned)((nin + 255) / 256)), dim3(256), 0, s, 
         static_cast<const __nv_bfloat16*>(workspace), static_cast<__nv_bfloat16*>(in_backprop), g,
         nin);
   note_launch();

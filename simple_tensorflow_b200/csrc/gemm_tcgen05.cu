@@ -157,6 +157,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
                     const __grid_constant__ CUtensorMap tmapC,
                     const __grid_constant__ CUtensorMap tmapF, TOut* __restrict__ C,
                     GemmShape s) {
+  pdl_launch_dependents();
   using Tr = GemmTraits<TIn>;
   constexpr int BK = Tr::kBK;
   constexpr int kStages = gemm_stages<BN, kCtas>();
@@ -232,6 +233,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
     __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above overlapped the previous kernel's tail (programmatic dependent launch);
+  // from here on this grid reads and writes global memory.
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer (one per CTA) =====================
@@ -662,6 +666,8 @@ template <typename TOut>
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, TOut* __restrict__ C, int splits,
                      long long batch, int M, int N, int ldc, long long strideC) {
+  pdl_launch_dependents();
+  pdl_wait();  // launched programmatically behind the GEMM that writes `partial`
   const long long per_split = batch * (long long)M * N;
   const int n4 = (N + 3) / 4;
   const long long total = batch * (long long)M * n4;
@@ -916,24 +922,32 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   const int grid_units = (int)(work < units ? work : units);
   const bool prof = profile_enabled();
   if (prof) profile_gemm_launch_begin(stream);
-  if (kCtas == 1) {
-    kern<<<grid_units, kGemmThreads, smem, stream>>>(ma, mb, mc, mf, static_cast<TOut*>(g.c), s);
-  } else {
+  const bool pdl = pdl_enabled();
+  {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid_units * kCtas);
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCtas;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (kCtas > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = kCtas;
+      attr[na].val.clusterDim.y = 1;
+      attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (pdl) {  // prologue overlaps the predecessor's tail; the kernel pdl_wait()s before global I/O
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mf, static_cast<TOut*>(g.c), s);
     if (e != cudaSuccess) {
-      set_last_error("gemm_tcgen05 (cta pair) launch: %s", cudaGetErrorString(e));
+      set_last_error("gemm_tcgen05 launch: %s", cudaGetErrorString(e));
       cudaGetLastError();
       return B200_INTERNAL;
     }
@@ -944,8 +958,24 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     const long long groups = g.batch * g.M * ((g.N + 3) / 4);
     long long rblocks = (groups + 255) / 256;
     if (rblocks > 8LL * sm_count()) rblocks = 8LL * sm_count();
-    splitk_reduce_kernel<TOut><<<(unsigned)rblocks, 256, 0, stream>>>(
-        s.partial, static_cast<TOut*>(g.c), splits, g.batch, s.M, s.N, s.ldc, s.strideC);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)rblocks);
+    cfg.blockDim = dim3(256);
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl && !prof ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<TOut>,
+                                       static_cast<const float*>(s.partial), static_cast<TOut*>(g.c),
+                                       splits, (long long)g.batch, s.M, s.N, s.ldc,
+                                       (long long)s.strideC);
+    if (e != cudaSuccess) {
+      set_last_error("splitk_reduce launch: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return B200_INTERNAL;
+    }
     note_launch();
   }
   return check_launch("gemm_tcgen05");

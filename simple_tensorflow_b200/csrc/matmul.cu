@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(256)
 gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int M, int N,
                  int K, long long lda, long long ldb, long long ldc, long long sA, long long sB,
                  long long sC, bool a_mn, bool b_mn) {
+  pdl_prologue();
   __shared__ float As[kSimtK][kSimtTile + 1];
   __shared__ float Bs[kSimtK][kSimtTile + 1];
   const int batch = blockIdx.z;
@@ -116,6 +117,7 @@ template <typename T, int NMAX>
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int M, int N,
                    int K, long long lda, long long ldb, long long ldc, bool a_mn, bool b_mn) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -143,7 +145,7 @@ int gemm_simt(const GemmArgs& g, cudaStream_t stream) {
   if (g.batch == 1 && g.N <= 32 && g.K >= 64 && g.M >= 64) {
     const unsigned grid = (unsigned)((g.M + 7) / 8);
 #define SKINNY(T, NMAX)                                                                      \
-  gemm_skinny_kernel<T, NMAX><<<grid, 256, 0, stream>>>(                                     \
+  launch_pdl(gemm_skinny_kernel<T, NMAX>, dim3(grid), dim3(256), 0, stream,                                      \
       static_cast<const T*>(g.a), static_cast<const T*>(g.b), static_cast<T*>(g.c), (int)g.M, \
       (int)g.N, (int)g.K, g.lda, g.ldb, g.ldc, g.a_mn_major, g.b_mn_major)
     if (g.dtype == B200_DT_FLOAT) {
@@ -165,12 +167,12 @@ int gemm_simt(const GemmArgs& g, cudaStream_t stream) {
   dim3 grid((unsigned)((g.N + kSimtTile - 1) / kSimtTile),
             (unsigned)((g.M + kSimtTile - 1) / kSimtTile), (unsigned)g.batch);
   if (g.dtype == B200_DT_FLOAT) {
-    gemm_simt_kernel<float><<<grid, 256, 0, stream>>>(
+    launch_pdl(gemm_simt_kernel<float>, dim3(grid), dim3(256), 0, stream, 
         static_cast<const float*>(g.a), static_cast<const float*>(g.b), static_cast<float*>(g.c),
         (int)g.M, (int)g.N, (int)g.K, g.lda, g.ldb, g.ldc, g.strideA, g.strideB, g.strideC,
         g.a_mn_major, g.b_mn_major);
   } else if (g.dtype == B200_DT_BFLOAT16) {
-    gemm_simt_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(
+    launch_pdl(gemm_simt_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, 
         static_cast<const __nv_bfloat16*>(g.a), static_cast<const __nv_bfloat16*>(g.b),
         static_cast<__nv_bfloat16*>(g.c), (int)g.M, (int)g.N, (int)g.K, g.lda, g.ldb, g.ldc,
         g.strideA, g.strideB, g.strideC, g.a_mn_major, g.b_mn_major);

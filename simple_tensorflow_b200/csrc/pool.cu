@@ -79,6 +79,7 @@ struct PoolVec<__nv_bfloat16, 1> {
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
 max_pool_fwd_kernel(const T* __restrict__ in, T* __restrict__ out, PoolGeom g, long long total) {
+  pdl_prologue();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
   const int CV = g.C / V;
@@ -110,6 +111,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256)
 max_pool_grad_kernel(const T* __restrict__ in, const T* __restrict__ grad, T* __restrict__ dx,
                      PoolGeom g, long long total) {
+  pdl_prologue();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
   const int CV = g.C / V;
@@ -173,6 +175,7 @@ template <typename T, int V>
 __global__ void __launch_bounds__(256)
 max_pool_grad_disjoint_kernel(const T* __restrict__ in, const T* __restrict__ grad,
                               T* __restrict__ dx, PoolGeom g, long long total) {
+  pdl_prologue();
   const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
   if (idx >= total) return;
   const int CV = g.C / V;
@@ -271,19 +274,19 @@ int b200_max_pool(int dtype, const void* in, void* out, int64_t batch, int64_t i
   if (dtype == B200_DT_FLOAT) {
     if (al && channels % 4 == 0) {
       const long long t = nout / 4;
-      max_pool_fwd_kernel<float, 4><<<(unsigned)((t + 255) / 256), 256, 0, s>>>(
+      launch_pdl(max_pool_fwd_kernel<float, 4>, dim3((unsigned)((t + 255) / 256)), dim3(256), 0, s, 
           static_cast<const float*>(in), static_cast<float*>(out), g, t);
     } else {
-      max_pool_fwd_kernel<float, 1><<<(unsigned)((nout + 255) / 256), 256, 0, s>>>(
+      launch_pdl(max_pool_fwd_kernel<float, 1>, dim3((unsigned)((nout + 255) / 256)), dim3(256), 0, s, 
           static_cast<const float*>(in), static_cast<float*>(out), g, nout);
     }
   } else {
     if (al && channels % 8 == 0) {
       const long long t = nout / 8;
-      max_pool_fwd_kernel<__nv_bfloat16, 8><<<(unsigned)((t + 255) / 256), 256, 0, s>>>(
+      launch_pdl(max_pool_fwd_kernel<__nv_bfloat16, 8>, dim3((unsigned)((t + 255) / 256)), dim3(256), 0, s, 
           static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), g, t);
     } else {
-      max_pool_fwd_kernel<__nv_bfloat16, 1><<<(unsigned)((nout + 255) / 256), 256, 0, s>>>(
+      launch_pdl(max_pool_fwd_kernel<__nv_bfloat16, 1>, dim3((unsigned)((nout + 255) / 256)), dim3(256), 0, s, 
           static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out), g, nout);
     }
   }
@@ -319,7 +322,7 @@ int b200_max_pool_grad(int dtype, const void* orig_in, const void* orig_out, con
 #define POOLG(T, V)                                                                            \
   do {                                                                                         \
     const long long t = nout / V;                                                              \
-    max_pool_grad_disjoint_kernel<T, V><<<(unsigned)((t + 255) / 256), 256, 0, s>>>(           \
+    launch_pdl(max_pool_grad_disjoint_kernel<T, V>, dim3((unsigned)((t + 255) / 256)), dim3(256), 0, s,            \
         static_cast<const T*>(orig_in), static_cast<const T*>(grad), static_cast<T*>(in_backprop), \
         g, t);                                                                                 \
   } while (0)
@@ -335,22 +338,22 @@ int b200_max_pool_grad(int dtype, const void* orig_in, const void* orig_out, con
   if (dtype == B200_DT_FLOAT) {
     if (al && channels % 4 == 0) {
       const long long t = nin / 4;
-      max_pool_grad_kernel<float, 4><<<(unsigned)((t + 255) / 256), 256, 0, s>>>(
+      launch_pdl(max_pool_grad_kernel<float, 4>, dim3((unsigned)((t + 255) / 256)), dim3(256), 0, s, 
           static_cast<const float*>(orig_in), static_cast<const float*>(grad),
           static_cast<float*>(in_backprop), g, t);
     } else {
-      max_pool_grad_kernel<float, 1><<<(unsigned)((nin + 255) / 256), 256, 0, s>>>(
+      launch_pdl(max_pool_grad_kernel<float, 1>, dim3((unsigned)((nin + 255) / 256)), dim3(256), 0, s, 
           static_cast<const float*>(orig_in), static_cast<const float*>(grad),
           static_cast<float*>(in_backprop), g, nin);
     }
   } else {
     if (al && channels % 8 == 0) {
       const long long t = nin / 8;
-      max_pool_grad_kernel<__nv_bfloat16, 8><<<(unsigned)((t + 255) / 256), 256, 0, s>>>(
+      launch_pdl(max_pool_grad_kernel<__nv_bfloat16, 8>, dim3((unsigned)((t + 255) / 256)), dim3(256), 0, s, 
           static_cast<const __nv_bfloat16*>(orig_in), static_cast<const __nv_bfloat16*>(grad),
           static_cast<__nv_bfloat16*>(in_backprop), g, t);
     } else {
-      max_pool_grad_kernel<__nv_bfloat16, 1><<<(unsigned)((nin + 255) / 256), 256, 0, s>>>(
+      launch_pdl(max_pool_grad_kernel<__nv_bfloat16, 1>, dim3((unsigned)((nin + 255) / 256)), dim3(256), 0, s, 
           static_cast<const __nv_bfloat16*>(orig_in), static_cast<const __nv_bfloat16*>(grad),
           static_cast<__nv_bfloat16*>(in_backprop), g, nin);
     }

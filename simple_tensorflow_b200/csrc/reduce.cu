@@ -8,6 +8,7 @@
 //                -> one kernel, one read + one write of the matrix
 //   Xent         xent_op_gpu.cu.cc (XentEigenImpl, xent_op.h:47-113) -> one kernel
 //   ArgMax       argmax_op_gpu.cu.cc (Eigen argmax reducer, argmax_op.h:29-42)
+#include <atomic>
 #include <cfloat>
 #include <cuda_bf16.h>
 
@@ -53,10 +54,18 @@ __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) {
 // vector-columns; if W < 32 the spare lanes fold extra rows (fold = 32 / W) so small channel
 // counts (LeNet: 32, 64, 10) still use every lane.  Each CTA reduces a contiguous chunk of rows
 // and writes one partial row; stage 2 adds the partial rows in chunk order.
-template <typename T, int VEC>
+// Single-launch form: the CTA that finishes a column tile LAST (ticket from a self-resetting
+// counter) adds that tile's partial rows in the same fixed order as bias_grad_stage2, so the result
+// is bit-identical to the two-kernel form and independent of which CTA happens to be last.
+constexpr int kBiasGradSlots = 32, kBiasGradMaxTiles = 1024;
+__device__ unsigned int g_bias_grad_tickets[kBiasGradSlots][kBiasGradMaxTiles];
+
+template <typename T, int VEC, typename TOut = T>
 __global__ void __launch_bounds__(256)
 bias_grad_stage1(const T* __restrict__ g, float* __restrict__ partial, long long rows,
-                 int channels, int rows_per_chunk) {
+                 int channels, int rows_per_chunk, TOut* __restrict__ fused_out = nullptr,
+                 unsigned int* __restrict__ tickets = nullptr) {
+  pdl_prologue();
   const int W = channels / VEC;
   const int wt = W < 32 ? W : 32;        // vector-columns handled per CTA
   const int fold = W < 32 ? 32 / W : 1;  // rows covered by one warp-row
@@ -126,13 +135,44 @@ bias_grad_stage1(const T* __restrict__ g, float* __restrict__ partial, long long
     float* dst = partial + (long long)blockIdx.y * channels + (long long)cv * VEC;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) dst[j] = tot[j];
+    __threadfence();  // publish this CTA's partial row before taking a ticket
   }
+  if (fused_out == nullptr) return;
+  __shared__ bool is_last;
+  __syncthreads();
+  if (x == 0 && y == 0) is_last = atomicAdd(&tickets[blockIdx.x], 1u) == gridDim.y - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int nchunks = gridDim.y;
+  float tot[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) tot[j] = 0.f;
+  if (sub == 0 && cv < W)
+    for (int k = y; k < nchunks; k += 8) {
+      const float* src = partial + (long long)k * channels + (long long)cv * VEC;
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) tot[j] += __ldcg(src + j);
+    }
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) sm[y][x][j] = tot[j];
+  __syncthreads();
+  if (y == 0 && sub == 0 && cv < W) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float t = 0.f;
+      for (int yy = 0; yy < 8; ++yy) t += sm[yy][x][j];
+      stf<TOut>(fused_out + (long long)cv * VEC + j, t);
+    }
+  }
+  if (x == 0 && y == 0) tickets[blockIdx.x] = 0;  // ready for the next launch that uses this slot
 }
 // Stage 2: out[c] = sum over chunks (ascending); block (32, 8), 8-way strided then ordered merge.
 template <typename T>
 __global__ void __launch_bounds__(256)
 bias_grad_stage2(const float* __restrict__ partial, T* __restrict__ out, int nchunks,
                  int channels) {
+  pdl_prologue();
   const int c = blockIdx.x * 32 + threadIdx.x;
   float acc = 0.f;
   if (c < channels)
@@ -176,6 +216,7 @@ static BiasGradPlan plan_bias_grad(int dtype, long long rows, long long channels
 template <typename T, int NV, bool kLog>
 __global__ void __launch_bounds__(256)
 softmax_warp_kernel(const T* __restrict__ logits, T* __restrict__ out, long long rows, int cols) {
+  pdl_prologue();
   constexpr int E = 16 / sizeof(T);  // elements per 16-byte vector
   const int lane = threadIdx.x & 31;
   // persistent: warps stride over rows (grid capped at ~8 CTAs/SM, no CTA wave transitions)
@@ -265,6 +306,7 @@ __device__ __forceinline__ float block_reduce(float v, bool is_max, float* sm) {
 template <typename T, bool kLog>
 __global__ void __launch_bounds__(256)
 softmax_block_kernel(const T* __restrict__ logits, T* __restrict__ out, int cols) {
+  pdl_prologue();
   __shared__ float sm[8];
   const T* x = logits + (long long)blockIdx.x * cols;
   T* y = out + (long long)blockIdx.x * cols;
@@ -284,8 +326,10 @@ softmax_block_kernel(const T* __restrict__ logits, T* __restrict__ out, int cols
 template <typename T>
 __global__ void __launch_bounds__(256)
 xent_block_kernel(const T* __restrict__ logits, const T* __restrict__ labels, T* __restrict__ loss,
-                  T* __restrict__ backprop, int cols) {
+                  T* __restrict__ backprop, int cols, const float* __restrict__ bp_scale) {
+  pdl_prologue();
   __shared__ float sm[8];
+  const float sc = bp_scale ? __ldg(bp_scale) : 1.0f;  // x * 1.0f is exact: unscaled unchanged
   const T* x = logits + (long long)blockIdx.x * cols;
   const T* l = labels + (long long)blockIdx.x * cols;
   T* bp = backprop + (long long)blockIdx.x * cols;
@@ -301,7 +345,7 @@ xent_block_kernel(const T* __restrict__ logits, const T* __restrict__ labels, T*
     const float s = ldf<T>(x + c) - mx;
     const float lab = ldf<T>(l + c);
     acc += lab * (ls - s);
-    stf<T>(bp + c, expf(s) / sum - lab);
+    stf<T>(bp + c, (expf(s) / sum - lab) * sc);
   }
   acc = block_reduce(acc, false, sm);
   if (threadIdx.x == 0) stf<T>(loss + blockIdx.x, acc);
@@ -310,7 +354,10 @@ xent_block_kernel(const T* __restrict__ logits, const T* __restrict__ labels, T*
 template <typename T>
 __global__ void __launch_bounds__(256)
 xent_warp_kernel(const T* __restrict__ logits, const T* __restrict__ labels, T* __restrict__ loss,
-                 T* __restrict__ backprop, long long rows, int cols) {
+                 T* __restrict__ backprop, long long rows, int cols,
+                 const float* __restrict__ bp_scale) {
+  pdl_prologue();
+  const float sc = bp_scale ? __ldg(bp_scale) : 1.0f;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -344,7 +391,7 @@ xent_warp_kernel(const T* __restrict__ logits, const T* __restrict__ labels, T* 
     const int c = lane + 32 * j;
     if (c < cols) {
       acc += lab[j] * (ls - v[j]);
-      stf<T>(bp + c, expf(v[j]) / sum - lab[j]);
+      stf<T>(bp + c, (expf(v[j]) / sum - lab[j]) * sc);
     }
   }
   acc = warp_sum(acc);
@@ -356,7 +403,9 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 xent_warp_vec_kernel(const float* __restrict__ logits, const float* __restrict__ labels,
                      float* __restrict__ loss, float* __restrict__ backprop, long long rows,
-                     int cols) {
+                     int cols, const float* __restrict__ bp_scale) {
+  pdl_prologue();
+  const float sc = bp_scale ? __ldg(bp_scale) : 1.0f;
   const int lane = threadIdx.x & 31;
   for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows;
        row += (long long)gridDim.x * 8) {
@@ -396,10 +445,10 @@ xent_warp_vec_kernel(const float* __restrict__ logits, const float* __restrict__
       acc += lab[j].x * (ls - v[j].x) + lab[j].y * (ls - v[j].y) + lab[j].z * (ls - v[j].z) +
              lab[j].w * (ls - v[j].w);
       float4 o;
-      o.x = expf(v[j].x) / sum - lab[j].x;
-      o.y = expf(v[j].y) / sum - lab[j].y;
-      o.z = expf(v[j].z) / sum - lab[j].z;
-      o.w = expf(v[j].w) / sum - lab[j].w;
+      o.x = (expf(v[j].x) / sum - lab[j].x) * sc;
+      o.y = (expf(v[j].y) / sum - lab[j].y) * sc;
+      o.z = (expf(v[j].z) / sum - lab[j].z) * sc;
+      o.w = (expf(v[j].w) / sum - lab[j].w) * sc;
       bp[i] = o;
     }
   }
@@ -428,6 +477,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 argmax_last_axis_kernel(const T* __restrict__ in, int64_t* __restrict__ out, long long outer,
                         long long axis) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= outer) return;
@@ -459,6 +509,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 argmax_strided_kernel(const T* __restrict__ in, int64_t* __restrict__ out, long long outer,
                       long long axis, long long inner) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= outer * inner) return;
   const long long o = i / inner, k = i - o * inner;
@@ -478,6 +529,7 @@ argmax_strided_kernel(const T* __restrict__ in, int64_t* __restrict__ out, long 
 // ================================================================== deterministic sum
 __global__ void __launch_bounds__(256)
 sum_stage1(const float* __restrict__ in, float* __restrict__ partial, long long n) {
+  pdl_prologue();
   __shared__ float sm[8];
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += 256LL * gridDim.x)
@@ -487,6 +539,7 @@ sum_stage1(const float* __restrict__ in, float* __restrict__ partial, long long 
 }
 __global__ void __launch_bounds__(256)
 sum_stage2(const float* __restrict__ partial, float* __restrict__ out, int n, float scale) {
+  pdl_prologue();
   __shared__ float sm[8];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += 256) acc += partial[i];
@@ -496,6 +549,7 @@ sum_stage2(const float* __restrict__ partial, float* __restrict__ out, int n, fl
 // single CTA variant when n is small: no scratch needed
 __global__ void __launch_bounds__(256)
 sum_single(const float* __restrict__ in, float* __restrict__ out, long long n, float scale) {
+  pdl_prologue();
   __shared__ float sm[8];
   float acc = 0.f;
   for (long long i = threadIdx.x; i < n; i += 256) acc += in[i];
@@ -518,9 +572,9 @@ static int launch_softmax(const void* logits, void* out, long long rows, int col
 #define SM_LAUNCH(NV)                                                                   \
   do {                                                                                  \
     if (log_sm)                                                                         \
-      softmax_warp_kernel<T, NV, true><<<wgrid, 256, 0, s>>>(x, y, rows, cols);         \
+      launch_pdl(softmax_warp_kernel<T, NV, true>, dim3(wgrid), dim3(256), 0, s, x, y, rows, cols);         \
     else                                                                                \
-      softmax_warp_kernel<T, NV, false><<<wgrid, 256, 0, s>>>(x, y, rows, cols);        \
+      launch_pdl(softmax_warp_kernel<T, NV, false>, dim3(wgrid), dim3(256), 0, s, x, y, rows, cols);        \
   } while (0)
   if (vec && nv <= 8) {
     if (nv <= 1)
@@ -533,9 +587,9 @@ static int launch_softmax(const void* logits, void* out, long long rows, int col
       SM_LAUNCH(8);
   } else {
     if (log_sm)
-      softmax_block_kernel<T, true><<<(unsigned)rows, 256, 0, s>>>(x, y, cols);
+      launch_pdl(softmax_block_kernel<T, true>, dim3((unsigned)rows), dim3(256), 0, s, x, y, cols);
     else
-      softmax_block_kernel<T, false><<<(unsigned)rows, 256, 0, s>>>(x, y, cols);
+      launch_pdl(softmax_block_kernel<T, false>, dim3((unsigned)rows), dim3(256), 0, s, x, y, cols);
   }
 #undef SM_LAUNCH
   note_launch();
@@ -586,27 +640,59 @@ int b200_bias_add_grad(int dtype, const void* out_backprop, void* out, int64_t r
   }
   float* partial = static_cast<float*>(workspace);
   dim3 grid(p.col_tiles, p.nchunks), block(32, 8);
+  static const bool two_kernels = getenv("B200TF_BIAS_GRAD_TWO_KERNELS") != nullptr;
+  if (!two_kernels && p.col_tiles <= kBiasGradMaxTiles) {
+    // Ticket counters: one row of a small ring per launch, so launches in flight on different
+    // streams never share counters unless more than kBiasGradSlots of them overlap.
+    static std::atomic<unsigned> next_slot{0};
+    unsigned int* base = nullptr;
+    if (cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_bias_grad_tickets) != cudaSuccess)
+      return check_launch("b200_bias_add_grad");
+    unsigned int* tickets =
+        base + (size_t)(next_slot.fetch_add(1) % kBiasGradSlots) * kBiasGradMaxTiles;
+    if (dtype == B200_DT_FLOAT) {
+      const float* gp = static_cast<const float*>(out_backprop);
+      float* op = static_cast<float*>(out);
+      if (p.vec == 4)
+        launch_pdl(bias_grad_stage1<float, 4>, dim3(grid), dim3(block), 0, s, gp, partial, rows, (int)channels,
+                                                          p.rows_per_chunk, op, tickets);
+      else
+        launch_pdl(bias_grad_stage1<float, 1>, dim3(grid), dim3(block), 0, s, gp, partial, rows, (int)channels,
+                                                          p.rows_per_chunk, op, tickets);
+    } else {
+      const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(out_backprop);
+      __nv_bfloat16* op = static_cast<__nv_bfloat16*>(out);
+      if (p.vec == 8)
+        launch_pdl(bias_grad_stage1<__nv_bfloat16, 8>, dim3(grid), dim3(block), 0, s, gp, partial, rows, (int)channels,
+                                                                  p.rows_per_chunk, op, tickets);
+      else
+        launch_pdl(bias_grad_stage1<__nv_bfloat16, 1>, dim3(grid), dim3(block), 0, s, gp, partial, rows, (int)channels,
+                                                                  p.rows_per_chunk, op, tickets);
+    }
+    note_launch(1);
+    return check_launch("b200_bias_add_grad");
+  }
   if (dtype == B200_DT_FLOAT) {
     if (p.vec == 4)
-      bias_grad_stage1<float, 4><<<grid, block, 0, s>>>(static_cast<const float*>(out_backprop),
+      launch_pdl(bias_grad_stage1<float, 4>, dim3(grid), dim3(block), 0, s, static_cast<const float*>(out_backprop),
                                                         partial, rows, (int)channels,
-                                                        p.rows_per_chunk);
+                                                        p.rows_per_chunk, nullptr, nullptr);
     else
-      bias_grad_stage1<float, 1><<<grid, block, 0, s>>>(static_cast<const float*>(out_backprop),
+      launch_pdl(bias_grad_stage1<float, 1>, dim3(grid), dim3(block), 0, s, static_cast<const float*>(out_backprop),
                                                         partial, rows, (int)channels,
-                                                        p.rows_per_chunk);
-    bias_grad_stage2<float><<<(unsigned)((channels + 31) / 32), block, 0, s>>>(
+                                                        p.rows_per_chunk, nullptr, nullptr);
+    launch_pdl(bias_grad_stage2<float>, dim3((unsigned)((channels + 31) / 32)), dim3(block), 0, s, 
         partial, static_cast<float*>(out), p.nchunks, (int)channels);
   } else {
     if (p.vec == 8)
-      bias_grad_stage1<__nv_bfloat16, 8><<<grid, block, 0, s>>>(
+      launch_pdl(bias_grad_stage1<__nv_bfloat16, 8>, dim3(grid), dim3(block), 0, s, 
           static_cast<const __nv_bfloat16*>(out_backprop), partial, rows, (int)channels,
-          p.rows_per_chunk);
+          p.rows_per_chunk, nullptr, nullptr);
     else
-      bias_grad_stage1<__nv_bfloat16, 1><<<grid, block, 0, s>>>(
+      launch_pdl(bias_grad_stage1<__nv_bfloat16, 1>, dim3(grid), dim3(block), 0, s, 
           static_cast<const __nv_bfloat16*>(out_backprop), partial, rows, (int)channels,
-          p.rows_per_chunk);
-    bias_grad_stage2<__nv_bfloat16><<<(unsigned)((channels + 31) / 32), block, 0, s>>>(
+          p.rows_per_chunk, nullptr, nullptr);
+    launch_pdl(bias_grad_stage2<__nv_bfloat16>, dim3((unsigned)((channels + 31) / 32)), dim3(block), 0, s, 
         partial, static_cast<__nv_bfloat16*>(out), p.nchunks, (int)channels);
   }
   note_launch(2);
@@ -633,6 +719,17 @@ int b200_softmax(int dtype, const void* logits, void* out, int64_t rows, int64_t
 
 int b200_softmax_xent(int dtype, const void* logits, const void* labels, void* loss,
                       void* backprop, int64_t rows, int64_t cols, void* stream) {
+  return b200_softmax_xent_scaled(dtype, logits, labels, loss, backprop, rows, cols, nullptr, stream);
+}
+
+int b200_softmax_xent_scaled(int dtype, const void* logits, const void* labels, void* loss,
+                             void* backprop, int64_t rows, int64_t cols,
+                             const float* backprop_scale, void* stream) {
+  const float* sc = backprop_scale;
+  if (sc != nullptr && dtype != B200_DT_FLOAT) {
+    set_last_error("b200_softmax_xent_scaled: the fused scale is fp32-only");
+    return B200_UNIMPLEMENTED;
+  }
   if (rows < 0 || cols < 0 || cols > INT32_MAX) {
     set_last_error("b200_softmax_xent: bad shape [%lld, %lld]", (long long)rows, (long long)cols);
     return B200_INVALID_ARGUMENT;
@@ -652,31 +749,32 @@ int b200_softmax_xent(int dtype, const void* logits, const void* labels, void* l
     unsigned wg = (unsigned)((rows + 7) / 8);
     if (wg > 8u * (unsigned)sm_count()) wg = 8u * (unsigned)sm_count();
     if (vec && cols <= 128)
-      xent_warp_vec_kernel<1><<<wg, 256, 0, s>>>(xl, ll, lo, bo, rows, (int)cols);
+      launch_pdl(xent_warp_vec_kernel<1>, dim3(wg), dim3(256), 0, s, xl, ll, lo, bo, rows, (int)cols, sc);
     else if (vec && cols <= 256)
-      xent_warp_vec_kernel<2><<<wg, 256, 0, s>>>(xl, ll, lo, bo, rows, (int)cols);
+      launch_pdl(xent_warp_vec_kernel<2>, dim3(wg), dim3(256), 0, s, xl, ll, lo, bo, rows, (int)cols, sc);
     else if (vec && cols <= 512)
-      xent_warp_vec_kernel<4><<<wg, 256, 0, s>>>(xl, ll, lo, bo, rows, (int)cols);
+      launch_pdl(xent_warp_vec_kernel<4>, dim3(wg), dim3(256), 0, s, xl, ll, lo, bo, rows, (int)cols, sc);
     else if (vec)
-      xent_warp_vec_kernel<8><<<wg, 256, 0, s>>>(xl, ll, lo, bo, rows, (int)cols);
+      launch_pdl(xent_warp_vec_kernel<8>, dim3(wg), dim3(256), 0, s, xl, ll, lo, bo, rows, (int)cols, sc);
     else if (cols <= 1024)
-      xent_warp_kernel<float><<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(
+      launch_pdl(xent_warp_kernel<float>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, 
           static_cast<const float*>(logits), static_cast<const float*>(labels),
-          static_cast<float*>(loss), static_cast<float*>(backprop), rows, (int)cols);
+          static_cast<float*>(loss), static_cast<float*>(backprop), rows, (int)cols, sc);
     else
-      xent_block_kernel<float><<<(unsigned)rows, 256, 0, s>>>(
+      launch_pdl(xent_block_kernel<float>, dim3((unsigned)rows), dim3(256), 0, s, 
           static_cast<const float*>(logits), static_cast<const float*>(labels),
-          static_cast<float*>(loss), static_cast<float*>(backprop), (int)cols);
+          static_cast<float*>(loss), static_cast<float*>(backprop), (int)cols, sc);
   } else if (dtype == B200_DT_BFLOAT16) {
     if (cols <= 1024)
-      xent_warp_kernel<__nv_bfloat16><<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(
+      launch_pdl(xent_warp_kernel<__nv_bfloat16>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, 
           static_cast<const __nv_bfloat16*>(logits), static_cast<const __nv_bfloat16*>(labels),
           static_cast<__nv_bfloat16*>(loss), static_cast<__nv_bfloat16*>(backprop), rows,
-          (int)cols);
+          (int)cols, nullptr);
     else
-      xent_block_kernel<__nv_bfloat16><<<(unsigned)rows, 256, 0, s>>>(
+      launch_pdl(xent_block_kernel<__nv_bfloat16>, dim3((unsigned)rows), dim3(256), 0, s, 
           static_cast<const __nv_bfloat16*>(logits), static_cast<const __nv_bfloat16*>(labels),
-          static_cast<__nv_bfloat16*>(loss), static_cast<__nv_bfloat16*>(backprop), (int)cols);
+          static_cast<__nv_bfloat16*>(loss), static_cast<__nv_bfloat16*>(backprop), (int)cols,
+          nullptr);
   } else {
     set_last_error("b200_softmax_xent: unsupported dtype %d", dtype);
     return B200_UNIMPLEMENTED;
@@ -699,10 +797,10 @@ int b200_argmax(int dtype, const void* in, int64_t* out, int64_t outer, int64_t 
 #define ARG_LAUNCH(T)                                                                          \
   do {                                                                                         \
     if (inner == 1 && axis_size >= 64)                                                         \
-      argmax_last_axis_kernel<T><<<(unsigned)((outer + 7) / 8), 256, 0, s>>>(                  \
+      launch_pdl(argmax_last_axis_kernel<T>, dim3((unsigned)((outer + 7) / 8)), dim3(256), 0, s,                   \
           static_cast<const T*>(in), out, outer, axis_size);                                   \
     else                                                                                       \
-      argmax_strided_kernel<T><<<(unsigned)((outer * inner + 255) / 256), 256, 0, s>>>(        \
+      launch_pdl(argmax_strided_kernel<T>, dim3((unsigned)((outer * inner + 255) / 256)), dim3(256), 0, s,         \
           static_cast<const T*>(in), out, outer, axis_size, inner);                            \
   } while (0)
   if (dtype == B200_DT_FLOAT)
@@ -731,7 +829,7 @@ int b200_reduce_sum(int dtype, const void* in, float scale, void* out, int64_t n
   }
   int rc = require_device("b200_reduce_sum");
   if (rc) return rc;
-  sum_single<<<1, 256, 0, as_stream(stream)>>>(static_cast<const float*>(in),
+  launch_pdl(sum_single, dim3(1), dim3(256), 0, as_stream(stream), static_cast<const float*>(in),
                                                 static_cast<float*>(out), n, scale);
   note_launch();
   return check_launch("b200_reduce_sum");

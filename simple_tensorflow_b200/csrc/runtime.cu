@@ -122,6 +122,10 @@ void profile_gemm_launch_begin(cudaStream_t stream) {
   g_prof.pending_start = prof_event();
   cudaEventRecord(g_prof.pending_start, stream);
 }
+bool pdl_enabled() {
+  static const bool on = getenv("B200TF_NO_PDL") == nullptr;
+  return on;
+}
 void profile_gemm_launch_end(cudaStream_t stream, double flops) {
   std::lock_guard<std::mutex> l(g_prof.mu);
   cudaEvent_t e = prof_event();

@@ -312,7 +312,10 @@ Status DirectSession::GetOrCreateExecutors(const std::vector<std::string>& feeds
     ek->fetches.push_back(src);
   }
   ek->node_first_entry = first_entry;
-  if (getenv("B200TF_DISABLE_FUSION") == nullptr) TF_RETURN_IF_ERROR(FuseMatMulChains(ek.get()));
+  if (getenv("B200TF_DISABLE_FUSION") == nullptr) {
+    TF_RETURN_IF_ERROR(FuseMatMulChains(ek.get()));
+    TF_RETURN_IF_ERROR(FuseXentScale(ek.get()));
+  }
   if (!EnvFlagOff("B200TF_GRADIENT_ARENA")) PlanGradientArenas(ek.get());
   *out = ek.get();
   executors_[key] = std::move(ek);
@@ -324,7 +327,7 @@ void DirectSession::PlanGradientArenas(ExecutorsAndKeys* ek) {
   for (size_t p = 0; p < ek->order.size(); ++p) {
     const PlanNode& pn = ek->order[p];
     for (int o = 0; o < pn.item->kernel->num_outputs(); ++o)
-      producer_of[pn.first_entry + o] = {static_cast<int>(p), o};
+      producer_of[pn.out_entry(o)] = {static_cast<int>(p), o};
   }
   for (PlanNode& pn : ek->order) {
     if (pn.item->def.op != "B200AllReduceN" || pn.inputs.size() < 2) continue;
@@ -355,6 +358,72 @@ void DirectSession::PlanGradientArenas(ExecutorsAndKeys* ek) {
       producer.arena_slots[prod.second] = {a, static_cast<int>(i)};
     }
   }
+}
+
+Status DirectSession::FuseXentScale(ExecutorsAndKeys* ek) {
+  for (size_t i = 0; i < ek->order.size(); ++i) {
+    PlanNode& xent = ek->order[i];
+    if (xent.dead || xent.node < 0 || xent.item->def.op != "SoftmaxCrossEntropyWithLogits") continue;
+    if (xent.item->kernel->input_type(0) != DT_FLOAT) continue;  // the fused scale is fp32-only
+    const int backprop = xent.out_entry(1);
+    if (ek->entry_consumers[backprop] != 1 || ek->entry_is_fetch[backprop]) continue;
+    // the one consumer: Mul(backprop, c) with c a one-element Const of the same type
+    int j = -1;
+    for (size_t k = i + 1; k < ek->order.size() && j < 0; ++k) {
+      const PlanNode& c = ek->order[k];
+      if (c.dead) continue;
+      for (const InputSource& in : c.inputs)
+        if (in.feed < 0 && in.id.node == xent.node && in.id.slot == 1) j = static_cast<int>(k);
+    }
+    if (j < 0) continue;
+    PlanNode& mul = ek->order[j];
+    if (mul.node < 0 || mul.item->def.op != "Mul" || mul.inputs.size() != 2) continue;
+    if (!(mul.inputs[0].feed < 0 && mul.inputs[0].id.node == xent.node &&
+          mul.inputs[0].id.slot == 1))
+      continue;
+    const InputSource scale = mul.inputs[1];
+    if (scale.feed >= 0 || scale.id.slot != 0) continue;
+    const NodeItem* cnode = nodes_[scale.id.node].get();
+    auto value = cnode->def.attr.find("value");
+    if (cnode->def.op != "Const" || value == cnode->def.attr.end() ||
+        value->second.tensor.dtype() != DT_FLOAT || value->second.tensor.NumElements() != 1)
+      continue;
+    // the Const must run before the fused node, which takes the xent's place in the order
+    int cpos = -1;
+    for (size_t k = 0; k < ek->order.size(); ++k)
+      if (!ek->order[k].dead && ek->order[k].node == scale.id.node) cpos = static_cast<int>(k);
+    if (cpos < 0) continue;
+
+    std::unique_ptr<NodeItem> fused(new NodeItem);
+    fused->def.name = mul.item->def.name + "/_scaled_xent";
+    fused->def.op = "_ScaledSoftmaxCrossEntropyWithLogits";
+    fused->def.attr["T"] = AttrValue::Type(DT_FLOAT);
+    fused->def.input = {xent.item->def.input[0], xent.item->def.input[1], "<fused>"};
+    TF_RETURN_IF_ERROR(EnsureKernel(fused.get()));
+    PlanNode repl;
+    repl.node = -1;
+    repl.item = fused.get();
+    repl.first_entry = xent.first_entry;
+    repl.output_entries = {xent.out_entry(0), mul.out_entry(0)};  // loss stays, scaled backprop
+    repl.inputs = {xent.inputs[0], xent.inputs[1], scale};
+    ek->entry_consumers[backprop] = 0;  // nobody reads the unscaled backprop any more
+    mul.dead = true;
+    if (cpos > static_cast<int>(i)) {  // hoist the Const (no inputs) in front of the fused node
+      PlanNode c = std::move(ek->order[cpos]);
+      ek->order.erase(ek->order.begin() + cpos);
+      ek->order.insert(ek->order.begin() + i, std::move(c));
+      ek->order[i + 1] = std::move(repl);
+      ++i;
+    } else {
+      ek->order[i] = std::move(repl);
+    }
+    ek->rewritten.push_back(std::move(fused));
+  }
+  std::vector<PlanNode> alive;
+  for (PlanNode& pn : ek->order)
+    if (!pn.dead) alive.push_back(std::move(pn));
+  ek->order.swap(alive);
+  return Status::OK();
 }
 
 Status DirectSession::FuseMatMulChains(ExecutorsAndKeys* ek) {
@@ -640,9 +709,9 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
       }
       for (int o = 0; o < kernel->num_outputs(); ++o) {
         TensorValue v = ctx.release_output(o);
-        Entry& out = entries[pn.first_entry + o];
+        Entry& out = entries[pn.out_entry(o)];
         if (v.tensor == nullptr) {
-          if (ek->entry_consumers[pn.first_entry + o] > 0 || ek->entry_is_fetch[pn.first_entry + o])
+          if (ek->entry_consumers[pn.out_entry(o)] > 0 || ek->entry_is_fetch[pn.out_entry(o)])
             return errors::Internal("Missing ", o, "-th output from ", SummarizeNodeDef(item->def));
           continue;
         }

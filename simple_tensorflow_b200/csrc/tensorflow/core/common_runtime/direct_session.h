@@ -78,6 +78,12 @@ class DirectSession : public Session {
     std::vector<std::pair<int, int>> arena_slots;
     std::vector<InputSource> inputs;
     int first_entry;  // index of output slot 0 in the entry table
+    // A node synthesised from several graph nodes may deliver its outputs to entries that are
+    // not consecutive (empty: output o lives in first_entry + o).
+    std::vector<int> output_entries;
+    int out_entry(int o) const {
+      return output_entries.empty() ? first_entry + o : output_entries[o];
+    }
   };
   // Gradient arena (the job of later TensorFlow's ScopedAllocator): the tensors one
   // B200AllReduceN reduces are produced directly into consecutive 256-byte-aligned windows of
@@ -128,6 +134,10 @@ class DirectSession : public Session {
   // GraphOptimizer-stage rewrite (direct_session.cc:1051 role): MatMul+BiasAdd(+Relu) and
   // MatMul+ReluGrad chains whose intermediates have a single consumer run as one _FusedMatMul.
   Status FuseMatMulChains(ExecutorsAndKeys* ek);
+  // SoftmaxCrossEntropyWithLogits whose backprop output only feeds Mul(backprop, scalar Const)
+  // (the gradient of a mean loss, nn_grad.py:323-333 + math_grad.py _MeanGrad) runs as one
+  // _ScaledSoftmaxCrossEntropyWithLogits: same fp32 roundings, one pass less over [batch, classes].
+  Status FuseXentScale(ExecutorsAndKeys* ek);
   void PlanGradientArenas(ExecutorsAndKeys* ek);
   Status RunPlan(ExecutorsAndKeys* ek, const std::vector<std::pair<std::string, Tensor>>& inputs,
                  std::vector<Tensor>* outputs);

@@ -28,7 +28,7 @@ class SoftmaxOp : public OpKernel {
   bool log_;
 };
 
-template <typename T>
+template <typename T, bool kScaled = false>
 class SoftmaxXentWithLogitsOp : public OpKernel {
  public:
   explicit SoftmaxXentWithLogitsOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
@@ -48,10 +48,17 @@ class SoftmaxXentWithLogitsOp : public OpKernel {
     // declares its operands __restrict__, so the output gets its own buffer)
     OP_REQUIRES_OK(ctx, ctx->allocate_output(1, logits_in.shape(), &back_out));
     if (logits_in.dim_size(0) == 0) return;
-    OP_REQUIRES_OK(ctx, FromAbi(b200_softmax_xent(AbiType<T>::v, logits_in.raw_data(),
-                                                  labels_in.raw_data(), loss_out->raw_data(),
-                                                  back_out->raw_data(), logits_in.dim_size(0),
-                                                  logits_in.dim_size(1), GetCudaStream(ctx)),
+    const float* scale = nullptr;
+    if (kScaled) {
+      OP_REQUIRES(ctx, ctx->input(2).NumElements() == 1,
+                  errors::InvalidArgument("backprop_scale must have one element"));
+      scale = ctx->input(2).template data<float>();
+    }
+    OP_REQUIRES_OK(ctx, FromAbi(b200_softmax_xent_scaled(AbiType<T>::v, logits_in.raw_data(),
+                                                         labels_in.raw_data(), loss_out->raw_data(),
+                                                         back_out->raw_data(), logits_in.dim_size(0),
+                                                         logits_in.dim_size(1), scale,
+                                                         GetCudaStream(ctx)),
                                 "SoftmaxCrossEntropyWithLogits"));
   }
 };
@@ -66,5 +73,10 @@ class SoftmaxXentWithLogitsOp : public OpKernel {
       SoftmaxXentWithLogitsOp<T>);
 REGISTER_B200_FLOAT_TYPES(REGISTER_GPU)
 #undef REGISTER_GPU
+typedef SoftmaxXentWithLogitsOp<float, true> ScaledSoftmaxXentOp;
+REGISTER_KERNEL_BUILDER(Name("_ScaledSoftmaxCrossEntropyWithLogits")
+                            .Device(DEVICE_GPU)
+                            .TypeConstraint<float>("T"),
+                        ScaledSoftmaxXentOp);
 
 }  // namespace tensorflow

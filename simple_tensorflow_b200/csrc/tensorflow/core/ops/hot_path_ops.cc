@@ -68,6 +68,11 @@ REGISTER_OP("SoftmaxCrossEntropyWithLogits")
     .Input("features: T").Input("labels: T").Output("loss: T").Output("backprop: T")
     .Attr("T: {half, float, double, bfloat16}");
 
+// Executor-internal (direct_session.cc FuseXentScale): backprop is multiplied by a scalar.
+REGISTER_OP("_ScaledSoftmaxCrossEntropyWithLogits")
+    .Input("features: T").Input("labels: T").Input("backprop_scale: T")
+    .Output("loss: T").Output("backprop: T").Attr("T: {float}");
+
 REGISTER_OP("MaxPool")
     .Attr("T: {float, half, bfloat16} = DT_FLOAT")
     .Attr("ksize: list(int) >= 4").Attr("strides: list(int) >= 4")

@@ -207,6 +207,37 @@ def test_fusion_rewrite_matches_unfused(oracle, rng, monkeypatch):
         np.testing.assert_allclose(a, b, rtol=1e-4, atol=1e-5)
 
 
+def test_xent_scale_rewrite_is_bit_exact(rng, monkeypatch):
+    # xent -> Mul(backprop, 1/N) (the gradient of a mean loss) runs as one scaled xent kernel:
+    # (softmax - labels) is rounded to fp32 and then multiplied, exactly like the two-op form
+    B, C = 300, 1000
+    logits = rng.uniform(-3, 3, (B, C)).astype(np.float32)
+    labels = np.eye(C, dtype=np.float32)[rng.randint(0, C, B)]
+
+    def run(disable):
+        if disable:
+            monkeypatch.setenv("B200TF_DISABLE_FUSION", "1")
+        else:
+            monkeypatch.delenv("B200TF_DISABLE_FUSION", raising=False)
+        tf.reset_default_graph()
+        xp, lp = tf.placeholder(tf.float32, [B, C]), tf.placeholder(tf.float32, [B, C])
+        h = tf.identity(xp)
+        loss = tf.reduce_mean(tf.softmax_cross_entropy_with_logits(h, lp))
+        (dlogits,) = tf.gradients(loss, [h])
+        with client.Session(tf.get_default_graph()) as sess:
+            out = sess.run([loss, dlogits], {xp: logits, lp: labels})
+            return out, sess.last_run_stats()["nodes_executed"]
+
+    (l0, g0), n0 = run(disable=True)
+    (l1, g1), n1 = run(disable=False)
+    assert n1 == n0 - 1  # the Mul is gone
+    np.testing.assert_array_equal(g0, g1)
+    assert l0 == l1
+    p = np.exp(logits - logits.max(1, keepdims=True))
+    ref = (p / p.sum(1, keepdims=True) - labels) / B
+    np.testing.assert_allclose(g1, ref, rtol=1e-4, atol=1e-7)
+
+
 def test_all_reduce_n_single_replica(rng):
     # without a communicator the op is an identity (times scale): the N>1 path runs in bench.py
     a = rng.randn(1000).astype(np.float32)
