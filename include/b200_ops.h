@@ -41,7 +41,8 @@ enum {
   B200_RESOURCE_EXHAUSTED = 8,
   B200_FAILED_PRECONDITION = 9,
   B200_UNIMPLEMENTED = 12,
-  B200_INTERNAL = 13
+  B200_INTERNAL = 13,
+  B200_UNAVAILABLE = 14
 };
 
 /* tensorflow::DataType subset (framework/types.proto:13-40) */
@@ -262,6 +263,28 @@ B200_API int b200_nccl_all_reduce(int dtype, const void* sendbuf, void* recvbuf,
                                   int average, void* comm, void* stream);
 B200_API int b200_nccl_all_reduce_sum(int dtype, const void* sendbuf, void* recvbuf,
                                       int64_t count, void* comm, void* stream);
+B200_API int b200_nccl_comm_user_rank(void* comm, int* rank);
+/* ncclAllGather of `bytes_per_rank` bytes (device buffers); used to exchange IPC handles. */
+B200_API int b200_nccl_all_gather_bytes(const void* sendbuf, void* recvbuf, int64_t bytes_per_rank,
+                                        void* comm, void* stream);
+
+/* ------------------------------------------------------------------ NVLink peer memory
+ * A peer arena is one device buffer per rank, mapped into every rank of the communicator with
+ * CUDA IPC (one process per GPU).  b200_peer_all_reduce is an in-place fp32 all-reduce over the
+ * same byte range of every rank's arena, done by ONE kernel with peer loads over NVLink: the
+ * gradient exchange of replica data-parallel training (the reference does it with
+ * _Send/_Recv + AddN, core/kernels/aggregate_ops.cc:153-176, common_runtime/gpu/gpu_util.cc:190-250).
+ * Creation is collective over `nccl_comm` (handle exchange) and returns B200_UNAVAILABLE on every
+ * rank when any rank cannot map its peers.  All ranks must issue the same sequence of
+ * b200_peer_all_reduce calls.  max_ctas <= 0: the default grid (64 CTAs of 256 threads, which fit
+ * on SMs next to resident GEMM CTAs). */
+B200_API int b200_peer_arena_create(void* nccl_comm, int rank, int nranks, size_t data_bytes,
+                                    void** arena);
+B200_API int b200_peer_arena_destroy(void* arena);
+B200_API void* b200_peer_arena_data(void* arena);
+B200_API size_t b200_peer_arena_bytes(void* arena);
+B200_API int b200_peer_all_reduce(void* arena, int dtype, size_t offset_bytes, int64_t count,
+                                  int average, int max_ctas, void* stream);
 
 #ifdef __cplusplus
 }

@@ -106,6 +106,13 @@ SIGNATURES = {
     "b200_nccl_group_end": (c_int, []),
     "b200_nccl_all_reduce": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p]),
     "b200_nccl_all_reduce_sum": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "b200_nccl_comm_user_rank": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
+    "b200_nccl_all_gather_bytes": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "b200_peer_arena_create": (c_int, [c_void_p, c_int, c_int, c_size_t, ctypes.POINTER(c_void_p)]),
+    "b200_peer_arena_destroy": (c_int, [c_void_p]),
+    "b200_peer_arena_data": (c_void_p, [c_void_p]),
+    "b200_peer_arena_bytes": (c_size_t, [c_void_p]),
+    "b200_peer_all_reduce": (c_int, [c_void_p, c_int, c_size_t, c_int64, c_int, c_int, c_void_p]),
 }
 
 _lib = None

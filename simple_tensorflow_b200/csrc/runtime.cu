@@ -146,6 +146,8 @@ struct NcclApi {
   int (*CommInitRank)(void**, int, /*ncclUniqueId by value: 128 bytes*/ Id128, int) = nullptr;
   int (*CommDestroy)(void*) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommUserRank)(void*, int*) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
   int (*GroupStart)() = nullptr;
   int (*GroupEnd)() = nullptr;
@@ -168,6 +170,10 @@ static bool load_nccl() {
     g_nccl.AllReduce =
         reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(
             dlsym(h, "ncclAllReduce"));
+    g_nccl.AllGather =
+        reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, cudaStream_t)>(
+            dlsym(h, "ncclAllGather"));
+    g_nccl.CommUserRank = reinterpret_cast<int (*)(void*, int*)>(dlsym(h, "ncclCommUserRank"));
     g_nccl.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
     g_nccl.GroupStart = reinterpret_cast<int (*)()>(dlsym(h, "ncclGroupStart"));
     g_nccl.GroupEnd = reinterpret_cast<int (*)()>(dlsym(h, "ncclGroupEnd"));
@@ -411,6 +417,17 @@ int b200_nccl_all_reduce(int dtype, const void* sendbuf, void* recvbuf, int64_t 
   return nccl_rc(g_nccl.AllReduce(sendbuf, recvbuf, (size_t)count, nccl_type,
                                   average ? /*ncclAvg*/ 4 : /*ncclSum*/ 0, comm, as_stream(stream)),
                  "ncclAllReduce");
+}
+int b200_nccl_comm_user_rank(void* comm, int* rank) {
+  if (!load_nccl() || !g_nccl.CommUserRank) return B200_FAILED_PRECONDITION;
+  return nccl_rc(g_nccl.CommUserRank(comm, rank), "ncclCommUserRank");
+}
+int b200_nccl_all_gather_bytes(const void* sendbuf, void* recvbuf, int64_t bytes_per_rank,
+                               void* comm, void* stream) {
+  if (!load_nccl() || !g_nccl.AllGather) return B200_FAILED_PRECONDITION;
+  return nccl_rc(g_nccl.AllGather(sendbuf, recvbuf, (size_t)bytes_per_rank, /*ncclInt8*/ 0, comm,
+                                  as_stream(stream)),
+                 "ncclAllGather");
 }
 int b200_nccl_all_reduce_sum(int dtype, const void* sendbuf, void* recvbuf, int64_t count,
                              void* comm, void* stream) {

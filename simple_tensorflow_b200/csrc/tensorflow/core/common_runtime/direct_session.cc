@@ -330,7 +330,7 @@ void DirectSession::PlanGradientArenas(ExecutorsAndKeys* ek) {
       producer_of[pn.out_entry(o)] = {static_cast<int>(p), o};
   }
   for (PlanNode& pn : ek->order) {
-    if (pn.item->def.op != "B200AllReduceN" || pn.inputs.size() < 2) continue;
+    if (pn.item->def.op != "B200AllReduceN") continue;
     bool eligible = true;
     for (const InputSource& src : pn.inputs) {
       if (src.feed >= 0) {
@@ -563,6 +563,7 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
     }
   }
   std::vector<Tensor> arena_root(ek->arenas.size());  // this step's gradient arenas
+  device_->ResetPeerArena();
   std::vector<Tensor> preallocated;
   std::vector<Entry> entries(ek->num_entries);
   std::vector<int> pending(ek->entry_consumers);
@@ -644,9 +645,19 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
         if (a < 0 || !ek->arenas[a].learned) continue;
         const GradientArena& ga = ek->arenas[a];
         const size_t esize = DataTypeSize(ga.dtype);
-        if (arena_root[a].buffer() == nullptr)
-          arena_root[a] = Tensor(device_allocator, ga.dtype,
-                                 TensorShape({static_cast<int64>(ga.total / esize)}));
+        if (arena_root[a].buffer() == nullptr) {
+          // replicas: carve the arena from the NVLink peer arena, so that its all-reduce is one
+          // kernel of peer loads (b200_peer_all_reduce); otherwise (or when it is full) the BFC arena
+          void* peer = ga.dtype == DT_FLOAT ? device_->AllocatePeerArena(ga.total) : nullptr;
+          if (peer != nullptr) {
+            TensorBuffer* wrap = new TensorBuffer(peer, ga.total);  // not owned
+            arena_root[a] = Tensor(ga.dtype, TensorShape({static_cast<int64>(ga.total / esize)}), wrap);
+            wrap->Unref();
+          } else {
+            arena_root[a] = Tensor(device_allocator, ga.dtype,
+                                   TensorShape({static_cast<int64>(ga.total / esize)}));
+          }
+        }
         if (arena_root[a].buffer() == nullptr || ga.bytes[pos] == 0) continue;
         TensorBuffer* window = new TensorBuffer(arena_root[a].buffer(), ga.offsets[pos], ga.bytes[pos]);
         preallocated[o] = Tensor(ga.dtype, TensorShape({static_cast<int64>(ga.bytes[pos] / esize)}),

@@ -43,7 +43,42 @@ void GPUDeviceContext::CopyDeviceTensorToCPU(const Tensor* device_tensor, const 
 BaseGPUDevice::BaseGPUDevice(int gpu_id, const std::string& name)
     : Device(name, DEVICE_GPU), gpu_id_(gpu_id) {}
 
+void BaseGPUDevice::set_collective_comm(void* comm, int num_replicas) {
+  collective_comm_ = comm;
+  num_replicas_ = num_replicas;
+  const char* off = getenv("B200TF_PEER_ALLREDUCE");
+  if (comm == nullptr || num_replicas < 2 || (off != nullptr && std::strcmp(off, "0") == 0)) return;
+  b200_set_device(gpu_id_);
+  int rank = -1;
+  if (b200_nccl_comm_user_rank(comm, &rank) != 0) return;
+  size_t mb = 64;
+  if (const char* v = getenv("B200TF_PEER_ARENA_MB")) mb = static_cast<size_t>(std::atoll(v));
+  if (b200_peer_arena_create(comm, rank, num_replicas, mb << 20, &peer_arena_) != 0)
+    peer_arena_ = nullptr;  // every rank took the same decision (b200_ops.h)
+}
+
+void* BaseGPUDevice::AllocatePeerArena(size_t bytes) {
+  if (peer_arena_ == nullptr) return nullptr;
+  bytes = (bytes + 255) / 256 * 256;
+  if (peer_arena_used_ + bytes > b200_peer_arena_bytes(peer_arena_)) return nullptr;
+  char* p = static_cast<char*>(b200_peer_arena_data(peer_arena_)) + peer_arena_used_;
+  peer_arena_used_ += bytes;
+  return p;
+}
+
+long long BaseGPUDevice::PeerArenaOffset(const void* p) const {
+  if (peer_arena_ == nullptr) return -1;
+  const char* base = static_cast<const char*>(b200_peer_arena_data(peer_arena_));
+  const char* q = static_cast<const char*>(p);
+  if (q < base || q >= base + b200_peer_arena_bytes(peer_arena_)) return -1;
+  return q - base;
+}
+
 BaseGPUDevice::~BaseGPUDevice() {
+  if (peer_arena_) {
+    b200_set_device(gpu_id_);
+    b200_peer_arena_destroy(peer_arena_);
+  }
   if (h2d_stream_) h2d_stream_->BlockHostUntilDone();
   if (collective_stream_) collective_stream_->BlockHostUntilDone();
   if (stream_) stream_->BlockHostUntilDone();

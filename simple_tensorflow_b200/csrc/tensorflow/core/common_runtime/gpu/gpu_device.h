@@ -52,10 +52,16 @@ class BaseGPUDevice : public Device {
 
   // Replica data-parallel: the NCCL communicator this device's B200AllReduce kernels use
   // (created by the host with b200_nccl_comm_init_rank; not owned).
-  void set_collective_comm(void* comm, int num_replicas) {
-    collective_comm_ = comm;
-    num_replicas_ = num_replicas;
-  }
+  // Also maps an NVLink peer arena across the replicas (collective over `comm`; skipped with
+  // B200TF_PEER_ALLREDUCE=0 or when any rank cannot map its peers -> NCCL carries the exchange).
+  void set_collective_comm(void* comm, int num_replicas);
+  // The peer arena: this step's gradient arenas are carved from it front to back.
+  void* peer_arena() const { return peer_arena_; }
+  void ResetPeerArena() { peer_arena_used_ = 0; }
+  // Reserves `bytes` (256-byte aligned) of the peer arena; nullptr when it does not fit.
+  void* AllocatePeerArena(size_t bytes);
+  // Byte offset of `p` inside the peer arena's data region, or -1 when it is not part of it.
+  long long PeerArenaOffset(const void* p) const;
   void* collective_comm() const { return collective_comm_; }
   int num_replicas() const { return num_replicas_; }
 
@@ -85,6 +91,8 @@ class BaseGPUDevice : public Device {
   GpuDeviceInfo gpu_device_info_;
   void* collective_comm_ = nullptr;
   int num_replicas_ = 1;
+  void* peer_arena_ = nullptr;
+  size_t peer_arena_used_ = 0;
 };
 
 }  // namespace tensorflow

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <type_traits>
 
 #include "tensorflow/core/common_runtime/device.h"
 #include "tensorflow/core/common_runtime/gpu/gpu_device.h"
@@ -377,7 +378,7 @@ class B200AllReduceNOp : public OpKernel {
                                                                 &outs[i]));
     // Inputs produced into one gradient arena (direct_session.cc PlanGradientArenas): consecutive
     // 256-byte-aligned windows of one root buffer -> ONE in-place collective, no copies.
-    bool contiguous = collective && n > 1 && ctx->input(0).buffer() != nullptr;
+    bool contiguous = collective && ctx->input(0).buffer() != nullptr;
     size_t span = 0;
     for (int i = 0; contiguous && i < n; ++i) {
       const Tensor& t = ctx->input(i);
@@ -394,9 +395,23 @@ class B200AllReduceNOp : public OpKernel {
     if (contiguous) {
       void* base = ctx->input(0).raw_data();
       const int64 total = static_cast<int64>(span / sizeof(T));  // padding included: inside the arena
-      OP_REQUIRES_OK(ctx, FromAbi(b200_nccl_all_reduce(AbiType<T>::v, base, base, total, average,
-                                                       dev->collective_comm(), stream),
-                                  "ncclAllReduce"));
+      const long long peer_offset = dev->PeerArenaOffset(base);
+      if (peer_offset >= 0 && average && std::is_same<T, float>::value) {
+        // the arena lives in NVLink peer memory: one kernel of peer loads instead of NCCL (its
+        // CTAs fit beside resident GEMM CTAs, so it also runs well on the collective stream)
+        static const int ctas = [] {
+          const char* v = getenv("B200TF_PEER_CTAS");
+          return v ? std::atoi(v) : 0;
+        }();
+        OP_REQUIRES_OK(ctx, FromAbi(b200_peer_all_reduce(dev->peer_arena(), AbiType<T>::v,
+                                                         static_cast<size_t>(peer_offset), total, 1,
+                                                         ctas, stream),
+                                    "b200_peer_all_reduce"));
+      } else {
+        OP_REQUIRES_OK(ctx, FromAbi(b200_nccl_all_reduce(AbiType<T>::v, base, base, total, average,
+                                                         dev->collective_comm(), stream),
+                                    "ncclAllReduce"));
+      }
       for (int i = 0; i < n; ++i)  // an input that could not be forwarded gets its copy
         if (outs[i]->raw_data() != ctx->input(i).raw_data())
           OP_REQUIRES_OK(ctx, FromAbi(b200_memcpy_d2d_async(outs[i]->raw_data(),

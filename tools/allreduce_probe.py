@@ -57,6 +57,45 @@ def main():
                      "busbw_gbs": 2.0 * (world - 1) / world * nbytes / (us * 1e-6) / 1e9})
         if rank == 0:
             print("%10d B  %8.1f us  busbw %7.1f GB/s" % (nbytes, us, rows[-1]["busbw_gbs"]), flush=True)
+    # ---- the NVLink peer-memory kernel (b200_peer_all_reduce), several grid sizes
+    arena = ctypes.c_void_p()
+    rc = L.b200_peer_arena_create(comm, rank, world, 64 << 20, ctypes.byref(arena))
+    if rc != 0:
+        if rank == 0:
+            print("peer arena unavailable:", L.b200_last_error().decode(), flush=True)
+    else:
+        data = L.b200_peer_arena_data(arena)
+        for ctas in (32, 64, 128, 256):
+            for nbytes in (4 << 10, 4 << 20, 12599296):
+                n = nbytes // 4
+                ones = torch.ones(n, device="cuda", dtype=torch.float32)
+                _lib.check(L.b200_memcpy_d2d_async(data, ones.data_ptr(), nbytes, stream))
+
+                def once_peer():
+                    _lib.check(L.b200_peer_all_reduce(arena, _lib.DT_FLOAT, 0, n, 1, ctas, stream))
+                for _ in range(5):
+                    once_peer()
+                _lib.check(L.b200_stream_synchronize(stream))
+                dist.barrier()
+                _lib.check(L.b200_event_record(e0, stream))
+                for _ in range(50):
+                    once_peer()
+                _lib.check(L.b200_event_record(e1, stream))
+                _lib.check(L.b200_stream_synchronize(stream))
+                ms = ctypes.c_float()
+                _lib.check(L.b200_event_elapsed_ms(e0, e1, ctypes.byref(ms)))
+                us = replica.max_over_ranks(ms.value * 1e3 / 50)
+                back = torch.empty(4, device="cuda", dtype=torch.float32)
+                _lib.check(L.b200_memcpy_d2d_async(back.data_ptr(), data, 16, stream))
+                _lib.check(L.b200_stream_synchronize(stream))
+                assert abs(float(back[0].item()) - 1.0) < 1e-6, back
+                rows.append({"bytes": nbytes, "us": us, "peer_kernel_ctas": ctas or "all",
+                             "busbw_gbs": 2.0 * (world - 1) / world * nbytes / (us * 1e-6) / 1e9})
+                if rank == 0:
+                    print("%10d B  %8.1f us  busbw %7.1f GB/s  (peer kernel, ctas=%s)"
+                          % (nbytes, us, rows[-1]["busbw_gbs"], ctas or "all"), flush=True)
+        dist.barrier()
+        _lib.check(L.b200_peer_arena_destroy(arena))
     # ---- same sizes on NCCL symmetric windows (ncclMemAlloc + ncclCommWindowRegister, 2.27+)
     try:
         nccl = ctypes.CDLL("libnccl.so.2")
