@@ -232,6 +232,12 @@ B200_API int b200_conv2d_backprop_filter(int dtype, const void* input, const voi
  * DEVICE scalar of the same dtype, as in the reference's GPU functor (training_ops_gpu.cu.cc). */
 B200_API int b200_apply_gradient_descent(int dtype, void* var, const void* alpha,
                                          const void* delta, int64_t n, void* stream);
+/* The same update for `count` variables in one launch (host arrays of device pointers / element
+ * counts).  Element-wise identical to `count` calls of b200_apply_gradient_descent. */
+B200_API int b200_apply_gradient_descent_multi(int dtype, int count, void* const* vars_host,
+                                               const void* const* alphas_host,
+                                               const void* const* deltas_host,
+                                               const int64_t* n_host, void* stream);
 /* Mul (core/kernels/cwise_op_mul_1.cc) for the two shapes gradient graphs need: same-shape, or
  * y a DEVICE scalar broadcast over x (y_is_scalar != 0). */
 B200_API int b200_mul(int dtype, const void* x, const void* y, void* out, int64_t n,

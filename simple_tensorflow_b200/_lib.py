@@ -95,6 +95,8 @@ SIGNATURES = {
                                             c_void_p]),
     "b200_apply_gradient_descent": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64,
                                             c_void_p]),
+    "b200_apply_gradient_descent_multi": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                                  c_void_p, c_void_p]),
     "b200_mul": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "b200_add_n": (c_int, [c_int, ctypes.POINTER(c_void_p), c_int, c_void_p, c_int64, c_void_p]),
     "b200_scale": (c_int, [c_int, c_void_p, c_float, c_void_p, c_int64, c_void_p]),

@@ -344,6 +344,85 @@ static int bad_n(const char* what, long long n) {
   return B200_INVALID_ARGUMENT;
 }
 
+// ApplyGradientDescent for up to kMultiMax variables in ONE launch (blockIdx.y = variable): the
+// per-element arithmetic is SgdF, i.e. bit-identical to one b200_apply_gradient_descent per variable.
+constexpr int kMultiMax = 16;
+template <typename T>
+struct MultiSgdArgs {
+  T* var[kMultiMax];
+  const T* alpha[kMultiMax];
+  const T* delta[kMultiMax];
+  long long n[kMultiMax];
+  int vec[kMultiMax];
+};
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+multi_sgd_kernel(const __grid_constant__ MultiSgdArgs<T> a) {
+  pdl_prologue();
+  constexpr int N = Lanes<T>::kN;
+  const int t = blockIdx.y;
+  T* var = a.var[t];
+  const T* delta = a.delta[t];
+  const long long n = a.n[t];
+  const SgdF<T> f{a.alpha[t]};
+  const long long nvec = a.vec[t] ? n / N : 0;
+  for (long long base = ((long long)blockIdx.x * kThreads * kUnroll) + threadIdx.x; base < nvec;
+       base += (long long)gridDim.x * kThreads * kUnroll) {
+    uint4 va[kUnroll], vb[kUnroll];
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = base + (long long)u * kThreads;
+      if (i < nvec) {
+        va[u] = ld16_rw(var + i * N);
+        vb[u] = ld16_rw(delta + i * N);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const long long i = base + (long long)u * kThreads;
+      if (i < nvec) {
+        float x[N], y[N], r[N];
+        Lanes<T>::unpack(va[u], x);
+        Lanes<T>::unpack(vb[u], y);
+#pragma unroll
+        for (int j = 0; j < N; ++j) r[j] = f(x[j], y[j]);
+        st16(var + i * N, Lanes<T>::pack(r));
+      }
+    }
+  }
+  for (long long i = nvec * N + (long long)blockIdx.x * kThreads + threadIdx.x; i < n;
+       i += (long long)gridDim.x * kThreads)
+    Lanes<T>::store1(var + i, f(Lanes<T>::load1(var + i), Lanes<T>::load1(delta + i)));
+}
+template <typename T>
+static int launch_multi_sgd(int count, void* const* vars, const void* const* alphas,
+                            const void* const* deltas, const int64_t* ns, cudaStream_t stream) {
+  constexpr int N = Lanes<T>::kN;
+  for (int first = 0; first < count; first += kMultiMax) {
+    MultiSgdArgs<T> a{};
+    const int m = count - first < kMultiMax ? count - first : kMultiMax;
+    long long max_units = 1;
+    int used = 0;
+    for (int i = 0; i < m; ++i) {
+      const int64_t n = ns[first + i];
+      if (n == 0) continue;
+      a.var[used] = static_cast<T*>(vars[first + i]);
+      a.alpha[used] = static_cast<const T*>(alphas[first + i]);
+      a.delta[used] = static_cast<const T*>(deltas[first + i]);
+      a.n[used] = n;
+      a.vec[used] = aligned16(vars[first + i]) && aligned16(deltas[first + i]);
+      const long long units = a.vec[used] ? n / N : n;
+      if (units > max_units) max_units = units;
+      ++used;
+    }
+    if (used == 0) continue;
+    launch_pdl(multi_sgd_kernel<T>, dim3(persistent_blocks(max_units, kThreads * kUnroll), used),
+               dim3(kThreads), 0, stream, a);
+    note_launch();
+  }
+  return check_launch("b200_apply_gradient_descent_multi");
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -440,6 +519,25 @@ int b200_apply_gradient_descent(int dtype, void* var, const void* alpha, const v
         "b200_apply_gradient_descent", var, delta, var, n,
         SgdF<__nv_bfloat16>{static_cast<const __nv_bfloat16*>(alpha)}, as_stream(stream));
   return bad_dtype("b200_apply_gradient_descent", dtype);
+}
+
+int b200_apply_gradient_descent_multi(int dtype, int count, void* const* vars_host,
+                                      const void* const* alphas_host,
+                                      const void* const* deltas_host, const int64_t* n_host,
+                                      void* stream) {
+  if (count < 0) return bad_n("b200_apply_gradient_descent_multi", count);
+  for (int i = 0; i < count; ++i)
+    if (n_host[i] < 0) return bad_n("b200_apply_gradient_descent_multi", n_host[i]);
+  if (count == 0) return B200_OK;
+  int rc = require_device("b200_apply_gradient_descent_multi");
+  if (rc) return rc;
+  if (dtype == B200_DT_FLOAT)
+    return launch_multi_sgd<float>(count, vars_host, alphas_host, deltas_host, n_host,
+                                   as_stream(stream));
+  if (dtype == B200_DT_BFLOAT16)
+    return launch_multi_sgd<__nv_bfloat16>(count, vars_host, alphas_host, deltas_host, n_host,
+                                           as_stream(stream));
+  return bad_dtype("b200_apply_gradient_descent_multi", dtype);
 }
 
 int b200_add_n(int dtype, const void* const* inputs_host, int n_inputs, void* out, int64_t n,

@@ -315,6 +315,7 @@ Status DirectSession::GetOrCreateExecutors(const std::vector<std::string>& feeds
   if (getenv("B200TF_DISABLE_FUSION") == nullptr) {
     TF_RETURN_IF_ERROR(FuseMatMulChains(ek.get()));
     TF_RETURN_IF_ERROR(FuseXentScale(ek.get()));
+    TF_RETURN_IF_ERROR(FuseApplyGradientDescent(ek.get()));
   }
   if (!EnvFlagOff("B200TF_GRADIENT_ARENA")) PlanGradientArenas(ek.get());
   *out = ek.get();
@@ -358,6 +359,63 @@ void DirectSession::PlanGradientArenas(ExecutorsAndKeys* ek) {
       producer.arena_slots[prod.second] = {a, static_cast<int>(i)};
     }
   }
+}
+
+Status DirectSession::FuseApplyGradientDescent(ExecutorsAndKeys* ek) {
+  size_t i = 0;
+  while (i < ek->order.size()) {
+    // a run: ApplyGradientDescent / Const nodes only, all updates of one dtype
+    std::vector<size_t> updates;
+    DataType dt = DT_INVALID;
+    size_t j = i;
+    for (; j < ek->order.size(); ++j) {
+      const PlanNode& pn = ek->order[j];
+      if (pn.node < 0) break;
+      if (pn.item->def.op == "Const") continue;
+      if (pn.item->def.op != "ApplyGradientDescent") break;
+      const DataType t = pn.item->kernel->input_type(1);
+      if ((t != DT_FLOAT && t != DT_BFLOAT16) || (dt != DT_INVALID && t != dt)) break;
+      bool fed = false;
+      for (const InputSource& in : pn.inputs) fed = fed || in.feed >= 0;
+      if (fed) break;
+      dt = t;
+      updates.push_back(j);
+    }
+    if (updates.size() < 2) {
+      i = j + 1;
+      continue;
+    }
+    const int n = static_cast<int>(updates.size());
+    std::unique_ptr<NodeItem> fused(new NodeItem);
+    fused->def.name = ek->order[updates.back()].item->def.name + "/_multi_apply";
+    fused->def.op = "_MultiApplyGradientDescent";
+    fused->def.attr["T"] = AttrValue::Type(dt);
+    fused->def.attr["N"] = AttrValue::I(n);
+    PlanNode repl;
+    repl.node = -1;
+    repl.first_entry = ek->order[updates.front()].first_entry;
+    repl.inputs.resize(3 * n);
+    fused->def.input.resize(3 * n);
+    for (int k = 0; k < n; ++k) {
+      const PlanNode& u = ek->order[updates[k]];
+      for (int a = 0; a < 3; ++a) {
+        repl.inputs[a * n + k] = u.inputs[a];
+        fused->def.input[a * n + k] = u.item->def.input[a];
+      }
+      repl.output_entries.push_back(u.out_entry(0));
+    }
+    TF_RETURN_IF_ERROR(EnsureKernel(fused.get()));
+    repl.item = fused.get();
+    for (int k = 0; k + 1 < n; ++k) ek->order[updates[k]].dead = true;
+    ek->order[updates.back()] = std::move(repl);  // every delta and alpha precedes the last update
+    ek->rewritten.push_back(std::move(fused));
+    i = j + 1;
+  }
+  std::vector<PlanNode> alive;
+  for (PlanNode& pn : ek->order)
+    if (!pn.dead) alive.push_back(std::move(pn));
+  ek->order.swap(alive);
+  return Status::OK();
 }
 
 Status DirectSession::FuseXentScale(ExecutorsAndKeys* ek) {

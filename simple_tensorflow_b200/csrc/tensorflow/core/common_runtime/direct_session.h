@@ -138,6 +138,9 @@ class DirectSession : public Session {
   // (the gradient of a mean loss, nn_grad.py:323-333 + math_grad.py _MeanGrad) runs as one
   // _ScaledSoftmaxCrossEntropyWithLogits: same fp32 roundings, one pass less over [batch, classes].
   Status FuseXentScale(ExecutorsAndKeys* ek);
+  // Runs of ApplyGradientDescent nodes separated only by Const nodes (what an optimizer emits)
+  // become one _MultiApplyGradientDescent: one launch instead of one per variable.
+  Status FuseApplyGradientDescent(ExecutorsAndKeys* ek);
   void PlanGradientArenas(ExecutorsAndKeys* ek);
   Status RunPlan(ExecutorsAndKeys* ek, const std::vector<std::pair<std::string, Tensor>>& inputs,
                  std::vector<Tensor>* outputs);

@@ -312,6 +312,50 @@ class ApplyGradientDescentOp : public OpKernel {
   }
 };
 
+// N ApplyGradientDescent nodes that sit next to each other in the plan, run as one launch
+// (direct_session.cc FuseApplyGradientDescent).  Same checks and arithmetic per variable.
+template <typename T>
+class MultiApplyGradientDescentOp : public OpKernel {
+ public:
+  explicit MultiApplyGradientDescentOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+    OP_REQUIRES_OK(ctx, ctx->GetAttr("N", &n_));
+  }
+  void Compute(OpKernelContext* ctx) override {
+    const int n = static_cast<int>(n_);
+    std::vector<void*> vars(n);
+    std::vector<const void*> alphas(n), deltas(n);
+    std::vector<int64_t> counts(n);
+    for (int i = 0; i < n; ++i) {
+      Tensor var = ctx->mutable_input(i, false);
+      OP_REQUIRES(ctx, var.IsInitialized() && var.NumElements() > 0,
+                  errors::FailedPrecondition("Attempting to use uninitialized variables: ",
+                                             def().input.size() > static_cast<size_t>(i)
+                                                 ? def().input[i]
+                                                 : name()));
+      const Tensor& alpha = ctx->input(n + i);
+      OP_REQUIRES(ctx, TensorShapeUtils::IsScalar(alpha.shape()),
+                  errors::InvalidArgument("alpha is not a scalar: ", alpha.shape().DebugString()));
+      const Tensor& delta = ctx->input(2 * n + i);
+      OP_REQUIRES(ctx, var.shape().IsSameSize(delta.shape()),
+                  errors::InvalidArgument("var and delta do not have the same shape",
+                                          var.shape().DebugString(), " ",
+                                          delta.shape().DebugString()));
+      vars[i] = var.raw_data();
+      alphas[i] = alpha.raw_data();
+      deltas[i] = delta.raw_data();
+      counts[i] = var.NumElements();
+    }
+    OP_REQUIRES_OK(ctx, FromAbi(b200_apply_gradient_descent_multi(AbiType<T>::v, n, vars.data(),
+                                                                  alphas.data(), deltas.data(),
+                                                                  counts.data(), GetCudaStream(ctx)),
+                                "ApplyGradientDescent"));
+    for (int i = 0; i < n; ++i) ctx->forward_ref_input_to_ref_output(i, i);
+  }
+
+ private:
+  int64 n_;
+};
+
 // ---------------------------------------------------------------- B200AllReduce (additive)
 // One ncclAllReduce(sum) on the compute stream over the referenced buffer, in place, followed by
 // an optional scale (1/replicas for a gradient average).  No host synchronisation.
@@ -481,6 +525,9 @@ class B200AllReduceNOp : public OpKernel {
   REGISTER_KERNEL_BUILDER(Name("Mul").Device(DEVICE_GPU).TypeConstraint<T>("T"), MulOp<T>);      \
   REGISTER_KERNEL_BUILDER(Name("ApplyGradientDescent").Device(DEVICE_GPU).TypeConstraint<T>("T"),\
                           ApplyGradientDescentOp<T>);                                            \
+  REGISTER_KERNEL_BUILDER(                                                                       \
+      Name("_MultiApplyGradientDescent").Device(DEVICE_GPU).TypeConstraint<T>("T"),              \
+      MultiApplyGradientDescentOp<T>);                                                           \
   REGISTER_KERNEL_BUILDER(Name("B200AllReduce").Device(DEVICE_GPU).TypeConstraint<T>("T"),       \
                           B200AllReduceOp<T>);
 REGISTER_B200_FLOAT_TYPES(REGISTER_GPU)

@@ -107,6 +107,11 @@ REGISTER_OP("ApplyGradientDescent")
     .Input("var: Ref(T)").Input("alpha: T").Input("delta: T").Output("out: Ref(T)")
     .Attr("T: numbertype").Attr("use_locking: bool = false");
 
+// Executor-internal (direct_session.cc FuseApplyGradientDescent): N updates, one launch.
+REGISTER_OP("_MultiApplyGradientDescent")
+    .Input("var: N * Ref(T)").Input("alpha: N * T").Input("delta: N * T")
+    .Output("out: N * Ref(T)").Attr("N: int >= 1").Attr("T: {float, bfloat16}");
+
 REGISTER_OP("VariableV2")
     .Output("ref: Ref(dtype)").Attr("shape: shape").Attr("dtype: type")
     .Attr("container: string = ''").Attr("shared_name: string = ''").SetIsStateful();
