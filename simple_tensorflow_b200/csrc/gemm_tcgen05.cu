@@ -21,6 +21,7 @@
 
 #include <cuda_bf16.h>
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -91,7 +92,17 @@ struct GemmShape {
   int ld_features;       // leading dimension of features (elements)
   int feat_tma;          // 1: features are fetched by TMA through tmapF (prefetched, coalesced)
   int bias_vec;          // 1: bias pointer is 16-byte aligned (vector loads)
+  // B200TF_GEMM_TRACE=1 (debug): %globaltimer at the phase boundaries of the first CTA
+  // (slots 0-8) and entry / exit of the last CTA (slots 9, 10)
+  unsigned long long* trace;
 };
+__device__ __forceinline__ void trace_mark(const GemmShape& s, int slot, bool last_cta = false) {
+  if (s.trace != nullptr && blockIdx.x == (last_cta ? gridDim.x - 1 : 0)) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    s.trace[slot] = t;
+  }
+}
 
 __device__ __forceinline__ bool partial_out_tile(const GemmShape& s) { return s.splits > 1; }
 
@@ -158,6 +169,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
                     const __grid_constant__ CUtensorMap tmapF, TOut* __restrict__ C,
                     GemmShape s) {
   pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    trace_mark(s, 0);
+    trace_mark(s, 9, true);
+  }
   using Tr = GemmTraits<TIn>;
   constexpr int BK = Tr::kBK;
   constexpr int kStages = gemm_stages<BN, kCtas>();
@@ -235,7 +250,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
   const uint32_t tmem_base = *tmem_slot;
   // Everything above overlapped the previous kernel's tail (programmatic dependent launch);
   // from here on this grid reads and writes global memory.
+  if (threadIdx.x == 0) trace_mark(s, 1);
   pdl_wait();
+  if (threadIdx.x == 0) trace_mark(s, 2);
 
   if (warp == 0) {
     // ===================== TMA producer (one per CTA) =====================
@@ -361,6 +378,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
+          if (kb == kb0 && work == unit) trace_mark(s, 3);
           const uint32_t a_addr = smem_u32(smA + stage * kABytes);
           const uint32_t b_addr = smem_u32(smB + stage * kBBytes);
 #pragma unroll
@@ -402,6 +420,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
           }
         }
         // accumulator ready for the epilogue warps (of both CTAs)
+        if (work == unit) trace_mark(s, 4);
         if (kCtas == 2)
           umma_commit_2cta(&tfull_bar[acc]);
         else
@@ -467,6 +486,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
       }
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
+      if (work == unit && warp == 2 && lane == 0) trace_mark(s, 5);
       const int row = row0 + lane;
       const bool partial_out = s.splits > 1;
       TOut* crow = C + (long long)b * s.strideC + (long long)row * s.ldc;
@@ -644,7 +664,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
         acc_phase ^= 1;
       }
     }
+    if (warp == 2 && lane == 0) trace_mark(s, 6);
     if (s.tma_store && lane == 0) tma_store_wait<0>();  // global writes done before exit
+    if (warp == 2 && lane == 0) trace_mark(s, 7);
   }
 
   tc_fence_before();
@@ -658,6 +680,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
       tmem_dealloc_2cta<kTmemCols>(tmem_base);
     else
       tmem_dealloc<kTmemCols>(tmem_base);
+  }
+  if (threadIdx.x == 0) {
+    trace_mark(s, 8);
+    trace_mark(s, 10, true);
   }
 }
 
@@ -918,6 +944,17 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
                                   sizeof(TOut), const_cast<void*>(g.relu_grad_features), g.M, g.N,
                                   g.ld_features, 1, g.M * g.ld_features);
   s.bias_vec = g.bias && (reinterpret_cast<uintptr_t>(g.bias) & 15) == 0;
+  static const bool trace_on = getenv("B200TF_GEMM_TRACE") != nullptr;
+  static unsigned long long* trace_buf = nullptr;
+  s.trace = nullptr;
+  if (trace_on) {
+    if (trace_buf == nullptr) cudaMalloc(&trace_buf, 16 * sizeof(unsigned long long));
+    if (trace_buf != nullptr) {
+      cudaMemsetAsync(trace_buf, 0, 16 * sizeof(unsigned long long), stream);
+      cudaStreamSynchronize(stream);
+      s.trace = trace_buf;
+    }
+  }
   const long long work = tiles * splits;
   const int grid_units = (int)(work < units ? work : units);
   const bool prof = profile_enabled();
@@ -953,6 +990,18 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     }
   }
   if (prof) profile_gemm_launch_end(stream, 2.0 * (double)g.M * (double)g.N * (double)g.K * g.batch);
+  if (s.trace != nullptr) {  // debug: phase boundaries, ns since the first CTA entered the kernel
+    unsigned long long t[16];
+    cudaStreamSynchronize(stream);
+    cudaMemcpy(t, s.trace, sizeof(t), cudaMemcpyDeviceToHost);
+    fprintf(stderr,
+            "[gemm trace] %dx%dx%d BN=%d ctas=%d splits=%d: prologue %llu | pdl_wait %llu | first "
+            "operands %llu | mainloop issued %llu | accumulator ready %llu | epilogue stored %llu | "
+            "stores drained %llu | exit %llu | last CTA entry %lld exit %lld (ns since entry)\n",
+            g.M, g.N, g.K, BN, kCtas, splits, t[1] - t[0], t[2] - t[0], t[3] - t[0], t[4] - t[0],
+            t[5] - t[0], t[6] - t[0], t[7] - t[0], t[8] - t[0], (long long)(t[9] - t[0]),
+            (long long)(t[10] - t[0]));
+  }
   note_launch();
   if (splits > 1) {
     const long long groups = g.batch * g.M * ((g.N + 3) / 4);
