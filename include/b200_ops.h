@@ -242,6 +242,9 @@ B200_API int b200_apply_gradient_descent_multi(int dtype, int count, void* const
  * y a DEVICE scalar broadcast over x (y_is_scalar != 0). */
 B200_API int b200_mul(int dtype, const void* x, const void* y, void* out, int64_t n,
                       int y_is_scalar, void* stream);
+/* Add (core/kernels/cwise_op_add_1.cc), same two shapes. */
+B200_API int b200_add(int dtype, const void* x, const void* y, void* out, int64_t n,
+                      int y_is_scalar, void* stream);
 /* AddN (core/kernels/aggregate_ops.cc:153-176) for n_inputs <= 8. */
 B200_API int b200_add_n(int dtype, const void* const* inputs_host, int n_inputs, void* out,
                         int64_t n, void* stream);

@@ -32,6 +32,10 @@ class TF_Output(ctypes.Structure):
     _fields_ = [("oper", c_void_p), ("index", c_int)]
 
 
+class TF_Buffer(ctypes.Structure):
+    _fields_ = [("data", c_void_p), ("length", c_size_t), ("data_deallocator", c_void_p)]
+
+
 class RunStats(ctypes.Structure):
     _fields_ = [("nodes_executed", c_int64), ("kernels_launched", c_int64),
                 ("h2d_bytes", c_int64), ("d2h_bytes", c_int64),
@@ -71,6 +75,15 @@ _SIGS = {
     "TF_OperationOutputType": (c_int, [TF_Output]),
     "TF_OperationNumInputs": (c_int, [c_void_p]),
     "TF_GraphOperationByName": (c_void_p, [c_void_p, c_char_p]),
+    "TF_GraphNextOperation": (c_void_p, [c_void_p, ctypes.POINTER(c_size_t)]),
+    "TF_NewBufferFromString": (c_void_p, [c_char_p, c_size_t]),
+    "TF_NewBuffer": (c_void_p, []), "TF_DeleteBuffer": (None, [c_void_p]),
+    "TF_GraphToGraphDef": (None, [c_void_p, c_void_p, c_void_p]),
+    "TF_NewImportGraphDefOptions": (c_void_p, []),
+    "TF_DeleteImportGraphDefOptions": (None, [c_void_p]),
+    "TF_ImportGraphDefOptionsSetPrefix": (None, [c_void_p, c_char_p]),
+    "TF_GraphImportGraphDef": (None, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "B200TF_GraphDefToText": (c_void_p, [c_char_p, c_size_t, c_void_p]),
     "TF_NewSession": (c_void_p, [c_void_p, c_void_p, c_void_p]),
     "TF_CloseSession": (None, [c_void_p, c_void_p]),
     "TF_DeleteSession": (None, [c_void_p, c_void_p]),
@@ -334,11 +347,84 @@ class Graph:
         self.operations.append(op)
         return op
 
+    # ---- GraphDef wire format (framework/graph.proto), hand-written codec on the C++ side
+    def as_graph_def(self):
+        """The graph as serialized GraphDef bytes (python/framework/ops.py Graph.as_graph_def +
+        SerializeToString): what a real TensorFlow 1.0 front-end can import."""
+        buf = self.fw.TF_NewBuffer()
+        status = _Status()
+        self.fw.TF_GraphToGraphDef(self.ptr, buf, status.ptr)
+        try:
+            status.check()
+            b = ctypes.cast(buf, ctypes.POINTER(TF_Buffer)).contents
+            return ctypes.string_at(b.data, b.length) if b.length else b""
+        finally:
+            self.fw.TF_DeleteBuffer(buf)
+
+    def import_graph_def(self, graph_def, name=""):
+        """importer.py import_graph_def: add every node of serialized GraphDef bytes to this
+        graph (names prefixed with `name/`), e.g. a graph written by real TensorFlow.  Nodes of
+        op types this runtime does not register import as opaque nodes (see c_api.h).  Returns
+        the new Operations by (prefixed) name."""
+        graph_def = bytes(graph_def)
+        buf = self.fw.TF_NewBufferFromString(graph_def, len(graph_def))
+        opts = self.fw.TF_NewImportGraphDefOptions()
+        status = _Status()
+        try:
+            if name:
+                self.fw.TF_ImportGraphDefOptionsSetPrefix(opts, name.encode())
+            known = len(self.operations)
+            self.fw.TF_GraphImportGraphDef(self.ptr, buf, opts, status.ptr)
+            status.check()
+        finally:
+            self.fw.TF_DeleteImportGraphDefOptions(opts)
+            self.fw.TF_DeleteBuffer(buf)
+        # wrap the operations the C graph gained (they follow the ones this wrapper created)
+        pos = c_size_t(0)
+        seen, new_ops = 0, {}
+        while True:
+            ptr = self.fw.TF_GraphNextOperation(self.ptr, ctypes.byref(pos))
+            if not ptr:
+                break
+            seen += 1
+            if seen <= known:
+                continue
+            op = Operation(self, ptr, [], [], {})
+            self.operations.append(op)
+            self._names[op.name] = self._names.get(op.name, 0) + 1
+            new_ops[op.name] = op
+        return new_ops
+
+    def get_operation_by_name(self, name):
+        for op in self.operations:
+            if op.name == name:
+                return op
+        raise KeyError("no operation named %r" % name)
+
+    def get_tensor_by_name(self, name):
+        op_name, _, idx = name.partition(":")
+        op = self.get_operation_by_name(op_name)
+        return op.outputs[int(idx or 0)]
+
     def __del__(self):
         try:
             self.fw.TF_DeleteGraph(self.ptr)
         except Exception:
             pass
+
+
+def graph_def_to_text(graph_def):
+    """One line per node of serialized GraphDef bytes (name, op, device, inputs, attr summaries):
+    a dump for eyes and tests, produced by the C++ wire reader."""
+    fw = framework()
+    status = _Status()
+    graph_def = bytes(graph_def)
+    p = fw.B200TF_GraphDefToText(graph_def, len(graph_def), status.ptr)
+    status.check()
+    try:
+        return ctypes.string_at(p).decode("utf-8", "replace")
+    finally:
+        ctypes.CDLL(None).free(c_void_p(p))
 
 
 # ------------------------------------------------------------------ session

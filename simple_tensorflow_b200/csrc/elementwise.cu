@@ -179,6 +179,14 @@ struct SgdF {
     return var - Lanes<T>::load1(alpha) * delta;
   }
 };
+struct AddF {
+  __device__ float operator()(float x, float y) const { return x + y; }
+};
+template <typename T>
+struct AddScalarF {
+  const T* y;  // device scalar broadcast over x
+  __device__ float operator()(float x, float) const { return x + Lanes<T>::load1(y); }
+};
 struct MulF {
   __device__ float operator()(float x, float y) const { return x * y; }
 };
@@ -480,6 +488,29 @@ int b200_scale(int dtype, const void* in, float scale, void* out, int64_t n, voi
     return launch_map<__nv_bfloat16, 1>("b200_scale", in, nullptr, out, n, ScaleF{scale},
                                         as_stream(stream));
   return bad_dtype("b200_scale", dtype);
+}
+
+int b200_add(int dtype, const void* x, const void* y, void* out, int64_t n, int y_is_scalar,
+             void* stream) {
+  if (n < 0) return bad_n("b200_add", n);
+  if (n == 0) return B200_OK;
+  int rc = require_device("b200_add");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  if (dtype == B200_DT_FLOAT) {
+    if (y_is_scalar)
+      return launch_map<float, 1>("b200_add", x, nullptr, out, n,
+                                  AddScalarF<float>{static_cast<const float*>(y)}, s);
+    return launch_map<float, 2>("b200_add", x, y, out, n, AddF{}, s);
+  }
+  if (dtype == B200_DT_BFLOAT16) {
+    if (y_is_scalar)
+      return launch_map<__nv_bfloat16, 1>(
+          "b200_add", x, nullptr, out, n,
+          AddScalarF<__nv_bfloat16>{static_cast<const __nv_bfloat16*>(y)}, s);
+    return launch_map<__nv_bfloat16, 2>("b200_add", x, y, out, n, AddF{}, s);
+  }
+  return bad_dtype("b200_add", dtype);
 }
 
 int b200_mul(int dtype, const void* x, const void* y, void* out, int64_t n, int y_is_scalar,

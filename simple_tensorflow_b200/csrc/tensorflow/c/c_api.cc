@@ -1,5 +1,7 @@
 #include "tensorflow/c/c_api.h"
 
+#include "tensorflow/core/framework/graph_def_wire.h"
+
 #include <dlfcn.h>
 
 #include <cstdlib>
@@ -34,6 +36,10 @@ struct TF_SessionOptions {
 struct TF_Operation {
   NodeDef node;
   tensorflow::DataTypeVector input_types, output_types;
+  bool opaque = false;  // imported node of an op type that is not registered here
+};
+struct TF_ImportGraphDefOptions {
+  std::string prefix;
 };
 struct TF_Graph {
   std::mutex mu;
@@ -246,6 +252,8 @@ const char* TF_OperationName(TF_Operation* oper) { return oper->node.name.c_str(
 const char* TF_OperationOpType(TF_Operation* oper) { return oper->node.op.c_str(); }
 int TF_OperationNumOutputs(TF_Operation* oper) { return static_cast<int>(oper->output_types.size()); }
 TF_DataType TF_OperationOutputType(TF_Output o) {
+  if (o.index < 0 || o.index >= static_cast<int>(o.oper->output_types.size()))
+    return static_cast<TF_DataType>(0);  // opaque imported node: types unknown
   return static_cast<TF_DataType>(o.oper->output_types[o.index]);
 }
 int TF_OperationNumInputs(TF_Operation* oper) { return static_cast<int>(oper->input_types.size()); }
@@ -253,6 +261,121 @@ TF_Operation* TF_GraphOperationByName(TF_Graph* graph, const char* oper_name) {
   std::lock_guard<std::mutex> l(graph->mu);
   auto it = graph->by_name.find(oper_name);
   return it == graph->by_name.end() ? nullptr : it->second;
+}
+
+TF_Operation* TF_GraphNextOperation(TF_Graph* graph, size_t* pos) {
+  std::lock_guard<std::mutex> l(graph->mu);
+  if (*pos >= graph->operations.size()) return nullptr;
+  return graph->operations[(*pos)++].get();
+}
+
+// ---------------------------------------------------------------- GraphDef import / export
+TF_Buffer* TF_NewBuffer(void) { return new TF_Buffer{nullptr, 0, nullptr}; }
+TF_Buffer* TF_NewBufferFromString(const void* proto, size_t proto_len) {
+  void* copy = malloc(proto_len ? proto_len : 1);
+  if (proto_len) memcpy(copy, proto, proto_len);
+  return new TF_Buffer{copy, proto_len, [](void* data, size_t) { free(data); }};
+}
+void TF_DeleteBuffer(TF_Buffer* b) {
+  if (b == nullptr) return;
+  if (b->data_deallocator) b->data_deallocator(const_cast<void*>(b->data), b->length);
+  delete b;
+}
+TF_Buffer TF_GetBuffer(TF_Buffer* b) { return *b; }
+
+void TF_GraphToGraphDef(TF_Graph* graph, TF_Buffer* out, TF_Status* status) {
+  tensorflow::GraphDef def;
+  {
+    std::lock_guard<std::mutex> l(graph->mu);
+    for (const auto& op : graph->operations) def.node.push_back(op->node);
+  }
+  def.versions_raw = std::string("\x08\x15", 2);  // VersionDef{ producer = 21 }
+  std::string bytes;
+  tensorflow::SerializeGraphDef(def, &bytes);
+  if (out->data_deallocator) out->data_deallocator(const_cast<void*>(out->data), out->length);
+  void* copy = malloc(bytes.size() ? bytes.size() : 1);
+  memcpy(copy, bytes.data(), bytes.size());
+  out->data = copy;
+  out->length = bytes.size();
+  out->data_deallocator = [](void* data, size_t) { free(data); };
+  status->status = Status::OK();
+}
+
+TF_ImportGraphDefOptions* TF_NewImportGraphDefOptions(void) { return new TF_ImportGraphDefOptions; }
+void TF_DeleteImportGraphDefOptions(TF_ImportGraphDefOptions* o) { delete o; }
+void TF_ImportGraphDefOptionsSetPrefix(TF_ImportGraphDefOptions* o, const char* prefix) {
+  o->prefix = prefix ? prefix : "";
+}
+
+void TF_GraphImportGraphDef(TF_Graph* graph, const TF_Buffer* graph_def,
+                            const TF_ImportGraphDefOptions* options, TF_Status* status) {
+  tensorflow::GraphDef def;
+  status->status = tensorflow::ParseGraphDef(graph_def->data, graph_def->length, &def);
+  if (!status->status.ok()) return;
+  std::string prefix = options ? options->prefix : "";
+  if (!prefix.empty() && prefix.back() != '/') prefix += "/";
+  std::vector<std::unique_ptr<TF_Operation>> added;
+  std::lock_guard<std::mutex> l(graph->mu);
+  std::map<std::string, TF_Operation*> names;
+  for (NodeDef& nd : def.node) {
+    std::unique_ptr<TF_Operation> op(new TF_Operation);
+    op->node = nd;
+    op->node.name = prefix + nd.name;
+    for (std::string& in : op->node.input)  // "node", "node:k", "^node"
+      in = (!in.empty() && in[0] == '^') ? "^" + prefix + in.substr(1) : prefix + in;
+    if (graph->by_name.count(op->node.name) || names.count(op->node.name)) {
+      status->status = tensorflow::errors::InvalidArgument("Duplicate node name in graph: '",
+                                                           op->node.name, "'");
+      return;
+    }
+    const tensorflow::OpDef* op_def = tensorflow::OpRegistry::Global()->LookUp(op->node.op);
+    if (op_def == nullptr) {
+      op->opaque = true;
+    } else {
+      status->status = tensorflow::ValidateNodeDef(&op->node, *op_def);
+      if (status->status.ok())
+        status->status = tensorflow::InOutTypesForNode(op->node, *op_def, &op->input_types,
+                                                       &op->output_types);
+      if (!status->status.ok()) return;
+      size_t data_inputs = 0;
+      for (const auto& in : op->node.input) data_inputs += (in.empty() || in[0] != '^');
+      if (data_inputs != op->input_types.size()) {
+        status->status = tensorflow::errors::InvalidArgument(
+            "Node '", op->node.name, "' of type ", op->node.op, " expects ",
+            op->input_types.size(), " inputs but has ", data_inputs);
+        return;
+      }
+    }
+    names[op->node.name] = op.get();
+    added.push_back(std::move(op));
+  }
+  // every input must name a node of the graph (graph_constructor.cc's edge check)
+  for (const auto& op : added)
+    for (const std::string& in : op->node.input) {
+      std::string src = (!in.empty() && in[0] == '^') ? in.substr(1) : in;
+      const size_t colon = src.rfind(':');
+      if (colon != std::string::npos) src = src.substr(0, colon);
+      if (!names.count(src) && !graph->by_name.count(src)) {
+        status->status = tensorflow::errors::InvalidArgument(
+            "Node '", op->node.name, "': Unknown input node '", in, "'");
+        return;
+      }
+    }
+  for (auto& op : added) {
+    graph->by_name[op->node.name] = op.get();
+    graph->operations.push_back(std::move(op));
+  }
+  status->status = Status::OK();
+}
+
+char* B200TF_GraphDefToText(const void* proto, size_t proto_len, TF_Status* status) {
+  tensorflow::GraphDef def;
+  status->status = tensorflow::ParseGraphDef(proto, proto_len, &def);
+  if (!status->status.ok()) return nullptr;
+  const std::string text = tensorflow::GraphDefDebugString(def);
+  char* out = static_cast<char*>(malloc(text.size() + 1));
+  memcpy(out, text.c_str(), text.size() + 1);
+  return out;
 }
 
 TF_Session* TF_NewSession(TF_Graph* graph, const TF_SessionOptions* opts, TF_Status* status) {

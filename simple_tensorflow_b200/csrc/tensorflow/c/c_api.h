@@ -109,6 +109,39 @@ TF_CAPI_EXPORT extern int TF_OperationNumOutputs(TF_Operation* oper);
 TF_CAPI_EXPORT extern TF_DataType TF_OperationOutputType(TF_Output oper_out);
 TF_CAPI_EXPORT extern int TF_OperationNumInputs(TF_Operation* oper);
 TF_CAPI_EXPORT extern TF_Operation* TF_GraphOperationByName(TF_Graph* graph, const char* oper_name);
+/* Iterate the operations of a graph: start with *pos = 0; returns NULL at the end (c_api.h:763). */
+TF_CAPI_EXPORT extern TF_Operation* TF_GraphNextOperation(TF_Graph* graph, size_t* pos);
+
+/* ---- GraphDef import / export in protobuf wire format (c_api.h:160-180, 786-836).
+ * The codec is hand-written (core/framework/graph_def_wire.cc): there is no protoc here. */
+typedef struct TF_Buffer {
+  const void* data;
+  size_t length;
+  void (*data_deallocator)(void* data, size_t length);
+} TF_Buffer;
+TF_CAPI_EXPORT extern TF_Buffer* TF_NewBufferFromString(const void* proto, size_t proto_len);
+TF_CAPI_EXPORT extern TF_Buffer* TF_NewBuffer(void);
+TF_CAPI_EXPORT extern void TF_DeleteBuffer(TF_Buffer*);
+TF_CAPI_EXPORT extern TF_Buffer TF_GetBuffer(TF_Buffer* buffer);
+/* Writes the graph as a serialized GraphDef (versions.producer = 21, the reference's
+ * TF_GRAPH_DEF_VERSION, core/public/version.h:90). */
+TF_CAPI_EXPORT extern void TF_GraphToGraphDef(TF_Graph* graph, TF_Buffer* output_graph_def,
+                                              TF_Status* status);
+typedef struct TF_ImportGraphDefOptions TF_ImportGraphDefOptions;
+TF_CAPI_EXPORT extern TF_ImportGraphDefOptions* TF_NewImportGraphDefOptions(void);
+TF_CAPI_EXPORT extern void TF_DeleteImportGraphDefOptions(TF_ImportGraphDefOptions* opts);
+TF_CAPI_EXPORT extern void TF_ImportGraphDefOptionsSetPrefix(TF_ImportGraphDefOptions* opts,
+                                                             const char* prefix);
+/* Imports every node of a serialized GraphDef.  Departure from the reference: a node whose op
+ * type is not registered here (savers, string ops, ...) is imported as an opaque node instead of
+ * failing the import; a Session::Run whose pruned sub-graph contains such a node fails with
+ * NOT_FOUND "Op type not registered".  `options` may be NULL. */
+TF_CAPI_EXPORT extern void TF_GraphImportGraphDef(TF_Graph* graph, const TF_Buffer* graph_def,
+                                                  const TF_ImportGraphDefOptions* options,
+                                                  TF_Status* status);
+/* Additive: a line-per-node text dump of a serialized GraphDef (malloc'ed; free() it). */
+TF_CAPI_EXPORT extern char* B200TF_GraphDefToText(const void* proto, size_t proto_len,
+                                                  TF_Status* status);
 
 typedef struct TF_Session TF_Session;
 TF_CAPI_EXPORT extern TF_Session* TF_NewSession(TF_Graph* graph, const TF_SessionOptions* opts,

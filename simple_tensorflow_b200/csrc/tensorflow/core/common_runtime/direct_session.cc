@@ -62,10 +62,17 @@ Status DirectSession::AddNodes(const GraphDef& graph) {
     if (node_index_.count(nd.name))
       return errors::InvalidArgument("Node '", nd.name, "' is not unique");
     const OpDef* op_def = OpRegistry::Global()->LookUp(nd.op);
-    if (op_def == nullptr)
-      return errors::NotFound("Op type not registered '", nd.op, "' (node '", nd.name, "')");
     std::unique_ptr<NodeItem> item(new NodeItem);
     item->def = nd;
+    if (op_def == nullptr) {
+      // Imported graphs (TF_GraphImportGraphDef) carry savers, string ops, parsers ... that this
+      // runtime does not implement: such a node only fails a Run() that actually needs it.
+      item->unsupported = strings::StrCat("Op type not registered '", nd.op, "' (node '", nd.name,
+                                          "'): outside the B200 hot path");
+      node_index_[nd.name] = static_cast<int>(nodes_.size());
+      nodes_.push_back(std::move(item));
+      continue;
+    }
     TF_RETURN_IF_ERROR(ValidateNodeDef(&item->def, *op_def));
     if (!nd.device.empty() && nd.device.find("CPU") != std::string::npos &&
         nd.device.find("cpu") != std::string::npos)
@@ -93,6 +100,7 @@ Status DirectSession::AddNodes(const GraphDef& graph) {
         return errors::InvalidArgument("Node '", item->def.name, "': Unknown input node '", in, "'");
       item->inputs.push_back(TensorId{it->second, slot});
     }
+    if (!item->unsupported.empty()) continue;
     const OpDef* op_def = OpRegistry::Global()->LookUp(item->def.op);
     DataTypeVector in_types, out_types;
     TF_RETURN_IF_ERROR(InOutTypesForNode(item->def, *op_def, &in_types, &out_types));
@@ -169,6 +177,7 @@ Status DirectSession::GetOrCreateExecutors(const std::vector<std::string>& feeds
     if (state[n] == 1)
       return errors::InvalidArgument("Graph has a cycle through node '", nodes_[n]->def.name,
                                      "' (control-flow loops are outside the hot path)");
+    if (!nodes_[n]->unsupported.empty()) return errors::NotFound(nodes_[n]->unsupported);
     state[n] = 1;
     for (const TensorId& in : nodes_[n]->inputs)
       if (!feed_of.count({in.node, in.slot})) TF_RETURN_IF_ERROR(visit(in.node));

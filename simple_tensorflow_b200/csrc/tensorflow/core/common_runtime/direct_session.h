@@ -63,6 +63,7 @@ class DirectSession : public Session {
     std::vector<TensorId> inputs;       // data inputs, in op-signature order
     std::vector<int> control_inputs;    // node indices
     std::unique_ptr<OpKernel> kernel;   // created on first use
+    std::string unsupported;            // non-empty: op type not registered (imported graphs)
   };
   struct InputSource {
     int feed = -1;  // >= 0: index into the step's feeds

@@ -15,7 +15,7 @@
 namespace tensorflow {
 
 struct AttrValue {
-  enum Kind { kNone, kS, kI, kF, kB, kType, kShape, kTensor, kListI, kListS, kListType };
+  enum Kind { kNone, kS, kI, kF, kB, kType, kShape, kTensor, kListI, kListS, kListType, kRaw };
   Kind kind = kNone;
   std::string s;
   int64 i = 0;
@@ -27,6 +27,9 @@ struct AttrValue {
   std::vector<int64> list_i;
   std::vector<std::string> list_s;
   std::vector<DataType> list_type;
+  // kRaw: a serialized AttrValue this runtime does not model (list(shape), list(float), func,
+  // string tensors, ...), carried verbatim so that graphs round-trip losslessly.
+  std::string raw;
 
   static AttrValue S(const std::string& v) { AttrValue a; a.kind = kS; a.s = v; return a; }
   static AttrValue I(int64 v) { AttrValue a; a.kind = kI; a.i = v; return a; }
@@ -49,6 +52,8 @@ struct NodeDef {
 
 struct GraphDef {
   std::vector<NodeDef> node;
+  // graph.proto fields 4 (VersionDef) and 2 (FunctionDefLibrary), serialized, carried verbatim.
+  std::string versions_raw, library_raw;
 };
 
 // node_def_util.h GetNodeAttr overloads.

@@ -167,6 +167,7 @@ bool KindMatches(const std::string& type, const AttrValue& v) {
     case AttrValue::kListI: return type == "list(int)";
     case AttrValue::kListS: return type == "list(string)";
     case AttrValue::kListType: return type == "list(type)";
+    case AttrValue::kRaw: return true;  // imported, not modelled here (checked by whoever uses it)
     default: return false;
   }
 }

@@ -254,6 +254,28 @@ class MulOp : public OpKernel {
   }
 };
 
+// Add with the same two shapes as Mul: equal shapes, or one operand a single element.
+template <typename T>
+class AddOp : public OpKernel {
+ public:
+  explicit AddOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor* x = &ctx->input(0);
+    const Tensor* y = &ctx->input(1);
+    if (x->NumElements() == 1 && y->NumElements() != 1) std::swap(x, y);  // commutative
+    const bool scalar = y->NumElements() == 1 && x->NumElements() != 1;
+    OP_REQUIRES(ctx, scalar || x->shape() == y->shape(),
+                errors::Unimplemented("Add on B200 supports equal shapes or a scalar operand; got ",
+                                      x->shape().DebugString(), " vs ", y->shape().DebugString()));
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, x->shape(), &out));
+    OP_REQUIRES_OK(ctx, FromAbi(b200_add(AbiType<T>::v, x->raw_data(), y->raw_data(),
+                                         out->raw_data(), x->NumElements(), scalar,
+                                         GetCudaStream(ctx)),
+                                "Add"));
+  }
+};
+
 // Mean over ALL elements (the loss reduction); reduction_indices is a host-memory vector.
 class MeanOp : public OpKernel {
  public:
@@ -523,6 +545,7 @@ class B200AllReduceNOp : public OpKernel {
                           B200AllReduceNOp<T>);                                                  \
   REGISTER_KERNEL_BUILDER(Name("AddN").Device(DEVICE_GPU).TypeConstraint<T>("T"), AddNOp<T>);    \
   REGISTER_KERNEL_BUILDER(Name("Mul").Device(DEVICE_GPU).TypeConstraint<T>("T"), MulOp<T>);      \
+  REGISTER_KERNEL_BUILDER(Name("Add").Device(DEVICE_GPU).TypeConstraint<T>("T"), AddOp<T>);      \
   REGISTER_KERNEL_BUILDER(Name("ApplyGradientDescent").Device(DEVICE_GPU).TypeConstraint<T>("T"),\
                           ApplyGradientDescentOp<T>);                                            \
   REGISTER_KERNEL_BUILDER(                                                                       \

@@ -97,6 +97,8 @@ REGISTER_OP("AddN").Input("inputs: N * T").Output("sum: T").Attr("N: int >= 1")
 
 REGISTER_OP("Mul").Input("x: T").Input("y: T").Output("z: T").Attr("T: numbertype")
     .SetIsCommutative();
+// math_ops.cc BINARY_MORE: "Add" (what a loaded model's bias / offset usually is)
+REGISTER_OP("Add").Input("x: T").Input("y: T").Output("z: T").Attr("T: numbertype");
 
 REGISTER_OP("Mean")
     .Input("input: T").Input("reduction_indices: Tidx").Output("output: T")

@@ -255,6 +255,20 @@ def multiply(x, y, name=None):
     return _set_shape(op.outputs[0], sx if sx and int(np.prod(sx)) != 1 else sy)
 
 
+def add(x, y, name=None):
+    """math_ops.add for equal shapes or a scalar operand."""
+    x, y = _val(x), _val(y)
+    op = _g(x).create_op("Add", [x, y], {"T": ("type", x.dtype)}, name or "Add")
+    sx, sy = _shape(x), _shape(y)
+    return _set_shape(op.outputs[0], sx if sx not in (None, ()) else sy)
+
+
+def import_graph_def(graph_def, name=""):
+    """importer.py import_graph_def into the default graph: serialized GraphDef bytes (e.g.
+    written by real TensorFlow 1.0) -> {prefixed name: Operation}."""
+    return get_default_graph().import_graph_def(graph_def, name)
+
+
 def add_n(inputs, name=None):
     if len(inputs) == 1:
         return inputs[0]
