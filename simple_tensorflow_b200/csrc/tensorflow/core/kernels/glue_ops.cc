@@ -242,11 +242,13 @@ class MulOp : public OpKernel {
     const Tensor* y = &ctx->input(1);
     if (x->NumElements() == 1 && y->NumElements() != 1) std::swap(x, y);  // commutative
     const bool scalar = y->NumElements() == 1 && x->NumElements() != 1;
-    OP_REQUIRES(ctx, scalar || x->shape() == y->shape(),
+    const bool both_single = x->NumElements() == 1 && y->NumElements() == 1;  // [] op [1,1] -> [1,1]
+    OP_REQUIRES(ctx, scalar || both_single || x->shape() == y->shape(),
                 errors::Unimplemented("Mul on B200 supports equal shapes or a scalar operand; got ",
                                       x->shape().DebugString(), " vs ", y->shape().DebugString()));
     Tensor* out = nullptr;
-    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, x->shape(), &out));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(
+                            0, both_single && y->dims() > x->dims() ? y->shape() : x->shape(), &out));
     OP_REQUIRES_OK(ctx, FromAbi(b200_mul(AbiType<T>::v, x->raw_data(), y->raw_data(),
                                          out->raw_data(), x->NumElements(), scalar,
                                          GetCudaStream(ctx)),
@@ -264,11 +266,13 @@ class AddOp : public OpKernel {
     const Tensor* y = &ctx->input(1);
     if (x->NumElements() == 1 && y->NumElements() != 1) std::swap(x, y);  // commutative
     const bool scalar = y->NumElements() == 1 && x->NumElements() != 1;
-    OP_REQUIRES(ctx, scalar || x->shape() == y->shape(),
+    const bool both_single = x->NumElements() == 1 && y->NumElements() == 1;  // [] op [1,1] -> [1,1]
+    OP_REQUIRES(ctx, scalar || both_single || x->shape() == y->shape(),
                 errors::Unimplemented("Add on B200 supports equal shapes or a scalar operand; got ",
                                       x->shape().DebugString(), " vs ", y->shape().DebugString()));
     Tensor* out = nullptr;
-    OP_REQUIRES_OK(ctx, ctx->allocate_output(0, x->shape(), &out));
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(
+                            0, both_single && y->dims() > x->dims() ? y->shape() : x->shape(), &out));
     OP_REQUIRES_OK(ctx, FromAbi(b200_add(AbiType<T>::v, x->raw_data(), y->raw_data(),
                                          out->raw_data(), x->NumElements(), scalar,
                                          GetCudaStream(ctx)),

@@ -448,6 +448,28 @@ def test_conv2d_full_size_adjoint_property(oracle, rng):
 
 
 # =============================================================================== glue ops
+def test_multi_tensor_sgd_is_bit_identical_to_per_variable_updates(rng):
+    import ctypes
+    L = au.lib()
+    sizes = [1024 * 1024, 1024, 7, 333 * 1001]
+    vars_ = [rng.randn(n).astype(np.float32) for n in sizes]
+    deltas = [rng.randn(n).astype(np.float32) for n in sizes]
+    alphas = [au.dev(np.array([a], np.float32)) for a in (0.01, 0.5, 1.0, 0.125)]
+    one = [au.dev(v) for v in vars_]
+    many = [au.dev(v) for v in vars_]
+    dd = [au.dev(d) for d in deltas]
+    for v, a, d, n in zip(one, alphas, dd, sizes):
+        au.call(L.b200_apply_gradient_descent, 1, v.data_ptr(), a.data_ptr(), d.data_ptr(), n, au.stream())
+    k = len(sizes)
+    au.call(L.b200_apply_gradient_descent_multi, 1, k,
+            (ctypes.c_void_p * k)(*[t.data_ptr() for t in many]),
+            (ctypes.c_void_p * k)(*[t.data_ptr() for t in alphas]),
+            (ctypes.c_void_p * k)(*[t.data_ptr() for t in dd]),
+            (ctypes.c_int64 * k)(*sizes), au.stream())
+    for a, b in zip(one, many):
+        np.testing.assert_array_equal(au.host(a), au.host(b))
+
+
 def test_apply_gradient_descent_add_n_scale_sum(oracle, rng):
     import torch
     L = au.lib()
@@ -463,6 +485,10 @@ def test_apply_gradient_descent_add_n_scale_sum(oracle, rng):
     np.testing.assert_array_equal(au.host(prod), delta * np.float32(0.01))
     au.call(L.b200_mul, 1, dd.data_ptr(), dd.data_ptr(), prod.data_ptr(), n, 0, au.stream())
     np.testing.assert_array_equal(au.host(prod), delta * delta)
+    au.call(L.b200_add, 1, dd.data_ptr(), alpha.data_ptr(), prod.data_ptr(), n, 1, au.stream())
+    np.testing.assert_array_equal(au.host(prod), delta + np.float32(0.01))
+    au.call(L.b200_add, 1, dd.data_ptr(), dd.data_ptr(), prod.data_ptr(), n, 0, au.stream())
+    np.testing.assert_array_equal(au.host(prod), delta + delta)
     np.testing.assert_allclose(au.host(dv), oracle.apply_gradient_descent(var, 0.01, delta),
                                rtol=1e-6, atol=1e-7)
     import ctypes
