@@ -233,6 +233,201 @@ static int run_im2col(const void* in, void* col, const ConvG& g, cudaStream_t s)
   return check_launch("im2col");
 }
 
+
+// ------------------------------------------------------------------ first layers (C_in <= 4)
+// A network's first convolution (LeNet conv1: C=1, VGG conv1_1: C=3) has K_gemm = R*S*C of a few
+// dozen: as a GEMM it would pad K to the MMA granularity AND need a patch matrix because TMA
+// im2col wants whole 128-byte channel blocks.  It is an HBM-bound streaming problem instead
+// (conv1 of LeNet at batch 512: 1.6 MB in, 51 MB out, 0.64 GFLOP), done on the CUDA cores in
+// IEEE fp32: the filter lives in shared memory, 8 consecutive threads produce the K outputs of
+// one pixel (4 each, so a pixel's row of K floats is written as one coalesced run) and the taps
+// of a pixel are broadcast loads out of L1.
+constexpr int kSmallCinThreads = 256;
+struct SmallCinFit {
+  bool ok;
+  int taps;  // R * S * C
+};
+static SmallCinFit small_cin_fit(int dtype, const ConvG& g) {
+  SmallCinFit f{false, g.R * g.S * g.C};
+  f.ok = dtype == B200_DT_FLOAT && g.C >= 1 && g.C <= 4 && g.K % 4 == 0 && g.K >= 4 && g.K <= 128 &&
+         (size_t)f.taps * g.K * sizeof(float) <= 40 * 1024 && f.taps <= 200 &&
+         (long long)g.N * g.OH * g.OW < (1LL << 30) && (long long)g.N * g.H * g.W * g.C < (1LL << 31);
+  return f;
+}
+
+// kR/kS/kC > 0: compile-time filter geometry (taps fully unrolled); 0: read it from `g`.
+template <int kR, int kS, int kC, int kKPerThread>
+__global__ void __launch_bounds__(kSmallCinThreads)
+conv_small_cin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                          float* __restrict__ y, ConvG g, int pixels) {
+  pdl_prologue();
+  extern __shared__ float wsm[];  // [taps][K]
+  const int R = kR ? kR : g.R, S = kS ? kS : g.S, C = kC ? kC : g.C;
+  const int taps = R * S * C;
+  for (int i = threadIdx.x; i < taps * g.K; i += kSmallCinThreads) wsm[i] = __ldg(w + i);
+  __syncthreads();
+  constexpr int KP = kKPerThread;            // filters per thread: one input load feeds KP FMAs
+  const int kgroups = g.K / KP;
+  const int ppc = kSmallCinThreads / kgroups;  // pixels per CTA pass
+  const int kg = threadIdx.x % kgroups, pl = threadIdx.x / kgroups;
+  if (pl >= ppc) return;
+  const float* wk = wsm + kg * KP;
+  for (int p = blockIdx.x * ppc + pl; p < pixels; p += gridDim.x * ppc) {
+    const int ow = p % g.OW;
+    const int t = p / g.OW;
+    const int oh = t % g.OH;
+    const int n = t / g.OH;
+    float acc[KP];
+#pragma unroll
+    for (int j = 0; j < KP; ++j) acc[j] = 0.f;
+    const float* xn = x + (long long)n * g.H * g.W * C;
+    const int ih0 = oh * g.sh - g.pt, iw0 = ow * g.sw - g.pl;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int ih = ih0 + r;
+      const bool row_in = ih >= 0 && ih < g.H;
+#pragma unroll
+      for (int sx = 0; sx < S; ++sx) {
+        const int iw = iw0 + sx;
+        const bool in = row_in && iw >= 0 && iw < g.W;
+        const float* xp = xn + (ih * g.W + iw) * C;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+          const float v = in ? __ldg(xp + c) : 0.f;
+          const float* wt = wk + ((r * S + sx) * C + c) * g.K;
+#pragma unroll
+          for (int q = 0; q < KP / 4; ++q) {
+            const float4 wv = *reinterpret_cast<const float4*>(wt + 4 * q);
+            acc[4 * q] = fmaf(v, wv.x, acc[4 * q]);
+            acc[4 * q + 1] = fmaf(v, wv.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v, wv.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
+          }
+        }
+      }
+    }
+    float4* out = reinterpret_cast<float4*>(y + (long long)p * g.K + kg * KP);
+#pragma unroll
+    for (int q = 0; q < KP / 4; ++q)
+      out[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+  }
+}
+
+// Filter gradient of a first layer: dW[tap, k] = sum over pixels of patch[p, tap] * dY[p, k].
+// The kernel is bound by bytes in flight on the dY stream (51 MB for LeNet conv1), so dY is
+// staged: a 64-thread CTA cp.async's tiles of 64 pixels x 32 filters (8 KB, double-buffered) into
+// shared memory; thread (tap = tid / 2, half = tid % 2) then owns 16 accumulators (one tap x 16
+// filters) for the whole kernel -- per pixel one gathered input value, four broadcast 16-byte
+// shared loads, 16 FMAs -- so no reduction is needed inside the CTA and the pixel order is fixed.
+// CTAs write partial [taps][K] tiles that a second kernel adds in CTA order: no atomics,
+// reproducible.  K % 32 == 0; more than 32 taps / 32 filters are further passes over dY.
+constexpr int kWgradThreads = 64, kWgradTilePix = 64;
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc)
+               : "memory");
+}
+__global__ void __launch_bounds__(kWgradThreads)
+conv_small_cin_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                            float* __restrict__ partial, ConvG g, int pixels) {
+  pdl_prologue();
+  __shared__ __align__(16) float tile[2][kWgradTilePix][32];
+  const int taps = g.R * g.S * g.C;
+  const int t = threadIdx.x >> 1, half = threadIdx.x & 1;
+  const int ntiles = (pixels + kWgradTilePix - 1) / kWgradTilePix;
+  for (int tb = 0; tb * 32 < taps; ++tb) {
+    const int tap = tb * 32 + t;
+    const bool tap_ok = tap < taps;
+    const int c = tap % g.C, rs = tap / g.C;
+    const int sx = rs % g.S, r = rs / g.S;
+    for (int kb = 0; kb * 32 < g.K; ++kb) {
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+      auto load_tile = [&](int ti, int buf) {
+        for (int i = threadIdx.x; i < kWgradTilePix * 8; i += kWgradThreads) {
+          const int pix = i >> 3, q = i & 7;
+          const int p = ti * kWgradTilePix + pix;
+          float* dst = &tile[buf][pix][q * 4];
+          if (p < pixels)
+            cp_async16(dst, dy + (long long)p * g.K + kb * 32 + q * 4);
+          else
+            *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      int buf = 0;
+      int ti = blockIdx.x;
+      if (ti < ntiles) load_tile(ti, 0);
+      for (; ti < ntiles; ti += gridDim.x) {
+        const int nxt = ti + gridDim.x;
+        if (nxt < ntiles) {
+          load_tile(nxt, buf ^ 1);
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncthreads();
+        const int p0 = ti * kWgradTilePix;
+        int ow = p0 % g.OW, tt = p0 / g.OW;
+        int oh = tt % g.OH, n = tt / g.OH;
+        const int npix = min(kWgradTilePix, pixels - p0);
+        for (int pix = 0; pix < npix; ++pix) {
+          const int ih = oh * g.sh - g.pt + r, iw = ow * g.sw - g.pl + sx;
+          const bool in = tap_ok && ih >= 0 && ih < g.H && iw >= 0 && iw < g.W;
+          const float v = in ? __ldg(x + (((long long)n * g.H + ih) * g.W + iw) * g.C + c) : 0.f;
+          const float4* d = reinterpret_cast<const float4*>(&tile[buf][pix][half * 16]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 dq = d[q];
+            acc[4 * q] = fmaf(v, dq.x, acc[4 * q]);
+            acc[4 * q + 1] = fmaf(v, dq.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(v, dq.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(v, dq.w, acc[4 * q + 3]);
+          }
+          if (++ow == g.OW) {  // next pixel, without divisions
+            ow = 0;
+            if (++oh == g.OH) {
+              oh = 0;
+              ++n;
+            }
+          }
+        }
+        __syncthreads();  // tile consumed: the next trip's prefetch may overwrite the other buffer
+        buf ^= 1;
+      }
+      if (tap_ok) {
+        float4* dst = reinterpret_cast<float4*>(partial + ((long long)blockIdx.x * taps + tap) * g.K +
+                                                kb * 32 + half * 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          dst[q] = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+      }
+    }
+  }
+}
+// dW[i] = sum over CTAs (fixed order) of partial[cta][i]: 32 elements x 8 strands per CTA, each
+// strand adds every 8th partial in ascending order, the strands are merged in strand order.
+__global__ void __launch_bounds__(256)
+conv_small_cin_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
+                                   int blocks, int elems) {
+  pdl_prologue();
+  __shared__ float strands[8][33];
+  const int e = blockIdx.x * 32 + (threadIdx.x & 31), st = threadIdx.x >> 5;
+  float sum = 0.f;
+  if (e < elems)
+    for (int b = st; b < blocks; b += 8) sum += partial[(long long)b * elems + e];
+  strands[st][threadIdx.x & 31] = sum;
+  __syncthreads();
+  if (st == 0 && e < elems) {
+    float t = 0.f;
+    for (int q = 0; q < 8; ++q) t += strands[q][threadIdx.x];
+    dw[e] = t;
+  }
+}
+static int small_cin_wgrad_blocks() { return 8 * sm_count(); }
+
 static GemmArgs base_gemm(int dtype) {
   GemmArgs a{};
   a.dtype = dtype;
@@ -253,6 +448,13 @@ size_t b200_conv2d_workspace_bytes(int dtype, const b200_conv2d_geometry* geom, 
   const long long rows = (long long)g.N * g.OH * g.OW;
   const long long rsc = (long long)g.R * g.S * g.C;
   const size_t col = is_pointwise(g) ? 0 : align256((size_t)rows * g.ldk * es);
+  const SmallCinFit small = small_cin_fit(dtype, g);
+  static const bool no_direct_ws = getenv("B200TF_CONV_NO_DIRECT") != nullptr;
+  if (small.ok && !no_direct_ws && !is_pointwise(g)) {
+    if (which == 0) return 0;
+    if (which == 2 && g.K % 32 == 0)
+      return align256((size_t)small_cin_wgrad_blocks() * small.taps * g.K * sizeof(float));
+  }
   if (which == 0) {
     // implicit GEMM needs no patch matrix (decided again at launch from the real pointers)
     ConvAOperand ca{reinterpret_cast<const void*>(16), g.N, g.H, g.W, g.C, g.R, g.S, g.OH, g.OW,
@@ -303,6 +505,34 @@ int b200_conv2d(int dtype, const void* input, const void* filter, void* output,
   if (need > 0 && (!workspace || workspace_bytes < need)) {
     set_last_error("b200_conv2d: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
     return B200_INVALID_ARGUMENT;
+  }
+  static const bool no_direct = getenv("B200TF_CONV_NO_DIRECT") != nullptr;
+  const SmallCinFit small = small_cin_fit(dtype, g);
+  if (small.ok && !no_direct && !is_pointwise(g) && aligned16(output)) {
+    // 16 filters per thread when K allows it (one input load feeds 16 FMAs), else 4
+    const int kp = g.K % 16 == 0 ? 16 : 4;
+    const int ppc = kSmallCinThreads / (g.K / kp);
+    long long blocks = (rows + ppc - 1) / ppc;
+    if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+    const size_t smem = (size_t)small.taps * g.K * sizeof(float);
+    const float* xin = static_cast<const float*>(input);
+    const float* win = static_cast<const float*>(filter);
+    float* yout = static_cast<float*>(output);
+    const int pixels = (int)rows;
+#define SMALL_FWD(R_, S_, C_, KP_)                                                                \
+  launch_pdl(conv_small_cin_fwd_kernel<R_, S_, C_, KP_>, dim3((unsigned)blocks),                  \
+             dim3(kSmallCinThreads), smem, s, xin, win, yout, g, pixels)
+    if (kp == 16 && g.R == 5 && g.S == 5 && g.C == 1)
+      SMALL_FWD(5, 5, 1, 16);
+    else if (kp == 16 && g.R == 3 && g.S == 3 && g.C == 3)
+      SMALL_FWD(3, 3, 3, 16);
+    else if (kp == 16)
+      SMALL_FWD(0, 0, 0, 16);
+    else
+      SMALL_FWD(0, 0, 0, 4);
+#undef SMALL_FWD
+    note_launch();
+    return check_launch("b200_conv2d");
   }
   GemmArgs a = base_gemm(dtype);
   a.b = filter;  // [R*S*C, K] row-major == HWIO
@@ -368,6 +598,21 @@ int b200_conv2d_backprop_filter(int dtype, const void* input, const void* out_ba
     set_last_error("b200_conv2d_backprop_filter: workspace too small (%zu < %zu bytes)",
                    workspace_bytes, need);
     return B200_INVALID_ARGUMENT;
+  }
+  static const bool no_direct = getenv("B200TF_CONV_NO_DIRECT") != nullptr;
+  const SmallCinFit small = small_cin_fit(dtype, g);
+  if (small.ok && g.K % 32 == 0 && !no_direct && !is_pointwise(g) && aligned16(out_backprop)) {
+    const int blocks = small_cin_wgrad_blocks();
+    float* partial = static_cast<float*>(workspace);
+    launch_pdl(conv_small_cin_wgrad_kernel, dim3(blocks), dim3(kWgradThreads), 0, s,
+               static_cast<const float*>(input), static_cast<const float*>(out_backprop), partial, g,
+               (int)rows);
+    const int elems = small.taps * g.K;
+    launch_pdl(conv_small_cin_wgrad_reduce_kernel, dim3((elems + 31) / 32), dim3(256), 0, s,
+               static_cast<const float*>(partial), static_cast<float*>(filter_backprop), blocks,
+               elems);
+    note_launch(2);
+    return check_launch("b200_conv2d_backprop_filter");
   }
   GemmArgs a = base_gemm(dtype);
   a.b = out_backprop;  // [rows, K]

@@ -387,6 +387,11 @@ CONV_SHAPES = [
     ((2, 8, 8, 96), (1, 3, 96, 40), (1, 1), "SAME"),
     ((5, 7, 7, 32), (7, 7, 32, 8), (1, 1), "SAME"),
     ((1, 33, 35, 32), (5, 5, 32, 64), (3, 2), "SAME"),
+    # first layers (C_in <= 4): the direct CUDA-core kernels (forward; filter gradient when K % 32 == 0)
+    ((2, 12, 12, 3), (3, 3, 3, 64), (1, 1), "SAME"),
+    ((3, 11, 9, 1), (5, 5, 1, 32), (2, 2), "SAME"),
+    ((2, 8, 8, 4), (3, 3, 4, 96), (1, 1), "VALID"),     # 36 taps: two tap blocks
+    ((2, 6, 7, 2), (7, 5, 2, 32), (1, 2), "SAME"),      # 70 taps: three tap blocks
 ]
 
 
@@ -430,6 +435,22 @@ def test_conv2d_bf16(oracle, rng):
     f = oracle.truncate_to_bf16(rng.rand(3, 3, 32, 64).astype(np.float32) - 0.5)
     got = au.conv2d(x, f, (1, 1), "SAME", oracle, bf16=True)
     assert au.rel_err(got, oracle.conv2d(x, f, (1, 1), "SAME")) < TOL
+
+
+@pytest.mark.parametrize("cin,cout", [(3, 64), (64, 64), (64, 128), (128, 128)])
+def test_conv_family_bf16_vgg_layers(oracle, rng, cin, cout):
+    # BASELINE config 5's layer type: 3x3 SAME stride 1 in bf16 (fp32 accumulate); C=3 runs the
+    # patch-matrix path, the 64-multiples the implicit GEMM (forward, input and filter gradient)
+    shape, fshape = (4, 16, 16, cin), (3, 3, cin, cout)
+    x = oracle.truncate_to_bf16(rng.rand(*shape).astype(np.float32) - 0.5)
+    f = oracle.truncate_to_bf16((rng.rand(*fshape).astype(np.float32) - 0.5) * 0.2)
+    y_ref = oracle.conv2d(x, f, (1, 1), "SAME")
+    assert au.rel_err(au.conv2d(x, f, (1, 1), "SAME", oracle, bf16=True), y_ref) < TOL
+    dy = oracle.truncate_to_bf16(rng.rand(*y_ref.shape).astype(np.float32) - 0.5)
+    dx = au.conv2d_backprop_input(shape, f, dy, (1, 1), "SAME", oracle, bf16=True)
+    assert au.rel_err(dx, oracle.conv2d_backprop_input(shape, f, dy, (1, 1), "SAME")) < TOL
+    dw = au.conv2d_backprop_filter(x, fshape, dy, (1, 1), "SAME", oracle, bf16=True)
+    assert au.rel_err(dw, oracle.conv2d_backprop_filter(x, fshape, dy, (1, 1), "SAME")) < TOL
 
 
 def test_conv2d_full_size_adjoint_property(oracle, rng):

@@ -167,6 +167,79 @@ def _lenet_step(oracle, rng, exact_fp32):
     assert pred.dtype == np.int64 and pred.shape == (B,)
 
 
+def test_vgg_style_training_step_config5_reduced(oracle, rng):
+    # BASELINE config 5's graph shape (8 x Conv2D 3x3 SAME + ReLU in four blocks with 2x2 pools,
+    # then a classifier), reduced to batch 4 / 16x16 inputs, fp32 graph: one fwd+bwd+SGD step vs
+    # the oracle.  The first layer (C=3) takes the patch-matrix path, the other seven the
+    # TMA-im2col implicit GEMM (forward, input gradient and filter gradient).
+    B, H = 4, 16
+    widths = [(3, 32), (32, 32), (32, 64), (64, 64), (64, 64), (64, 64), (64, 96), (96, 96)]
+    pool_after = {1, 3, 5, 7}
+    x = rng.uniform(-1, 1, (B, H, H, 3)).astype(np.float32)
+    labels = np.eye(10, dtype=np.float32)[rng.randint(0, 10, B)]
+    ws = [(rng.randn(3, 3, ci, co) * np.sqrt(2.0 / (9 * ci))).astype(np.float32) for ci, co in widths]
+    bs = [np.full(co, 0.05, np.float32) for _, co in widths]
+    wf = (rng.randn(96, 10) * 0.1).astype(np.float32)
+    bf = np.zeros(10, np.float32)
+    lr = 0.05
+    tf.reset_default_graph()
+    xp, lp = tf.placeholder(tf.float32, [B, H, H, 3]), tf.placeholder(tf.float32, [B, 10])
+    Wv = [tf.Variable(w, name="w%d" % i) for i, w in enumerate(ws)]
+    Bv = [tf.Variable(b, name="b%d" % i) for i, b in enumerate(bs)]
+    Wf, Bf = tf.Variable(wf, name="wf"), tf.Variable(bf, name="bf")
+    h = xp
+    for i in range(8):
+        h = tf.relu(tf.bias_add(tf.conv2d(h, Wv[i], [1, 1, 1, 1], "SAME"), Bv[i]))
+        if i in pool_after:
+            h = tf.max_pool(h, [1, 2, 2, 1], [1, 2, 2, 1], "SAME")
+    logits = tf.bias_add(tf.matmul(tf.reshape(h, [B, 96]), Wf), Bf)
+    loss = tf.reduce_mean(tf.softmax_cross_entropy_with_logits(logits, lp))
+    train = tf.GradientDescentOptimizer(lr).minimize(loss)
+    with client.Session(tf.get_default_graph()) as sess:
+        sess.run(tf.global_variables_initializer())
+        got_loss, _ = sess.run([loss, train], {xp: x, lp: labels})
+        got_w = sess.run([v.ref for v in Wv] + [Wf.ref])
+        got_b = sess.run([v.ref for v in Bv] + [Bf.ref])
+
+    o = oracle
+    acts, pre_pool, inputs = [], [], []
+    a = x
+    for i in range(8):
+        inputs.append(a)
+        a = o.relu(o.bias_add(o.conv2d(a, ws[i], (1, 1), "SAME"), bs[i]))
+        acts.append(a)
+        if i in pool_after:
+            pre_pool.append(a)
+            a = o.max_pool(a, (2, 2), (2, 2), "SAME")
+    flat = a.reshape(B, 96)
+    lg = o.bias_add(o.matmul(flat, wf), bf)
+    lvec, bp = o.softmax_xent(lg, labels)
+    d = bp / np.float32(B)
+    ref_w, ref_b = [None] * 9, [None] * 9
+    ref_b[8] = o.apply_gradient_descent(bf, lr, o.bias_add_grad(d))
+    ref_w[8] = o.apply_gradient_descent(wf, lr, o.matmul(flat, d, True, False))
+    d = o.matmul(d, wf, False, True).reshape(a.shape)
+    for i in reversed(range(8)):
+        if i in pool_after:
+            d = o.max_pool_grad(acts[i], d, (2, 2), (2, 2), "SAME")
+        d = o.relu_grad(d, acts[i])
+        ref_b[i] = o.apply_gradient_descent(bs[i], lr, o.bias_add_grad(d))
+        ref_w[i] = o.apply_gradient_descent(
+            ws[i], lr, o.conv2d_backprop_filter(inputs[i], ws[i].shape, d, (1, 1), "SAME"))
+        if i > 0:
+            d = o.conv2d_backprop_input(inputs[i].shape, ws[i], d, (1, 1), "SAME")
+    assert abs(got_loss - lvec.mean()) < 1e-2 * abs(lvec.mean())
+    # The bar is on the updated values (1e-2 relative, Frobenius: TF32 may flip single ReLU masks at
+    # this batch size, see the LeNet test); the update itself -- after eight TF32 layers of
+    # backprop -- is additionally held to 5 % so that a wrong gradient cannot hide behind lr.
+    for name, got, ref, old in ([("w%d" % i, got_w[i], ref_w[i], (ws + [wf])[i]) for i in range(9)] +
+                                [("b%d" % i, got_b[i], ref_b[i], (bs + [bf])[i]) for i in range(9)]):
+        upd_ref = (ref - old).ravel().astype(np.float64)
+        upd_got = (got - old).ravel().astype(np.float64)
+        assert np.linalg.norm(upd_got - upd_ref) <= 5e-2 * max(np.linalg.norm(upd_ref), 1e-12), name
+        assert np.linalg.norm((got - ref).ravel()) <= 1e-2 * np.linalg.norm(ref.ravel()), name
+
+
 def test_fusion_rewrite_matches_unfused(oracle, rng, monkeypatch):
     # MatMul+BiasAdd+Relu and MatMul+ReluGrad chains run as _FusedMatMul (fewer launches), with
     # results identical (same GEMM, same fp32 tail) to the op-by-op execution.
