@@ -64,10 +64,27 @@ def bucket_kw():
 
 
 # =================================================================================== CPU arm
+def host_threads():
+    """Threads of the CPU arms: the schedulable CPUs (what the reference's NumSchedulableCPUs
+    returns, platform/posix/port.cc:50-55), but not more than the physical cores -- on this
+    GEMM-bound step two hyper-threads per core run 3-4x slower than one (measured: 128 threads
+    2.5 K samples/s, 64 threads 9.2 K), and the baseline should be the CPU's best."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        import psutil
+        phys = psutil.cpu_count(logical=False)
+        if phys:
+            n = min(n, phys)
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def cpu_step_fn():
     """One full MLP training step on the CPU oracle (test infrastructure used as the baseline)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_bind as o
+    o.set_num_threads(host_threads())
     x, labels, ws, bs = synthetic(1234)
 
     def step():
@@ -355,6 +372,18 @@ def run_b200(args):
         sess.run(res_fetch)
     gemm_ms, gemm_n, gemm_fl = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_double()
     _lib.check(L.b200_profile_end(ctypes.byref(gemm_ms), ctypes.byref(gemm_n), ctypes.byref(gemm_fl)))
+    # what an event pair with nothing between costs on this stream (reported next to the raw
+    # per-launch time: the bracket itself, not the kernel, explains why the kernel's share of the
+    # step looks larger here than in the ncu launch list)
+    pair = []
+    for _ in range(50):
+        _lib.check(L.b200_event_record(ev0, stream))
+        _lib.check(L.b200_event_record(ev1, stream))
+        _lib.check(L.b200_stream_synchronize(stream))
+        ms_pair = ctypes.c_float()
+        _lib.check(L.b200_event_elapsed_ms(ev0, ev1, ctypes.byref(ms_pair)))
+        pair.append(ms_pair.value * 1e3)
+    event_pair_us = statistics.median(pair)
 
     if rank != 0:
         sess.close()
@@ -415,6 +444,7 @@ def run_b200(args):
                      "frac": achieved / peak if peak else None, "traffic": traffic,
                      "peak_source": peak_src, "launches_timed": int(gemm_n.value),
                      "us_per_launch": 1e3 * gemm_ms.value / max(1, gemm_n.value),
+                     "empty_event_pair_us": event_pair_us,
                      "flops_per_launch": (gemm_fl.value / max(1, gemm_n.value)),
                      "gemm_share_of_step": (gemm_ms.value / prof_steps) / (ms_res / args.steps)},
         "cpu_baseline": base,

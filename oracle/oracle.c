@@ -34,6 +34,14 @@ API int oracle_num_threads(void) {
   return 1;
 #endif
 }
+/* Thread count of the following calls (bench.py pins both CPU arms to the same number). */
+API void oracle_set_num_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 /* ---------------------------------------------------------------------------------------------
  * GetWindowedOutputSizeVerbose -- core/framework/common_shape_fns.cc:19-47.

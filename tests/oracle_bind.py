@@ -88,6 +88,13 @@ def num_threads():
     return lib().oracle_num_threads()
 
 
+def set_num_threads(n):
+    L = lib()
+    L.oracle_set_num_threads.argtypes = [ctypes.c_int]
+    L.oracle_set_num_threads.restype = None
+    L.oracle_set_num_threads(int(n))
+
+
 def windowed_output_size(input_size, filter_size, stride, padding):
     """-> (output_size, pad_before, pad_after); padding is 'SAME' or 'VALID'."""
     o, b, a = i64(), i64(), i64()
