@@ -148,12 +148,24 @@ bias_grad_stage1(const T* __restrict__ g, float* __restrict__ partial, long long
   float tot[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) tot[j] = 0.f;
-  if (sub == 0 && cv < W)
+  if (sub == 0 && cv < W) {
+    // up to four partial rows in flight per thread (the loads are independent; only the adds
+    // are ordered), 16-byte loads when the row is vectorised
+#pragma unroll 4
     for (int k = y; k < nchunks; k += 8) {
       const float* src = partial + (long long)k * channels + (long long)cv * VEC;
+      if (VEC == 4) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
+        tot[0] += v.x;
+        tot[1 % VEC] += v.y;
+        tot[2 % VEC] += v.z;
+        tot[3 % VEC] += v.w;
+      } else {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) tot[j] += __ldcg(src + j);
+        for (int j = 0; j < VEC; ++j) tot[j] += __ldcg(src + j);
+      }
     }
+  }
 #pragma unroll
   for (int j = 0; j < VEC; ++j) sm[y][x][j] = tot[j];
   __syncthreads();
@@ -197,9 +209,10 @@ static BiasGradPlan plan_bias_grad(int dtype, long long rows, long long channels
   const long long W = channels / p.vec;
   p.col_tiles = (int)((W + 31) / 32);
   const int fold = W < 32 ? (int)(32 / W) : 1;
-  // Enough CTAs to keep ~5 MB of loads in flight (HBM latency x bandwidth): ~8 CTAs per SM, each
+  // Enough CTAs to keep several MB of loads in flight (HBM latency x bandwidth) without making the
+  // ordered second stage long (it reads one partial row per chunk): ~4 CTAs per SM, each
   // thread issuing one batch of four independent 16-byte loads.
-  long long want = (8LL * 148 + p.col_tiles - 1) / p.col_tiles;
+  long long want = (4LL * 148 + p.col_tiles - 1) / p.col_tiles;
   long long max_chunks = (rows + 8LL * fold * 4 - 1) / (8LL * fold * 4);  // >= 4 rows per thread
   if (max_chunks < 1) max_chunks = 1;
   if (want > max_chunks) want = max_chunks;
@@ -413,7 +426,7 @@ xent_warp_vec_kernel(const float* __restrict__ logits, const float* __restrict__
   const float4* l = reinterpret_cast<const float4*>(labels + row * cols);
   float4* bp = reinterpret_cast<float4*>(backprop + row * cols);
   const int nvec = cols >> 2;
-  float4 v[NV], lab[NV];
+  float4 v[NV], lab[NV], ex[NV];
   float mx = -FLT_MAX;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
@@ -433,7 +446,9 @@ xent_warp_vec_kernel(const float* __restrict__ logits, const float* __restrict__
       v[j].y -= mx;
       v[j].z -= mx;
       v[j].w -= mx;
-      sum += expf(v[j].x) + expf(v[j].y) + expf(v[j].z) + expf(v[j].w);
+      // exp is evaluated once per element and kept for the backprop pass
+      ex[j] = make_float4(expf(v[j].x), expf(v[j].y), expf(v[j].z), expf(v[j].w));
+      sum += ex[j].x + ex[j].y + ex[j].z + ex[j].w;
     }
   sum = warp_sum(sum);
   const float ls = logf(sum);
@@ -445,10 +460,10 @@ xent_warp_vec_kernel(const float* __restrict__ logits, const float* __restrict__
       acc += lab[j].x * (ls - v[j].x) + lab[j].y * (ls - v[j].y) + lab[j].z * (ls - v[j].z) +
              lab[j].w * (ls - v[j].w);
       float4 o;
-      o.x = (expf(v[j].x) / sum - lab[j].x) * sc;
-      o.y = (expf(v[j].y) / sum - lab[j].y) * sc;
-      o.z = (expf(v[j].z) / sum - lab[j].z) * sc;
-      o.w = (expf(v[j].w) / sum - lab[j].w) * sc;
+      o.x = (ex[j].x / sum - lab[j].x) * sc;
+      o.y = (ex[j].y / sum - lab[j].y) * sc;
+      o.z = (ex[j].z / sum - lab[j].z) * sc;
+      o.w = (ex[j].w / sum - lab[j].w) * sc;
       bp[i] = o;
     }
   }
