@@ -445,6 +445,9 @@ def run_b200(args):
                      "peak_source": peak_src, "launches_timed": int(gemm_n.value),
                      "us_per_launch": 1e3 * gemm_ms.value / max(1, gemm_n.value),
                      "empty_event_pair_us": event_pair_us,
+                     "achieved_net_of_event_pair": ((gemm_fl.value / 1e12) /
+                                                    max(1e-9, gemm_ms.value / 1e3 -
+                                                        gemm_n.value * event_pair_us / 1e6)),
                      "flops_per_launch": (gemm_fl.value / max(1, gemm_n.value)),
                      "gemm_share_of_step": (gemm_ms.value / prof_steps) / (ms_res / args.steps)},
         "cpu_baseline": base,
