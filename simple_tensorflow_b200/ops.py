@@ -327,6 +327,50 @@ def _matmul_grad(op, grad):
             matmul(grad, a, transpose_a=True, transpose_b=True))
 
 
+@_register_gradient("BatchMatMul")
+def _batch_matmul_grad(op, grad):
+    # math_grad.py:871-894
+    x, y = op.inputs
+    adj_x, adj_y = op.attrs["adj_x"], op.attrs["adj_y"]
+    if not adj_x:
+        if not adj_y:
+            return batch_matmul(grad, y, False, True), batch_matmul(x, grad, True, False)
+        return batch_matmul(grad, y, False, False), batch_matmul(grad, x, True, False)
+    if not adj_y:
+        return batch_matmul(y, grad, False, True), batch_matmul(x, grad, False, False)
+    return batch_matmul(y, grad, True, True), batch_matmul(grad, x, True, True)
+
+
+@_register_gradient("Add")
+def _add_grad(op, grad):
+    # math_grad.py:592-600 for the case without broadcasting (equal static shapes)
+    x, y = op.inputs
+    if _shape(x) is None or _shape(x) != _shape(y):
+        raise NotImplementedError("gradient of a broadcasting Add is outside the hot path")
+    return grad, grad
+
+
+@_register_gradient("Mul")
+def _mul_grad(op, grad):
+    # math_grad.py _MulGrad without broadcasting; a scalar operand only receives the other side's
+    # gradient (its own would need a full reduction and is not asked for on the hot path)
+    x, y = op.inputs
+    sx, sy = _shape(x), _shape(y)
+    if sx is not None and sx == sy:
+        return multiply(grad, y), multiply(grad, x)
+    if sy is not None and int(np.prod(sy)) == 1:
+        return multiply(grad, y), None
+    if sx is not None and int(np.prod(sx)) == 1:
+        return None, multiply(grad, x)
+    raise NotImplementedError("gradient of a broadcasting Mul is outside the hot path")
+
+
+@_register_gradient("Cast")
+def _cast_grad(op, grad):
+    # math_grad.py:942-953: float types cast the gradient back
+    return (cast(grad, op.inputs[0].dtype),)
+
+
 @_register_gradient("BiasAdd")
 def _bias_add_grad(op, grad):
     # nn_grad.py:180-204: (received_grad, BiasAddGrad(received_grad))

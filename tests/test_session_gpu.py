@@ -311,6 +311,34 @@ def test_xent_scale_rewrite_is_bit_exact(rng, monkeypatch):
     np.testing.assert_allclose(g1, ref, rtol=1e-4, atol=1e-7)
 
 
+@pytest.mark.parametrize("adj_x", [False, True])
+@pytest.mark.parametrize("adj_y", [False, True])
+def test_batch_matmul_gradients(oracle, rng, adj_x, adj_y):
+    # math_grad.py:871-894 through the graph: d/dx, d/dy of sum(w * BatchMatMul(x, y)) vs the oracle
+    b, m, k, n = 3, 40, 24, 56
+    x = rng.randn(*((b, k, m) if adj_x else (b, m, k))).astype(np.float32)
+    y = rng.randn(*((b, n, k) if adj_y else (b, k, n))).astype(np.float32)
+    w = rng.randn(b, m, n).astype(np.float32)
+    tf.reset_default_graph()
+    xp, yp = tf.placeholder(tf.float32, list(x.shape)), tf.placeholder(tf.float32, list(y.shape))
+    z = tf.batch_matmul(xp, yp, adj_x, adj_y)
+    loss = tf.reduce_mean(tf.multiply(z, tf.constant(w)))
+    gx, gy = tf.gradients(loss, [xp, yp])
+    with client.Session(tf.get_default_graph()) as sess:
+        got_z, got_gx, got_gy = sess.run([z, gx, gy], {xp: x, yp: y})
+    ref_z = oracle.batch_matmul(x, y, adj_x, adj_y)
+    g = w / np.float32(w.size)
+    xm = np.swapaxes(x, 1, 2) if adj_x else x           # [b, m, k]
+    ym = np.swapaxes(y, 1, 2) if adj_y else y           # [b, k, n]
+    dxm = np.einsum("bmn,bkn->bmk", g.astype(np.float64), ym.astype(np.float64))
+    dym = np.einsum("bmk,bmn->bkn", xm.astype(np.float64), g.astype(np.float64))
+    ref_gx = np.swapaxes(dxm, 1, 2) if adj_x else dxm
+    ref_gy = np.swapaxes(dym, 1, 2) if adj_y else dym
+    assert np.abs(got_z - ref_z).max() / np.abs(ref_z).max() < 3e-3
+    assert np.abs(got_gx - ref_gx).max() / np.abs(ref_gx).max() < 3e-3
+    assert np.abs(got_gy - ref_gy).max() / np.abs(ref_gy).max() < 3e-3
+
+
 def test_all_reduce_n_single_replica(rng):
     # without a communicator the op is an identity (times scale): the N>1 path runs in bench.py
     a = rng.randn(1000).astype(np.float32)
