@@ -1064,7 +1064,12 @@ static TileConfig choose_config(const GemmArgs& g) {
   if (g.force_bn == 2256) return {2, 256};
   const char* env = getenv("B200TF_GEMM_CTAS");
   const bool allow_pairs = !(env && env[0] == '1');
-  if (allow_pairs && g.M >= 256 && g.N >= 128) return {2, g.N >= 256 ? 256 : 128};
+  static const int pair_bn = [] {  // experiment switch: B200TF_GEMM_PAIR_BN=128 forces 256x128 pair tiles
+    const char* v = getenv("B200TF_GEMM_PAIR_BN");
+    return v ? atoi(v) : 0;
+  }();
+  if (allow_pairs && g.M >= 256 && g.N >= 128)
+    return {2, pair_bn == 128 ? 128 : (g.N >= 256 ? 256 : 128)};
   if (g.N <= 64) return {1, 64};
   const long long t128 = ((g.M + kBM - 1) / kBM) * ((g.N + 127) / 128) * g.batch;
   if (t128 >= sm_count()) return {1, 128};
