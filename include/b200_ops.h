@@ -242,6 +242,11 @@ B200_API int b200_apply_gradient_descent_multi(int dtype, int count, void* const
  * y a DEVICE scalar broadcast over x (y_is_scalar != 0). */
 B200_API int b200_mul(int dtype, const void* x, const void* y, void* out, int64_t n,
                       int y_is_scalar, void* stream);
+/* out[b][col][row] = in[b][row][col]: the NCHW <-> NHWC layout change the reference's GPU kernels do
+ * around cuDNN (core/kernels/conv_ops.cc:558-612,712-719, conv_2d.h NHWCToNCHW / NCHWToNHWC); here
+ * it lets NCHW graphs use the NHWC-native kernels.  batch <= 65535, rows <= 2 M. */
+B200_API int b200_batched_transpose(int dtype, const void* in, void* out, int64_t batch,
+                                    int64_t rows, int64_t cols, void* stream);
 /* Add (core/kernels/cwise_op_add_1.cc), same two shapes. */
 B200_API int b200_add(int dtype, const void* x, const void* y, void* out, int64_t n,
                       int y_is_scalar, void* stream);

@@ -98,6 +98,7 @@ SIGNATURES = {
     "b200_apply_gradient_descent_multi": (c_int, [c_int, c_int, c_void_p, c_void_p, c_void_p,
                                                   c_void_p, c_void_p]),
     "b200_mul": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
+    "b200_batched_transpose": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "b200_add": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p]),
     "b200_add_n": (c_int, [c_int, ctypes.POINTER(c_void_p), c_int, c_void_p, c_int64, c_void_p]),
     "b200_scale": (c_int, [c_int, c_void_p, c_float, c_void_p, c_int64, c_void_p]),

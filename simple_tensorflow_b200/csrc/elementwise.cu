@@ -352,6 +352,30 @@ static int bad_n(const char* what, long long n) {
   return B200_INVALID_ARGUMENT;
 }
 
+// out[b][col][row] = in[b][row][col]: the NCHW <-> NHWC layout change of one activation tensor
+// (rows = C, cols = H*W one way, rows = H*W, cols = C the other).  32x32 tiles through shared
+// memory (padded against bank conflicts), both sides coalesced.
+template <typename T>
+__global__ void __launch_bounds__(256)
+batched_transpose_kernel(const T* __restrict__ in, T* __restrict__ out, long long rows,
+                         long long cols) {
+  pdl_prologue();
+  __shared__ T tile[32][33];
+  const long long b = blockIdx.z;
+  const T* src = in + b * rows * cols;
+  T* dst = out + b * rows * cols;
+  const long long c0 = (long long)blockIdx.x * 32, r0 = (long long)blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const long long r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = src[r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const long long c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
 // ApplyGradientDescent for up to kMultiMax variables in ONE launch (blockIdx.y = variable): the
 // per-element arithmetic is SgdF, i.e. bit-identical to one b200_apply_gradient_descent per variable.
 constexpr int kMultiMax = 16;
@@ -550,6 +574,36 @@ int b200_apply_gradient_descent(int dtype, void* var, const void* alpha, const v
         "b200_apply_gradient_descent", var, delta, var, n,
         SgdF<__nv_bfloat16>{static_cast<const __nv_bfloat16*>(alpha)}, as_stream(stream));
   return bad_dtype("b200_apply_gradient_descent", dtype);
+}
+
+int b200_batched_transpose(int dtype, const void* in, void* out, int64_t batch, int64_t rows,
+                           int64_t cols, void* stream) {
+  if (batch < 0 || rows < 0 || cols < 0 || batch > 65535) {
+    set_last_error("b200_batched_transpose: bad shape [%lld, %lld, %lld]", (long long)batch,
+                   (long long)rows, (long long)cols);
+    return B200_INVALID_ARGUMENT;
+  }
+  if (batch * rows * cols == 0) return B200_OK;
+  int rc = require_device("b200_batched_transpose");
+  if (rc) return rc;
+  const long long gy = (rows + 31) / 32, gx = (cols + 31) / 32;
+  if (gy > 65535) {
+    set_last_error("b200_batched_transpose: %lld rows exceed the grid limit", (long long)rows);
+    return B200_INVALID_ARGUMENT;
+  }
+  const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)batch), block(32, 8);
+  if (dtype == B200_DT_FLOAT)
+    launch_pdl(batched_transpose_kernel<float>, grid, block, 0, as_stream(stream),
+               static_cast<const float*>(in), static_cast<float*>(out), (long long)rows,
+               (long long)cols);
+  else if (dtype == B200_DT_BFLOAT16)
+    launch_pdl(batched_transpose_kernel<__nv_bfloat16>, grid, block, 0, as_stream(stream),
+               static_cast<const __nv_bfloat16*>(in), static_cast<__nv_bfloat16*>(out),
+               (long long)rows, (long long)cols);
+  else
+    return bad_dtype("b200_batched_transpose", dtype);
+  note_launch();
+  return check_launch("b200_batched_transpose");
 }
 
 int b200_apply_gradient_descent_multi(int dtype, int count, void* const* vars_host,

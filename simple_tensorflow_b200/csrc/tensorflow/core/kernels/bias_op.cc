@@ -1,4 +1,5 @@
-// BiasAdd / BiasAddGrad for DEVICE_GPU on B200 (NHWC).
+// BiasAdd / BiasAddGrad for DEVICE_GPU on B200 (NHWC-native; data_format NCHW -- GPU-only in the
+// reference too, bias_op.cc:242-299 -- transposes 4-D activations in and out).
 // Validation follows BiasOp::Compute (core/kernels/bias_op.cc:62-117) and BiasGradOp::Compute
 // (:185-227); launches replace BiasGPU / BiasGradGPU (bias_op_gpu.cu.cc:69-88,189-242).
 #include "tensorflow/core/kernels/gpu_kernel_util.h"
@@ -6,11 +7,14 @@
 
 namespace tensorflow {
 
-static Status RequireNHWC(OpKernelConstruction* ctx, const char* op) {
+static Status ReadFormat(OpKernelConstruction* ctx, bool* nchw) {
   std::string data_format;
-  if (ctx->GetAttr("data_format", &data_format).ok() && data_format != "NHWC")
-    return errors::Unimplemented(op, " on B200 supports only the NHWC data_format (the CPU "
-                                 "kernel the oracle follows is NHWC-only too, bias_op.cc:54-55)");
+  *nchw = false;
+  if (ctx->GetAttr("data_format", &data_format).ok()) {
+    TensorFormat fmt;
+    if (!FormatFromString(data_format, &fmt)) return errors::InvalidArgument("Invalid data format");
+    *nchw = fmt == FORMAT_NCHW;
+  }
   return Status::OK();
 }
 
@@ -18,7 +22,7 @@ template <typename T>
 class BiasOp : public OpKernel {
  public:
   explicit BiasOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
-    OP_REQUIRES_OK(ctx, RequireNHWC(ctx, "BiasAdd"));
+    OP_REQUIRES_OK(ctx, ReadFormat(ctx, &nchw_));
   }
   void Compute(OpKernelContext* ctx) override {
     const Tensor& input = ctx->input(0);
@@ -28,6 +32,26 @@ class BiasOp : public OpKernel {
                                         input.shape().DebugString()));
     OP_REQUIRES(ctx, TensorShapeUtils::IsVector(bias.shape()),
                 errors::InvalidArgument("Biases must be 1D: ", bias.shape().DebugString()));
+    if (nchw_ && input.dims() > 2) {  // channel = dimension 1
+      OP_REQUIRES(ctx, input.dims() == 4,
+                  errors::Unimplemented("NCHW BiasAdd on B200 takes 2-D or 4-D inputs"));
+      OP_REQUIRES(ctx, bias.dim_size(0) == input.dim_size(1),
+                  errors::InvalidArgument("Must provide as many biases as the channel dimension "
+                                          "of the input tensor: ", bias.shape().DebugString(),
+                                          " vs. ", input.shape().DebugString()));
+      Tensor* output = nullptr;
+      OP_REQUIRES_OK(ctx, ctx->allocate_output(0, input.shape(), &output));
+      if (input.NumElements() == 0) return;
+      Tensor nhwc;
+      OP_REQUIRES_OK(ctx, NchwToNhwc<T>(ctx, input, &nhwc));
+      const int64 channels = input.dim_size(1);
+      OP_REQUIRES_OK(ctx, FromAbi(b200_bias_add(AbiType<T>::v, nhwc.raw_data(), bias.raw_data(),
+                                                nhwc.raw_data(), nhwc.NumElements() / channels,
+                                                channels, GetCudaStream(ctx)),
+                                  "BiasAdd"));
+      OP_REQUIRES_OK(ctx, NhwcToNchw<T>(ctx, nhwc, output));
+      return;
+    }
     const int64 channels = input.dim_size(input.dims() - 1);
     OP_REQUIRES(ctx, bias.dim_size(0) == channels,
                 errors::InvalidArgument("Must provide as many biases as the last dimension of the "
@@ -41,19 +65,37 @@ class BiasOp : public OpKernel {
                                               channels, GetCudaStream(ctx)),
                                 "BiasAdd"));
   }
+
+ private:
+  bool nchw_;
 };
 
 template <typename T>
 class BiasGradOp : public OpKernel {
  public:
   explicit BiasGradOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
-    OP_REQUIRES_OK(ctx, RequireNHWC(ctx, "BiasAddGrad"));
+    OP_REQUIRES_OK(ctx, ReadFormat(ctx, &nchw_));
   }
   void Compute(OpKernelContext* ctx) override {
-    const Tensor& g = ctx->input(0);
+    Tensor g = ctx->input(0);
     OP_REQUIRES(ctx, TensorShapeUtils::IsMatrixOrHigher(g.shape()),
                 errors::InvalidArgument("Input tensor must be at least 2D: ",
                                         g.shape().DebugString()));
+    if (nchw_ && g.dims() > 2) {
+      OP_REQUIRES(ctx, g.dims() == 4,
+                  errors::Unimplemented("NCHW BiasAddGrad on B200 takes 2-D or 4-D inputs"));
+      if (g.NumElements() > 0) {
+        OP_REQUIRES_OK(ctx, NchwToNhwc<T>(ctx, ctx->input(0), &g));
+      } else {
+        Tensor* output = nullptr;
+        OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({g.dim_size(1)}), &output));
+        if (output->NumElements() > 0)
+          OP_REQUIRES_OK(ctx, FromAbi(b200_memset_async(output->raw_data(), 0, output->TotalBytes(),
+                                                        GetCudaStream(ctx)),
+                                      "BiasAddGrad"));
+        return;
+      }
+    }
     const int64 channels = g.dim_size(g.dims() - 1);
     Tensor* output = nullptr;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({channels}), &output));
@@ -67,6 +109,9 @@ class BiasGradOp : public OpKernel {
                                                    ws, GetCudaStream(ctx)),
                                 "BiasAddGrad"));
   }
+
+ private:
+  bool nchw_;
 };
 
 #define REGISTER_GPU(T)                                                                     \

@@ -1,4 +1,5 @@
-// Conv2D / Conv2DBackpropInput / Conv2DBackpropFilter for DEVICE_GPU on B200 (NHWC, HWIO).
+// Conv2D / Conv2DBackpropInput / Conv2DBackpropFilter for DEVICE_GPU on B200 (NHWC-native, HWIO;
+// data_format NCHW is served by transposing the activations in and out, gpu_kernel_util.h).
 // Attr and shape validation follows Conv2DOp (core/kernels/conv_ops.cc:244-391),
 // Conv2DSlowBackpropInputOp (conv_grad_input_ops.cc:533-917) and Conv2DSlowBackpropFilterOp
 // (conv_grad_filter_ops.cc:361-738) with ConvBackpropComputeDimensions (conv_grad_ops.cc:37-126);
@@ -14,19 +15,19 @@ namespace tensorflow {
 namespace {
 
 struct ConvAttrs {
-  std::vector<int32> strides;
+  std::vector<int32> strides;  // always in NHWC order after Init()
   Padding padding;
+  bool nchw = false;
   Status Init(OpKernelConstruction* context) {
     TF_RETURN_IF_ERROR(context->GetAttr("strides", &strides));
     std::string data_format;
     TF_RETURN_IF_ERROR(context->GetAttr("data_format", &data_format));
     TensorFormat fmt;
     if (!FormatFromString(data_format, &fmt)) return errors::InvalidArgument("Invalid data format");
-    if (fmt != FORMAT_NHWC)
-      return errors::Unimplemented("The B200 convolution kernels are NHWC-native; NCHW graphs "
-                                   "need a Transpose (SURVEY 8f rank 4)");
+    nchw = fmt == FORMAT_NCHW;
     if (strides.size() != 4)
       return errors::InvalidArgument("Sliding window strides field must specify 4 dimensions");
+    if (nchw) strides = {strides[0], strides[2], strides[3], strides[1]};  // N C H W -> N H W C
     if (strides[0] != 1 || strides[3] != 1)
       return errors::InvalidArgument("Current implementation does not yet support strides in the "
                                      "batch and depth dimensions.");
@@ -109,23 +110,34 @@ class Conv2DOp : public OpKernel {
     OP_REQUIRES_OK(context, attrs_.Init(context));
   }
   void Compute(OpKernelContext* context) override {
-    const Tensor& input = context->input(0);
+    Tensor input = context->input(0);
     const Tensor& filter = context->input(1);
+    OP_REQUIRES(context, input.dims() == 4,
+                errors::InvalidArgument("input must be 4-dimensional", input.shape().DebugString()));
+    const bool nchw = attrs_.nchw && input.NumElements() > 0;
+    if (nchw) OP_REQUIRES_OK(context, NchwToNhwc<T>(context, context->input(0), &input));
+    const TensorShape in_nhwc = attrs_.nchw && !nchw ? NchwToNhwcShape(input.shape()) : input.shape();
     b200_conv2d_geometry g;
-    TensorShape out_shape;
-    OP_REQUIRES_OK(context, MakeGeometry("Conv2D", input.shape(), filter.shape(), nullptr, attrs_,
-                                         &g, &out_shape));
+    TensorShape out_shape;  // NHWC
+    OP_REQUIRES_OK(context, MakeGeometry("Conv2D", in_nhwc, filter.shape(), nullptr, attrs_, &g,
+                                         &out_shape));
     Tensor* output = nullptr;
-    OP_REQUIRES_OK(context, context->allocate_output(0, out_shape, &output));
+    OP_REQUIRES_OK(context, context->allocate_output(
+                                0, attrs_.nchw ? NhwcToNchwShape(out_shape) : out_shape, &output));
     if (out_shape.num_elements() == 0) return;  // conv_ops.cc:357-359
+    Tensor out_nhwc;
+    if (attrs_.nchw)
+      OP_REQUIRES_OK(context, context->allocate_temp(output->dtype(), out_shape, &out_nhwc));
     const size_t ws = b200_conv2d_workspace_bytes(AbiType<T>::v, &g, 0);
     Tensor scratch;
     OP_REQUIRES_OK(context, Scratch(context, ws, &scratch));
     OP_REQUIRES_OK(context,
                    FromAbi(b200_conv2d(AbiType<T>::v, input.raw_data(), filter.raw_data(),
-                                       output->raw_data(), &g, ws ? scratch.raw_data() : nullptr,
-                                       ws, GetCudaStream(context)),
+                                       attrs_.nchw ? out_nhwc.raw_data() : output->raw_data(), &g,
+                                       ws ? scratch.raw_data() : nullptr, ws,
+                                       GetCudaStream(context)),
                            "Conv2D"));
+    if (attrs_.nchw) OP_REQUIRES_OK(context, NhwcToNchw<T>(context, out_nhwc, output));
   }
 
  private:
@@ -141,25 +153,37 @@ class Conv2DBackpropInputOp : public OpKernel {
   void Compute(OpKernelContext* context) override {
     const Tensor& input_sizes = context->input(0);  // host memory
     const Tensor& filter = context->input(1);
-    const Tensor& out_backprop = context->input(2);
-    TensorShape input_shape;
+    Tensor out_backprop = context->input(2);
+    TensorShape input_shape;  // as given: data_format order
     OP_REQUIRES_OK(context, ShapeFromHostVector(input_sizes, "input_sizes", &input_shape));
+    OP_REQUIRES(context, input_shape.dims() == 4 && out_backprop.dims() == 4,
+                errors::InvalidArgument("Conv2DBackpropInput: input_sizes and out_backprop must be "
+                                        "4-dimensional"));
+    const TensorShape in_nhwc = attrs_.nchw ? NchwToNhwcShape(input_shape) : input_shape;
+    const bool nchw = attrs_.nchw && out_backprop.NumElements() > 0;
+    if (nchw) OP_REQUIRES_OK(context, NchwToNhwc<T>(context, context->input(2), &out_backprop));
+    const TensorShape dy_nhwc =
+        attrs_.nchw && !nchw ? NchwToNhwcShape(out_backprop.shape()) : out_backprop.shape();
     b200_conv2d_geometry g;
     TensorShape out_shape;
-    OP_REQUIRES_OK(context, MakeGeometry("Conv2DBackpropInput", input_shape, filter.shape(),
-                                         &out_backprop.shape(), attrs_, &g, &out_shape));
+    OP_REQUIRES_OK(context, MakeGeometry("Conv2DBackpropInput", in_nhwc, filter.shape(), &dy_nhwc,
+                                         attrs_, &g, &out_shape));
     Tensor* in_backprop = nullptr;
     OP_REQUIRES_OK(context, context->allocate_output(0, input_shape, &in_backprop));
     if (input_shape.num_elements() == 0) return;
+    Tensor dx_nhwc;
+    if (attrs_.nchw)
+      OP_REQUIRES_OK(context, context->allocate_temp(in_backprop->dtype(), in_nhwc, &dx_nhwc));
     const size_t ws = b200_conv2d_workspace_bytes(AbiType<T>::v, &g, 1);
     Tensor scratch;
     OP_REQUIRES_OK(context, Scratch(context, ws, &scratch));
     OP_REQUIRES_OK(context, FromAbi(b200_conv2d_backprop_input(
                                         AbiType<T>::v, filter.raw_data(), out_backprop.raw_data(),
-                                        in_backprop->raw_data(), &g,
-                                        ws ? scratch.raw_data() : nullptr, ws,
+                                        attrs_.nchw ? dx_nhwc.raw_data() : in_backprop->raw_data(),
+                                        &g, ws ? scratch.raw_data() : nullptr, ws,
                                         GetCudaStream(context)),
                                     "Conv2DBackpropInput"));
+    if (attrs_.nchw) OP_REQUIRES_OK(context, NhwcToNchw<T>(context, dx_nhwc, in_backprop));
   }
 
  private:
@@ -173,15 +197,27 @@ class Conv2DBackpropFilterOp : public OpKernel {
     OP_REQUIRES_OK(context, attrs_.Init(context));
   }
   void Compute(OpKernelContext* context) override {
-    const Tensor& input = context->input(0);
+    Tensor input = context->input(0);
     const Tensor& filter_sizes = context->input(1);  // host memory
-    const Tensor& out_backprop = context->input(2);
+    Tensor out_backprop = context->input(2);
     TensorShape filter_shape;
     OP_REQUIRES_OK(context, ShapeFromHostVector(filter_sizes, "filter_sizes", &filter_shape));
+    OP_REQUIRES(context, input.dims() == 4 && out_backprop.dims() == 4,
+                errors::InvalidArgument("Conv2DBackpropFilter: input and out_backprop must be "
+                                        "4-dimensional"));
+    TensorShape x_nhwc = input.shape(), dy_nhwc = out_backprop.shape();
+    if (attrs_.nchw) {
+      x_nhwc = NchwToNhwcShape(input.shape());
+      dy_nhwc = NchwToNhwcShape(out_backprop.shape());
+      if (input.NumElements() > 0)
+        OP_REQUIRES_OK(context, NchwToNhwc<T>(context, context->input(0), &input));
+      if (out_backprop.NumElements() > 0)
+        OP_REQUIRES_OK(context, NchwToNhwc<T>(context, context->input(2), &out_backprop));
+    }
     b200_conv2d_geometry g;
     TensorShape out_shape;
-    OP_REQUIRES_OK(context, MakeGeometry("Conv2DBackpropFilter", input.shape(), filter_shape,
-                                         &out_backprop.shape(), attrs_, &g, &out_shape));
+    OP_REQUIRES_OK(context, MakeGeometry("Conv2DBackpropFilter", x_nhwc, filter_shape, &dy_nhwc,
+                                         attrs_, &g, &out_shape));
     Tensor* filter_backprop = nullptr;
     OP_REQUIRES_OK(context, context->allocate_output(0, filter_shape, &filter_backprop));
     if (filter_shape.num_elements() == 0) return;

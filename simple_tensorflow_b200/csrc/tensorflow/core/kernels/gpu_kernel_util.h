@@ -32,5 +32,33 @@ template <> struct AbiType<int64> { static constexpr int v = B200_DT_INT64; };
 
 #define REGISTER_B200_FLOAT_TYPES(M) M(float) M(bfloat16)
 
+// ---- data_format = "NCHW": the kernels of this library are NHWC-native, so an NCHW op transposes
+// its activations on the way in and out (what the reference's GPU kernels do in the other
+// direction around cuDNN, conv_ops.cc:558-612,712-719).
+inline TensorShape NchwToNhwcShape(const TensorShape& s) {
+  return TensorShape({s.dim_size(0), s.dim_size(2), s.dim_size(3), s.dim_size(1)});
+}
+inline TensorShape NhwcToNchwShape(const TensorShape& s) {
+  return TensorShape({s.dim_size(0), s.dim_size(3), s.dim_size(1), s.dim_size(2)});
+}
+// nchw [N, C, H, W] -> *nhwc (allocate_temp) [N, H, W, C]
+template <typename T>
+Status NchwToNhwc(OpKernelContext* ctx, const Tensor& nchw, Tensor* nhwc) {
+  if (nchw.dims() != 4) return errors::InvalidArgument("NCHW tensors must be 4-dimensional");
+  TF_RETURN_IF_ERROR(ctx->allocate_temp(nchw.dtype(), NchwToNhwcShape(nchw.shape()), nhwc));
+  return FromAbi(b200_batched_transpose(AbiType<T>::v, nchw.raw_data(), nhwc->raw_data(),
+                                        nchw.dim_size(0), nchw.dim_size(1),
+                                        nchw.dim_size(2) * nchw.dim_size(3), GetCudaStream(ctx)),
+                 "NCHW->NHWC");
+}
+// nhwc [N, H, W, C] -> nchw (already allocated) [N, C, H, W]
+template <typename T>
+Status NhwcToNchw(OpKernelContext* ctx, const Tensor& nhwc, Tensor* nchw) {
+  return FromAbi(b200_batched_transpose(AbiType<T>::v, nhwc.raw_data(), nchw->raw_data(),
+                                        nhwc.dim_size(0), nhwc.dim_size(1) * nhwc.dim_size(2),
+                                        nhwc.dim_size(3), GetCudaStream(ctx)),
+                 "NHWC->NCHW");
+}
+
 }  // namespace tensorflow
 #endif

@@ -1,4 +1,5 @@
-// MaxPool / MaxPoolGrad for DEVICE_GPU on B200 (NHWC, spatial pooling).
+// MaxPool / MaxPoolGrad for DEVICE_GPU on B200 (NHWC-native, spatial pooling; data_format NCHW
+// -- which the reference registers for GPU only, maxpooling_op.cc:341-404 -- transposes in and out).
 // Parameter checks follow MaxPoolingOp / PoolParameters (core/kernels/pooling_ops_common.h:73-130,
 // pooling_ops_common.cc:31-90) and MaxPoolingGradOp (core/kernels/maxpooling_op.cc:230-306).
 #include "tensorflow/core/kernels/gpu_kernel_util.h"
@@ -10,10 +11,14 @@ namespace {
 struct PoolAttrs {
   std::vector<int32> ksize, stride;
   Padding padding;
+  bool nchw = false;
   Status Init(OpKernelConstruction* context) {
     std::string data_format;
-    if (context->GetAttr("data_format", &data_format).ok() && data_format != "NHWC")
-      return errors::InvalidArgument("Default MaxPoolingOp only supports NHWC.");
+    if (context->GetAttr("data_format", &data_format).ok()) {
+      TensorFormat fmt;
+      if (!FormatFromString(data_format, &fmt)) return errors::InvalidArgument("Invalid data format");
+      nchw = fmt == FORMAT_NCHW;
+    }
     TF_RETURN_IF_ERROR(context->GetAttr("ksize", &ksize));
     if (ksize.size() != 4)
       return errors::InvalidArgument("Sliding window ksize field must specify 4 dimensions");
@@ -21,6 +26,10 @@ struct PoolAttrs {
     if (stride.size() != 4)
       return errors::InvalidArgument("Sliding window stride field must specify 4 dimensions");
     TF_RETURN_IF_ERROR(context->GetAttr("padding", &padding));
+    if (nchw) {  // N C H W -> N H W C
+      ksize = {ksize[0], ksize[2], ksize[3], ksize[1]};
+      stride = {stride[0], stride[2], stride[3], stride[1]};
+    }
     if (ksize[0] != 1 || stride[0] != 1)
       return errors::Unimplemented("Pooling is not yet supported on the batch dimension.");
     if (ksize[3] != 1 || stride[3] != 1)
@@ -54,13 +63,25 @@ class MaxPoolingOp : public OpKernel {
     OP_REQUIRES_OK(context, attrs_.Init(context));
   }
   void Compute(OpKernelContext* context) override {
-    const Tensor& tensor_in = context->input(0);
+    Tensor tensor_in = context->input(0);
+    OP_REQUIRES(context, tensor_in.dims() == 4,
+                errors::InvalidArgument("tensor_in must be 4-dimensional"));
+    const TensorShape in_nhwc =
+        attrs_.nchw ? NchwToNhwcShape(tensor_in.shape()) : tensor_in.shape();
     PoolDims d;
-    OP_REQUIRES_OK(context, ComputePoolDims(tensor_in.shape(), attrs_, &d));
-    Tensor* output = nullptr;
+    OP_REQUIRES_OK(context, ComputePoolDims(in_nhwc, attrs_, &d));
+    const TensorShape out_nhwc({d.batch, d.out_rows, d.out_cols, d.depth});
+    Tensor* result = nullptr;
     OP_REQUIRES_OK(context, context->allocate_output(
-                                0, TensorShape({d.batch, d.out_rows, d.out_cols, d.depth}), &output));
-    if (output->NumElements() == 0) return;
+                                0, attrs_.nchw ? NhwcToNchwShape(out_nhwc) : out_nhwc, &result));
+    if (result->NumElements() == 0) return;
+    Tensor pooled_nhwc;
+    Tensor* output = result;
+    if (attrs_.nchw) {
+      OP_REQUIRES_OK(context, NchwToNhwc<T>(context, context->input(0), &tensor_in));
+      OP_REQUIRES_OK(context, context->allocate_temp(result->dtype(), out_nhwc, &pooled_nhwc));
+      output = &pooled_nhwc;
+    }
     OP_REQUIRES_OK(context,
                    FromAbi(b200_max_pool(AbiType<T>::v, tensor_in.raw_data(), output->raw_data(),
                                          d.batch, d.rows, d.cols, d.depth, d.out_rows, d.out_cols,
@@ -68,6 +89,7 @@ class MaxPoolingOp : public OpKernel {
                                          attrs_.stride[2], (int)d.pad_rows, (int)d.pad_cols,
                                          GetCudaStream(context)),
                            "MaxPool"));
+    if (attrs_.nchw) OP_REQUIRES_OK(context, NhwcToNchw<T>(context, pooled_nhwc, result));
   }
 
  private:
@@ -81,32 +103,47 @@ class MaxPoolingGradOp : public OpKernel {
     OP_REQUIRES_OK(context, attrs_.Init(context));
   }
   void Compute(OpKernelContext* context) override {
-    const Tensor& tensor_in = context->input(0);
-    const Tensor& tensor_out = context->input(1);
-    const Tensor& out_backprop = context->input(2);
+    Tensor tensor_in = context->input(0);
+    Tensor tensor_out = context->input(1);
+    Tensor out_backprop = context->input(2);
     OP_REQUIRES(context, tensor_in.dims() == 4,
                 errors::InvalidArgument("tensor_in must be 4-dimensional"));
     OP_REQUIRES(context, tensor_out.dims() == 4,
                 errors::InvalidArgument("tensor_out must be 4-dimensional"));
     OP_REQUIRES(context, out_backprop.dims() == 4,
                 errors::InvalidArgument("out_backprop must be 4-dimensional"));
+    const TensorShape in_nhwc =
+        attrs_.nchw ? NchwToNhwcShape(tensor_in.shape()) : tensor_in.shape();
+    const TensorShape dy_nhwc =
+        attrs_.nchw ? NchwToNhwcShape(out_backprop.shape()) : out_backprop.shape();
     PoolDims d;
-    OP_REQUIRES_OK(context, ComputePoolDims(tensor_in.shape(), attrs_, &d));
+    OP_REQUIRES_OK(context, ComputePoolDims(in_nhwc, attrs_, &d));
     const TensorShape expect({d.batch, d.out_rows, d.out_cols, d.depth});
-    OP_REQUIRES(context, out_backprop.shape() == expect,
+    OP_REQUIRES(context, dy_nhwc == expect,
                 errors::InvalidArgument("out_backprop shape ", out_backprop.shape().DebugString(),
                                         " does not match the pooled shape ", expect.DebugString()));
-    Tensor* output = nullptr;
-    OP_REQUIRES_OK(context, context->allocate_output(0, tensor_in.shape(), &output));
-    if (output->NumElements() == 0) return;
+    Tensor* result = nullptr;
+    OP_REQUIRES_OK(context, context->allocate_output(0, tensor_in.shape(), &result));
+    if (result->NumElements() == 0) return;
+    Tensor dx_nhwc;
+    Tensor* output = result;
+    if (attrs_.nchw) {
+      OP_REQUIRES_OK(context, NchwToNhwc<T>(context, context->input(0), &tensor_in));
+      OP_REQUIRES_OK(context, NchwToNhwc<T>(context, context->input(2), &out_backprop));
+      OP_REQUIRES_OK(context, context->allocate_temp(result->dtype(), in_nhwc, &dx_nhwc));
+      output = &dx_nhwc;
+    }
     OP_REQUIRES_OK(context, FromAbi(b200_max_pool_grad(
-                                        AbiType<T>::v, tensor_in.raw_data(), tensor_out.raw_data(),
+                                        AbiType<T>::v, tensor_in.raw_data(),
+                                        attrs_.nchw ? nullptr : tensor_out.raw_data(),  // unused by the kernel
+                                       
                                         out_backprop.raw_data(), output->raw_data(), d.batch,
                                         d.rows, d.cols, d.depth, d.out_rows, d.out_cols,
                                         attrs_.ksize[1], attrs_.ksize[2], attrs_.stride[1],
                                         attrs_.stride[2], (int)d.pad_rows, (int)d.pad_cols,
                                         GetCudaStream(context)),
                                     "MaxPoolGrad"));
+    if (attrs_.nchw) OP_REQUIRES_OK(context, NhwcToNchw<T>(context, dx_nhwc, result));
   }
 
  private:

@@ -143,9 +143,10 @@ def batch_matmul(x, y, adj_x=False, adj_y=False, name=None):
     return _set_shape(op.outputs[0], shape)
 
 
-def bias_add(value, bias, name=None):
+def bias_add(value, bias, data_format="NHWC", name=None):
     value, bias = _val(value), _val(bias)
-    op = _g(value).create_op("BiasAdd", [value, bias], {"T": ("type", value.dtype)},
+    op = _g(value).create_op("BiasAdd", [value, bias],
+                             {"T": ("type", value.dtype), "data_format": data_format},
                              name or "BiasAdd")
     return _set_shape(op.outputs[0], _shape(value))
 
@@ -183,29 +184,45 @@ def _windowed(in_size, filt, stride, padding):
     return (in_size + stride - 1) // stride
 
 
-def conv2d(input, filter, strides, padding, name=None):  # noqa: A002 (reference arg names)
+def _hw(data_format):
+    """Positions of (H, W, C) in a 4-D activation of this data_format."""
+    if data_format == "NCHW":
+        return 2, 3, 1
+    if data_format == "NHWC":
+        return 1, 2, 3
+    raise ValueError("data_format must be NHWC or NCHW")
+
+
+def _spatial(shape, out_h, out_w, channels, data_format):
+    return (shape[0], channels, out_h, out_w) if data_format == "NCHW" else (shape[0], out_h, out_w,
+                                                                             channels)
+
+
+def conv2d(input, filter, strides, padding, data_format="NHWC", name=None):  # noqa: A002
     input, filter = _val(input), _val(filter)
+    h, w, _ = _hw(data_format)
     op = _g(input).create_op("Conv2D", [input, filter],
                              {"T": ("type", input.dtype), "strides": ("ints", list(strides)),
-                              "padding": padding}, name or "Conv2D")
+                              "padding": padding, "data_format": data_format}, name or "Conv2D")
     si, sf = _shape(input), _shape(filter)
     shape = None
     if si and sf:
-        shape = (si[0], _windowed(si[1], sf[0], strides[1], padding),
-                 _windowed(si[2], sf[1], strides[2], padding), sf[3])
+        shape = _spatial(si, _windowed(si[h], sf[0], strides[h], padding),
+                         _windowed(si[w], sf[1], strides[w], padding), sf[3], data_format)
     return _set_shape(op.outputs[0], shape)
 
 
-def max_pool(value, ksize, strides, padding, name=None):
+def max_pool(value, ksize, strides, padding, data_format="NHWC", name=None):
+    h, w, c = _hw(data_format)
     op = _g(value).create_op("MaxPool", [value],
                              {"T": ("type", value.dtype), "ksize": ("ints", list(ksize)),
-                              "strides": ("ints", list(strides)), "padding": padding},
-                             name or "MaxPool")
+                              "strides": ("ints", list(strides)), "padding": padding,
+                              "data_format": data_format}, name or "MaxPool")
     s = _shape(value)
     shape = None
     if s:
-        shape = (s[0], _windowed(s[1], ksize[1], strides[1], padding),
-                 _windowed(s[2], ksize[2], strides[2], padding), s[3])
+        shape = _spatial(s, _windowed(s[h], ksize[h], strides[h], padding),
+                         _windowed(s[w], ksize[w], strides[w], padding), s[c], data_format)
     return _set_shape(op.outputs[0], shape)
 
 
@@ -374,8 +391,11 @@ def _cast_grad(op, grad):
 @_register_gradient("BiasAdd")
 def _bias_add_grad(op, grad):
     # nn_grad.py:180-204: (received_grad, BiasAddGrad(received_grad))
-    g = op.graph.create_op("BiasAddGrad", [grad], {"T": ("type", grad.dtype)}, "BiasAddGrad")
-    return grad, _set_shape(g.outputs[0], (_shape(grad)[-1],) if _shape(grad) else None)
+    fmt = op.attrs.get("data_format", "NHWC")
+    g = op.graph.create_op("BiasAddGrad", [grad], {"T": ("type", grad.dtype), "data_format": fmt},
+                           "BiasAddGrad")
+    cdim = 1 if fmt == "NCHW" and _shape(grad) and len(_shape(grad)) > 2 else -1
+    return grad, _set_shape(g.outputs[0], (_shape(grad)[cdim],) if _shape(grad) else None)
 
 
 @_register_gradient("Relu")
@@ -404,7 +424,8 @@ def _mean_grad(op, grad):
 def _conv2d_grad(op, grad):
     # nn_grad.py:363-374
     x, w = op.inputs
-    attrs = {"T": ("type", x.dtype), "strides": op.attrs["strides"], "padding": op.attrs["padding"]}
+    attrs = {"T": ("type", x.dtype), "strides": op.attrs["strides"], "padding": op.attrs["padding"],
+             "data_format": op.attrs.get("data_format", "NHWC")}
     g = op.graph
     in_sizes = constant(np.asarray(_shape(x), np.int32), int32)
     f_sizes = constant(np.asarray(_shape(w), np.int32), int32)
@@ -417,7 +438,7 @@ def _conv2d_grad(op, grad):
 def _max_pool_grad(op, grad):
     # nn_grad.py:430-438: MaxPoolGrad(op.inputs[0], op.outputs[0], grad)
     attrs = {"T": ("type", grad.dtype), "ksize": op.attrs["ksize"], "strides": op.attrs["strides"],
-             "padding": op.attrs["padding"]}
+             "padding": op.attrs["padding"], "data_format": op.attrs.get("data_format", "NHWC")}
     g = op.graph.create_op("MaxPoolGrad", [op.inputs[0], op.outputs[0], grad], attrs, "MaxPoolGrad")
     return (_set_shape(g.outputs[0], _shape(op.inputs[0])),)
 

@@ -526,6 +526,21 @@ def test_apply_gradient_descent_add_n_scale_sum(oracle, rng):
     np.testing.assert_allclose(au.host(tot)[0], delta.astype(np.float64).mean(), rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("shape", [(3, 32, 49), (2, 1, 5), (4, 96, 1000), (1, 33, 31), (5, 7, 1)])
+def test_batched_transpose_bit_exact(rng, shape):
+    # pure data movement: the NCHW <-> NHWC layout change must be bit-exact (fp32 and bf16)
+    L = au.lib()
+    b, r, c = shape
+    x = rng.randn(*shape).astype(np.float32)
+    dx, out = au.dev(x), au.empty((b, c, r))
+    au.call(L.b200_batched_transpose, 1, dx.data_ptr(), out.data_ptr(), b, r, c, au.stream())
+    np.testing.assert_array_equal(au.host(out), np.swapaxes(x, 1, 2))
+    xb = au.dev(x, True)
+    outb = au.empty((b, c, r), au.tdt(True))
+    au.call(L.b200_batched_transpose, 14, xb.data_ptr(), outb.data_ptr(), b, r, c, au.stream())
+    np.testing.assert_array_equal(au.host(outb), np.swapaxes(au.host(xb), 1, 2))
+
+
 def test_stream_event_memcpy_shim():
     import ctypes
     L = au.lib()
