@@ -188,7 +188,27 @@ int b200_peer_arena_create(void* nccl_comm, int rank, int nranks, size_t data_by
   }
   int rc = require_device("b200_peer_arena_create");
   if (rc) return rc;
+  // owns the arena record, this rank's buffer and the handle scratch until creation succeeded
+  struct Guard {
+    PeerArena* a = nullptr;
+    char* local = nullptr;
+    void* scratch = nullptr;
+    void* vote = nullptr;
+    ~Guard() {
+      if (scratch) cudaFree(scratch);
+      if (vote) cudaFree(vote);
+      if (a) {
+        for (int p = 0; p < a->table.nranks; ++p)
+          if (p != a->table.rank && a->table.base[p]) cudaIpcCloseMemHandle(a->table.base[p]);
+        delete a;
+      }
+      if (local) cudaFree(local);
+      cudaGetLastError();
+    }
+  } guard;
   PeerArena* a = new PeerArena();
+  guard.a = a;
+  memset(&a->table, 0, sizeof(a->table));
   PEER_CUDA(cudaGetDevice(&a->device), "cudaGetDevice");
   a->data_bytes = (data_bytes + 255) / 256 * 256;
   a->table.rank = rank;
@@ -196,7 +216,7 @@ int b200_peer_arena_create(void* nccl_comm, int rank, int nranks, size_t data_by
   const size_t total = kHeaderBytes + a->data_bytes;
   char* local = nullptr;
   cudaIpcMemHandle_t mine;
-  int ok = cudaMalloc(&local, total) == cudaSuccess &&
+  int ok = cudaMalloc(&local, total) == cudaSuccess && (guard.local = local) != nullptr &&
            cudaMemset(local, 0, total) == cudaSuccess &&
            cudaIpcGetMemHandle(&mine, local) == cudaSuccess &&
            cudaDeviceSynchronize() == cudaSuccess;
@@ -215,6 +235,7 @@ int b200_peer_arena_create(void* nccl_comm, int rank, int nranks, size_t data_by
   my_slot.ok = ok;
   Slot* dev_slots = nullptr;
   PEER_CUDA(cudaMalloc(&dev_slots, sizeof(Slot) * (kMaxRanks + 1)), "cudaMalloc(handles)");
+  guard.scratch = dev_slots;
   PEER_CUDA(cudaMemcpy(dev_slots + kMaxRanks, &my_slot, sizeof(Slot), cudaMemcpyHostToDevice),
             "cudaMemcpy(handle)");
   rc = b200_nccl_all_gather_bytes(dev_slots + kMaxRanks, dev_slots, sizeof(Slot), nccl_comm, nullptr);
@@ -223,7 +244,6 @@ int b200_peer_arena_create(void* nccl_comm, int rank, int nranks, size_t data_by
     PEER_CUDA(cudaMemcpy(host_slots, dev_slots, sizeof(Slot) * nranks, cudaMemcpyDeviceToHost),
               "cudaMemcpy(handles)");
   }
-  cudaFree(dev_slots);
   bool all_ok = rc == B200_OK;
   for (int p = 0; all_ok && p < nranks; ++p) all_ok = host_slots[p].ok != 0;
   // map the peers; a rank that cannot must tell the others, hence a second vote
@@ -245,6 +265,7 @@ int b200_peer_arena_create(void* nccl_comm, int rank, int nranks, size_t data_by
   if (rc == B200_OK) {  // everybody reaches this collective whatever happened above
     float* vote = nullptr;
     PEER_CUDA(cudaMalloc(&vote, sizeof(float)), "cudaMalloc(vote)");
+    guard.vote = vote;
     const float v = mapped ? 1.f : 0.f;
     PEER_CUDA(cudaMemcpy(vote, &v, sizeof(float), cudaMemcpyHostToDevice), "vote");
     rc = b200_nccl_all_reduce_sum(B200_DT_FLOAT, vote, vote, 1, nccl_comm, nullptr);
@@ -253,20 +274,16 @@ int b200_peer_arena_create(void* nccl_comm, int rank, int nranks, size_t data_by
       PEER_CUDA(cudaDeviceSynchronize(), "vote");
       PEER_CUDA(cudaMemcpy(&sum, vote, sizeof(float), cudaMemcpyDeviceToHost), "vote");
     }
-    cudaFree(vote);
     if (rc != B200_OK || (int)(sum + 0.5f) != nranks) mapped = 0;
   } else {
     mapped = 0;
   }
   if (!mapped) {
-    for (int p = 0; p < nranks; ++p)
-      if (p != rank && a->table.base[p]) cudaIpcCloseMemHandle(a->table.base[p]);
-    if (local) cudaFree(local);
-    delete a;
-    cudaGetLastError();
     set_last_error("b200_peer_arena_create: peer mapping unavailable on at least one rank");
-    return B200_UNAVAILABLE;
+    return B200_UNAVAILABLE;  // the guard releases everything
   }
+  guard.a = nullptr;      // success: the caller owns the arena (and through it the buffer)
+  guard.local = nullptr;
   *out = a;
   return B200_OK;
 }

@@ -865,6 +865,14 @@ Status DirectSession::StageFeed(const Tensor& host, Tensor* staged) {
   st.host = host;
   Tensor dev;
   TF_RETURN_IF_ERROR(device_->StageTensorFromHost(host, &dev, st.ready.get()));
+  // An entry whose copy has completed has served both purposes (ordering and keeping the pinned
+  // source alive): drop it, so staged tensors that are deleted without being fed leave nothing.
+  for (auto it = staged_.begin(); it != staged_.end();) {
+    if (it->second.ready->PollForStatus() == gpu::Event::Status::kComplete)
+      it = staged_.erase(it);
+    else
+      ++it;
+  }
   staged_[dev.buffer()] = std::move(st);  // a stale entry for a recycled buffer is replaced
   *staged = std::move(dev);
   return Status::OK();

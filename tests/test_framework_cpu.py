@@ -130,6 +130,58 @@ def test_gradient_graph_matches_reference_rules():
     assert {c.type for c in train.control_inputs} == {"ApplyGradientDescent"}
 
 
+def _mlp(widths):
+    tf.reset_default_graph()
+    x = tf.placeholder(tf.float32, [8, widths[0]], "x")
+    lab = tf.placeholder(tf.float32, [8, widths[-1]], "labels")
+    Ws = [tf.Variable(np.zeros((a, b), np.float32), name="W%d" % i)
+          for i, (a, b) in enumerate(zip(widths[:-1], widths[1:]))]
+    Bs = [tf.Variable(np.zeros(b, np.float32), name="b%d" % i) for i, b in enumerate(widths[1:])]
+    h = x
+    for i, (w, b) in enumerate(zip(Ws, Bs)):
+        h = tf.bias_add(tf.matmul(h, w), b)
+        if i < len(Ws) - 1:
+            h = tf.relu(h)
+    return tf.reduce_mean(tf.softmax_cross_entropy_with_logits(h, lab)), Ws, Bs
+
+
+def test_replica_gradient_exchange_graph():
+    # num_replicas > 1: gradients go through B200AllReduceN (scale 1/p) before the updates;
+    # default = one collective over everything, bucket_bytes = size-capped buckets filled in the
+    # order backprop emits the gradients (last layer first)
+    loss, Ws, Bs = _mlp([64, 512, 512, 16])
+    train = tf.GradientDescentOptimizer(0.1).minimize(loss, Ws + Bs, num_replicas=4)
+    g = tf.get_default_graph()
+    ars = [op for op in g.operations if op.type == "B200AllReduceN"]
+    assert len(ars) == 1 and len(ars[0].inputs) == 6
+    assert abs(ars[0].attrs["scale"] - 0.25) < 1e-9
+    applies = [op for op in g.operations if op.type == "ApplyGradientDescent"]
+    assert len(applies) == 6 and all(a.inputs[2].op is ars[0] for a in applies)
+    # every variable is updated with ITS reduced gradient
+    for a in applies:
+        var = a.inputs[0].op.name
+        src = ars[0].inputs[a.inputs[2].index].op
+        assert (src.type == "BiasAddGrad") == var.startswith("b")
+    assert train.type == "NoOp"
+
+    loss, Ws, Bs = _mlp([64, 512, 512, 16])
+    tf.GradientDescentOptimizer(0.1).minimize(loss, Ws + Bs, num_replicas=2,
+                                              bucket_bytes=256 * 1024)
+    ars = [op for op in tf.get_default_graph().operations if op.type == "B200AllReduceN"]
+    # layer 2 (512x16 = 32 KB + bias) is too small to close a bucket: it rides with layer 1
+    # (512x512 = 1 MB), layer 0 (64x512 = 128 KB + bias) is the tail
+    sizes = [[int(np.prod(g.shapes[i.name])) for i in op.inputs] for op in ars
+             for g in [tf.get_default_graph()]]
+    assert sizes == [[16, 512 * 16, 512, 512 * 512], [512, 64 * 512]], sizes
+    order = [op.inputs[0].op.name for op in ars]
+    assert order[0].startswith("BiasAddGrad")        # the last layer's gradients come first
+
+    # one replica: no collective at all
+    loss, Ws, Bs = _mlp([8, 8])
+    tf.GradientDescentOptimizer(0.1).minimize(loss)
+    assert not [op for op in tf.get_default_graph().operations if op.type.startswith("B200AllReduce")]
+
+
 def test_host_tensor_roundtrip():
     a = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
     t = client.HostTensor.from_numpy(a)

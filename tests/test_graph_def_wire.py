@@ -157,3 +157,136 @@ def test_real_tensorflow_graph_runs_to_the_known_answer():
         # the session is still usable afterwards
         out = sess.run(y, {x: np.zeros((2, 1), np.float32)})
         np.testing.assert_array_equal(out, np.full((2, 1), 2.0, np.float32))
+
+
+# ------------------------------------------------------------------ property test: an independent
+# (test-side, pure Python) protobuf encoder writes random GraphDefs; the C++ reader must see
+# exactly what was written, and re-serialising must not change what it reads.
+def _varint(v):
+    v &= (1 << 64) - 1
+    out = bytearray()
+    while v >= 0x80:
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+    out.append(v)
+    return bytes(out)
+
+
+def _ld(field, payload):
+    return _varint(field << 3 | 2) + _varint(len(payload)) + payload
+
+
+def _enc_attr(kind, v):
+    import struct
+    if kind == "s":
+        return _ld(2, v)
+    if kind == "i":
+        return _varint(3 << 3) + _varint(v)
+    if kind == "f":
+        return _varint(4 << 3 | 5) + struct.pack("<f", v)
+    if kind == "b":
+        return _varint(5 << 3) + _varint(1 if v else 0)
+    if kind == "type":
+        return _varint(6 << 3) + _varint(v)
+    if kind == "shape":
+        return _ld(7, b"".join(_ld(2, (_varint(1 << 3) + _varint(d)) if d else b"") for d in v))
+    if kind == "list_i":     # packed or not: both are legal on the wire
+        packed, vals = v
+        body = _ld(3, b"".join(_varint(x) for x in vals)) if packed else \
+            b"".join(_varint(3 << 3) + _varint(x) for x in vals)
+        return _ld(1, body)
+    if kind == "list_s":
+        return _ld(1, b"".join(_ld(2, x) for x in v))
+    if kind == "tensor_f32":  # float_val form, possibly fewer values than elements
+        shape, vals = v
+        tshape = b"".join(_ld(2, _varint(1 << 3) + _varint(d)) for d in shape)
+        body = _varint(1 << 3) + _varint(1) + _ld(2, tshape)
+        body += _ld(5, b"".join(struct.pack("<f", x) for x in vals))
+        return _ld(8, body)
+    raise AssertionError(kind)
+
+
+def _expect_attr(kind, v):
+    if kind == "s":
+        return "s:" + _quote(v)
+    if kind == "i":
+        return "i:%d" % v
+    if kind == "f":
+        return "f:%.9g" % np.float32(v)
+    if kind == "b":
+        return "b:true" if v else "b:false"
+    if kind == "type":
+        return "type:%d" % v
+    if kind == "shape":
+        return "shape:[%s]" % ",".join(map(str, v))
+    if kind == "list_i":
+        return "list_i:[%s]" % ",".join(map(str, v[1])) if v[1] else None  # empty list: raw
+    if kind == "list_s":
+        return "list_s:[%s]" % ",".join(_quote(x) for x in v) if v else None
+    if kind == "tensor_f32":
+        shape, vals = v
+        n = int(np.prod(shape)) if shape else 1
+        full = ([np.float32(x) for x in vals] + [np.float32(vals[-1])] * n)[:n]
+        return "tensor:1:[%s]:%s" % (",".join(map(str, shape)), ",".join("%.9g" % x for x in full[:8]))
+    raise AssertionError(kind)
+
+
+def _quote(b):
+    out = '"'
+    for c in b:
+        if c in (34, 92):
+            out += "\\" + chr(c)
+        elif c < 32 or c > 126:
+            out += "\\%03o" % c
+        else:
+            out += chr(c)
+    return out + '"'
+
+
+def test_random_graphdefs_read_back_exactly():
+    from hypothesis import given, settings, strategies as st
+    name = st.text(alphabet="abcdefghijklmnopqrstuvwxyz_/0123456789", min_size=1, max_size=12)
+    attr = st.one_of(
+        st.tuples(st.just("s"), st.binary(max_size=12)),
+        st.tuples(st.just("i"), st.integers(-2**63, 2**63 - 1)),
+        st.tuples(st.just("f"), st.floats(width=32, allow_nan=False, allow_infinity=False)),
+        st.tuples(st.just("b"), st.booleans()),
+        st.tuples(st.just("type"), st.sampled_from([1, 2, 3, 7, 9, 14, 19])),
+        st.tuples(st.just("shape"), st.lists(st.integers(0, 10**6), max_size=5)),
+        st.tuples(st.just("list_i"), st.tuples(st.booleans(), st.lists(st.integers(-2**40, 2**40), max_size=6))),
+        st.tuples(st.just("list_s"), st.lists(st.binary(max_size=6), max_size=4)),
+        st.tuples(st.just("tensor_f32"),
+                  st.tuples(st.lists(st.integers(1, 4), max_size=3),
+                            st.lists(st.floats(width=32, allow_nan=False, allow_infinity=False),
+                                     min_size=1, max_size=3))),
+    )
+    node = st.tuples(name, name, st.lists(name, max_size=3), st.sampled_from(["", "/gpu:0"]),
+                     st.dictionaries(st.text(alphabet="abcdefgh_", min_size=1, max_size=6), attr,
+                                     max_size=4))
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(node, max_size=5))
+    def check(nodes):
+        blob = b""
+        for nm, op, inputs, device, attrs in nodes:
+            body = _ld(1, nm.encode()) + _ld(2, op.encode())
+            body += b"".join(_ld(3, i.encode()) for i in inputs)
+            if device:
+                body += _ld(4, device.encode())
+            for k, (kind, v) in attrs.items():
+                body += _ld(5, _ld(1, k.encode()) + _ld(2, _enc_attr(kind, v)))
+            blob += _ld(1, body)
+        blob += _ld(4, b"\x08\x15")   # versions { producer: 21 }: carried verbatim
+        got = _parse_dump(client.graph_def_to_text(blob)) if nodes else []
+        assert len(got) == len(nodes)
+        for g, (nm, op, inputs, device, attrs) in zip(got, nodes):
+            assert (g["name"], g["op"], g["device"], g["input"]) == (nm, op, device, inputs)
+            assert set(g["attr"]) == set(attrs)
+            for k, (kind, v) in attrs.items():
+                want = _expect_attr(kind, v)
+                if want is None:
+                    assert g["attr"][k].startswith("raw:")
+                else:
+                    assert g["attr"][k] == want, (k, kind, v)
+
+    check()
