@@ -31,10 +31,20 @@ class ConvGeom(ctypes.Structure):
 _lib = None
 
 
+XX
+
+
 def build():
+    """(Re)build oracle/_build/liboracle.so when it is missing, older than its source, or was
+    compiled (-march=native) on a different CPU model than the one we are running on."""
     src = os.path.join(ORACLE_DIR, "oracle.c")
-    if (not os.path.exists(ORACLE_SO)) or (
+    stamp = os.path.join(os.path.dirname(ORACLE_SO), "host.txt")
+    built_on = open(stamp).read().strip() if os.path.exists(stamp) else None
+    foreign = built_on is not None and built_on != _host_cpu()
+    if (not os.path.exists(ORACLE_SO)) or foreign or (
             os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(ORACLE_SO)):
+        if foreign:
+            subprocess.check_call(["make", "-C", ORACLE_DIR, "clean"], stdout=subprocess.DEVNULL)
         subprocess.check_call(["make", "-C", ORACLE_DIR], stdout=subprocess.DEVNULL)
 
 
