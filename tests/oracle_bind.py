@@ -31,7 +31,15 @@ class ConvGeom(ctypes.Structure):
 _lib = None
 
 
-XX
+def _host_cpu():
+    """What oracle/Makefile writes to _build/host.txt: CPU model + md5 of the ISA flags line."""
+    try:
+        out = subprocess.run(
+            ["sh", "-c", '(grep -m1 "model name" /proc/cpuinfo; grep -m1 "^flags" /proc/cpuinfo | md5sum)'],
+            capture_output=True, text=True, timeout=10).stdout.strip()
+        return out or "unknown"
+    except Exception:
+        return "unknown"
 
 
 def build():
