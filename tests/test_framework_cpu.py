@@ -29,6 +29,19 @@ def test_abi_header_matches_library_and_binding():
     assert exported == declared, set(exported) ^ set(declared)
 
 
+def test_c_api_header_matches_framework_library():
+    # every TF_* / B200TF_* function the C API header declares is exported by
+    # libb200tf_framework.so, nothing else is, and the Python binding only names real functions
+    text = open(os.path.join(ROOT, "simple_tensorflow_b200", "csrc", "tensorflow", "c",
+                             "c_api.h")).read()
+    declared = sorted(set(re.findall(r"TF_CAPI_EXPORT\s+extern\s+[\w\s\*]+?\b((?:B200)?TF_\w+)\s*\(", text)))
+    assert len(declared) >= 50
+    out = subprocess.check_output(["nm", "-D", "--defined-only", client.FRAMEWORK_PATH]).decode()
+    exported = sorted(set(re.findall(r"\bT ((?:B200)?TF_\w+)", out)))
+    assert exported == declared, set(exported) ^ set(declared)
+    assert set(client._SIGS) <= set(declared), set(client._SIGS) - set(declared)
+
+
 def test_no_vendor_gemm_or_dnn_libraries_linked():
     for path in (_lib.LIB_PATH, client.FRAMEWORK_PATH):
         out = subprocess.check_output(["ldd", path]).decode().lower()
