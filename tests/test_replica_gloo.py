@@ -46,3 +46,27 @@ def test_reference_arm_runs_on_rank0_only():
                           "--gpus", "2", "--steps", "1", "--warmup", "1"], env=env,
                          capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_reference_arm_line_follows_the_bench_contract():
+    """`bench.py --impl reference` (the CPU oracle port on the host cores): ONE JSON line on
+    stdout with the contract's keys, `impl: reference`, zero copy bytes, its own cpu_baseline."""
+    env = dict(os.environ)
+    env.pop("RANK", None)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference",
+                          "--gpus", "1", "--steps", "1", "--warmup", "1"], env=env,
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+                "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config", "e2e",
+                "cpu_baseline"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["unit"] == "samples/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and abs(d["value"] - 4096 * d["steps"] / (d["ms_per_step"] * d["steps"] / 1e3)) < 1e-6 * d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["e2e"]["value"] == d["value"] and d["cpu_baseline"]["value"] == d["value"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert "workload" in d["config"]
