@@ -58,6 +58,12 @@ def test_product_code_never_touches_the_oracle():
             if f.endswith((".py", ".cc", ".cu", ".h", ".cuh")):
                 text = open(os.path.join(base, f), errors="replace").read()
                 assert "oracle_bind" not in text and "liboracle" not in text, os.path.join(base, f)
+    # developer tools are not test infrastructure either: only tests/, smoke() and bench.py's CPU
+    # legs may use the oracle
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith(".py"):
+            text = open(os.path.join(ROOT, "tools", f)).read()
+            assert "oracle_bind" not in text and "liboracle" not in text, f
 
 
 def test_library_loads_without_gpu_and_fails_loudly():
