@@ -65,42 +65,80 @@ API int oracle_windowed_output_size(int64_t input_size, int64_t filter_size, int
 }
 
 /* ---------------------------------------------------------------------------------------------
- * Blocked fp32 GEMM used by MatMul, BatchMatMul and the im2col convolutions.
+ * Blocked, register-tiled fp32 GEMM used by MatMul, BatchMatMul and the im2col convolutions.
  * C[M,N] (+)= A * B with generic element strides, fp32 accumulate (what Eigen's gebp kernel does,
  * matmul_op.h:35-40: out = in0.contract(in1, dim_pair)).  Summation order over k is ascending
  * within a K block and blocks are added in ascending order. */
+/* Register-blocked inner kernel: MR rows x NR columns of C stay in registers over a K block, so
+ * a row of B is loaded once per MR rows (the job of Eigen's gebp micro-kernel).  Per C element
+ * the arithmetic is exactly `c += a * b` for k ascending -- separate multiply and add
+ * (-ffp-contract=off), same order as the plain triple loop it replaces, so results are
+ * bit-identical to it; only the speed of the CPU baseline changes. */
+enum { GEMM_MR = 6, GEMM_NR = 32 };
+static inline void sgemm_micro(const float* A, int64_t a_rs, int64_t a_cs, const float* Bp,
+                               int64_t brs, float* C, int64_t ldc, int64_t kn, int zero_first) {
+  float acc[GEMM_MR][GEMM_NR];
+  for (int r = 0; r < GEMM_MR; ++r)
+    for (int j = 0; j < GEMM_NR; ++j) acc[r][j] = zero_first ? 0.f : C[r * ldc + j];
+  for (int64_t k = 0; k < kn; ++k) {
+    const float* b = Bp + k * brs;
+    for (int r = 0; r < GEMM_MR; ++r) {
+      const float a = A[r * a_rs + k * a_cs];
+      for (int j = 0; j < GEMM_NR; ++j) acc[r][j] += a * b[j];
+    }
+  }
+  for (int r = 0; r < GEMM_MR; ++r)
+    for (int j = 0; j < GEMM_NR; ++j) C[r * ldc + j] = acc[r][j];
+}
+
 static void sgemm_strided(const float* A, int64_t a_rs, int64_t a_cs, const float* B,
                           int64_t b_rs, int64_t b_cs, float* C, int64_t ldc, int64_t M, int64_t N,
                           int64_t K, int accumulate, int parallel) {
-  enum { KB = 256, MB = 64 };
-  const int64_t mblocks = (M + MB - 1) / MB;
-#pragma omp parallel for schedule(dynamic, 1) if (parallel)
+  /* work items = (row block, column panel): 66 x 256 tiles give 62 x 4 items for the MLP's
+   * 4096 x 1024 products and 16 x 4 for its 1024 x 1024 weight gradients, enough for 64 threads */
+  enum { KB = 256, MB = 66, NB = 256 };
+  const int64_t mblocks = (M + MB - 1) / MB, nblocks = (N + NB - 1) / NB;
+#pragma omp parallel for collapse(2) schedule(dynamic, 1) if (parallel)
   for (int64_t mb = 0; mb < mblocks; ++mb) {
-    const int64_t m0 = mb * MB, m1 = m0 + MB < M ? m0 + MB : M;
-    float* packB = NULL;
-    if (b_cs != 1) packB = (float*)malloc(sizeof(float) * KB * (size_t)N);
-    for (int64_t k0 = 0; k0 < K; k0 += KB) {
-      const int64_t k1 = k0 + KB < K ? k0 + KB : K;
-      const float* Bp = B + k0 * b_rs;
-      int64_t brs = b_rs;
-      if (packB) { /* make B rows contiguous so the j loop vectorises */
-        for (int64_t k = k0; k < k1; ++k)
-          for (int64_t j = 0; j < N; ++j) packB[(k - k0) * N + j] = B[k * b_rs + j * b_cs];
-        Bp = packB;
-        brs = N;
-      }
-      for (int64_t i = m0; i < m1; ++i) {
-        float* c = C + i * ldc;
-        if (k0 == 0 && !accumulate)
-          for (int64_t j = 0; j < N; ++j) c[j] = 0.f;
-        for (int64_t k = k0; k < k1; ++k) {
-          const float a = A[i * a_rs + k * a_cs];
-          const float* b = Bp + (k - k0) * brs;
-          for (int64_t j = 0; j < N; ++j) c[j] += a * b[j];
+    for (int64_t nb = 0; nb < nblocks; ++nb) {
+      const int64_t m0 = mb * MB, m1 = m0 + MB < M ? m0 + MB : M;
+      const int64_t n0 = nb * NB, n1 = n0 + NB < N ? n0 + NB : N;
+      const int64_t nw = n1 - n0;
+      float* packB = NULL;
+      if (b_cs != 1) packB = (float*)malloc(sizeof(float) * KB * (size_t)nw);
+      for (int64_t k0 = 0; k0 < K; k0 += KB) {
+        const int64_t k1 = k0 + KB < K ? k0 + KB : K;
+        const float* Bp = B + k0 * b_rs + n0 * b_cs;
+        int64_t brs = b_rs;
+        if (packB) { /* make B rows contiguous so the j loop vectorises */
+          for (int64_t k = k0; k < k1; ++k)
+            for (int64_t j = 0; j < nw; ++j) packB[(k - k0) * nw + j] = B[k * b_rs + (n0 + j) * b_cs];
+          Bp = packB;
+          brs = nw;
+        }
+        const int zero_first = k0 == 0 && !accumulate;
+        const int64_t mfull = m0 + (m1 - m0) / GEMM_MR * GEMM_MR;
+        const int64_t nfull = nw / GEMM_NR * GEMM_NR;
+        for (int64_t i = m0; i < mfull; i += GEMM_MR)
+          for (int64_t j = 0; j < nfull; j += GEMM_NR)
+            sgemm_micro(A + i * a_rs + k0 * a_cs, a_rs, a_cs, Bp + j, brs, C + i * ldc + n0 + j, ldc,
+                        k1 - k0, zero_first);
+        /* edges: the remaining columns of the full row groups, then the remaining rows */
+        for (int64_t i = m0; i < m1; ++i) {
+          const int64_t j0 = i < mfull ? nfull : 0;
+          if (j0 >= nw) continue;
+          float* c = C + i * ldc + n0;
+          if (zero_first)
+            for (int64_t j = j0; j < nw; ++j) c[j] = 0.f;
+          for (int64_t k = k0; k < k1; ++k) {
+            const float a = A[i * a_rs + k * a_cs];
+            const float* b = Bp + (k - k0) * brs;
+            for (int64_t j = j0; j < nw; ++j) c[j] += a * b[j];
+          }
         }
       }
+      free(packB);
     }
-    free(packB);
   }
 }
 
