@@ -64,11 +64,34 @@ def bucket_kw():
 
 
 # =================================================================================== CPU arm
+def _cgroup_cpu_quota():
+    """CPUs this container may use per the cgroup bandwidth controller (None = unlimited)."""
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]  # cgroup v2
+        if quota != "max":
+            return max(1, -(-int(quota) // int(period)))
+        return None
+    except Exception:
+        pass
+    try:  # cgroup v1
+        quota = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+        period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if quota > 0 and period > 0:
+            return max(1, -(-quota // period))
+    except Exception:
+        pass
+    return None
+
+
 def host_threads():
-    """Threads of the CPU arms: the schedulable CPUs (what the reference's NumSchedulableCPUs
-    returns, platform/posix/port.cc:50-55), but not more than the physical cores -- on this
-    GEMM-bound step two hyper-threads per core run 3-4x slower than one (measured: 128 threads
-    2.5 K samples/s, 64 threads 9.2 K), and the baseline should be the CPU's best."""
+    """Threads of the CPU arms = the CPUs this process can really use: the schedulable CPUs (what
+    the reference's NumSchedulableCPUs returns, platform/posix/port.cc:50-55), capped by the
+    physical core count and by the container's cgroup CPU quota.  Measured on the GPU box
+    (128 logical / 64 physical CPUs, cpu.max = 16 CPUs): 16 threads 40.2 K samples/s, 64 threads
+    21.0 K, 128 threads 2.7 K -- oversubscribing the quota only throttles, and the baseline
+    should be the CPU's best.  B200TF_HOST_THREADS overrides."""
+    if os.environ.get("B200TF_HOST_THREADS"):
+        return max(1, int(os.environ["B200TF_HOST_THREADS"]))
     n = len(os.sched_getaffinity(0))
     try:
         import psutil
@@ -77,6 +100,9 @@ def host_threads():
             n = min(n, phys)
     except Exception:
         pass
+    quota = _cgroup_cpu_quota()
+    if quota:
+        n = min(n, quota)
     return max(1, n)
 
 
