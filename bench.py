@@ -132,7 +132,7 @@ def cpu_step_fn():
     return step, o.num_threads()
 
 
-def cpu_baseline(max_seconds=15.0, max_steps=24):
+def cpu_baseline(max_seconds=15.0, max_steps=150):
     step, cores = cpu_step_fn()
     step()  # warm-up (page faults, thread pool)
     t0 = time.perf_counter()
