@@ -131,6 +131,23 @@ def test_matmul_numpy(oracle, rng, m, n, k, ta, tb):
     np.testing.assert_allclose(out, ref, rtol=1e-5, atol=1e-3)
 
 
+@pytest.mark.parametrize("m,n,k", [(67, 257, 5), (133, 300, 600), (6, 32, 256), (7, 33, 257),
+                                   (200, 1024, 513)])
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+def test_matmul_blocking_edges_are_sequential_fp32_sums(oracle, rng, m, n, k, ta, tb):
+    # the register-blocked GEMM (6 x 32 micro tiles, 66 x 256 x 256 blocks) must equal the plain
+    # "c += a * b for k ascending" fp32 loop bit for bit at every tile / block edge
+    a = rng.randn(*((k, m) if ta else (m, k))).astype(np.float32)
+    b = rng.randn(*((n, k) if tb else (k, n))).astype(np.float32)
+    A = a.T if ta else a
+    B = b.T if tb else b
+    ref = np.zeros((m, n), np.float32)
+    for kk in range(k):   # separate multiply and add, ascending k: what -ffp-contract=off compiles to
+        ref += (A[:, kk:kk + 1] * B[kk:kk + 1, :]).astype(np.float32)
+    np.testing.assert_array_equal(oracle.matmul(a, b, ta, tb), ref)
+
+
 def test_matmul_direct_session_known_answers(oracle):
     # core/common_runtime/direct_session_test.cc:54-108: a=[[3,2],[-1,0]], x=[[1],[1]] -> y=a*x
     a = np.array([[3, 2], [-1, 0]], np.float32)
