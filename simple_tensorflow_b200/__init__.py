@@ -10,8 +10,9 @@ Layers (bottom up):
                             -> lib/libb200tf_framework.so            (binding: client.py)
   ops.py                    Python op constructors + gradients + SGD (what the reference's
                             python/ops and python/training do for these ops)
+  compat.py                 the same under the reference's names (tf.nn.*, tf.train.*, tf.Session)
 Nothing here falls back to CPU or PyTorch math: without the built libraries imports fail loudly.
 """
 from . import _lib  # noqa: F401
 
-__all__ = ["_lib", "client", "ops"]
+__all__ = ["_lib", "client", "ops", "compat"]

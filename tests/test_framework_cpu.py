@@ -201,6 +201,30 @@ def test_replica_gradient_exchange_graph():
     assert not [op for op in tf.get_default_graph().operations if op.type.startswith("B200AllReduce")]
 
 
+def test_reference_style_names_build_the_same_graph():
+    # simple_tensorflow_b200.compat: tf.nn.* / tf.train.* / named-argument xent as in nn_ops.py
+    import simple_tensorflow_b200.compat as tfc
+    tfc.reset_default_graph()
+    x = tfc.placeholder(tfc.float32, [8, 16])
+    y = tfc.placeholder(tfc.float32, [8, 4])
+    W = tfc.Variable(np.zeros((16, 4), np.float32))
+    b = tfc.Variable(np.zeros(4, np.float32))
+    logits = tfc.nn.bias_add(tfc.matmul(tfc.nn.relu(x), W), b)
+    loss = tfc.reduce_mean(tfc.nn.softmax_cross_entropy_with_logits(labels=y, logits=logits))
+    train = tfc.train.GradientDescentOptimizer(0.1).minimize(loss)
+    types = [op.type for op in tfc.get_default_graph().operations]
+    for t in ("Relu", "MatMul", "BiasAdd", "SoftmaxCrossEntropyWithLogits", "Mean", "BiasAddGrad",
+              "ApplyGradientDescent"):
+        assert t in types, t
+    assert train.type == "NoOp"
+    with pytest.raises(ValueError):   # positional arguments are refused, like the reference
+        tfc.nn.softmax_cross_entropy_with_logits(logits, y)
+    # the labels really are the second kernel input
+    xent = [op for op in tfc.get_default_graph().operations
+            if op.type == "SoftmaxCrossEntropyWithLogits"][0]
+    assert xent.inputs[0].name == logits.name and xent.inputs[1].name == y.name
+
+
 def test_host_tensor_roundtrip():
     a = np.arange(24, dtype=np.float32).reshape(2, 3, 4)
     t = client.HostTensor.from_numpy(a)
