@@ -375,6 +375,27 @@ def test_nchw_graph_matches_nhwc_graph(rng):
         np.testing.assert_array_equal(r, g)
 
 
+def test_reference_style_script_runs():
+    # simple_tensorflow_b200.compat: the names of a TensorFlow-1.0 script (tf.nn.*, tf.train.*,
+    # tf.Session() on the default graph); uniform logits -> loss = log(4)
+    import simple_tensorflow_b200.compat as tfc
+    tfc.reset_default_graph()
+    x = tfc.placeholder(tfc.float32, [8, 16])
+    y = tfc.placeholder(tfc.float32, [8, 4])
+    W = tfc.Variable(np.full((16, 4), 0.1, np.float32))
+    b = tfc.Variable(np.zeros(4, np.float32))
+    logits = tfc.nn.bias_add(tfc.matmul(tfc.nn.relu(x), W), b)
+    loss = tfc.reduce_mean(tfc.nn.softmax_cross_entropy_with_logits(labels=y, logits=logits))
+    train = tfc.train.GradientDescentOptimizer(0.1).minimize(loss)
+    with tfc.Session() as sess:
+        sess.run(tfc.global_variables_initializer())
+        xv = np.ones((8, 16), np.float32)
+        yv = np.eye(4, dtype=np.float32)[np.arange(8) % 4]
+        l0, _ = sess.run([loss, train], {x: xv, y: yv})
+        l1 = sess.run(loss, {x: xv, y: yv})
+    assert abs(l0 - np.log(4)) < 1e-5 and l1 <= l0 + 1e-6
+
+
 def test_all_reduce_n_single_replica(rng):
     # without a communicator the op is an identity (times scale): the N>1 path runs in bench.py
     a = rng.randn(1000).astype(np.float32)
