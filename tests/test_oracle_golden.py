@@ -242,6 +242,10 @@ def test_cast_bfloat16_is_truncation(oracle, rng):
     back = oracle.cast_bf16_to_f32(b)
     np.testing.assert_array_equal(back.view(np.uint32), (x.view(np.uint32) >> 16) << 16)
     np.testing.assert_allclose(back, x, rtol=1 / 128.)
+    # framework/bfloat16_test.cc:31-45 (Bfloat16Test.Conversion): a[i] = i + 1.25, |c - a| / a <= 1/128
+    a = (np.arange(100) + 1.25).astype(np.float32)
+    c = oracle.cast_bf16_to_f32(oracle.cast_f32_to_bf16(a))
+    assert np.all(np.abs(c - a) / a <= 1.0 / 128)
     # just below the next bf16 value (1 + 2^-7): round-to-nearest would go up, truncation stays
     v = np.array([1.0 + 2 ** -7 - 2 ** -20], np.float32)
     assert oracle.cast_bf16_to_f32(oracle.cast_f32_to_bf16(v))[0] == np.float32(1.0)
