@@ -32,6 +32,15 @@ class TF_Output(ctypes.Structure):
     _fields_ = [("oper", c_void_p), ("index", c_int)]
 
 
+class TF_Input(ctypes.Structure):
+    _fields_ = [("oper", c_void_p), ("index", c_int)]
+
+
+class TF_AttrMetadata(ctypes.Structure):
+    _fields_ = [("is_list", ctypes.c_ubyte), ("list_size", c_int64), ("type", c_int),
+                ("total_size", c_int64)]
+
+
 class TF_Buffer(ctypes.Structure):
     _fields_ = [("data", c_void_p), ("length", c_size_t), ("data_deallocator", c_void_p)]
 
@@ -76,6 +85,19 @@ _SIGS = {
     "TF_OperationNumInputs": (c_int, [c_void_p]),
     "TF_GraphOperationByName": (c_void_p, [c_void_p, c_char_p]),
     "TF_GraphNextOperation": (c_void_p, [c_void_p, ctypes.POINTER(c_size_t)]),
+    "TF_OperationInput": (TF_Output, [TF_Input]),
+    "TF_OperationNumControlInputs": (c_int, [c_void_p]),
+    "TF_OperationGetControlInputs": (c_int, [c_void_p, ctypes.POINTER(c_void_p), c_int]),
+    "TF_OperationGetAttrMetadata": (TF_AttrMetadata, [c_void_p, c_char_p, c_void_p]),
+    "TF_OperationGetAttrString": (None, [c_void_p, c_char_p, c_void_p, c_size_t, c_void_p]),
+    "TF_OperationGetAttrInt": (None, [c_void_p, c_char_p, ctypes.POINTER(c_int64), c_void_p]),
+    "TF_OperationGetAttrIntList": (None, [c_void_p, c_char_p, ctypes.POINTER(c_int64), c_int, c_void_p]),
+    "TF_OperationGetAttrFloat": (None, [c_void_p, c_char_p, ctypes.POINTER(ctypes.c_float), c_void_p]),
+    "TF_OperationGetAttrBool": (None, [c_void_p, c_char_p, ctypes.POINTER(ctypes.c_ubyte), c_void_p]),
+    "TF_OperationGetAttrType": (None, [c_void_p, c_char_p, ctypes.POINTER(c_int), c_void_p]),
+    "TF_OperationGetAttrShape": (None, [c_void_p, c_char_p, ctypes.POINTER(c_int64), c_int, c_void_p]),
+    "TF_OperationGetAttrTensor": (None, [c_void_p, c_char_p, ctypes.POINTER(c_void_p), c_void_p]),
+    "B200TF_OperationAttrNames": (c_void_p, [c_void_p]),
     "TF_NewBufferFromString": (c_void_p, [c_char_p, c_size_t]),
     "TF_NewBuffer": (c_void_p, []), "TF_DeleteBuffer": (None, [c_void_p]),
     "TF_GraphToGraphDef": (None, [c_void_p, c_void_p, c_void_p]),
@@ -294,9 +316,17 @@ class Graph:
         self.shapes = {}          # static shapes recorded by the op constructors (Output.name -> tuple)
 
     def unique_name(self, base):
+        """ops.py Graph.unique_name: base, base_1, base_2, ... skipping names already taken (an
+        imported graph may already contain "Const_1")."""
         n = self._names.get(base, 0)
+        name = base if n == 0 else "%s_%d" % (base, n)
+        while name in self._names and (n > 0 or self._names.get(base, 0) > 0):
+            n += 1
+            name = "%s_%d" % (base, n)
         self._names[base] = n + 1
-        return base if n == 0 else "%s_%d" % (base, n)
+        if name != base:
+            self._names[name] = self._names.get(name, 0) + 1
+        return name
 
     def create_op(self, op_type, inputs, attrs=None, name=None, control_inputs=(),
                   input_lists=()):
@@ -393,7 +423,156 @@ class Graph:
             self.operations.append(op)
             self._names[op.name] = self._names.get(op.name, 0) + 1
             new_ops[op.name] = op
+        # second pass (GraphDefs need not be topologically sorted): wire inputs, control inputs
+        # and attributes through the C API's introspection calls, record the static shapes that
+        # the nodes themselves state (Placeholder / VariableV2 shape attrs, Const values)
+        by_ptr = {o.ptr: o for o in self.operations}
+        for op in new_ops.values():
+            n_in = self.fw.TF_OperationNumInputs(op.ptr)
+            for i in range(n_in):
+                src = self.fw.TF_OperationInput(TF_Input(op.ptr, i))
+                if src.oper in by_ptr and src.index < len(by_ptr[src.oper].outputs):
+                    op.inputs.append(by_ptr[src.oper].outputs[src.index])
+                elif src.oper in by_ptr:       # output of an opaque node: types unknown
+                    op.inputs.append(Output(by_ptr[src.oper], src.index))
+            nc = self.fw.TF_OperationNumControlInputs(op.ptr)
+            if nc:
+                arr = (c_void_p * nc)()
+                got = self.fw.TF_OperationGetControlInputs(op.ptr, arr, nc)
+                op.control_inputs = [by_ptr[arr[i]] for i in range(got) if arr[i] in by_ptr]
+            op.attrs = self._read_attrs(op)
+            shape = op.attrs.get("shape")
+            if op.type in ("Placeholder", "VariableV2") and isinstance(shape, tuple) and op.outputs:
+                self.shapes[op.outputs[0].name] = tuple(shape[1])
+            if op.type == "Const" and op.outputs and "_value_shape" in op.attrs:
+                self.shapes[op.outputs[0].name] = op.attrs.pop("_value_shape")
+        self._infer_shapes(new_ops)
         return new_ops
+
+    def _infer_shapes(self, new_ops):
+        """Static shapes of imported hot-path ops, by the same rules the op constructors in ops.py
+        apply (the reference's shape functions, framework/common_shape_fns.cc): gradient
+        construction needs them.  Anything unknown simply stays unknown."""
+        def windowed(size, filt, stride, padding):
+            return (size - filt + stride) // stride if padding == "VALID" else (size + stride - 1) // stride
+
+        def ints(op, key):
+            v = op.attrs.get(key)
+            return v[1] if isinstance(v, tuple) else None
+
+        pending = [op for op in new_ops.values() if op.outputs]
+        for _ in range(len(pending) + 1):       # GraphDefs need not be sorted: iterate to a fixed point
+            progress = False
+            for op in pending:
+                if op.outputs[0].name in self.shapes and op.type != "SoftmaxCrossEntropyWithLogits":
+                    continue
+                ins = [self.shapes.get(i.name) for i in op.inputs]
+                out = None
+                t = op.type
+                if t in ("Identity", "Relu", "Softmax", "LogSoftmax", "Cast", "BiasAdd", "ReluGrad"):
+                    out = ins[0] if ins else None
+                elif t in ("Add", "Mul") and len(ins) == 2 and None not in ins:
+                    a, b = ins
+                    out = a if int(np.prod(a or (1,))) != 1 or len(a) >= len(b) else b
+                    if int(np.prod(a or (1,))) == 1 and int(np.prod(b or (1,))) != 1:
+                        out = b
+                elif t == "MatMul" and len(ins) == 2 and None not in ins:
+                    a, b = ins
+                    out = (a[1] if op.attrs.get("transpose_a") else a[0],
+                           b[0] if op.attrs.get("transpose_b") else b[1])
+                elif t == "BatchMatMul" and len(ins) == 2 and None not in ins:
+                    a, b = ins
+                    out = tuple(a[:-2]) + (a[-1] if op.attrs.get("adj_x") else a[-2],
+                                           b[-2] if op.attrs.get("adj_y") else b[-1])
+                elif t in ("Conv2D", "MaxPool") and ins and ins[0] is not None:
+                    nchw = op.attrs.get("data_format", "NHWC") == "NCHW"
+                    h, w, c = (2, 3, 1) if nchw else (1, 2, 3)
+                    st, pad, x = ints(op, "strides"), op.attrs.get("padding"), ins[0]
+                    if t == "Conv2D" and len(ins) == 2 and ins[1] is not None and st:
+                        f = ins[1]
+                        oh, ow, oc = windowed(x[h], f[0], st[h], pad), windowed(x[w], f[1], st[w], pad), f[3]
+                    elif t == "MaxPool" and st and ints(op, "ksize"):
+                        k = ints(op, "ksize")
+                        oh, ow, oc = windowed(x[h], k[h], st[h], pad), windowed(x[w], k[w], st[w], pad), x[c]
+                    else:
+                        continue
+                    out = (x[0], oc, oh, ow) if nchw else (x[0], oh, ow, oc)
+                elif t == "Reshape" and len(op.inputs) == 2 and ins[0] is not None:
+                    target = op.inputs[1].op.attrs.get("_const_ints")
+                    if target is not None:
+                        n = int(np.prod(ins[0], dtype=np.int64))
+                        known = int(np.prod([d for d in target if d >= 0], dtype=np.int64)) or 1
+                        out = tuple(d if d >= 0 else n // known for d in target)
+                elif t == "SoftmaxCrossEntropyWithLogits" and ins and ins[0] is not None:
+                    if op.outputs[1].name not in self.shapes:
+                        self.shapes[op.outputs[0].name] = (ins[0][0],)
+                        self.shapes[op.outputs[1].name] = tuple(ins[0])
+                        progress = True
+                    continue
+                elif t == "Mean" and ins and ins[0] is not None:
+                    out = ()     # the runtime's Mean reduces over all dimensions
+                elif t == "ArgMax" and len(op.inputs) == 2 and ins[0] is not None:
+                    axis = op.inputs[1].op.attrs.get("_const_ints")
+                    if axis:
+                        ax = axis[0] % len(ins[0])
+                        out = tuple(d for i, d in enumerate(ins[0]) if i != ax)
+                if out is not None:
+                    self.shapes[op.outputs[0].name] = tuple(int(d) for d in out)
+                    progress = True
+            if not progress:
+                break
+
+    def _read_attrs(self, op):
+        """The op's attributes in the tagged form create_op takes (so gradient functions can copy
+        them): bool / int / float / str, ('type', dt), ('shape', dims), ('ints', [...]).  Attributes
+        the runtime keeps as opaque bytes, and tensors, are left out."""
+        fw, st = self.fw, _Status()
+        names = _free_cstr_list(fw.B200TF_OperationAttrNames(op.ptr))
+        out = {}
+        for name in names:
+            nb = name.encode()
+            m = fw.TF_OperationGetAttrMetadata(op.ptr, nb, st.ptr)
+            st.check()
+            if m.is_list:
+                if m.type == 1:  # TF_ATTR_INT
+                    vals = (c_int64 * max(m.list_size, 1))()
+                    fw.TF_OperationGetAttrIntList(op.ptr, nb, vals, m.list_size, st.ptr)
+                    out[name] = ("ints", [int(v) for v in vals[:m.list_size]])
+                continue
+            if m.type == 0:      # string
+                buf = ctypes.create_string_buffer(max(m.total_size, 1))
+                fw.TF_OperationGetAttrString(op.ptr, nb, buf, m.total_size, st.ptr)
+                out[name] = buf.raw[:m.total_size].decode("utf-8", "replace")
+            elif m.type == 1:
+                v = c_int64()
+                fw.TF_OperationGetAttrInt(op.ptr, nb, ctypes.byref(v), st.ptr)
+                out[name] = int(v.value)
+            elif m.type == 2:
+                v = ctypes.c_float()
+                fw.TF_OperationGetAttrFloat(op.ptr, nb, ctypes.byref(v), st.ptr)
+                out[name] = float(v.value)
+            elif m.type == 3:
+                v = ctypes.c_ubyte()
+                fw.TF_OperationGetAttrBool(op.ptr, nb, ctypes.byref(v), st.ptr)
+                out[name] = bool(v.value)
+            elif m.type == 4:
+                v = c_int()
+                fw.TF_OperationGetAttrType(op.ptr, nb, ctypes.byref(v), st.ptr)
+                out[name] = ("type", int(v.value))
+            elif m.type == 5 and m.total_size >= 0:
+                dims = (c_int64 * max(m.total_size, 1))()
+                fw.TF_OperationGetAttrShape(op.ptr, nb, dims, m.total_size, st.ptr)
+                out[name] = ("shape", [int(d) for d in dims[:m.total_size]])
+            elif m.type == 6 and name == "value":
+                t = c_void_p()
+                fw.TF_OperationGetAttrTensor(op.ptr, nb, ctypes.byref(t), st.ptr)
+                if t.value:
+                    ht = HostTensor(t.value)
+                    out["_value_shape"] = ht.shape
+                    if ht.dtype in (TF_INT32, TF_INT64) and int(np.prod(ht.shape, dtype=np.int64)) <= 16:
+                        out["_const_ints"] = [int(v) for v in np.array(ht.numpy()).ravel()]
+            st.check()
+        return out
 
     def get_operation_by_name(self, name):
         for op in self.operations:

@@ -4,6 +4,7 @@
 
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -37,6 +38,7 @@ struct TF_Operation {
   NodeDef node;
   tensorflow::DataTypeVector input_types, output_types;
   bool opaque = false;  // imported node of an op type that is not registered here
+  TF_Graph* graph = nullptr;
 };
 struct TF_ImportGraphDefOptions {
   std::string prefix;
@@ -243,6 +245,7 @@ TF_Operation* TF_FinishOperation(TF_OperationDescription* d, TF_Status* status) 
     return nullptr;
   }
   TF_Operation* raw = op.get();
+  raw->graph = d->graph;
   d->graph->by_name[raw->node.name] = raw;
   d->graph->operations.push_back(std::move(op));
   return raw;
@@ -256,11 +259,164 @@ TF_DataType TF_OperationOutputType(TF_Output o) {
     return static_cast<TF_DataType>(0);  // opaque imported node: types unknown
   return static_cast<TF_DataType>(o.oper->output_types[o.index]);
 }
-int TF_OperationNumInputs(TF_Operation* oper) { return static_cast<int>(oper->input_types.size()); }
+int TF_OperationNumInputs(TF_Operation* oper) {
+  if (!oper->opaque) return static_cast<int>(oper->input_types.size());
+  int n = 0;  // opaque imported node: the types are unknown, the edges are not
+  for (const std::string& name : oper->node.input) n += name.empty() || name[0] != '^';
+  return n;
+}
 TF_Operation* TF_GraphOperationByName(TF_Graph* graph, const char* oper_name) {
   std::lock_guard<std::mutex> l(graph->mu);
   auto it = graph->by_name.find(oper_name);
   return it == graph->by_name.end() ? nullptr : it->second;
+}
+
+// ---------------------------------------------------------------- operation introspection
+static const AttrValue* FindAttr(TF_Operation* oper, const char* name, TF_Status* status) {
+  auto it = oper->node.attr.find(name);
+  if (it == oper->node.attr.end()) {
+    status->status = tensorflow::errors::InvalidArgument("Operation '", oper->node.name,
+                                                         "' has no attr named '", name, "'.");
+    return nullptr;
+  }
+  status->status = Status::OK();
+  return &it->second;
+}
+static bool RequireKind(const AttrValue* a, AttrValue::Kind kind, const char* name,
+                        TF_Status* status) {
+  if (a == nullptr) return false;
+  if (a->kind != kind) {
+    status->status = tensorflow::errors::InvalidArgument("Attribute '", name,
+                                                         "' does not have the requested type");
+    return false;
+  }
+  return true;
+}
+
+TF_Output TF_OperationInput(TF_Input in) {
+  TF_Output none{nullptr, 0};
+  if (in.oper == nullptr || in.oper->graph == nullptr || in.index < 0) return none;
+  int seen = 0;
+  for (const std::string& name : in.oper->node.input) {
+    if (!name.empty() && name[0] == '^') continue;
+    if (seen++ != in.index) continue;
+    std::string src = name;
+    int slot = 0;
+    const size_t colon = src.rfind(':');
+    if (colon != std::string::npos) {
+      slot = atoi(src.c_str() + colon + 1);
+      src = src.substr(0, colon);
+    }
+    std::lock_guard<std::mutex> l(in.oper->graph->mu);
+    auto it = in.oper->graph->by_name.find(src);
+    if (it == in.oper->graph->by_name.end()) return none;
+    return TF_Output{it->second, slot};
+  }
+  return none;
+}
+int TF_OperationNumControlInputs(TF_Operation* oper) {
+  int n = 0;
+  for (const std::string& name : oper->node.input) n += !name.empty() && name[0] == '^';
+  return n;
+}
+int TF_OperationGetControlInputs(TF_Operation* oper, TF_Operation** control_inputs, int max) {
+  int n = 0;
+  if (oper->graph == nullptr) return 0;
+  std::lock_guard<std::mutex> l(oper->graph->mu);
+  for (const std::string& name : oper->node.input) {
+    if (name.empty() || name[0] != '^' || n >= max) continue;
+    auto it = oper->graph->by_name.find(name.substr(1));
+    if (it != oper->graph->by_name.end()) control_inputs[n++] = it->second;
+  }
+  return n;
+}
+
+TF_AttrMetadata TF_OperationGetAttrMetadata(TF_Operation* oper, const char* name,
+                                            TF_Status* status) {
+  TF_AttrMetadata m{0, -1, TF_ATTR_PLACEHOLDER, -1};
+  const AttrValue* a = FindAttr(oper, name, status);
+  if (a == nullptr) return m;
+  switch (a->kind) {
+    case AttrValue::kS: m.type = TF_ATTR_STRING; m.total_size = (int64_t)a->s.size(); break;
+    case AttrValue::kI: m.type = TF_ATTR_INT; break;
+    case AttrValue::kF: m.type = TF_ATTR_FLOAT; break;
+    case AttrValue::kB: m.type = TF_ATTR_BOOL; break;
+    case AttrValue::kType: m.type = TF_ATTR_TYPE; break;
+    case AttrValue::kShape: m.type = TF_ATTR_SHAPE; m.total_size = a->shape.dims(); break;
+    case AttrValue::kTensor: m.type = TF_ATTR_TENSOR; break;
+    case AttrValue::kListI:
+      m.is_list = 1; m.type = TF_ATTR_INT; m.list_size = (int64_t)a->list_i.size(); break;
+    case AttrValue::kListS:
+      m.is_list = 1; m.type = TF_ATTR_STRING; m.list_size = (int64_t)a->list_s.size();
+      m.total_size = 0;
+      for (const auto& s : a->list_s) m.total_size += (int64_t)s.size();
+      break;
+    case AttrValue::kListType:
+      m.is_list = 1; m.type = TF_ATTR_TYPE; m.list_size = (int64_t)a->list_type.size(); break;
+    case AttrValue::kRaw: m.type = TF_ATTR_PLACEHOLDER; m.total_size = (int64_t)a->raw.size(); break;
+    case AttrValue::kNone: break;
+  }
+  return m;
+}
+void TF_OperationGetAttrString(TF_Operation* oper, const char* name, void* value, size_t max_length,
+                               TF_Status* status) {
+  const AttrValue* a = FindAttr(oper, name, status);
+  if (!RequireKind(a, AttrValue::kS, name, status)) return;
+  memcpy(value, a->s.data(), std::min(max_length, a->s.size()));
+}
+void TF_OperationGetAttrInt(TF_Operation* oper, const char* name, int64_t* value,
+                            TF_Status* status) {
+  const AttrValue* a = FindAttr(oper, name, status);
+  if (RequireKind(a, AttrValue::kI, name, status)) *value = a->i;
+}
+void TF_OperationGetAttrIntList(TF_Operation* oper, const char* name, int64_t* values,
+                                int max_values, TF_Status* status) {
+  const AttrValue* a = FindAttr(oper, name, status);
+  if (!RequireKind(a, AttrValue::kListI, name, status)) return;
+  for (int i = 0; i < max_values && i < (int)a->list_i.size(); ++i) values[i] = a->list_i[i];
+}
+void TF_OperationGetAttrFloat(TF_Operation* oper, const char* name, float* value,
+                              TF_Status* status) {
+  const AttrValue* a = FindAttr(oper, name, status);
+  if (RequireKind(a, AttrValue::kF, name, status)) *value = a->f;
+}
+void TF_OperationGetAttrBool(TF_Operation* oper, const char* name, unsigned char* value,
+                             TF_Status* status) {
+  const AttrValue* a = FindAttr(oper, name, status);
+  if (RequireKind(a, AttrValue::kB, name, status)) *value = a->b ? 1 : 0;
+}
+void TF_OperationGetAttrType(TF_Operation* oper, const char* name, TF_DataType* value,
+                             TF_Status* status) {
+  const AttrValue* a = FindAttr(oper, name, status);
+  if (RequireKind(a, AttrValue::kType, name, status)) *value = static_cast<TF_DataType>(a->type);
+}
+void TF_OperationGetAttrShape(TF_Operation* oper, const char* name, int64_t* value, int num_dims,
+                              TF_Status* status) {
+  const AttrValue* a = FindAttr(oper, name, status);
+  if (!RequireKind(a, AttrValue::kShape, name, status)) return;
+  for (int i = 0; i < num_dims && i < a->shape.dims(); ++i) value[i] = a->shape.dim_size(i);
+}
+void TF_OperationGetAttrTensor(TF_Operation* oper, const char* name, TF_Tensor** value,
+                               TF_Status* status) {
+  *value = nullptr;
+  const AttrValue* a = FindAttr(oper, name, status);
+  if (!RequireKind(a, AttrValue::kTensor, name, status)) return;
+  Tensor copy(HostTensorAllocator(), a->tensor.dtype(), a->tensor.shape());
+  if (a->tensor.TotalBytes() > 0) {
+    if (!copy.IsInitialized()) {
+      status->status = tensorflow::errors::ResourceExhausted("OOM copying attr '", name, "'");
+      return;
+    }
+    memcpy(copy.raw_data(), a->tensor.raw_data(), a->tensor.TotalBytes());
+  }
+  *value = new TF_Tensor{copy};
+}
+char* B200TF_OperationAttrNames(TF_Operation* oper) {
+  std::string s;
+  for (const auto& kv : oper->node.attr) s += kv.first + "\n";
+  char* out = static_cast<char*>(malloc(s.size() + 1));
+  memcpy(out, s.c_str(), s.size() + 1);
+  return out;
 }
 
 TF_Operation* TF_GraphNextOperation(TF_Graph* graph, size_t* pos) {
@@ -362,6 +518,7 @@ void TF_GraphImportGraphDef(TF_Graph* graph, const TF_Buffer* graph_def,
       }
     }
   for (auto& op : added) {
+    op->graph = graph;
     graph->by_name[op->node.name] = op.get();
     graph->operations.push_back(std::move(op));
   }

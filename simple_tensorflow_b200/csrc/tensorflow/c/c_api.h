@@ -109,6 +109,49 @@ TF_CAPI_EXPORT extern int TF_OperationNumOutputs(TF_Operation* oper);
 TF_CAPI_EXPORT extern TF_DataType TF_OperationOutputType(TF_Output oper_out);
 TF_CAPI_EXPORT extern int TF_OperationNumInputs(TF_Operation* oper);
 TF_CAPI_EXPORT extern TF_Operation* TF_GraphOperationByName(TF_Graph* graph, const char* oper_name);
+/* ---- inspecting operations (c_api.h:536-563, 585-760): what an importer needs to walk a graph */
+TF_CAPI_EXPORT extern TF_Output TF_OperationInput(TF_Input oper_in);
+TF_CAPI_EXPORT extern int TF_OperationNumControlInputs(TF_Operation* oper);
+TF_CAPI_EXPORT extern int TF_OperationGetControlInputs(TF_Operation* oper,
+                                                       TF_Operation** control_inputs,
+                                                       int max_control_inputs);
+typedef enum TF_AttrType {
+  TF_ATTR_STRING = 0, TF_ATTR_INT = 1, TF_ATTR_FLOAT = 2, TF_ATTR_BOOL = 3, TF_ATTR_TYPE = 4,
+  TF_ATTR_SHAPE = 5, TF_ATTR_TENSOR = 6, TF_ATTR_PLACEHOLDER = 7, TF_ATTR_FUNC = 8
+} TF_AttrType;
+typedef struct TF_AttrMetadata {
+  unsigned char is_list;
+  int64_t list_size;
+  TF_AttrType type;
+  int64_t total_size; /* string: bytes; shape: number of dims (-1 unknown rank); c_api.h:608-626 */
+} TF_AttrMetadata;
+/* Attributes this runtime carries as opaque bytes (list(shape), list(float), func, string tensors)
+ * report TF_ATTR_PLACEHOLDER with total_size = their serialized size and cannot be read back. */
+TF_CAPI_EXPORT extern TF_AttrMetadata TF_OperationGetAttrMetadata(TF_Operation* oper,
+                                                                  const char* attr_name,
+                                                                  TF_Status* status);
+TF_CAPI_EXPORT extern void TF_OperationGetAttrString(TF_Operation* oper, const char* attr_name,
+                                                     void* value, size_t max_length,
+                                                     TF_Status* status);
+TF_CAPI_EXPORT extern void TF_OperationGetAttrInt(TF_Operation* oper, const char* attr_name,
+                                                  int64_t* value, TF_Status* status);
+TF_CAPI_EXPORT extern void TF_OperationGetAttrIntList(TF_Operation* oper, const char* attr_name,
+                                                      int64_t* values, int max_values,
+                                                      TF_Status* status);
+TF_CAPI_EXPORT extern void TF_OperationGetAttrFloat(TF_Operation* oper, const char* attr_name,
+                                                    float* value, TF_Status* status);
+TF_CAPI_EXPORT extern void TF_OperationGetAttrBool(TF_Operation* oper, const char* attr_name,
+                                                   unsigned char* value, TF_Status* status);
+TF_CAPI_EXPORT extern void TF_OperationGetAttrType(TF_Operation* oper, const char* attr_name,
+                                                   TF_DataType* value, TF_Status* status);
+TF_CAPI_EXPORT extern void TF_OperationGetAttrShape(TF_Operation* oper, const char* attr_name,
+                                                    int64_t* value, int num_dims,
+                                                    TF_Status* status);
+/* Returns a new host tensor holding a copy of the attribute (caller deletes it). */
+TF_CAPI_EXPORT extern void TF_OperationGetAttrTensor(TF_Operation* oper, const char* attr_name,
+                                                     TF_Tensor** value, TF_Status* status);
+/* Additive: the names of all attributes of an operation, one per line (malloc'ed; free() it). */
+TF_CAPI_EXPORT extern char* B200TF_OperationAttrNames(TF_Operation* oper);
 /* Iterate the operations of a graph: start with *pos = 0; returns NULL at the end (c_api.h:763). */
 TF_CAPI_EXPORT extern TF_Operation* TF_GraphNextOperation(TF_Graph* graph, size_t* pos);
 

@@ -96,6 +96,19 @@ class Variable:
         self.shape = tuple(arr.shape)
         g.variables.append(self)
 
+    @classmethod
+    def from_imported(cls, ref):
+        """Wrap the output of an imported VariableV2 node (Graph.import_graph_def) so that
+        optimizers can update it; no node is added.  Its initializer is whatever Assign the
+        imported graph carries (e.g. the node named "<var>/Assign")."""
+        if ref.op.type != "VariableV2":
+            raise ValueError("%s is a %s, not a VariableV2" % (ref.op.name, ref.op.type))
+        v = cls.__new__(cls)
+        v.op, v.ref, v.dtype = ref.op, ref, ref.dtype
+        v.shape = _shape(ref)
+        v.initial_value = v.initializer = None
+        return v
+
     def value(self):
         return self.ref
 

@@ -113,6 +113,76 @@ def test_graph_built_here_round_trips_and_is_byte_stable(rng):
         assert a["attr"] == c["attr"]
 
 
+def test_imported_operations_can_be_walked():
+    # TF_OperationInput / GetControlInputs / GetAttr*: the importer wires inputs, control inputs,
+    # attributes and the static shapes the nodes state themselves
+    tf.reset_default_graph()
+    g = tf.get_default_graph()
+    ops = g.import_graph_def(open(GOLDEN_PB, "rb").read())
+    y = ops["y"]
+    assert [i.op.name for i in y.inputs] == ["Mul", "b/read"] and y.inputs[0].index == 0
+    assert ops["x2"].inputs[0].op.name == "ParseExample/ParseExample" and ops["x2"].inputs[0].index == 1
+    assert sorted(c.name for c in ops["init"].control_inputs) == ["a/Assign", "b/Assign", "c/Assign"]
+    assert y.attrs["T"] == ("type", tf.float32)
+    assign = ops["a/Assign"]
+    assert assign.attrs["use_locking"] is True and assign.attrs["validate_shape"] is True
+    assert ops["a"].attrs["shape"] == ("shape", []) and ops["a"].attrs["container"] == ""
+    assert g.shapes["a:0"] == () and g.shapes["a/initial_value:0"] == ()
+    assert ops["save/SaveV2"].type == "SaveV2"          # opaque node: still listed, still wired
+    assert [i.op.name for i in ops["save/SaveV2"].inputs][-3:] == ["a", "b", "c"]
+    # a graph built here and re-imported: attributes survive in the form create_op takes
+    tf.reset_default_graph()
+    x = tf.placeholder(tf.float32, [2, 8, 8, 4], "x")
+    w = tf.Variable(np.zeros((3, 3, 4, 8), np.float32), name="w")
+    tf.max_pool(tf.conv2d(x, w, [1, 2, 2, 1], "SAME", name="conv"), [1, 2, 2, 1], [1, 2, 2, 1], "VALID",
+                name="pool")
+    blob = tf.get_default_graph().as_graph_def()
+    tf.reset_default_graph()
+    again = tf.get_default_graph().import_graph_def(blob)
+    conv = again["conv"]
+    assert conv.attrs["strides"] == ("ints", [1, 2, 2, 1]) and conv.attrs["padding"] == "SAME"
+    assert conv.attrs["data_format"] == "NHWC" and conv.attrs["use_cudnn_on_gpu"] is True
+    assert again["pool"].attrs["ksize"] == ("ints", [1, 2, 2, 1])
+    assert tf.get_default_graph().shapes["x:0"] == (2, 8, 8, 4)
+    assert tf.get_default_graph().shapes["w:0"] == (3, 3, 4, 8)
+
+
+def test_training_graph_on_top_of_an_imported_model():
+    # forward model built, serialized, imported; gradients + SGD are then attached to the IMPORTED
+    # nodes: same backward ops as on the original graph (shapes are re-inferred on import)
+    def forward():
+        tf.reset_default_graph()
+        x = tf.placeholder(tf.float32, [8, 12, 12, 4], "x")
+        lab = tf.placeholder(tf.float32, [8, 10], "lab")
+        w = tf.Variable(np.zeros((3, 3, 4, 8), np.float32), name="w")
+        b = tf.Variable(np.zeros(8, np.float32), name="b")
+        wf = tf.Variable(np.zeros((6 * 6 * 8, 10), np.float32), name="wf")
+        bf = tf.Variable(np.zeros(10, np.float32), name="bf")
+        c = tf.relu(tf.bias_add(tf.conv2d(x, w, [1, 1, 1, 1], "SAME", name="conv"), b))
+        p = tf.max_pool(c, [1, 2, 2, 1], [1, 2, 2, 1], "SAME", name="pool")
+        logits = tf.bias_add(tf.matmul(tf.reshape(p, [8, 288], name="flat"), wf, name="fc"), bf)
+        return tf.reduce_mean(tf.softmax_cross_entropy_with_logits(logits, lab), name="loss"), [w, b, wf, bf]
+
+    loss, variables = forward()
+    original_shapes = dict(tf.get_default_graph().shapes)
+    blob = tf.get_default_graph().as_graph_def()
+    tf.GradientDescentOptimizer(0.1).minimize(loss, variables)
+    want = sorted(op.type for op in tf.get_default_graph().operations)
+
+    tf.reset_default_graph()
+    g = tf.get_default_graph()
+    g.import_graph_def(blob)
+    assert {k: g.shapes.get(k) for k in original_shapes} == original_shapes   # inferred again
+    imported = [tf.Variable.from_imported(g.get_tensor_by_name(n + ":0")) for n in ("w", "b", "wf", "bf")]
+    train = tf.GradientDescentOptimizer(0.1).minimize(g.get_tensor_by_name("loss:0"), imported)
+    assert sorted(op.type for op in g.operations) == want and train.type == "NoOp"
+    # new names never collide with imported ones ("Const_1" exists in the import)
+    names = [op.name for op in g.operations]
+    assert len(names) == len(set(names))
+    with pytest.raises(ValueError):
+        tf.Variable.from_imported(g.get_tensor_by_name("x:0"))
+
+
 def test_import_errors():
     tf.reset_default_graph()
     g = tf.get_default_graph()
