@@ -17,6 +17,13 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    # The shared libraries are build products (git-ignored): a fresh checkout builds them once
+    # (nvcc cross-compiles sm_100a without a GPU); on the GPU box the snapshot carries them.
+    lib_dir = os.path.join(ROOT, "simple_tensorflow_b200", "lib")
+    if not (os.path.exists(os.path.join(lib_dir, "libb200tf.so")) and
+            os.path.exists(os.path.join(lib_dir, "libb200tf_framework.so"))):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")
