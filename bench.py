@@ -1,23 +1,31 @@
 #!/usr/bin/env python3
-"""bench.py -- Session.Run samples/sec of the B200 op-kernel layer (BASELINE.json metric).
+"""bench.py -- Session.Run samples/sec of the B200 op-kernel layer (BASELINE.json metric:
+"Session.Run samples/sec (MLP-1024 & LeNet) at 1/2/4/8 B200 vs Eigen CPU").
 
     python bench.py --gpus N --steps K --warmup W            # this repo's arm
     python bench.py --impl reference --gpus N --steps K ...  # CPU arm (oracle port, see below)
 
-Workload at N=1 (BASELINE.json configs[1], SURVEY 8d "C2"): 3-layer MLP 1024-1024-1024, batch
-4096, fp32 graph, forward + backward + SGD update, softmax cross-entropy over 1024 classes.
-One "step" = one Session.Run([loss, train_op]) through the C API (TF_SessionRun).
-N>1: one process per GPU (torchrun), one graph replica per rank, weak scaling (4096 samples per
-rank), gradients averaged by ONE fused NCCL all-reduce per step (B200AllReduceN).
+ONE JSON line.  Its top level is the MLP record (BASELINE configs[1], the config the metric is
+quoted on): 3-layer MLP 1024-1024-1024, batch 4096, fp32 graph, fwd + bwd + SGD, one "step" =
+one Session.Run([loss, train_op]) through the C API (TF_SessionRun).  `workloads` carries the
+same record for the other configs the metric names, each measured the same way in the same run:
+    lenet     BASELINE configs[2]: LeNet-5 conv graph, batch 512, NHWC fp32
+    mlp_bf16  BASELINE configs[3] per replica: the MLP with bf16 storage, fp32 accumulate
+N>1: one process per GPU (torchrun), one graph replica per rank, weak scaling (per-replica batch
+fixed), gradients averaged by ONE all-reduce of the gradient arena per step (B200AllReduceN).
 
-  value : samples/s with inputs resident in HBM (x / labels live in device variables).
-  e2e   : the same step fed from pinned HOST buffers through TF_SessionRun: H2D of x+labels and
-          D2H of the loss inside the timed region.
-  roofline     : the tcgen05 GEMM (dominant kernel), device time per launch measured with CUDA
-                 events on the session's stream (b200_profile_begin/end) in a second pass.
-  cpu_baseline : the CPU oracle (oracle/oracle.c, a restatement of the reference's Eigen path;
-                 the reference itself cannot be built offline) on the box's host cores.
---impl reference: times that same CPU port with all host threads (the reference's own CPU
+Per record:
+  value    samples/s with inputs resident in HBM (x / labels live in device variables).
+  e2e      the same step fed from pinned HOST buffers through TF_SessionRun: H2D of x+labels and
+           D2H of the loss inside the timed region.
+  parity   step-1 loss, gradients and updated weights of THIS full-size graph vs the CPU oracle,
+           computed before any timed region (tests/workloads.py::check_parity); N>1: vs the oracle
+           on the global batch.
+  roofline the tcgen05 GEMM / convolution kernels (dominant), device time per launch measured
+           with CUDA events on the session's stream (b200_profile_begin/end) in a separate pass.
+  cpu_baseline  the CPU oracle port (FMA build, oracle/_build/liboracle_fast.so) on the box's
+           host cores, rank 0.
+--impl reference times that same CPU port with all host threads (the reference's own CPU
 implementation is unbuildable here: no bazel / protoc / Eigen).
 """
 import argparse
@@ -34,33 +42,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "Session.Run samples/sec (MLP-1024 & LeNet) at 1/2/4/8 B200 vs Eigen CPU"
-BATCH, WIDTH, LAYERS, LR = 4096, 1024, 3, 0.01
-GEMM_FLOPS = 2.0 * BATCH * WIDTH * WIDTH  # every GEMM of the step: 8.59 GFLOP
-STEP_GEMMS = 8                            # 3 fwd + 3 dW + 2 dX (input is data)
-
-
-def synthetic(seed):
-    """SURVEY 8d inputs: activations U(-1,1), weights N(0, 1/sqrt(fan_in)), biases 0.1,
-    one-hot labels, fixed seed.  `seed` selects the replica's data shard; the initial weights
-    are the same on every replica."""
-    rng = np.random.RandomState(seed)
-    x = rng.uniform(-1, 1, (BATCH, WIDTH)).astype(np.float32)
-    labels = np.zeros((BATCH, WIDTH), np.float32)
-    labels[np.arange(BATCH), rng.randint(0, WIDTH, BATCH)] = 1.0
-    rng = np.random.RandomState(4321)
-    ws = [(rng.randn(WIDTH, WIDTH) / np.sqrt(WIDTH)).astype(np.float32) for _ in range(LAYERS)]
-    bs = [np.full(WIDTH, 0.1, np.float32) for _ in range(LAYERS)]
-    return x, labels, ws, bs
-
-
-def bucket_kw():
-    """B200TF_BUCKET_BYTES=none|<bytes>: gradient all-reduce bucket size (default: optimizer's)."""
-    v = os.environ.get("B200TF_BUCKET_BYTES")
-    if not v:
-        return {}
-    return {"bucket_bytes": None if v == "none" else int(v)}
+ALL_WORKLOADS = ["mlp", "lenet", "mlp_bf16"]
+MIN_WARMUP = 20   # steps; the first steps after a cold start run below the sustained clock
 
 
 # =================================================================================== CPU arm
@@ -106,34 +92,34 @@ def host_threads():
     return max(1, n)
 
 
-def cpu_step_fn():
-    """One full MLP training step on the CPU oracle (test infrastructure used as the baseline)."""
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
+def cpu_step_fn(w):
+    """One full training step of workload `w` on the CPU port, FMA build (the timed CPU arm; the
+    bit-stable -ffp-contract=off build stays the checker)."""
     import oracle_bind as o
+    prev = o.select("fast")
     o.set_num_threads(host_threads())
-    x, labels, ws, bs = synthetic(1234)
+    cores = o.num_threads()
+    o.select(prev)
+    # bf16 workloads: the reference's CPU device has no bf16 MatMul (types.proto:30 "only for
+    # cast ops"), its CPU path for the same graph is fp32 -- that is what this arm times (the
+    # bf16 storage rounding of tests/workloads.py is a numpy emulation for the parity check only)
+    import workloads as W
+    wt = W.MLP("f32", w.batch, w.width, w.layers) if w.dtype == "bf16" else w
+    x, labels = wt.data(1234)
+    params = wt.init_params()
 
     def step():
-        acts = [x]
-        for i in range(LAYERS):
-            pre = o.bias_add(o.matmul(acts[-1], ws[i]), bs[i])
-            acts.append(o.relu(pre) if i < LAYERS - 1 else pre)
-        lvec, bp = o.softmax_xent(acts[-1], labels)
-        g = bp * np.float32(1.0 / BATCH)
-        for i in reversed(range(LAYERS)):
-            db = o.bias_add_grad(g)
-            dw = o.matmul(acts[i], g, True, False)
-            if i > 0:
-                g = o.relu_grad(o.matmul(g, ws[i], False, True), acts[i])
-            ws[i] = o.apply_gradient_descent(ws[i], LR, dw)
-            bs[i] = o.apply_gradient_descent(bs[i], LR, db)
-        return float(lvec.mean())
+        prev = o.select("fast")
+        try:
+            return wt.reference_step(o, x, labels, params)
+        finally:
+            o.select(prev)
 
-    return step, o.num_threads()
+    return step, cores
 
 
-def cpu_baseline(max_seconds=15.0, max_steps=150):
-    step, cores = cpu_step_fn()
+def cpu_baseline(w, max_seconds=10.0, max_steps=200):
+    step, cores = cpu_step_fn(w)
     step()  # warm-up (page faults, thread pool)
     t0 = time.perf_counter()
     n = 0
@@ -141,36 +127,56 @@ def cpu_baseline(max_seconds=15.0, max_steps=150):
         step()
         n += 1
     dt = time.perf_counter() - t0
-    return {"value": BATCH * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
-            "sample": "%d full training steps (batch %d, 3x1024 MLP, fwd+bwd+SGD) of the CPU "
-                      "oracle port, OpenMP over %d host threads; %.2f s" % (n, BATCH, cores, dt)}
+    gf = w.flops_per_step * n / dt / 1e9
+    return {"value": w.batch * n / dt, "unit": "samples/s", "cores": cores, "kind": "port",
+            "gflops": gf, "gflops_per_core": gf / cores,
+            "build": "oracle.c -O3 -march=native -ffp-contract=fast (FMA), OpenMP",
+            "sample": "%d full training steps (%s) of the CPU oracle port, OpenMP over %d host "
+                      "threads; %.2f s" % (n, w.describe.split(";")[0], cores, dt)}
 
 
 def run_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return  # under torchrun only rank 0 runs the CPU arm
-    step, cores = cpu_step_fn()
-    for _ in range(max(1, min(args.warmup, 2))):
-        step()
-    steps = max(1, min(args.steps, 5))  # bounded: each step is a full 68.7 GFLOP CPU pass
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    dt = time.perf_counter() - t0
-    value = BATCH * steps / dt
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s",
-        "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "mlp-3x1024 batch 4096 fp32 fwd+bwd+sgd (BASELINE configs[1])",
-                   "note": "CPU restatement of the reference's Eigen path (reference unbuildable "
-                           "offline: needs bazel+protoc+Eigen); steps bounded to %d" % steps},
-        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": "%d full training steps, %d OpenMP threads" % (steps, cores)},
-        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0,
-                "d2h_bytes_per_step": 0},
-    }))
+    import workloads as W
+    records = {}
+    for name in args.workloads:
+        w = W.get(name)
+        step, cores = cpu_step_fn(w)
+        for _ in range(max(1, min(args.warmup, 2))):
+            step()
+        # each step is a full training step of the workload; the run is bounded in time
+        steps, t0 = 0, time.perf_counter()
+        budget_s = 40.0 if name == "mlp" else 15.0
+        while steps < args.steps and (steps == 0 or time.perf_counter() - t0 < budget_s):
+            step()
+            steps += 1
+        dt = time.perf_counter() - t0
+        value = w.batch * steps / dt
+        gf = w.flops_per_step * steps / dt / 1e9
+        note = ("CPU restatement of the reference's Eigen path, FMA build (reference unbuildable "
+                "offline: needs bazel+protoc+Eigen); %d of the requested %d steps ran inside the "
+                "%.0f s bound" % (steps, args.steps, budget_s))
+        if w.dtype == "bf16":
+            note += ("; the reference has no bf16 MatMul on CPU (types.proto:30): this arm runs the "
+                     "same graph in fp32")
+        records[name] = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": "samples/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w.describe, "note": note},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": cores, "kind": "port",
+                             "gflops": gf, "gflops_per_core": gf / cores,
+                             "sample": "%d full training steps, %d OpenMP threads, FMA build"
+                                       % (steps, cores)},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0,
+                    "d2h_bytes_per_step": 0},
+        }
+    head = args.workloads[0]
+    line = dict(records[head])
+    line["workloads"] = {n: r for n, r in records.items() if n != head}
+    print(json.dumps(line))
 
 
 # =================================================================================== GPU arm
@@ -214,78 +220,274 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
-LENET_BATCH = 512
+def load_peaks():
+    """Roofline denominators.  bf16 / HBM: MEASURED_PEAKS.json (driver-written).  TF32: the file
+    has no TF32 figure, so tools/measure_peaks.py measured cuBLAS TF32 with the driver's protocol
+    on this pool's B200 (committed: profiles/r02_measured_peaks.json).  Kernels timed per launch
+    (this roofline pass) are compared with the BURST figure."""
+    peaks, src = {}, {}
+    try:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peaks["bf16"] = d.get("bf16_tflops")
+        src["bf16"] = "MEASURED_PEAKS.json bf16_tflops (burst, cuBLAS 8192^3)"
+        peaks["hbm"] = d.get("hbm_gbs")
+    except Exception:
+        pass
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r02_measured_peaks.json")))
+        peaks["tf32"] = d.get("tf32_tflops")
+        src["tf32"] = ("profiles/r02_measured_peaks.json tf32_tflops (burst; cuBLAS TF32 8192^3, "
+                       "tools/measure_peaks.py on this pool's B200; sustained %.0f)"
+                       % d.get("tf32_tflops_sustained", 0))
+        if not peaks.get("bf16"):
+            peaks["bf16"] = d.get("bf16_tflops")
+            src["bf16"] = "profiles/r02_measured_peaks.json bf16_tflops (burst)"
+    except Exception:
+        pass
+    if not peaks.get("bf16"):
+        peaks["bf16"], src["bf16"] = 1680.0, "fallback burst bf16 1.68 PF (B200_PROFILING.md)"
+    if not peaks.get("tf32"):
+        peaks["tf32"] = 0.5 * peaks["bf16"]
+        src["tf32"] = "0.5 x " + src["bf16"] + " (no measured TF32 figure)"
+    return peaks, src
 
 
-def build_lenet_graph(num_replicas, seed):
-    """BASELINE configs[2] / SURVEY 8d C3: conv5x5x1x32 SAME -> relu -> pool2 -> conv5x5x32x64 SAME
-    -> relu -> pool2 -> fc 3136x1024 + relu -> fc 1024x10 -> xent; batch 512, NHWC fp32."""
-    from simple_tensorflow_b200 import ops as tf
-    rng = np.random.RandomState(seed)
-    B = LENET_BATCH
-    x = rng.uniform(-1, 1, (B, 28, 28, 1)).astype(np.float32)
-    labels = np.zeros((B, 10), np.float32)
-    labels[np.arange(B), rng.randint(0, 10, B)] = 1.0
-    shapes = dict(w1=(5, 5, 1, 32), w2=(5, 5, 32, 64), w3=(3136, 1024), w4=(1024, 10))
-    rng = np.random.RandomState(4321)  # identical initial weights on every replica
-    tf.reset_default_graph()
-    V = {}
-    for n, shp in shapes.items():
-        fan_in = int(np.prod(shp[:-1]))
-        V[n] = tf.Variable((rng.randn(*shp) / np.sqrt(fan_in)).astype(np.float32), name=n)
-        V["b" + n[1]] = tf.Variable(np.full(shp[-1], 0.1, np.float32), name="b" + n[1])
-    train_vars = list(V.values())
-
-    def tower(inp, lab, tag):
-        c1 = tf.relu(tf.bias_add(tf.conv2d(inp, V["w1"], [1, 1, 1, 1], "SAME"), V["b1"]))
-        p1 = tf.max_pool(c1, [1, 2, 2, 1], [1, 2, 2, 1], "SAME")
-        c2 = tf.relu(tf.bias_add(tf.conv2d(p1, V["w2"], [1, 1, 1, 1], "SAME"), V["b2"]))
-        p2 = tf.max_pool(c2, [1, 2, 2, 1], [1, 2, 2, 1], "SAME")
-        flat = tf.reshape(p2, [B, 3136])
-        f1 = tf.relu(tf.bias_add(tf.matmul(flat, V["w3"]), V["b3"]))
-        logits = tf.bias_add(tf.matmul(f1, V["w4"]), V["b4"])
-        loss = tf.reduce_mean(tf.softmax_cross_entropy_with_logits(logits, lab), name=tag + "/loss")
-        train = tf.GradientDescentOptimizer(LR).minimize(loss, train_vars, name=tag + "/train",
-                                                         num_replicas=num_replicas, **bucket_kw())
-        return loss, train
-
-    x_res = tf.Variable(x, name="x_resident")
-    l_res = tf.Variable(labels, name="labels_resident")
-    res = tower(x_res.ref, l_res.ref, "resident")
-    xp = tf.placeholder(tf.float32, [B, 28, 28, 1], "x")
-    lp = tf.placeholder(tf.float32, [B, 10], "labels")
-    fed = tower(xp, lp, "fed")
-    return tf, dict(x=x, labels=labels, xp=xp, lp=lp, resident=res, fed=fed)
+def load_traffic(name):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    of this workload (profiles/r02_traffic.json); null when no capture is committed."""
+    for f in ("r02_traffic.json",):
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", f)))
+            if name in d:
+                return d[name].get("dram_bytes_per_launch"), d[name].get("source")
+        except Exception:
+            pass
+    if name == "mlp":
+        try:
+            d = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))
+            return d["dram_bytes_per_launch"], "ncu --set full capture of round 1 (profiles/r01_gemm_traffic.json)"
+        except Exception:
+            pass
+    return None, None
 
 
-def build_graph(num_replicas, seed):
-    from simple_tensorflow_b200 import ops as tf
-    x, labels, ws, bs = synthetic(seed)
-    tf.reset_default_graph()
-    Ws = [tf.Variable(w, name="W%d" % i) for i, w in enumerate(ws)]
-    Bs = [tf.Variable(b, name="b%d" % i) for i, b in enumerate(bs)]
+class Bench:
+    def __init__(self, args):
+        import torch
+        from simple_tensorflow_b200 import _lib
+        self.args = args
+        self.torch = torch
+        self._lib = _lib
+        self.L = _lib.load()
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus and self.world > 1:
+            raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, self.world))
+        if self.L.b200_device_count() < 1:
+            raise SystemExit("bench.py needs a CUDA device: libb200tf has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        self.comm = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            from simple_tensorflow_b200 import replica
+            self.comm = replica.init_nccl_comm(self.L, self.rank, self.world, self.local_rank)
+        self.peaks, self.peak_src = load_peaks()
 
-    def tower(inp, lab, tag):
-        h = inp
-        for i in range(LAYERS):
-            h = tf.bias_add(tf.matmul(h, Ws[i], name="%s/fc%d" % (tag, i)), Bs[i])
-            if i < LAYERS - 1:
-                h = tf.relu(h)
-        loss = tf.reduce_mean(tf.softmax_cross_entropy_with_logits(h, lab), name=tag + "/loss")
-        train = tf.GradientDescentOptimizer(LR).minimize(loss, Ws + Bs, name=tag + "/train",
-                                                         num_replicas=num_replicas, **bucket_kw())
-        return loss, train
+    def collective_counts(self):
+        p, n = ctypes.c_uint64(), ctypes.c_uint64()
+        self.L.b200_collective_counts(ctypes.byref(p), ctypes.byref(n))
+        return p.value, n.value
 
-    # (a) inputs resident in HBM: device variables, assigned once
-    x_res = tf.Variable(x, name="x_resident")
-    l_res = tf.Variable(labels, name="labels_resident")
-    # the towers must not train the data variables
-    res = tower(x_res.ref, l_res.ref, "resident")
-    # (b) host-fed placeholders
-    xp = tf.placeholder(tf.float32, [BATCH, WIDTH], "x")
-    lp = tf.placeholder(tf.float32, [BATCH, WIDTH], "labels")
-    fed = tower(xp, lp, "fed")
-    return tf, dict(x=x, labels=labels, xp=xp, lp=lp, resident=res, fed=fed)
+    def run_workload(self, name):
+        import workloads as W
+        from simple_tensorflow_b200 import client
+        args, L, _lib, torch = self.args, self.L, self._lib, self.torch
+        world, rank = self.world, self.rank
+        w = W.get(name)
+        B = w.build(num_replicas=world, seed=1234 + rank)
+        tf = B.tf
+        sess = client.Session(tf.get_default_graph(), gpu=self.local_rank,
+                              collective_comm=self.comm, num_replicas=world)
+        init = tf.global_variables_initializer()
+        sess.run(init)
+        stream = sess.stream()
+        ev0, ev1 = ctypes.c_void_p(), ctypes.c_void_p()
+        _lib.check(L.b200_event_create(ctypes.byref(ev0)))
+        _lib.check(L.b200_event_create(ctypes.byref(ev1)))
+
+        # ---- parity of the full-size graph, before anything is timed (all ranks: collective)
+        parity = None
+        if not args.no_parity:
+            import oracle_bind as o
+            o.select("exact")
+            o.set_num_threads(host_threads())
+            parity = W.check_parity(w, B, sess, o, world=world, rank=rank)
+            # restore the initial weights: the timed runs start from the same state every time
+            sess.run(init)
+
+        hx, hl = w.host_tensor(B.x), w.host_tensor(B.labels)   # pinned, reused every step
+
+        def barrier():
+            _lib.check(L.b200_stream_synchronize(stream))
+            torch.cuda.synchronize()
+            if world > 1:
+                import torch.distributed as dist
+                dist.barrier()
+
+        def timed(fetches, feed, steps, prefetch=None):
+            """-> (device ms between events on the session stream, launches, last loss).
+
+            prefetch: list of (HostTensor x, HostTensor labels) buffer pairs used round-robin; the
+            inputs of step i+1 are staged (Session.stage: H2D on the copy stream) before step i is
+            run, so every step's host->device copy is inside the timed region but overlaps the
+            previous step's kernels."""
+            launches, loss, enq = 0, None, 0
+            barrier()
+            _lib.check(L.b200_event_record(ev0, stream))
+            staged = None
+            if prefetch:
+                staged = tuple(sess.stage(t) for t in prefetch[0])
+            for i in range(steps):
+                if prefetch:
+                    nxt = (tuple(sess.stage(t) for t in prefetch[(i + 1) % len(prefetch)])
+                           if i + 1 < steps else None)
+                    loss = sess.run(fetches, {B.xp: staged[0], B.lp: staged[1]})[0]
+                    staged = nxt
+                else:
+                    loss = sess.run(fetches, feed)[0]
+                st = sess.last_run_stats()
+                launches += st["kernels_launched"]
+                enq += st["host_enqueue_us"]
+            timed.host_enqueue_us = enq / max(steps, 1)
+            _lib.check(L.b200_event_record(ev1, stream))
+            barrier()
+            ms = ctypes.c_float()
+            _lib.check(L.b200_event_elapsed_ms(ev0, ev1, ctypes.byref(ms)))
+            loss = float(w.to_f32(loss))
+            if world > 1:
+                import torch.distributed as dist
+                t = torch.tensor([ms.value], device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+                return float(t.item()), launches, loss
+            return ms.value, launches, loss
+
+        res_fetch = list(B.resident)
+        fed_fetch = list(B.fed)
+        feed = {B.xp: hx, B.lp: hl}
+        # second pinned buffer pair: the input pipeline fills one while the other is in flight
+        buffers = [(hx, hl), (w.host_tensor(B.x), w.host_tensor(B.labels))]
+        warm = max(args.warmup, 3, MIN_WARMUP)
+        for _ in range(warm):
+            sess.run(res_fetch)
+        for _ in range(max(args.warmup, 3)):
+            sess.run(fed_fetch, feed)
+        timed(fed_fetch, None, max(args.warmup, 3), prefetch=buffers)
+        for _ in range(3):
+            sess.run(res_fetch)
+
+        sampler = ClockSampler(self.local_rank)
+        if rank == 0:
+            sampler.start()
+        c0 = self.collective_counts()
+        ms_res, launches, loss_res = timed(res_fetch, None, args.steps)
+        c1 = self.collective_counts()
+        host_enqueue_us = timed.host_enqueue_us
+        # the same K steps again in chunks: the median chunk is the figure robust to a cold start
+        chunk = max(1, args.steps // 5)
+        chunks = [timed(res_fetch, None, chunk)[0] / chunk for _ in range(5)] if args.steps >= 10 else []
+        ms_sync, _, _ = timed(fed_fetch, feed, args.steps)  # feed pinned buffers, copy inside Run()
+        h2d = sess.last_run_stats()["h2d_bytes"]
+        ms_e2e, _, loss_e2e = timed(fed_fetch, None, args.steps, prefetch=buffers)
+        clocks = sampler.summary() if rank == 0 else None
+        assert sum(client.HostTensor.numpy(t).nbytes for t in buffers[0]) == h2d
+        d2h = sess.last_run_stats()["d2h_bytes"]
+
+        # ---- roofline pass: per-launch device time of the tcgen05 kernels, events on the same stream
+        _lib.check(L.b200_profile_begin())
+        prof_steps = min(args.steps, 20)
+        for _ in range(prof_steps):
+            sess.run(res_fetch)
+        gemm_ms, gemm_n, gemm_fl = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_double()
+        _lib.check(L.b200_profile_end(ctypes.byref(gemm_ms), ctypes.byref(gemm_n),
+                                      ctypes.byref(gemm_fl)))
+        # what an event pair with nothing between costs on this stream
+        pair = []
+        for _ in range(50):
+            _lib.check(L.b200_event_record(ev0, stream))
+            _lib.check(L.b200_event_record(ev1, stream))
+            _lib.check(L.b200_stream_synchronize(stream))
+            ms_pair = ctypes.c_float()
+            _lib.check(L.b200_event_elapsed_ms(ev0, ev1, ctypes.byref(ms_pair)))
+            pair.append(ms_pair.value * 1e3)
+        event_pair_us = statistics.median(pair)
+        sess.close()
+        if rank != 0:
+            return None
+
+        if world > 1:
+            peer, nccl = c1[0] - c0[0], c1[1] - c0[1]
+            collective = {"kind": "peer" if peer and not nccl else ("nccl" if nccl and not peer
+                                                                    else "mixed" if peer else "none"),
+                          "peer_kernel_launches": peer, "nccl_calls": nccl,
+                          "per_step": (peer + nccl) / max(1, args.steps)}
+        else:
+            collective = {"kind": "none (1 replica)"}
+        kind = "bf16" if w.dtype == "bf16" else "tf32"
+        peak, peak_src = self.peaks[kind], self.peak_src[kind]
+        achieved = (gemm_fl.value / 1e12) / (gemm_ms.value / 1e3) if gemm_ms.value > 0 else 0.0
+        traffic, traffic_src = load_traffic(name)
+        base = None
+        if not args.no_cpu_baseline:
+            base = cpu_baseline(w, max_seconds=10.0 if name == "mlp" else 6.0)
+        n_samples = w.batch * world * args.steps
+        rec = {
+            "metric": METRIC, "value": n_samples / (ms_res / 1e3), "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": warm,
+            "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": ("bf16 graph; GEMMs on kind::f16 (bf16) tensor cores, fp32 accumulate"
+                      if w.dtype == "bf16" else
+                      "f32 graph; GEMMs / convolutions on TF32 tensor cores, fp32 accumulate"),
+            "data": "synthetic",
+            "config": {"workload": w.describe, "global_batch": w.batch * world,
+                       "parallelism": "dp%d" % world,
+                       "l2": "no flush: %d launches per step stream distinct operands; per-step "
+                             "working set exceeds the 126 MB L2 for the MLPs (~193 MB fp32), LeNet's "
+                             "(~75 MB activations + patches) is re-produced every step"
+                             % (launches // max(1, args.steps)),
+                       "loss_resident": loss_res, "loss_e2e": loss_e2e,
+                       "host_enqueue_us_per_step": host_enqueue_us,
+                       "ms_per_step_median_of_5_chunks": statistics.median(chunks) if chunks else None,
+                       "collective": collective},
+            "clocks": clocks,
+            "e2e": {"value": n_samples / (ms_e2e / 1e3), "unit": "samples/s",
+                    "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "how": ("Session.stage() of step i+1's pinned inputs (copy stream) before "
+                            "Session.run of step i; loss fetched to the host every step"),
+                    "unpipelined_value": n_samples / (ms_sync / 1e3),
+                    "unpipelined_ms_per_step": ms_sync / args.steps},
+            "gpu_launches": launches,
+            "parity": parity,
+            "roofline": {"kernel": "tcgen05 GEMM / implicit-GEMM convolution kernels (kind::%s)"
+                                   % ("f16 bf16" if w.dtype == "bf16" else "tf32"),
+                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "traffic_source": traffic_src,
+                         "peak_source": peak_src, "launches_timed": int(gemm_n.value),
+                         "us_per_launch": 1e3 * gemm_ms.value / max(1, gemm_n.value),
+                         "empty_event_pair_us": event_pair_us,
+                         "achieved_net_of_event_pair": ((gemm_fl.value / 1e12) /
+                                                        max(1e-9, gemm_ms.value / 1e3 -
+                                                            gemm_n.value * event_pair_us / 1e6)),
+                         "flops_per_launch": (gemm_fl.value / max(1, gemm_n.value)),
+                         "share_of_step": (gemm_ms.value / prof_steps) / (ms_res / args.steps),
+                         "step_tflops": w.flops_per_step * world * args.steps / (ms_res / 1e3) / 1e12},
+            "cpu_baseline": base,
+        }
+        return rec
 
 
 def run_b200(args):
@@ -294,195 +496,20 @@ def run_b200(args):
     sys.stdout.flush()
     real_stdout = os.dup(1)
     os.dup2(2, 1)
-    import torch
-    from simple_tensorflow_b200 import _lib, client
-    L = _lib.load()
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus and world > 1:
-        raise SystemExit("--gpus %d does not match WORLD_SIZE %d" % (args.gpus, world))
-    if L.b200_device_count() < 1:
-        raise SystemExit("bench.py needs a CUDA device: libb200tf has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    comm = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        from simple_tensorflow_b200 import replica
-        comm = replica.init_nccl_comm(L, rank, world, local_rank)
-
-    lenet = args.workload == "lenet"
-    batch = LENET_BATCH if lenet else BATCH
-    tf, G = (build_lenet_graph if lenet else build_graph)(world, seed=1234 + rank)
-    sess = client.Session(tf.get_default_graph(), gpu=local_rank, collective_comm=comm,
-                          num_replicas=world)
-    sess.run(tf.global_variables_initializer())
-    stream = sess.stream()
-    ev0, ev1 = ctypes.c_void_p(), ctypes.c_void_p()
-    _lib.check(L.b200_event_create(ctypes.byref(ev0)))
-    _lib.check(L.b200_event_create(ctypes.byref(ev1)))
-    hx = client.HostTensor.from_numpy(G["x"])        # pinned host buffers, reused every step
-    hl = client.HostTensor.from_numpy(G["labels"])
-
-    def barrier():
-        _lib.check(L.b200_stream_synchronize(stream))
-        torch.cuda.synchronize()
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-
-    def timed(fetches, feed, steps, prefetch=None):
-        """-> (device ms between events on the session stream, launches, last loss).
-
-        prefetch: list of (HostTensor x, HostTensor labels) buffer pairs used round-robin; the
-        inputs of step i+1 are staged (Session.stage: H2D on the copy stream) before step i is
-        run, so every step's host->device copy is inside the timed region but overlaps the
-        previous step's kernels."""
-        launches, loss, enq = 0, None, 0
-        barrier()
-        _lib.check(L.b200_event_record(ev0, stream))
-        staged = None
-        if prefetch:
-            staged = tuple(sess.stage(t) for t in prefetch[0])
-        for i in range(steps):
-            if prefetch:
-                nxt = (tuple(sess.stage(t) for t in prefetch[(i + 1) % len(prefetch)])
-                       if i + 1 < steps else None)
-                loss = sess.run(fetches, {G["xp"]: staged[0], G["lp"]: staged[1]})[0]
-                staged = nxt
-            else:
-                loss = sess.run(fetches, feed)[0]
-            st = sess.last_run_stats()
-            launches += st["kernels_launched"]
-            enq += st["host_enqueue_us"]
-        timed.host_enqueue_us = enq / max(steps, 1)
-        _lib.check(L.b200_event_record(ev1, stream))
-        barrier()
-        ms = ctypes.c_float()
-        _lib.check(L.b200_event_elapsed_ms(ev0, ev1, ctypes.byref(ms)))
-        if world > 1:
-            import torch.distributed as dist
-            t = torch.tensor([ms.value], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
-            return float(t.item()), launches, float(loss)
-        return ms.value, launches, float(loss)
-
-    res_fetch = list(G["resident"])
-    fed_fetch = list(G["fed"])
-    feed = {G["xp"]: hx, G["lp"]: hl}
-    # second pinned buffer pair: the input pipeline fills one while the other is in flight
-    buffers = [(hx, hl), (client.HostTensor.from_numpy(G["x"]), client.HostTensor.from_numpy(G["labels"]))]
-    warm = max(args.warmup, 3)
-    for _ in range(warm):
-        sess.run(res_fetch)
-        sess.run(fed_fetch, feed)
-    timed(fed_fetch, None, warm, prefetch=buffers)
-
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ms_res, launches, loss_res = timed(res_fetch, None, args.steps)
-    host_enqueue_us = timed.host_enqueue_us
-    ms_sync, _, _ = timed(fed_fetch, feed, args.steps)  # feed pinned buffers, copy inside Run()
-    h2d = sess.last_run_stats()["h2d_bytes"]
-    ms_e2e, _, loss_e2e = timed(fed_fetch, None, args.steps, prefetch=buffers)
-    clocks = sampler.summary() if rank == 0 else None
-    assert sum(client.HostTensor.numpy(t).nbytes for t in buffers[0]) == h2d
-    d2h = sess.last_run_stats()["d2h_bytes"]
-
-    # ---- roofline pass: per-launch device time of the tcgen05 GEMM, events on the same stream
-    _lib.check(L.b200_profile_begin())
-    prof_steps = min(args.steps, 20)
-    for _ in range(prof_steps):
-        sess.run(res_fetch)
-    gemm_ms, gemm_n, gemm_fl = ctypes.c_double(), ctypes.c_uint64(), ctypes.c_double()
-    _lib.check(L.b200_profile_end(ctypes.byref(gemm_ms), ctypes.byref(gemm_n), ctypes.byref(gemm_fl)))
-    # what an event pair with nothing between costs on this stream (reported next to the raw
-    # per-launch time: the bracket itself, not the kernel, explains why the kernel's share of the
-    # step looks larger here than in the ncu launch list)
-    pair = []
-    for _ in range(50):
-        _lib.check(L.b200_event_record(ev0, stream))
-        _lib.check(L.b200_event_record(ev1, stream))
-        _lib.check(L.b200_stream_synchronize(stream))
-        ms_pair = ctypes.c_float()
-        _lib.check(L.b200_event_elapsed_ms(ev0, ev1, ctypes.byref(ms_pair)))
-        pair.append(ms_pair.value * 1e3)
-    event_pair_us = statistics.median(pair)
-
-    if rank != 0:
-        sess.close()
+    b = Bench(args)
+    records = {}
+    for name in args.workloads:
+        records[name] = b.run_workload(name)
+    if b.world > 1:
         import torch.distributed as dist
         dist.barrier()
-        dist.destroy_process_group()
-        return
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    bf16_sustained = peaks.get("bf16_tflops_sustained")
-    if bf16_sustained:
-        peak, peak_src = 0.5 * bf16_sustained, ("0.5 x measured sustained bf16 cuBLAS (%.1f TF): "
-                                                "no measured TF32 figure in MEASURED_PEAKS.json"
-                                                % bf16_sustained)
-    else:
-        peak, peak_src = 0.5 * 1400.0, "0.5 x fallback sustained bf16 1.4 PF (B200_PROFILING.md)"
-    achieved = (gemm_fl.value / 1e12) / (gemm_ms.value / 1e3) if gemm_ms.value > 0 else 0.0
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")))[
-            "dram_bytes_per_launch"]
-    except Exception:
-        pass
-    base = cpu_baseline() if world == 1 and not args.no_cpu_baseline and not lenet else None
-    n_samples = batch * world * args.steps
-    working_set_mb = (2 * BATCH * WIDTH * 4 + LAYERS * WIDTH * WIDTH * 4 * 2 +
-                      8 * BATCH * WIDTH * 4) / 1e6
-    line = {
-        "metric": METRIC, "value": n_samples / (ms_res / 1e3), "unit": "samples/s",
-        "n_gpus": world, "steps": args.steps, "warmup": warm,
-        "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 graph; GEMMs on TF32 tensor cores, fp32 accumulate",
-        "data": "synthetic",
-        "config": {"workload": ("lenet-5 batch 512/replica NHWC fp32 fwd+bwd+sgd (BASELINE "
-                                "configs[2]); Session.Run([loss, train_op])") if lenet else
-                               ("mlp-3x1024 batch 4096/replica fp32 fwd+bwd+sgd "
-                                "(BASELINE configs[1]); Session.Run([loss, train_op])"),
-                   "global_batch": batch * world, "parallelism": "dp%d" % world,
-                   "l2": ("no flush: per-step working set > 126 MB L2 (conv2 patch matrix alone is "
-                          "321 MB)") if lenet else
-                         ("no flush: per-step working set ~%.0f MB > 126 MB L2" % working_set_mb),
-                   "loss_resident": loss_res, "loss_e2e": loss_e2e,
-                   "host_enqueue_us_per_step": host_enqueue_us},
-        "clocks": clocks,
-        "e2e": {"value": n_samples / (ms_e2e / 1e3), "unit": "samples/s",
-                "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h,
-                "how": ("Session.stage() of step i+1's pinned inputs (copy stream) before "
-                        "Session.run of step i; loss fetched to the host every step"),
-                "unpipelined_value": n_samples / (ms_sync / 1e3),
-                "unpipelined_ms_per_step": ms_sync / args.steps},
-        "gpu_launches": launches,
-        "roofline": {"kernel": "gemm_tcgen05_kernel (kind::tf32)", "bound": "tensor",
-                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                     "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "peak_source": peak_src, "launches_timed": int(gemm_n.value),
-                     "us_per_launch": 1e3 * gemm_ms.value / max(1, gemm_n.value),
-                     "empty_event_pair_us": event_pair_us,
-                     "achieved_net_of_event_pair": ((gemm_fl.value / 1e12) /
-                                                    max(1e-9, gemm_ms.value / 1e3 -
-                                                        gemm_n.value * event_pair_us / 1e6)),
-                     "flops_per_launch": (gemm_fl.value / max(1, gemm_n.value)),
-                     "gemm_share_of_step": (gemm_ms.value / prof_steps) / (ms_res / args.steps)},
-        "cpu_baseline": base,
-    }
-    os.write(real_stdout, (json.dumps(line) + "\n").encode())
-    sess.close()
-    if world > 1:
+    if b.rank == 0:
+        head = args.workloads[0]
+        line = dict(records[head])
+        line["workloads"] = {n: r for n, r in records.items() if n != head}
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+    if b.world > 1:
         import torch.distributed as dist
-        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -493,9 +520,16 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="mlp", choices=["mlp", "lenet"],
-                    help="mlp = BASELINE configs[1] (default, the metric's config); lenet = configs[2]")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--workloads", default=",".join(ALL_WORKLOADS),
+                    help="comma list; the first is the line's top-level record (default: mlp = "
+                         "BASELINE configs[1], then lenet = configs[2], mlp_bf16 = configs[3])")
+    ap.add_argument("--workload", default=None, help="shorthand for --workloads <one>")
     args = ap.parse_args()
+    args.workloads = [args.workload] if args.workload else [s for s in args.workloads.split(",") if s]
+    for n in args.workloads:
+        if n not in ALL_WORKLOADS:
+            raise SystemExit("unknown workload %r (choose from %s)" % (n, ALL_WORKLOADS))
     if args.impl == "reference":
         run_reference(args)
     else:

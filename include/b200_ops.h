@@ -61,6 +61,12 @@ B200_API int b200_device_count(void);
 B200_API int b200_set_device(int ordinal);
 /* Kernels launched by this library in the calling process since load (all threads). */
 B200_API uint64_t b200_launch_count(void);
+/* Gradient exchanges issued by this process since load: launches of the NVLink peer-memory
+ * all-reduce kernel (b200_peer_all_reduce) and NCCL all-reduce calls (b200_nccl_all_reduce*).
+ * bench.py reads it around the timed region to say which exchange actually ran (the device falls
+ * back to NCCL when the peer arena cannot be mapped).  No reference counterpart: the reference
+ * ships no collective (third_party/nccl.BUILD has no call sites). */
+B200_API void b200_collective_counts(uint64_t* peer_launches, uint64_t* nccl_calls);
 /* Measurement hook for bench.py's roofline: between begin and end every tensor-core GEMM launch
  * (MatMul, BatchMatMul, the conv GEMMs) is bracketed by CUDA events on its own stream;
  * end() waits for them and returns the summed device time, launch count and 2*M*N*K FLOPs. */

@@ -35,6 +35,7 @@ SIGNATURES = {
     "b200_device_count": (c_int, []),
     "b200_set_device": (c_int, [c_int]),
     "b200_launch_count": (ctypes.c_uint64, []),
+    "b200_collective_counts": (None, [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "b200_profile_begin": (c_int, []),
     "b200_profile_end": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64),
                                  ctypes.POINTER(ctypes.c_double)]),

@@ -93,6 +93,7 @@ __device__ __forceinline__ void pdl_prologue() {
   pdl_launch_dependents();
   pdl_wait();
 }
+void note_collective(bool peer);  // runtime.cu: b200_collective_counts()
 bool pdl_enabled();  // runtime.cu: on unless B200TF_NO_PDL is set
 // kernel<<<grid, block, smem, stream>>>(args...) with programmatic stream serialization allowed:
 // the grid may be scheduled while its predecessor in the stream drains (every kernel begins with

@@ -363,5 +363,6 @@ int b200_peer_all_reduce(void* arena, int dtype, size_t offset_bytes, int64_t co
     return B200_INTERNAL;
   }
   note_launch();
+  note_collective(true);
   return check_launch("b200_peer_all_reduce");
 }

@@ -17,6 +17,7 @@ namespace b200 {
 
 static thread_local char g_err[1024] = "";
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<uint64_t> g_peer_collectives{0}, g_nccl_collectives{0};
 static std::atomic<int> g_matmul_precision{0};
 
 void set_last_error(const char* fmt, ...) {
@@ -27,6 +28,9 @@ void set_last_error(const char* fmt, ...) {
 }
 
 void note_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+void note_collective(bool peer) {
+  (peer ? g_peer_collectives : g_nccl_collectives).fetch_add(1, std::memory_order_relaxed);
+}
 
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
@@ -223,6 +227,10 @@ int b200_set_device(int ordinal) {
   return B200_OK;
 }
 uint64_t b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+void b200_collective_counts(uint64_t* peer_launches, uint64_t* nccl_calls) {
+  if (peer_launches) *peer_launches = g_peer_collectives.load(std::memory_order_relaxed);
+  if (nccl_calls) *nccl_calls = g_nccl_collectives.load(std::memory_order_relaxed);
+}
 
 int b200_set_matmul_precision(int mode) {
   if (mode < 0 || mode > 1) {
@@ -404,6 +412,7 @@ int b200_nccl_group_end(void) {
 int b200_nccl_all_reduce(int dtype, const void* sendbuf, void* recvbuf, int64_t count, int average,
                          void* comm, void* stream) {
   if (!load_nccl()) return B200_FAILED_PRECONDITION;
+  note_collective(false);
   int nccl_type;
   if (dtype == B200_DT_FLOAT)
     nccl_type = 7;
@@ -432,6 +441,7 @@ int b200_nccl_all_gather_bytes(const void* sendbuf, void* recvbuf, int64_t bytes
 int b200_nccl_all_reduce_sum(int dtype, const void* sendbuf, void* recvbuf, int64_t count,
                              void* comm, void* stream) {
   if (!load_nccl()) return B200_FAILED_PRECONDITION;
+  note_collective(false);
   int nccl_type;
   if (dtype == B200_DT_FLOAT)
     nccl_type = 7;  // ncclFloat32

@@ -68,7 +68,7 @@ namespace {
 tensorflow::Allocator* HostTensorAllocator() {
   static tensorflow::Allocator* a = [] {
     if (b200_device_count() > 0)
-      return static_cast<tensorflow::Allocator*>(new tensorflow::GPUHostAllocator);
+      return static_cast<tensorflow::Allocator*>(tensorflow::GPUHostAllocator::Process());
     return tensorflow::cpu_allocator();
   }();
   return a;
@@ -113,6 +113,7 @@ TF_Tensor* TF_NewTensor(TF_DataType dtype, const int64_t* dims, int num_dims, vo
                         void* deallocator_arg) {
   TensorShape shape;
   for (int i = 0; i < num_dims; ++i) shape.AddDim(dims[i]);
+  if (!shape.IsValid(tensorflow::DataTypeSize(static_cast<DataType>(dtype)))) return nullptr;
   const size_t need =
       static_cast<size_t>(shape.num_elements()) * tensorflow::DataTypeSize(static_cast<DataType>(dtype));
   if (need > len || need == 0) {
@@ -129,6 +130,7 @@ TF_Tensor* TF_AllocateTensor(TF_DataType dtype, const int64_t* dims, int num_dim
   TensorShape shape;
   for (int i = 0; i < num_dims; ++i) shape.AddDim(dims[i]);
   (void)len;
+  if (!shape.IsValid(tensorflow::DataTypeSize(static_cast<DataType>(dtype)))) return nullptr;
   Tensor t(HostTensorAllocator(), static_cast<DataType>(dtype), shape);
   if (!t.IsInitialized()) return nullptr;
   return new TF_Tensor{std::move(t)};
@@ -561,8 +563,11 @@ static Status ExtendSession(TF_Session* s) {
       delta.node.push_back(s->graph->operations[i]->node);
     if (delta.node.empty()) return Status::OK();
     const bool first = s->num_nodes_sent == 0;
-    s->num_nodes_sent = s->graph->operations.size();
-    return first ? s->session->Create(delta) : s->session->Extend(delta);
+    // last_num_graph_nodes advances only on success (c_api.cc ExtendSessionGraphHelper): a failed
+    // extend leaves the session unchanged and the same delta is offered again next time.
+    Status st = first ? s->session->Create(delta) : s->session->Extend(delta);
+    if (st.ok()) s->num_nodes_sent += delta.node.size();
+    return st;
   }
 }
 

@@ -57,6 +57,18 @@ Status DirectSession::ParseTensorName(const std::string& name, std::string* node
 }
 
 Status DirectSession::AddNodes(const GraphDef& graph) {
+  // Transactional, like the reference's Extend (a failed GraphDef leaves the session's graph
+  // unchanged, direct_session.cc ExtendLocked): on any error roll nodes_ / node_index_ back.
+  const size_t rollback_to = nodes_.size();
+  Status s = AddNodesImpl(graph);
+  if (!s.ok()) {
+    for (size_t i = rollback_to; i < nodes_.size(); ++i) node_index_.erase(nodes_[i]->def.name);
+    nodes_.resize(rollback_to);
+  }
+  return s;
+}
+
+Status DirectSession::AddNodesImpl(const GraphDef& graph) {
   const size_t first_new = nodes_.size();
   for (const NodeDef& nd : graph.node) {
     if (node_index_.count(nd.name))
@@ -74,10 +86,8 @@ Status DirectSession::AddNodes(const GraphDef& graph) {
       continue;
     }
     TF_RETURN_IF_ERROR(ValidateNodeDef(&item->def, *op_def));
-    if (!nd.device.empty() && nd.device.find("CPU") != std::string::npos &&
-        nd.device.find("cpu") != std::string::npos)
-      return errors::InvalidArgument("Node '", nd.name, "' requests device '", nd.device,
-                                     "' but this runtime places every node on the GPU");
+    // Explicit /cpu:0 placements (imported inference graphs pin their string / parsing front
+    // end there) are accepted and ignored: every node this runtime can run runs on the GPU.
     node_index_[nd.name] = static_cast<int>(nodes_.size());
     nodes_.push_back(std::move(item));
   }
@@ -654,7 +664,11 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
         if (kernel->input_is_ref(i))
           return errors::InvalidArgument("Node '", item->def.name, "': input ", i,
                                          " is a reference and cannot be fed");
-        input_values.push_back(TensorValue(want_host ? &feed_host[src.feed] : &feed_dev[src.feed]));
+        // A feed may have several consumers (and the caller may still hold the buffer): hand the
+        // kernel its own handle, so that forward_input_or_allocate_output() never sees an
+        // exclusively owned buffer and cannot overwrite the feed in place.
+        deref_storage.push_back(want_host ? feed_host[src.feed] : feed_dev[src.feed]);
+        input_values.push_back(TensorValue(&deref_storage.back()));
         continue;
       }
       Entry& en = entries[entry_index_of(ek, src.id)];
@@ -674,6 +688,15 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
         en.pending = nullptr;
       }
       Tensor* t = &en.val;
+      const int eidx_in = entry_index_of(ek, src.id);
+      if (en.ref == nullptr && (pending[eidx_in] > 1 || ek->entry_is_fetch[eidx_in])) {
+        // Other plan nodes still have to read this entry, or it is fetched: the reference gives
+        // every edge its own Tensor (executor.cc Entry copies), so a kernel that forwards an
+        // input in place (Relu, BiasAdd, ReluGrad ...) only ever does so for a buffer nobody else
+        // will read.  Here the entry is shared, so the extra handle keeps RefCountIsOne() false.
+        deref_storage.push_back(en.val);
+        t = &deref_storage.back();
+      }
       if (en.ref != nullptr) {  // dereference a variable for a by-value consumer
         std::lock_guard<std::mutex> rl(*en.ref_mu);
         deref_storage.push_back(*en.ref);

@@ -128,6 +128,7 @@ class DirectSession : public Session {
   }
   static Status ParseTensorName(const std::string& name, std::string* node, int* slot);
   Status AddNodes(const GraphDef& graph);
+  Status AddNodesImpl(const GraphDef& graph);
   Status GetOrCreateExecutors(const std::vector<std::string>& feeds,
                               const std::vector<std::string>& fetches,
                               const std::vector<std::string>& targets, ExecutorsAndKeys** out);

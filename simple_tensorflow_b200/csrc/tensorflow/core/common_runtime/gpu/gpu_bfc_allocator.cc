@@ -13,7 +13,12 @@ GPUBFCAllocator::GPUBFCAllocator(int device_id, size_t total_memory, const std::
       next_region_bytes_(256u << 20) {}
 
 GPUBFCAllocator::~GPUBFCAllocator() {
+  b200_set_device(device_id_);
   for (auto& r : regions_) b200_free(r.first);
+}
+
+void GPUBFCAllocator::Unref() {
+  if (refs_.fetch_sub(1, std::memory_order_acq_rel) == 1) delete this;
 }
 
 void GPUBFCAllocator::InsertFree(char* ptr, size_t size) { free_by_size_.insert({size, ptr}); }
@@ -40,7 +45,13 @@ bool GPUBFCAllocator::Extend(size_t rounded_bytes) {
   return true;
 }
 
-void* GPUBFCAllocator::AllocateRaw(size_t /*alignment*/, size_t num_bytes) {
+void* GPUBFCAllocator::AllocateRaw(size_t alignment, size_t num_bytes) {
+  void* p = AllocateLocked(alignment, num_bytes);
+  if (p != nullptr) refs_.fetch_add(1, std::memory_order_relaxed);  // released by DeallocateRaw
+  return p;
+}
+
+void* GPUBFCAllocator::AllocateLocked(size_t /*alignment*/, size_t num_bytes) {
   if (num_bytes == 0) return nullptr;
   const size_t rounded = RoundUp(num_bytes, kMinAllocationSize);
   std::lock_guard<std::mutex> l(mu_);
@@ -70,9 +81,13 @@ void* GPUBFCAllocator::AllocateRaw(size_t /*alignment*/, size_t num_bytes) {
 
 void GPUBFCAllocator::DeallocateRaw(void* p) {
   if (p == nullptr) return;
+  if (DeallocateLocked(p)) Unref();  // may delete this: the lock is already released
+}
+
+bool GPUBFCAllocator::DeallocateLocked(void* p) {
   std::lock_guard<std::mutex> l(mu_);
   auto it = chunks_.find(static_cast<char*>(p));
-  if (it == chunks_.end() || !it->second.in_use) return;
+  if (it == chunks_.end() || !it->second.in_use) return false;
   it->second.in_use = false;
   stats_.bytes_in_use -= it->second.size;
   // coalesce with the next chunk, if free and in the same region (contiguous address)
@@ -101,6 +116,7 @@ void GPUBFCAllocator::DeallocateRaw(void* p) {
     }
   }
   InsertFree(it->second.ptr, it->second.size);
+  return true;
 }
 
 void GPUBFCAllocator::GetStats(AllocatorStats* stats) {
@@ -108,8 +124,13 @@ void GPUBFCAllocator::GetStats(AllocatorStats* stats) {
   *stats = stats_;
 }
 
+GPUHostAllocator* GPUHostAllocator::Process() {
+  static GPUHostAllocator* a = new GPUHostAllocator;  // leaked on purpose: process lifetime
+  return a;
+}
 GPUHostAllocator::~GPUHostAllocator() {
   for (auto& kv : free_) b200_host_free(kv.second);
+  for (auto& kv : live_) b200_host_free(kv.first);  // nothing may still use them at this point
 }
 void* GPUHostAllocator::AllocateRaw(size_t, size_t num_bytes) {
   if (num_bytes == 0) return nullptr;

@@ -10,6 +10,7 @@
 #ifndef B200TF_CORE_COMMON_RUNTIME_GPU_GPU_BFC_ALLOCATOR_H_
 #define B200TF_CORE_COMMON_RUNTIME_GPU_GPU_BFC_ALLOCATOR_H_
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <set>
@@ -25,6 +26,11 @@ class GPUBFCAllocator : public Allocator {
   // total_memory: cap on the sum of regions (0 = no cap beyond the device).
   GPUBFCAllocator(int device_id, size_t total_memory, const std::string& name);
   ~GPUBFCAllocator() override;
+  // Lifetime: the device that created the arena holds one reference and every live allocation
+  // holds one, so a Tensor that outlives its session (TF_DeleteSession before TF_DeleteTensor is
+  // legal in the reference's C API) still deallocates into a live allocator; the regions are
+  // returned to the driver when the last of them goes.  The device calls Unref() instead of delete.
+  void Unref();
   std::string Name() override { return name_; }
   void* AllocateRaw(size_t alignment, size_t num_bytes) override;
   void DeallocateRaw(void* ptr) override;
@@ -39,6 +45,8 @@ class GPUBFCAllocator : public Allocator {
     bool in_use;
   };
   bool Extend(size_t rounded_bytes);
+  void* AllocateLocked(size_t alignment, size_t num_bytes);
+  bool DeallocateLocked(void* ptr);
   void InsertFree(char* ptr, size_t size);
   void RemoveFree(char* ptr, size_t size);
 
@@ -51,12 +59,17 @@ class GPUBFCAllocator : public Allocator {
   std::vector<std::pair<char*, size_t>> regions_;
   size_t next_region_bytes_;
   AllocatorStats stats_;
+  std::atomic<long long> refs_{1};
 };
 
 // Pinned host memory for feeds/fetches (the role of PoolAllocator + CUDAHostAllocator,
 // common_runtime/gpu/pool_allocator.h): size-bucketed free lists over b200_host_malloc.
 class GPUHostAllocator : public Allocator {
  public:
+  // The process-lifetime instance every device and the C API share (the reference's
+  // ProcessState::GetCUDAHostAllocator, common_runtime/gpu/process_state.cc): fetched tensors
+  // may outlive the session that produced them.  Never destroyed.
+  static GPUHostAllocator* Process();
   ~GPUHostAllocator() override;
   std::string Name() override { return "cuda_host_bfc"; }
   void* AllocateRaw(size_t alignment, size_t num_bytes) override;

@@ -82,6 +82,8 @@ BaseGPUDevice::~BaseGPUDevice() {
   if (h2d_stream_) h2d_stream_->BlockHostUntilDone();
   if (collective_stream_) collective_stream_->BlockHostUntilDone();
   if (stream_) stream_->BlockHostUntilDone();
+  // tensors that outlive the session keep the arena alive (gpu_bfc_allocator.h)
+  if (gpu_allocator_) gpu_allocator_->Unref();
 }
 
 Status BaseGPUDevice::Create(int gpu_id, size_t memory_limit_bytes,
@@ -112,12 +114,12 @@ Status BaseGPUDevice::Create(int gpu_id, size_t memory_limit_bytes,
     const size_t reserve = std::max<size_t>(300u << 20, static_cast<size_t>(free_b * 0.05));
     memory_limit_bytes = free_b > reserve ? free_b - reserve : free_b;
   }
-  d->gpu_allocator_.reset(new GPUBFCAllocator(gpu_id, memory_limit_bytes,
-                                              strings::StrCat("GPU_", gpu_id, "_bfc")));
-  d->host_allocator_.reset(new GPUHostAllocator());
-  d->context_.reset(new GPUDeviceContext(d->stream_.get(), d->host_allocator_.get()));
+  d->gpu_allocator_ = new GPUBFCAllocator(gpu_id, memory_limit_bytes,
+                                          strings::StrCat("GPU_", gpu_id, "_bfc"));
+  d->host_allocator_ = GPUHostAllocator::Process();
+  d->context_.reset(new GPUDeviceContext(d->stream_.get(), d->host_allocator_));
   d->collective_context_.reset(
-      new GPUDeviceContext(d->collective_stream_.get(), d->host_allocator_.get()));
+      new GPUDeviceContext(d->collective_stream_.get(), d->host_allocator_));
   d->gpu_device_info_.stream = d->stream_.get();
   d->gpu_device_info_.default_context = d->context_.get();
   d->gpu_device_info_.gpu_id = gpu_id;
@@ -143,7 +145,7 @@ Status BaseGPUDevice::Sync() {
 
 Status BaseGPUDevice::MakeTensorFromHost(const Tensor& host, Tensor* device_tensor) {
   b200_set_device(gpu_id_);
-  Tensor t(gpu_allocator_.get(), host.dtype(), host.shape());
+  Tensor t(gpu_allocator_, host.dtype(), host.shape());
   if (!t.IsInitialized())
     return errors::ResourceExhausted("OOM when allocating feed tensor ", host.shape().DebugString());
   Status s;
@@ -156,7 +158,7 @@ Status BaseGPUDevice::MakeTensorFromHost(const Tensor& host, Tensor* device_tens
 Status BaseGPUDevice::StageTensorFromHost(const Tensor& host, Tensor* device_tensor,
                                           gpu::Event* ready) {
   b200_set_device(gpu_id_);
-  Tensor t(gpu_allocator_.get(), host.dtype(), host.shape());
+  Tensor t(gpu_allocator_, host.dtype(), host.shape());
   if (!t.IsInitialized())
     return errors::ResourceExhausted("OOM when allocating staged feed ", host.shape().DebugString());
   // The arena hands out chunks whose last use may still be queued on the compute stream.
@@ -176,7 +178,7 @@ Status BaseGPUDevice::StageTensorFromHost(const Tensor& host, Tensor* device_ten
 
 Status BaseGPUDevice::CopyTensorToHost(const Tensor& device_tensor, Tensor* host) {
   b200_set_device(gpu_id_);
-  Tensor t(host_allocator_.get(), device_tensor.dtype(), device_tensor.shape());
+  Tensor t(host_allocator_, device_tensor.dtype(), device_tensor.shape());
   if (!t.IsInitialized())
     return errors::ResourceExhausted("OOM when allocating pinned fetch buffer");
   Status s;

@@ -42,8 +42,8 @@ class BaseGPUDevice : public Device {
   ~BaseGPUDevice() override;
 
   Allocator* GetAllocator(AllocatorAttributes attr) override {
-    return attr.on_host() ? static_cast<Allocator*>(host_allocator_.get())
-                          : static_cast<Allocator*>(gpu_allocator_.get());
+    return attr.on_host() ? static_cast<Allocator*>(host_allocator_)
+                          : static_cast<Allocator*>(gpu_allocator_);
   }
   void Compute(OpKernel* op_kernel, OpKernelContext* context) override;
   Status Sync() override;
@@ -78,15 +78,15 @@ class BaseGPUDevice : public Device {
   // ThenWaitFor(compute), gpu_util.cc:300-306) and returns at once; `ready` is recorded behind
   // the copy.  The caller makes the consuming stream wait for `ready`.
   Status StageTensorFromHost(const Tensor& host, Tensor* device_tensor, gpu::Event* ready);
-  Allocator* host_allocator() const { return host_allocator_.get(); }
+  Allocator* host_allocator() const { return host_allocator_; }
 
  private:
   BaseGPUDevice(int gpu_id, const std::string& name);
   const int gpu_id_;
   std::unique_ptr<gpu::Stream> stream_, h2d_stream_, collective_stream_;
   std::unique_ptr<gpu::Event> h2d_fence_;
-  std::unique_ptr<GPUBFCAllocator> gpu_allocator_;
-  std::unique_ptr<GPUHostAllocator> host_allocator_;
+  GPUBFCAllocator* gpu_allocator_ = nullptr;   // ref-counted: Unref() in the destructor
+  GPUHostAllocator* host_allocator_ = nullptr;  // GPUHostAllocator::Process(), never destroyed
   std::unique_ptr<GPUDeviceContext> context_, collective_context_;
   GpuDeviceInfo gpu_device_info_;
   void* collective_comm_ = nullptr;

@@ -128,6 +128,7 @@ bool ParseShape(Reader r, TensorShape* shape) {
       if (!d.ok) return false;
       if (size < 0) representable = false;
       shape->AddDim(size);
+      if (shape->dims() > 254) return false;  // TensorShape::MaxDimensions()
     } else {
       if ((t >> 3) == 3 && (t & 7) == 0) {
         if (r.varint()) representable = false;
@@ -173,9 +174,18 @@ bool ParseTensor(Reader r, Tensor* out) {
     const uint64_t t = r.varint();
     const int field = static_cast<int>(t >> 3), wt = static_cast<int>(t & 7);
     switch (field) {
-      case 1: dtype = static_cast<DataType>(r.varint()); break;
-      case 2: if (!ParseShape(r.bytes(), &shape)) return false; break;
-      case 4: content = r.bytes(); has_content = true; break;
+      case 1:
+        if (wt != 0) return false;  // dtype is a varint enum: anything else is a malformed proto
+        dtype = static_cast<DataType>(r.varint());
+        break;
+      case 2:
+        if (wt != 2 || !ParseShape(r.bytes(), &shape)) return false;
+        break;
+      case 4:
+        if (wt != 2) return false;
+        content = r.bytes();
+        has_content = true;
+        break;
       case 5:
         if (wt == 2) {
           Reader v = r.bytes();
@@ -210,6 +220,12 @@ bool ParseTensor(Reader r, Tensor* out) {
   const size_t esize = DataTypeSize(dtype);
   if (!r.ok || unsupported || esize == 0 || dtype == DT_COMPLEX64 || dtype == DT_COMPLEX128)
     return false;
+  // Untrusted dimensions: reject negative / overflowing products before any allocation
+  // (TensorShape::IsValid in the reference, tensor.cc Tensor::FromProto), and never allocate
+  // more than the proto itself can describe -- a typed *_val list repeats its last value, so a
+  // tiny proto may legally describe a large tensor, but not an absurd one.
+  if (!shape.IsValid(esize)) return false;
+  if (static_cast<unsigned long long>(shape.num_elements()) * esize > (1ull << 34)) return false;
   Tensor t(dtype, shape);
   const int64 n = t.NumElements();
   if (n > 0 && !t.IsInitialized()) return false;

@@ -26,6 +26,26 @@ class TensorShape {
     for (int64 d : dims_) n *= d;
     return n;
   }
+  // TensorShape::IsValid (tensor_shape.cc): every dimension >= 0 and the element count (and,
+  // with `element_bytes`, the byte size) representable.  Untrusted shapes (GraphDef import,
+  // TF_NewTensor / TF_AllocateTensor) must pass this before num_elements() is trusted.
+  static constexpr int64 kMaxElements = int64(1) << 40;  // 1 Ti elements: far above 180 GB tensors
+  bool IsValid(size_t element_bytes = 1) const {
+    unsigned long long n = 1;
+    bool empty = false;
+    for (int64 d : dims_) {
+      if (d < 0) return false;
+      if (d == 0) empty = true;
+    }
+    if (empty) return true;  // zero elements: nothing can overflow
+    for (int64 d : dims_) {
+      if (n > static_cast<unsigned long long>(kMaxElements) / static_cast<unsigned long long>(d))
+        return false;
+      n *= static_cast<unsigned long long>(d);
+    }
+    if (element_bytes > 1 && n > (~0ull >> 1) / element_bytes) return false;
+    return true;
+  }
   bool IsSameSize(const TensorShape& b) const { return dims_ == b.dims_; }
   bool operator==(const TensorShape& b) const { return dims_ == b.dims_; }
   bool operator!=(const TensorShape& b) const { return dims_ != b.dims_; }

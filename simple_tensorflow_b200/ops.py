@@ -420,17 +420,33 @@ def _relu_grad(op, grad):
 
 @_register_gradient("SoftmaxCrossEntropyWithLogits")
 def _xent_grad(op, grad_loss, grad_backprop=None):
-    # nn_grad.py:323-333: backprop * expand_dims(grad_loss, -1); labels get no gradient here
+    # nn_grad.py:323-333: backprop * expand_dims(grad_loss, -1); labels get no gradient here.
+    # The GPU Mul kernel broadcasts a one-element operand only, so a per-example grad_loss
+    # ([batch] weights) is rejected while the graph is built instead of failing inside Run().
+    sg = _shape(grad_loss)
+    if sg is None or int(np.prod(sg, dtype=np.int64)) != 1:
+        raise NotImplementedError(
+            "gradient of SoftmaxCrossEntropyWithLogits with a per-example loss gradient %s needs a "
+            "row-broadcasting Mul, which is outside the hot path; reduce the loss with reduce_mean"
+            % (sg,))
     return multiply(op.outputs[1], grad_loss), None
 
 
 @_register_gradient("Mean")
 def _mean_grad(op, grad):
-    # math_grad.py _MeanGrad for a full reduction: grad / N broadcast to the input shape.
-    # grad is the scalar d(final)/d(mean); we emit it as a scalar and let Mul broadcast.
-    n = int(np.prod(_shape(op.inputs[0]), dtype=np.int64))
-    scale = constant(np.float32(1.0 / n), op.inputs[0].dtype)
-    return (multiply(grad, scale) if grad is not None else scale), None
+    # math_grad.py _MeanGrad for a full reduction: grad / N tiled to the input shape.
+    x = op.inputs[0]
+    n = int(np.prod(_shape(x), dtype=np.int64))
+    scale = constant(np.float32(1.0 / n), x.dtype)
+    g = multiply(grad, scale) if grad is not None else scale
+    if x.op.type == "SoftmaxCrossEntropyWithLogits" and x.name == x.op.outputs[0].name:
+        # the xent gradient multiplies its backprop by this scalar (one-element broadcast in the
+        # Mul kernel; the executor folds it into the xent kernel): no [batch] tile is materialised
+        return g, None
+    # any other producer (Relu, MatMul, Reshape ...) needs a gradient of the input's own shape,
+    # as _MeanGrad's tile() delivers: a constant 1/N tensor, scaled by the incoming scalar
+    tile = constant(np.full(_shape(x), 1.0 / n, np.float32), x.dtype)
+    return (multiply(tile, grad) if grad is not None else tile), None
 
 
 @_register_gradient("Conv2D")
@@ -571,6 +587,9 @@ class GradientDescentOptimizer:
                         reduced[id(v0)] = r
                     bucket, held = [], 0
             grads_and_vars = [(reduced[id(v)], v) for _, v in grads_and_vars]
+        # what ApplyGradientDescent consumes (the replica average when num_replicas > 1):
+        # fetchable, e.g. to check a data-parallel step against a full-batch reference
+        self.applied_gradients = list(grads_and_vars)
         for grad, var in grads_and_vars:
             if grad is None:
                 continue

@@ -162,7 +162,7 @@ def softmax_xent(logits, labels, bf16=False):
 
 def max_pool(x, ksize, strides, padding, oracle, bf16=False):
     n, h, w, c = x.shape
-    oh, ow, pt, pl = oracle.pool_geometry(x.shape, ksize, strides, padding)
+    oh, ow, pt, pl = pool_geometry(x.shape, ksize, strides, padding)
     dx = dev(x, bf16)
     out = empty((n, oh, ow, c), tdt(bf16), fill=float("nan"))
     call(lib().b200_max_pool, cdt(bf16), dx.data_ptr(), out.data_ptr(), n, h, w, c, oh, ow,
@@ -172,7 +172,7 @@ def max_pool(x, ksize, strides, padding, oracle, bf16=False):
 
 def max_pool_grad(x, grad, ksize, strides, padding, oracle, bf16=False):
     n, h, w, c = x.shape
-    oh, ow, pt, pl = oracle.pool_geometry(x.shape, ksize, strides, padding)
+    oh, ow, pt, pl = pool_geometry(x.shape, ksize, strides, padding)
     dx, dg = dev(x, bf16), dev(grad, bf16)
     out = empty(x.shape, tdt(bf16), fill=float("nan"))
     call(lib().b200_max_pool_grad, cdt(bf16), dx.data_ptr(), None, dg.data_ptr(), out.data_ptr(), n,
@@ -205,10 +205,33 @@ def argmax(x, axis):
     return host(out)
 
 
+def windowed(in_size, filt, stride, padding):
+    """SAME / VALID output size and leading pad, restated here from the documented rule
+    (core/framework/common_shape_fns.cc:19-47) INDEPENDENTLY of the oracle and of the product's
+    padding.h, so that the raw C-ABI tests do not take their geometry from the thing they check:
+    VALID: out = ceil((in - filt + 1) / stride), no padding;  SAME: out = ceil(in / stride),
+    total pad = max((out - 1) * stride + filt - in, 0), the smaller half goes in front."""
+    if padding == "VALID":
+        return -(-(in_size - filt + 1) // stride), 0
+    out = -(-in_size // stride)
+    total = max((out - 1) * stride + filt - in_size, 0)
+    return out, total // 2
+
+
 def _geom(oracle, in_shape, filter_shape, strides, padding):
-    g = oracle.conv_geometry(in_shape, filter_shape, strides, padding)
-    return _lib.ConvGeometry(g.batch, g.in_h, g.in_w, g.in_c, g.filter_h, g.filter_w, g.out_c,
-                             g.out_h, g.out_w, g.stride_h, g.stride_w, g.pad_top, g.pad_left)
+    n, h, w, c = in_shape
+    r, s, c2, k = filter_shape
+    assert c == c2
+    oh, pt = windowed(h, r, strides[0], padding)
+    ow, pl = windowed(w, s, strides[1], padding)
+    return _lib.ConvGeometry(n, h, w, c, r, s, k, oh, ow, strides[0], strides[1], pt, pl)
+
+
+def pool_geometry(in_shape, ksize, strides, padding):
+    n, h, w, c = in_shape
+    oh, pt = windowed(h, ksize[0], strides[0], padding)
+    ow, pl = windowed(w, ksize[1], strides[1], padding)
+    return oh, ow, pt, pl
 
 
 def conv2d(x, f, strides, padding, oracle, bf16=False):

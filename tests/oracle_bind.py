@@ -12,6 +12,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "_build", "liboracle.so")
+# Same source built with -ffp-contract=fast (FMA): the CPU ARM bench.py times, never the checker.
+ORACLE_FAST_SO = os.path.join(ORACLE_DIR, "_build", "liboracle_fast.so")
 
 i64 = ctypes.c_int64
 _f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
@@ -29,6 +31,8 @@ class ConvGeom(ctypes.Structure):
 
 
 _lib = None
+_libs = {}
+_kind = "exact"
 
 
 def _host_cpu():
@@ -49,8 +53,10 @@ def build():
     stamp = os.path.join(os.path.dirname(ORACLE_SO), "host.txt")
     built_on = open(stamp).read().strip() if os.path.exists(stamp) else None
     foreign = built_on is not None and built_on != _host_cpu()
-    if (not os.path.exists(ORACLE_SO)) or foreign or (
-            os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(ORACLE_SO)):
+    stale = any((not os.path.exists(so)) or
+                (os.path.exists(src) and os.path.getmtime(src) > os.path.getmtime(so))
+                for so in (ORACLE_SO, ORACLE_FAST_SO))
+    if stale or foreign:
         if foreign:
             subprocess.check_call(["make", "-C", ORACLE_DIR, "clean"], stdout=subprocess.DEVNULL)
         subprocess.check_call(["make", "-C", ORACLE_DIR], stdout=subprocess.DEVNULL)
@@ -59,8 +65,10 @@ def build():
 def lib():
     global _lib
     if _lib is None:
+        _lib = _libs.get(_kind)
+    if _lib is None:
         build()
-        L = ctypes.CDLL(ORACLE_SO)
+        L = ctypes.CDLL(ORACLE_FAST_SO if _kind == "fast" else ORACLE_SO)
         L.oracle_num_threads.restype = ctypes.c_int
         L.oracle_windowed_output_size.argtypes = [i64, i64, i64, ctypes.c_int] + \
             [ctypes.POINTER(i64)] * 3
@@ -94,8 +102,18 @@ def lib():
         L.oracle_conv2d_backprop_filter_f32.argtypes = [_f32p, _f32p, _f32p,
                                                         ctypes.POINTER(ConvGeom)]
         L.oracle_apply_gradient_descent_f32.argtypes = [_f32p, ctypes.c_float, _f32p, i64]
-        _lib = L
+        _lib = _libs[_kind] = L
     return _lib
+
+
+def select(kind):
+    """"exact" (default): the bit-stable checker build.  "fast": the FMA build that bench.py's
+    CPU arms time.  Returns the previous selection."""
+    global _lib, _kind
+    assert kind in ("exact", "fast")
+    prev, _kind = _kind, kind
+    _lib = None
+    return prev
 
 
 def _f32(a):

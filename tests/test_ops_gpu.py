@@ -453,19 +453,37 @@ def test_conv_family_bf16_vgg_layers(oracle, rng, cin, cout):
     assert au.rel_err(dw, oracle.conv2d_backprop_filter(x, fshape, dy, (1, 1), "SAME")) < TOL
 
 
-def test_conv2d_full_size_adjoint_property(oracle, rng):
-    # BASELINE config 3 full size (batch 512 LeNet conv2): <dy, conv(x,w)> == <dX, x> == <dW, w>
+def test_conv2d_full_size_vs_oracle(oracle, rng):
+    # BASELINE config 3 full size (batch 512 LeNet conv2, the shapes bench.py times): forward,
+    # input gradient and filter gradient against the CPU oracle, element-wise and in norm
     shape, fshape = (512, 14, 14, 32), (5, 5, 32, 64)
     x = rng.rand(*shape).astype(np.float32) - 0.5
     f = (rng.rand(*fshape).astype(np.float32) - 0.5) * 0.1
     y = au.conv2d(x, f, (1, 1), "SAME", oracle)
+    y_ref = oracle.conv2d(x, f, (1, 1), "SAME")
+    assert au.rel_err(y, y_ref) < TOL_TF32
     dy = rng.rand(*y.shape).astype(np.float32) - 0.5
     dx = au.conv2d_backprop_input(shape, f, dy, (1, 1), "SAME", oracle)
+    assert au.rel_err(dx, oracle.conv2d_backprop_input(shape, f, dy, (1, 1), "SAME")) < TOL_TF32
     dw = au.conv2d_backprop_filter(x, fshape, dy, (1, 1), "SAME", oracle)
+    assert au.rel_err(dw, oracle.conv2d_backprop_filter(x, fshape, dy, (1, 1), "SAME")) < TOL_TF32
+    # and the adjoint identities <dy, conv(x,w)> == <dX, x> == <dW, w> (size-independent property)
     lhs = float(np.sum(dy.astype(np.float64) * y))
     scale = float(np.sqrt(np.sum(dy.astype(np.float64) ** 2) * np.sum(y.astype(np.float64) ** 2)))
     assert abs(lhs - float(np.sum(dx.astype(np.float64) * x))) < 2e-3 * scale
     assert abs(lhs - float(np.sum(dw.astype(np.float64) * f))) < 2e-3 * scale
+
+
+def test_conv1_full_size_vs_oracle(oracle, rng):
+    # LeNet conv1 at batch 512 (C_in = 1: the direct first-layer kernels), forward + filter gradient
+    shape, fshape = (512, 28, 28, 1), (5, 5, 1, 32)
+    x = rng.rand(*shape).astype(np.float32) - 0.5
+    f = (rng.rand(*fshape).astype(np.float32) - 0.5) * 0.2
+    y_ref = oracle.conv2d(x, f, (1, 1), "SAME")
+    assert au.rel_err(au.conv2d(x, f, (1, 1), "SAME", oracle), y_ref) < TOL_TF32
+    dy = rng.rand(*y_ref.shape).astype(np.float32) - 0.5
+    dw = au.conv2d_backprop_filter(x, fshape, dy, (1, 1), "SAME", oracle)
+    assert au.rel_err(dw, oracle.conv2d_backprop_filter(x, fshape, dy, (1, 1), "SAME")) < TOL_TF32
 
 
 # =============================================================================== glue ops
