@@ -365,7 +365,7 @@ class Bench:
             barrier()
             ms = ctypes.c_float()
             _lib.check(L.b200_event_elapsed_ms(ev0, ev1, ctypes.byref(ms)))
-            loss = float(w.to_f32(loss))
+            loss = float(np.asarray(w.to_f32(loss)).reshape(-1)[0])
             if world > 1:
                 import torch.distributed as dist
                 t = torch.tensor([ms.value], device="cuda")

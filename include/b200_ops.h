@@ -265,6 +265,13 @@ B200_API int b200_scale(int dtype, const void* in, float scale, void* out, int64
 /* out[0] = sum(in[0..n)) * scale; fp32, deterministic (loss reduction: Mean/Sum glue). */
 B200_API int b200_reduce_sum(int dtype, const void* in, float scale, void* out, int64_t n,
                              void* stream);
+/* Sum / Mean over one contiguous run of axes: `in` viewed as [outer, reduce, inner],
+ * out[o, i] = scale * sum_r in[o, r, i]; fp32 accumulation, fixed order, float / bfloat16.
+ * Replaces ReductionOp<GPUDevice, T, SumReducer / MeanReducer> for the axis patterns that
+ * collapse to one reduced run (core/kernels/reduction_ops_common.h ReductionHelper::Simplify,
+ * reduction_ops_sum.cc, reduction_ops_mean.cc). */
+B200_API int b200_reduce(int dtype, const void* in, void* out, int64_t outer, int64_t reduce,
+                         int64_t inner, float scale, void* stream);
 
 /* ------------------------------------------------------------------ replica data-parallel
  * One NCCL all-reduce (sum) over a contiguous gradient arena on the compute stream

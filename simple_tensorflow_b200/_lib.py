@@ -104,6 +104,7 @@ SIGNATURES = {
     "b200_add_n": (c_int, [c_int, ctypes.POINTER(c_void_p), c_int, c_void_p, c_int64, c_void_p]),
     "b200_scale": (c_int, [c_int, c_void_p, c_float, c_void_p, c_int64, c_void_p]),
     "b200_reduce_sum": (c_int, [c_int, c_void_p, c_float, c_void_p, c_int64, c_void_p]),
+    "b200_reduce": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_float, c_void_p]),
     "b200_nccl_unique_id": (c_int, [c_void_p]),
     "b200_nccl_comm_init_rank": (c_int, [ctypes.POINTER(c_void_p), c_int, c_void_p, c_int]),
     "b200_nccl_comm_destroy": (c_int, [c_void_p]),

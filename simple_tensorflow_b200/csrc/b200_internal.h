@@ -60,6 +60,18 @@ struct GemmArgs {
   long long ld_features;
   const ConvAOperand* conv_a;      // non-null: A is gathered on the fly (a / lda unused)
 };
+// Halo-tile implicit-GEMM convolution (conv_halo.cu): unit stride, C and K whole 128-byte channel
+// blocks.  `filter` is the row-major [R*S*C, K] matrix (HWIO as stored).
+struct ConvHaloArgs {
+  const void* input;   // NHWC [N, H, W, C]
+  const void* filter;  // [R*S*C, K]
+  void* output;        // NHWC [N, OH, OW, K]
+  const void* bias;    // optional fused + bias[k]
+  bool relu;           // optional fused max(x, 0)
+  int N, H, W, C, K, R, S, pt, pl, OH, OW;
+};
+bool conv_halo_supported(int dtype, const ConvHaloArgs& a);
+int conv_halo(int dtype, const ConvHaloArgs& a, cudaStream_t stream);
 bool gemm_tcgen05_supported(const GemmArgs& g);
 // Can this convolution's patch operand be fetched by TMA im2col (channel / padding limits)?
 bool conv_a_supported(int dtype, const ConvAOperand& c);

@@ -14,8 +14,11 @@
 // conv_grad_input_ops.cc:57-87) with the GEMMs on the tcgen05 kernel (gemm_tcgen05.cu).  The
 // filter needs no reshuffle: HWIO is already the row-major [R*S*C, K] GEMM operand.  1x1/stride-1
 // convolutions skip the patch matrix entirely (same shortcut as conv_ops.cc:454-480).
-// Round-1 data path: the patch matrix is materialised in the caller-provided workspace; the
-// implicit-GEMM (TMA im2col) variant that removes this traffic is the next optimisation step.
+// Data paths, fastest first: unit-stride convolutions whose channel counts are whole 128-byte
+// blocks run the halo-tile kernel (conv_halo.cu: forward and, with the flipped filter, dInput);
+// other strides / the filter gradient use TMA im2col-mode loads on the tcgen05 GEMM (no patch
+// matrix either); first layers (C <= 4) use direct CUDA-core kernels; everything else
+// materialises the patch matrix in the caller-provided workspace.
 #include <cuda_bf16.h>
 #include <cstdlib>
 
@@ -546,6 +549,13 @@ int b200_conv2d(int dtype, const void* input, const void* filter, void* output,
   a.b_mn_major = true;
   ConvAOperand ca{input, g.N, g.H, g.W, g.C, g.R, g.S, g.OH, g.OW, g.sh, g.sw, g.pt, g.pl};
   static const bool no_implicit = getenv("B200TF_CONV_EXPLICIT") != nullptr;
+  if (!is_pointwise(g) && g.sh == 1 && g.sw == 1 && !no_implicit &&
+      b200_get_matmul_precision() == 0) {
+    // unit stride: halo tile in shared memory, every tap a shifted view of it (conv_halo.cu)
+    ConvHaloArgs h{input, filter, output, nullptr, false, g.N, g.H, g.W, g.C, g.K,
+                   g.R, g.S, g.pt, g.pl, g.OH, g.OW};
+    if (conv_halo_supported(dtype, h)) return conv_halo(dtype, h, s);
+  }
   if (is_pointwise(g)) {
     a.a = input;
     a.lda = g.C;
@@ -697,6 +707,12 @@ int b200_conv2d_backprop_input(int dtype, const void* filter, const void* out_ba
             static_cast<const __nv_bfloat16*>(filter), static_cast<__nv_bfloat16*>(workspace), g.R,
             g.S, g.C, g.K);
       note_launch();
+      {
+        // dInput = unit-stride convolution of dY with the flipped filter [R, S, K, C]
+        ConvHaloArgs h{out_backprop, workspace, in_backprop, nullptr, false, g.N, g.OH, g.OW, g.K,
+                       g.C, g.R, g.S, cd.pt, cd.pl, g.H, g.W};
+        if (conv_halo_supported(dtype, h)) return conv_halo(dtype, h, s);
+      }
       GemmArgs d = base_gemm(dtype);
       d.a = out_backprop;
       d.lda = g.K;

@@ -21,6 +21,7 @@
 
 #include <cuda_bf16.h>
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -81,6 +82,12 @@ struct GemmShape {
   int splits;         // split-K factor (1 = none)
   int kb_per_split;   // K blocks per split
   float* partial;     // [splits][batch][M][N] fp32 partial sums when splits > 1
+  // In-kernel split-K reduction (splits > 1): per-tile arrive / depart counters.  Every epilogue
+  // warp that has stored its partial rows arrives; once all splits of a tile have arrived the
+  // warps add the partials (ascending split order: deterministic) for their share of the rows
+  // and write C, so no second kernel and no second pass over the launch boundary is needed.
+  // nullptr: partials are left for splitk_reduce_kernel.
+  unsigned int* tickets;
   int a_map4d, b_map4d;  // MN-major operand described by a 4-D map: one TMA per stage
   // implicit-GEMM convolution A operand (conv_a != 0): K blocks enumerate (filter tap, channel block)
   int conv_a, cv_OW, cv_OH, cv_sh, cv_sw, cv_pt, cv_pl, cv_S, cv_C, cv_cblocks, cv_taps;
@@ -159,6 +166,45 @@ __host__ __device__ constexpr int partial_out_iters() {
 }
 struct GemmShape;
 __device__ __forceinline__ bool partial_out_tile(const GemmShape& s);
+
+constexpr int kSplitKSlots = 16, kSplitKMaxTiles = 1024;
+// [slot][0..kMaxTiles) arrivals, [slot][kMaxTiles..2*kMaxTiles) departures; zero at rest (the last
+// warp to depart from a tile resets both), one slot per launch in rotation so that launches on
+// different streams of a device never share counters.
+__device__ unsigned int g_splitk_tickets[kSplitKSlots][2 * kSplitKMaxTiles];
+
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {  // L2-coherent (never L1 / nc)
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_cg_f1(const float* p) {
+  float v;
+  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void store_out4(float* dst, const float4& a) {
+  *reinterpret_cast<float4*>(dst) = a;
+}
+__device__ __forceinline__ void store_out4(__nv_bfloat16* dst, const float4& a) {
+  __nv_bfloat162 lo = __floats2bfloat162_rn(a.x, a.y), hi = __floats2bfloat162_rn(a.z, a.w);
+  uint2 p;
+  p.x = *reinterpret_cast<uint32_t*>(&lo);
+  p.y = *reinterpret_cast<uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(dst) = p;
+}
+__device__ __forceinline__ void store_out1(float* dst, float a) { *dst = a; }
+__device__ __forceinline__ void store_out1(__nv_bfloat16* dst, float a) {
+  *dst = __float2bfloat16_rn(a);
+}
 
 // TIn: operand element type (float -> tf32 MMA, bf16 -> f16-kind MMA); TOut: stored type.
 template <typename TIn, typename TOut, bool kAMN, bool kBMN, int BN, int kCtas>
@@ -663,6 +709,85 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
         acc = 0;
         acc_phase ^= 1;
       }
+      if (partial_out && s.tickets != nullptr) {
+        // ---- in-kernel split-K reduction.  (1) publish this warp's partial rows
+        unsigned int* arrive = s.tickets + tile;
+        unsigned int* depart = s.tickets + kSplitKMaxTiles + tile;
+        const unsigned int expected = (unsigned int)s.splits * kCtas * 4u;
+        if (s.tma_store) {
+          if (lane == 0) {
+            tma_store_wait<0>();  // the bulk stores have been performed
+            asm volatile("fence.proxy.async;" ::: "memory");  // async-proxy writes -> generic
+          }
+          stores_in_flight = 0;
+        }
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+          atomicAdd(arrive, 1u);
+          // (2) all splits of this tile have published (every CTA of the grid is resident: the
+          // grid never exceeds one CTA per SM, see launch_gemm)
+          while (ld_acquire_gpu_u32(arrive) < expected) {
+          }
+        }
+        __syncwarp();
+        // (3) this warp reduces rows split, split + splits, ... of its 32-row group over all
+        // splits in ascending order and writes C (coalesced: a warp covers 128 columns per access)
+        const bool n4 = (s.N & 3) == 0 && (s.ldc & 3) == 0 && (s.strideC & 3) == 0 &&
+                        ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+        const long long per_split = (long long)s.batch * s.M * s.N;
+        for (int j = split; j < 32; j += s.splits) {
+          const int r = row0 + j;
+          if (r >= s.M) break;
+          const float* prow0 = s.partial + ((long long)b * s.M + r) * (long long)s.N;
+          TOut* crow_r = C + (long long)b * s.strideC + (long long)r * s.ldc;
+          if (n4) {
+#pragma unroll
+            for (int i = 0; i < BN / 128; ++i) {
+              const int col = n0 + (i * 32 + lane) * 4;
+              if (col < s.N) {
+                float4 a = ld_cg_f4(prow0 + col);
+                for (int sp = 1; sp < s.splits; ++sp) {
+                  const float4 v = ld_cg_f4(prow0 + sp * per_split + col);
+                  a.x += v.x;
+                  a.y += v.y;
+                  a.z += v.z;
+                  a.w += v.w;
+                }
+                store_out4(crow_r + col, a);
+              }
+            }
+            if (BN < 128) {
+              const int col = n0 + lane * 4;
+              if (lane * 4 < BN && col < s.N) {
+                float4 a = ld_cg_f4(prow0 + col);
+                for (int sp = 1; sp < s.splits; ++sp) {
+                  const float4 v = ld_cg_f4(prow0 + sp * per_split + col);
+                  a.x += v.x;
+                  a.y += v.y;
+                  a.z += v.z;
+                  a.w += v.w;
+                }
+                store_out4(crow_r + col, a);
+              }
+            }
+          } else {
+            for (int col = n0 + lane; col < n0 + BN && col < s.N; col += 32) {
+              float a = ld_cg_f1(prow0 + col);
+              for (int sp = 1; sp < s.splits; ++sp) a += ld_cg_f1(prow0 + sp * per_split + col);
+              store_out1(crow_r + col, a);
+            }
+          }
+        }
+        // (4) depart; the last warp out of the tile leaves both counters at zero
+        __syncwarp();
+        if (lane == 0) {
+          if (atomicAdd(depart, 1u) == expected - 1u) {
+            *depart = 0u;
+            *arrive = 0u;
+          }
+        }
+      }
     }
     if (warp == 2 && lane == 0) trace_mark(s, 6);
     if (s.tma_store && lane == 0) tma_store_wait<0>();  // global writes done before exit
@@ -957,6 +1082,29 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   }
   const long long work = tiles * splits;
   const int grid_units = (int)(work < units ? work : units);
+  // In-kernel reduction needs every (split, tile) work item on its own resident CTA (pair), so
+  // that waiting for the other splits of a tile cannot deadlock: plan_splits guarantees
+  // work <= units.  B200TF_SPLITK_SEPARATE=1 keeps the second kernel (comparison switch).
+  s.tickets = nullptr;
+  static const bool separate_reduce = getenv("B200TF_SPLITK_SEPARATE") != nullptr;
+  if (splits > 1 && !separate_reduce && work <= units && tiles <= kSplitKMaxTiles) {
+    static unsigned int* ticket_base[64] = {nullptr};
+    static std::atomic<unsigned> next_slot{0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64) {
+      if (ticket_base[dev] == nullptr) {
+        void* sym = nullptr;
+        if (cudaGetSymbolAddress(&sym, g_splitk_tickets) == cudaSuccess)
+          ticket_base[dev] = static_cast<unsigned int*>(sym);
+        else
+          cudaGetLastError();
+      }
+      if (ticket_base[dev] != nullptr)
+        s.tickets = ticket_base[dev] +
+                    (size_t)(next_slot.fetch_add(1) % kSplitKSlots) * 2 * kSplitKMaxTiles;
+    }
+  }
   const bool prof = profile_enabled();
   if (prof) profile_gemm_launch_begin(stream);
   const bool pdl = pdl_enabled();
@@ -1003,7 +1151,7 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
             (long long)(t[10] - t[0]));
   }
   note_launch();
-  if (splits > 1) {
+  if (splits > 1 && s.tickets == nullptr) {
     const long long groups = g.batch * g.M * ((g.N + 3) / 4);
     long long rblocks = (groups + 255) / 256;
     if (rblocks > 8LL * sm_count()) rblocks = 8LL * sm_count();

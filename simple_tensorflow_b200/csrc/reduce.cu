@@ -572,6 +572,59 @@ sum_single(const float* __restrict__ in, float* __restrict__ out, long long n, f
   if (threadIdx.x == 0) out[0] = acc * scale;
 }
 
+// General Sum / Mean over one contiguous run of axes: in viewed as [outer, reduce, inner],
+// out[o, i] = scale * sum_r in[o, r, i], fp32 accumulation in a fixed order (deterministic).
+// (the reference: ReductionOp<Device, T, Reducer>, core/kernels/reduction_ops_common.h, which
+// collapses adjacent reduced / kept axes the same way before handing Eigen a 2-D / 3-D reduce)
+//   inner == 1: one CTA per outer row, 256 threads stride over `reduce`, tree in the block.
+//   inner  > 1: a CTA owns 32 inner columns x 8 row groups; threads of a warp read consecutive
+//               columns (coalesced), the 8 groups are combined through shared memory.
+template <typename T>
+__global__ void __launch_bounds__(256)
+reduce_rows_kernel(const T* __restrict__ in, T* __restrict__ out, long long reduce, float scale) {
+  pdl_prologue();
+  __shared__ float sm[8];
+  const T* x = in + (long long)blockIdx.x * reduce;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < reduce; i += 256) acc += ldf<T>(x + i);
+  acc = block_reduce(acc, false, sm);
+  if (threadIdx.x == 0) stf<T>(out + blockIdx.x, acc * scale);
+}
+template <typename T>
+__global__ void __launch_bounds__(256)
+reduce_mid_kernel(const T* __restrict__ in, T* __restrict__ out, long long reduce, long long inner,
+                  float scale) {
+  pdl_prologue();
+  __shared__ float sm[8][32];
+  const int x = threadIdx.x & 31, y = threadIdx.x >> 5;
+  const long long col = (long long)blockIdx.x * 32 + x;
+  const T* base = in + (long long)blockIdx.y * reduce * inner;
+  float acc = 0.f;
+  if (col < inner)
+    for (long long r = y; r < reduce; r += 8) acc += ldf<T>(base + r * inner + col);
+  sm[y][x] = acc;
+  __syncthreads();
+  if (y == 0 && col < inner) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += sm[i][x];
+    stf<T>(out + (long long)blockIdx.y * inner + col, t * scale);
+  }
+}
+template <typename T>
+static int launch_reduce(const void* in, void* out, long long outer, long long reduce,
+                         long long inner, float scale, cudaStream_t s) {
+  const T* x = static_cast<const T*>(in);
+  T* y = static_cast<T*>(out);
+  if (inner == 1) {
+    launch_pdl(reduce_rows_kernel<T>, dim3((unsigned)outer), dim3(256), 0, s, x, y, reduce, scale);
+  } else {
+    launch_pdl(reduce_mid_kernel<T>, dim3((unsigned)((inner + 31) / 32), (unsigned)outer), dim3(256),
+               0, s, x, y, reduce, inner, scale);
+  }
+  return B200_OK;
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <typename T>
@@ -834,20 +887,35 @@ int b200_argmax(int dtype, const void* in, int64_t* out, int64_t outer, int64_t 
 }
 
 int b200_reduce_sum(int dtype, const void* in, float scale, void* out, int64_t n, void* stream) {
-  if (dtype != B200_DT_FLOAT) {
-    set_last_error("b200_reduce_sum: only DT_FLOAT is supported (got %d)", dtype);
-    return B200_UNIMPLEMENTED;
-  }
-  if (n < 0) {
-    set_last_error("b200_reduce_sum: negative n");
+  return b200_reduce(dtype, in, out, 1, n, 1, scale, stream);
+}
+
+int b200_reduce(int dtype, const void* in, void* out, int64_t outer, int64_t reduce, int64_t inner,
+                float scale, void* stream) {
+  if (outer < 0 || reduce < 0 || inner < 0) {
+    set_last_error("b200_reduce: negative extent (%lld, %lld, %lld)", (long long)outer,
+                   (long long)reduce, (long long)inner);
     return B200_INVALID_ARGUMENT;
   }
-  int rc = require_device("b200_reduce_sum");
+  if (dtype != B200_DT_FLOAT && dtype != B200_DT_BFLOAT16) {
+    set_last_error("b200_reduce: only DT_FLOAT / DT_BFLOAT16 are supported (got %d)", dtype);
+    return B200_UNIMPLEMENTED;
+  }
+  if (outer == 0 || inner == 0) return B200_OK;  // empty output
+  if (outer > 0x7fffffffLL || (inner + 31) / 32 > 0x7fffffffLL || (inner > 1 && outer > 65535)) {
+    set_last_error("b200_reduce: extent beyond the launch grid (outer %lld, inner %lld)",
+                   (long long)outer, (long long)inner);
+    return B200_UNIMPLEMENTED;
+  }
+  int rc = require_device("b200_reduce");
   if (rc) return rc;
-  launch_pdl(sum_single, dim3(1), dim3(256), 0, as_stream(stream), static_cast<const float*>(in),
-                                                static_cast<float*>(out), n, scale);
+  // reduce == 0: the sum over an empty set is 0 (the kernels' loops simply do not run)
+  if (dtype == B200_DT_FLOAT)
+    launch_reduce<float>(in, out, outer, reduce, inner, scale, as_stream(stream));
+  else
+    launch_reduce<__nv_bfloat16>(in, out, outer, reduce, inner, scale, as_stream(stream));
   note_launch();
-  return check_launch("b200_reduce_sum");
+  return check_launch("b200_reduce");
 }
 
 }  // extern "C"

@@ -222,14 +222,20 @@ class AddNOp : public OpKernel {
                                           type_string(), " must have the same size and shape.  "
                                           "Input 0: ", input0.shape().DebugString(), " != input ",
                                           i, ": ", ctx->input(i).shape().DebugString()));
-    OP_REQUIRES(ctx, num <= 8, errors::Unimplemented("AddN with more than 8 inputs"));
     Tensor* output = nullptr;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, input0.shape(), &output));
+    // One launch adds up to 8 operands; more inputs (aggregate_ops.cc:60-130 unrolls by 8 too) are
+    // folded in passes of  out = out + next 7  -- same left-to-right summation order.
     const void* ptrs[8];
-    for (int i = 0; i < num; ++i) ptrs[i] = ctx->input(i).raw_data();
-    OP_REQUIRES_OK(ctx, FromAbi(b200_add_n(AbiType<T>::v, ptrs, num, output->raw_data(),
-                                           input0.NumElements(), GetCudaStream(ctx)),
-                                "AddN"));
+    int first = 0;
+    while (first < num) {
+      int k = 0;
+      if (first > 0) ptrs[k++] = output->raw_data();
+      while (k < 8 && first < num) ptrs[k++] = ctx->input(first++).raw_data();
+      OP_REQUIRES_OK(ctx, FromAbi(b200_add_n(AbiType<T>::v, ptrs, k, output->raw_data(),
+                                             input0.NumElements(), GetCudaStream(ctx)),
+                                  "AddN"));
+    }
   }
 };
 
@@ -280,36 +286,86 @@ class AddOp : public OpKernel {
   }
 };
 
-// Mean over ALL elements (the loss reduction); reduction_indices is a host-memory vector.
-class MeanOp : public OpKernel {
+// Sum / Mean (core/kernels/reduction_ops_common.h ReductionOp + ReductionHelper::Simplify):
+// reduction_indices is a host-memory int32 / int64 vector, negative indices count from the back,
+// duplicates are allowed, adjacent reduced / kept axes are collapsed.  The GPU kernel handles the
+// patterns that collapse to [outer, REDUCE, inner] (one run of reduced axes: full reductions, row
+// / column sums, NHWC channel means ...); alternating patterns return Unimplemented.
+template <typename T, bool kMean>
+class ReductionOp : public OpKernel {
  public:
-  explicit MeanOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
+  explicit ReductionOp(OpKernelConstruction* ctx) : OpKernel(ctx) {
     OP_REQUIRES_OK(ctx, ctx->GetAttr("keep_dims", &keep_dims_));
   }
   void Compute(OpKernelContext* ctx) override {
     const Tensor& data = ctx->input(0);
     const Tensor& axes = ctx->input(1);
-    OP_REQUIRES(ctx, axes.NumElements() == data.dims(),
-                errors::Unimplemented("Mean on B200 reduces over all dimensions only (got ",
-                                      axes.NumElements(), " axes for rank ", data.dims(), ")"));
+    OP_REQUIRES(ctx, axes.dims() <= 1,
+                errors::InvalidArgument("Expected scalar or vector as reduction_indices: ",
+                                        axes.shape().DebugString()));
+    const int rank = data.dims();
+    std::vector<bool> reduced(rank, false);
+    for (int64 i = 0; i < axes.NumElements(); ++i) {
+      int64 a = axes.dtype() == DT_INT64 ? axes.flat<int64>()[i]
+                                         : static_cast<int64>(axes.flat<int32>()[i]);
+      OP_REQUIRES(ctx, a >= -rank && a < rank,
+                  errors::InvalidArgument("Invalid reduction dimension (", a, " for input with ",
+                                          rank, " dimension(s)"));
+      reduced[(a + rank) % rank] = true;
+    }
     TensorShape out_shape;
-    if (keep_dims_)
-      for (int i = 0; i < data.dims(); ++i) out_shape.AddDim(1);
+    for (int d = 0; d < rank; ++d) {
+      if (!reduced[d])
+        out_shape.AddDim(data.dim_size(d));
+      else if (keep_dims_)
+        out_shape.AddDim(1);
+    }
+    // collapse: runs of equal `reduced` flags (size-1 axes join either neighbour)
+    std::vector<std::pair<bool, int64>> runs;
+    for (int d = 0; d < rank; ++d) {
+      if (data.dim_size(d) == 1) continue;
+      if (!runs.empty() && runs.back().first == reduced[d])
+        runs.back().second *= data.dim_size(d);
+      else
+        runs.push_back({reduced[d], data.dim_size(d)});
+    }
     Tensor* out = nullptr;
     OP_REQUIRES_OK(ctx, ctx->allocate_output(0, out_shape, &out));
-    const int64 n = data.NumElements();
-    OP_REQUIRES_OK(ctx, FromAbi(b200_reduce_sum(B200_DT_FLOAT, data.raw_data(),
-                                                n ? 1.0f / static_cast<float>(n) : 0.f,
-                                                out->raw_data(), n, GetCudaStream(ctx)),
-                                "Mean"));
+    if (out->NumElements() == 0) return;
+    int64 outer = 1, reduce = 1, inner = 1;
+    int n_reduced_runs = 0;
+    for (const auto& r : runs) n_reduced_runs += r.first ? 1 : 0;
+    OP_REQUIRES(ctx, n_reduced_runs <= 1 && runs.size() <= 3,
+                errors::Unimplemented(type_string(), " on B200 reduces one contiguous run of axes "
+                                      "(got input ", data.shape().DebugString(), ")"));
+    bool seen = false;
+    for (const auto& r : runs) {
+      if (r.first) { reduce = r.second; seen = true; }
+      else if (!seen) outer *= r.second;
+      else inner *= r.second;
+    }
+    if (n_reduced_runs == 0 && !runs.empty()) {  // nothing (but size-1 axes) reduced: a copy
+      outer = data.NumElements();
+      inner = 1;
+    }
+    const float scale = kMean ? (reduce > 0 ? 1.0f / static_cast<float>(reduce) : 0.f) : 1.0f;
+    OP_REQUIRES_OK(ctx, FromAbi(b200_reduce(AbiType<T>::v, data.raw_data(), out->raw_data(), outer,
+                                            reduce, inner, scale, GetCudaStream(ctx)),
+                                type_string().c_str()));
   }
 
  private:
   bool keep_dims_;
 };
-REGISTER_KERNEL_BUILDER(
-    Name("Mean").Device(DEVICE_GPU).TypeConstraint<float>("T").HostMemory("reduction_indices"),
-    MeanOp);
+#define REGISTER_REDUCTIONS(T)                                                              \
+  REGISTER_KERNEL_BUILDER(                                                                  \
+      Name("Mean").Device(DEVICE_GPU).TypeConstraint<T>("T").HostMemory("reduction_indices"), \
+      ReductionOp<T, true>);                                                                \
+  REGISTER_KERNEL_BUILDER(                                                                  \
+      Name("Sum").Device(DEVICE_GPU).TypeConstraint<T>("T").HostMemory("reduction_indices"),  \
+      ReductionOp<T, false>);
+REGISTER_B200_FLOAT_TYPES(REGISTER_REDUCTIONS)
+#undef REGISTER_REDUCTIONS
 
 // ---------------------------------------------------------------- ApplyGradientDescent
 // training_ops.cc:369-412: var -= alpha * delta on the variable's own buffer; out = ref(var).

@@ -105,6 +105,12 @@ REGISTER_OP("Mean")
     .Attr("keep_dims: bool = false").Attr("T: numbertype")
     .Attr("Tidx: {int32, int64} = DT_INT32");
 
+// math_ops.cc:1330-1343 ("Sum": same signature as "Mean")
+REGISTER_OP("Sum")
+    .Input("input: T").Input("reduction_indices: Tidx").Output("output: T")
+    .Attr("keep_dims: bool = false").Attr("T: numbertype")
+    .Attr("Tidx: {int32, int64} = DT_INT32");
+
 REGISTER_OP("ApplyGradientDescent")
     .Input("var: Ref(T)").Input("alpha: T").Input("delta: T").Output("out: Ref(T)")
     .Attr("T: numbertype").Attr("use_locking: bool = false");

@@ -270,13 +270,30 @@ def argmax(input, axis, name=None):  # noqa: A002
     return _set_shape(op.outputs[0], s)
 
 
-def reduce_mean(x, name=None):
-    """math_ops.reduce_mean over all axes -> scalar."""
+def _reduce(op_type, x, axis, keep_dims, name):
     x = _val(x)
     s = _shape(x)
-    axes = constant(np.arange(len(s), dtype=np.int32), int32)
-    op = _g(x).create_op("Mean", [x, axes], {"T": ("type", x.dtype)}, name or "Mean")
-    return _set_shape(op.outputs[0], ())
+    rank = len(s)
+    if axis is None:
+        axes = list(range(rank))
+    else:
+        axes = [int(a) for a in (axis if isinstance(axis, (list, tuple)) else [axis])]
+    idx = constant(np.asarray(axes, dtype=np.int32).reshape(len(axes)), int32)
+    op = _g(x).create_op(op_type, [x, idx], {"T": ("type", x.dtype), "keep_dims": bool(keep_dims)},
+                         name or op_type)
+    red = {a % rank for a in axes} if rank else set()
+    out = tuple((1 if d in red else s[d]) for d in range(rank) if keep_dims or d not in red)
+    return _set_shape(op.outputs[0], out)
+
+
+def reduce_mean(x, axis=None, keep_dims=False, name=None):
+    """math_ops.reduce_mean (axis=None: over all axes -> scalar)."""
+    return _reduce("Mean", x, axis, keep_dims, name)
+
+
+def reduce_sum(x, axis=None, keep_dims=False, name=None):
+    """math_ops.reduce_sum (axis=None: over all axes -> scalar)."""
+    return _reduce("Sum", x, axis, keep_dims, name)
 
 
 def multiply(x, y, name=None):
@@ -432,11 +449,18 @@ def _xent_grad(op, grad_loss, grad_backprop=None):
     return multiply(op.outputs[1], grad_loss), None
 
 
+def _full_reduction(op):
+    x = op.inputs[0]
+    out_elems = int(np.prod(_shape(op.outputs[0]) or (), dtype=np.int64))
+    if out_elems != 1:
+        raise NotImplementedError("gradient of a partial-axis %s is outside the hot path" % op.type)
+    return x, int(np.prod(_shape(x), dtype=np.int64))
+
+
 @_register_gradient("Mean")
 def _mean_grad(op, grad):
     # math_grad.py _MeanGrad for a full reduction: grad / N tiled to the input shape.
-    x = op.inputs[0]
-    n = int(np.prod(_shape(x), dtype=np.int64))
+    x, n = _full_reduction(op)
     scale = constant(np.float32(1.0 / n), x.dtype)
     g = multiply(grad, scale) if grad is not None else scale
     if x.op.type == "SoftmaxCrossEntropyWithLogits" and x.name == x.op.outputs[0].name:
@@ -446,6 +470,16 @@ def _mean_grad(op, grad):
     # any other producer (Relu, MatMul, Reshape ...) needs a gradient of the input's own shape,
     # as _MeanGrad's tile() delivers: a constant 1/N tensor, scaled by the incoming scalar
     tile = constant(np.full(_shape(x), 1.0 / n, np.float32), x.dtype)
+    return (multiply(tile, grad) if grad is not None else tile), None
+
+
+@_register_gradient("Sum")
+def _sum_grad(op, grad):
+    # math_grad.py _SumGrad for a full reduction: grad tiled to the input shape
+    x, _ = _full_reduction(op)
+    if x.op.type == "SoftmaxCrossEntropyWithLogits" and x.name == x.op.outputs[0].name:
+        return (grad if grad is not None else constant(np.float32(1.0), x.dtype)), None
+    tile = constant(np.ones(_shape(x), np.float32), x.dtype)
     return (multiply(tile, grad) if grad is not None else tile), None
 
 
@@ -529,7 +563,7 @@ def gradients(ys, xs):
             raise LookupError("No gradient defined for operation '%s' (op type: %s)" %
                               (op.name, op.type))
         seed_only = op.outputs[0].name == y.name and out_grads[0] is None
-        if seed_only and op.type != "Mean":  # explicit ones seed (gradients_impl.py grad_ys=None)
+        if seed_only and op.type not in ("Mean", "Sum"):  # explicit ones seed (gradients_impl.py grad_ys=None)
             out_grads[0] = constant(np.ones(_shape(y) or (), np.float32), y.dtype)
             seed_only = False
         in_grads = _GRAD[op.type](op, *([None] if seed_only else out_grads[:1]))

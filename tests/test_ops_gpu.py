@@ -409,6 +409,56 @@ def test_conv_family_vs_oracle(oracle, rng, shape, fshape, strides, padding):
     assert au.rel_err(dw, oracle.conv2d_backprop_filter(x, fshape, dy, strides, padding)) < TOL_TF32
 
 
+HALO_SHAPES = [
+    # unit-stride shapes on the halo-tile kernel (conv_halo.cu): tile tails, several tiles per
+    # image in both directions, VALID / SAME, 1 and 2 channel blocks, several N blocks, odd sizes
+    ((3, 14, 14, 32), (5, 5, 32, 64), "SAME"),       # LeNet conv2: one image = one work item
+    ((9, 14, 14, 64), (5, 5, 64, 32), "SAME"),       # its input gradient's shape (2 channel blocks)
+    ((2, 40, 70, 32), (3, 3, 32, 32), "SAME"),       # several row bands per image
+    ((1, 9, 300, 32), (3, 3, 32, 64), "VALID"),      # wider than one 256-pixel box: column tiles
+    ((5, 11, 13, 32), (2, 4, 32, 96), "SAME"),       # even filter sizes: asymmetric SAME padding
+    ((2, 8, 8, 64), (1, 3, 64, 320), "SAME"),        # K > 256: two N blocks, the second ragged
+    ((7, 6, 6, 32), (6, 6, 32, 32), "VALID"),        # filter covers the image: 1x1 output
+    ((37, 5, 5, 32), (3, 3, 32, 32), "SAME"),        # many small items: cluster tail padding
+]
+
+
+@pytest.mark.parametrize("shape,fshape,padding", HALO_SHAPES)
+def test_conv_halo_forward_and_input_gradient_vs_oracle(oracle, rng, shape, fshape, padding):
+    x = rng.rand(*shape).astype(np.float32) - 0.5
+    f = (rng.rand(*fshape).astype(np.float32) - 0.5)
+    y_ref = oracle.conv2d(x, f, (1, 1), padding)
+    assert au.rel_err(au.conv2d(x, f, (1, 1), padding, oracle), y_ref) < TOL_TF32
+    if shape[3] % 32 == 0 and fshape[3] % 32 == 0:
+        dy = rng.rand(*y_ref.shape).astype(np.float32) - 0.5
+        dx = au.conv2d_backprop_input(shape, f, dy, (1, 1), padding, oracle)
+        assert au.rel_err(dx, oracle.conv2d_backprop_input(shape, f, dy, (1, 1), padding)) < TOL_TF32
+
+
+def test_conv_halo_integer_data_is_exact(oracle, rng):
+    # integers are exact in tf32 and their sums exact in fp32: any mis-addressed tap shows up
+    x = rng.randint(-3, 4, (4, 14, 14, 32)).astype(np.float32)
+    f = rng.randint(-3, 4, (5, 5, 32, 64)).astype(np.float32)
+    np.testing.assert_array_equal(au.conv2d(x, f, (1, 1), "SAME", oracle),
+                                  oracle.conv2d(x, f, (1, 1), "SAME"))
+    np.testing.assert_array_equal(au.conv2d(x, f, (1, 1), "VALID", oracle),
+                                  oracle.conv2d(x, f, (1, 1), "VALID"))
+    dy = rng.randint(-3, 4, (4, 14, 14, 64)).astype(np.float32)
+    np.testing.assert_array_equal(
+        au.conv2d_backprop_input(x.shape, f, dy, (1, 1), "SAME", oracle),
+        oracle.conv2d_backprop_input(x.shape, f, dy, (1, 1), "SAME"))
+
+
+def test_conv_halo_bf16(oracle, rng):
+    x = oracle.truncate_to_bf16(rng.rand(3, 20, 20, 64).astype(np.float32) - 0.5)
+    f = oracle.truncate_to_bf16((rng.rand(3, 3, 64, 128).astype(np.float32) - 0.5) * 0.2)
+    y_ref = oracle.conv2d(x, f, (1, 1), "SAME")
+    assert au.rel_err(au.conv2d(x, f, (1, 1), "SAME", oracle, bf16=True), y_ref) < TOL
+    dy = oracle.truncate_to_bf16(rng.rand(*y_ref.shape).astype(np.float32) - 0.5)
+    dx = au.conv2d_backprop_input(x.shape, f, dy, (1, 1), "SAME", oracle, bf16=True)
+    assert au.rel_err(dx, oracle.conv2d_backprop_input(x.shape, f, dy, (1, 1), "SAME")) < TOL
+
+
 def test_conv2d_empty_batch(oracle):
     out = au.conv2d(np.zeros((0, 2, 3, 3), np.float32), gu.iota([1, 1, 3, 3]), [1, 1], "VALID",
                     oracle)

@@ -38,7 +38,7 @@ def _mlp_f64(x, labels, P, layers):
     return loss, G
 
 
-@pytest.mark.parametrize("dtype,tol", [("f32", 2e-5), ("bf16", 2e-2)])
+@pytest.mark.parametrize("dtype,tol", [("f32", 2e-5), ("bf16", 6e-2)])
 def test_mlp_oracle_chain_matches_float64_numpy(oracle, dtype, tol):
     w = W.MLP(dtype, batch=96, width=64, layers=3)
     x, labels = w.data(7)
@@ -110,3 +110,18 @@ def test_weighted_xent_gradient_is_rejected_at_graph_construction():
     loss = tf.reduce_mean(tf.multiply(per_example, weights))
     with pytest.raises(NotImplementedError):
         tf.gradients(loss, [v])
+
+
+def test_tf32_input_rounding_moves_early_gradients_more_than_late_ones(oracle):
+    # the effect KernelRounding exists for, on the CPU alone: the same oracle chain with its MatMul
+    # operands truncated to TF32 differs from the exact chain by ~5e-4 in the last layer's gradient
+    # but by far more in the first layer's (ReLU masks flipped by the forward rounding)
+    w = W.MLP("f32", batch=512, width=256, layers=3)
+    x, labels = w.data(11)
+    P = w.init_params()
+    _, G = w.reference(oracle, x, labels, P)
+    _, Gk = w.reference(W.KernelRounding(oracle), x, labels, P)
+    last, first = W.rel_fro(Gk["W2"], G["W2"]), W.rel_fro(Gk["W0"], G["W0"])
+    assert last < 5e-3
+    assert first > 2 * last
+    assert first < 5e-2

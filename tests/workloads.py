@@ -43,6 +43,53 @@ def bf16_from_bits(bits):
     return (np.ascontiguousarray(bits, np.uint16).astype(np.uint32) << 16).view(np.float32)
 
 
+def tf32_truncate(a):
+    """fp32 -> the value tcgen05 kind::tf32 multiplies with: the low 13 mantissa bits are ignored
+    (DESIGN.md section 3).  Sums stay fp32."""
+    a = np.ascontiguousarray(a, np.float32)
+    return (a.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+
+class KernelRounding:
+    """The oracle evaluated under the tensor-core kernels' documented INPUT rounding: MatMul and
+    the implicit-GEMM convolutions read their fp32 operands as TF32 (truncation), accumulate in
+    fp32.  First-layer convolutions (C_in <= 4) run on the CUDA cores in IEEE fp32 and are left
+    exact.  Everything else is forwarded to the oracle unchanged.
+
+    Why it exists: a ReLU network's gradient is discontinuous in its pre-activations -- a forward
+    pass that differs by TF32 rounding (5e-4) flips a fraction f ~ 5e-4 of the ReLU masks, which
+    moves the early layers' gradients by ~sqrt(f) ~ 2 % in Frobenius norm whatever the backward
+    kernels do (tests/test_workloads_cpu.py reproduces the figure on the CPU alone).  Comparing
+    with the oracle under the same input rounding removes that effect and checks the kernels
+    themselves: summation, masks, layout, scaling."""
+
+    def __init__(self, o):
+        self._o = o
+
+    def __getattr__(self, name):
+        return getattr(self._o, name)
+
+    def matmul(self, a, b, transpose_a=False, transpose_b=False):
+        return self._o.matmul(tf32_truncate(a), tf32_truncate(b), transpose_a, transpose_b)
+
+    def conv2d(self, x, f, strides, padding):
+        if x.shape[-1] <= 4:
+            return self._o.conv2d(x, f, strides, padding)
+        return self._o.conv2d(tf32_truncate(x), tf32_truncate(f), strides, padding)
+
+    def conv2d_backprop_input(self, in_shape, f, dy, strides, padding):
+        if in_shape[-1] <= 4:
+            return self._o.conv2d_backprop_input(in_shape, f, dy, strides, padding)
+        return self._o.conv2d_backprop_input(in_shape, tf32_truncate(f), tf32_truncate(dy), strides,
+                                             padding)
+
+    def conv2d_backprop_filter(self, x, filter_shape, dy, strides, padding):
+        if x.shape[-1] <= 4:
+            return self._o.conv2d_backprop_filter(x, filter_shape, dy, strides, padding)
+        return self._o.conv2d_backprop_filter(tf32_truncate(x), filter_shape, tf32_truncate(dy),
+                                              strides, padding)
+
+
 def bucket_kw():
     """B200TF_BUCKET_BYTES=none|<bytes>: gradient all-reduce bucket size (default: optimizer's)."""
     import os
@@ -193,20 +240,23 @@ class MLP(Workload):
         return tf.reduce_mean(tf.softmax_cross_entropy_with_logits(h, lab), name=tag + "/loss")
 
     def reference(self, o, x, labels, params):
+        # bf16: storage rounding where the kernels round -- once per FUSED op (MatMul+BiasAdd(+Relu)
+        # and MatMul+ReluGrad each round their fp32 accumulator once; xent scales its backprop by
+        # 1/batch in fp32 before the store)
         q = self._q
         L = self.layers
         acts = [x]
         for i in range(L):
-            pre = q(o.bias_add(q(o.matmul(acts[-1], params["W%d" % i])), params["b%d" % i]))
+            pre = q(o.bias_add(o.matmul(acts[-1], params["W%d" % i]), params["b%d" % i]))
             acts.append(o.relu(pre) if i < L - 1 else pre)
         lvec, bp = o.softmax_xent(acts[-1], labels)
-        g = q(q(bp) * np.float32(1.0 / x.shape[0]))
+        g = q(bp * np.float32(1.0 / x.shape[0]))
         grads = {}
         for i in reversed(range(L)):
             grads["b%d" % i] = q(o.bias_add_grad(g))
             grads["W%d" % i] = q(o.matmul(acts[i], g, True, False))
             if i > 0:
-                g = o.relu_grad(q(o.matmul(g, params["W%d" % i], False, True)), acts[i])
+                g = q(o.relu_grad(o.matmul(g, params["W%d" % i], False, True), acts[i]))
         return float(q(lvec).mean()), grads
 
 
@@ -318,37 +368,57 @@ def check_parity(w, B, sess, o, world=1, rank=0, seeds=None, tol=1e-2):
     feed = {B.xp: hx, B.lp: hl}
     names = [n for n, _ in B.applied_grads]
     vals = sess.run([B.fed[0]] + [g for _, g in B.applied_grads], feed)
-    got_loss = float(w.to_f32(vals[0]))
+    got_loss = float(np.asarray(w.to_f32(vals[0])).reshape(-1)[0])
     got_grads = {n: w.to_f32(v) for n, v in zip(names, vals[1:])}
     sess.run([B.fed[0], B.fed[1]], feed)
     got_w = {n: w.to_f32(a) for n, a in zip(B.V, sess.run([v.ref for v in B.V.values()]))}
 
-    ref_loss_local, ref_grads = None, None
-    for r, seed in enumerate(seeds):
-        x, labels = w.data(seed)
-        loss_r, g_r = w.reference(o, x, labels, B.params)
-        if r == rank:
-            ref_loss_local = loss_r
-        if ref_grads is None:
-            ref_grads = {n: np.asarray(g, np.float64) for n, g in g_r.items()}
-        else:
-            for n in ref_grads:
-                ref_grads[n] += g_r[n]
-    for n in ref_grads:
-        ref_grads[n] = (ref_grads[n] / len(seeds)).astype(np.float32)
+    def global_reference(oracle_like):
+        loss_local, grads = None, None
+        for r, seed in enumerate(seeds):
+            x, labels = w.data(seed)
+            loss_r, g_r = w.reference(oracle_like, x, labels, B.params)
+            if r == rank:
+                loss_local = loss_r
+            if grads is None:
+                grads = {n: np.asarray(g, np.float64) for n, g in g_r.items()}
+            else:
+                for n in grads:
+                    grads[n] += g_r[n]
+        return loss_local, {n: (g / len(seeds)).astype(np.float32) for n, g in grads.items()}
+
+    ref_loss_local, ref_grads = global_reference(o)
     grad_err = {n: rel_fro(got_grads[n], ref_grads[n]) for n in names}
+    # the same comparison with the oracle under the kernels' input rounding (KernelRounding): for
+    # fp32 graphs the TF32 operand truncation; the bf16 chain already models its storage rounding
+    if w.dtype == "f32":
+        _, kr_grads = global_reference(KernelRounding(o))
+        grad_err_kr = {n: rel_fro(got_grads[n], kr_grads[n]) for n in names}
+    else:
+        grad_err_kr = dict(grad_err)
     w_err = {}
     for n in B.V:
         ref_w = B.params[n] - np.float32(LR) * ref_grads[n]
         w_err[n] = rel_fro(got_w[n], w._q(ref_w) if w.dtype == "bf16" else ref_w)
     loss_err = abs(got_loss - ref_loss_local) / max(abs(ref_loss_local), 1e-30)
     worst_g = max(grad_err.values())
+    worst_g_kr = max(grad_err_kr.values())
     worst_w = max(w_err.values())
-    return {"ok": bool(loss_err <= tol and worst_g <= tol and worst_w <= tol), "tol": tol,
+    return {"ok": bool(loss_err <= tol and worst_w <= tol and worst_g_kr <= tol), "tol": tol,
             "loss": got_loss, "loss_oracle": ref_loss_local, "loss_rel_err": loss_err,
-            "grad_rel_err_max": worst_g, "weight_rel_err_max": worst_w,
-            "grad_rel_err": grad_err,
-            "what": "step-1 loss, gradients (as consumed by ApplyGradientDescent%s) and updated "
-                    "weights of the full-size graph vs the CPU oracle%s; relative Frobenius norm"
+            "weight_rel_err_max": worst_w,
+            "grad_rel_err_max_same_input_rounding": worst_g_kr,
+            "grad_rel_err_max_vs_exact_fp32": worst_g,
+            "grad_rel_err_same_input_rounding": grad_err_kr,
+            "grad_rel_err_vs_exact_fp32": grad_err,
+            "what": "step-1 loss, updated weights and gradients (as consumed by "
+                    "ApplyGradientDescent%s) of the full-size graph vs the CPU oracle%s; relative "
+                    "Frobenius norms.  ok = loss, weights (vs the exact fp32 oracle) and gradients "
+                    "(vs the oracle under the kernels' documented input rounding: %s) all <= tol.  "
+                    "The gradients vs the exact fp32 oracle are reported too: ReLU masks flipped by "
+                    "the forward pass's rounding move early-layer gradients by ~sqrt(flip fraction) "
+                    "whatever the backward kernels do (tests/workloads.py::KernelRounding)."
                     % (", replica-averaged" if world > 1 else "",
-                       " on the global batch of %d replicas" % world if world > 1 else "")}
+                       " on the global batch of %d replicas" % world if world > 1 else "",
+                       "TF32 operand truncation" if w.dtype == "f32" else
+                       "bf16 storage, one rounding per fused op")}
