@@ -224,6 +224,13 @@ B200_API size_t b200_conv2d_workspace_bytes(int dtype, const b200_conv2d_geometr
 B200_API int b200_conv2d(int dtype, const void* input, const void* filter, void* output,
                          const b200_conv2d_geometry* g, void* workspace, size_t workspace_bytes,
                          void* stream);
+/* out = [relu](conv2d(input, filter) + bias[k]) in one pass: the tail the executor's rewrite of
+ * Conv2D -> BiasAdd (-> Relu) chains asks for (`_FusedConv2D`; what later TensorFlow's remapper
+ * does).  Replaces LaunchConv2DOp (conv_ops.cc:433-720) + BiasOp (bias_op.cc:62-117) +
+ * ReluOp (relu_op.h:34-60) launched back to back; same arithmetic, same workspace as b200_conv2d. */
+B200_API int b200_fused_conv2d(int dtype, const void* input, const void* filter, const void* bias,
+                               int relu, void* output, const b200_conv2d_geometry* geom,
+                               void* workspace, size_t workspace_bytes, void* stream);
 /* Replaces Conv2DSlowBackpropInputOp<GPUDevice,T> (core/kernels/conv_grad_input_ops.cc:533-917). */
 B200_API int b200_conv2d_backprop_input(int dtype, const void* filter, const void* out_backprop,
                                         void* in_backprop, const b200_conv2d_geometry* g,

@@ -88,6 +88,8 @@ SIGNATURES = {
     "b200_conv2d_workspace_bytes": (c_size_t, [c_int, ctypes.POINTER(ConvGeometry), c_int]),
     "b200_conv2d": (c_int, [c_int, c_void_p, c_void_p, c_void_p, ctypes.POINTER(ConvGeometry),
                             c_void_p, c_size_t, c_void_p]),
+    "b200_fused_conv2d": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                  ctypes.POINTER(ConvGeometry), c_void_p, c_size_t, c_void_p]),
     "b200_conv2d_backprop_input": (c_int, [c_int, c_void_p, c_void_p, c_void_p,
                                            ctypes.POINTER(ConvGeometry), c_void_p, c_size_t,
                                            c_void_p]),

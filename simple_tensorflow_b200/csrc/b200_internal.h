@@ -72,6 +72,13 @@ struct ConvHaloArgs {
 };
 bool conv_halo_supported(int dtype, const ConvHaloArgs& a);
 int conv_halo(int dtype, const ConvHaloArgs& a, cudaStream_t stream);
+// Filter gradient on the same idea (conv_halo_wgrad.cu).  ConvHaloArgs here: input = x,
+// filter = out_backprop [N, OH, OW, K], output = dW [R*S*C, K]; workspace holds one fp32 partial
+// filter gradient per CTA.
+bool conv_halo_wgrad_supported(int dtype, const ConvHaloArgs& a);
+size_t conv_halo_wgrad_workspace_bytes(int dtype, const ConvHaloArgs& a);
+int conv_halo_wgrad(int dtype, const ConvHaloArgs& a, void* workspace, size_t workspace_bytes,
+                    cudaStream_t stream);
 bool gemm_tcgen05_supported(const GemmArgs& g);
 // Can this convolution's patch operand be fetched by TMA im2col (channel / padding limits)?
 bool conv_a_supported(int dtype, const ConvAOperand& c);

@@ -262,7 +262,8 @@ static SmallCinFit small_cin_fit(int dtype, const ConvG& g) {
 template <int kR, int kS, int kC, int kKPerThread>
 __global__ void __launch_bounds__(kSmallCinThreads)
 conv_small_cin_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                          float* __restrict__ y, ConvG g, int pixels) {
+                          float* __restrict__ y, ConvG g, int pixels,
+                          const float* __restrict__ bias, int relu) {
   pdl_prologue();
   extern __shared__ float wsm[];  // [taps][K]
   const int R = kR ? kR : g.R, S = kS ? kS : g.S, C = kC ? kC : g.C;
@@ -307,6 +308,13 @@ conv_small_cin_fwd_kernel(const float* __restrict__ x, const float* __restrict__
             acc[4 * q + 3] = fmaf(v, wv.w, acc[4 * q + 3]);
           }
         }
+      }
+    }
+    if (bias != nullptr) {  // fused BiasAdd (+ Relu): same fp32 add / max as the separate kernels
+#pragma unroll
+      for (int j = 0; j < KP; ++j) {
+        acc[j] += __ldg(bias + kg * KP + j);
+        if (relu) acc[j] = acc[j] > 0.f ? acc[j] : 0.f;
       }
     }
     float4* out = reinterpret_cast<float4*>(y + (long long)p * g.K + kg * KP);
@@ -479,6 +487,15 @@ size_t b200_conv2d_workspace_bytes(int dtype, const b200_conv2d_geometry* geom, 
     return col + align256(gemm_workspace_bytes(dtype, rows, rsc, g.K, 1));
   }
   if (which == 2) {
+    if (!is_pointwise(g) && g.sh == 1 && g.sw == 1 && getenv("B200TF_CONV_EXPLICIT") == nullptr &&
+        b200_get_matmul_precision() == 0) {
+      // halo-tile filter gradient: one fp32 partial per CTA (conv_halo_wgrad.cu)
+      ConvHaloArgs h{reinterpret_cast<const void*>(16), reinterpret_cast<const void*>(16),
+                     reinterpret_cast<void*>(16), nullptr, false, g.N, g.H, g.W, g.C, g.K,
+                     g.R, g.S, g.pt, g.pl, g.OH, g.OW};
+      if (conv_halo_wgrad_supported(dtype, h))
+        return align256(conv_halo_wgrad_workspace_bytes(dtype, h));
+    }
     ConvAOperand ca{reinterpret_cast<const void*>(16), g.N, g.H, g.W, g.C, g.R, g.S, g.OH, g.OW,
                     g.sh, g.sw, g.pt, g.pl};
     if (!is_pointwise(g) && getenv("B200TF_CONV_EXPLICIT") == nullptr &&
@@ -490,9 +507,42 @@ size_t b200_conv2d_workspace_bytes(int dtype, const b200_conv2d_geometry* geom, 
   return 0;
 }
 
+// Forward convolution with an optional fused tail  out = [relu](conv + bias[k]).  The halo-tile
+// kernel and the first-layer kernel apply the tail in their epilogues; every other path runs the
+// convolution and then the library's own BiasAdd / Relu kernels in place (same arithmetic).
+static int conv2d_impl(int dtype, const void* input, const void* filter, void* output,
+                       const b200_conv2d_geometry* geom, void* workspace, size_t workspace_bytes,
+                       void* stream, const void* bias, bool relu);
+
 int b200_conv2d(int dtype, const void* input, const void* filter, void* output,
                 const b200_conv2d_geometry* geom, void* workspace, size_t workspace_bytes,
                 void* stream) {
+  return conv2d_impl(dtype, input, filter, output, geom, workspace, workspace_bytes, stream,
+                     nullptr, false);
+}
+
+int b200_fused_conv2d(int dtype, const void* input, const void* filter, const void* bias, int relu,
+                      void* output, const b200_conv2d_geometry* geom, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (bias == nullptr && relu) {
+    set_last_error("b200_fused_conv2d: relu without bias is not a fusion the executor produces");
+    return B200_INVALID_ARGUMENT;
+  }
+  return conv2d_impl(dtype, input, filter, output, geom, workspace, workspace_bytes, stream, bias,
+                     relu != 0);
+}
+
+static int conv2d_tail(int dtype, void* output, long long rows, int K, const void* bias, bool relu,
+                       void* stream) {
+  if (bias == nullptr) return B200_OK;
+  int rc = b200_bias_add(dtype, output, bias, output, rows, K, stream);
+  if (rc == B200_OK && relu) rc = b200_relu(dtype, output, output, rows * K, stream);
+  return rc;
+}
+
+static int conv2d_impl(int dtype, const void* input, const void* filter, void* output,
+                       const b200_conv2d_geometry* geom, void* workspace, size_t workspace_bytes,
+                       void* stream, const void* bias, bool relu) {
   ConvG g;
   int rc = to_geom("b200_conv2d", dtype, geom, &g);
   if (rc) return rc;
@@ -503,7 +553,10 @@ int b200_conv2d(int dtype, const void* input, const void* filter, void* output,
   cudaStream_t s = as_stream(stream);
   const size_t es = esize_of(dtype);
   const long long rsc = (long long)g.R * g.S * g.C;
-  if (rsc == 0) return b200_memset_async(output, 0, (size_t)rows * g.K * es, stream);
+  if (rsc == 0) {
+    rc = b200_memset_async(output, 0, (size_t)rows * g.K * es, stream);
+    return rc ? rc : conv2d_tail(dtype, output, rows, g.K, bias, relu, stream);
+  }
   const size_t need = b200_conv2d_workspace_bytes(dtype, geom, 0);
   if (need > 0 && (!workspace || workspace_bytes < need)) {
     set_last_error("b200_conv2d: workspace too small (%zu < %zu bytes)", workspace_bytes, need);
@@ -524,7 +577,8 @@ int b200_conv2d(int dtype, const void* input, const void* filter, void* output,
     const int pixels = (int)rows;
 #define SMALL_FWD(R_, S_, C_, KP_)                                                                \
   launch_pdl(conv_small_cin_fwd_kernel<R_, S_, C_, KP_>, dim3((unsigned)blocks),                  \
-             dim3(kSmallCinThreads), smem, s, xin, win, yout, g, pixels)
+             dim3(kSmallCinThreads), smem, s, xin, win, yout, g, pixels,                          \
+             static_cast<const float*>(bias), relu ? 1 : 0)
     if (kp == 16 && g.R == 5 && g.S == 5 && g.C == 1)
       SMALL_FWD(5, 5, 1, 16);
     else if (kp == 16 && g.R == 3 && g.S == 3 && g.C == 3)
@@ -552,7 +606,7 @@ int b200_conv2d(int dtype, const void* input, const void* filter, void* output,
   if (!is_pointwise(g) && g.sh == 1 && g.sw == 1 && !no_implicit &&
       b200_get_matmul_precision() == 0) {
     // unit stride: halo tile in shared memory, every tap a shifted view of it (conv_halo.cu)
-    ConvHaloArgs h{input, filter, output, nullptr, false, g.N, g.H, g.W, g.C, g.K,
+    ConvHaloArgs h{input, filter, output, bias, relu, g.N, g.H, g.W, g.C, g.K,
                    g.R, g.S, g.pt, g.pl, g.OH, g.OW};
     if (conv_halo_supported(dtype, h)) return conv_halo(dtype, h, s);
   }
@@ -569,7 +623,8 @@ int b200_conv2d(int dtype, const void* input, const void* filter, void* output,
     a.conv_a = &ca;
     a.workspace = nullptr;
     a.workspace_bytes = 0;
-    return gemm_tcgen05(a, s);
+    rc = gemm_tcgen05(a, s);
+    return rc ? rc : conv2d_tail(dtype, output, rows, g.K, bias, relu, stream);
   } else {
     const size_t col_bytes = align256((size_t)rows * g.ldk * es);
     if (!workspace || workspace_bytes < col_bytes) {  // e.g. unaligned pointers ruled out TMA im2col
@@ -586,7 +641,8 @@ int b200_conv2d(int dtype, const void* input, const void* filter, void* output,
     a.workspace_bytes = workspace_bytes - col_bytes;
     if (a.workspace_bytes == 0) a.workspace = nullptr;
   }
-  return gemm_dispatch(a, s);
+  rc = gemm_dispatch(a, s);
+  return rc ? rc : conv2d_tail(dtype, output, rows, g.K, bias, relu, stream);
 }
 
 int b200_conv2d_backprop_filter(int dtype, const void* input, const void* out_backprop,
@@ -623,6 +679,14 @@ int b200_conv2d_backprop_filter(int dtype, const void* input, const void* out_ba
                elems);
     note_launch(2);
     return check_launch("b200_conv2d_backprop_filter");
+  }
+  if (!is_pointwise(g) && g.sh == 1 && g.sw == 1 && getenv("B200TF_CONV_EXPLICIT") == nullptr &&
+      b200_get_matmul_precision() == 0) {
+    ConvHaloArgs h{input, out_backprop, filter_backprop, nullptr, false, g.N, g.H, g.W, g.C, g.K,
+                   g.R, g.S, g.pt, g.pl, g.OH, g.OW};
+    if (conv_halo_wgrad_supported(dtype, h) &&
+        workspace_bytes >= conv_halo_wgrad_workspace_bytes(dtype, h))
+      return conv_halo_wgrad(dtype, h, workspace, workspace_bytes, s);
   }
   GemmArgs a = base_gemm(dtype);
   a.b = out_backprop;  // [rows, K]

@@ -28,9 +28,13 @@
 //   * accumulators: n_mtiles x BN fp32 columns of TMEM, double buffered (2 x 256 columns) so the
 //     epilogue of one tile overlaps the MMAs of the next.
 //
-// CTA layout (192 threads, persistent, one CTA per SM): warp 0 = TMA producer, warp 1 = TMEM
-// allocator + single-thread tcgen05.mma issuer, warps 2..5 = epilogue (TMEM -> registers ->
-// [bias, relu] -> swizzled smem -> coalesced 16-byte global stores of the valid pixel rows).
+// CTA layout (224 threads, persistent, one CTA per SM): warp 0 = TMA producer, warp 1 = TMEM
+// allocator + tcgen05.mma issuer, warps 2..5 = epilogue (TMEM -> registers -> [bias, relu] ->
+// swizzled smem -> coalesced 16-byte global stores of the valid pixel rows), warp 6 = second
+// tcgen05.mma issuer.  Two issuers because an M128 x N64 x K8 MMA lasts 32 cycles but costs its
+// issuing warp ~130 (five R2UR moves of descriptor words into uniform registers, measured): each
+// issuer owns the M tiles mt = issuer, issuer + 2, ... and therefore its own TMEM accumulators, so
+// no two warps ever accumulate into the same columns and the summation order stays fixed.
 #include <cuda_bf16.h>
 
 #include <algorithm>
@@ -45,7 +49,8 @@ namespace b200 {
 
 namespace {
 
-constexpr int kHaloThreads = 192;
+constexpr int kIssueWarps = 2;   // MMA-issuing warps: warp 1 and warp 6 (see the kernel comment)
+constexpr int kHaloThreads = 192 + 32 * (kIssueWarps - 1);
 constexpr int kMaxBStages = 8;
 constexpr int kRowBytes = 128;            // one pixel row of one channel block
 constexpr int kAccCols = 256;             // TMEM columns per accumulator stage
@@ -153,7 +158,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
   uint64_t* tempty = bars + 6 + 2 * kMaxBStages;  // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8 + 2 * kMaxBStages);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = uniform_warp_idx(), lane = threadIdx.x & 31;
   const int cl = s.cl;
   const uint32_t rank = cl > 1 ? cluster_ctarank() : 0;
   const long long first = (long long)(blockIdx.x / cl) * cl + rank;
@@ -169,13 +174,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) {
         mbar_init(&halo_full[i], 1);
-        mbar_init(&halo_empty[i], 1);
-        mbar_init(&tfull[i], 1);
+        mbar_init(&halo_empty[i], kIssueWarps);
+        mbar_init(&tfull[i], kIssueWarps);
         mbar_init(&tempty[i], 4);
       }
       for (int i = 0; i < kMaxBStages; ++i) {
         mbar_init(&b_full[i], 1);
-        mbar_init(&b_empty[i], cl);  // one commit per CTA of the cluster
+        mbar_init(&b_empty[i], cl * kIssueWarps);  // one commit per issuing warp of every CTA
       }
       fence_mbar_init();
     }
@@ -188,7 +193,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
   else
     __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  // (the shuffle makes the value provably warp-uniform: uniform-register descriptor math)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   pdl_wait();  // everything above overlapped the previous kernel's tail
 
   if (warp == 0) {
@@ -200,18 +206,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
       const int pieces = kNChunks * row_parts;
       const int per_cta = pieces / cl;  // >= 1 (host guarantees divisibility)
       const int rows_per_piece = kChunk / row_parts;
+      // The halo tile of item i + 1 is requested BEFORE the filter tiles of item i: the filter
+      // ring throttles the producer to a few taps ahead of the MMAs, so a halo load issued after
+      // it would start only when item i is almost finished and its latency would be exposed.
+      auto issue_halo = [&](const WorkItem& h) {
+        mbar_wait(&halo_empty[hb], hphase ^ 1);
+        mbar_expect_tx(&halo_full[hb], (uint32_t)(s.cblocks * s.HP * s.WP * kRowBytes));
+        for (int cb = 0; cb < s.cblocks; ++cb)
+          tma_load_4d(smHalo + hb * halo_bytes + cb * s.halo_rows * kRowBytes, &tmapX,
+                      &halo_full[hb], cb * kChunk, h.ow0 - s.pl, h.oh0 - s.pt, h.n);
+        if (++hb == 2) {
+          hb = 0;
+          hphase ^= 1;
+        }
+      };
+      if (first < s.work_padded) {
+        const WorkItem it0 = decode_work(s, first);
+        if (it0.active) issue_halo(it0);
+      }
       for (long long w = first; w < s.work_padded; w += stride) {
         const WorkItem it = decode_work(s, w);
-        if (it.active) {
-          mbar_wait(&halo_empty[hb], hphase ^ 1);
-          mbar_expect_tx(&halo_full[hb], (uint32_t)(s.cblocks * s.HP * s.WP * kRowBytes));
-          for (int cb = 0; cb < s.cblocks; ++cb)
-            tma_load_4d(smHalo + hb * halo_bytes + cb * s.halo_rows * kRowBytes, &tmapX,
-                        &halo_full[hb], cb * kChunk, it.ow0 - s.pl, it.oh0 - s.pt, it.n);
-          if (++hb == 2) {
-            hb = 0;
-            hphase ^= 1;
-          }
+        if (w + stride < s.work_padded) {
+          const WorkItem nx = decode_work(s, w + stride);
+          if (nx.active) issue_halo(nx);
         }
         for (int cb = 0; cb < s.cblocks; ++cb) {
           for (int tap = 0; tap < taps; ++tap) {
@@ -238,9 +255,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+  } else if (warp == 1 || warp >= 6) {
+    // ===================== MMA issuers =====================
+    // the whole warp runs this loop; one elected lane issues each tcgen05 instruction
+    const int iw = warp == 1 ? 0 : warp - 5;  // issuer index: owns M tiles iw, iw + kIssueWarps, ...
+    {
       uint32_t stage = 0, phase = 0, hb = 0, hphase = 0, acc = 0, acc_phase = 0;
       for (long long w = first; w < s.work_padded; w += stride) {
         const WorkItem it = decode_work(s, w);
@@ -249,41 +268,54 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
           mbar_wait(&tempty[acc], acc_phase ^ 1);
           tc_fence_after();
         }
-        const uint32_t halo_addr = smem_u32(smHalo + hb * halo_bytes);
+        // Descriptors differ only in their start-address field (bits 0-13, address >> 4): build
+        // them once and add offsets -- one thread issues every MMA and an M128 x N64 x K8 MMA
+        // lasts 32 cycles, so the per-MMA instruction count is on the critical path.
+        const uint64_t adesc_hb =
+            make_smem_desc_sw128(smem_u32(smHalo + hb * halo_bytes), 16, 1024);
+        const uint64_t bdesc_0 = make_smem_desc_sw128(smem_u32(smB), kChunk * kRowBytes,
+                                                      Tr::kMn32 ? 512 : 1024, Tr::kMn32 ? 1 : 2);
+        constexpr uint32_t kAStepK = (Tr::kUmmaK * (int)sizeof(TIn)) >> 4;   // +32 B per k step
+        constexpr uint32_t kAStepMt = (128 * kRowBytes) >> 4;                 // next 128 rows
+        constexpr uint32_t kBStepK = (Tr::kUmmaK * kRowBytes) >> 4;           // kUmmaK rows
         for (int cb = 0; cb < s.cblocks; ++cb) {
-          const uint32_t a_cb = halo_addr + cb * s.halo_rows * kRowBytes;
+          const uint64_t adesc_cb = adesc_hb + (uint64_t)((cb * s.halo_rows * kRowBytes) >> 4);
+          int r = 0, sx = 0;
           for (int tap = 0; tap < taps; ++tap) {
             mbar_wait(&b_full[stage], phase);
+            __syncwarp();  // the spin loop above is per-lane: tell ptxas the warp is converged
             tc_fence_after();
             if (it.active) {
-              const int r = tap / s.S, sx = tap - r * s.S;
-              const uint32_t a_tap = a_cb + (uint32_t)(r * s.WP + sx) * kRowBytes;
-              const uint32_t b_addr = smem_u32(smB + stage * kBStageBytes);
-              for (int mt = 0; mt < s.n_mtiles; ++mt) {
-                const uint32_t d_tmem = tmem_base + acc * kAccCols + mt * BN;
+              const uint64_t adesc_tap = adesc_cb + (uint64_t)(((r * s.WP + sx) * kRowBytes) >> 4);
+              const uint64_t bdesc_st = bdesc_0 + (uint64_t)((stage * kBStageBytes) >> 4);
+              const uint32_t a_hi = (uint32_t)(adesc_tap >> 32), b_hi = (uint32_t)(bdesc_st >> 32);
+              const uint32_t a_lo0 = (uint32_t)adesc_tap, b_lo0 = (uint32_t)bdesc_st;
+              const uint32_t d0 = tmem_base + acc * kAccCols;
+              const uint32_t acc_first = (cb | tap) == 0 ? 0u : 1u;
+              // k outer, M tile inner: the B descriptor changes once per k step, the address
+              // fields never carry into the high words (smem addresses < 256 KB)
 #pragma unroll
-                for (int k = 0; k < kChunk / Tr::kUmmaK; ++k) {
-                  // A: K-major rows of the halo tile, +32 B per k step inside the swizzle row
-                  const uint64_t adesc = make_smem_desc_sw128(
-                      a_tap + (uint32_t)mt * 128 * kRowBytes + k * Tr::kUmmaK * (int)sizeof(TIn), 16,
-                      1024);
-                  // B: MN-major filter tile, kUmmaK rows per k step
-                  const uint64_t bdesc = make_smem_desc_sw128(
-                      b_addr + k * Tr::kUmmaK * kRowBytes, kChunk * kRowBytes,
-                      Tr::kMn32 ? 512 : 1024, Tr::kMn32 ? 1 : 2);
-                  const uint32_t accum = (cb | tap | k) != 0;
+              for (int k = 0; k < kChunk / Tr::kUmmaK; ++k) {
+                const uint32_t b_lo = b_lo0 + k * kBStepK;
+                const uint32_t accum = k == 0 ? acc_first : 1u;
+                for (int mt = iw; mt < s.n_mtiles; mt += kIssueWarps) {
+                  const uint32_t a_lo = a_lo0 + mt * kAStepMt + k * kAStepK;
                   if (sizeof(TIn) == 4)
-                    umma_tf32(d_tmem, adesc, bdesc, kIdesc, accum);
+                    umma_tf32_elect_lohi(d0 + mt * BN, a_lo, a_hi, b_lo, b_hi, kIdesc, accum);
                   else
-                    umma_f16(d_tmem, adesc, bdesc, kIdesc, accum);
+                    umma_f16_elect_lohi(d0 + mt * BN, a_lo, a_hi, b_lo, b_hi, kIdesc, accum);
                 }
               }
             }
+            if (++sx == s.S) {
+              sx = 0;
+              ++r;
+            }
             // the filter slot is free (in every CTA of the cluster) once these MMAs retire
             if (cl > 1)
-              umma_commit_mc(&b_empty[stage], mask);
+              umma_commit_mc_elect(&b_empty[stage], mask);
             else
-              umma_commit(&b_empty[stage]);
+              umma_commit_elect(&b_empty[stage]);
             if (++stage == (uint32_t)s.b_stages) {
               stage = 0;
               phase ^= 1;
@@ -291,8 +323,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
           }
         }
         if (it.active) {
-          umma_commit(&tfull[acc]);        // accumulators complete -> epilogue
-          umma_commit(&halo_empty[hb]);    // halo tile consumed -> producer may refill it
+          umma_commit_elect(&tfull[acc]);        // accumulators complete -> epilogue
+          umma_commit_elect(&halo_empty[hb]);    // halo tile consumed -> producer may refill it
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
@@ -320,6 +352,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
       for (int mt = 0; mt < s.n_mtiles; ++mt) {
         const int prow0 = mt * 128 + quad * 32;  // first padded pixel of this warp's 32 rows
         if (prow0 >= vh * s.WP) continue;        // warp-uniform: nothing valid in these rows
+        // copy-out geometry of this lane's 8 pixel rows, once per M tile (integer divisions)
+        long long poff[8];
+#pragma unroll
+        for (int itr = 0; itr < 8; ++itr) {
+          const int pp = prow0 + itr * 4 + sub;
+          const int rr = pp / s.WP, cc = pp - rr * s.WP;
+          poff[itr] = (rr < vh && cc < vw)
+                          ? (((long long)it.n * s.OH + it.oh0 + rr) * s.OW + it.ow0 + cc) * s.K
+                          : -1;
+        }
 #pragma unroll 1
         for (int c = 0; c < BN / kEpiCols; ++c) {
           const int col = n0 + c * kEpiCols;
@@ -386,17 +428,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
 #pragma unroll
           for (int itr = 0; itr < 8; ++itr) {
             const int row = itr * 4 + sub;
-            const int p = prow0 + row;
-            const int rr = p / s.WP, cc = p - rr * s.WP;
-            if (rr < vh && cc < vw) {
+            if (poff[itr] >= 0) {
               uint32_t x0, x1, x2, x3;
               asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                            : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3)
                            : "r"(smem_u32(buf) + row * kRowBytes +
                                  (uint32_t)((c16 ^ (row & 7)) << 4)));
-              TOut* dst = out +
-                          (((long long)it.n * s.OH + it.oh0 + rr) * s.OW + it.ow0 + cc) * s.K + col +
-                          c16 * (16 / (int)sizeof(TOut));
+              TOut* dst = out + poff[itr] + col + c16 * (16 / (int)sizeof(TOut));
               if (vec_ok) {
                 *reinterpret_cast<uint4*>(dst) = make_uint4(x0, x1, x2, x3);
               } else {
@@ -515,7 +553,8 @@ static HaloPlan plan_halo(int dtype, int N, int H, int W, int C, int K, int R, i
     const char* v = getenv("B200TF_CONV_HALO_CLUSTER");
     return v ? atoi(v) : 0;
   }();
-  int cl = force_cl ? force_cl : 4;
+  // pairs tile all 148 SMs; clusters of 4 fit only 33 x 4 = 132 CTAs on this part (measured)
+  int cl = force_cl ? force_cl : 2;
   while (cl > 1 && s.items_per_nb < (long long)cl * 8) cl /= 2;
   if (cl != 1 && cl != 2 && cl != 4) cl = 1;
   s.cl = cl;
@@ -582,11 +621,7 @@ static int launch_halo(const HaloPlan& p, const void* input, const void* filter,
     }
     attr_smem = kSmemLimit;
   }
-  const long long clusters_wanted = s.work_padded / s.cl;
-  const long long clusters_max = sm_count() / s.cl;
-  const int clusters = (int)std::min(clusters_wanted, clusters_max);
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)(clusters * s.cl));
   cfg.blockDim = dim3(kHaloThreads);
   cfg.dynamicSmemBytes = p.smem;
   cfg.stream = stream;
@@ -599,6 +634,24 @@ static int launch_halo(const HaloPlan& p, const void* input, const void* filter,
     attr[na].val.clusterDim.z = 1;
     ++na;
   }
+  // Persistent static schedule: the grid must not exceed what is co-resident, or the surplus
+  // clusters run as a second wave.  A GPC holds a whole number of clusters, so fewer than
+  // SMs / cl clusters may fit: ask the occupancy calculator (cached per cluster size).
+  static int max_clusters[5] = {0, 0, 0, 0, 0};
+  if (max_clusters[s.cl] == 0) {
+    int n = 0;
+    cfg.gridDim = dim3((unsigned)(sm_count() / s.cl * s.cl));
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    if (s.cl > 1 && cudaOccupancyMaxActiveClusters(&n, kern, &cfg) == cudaSuccess && n > 0)
+      max_clusters[s.cl] = n;
+    else
+      max_clusters[s.cl] = sm_count() / s.cl;
+    cudaGetLastError();
+  }
+  const long long clusters_wanted = s.work_padded / s.cl;
+  const int clusters = (int)std::min<long long>(clusters_wanted, max_clusters[s.cl]);
+  cfg.gridDim = dim3((unsigned)(clusters * s.cl));
   if (pdl_enabled()) {
     attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[na].val.programmaticStreamSerializationAllowed = 1;

@@ -178,19 +178,6 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ float4 ld_cg_f4(const float* p) {  // L2-coherent (never L1 / nc)
-  float4 v;
-  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p)
-               : "memory");
-  return v;
-}
-__device__ __forceinline__ float ld_cg_f1(const float* p) {
-  float v;
-  asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void store_out4(float* dst, const float4& a) {
   *reinterpret_cast<float4*>(dst) = a;
 }
@@ -736,45 +723,63 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
         const bool n4 = (s.N & 3) == 0 && (s.ldc & 3) == 0 && (s.strideC & 3) == 0 &&
                         ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
         const long long per_split = (long long)s.batch * s.M * s.N;
-        for (int j = split; j < 32; j += s.splits) {
-          const int r = row0 + j;
-          if (r >= s.M) break;
-          const float* prow0 = s.partial + ((long long)b * s.M + r) * (long long)s.N;
-          TOut* crow_r = C + (long long)b * s.strideC + (long long)r * s.ldc;
-          if (n4) {
+        if (n4) {
+          // Vector v of this warp = (row j = split + (v / kVecPerRow) * splits, 128-column group
+          // v % kVecPerRow).  kInFlight vectors x up to 4 splits of independent 16-byte loads are
+          // issued before the first add, so the L2 round trips overlap; the adds stay in
+          // ascending split order.
+          constexpr int kVecPerRow = BN >= 128 ? BN / 128 : 1;
+          constexpr int kInFlight = 4;
+          const int my_rows = split < 32 ? (32 - split + s.splits - 1) / s.splits : 0;
+          const int nvec = my_rows * kVecPerRow;
+          for (int v0 = 0; v0 < nvec; v0 += kInFlight) {
+            float4 a[kInFlight];
+            const float* src[kInFlight];
+            TOut* dst[kInFlight];
+            bool on[kInFlight];
 #pragma unroll
-            for (int i = 0; i < BN / 128; ++i) {
-              const int col = n0 + (i * 32 + lane) * 4;
-              if (col < s.N) {
-                float4 a = ld_cg_f4(prow0 + col);
-                for (int sp = 1; sp < s.splits; ++sp) {
-                  const float4 v = ld_cg_f4(prow0 + sp * per_split + col);
-                  a.x += v.x;
-                  a.y += v.y;
-                  a.z += v.z;
-                  a.w += v.w;
-                }
-                store_out4(crow_r + col, a);
-              }
+            for (int u = 0; u < kInFlight; ++u) {
+              const int v = v0 + u;
+              const int j = split + (v / kVecPerRow) * s.splits;
+              const int r = row0 + j;
+              const int col = n0 + ((v % kVecPerRow) * 32 + lane) * 4;
+              on[u] = v < nvec && r < s.M && col < s.N && (BN >= 128 || lane * 4 < BN);
+              src[u] = s.partial + ((long long)b * s.M + r) * (long long)s.N + col;
+              dst[u] = C + (long long)b * s.strideC + (long long)r * s.ldc + col;
+              a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            if (BN < 128) {
-              const int col = n0 + lane * 4;
-              if (lane * 4 < BN && col < s.N) {
-                float4 a = ld_cg_f4(prow0 + col);
-                for (int sp = 1; sp < s.splits; ++sp) {
-                  const float4 v = ld_cg_f4(prow0 + sp * per_split + col);
-                  a.x += v.x;
-                  a.y += v.y;
-                  a.z += v.z;
-                  a.w += v.w;
-                }
-                store_out4(crow_r + col, a);
-              }
+            for (int sp0 = 0; sp0 < s.splits; sp0 += 4) {
+              float4 t[kInFlight][4];
+#pragma unroll
+              for (int u = 0; u < kInFlight; ++u)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (on[u] && sp0 + q < s.splits)
+                    t[u][q] = __ldcg(reinterpret_cast<const float4*>(src[u] + (sp0 + q) * per_split));
+#pragma unroll
+              for (int u = 0; u < kInFlight; ++u)
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (on[u] && sp0 + q < s.splits) {
+                    a[u].x += t[u][q].x;
+                    a[u].y += t[u][q].y;
+                    a[u].z += t[u][q].z;
+                    a[u].w += t[u][q].w;
+                  }
             }
-          } else {
+#pragma unroll
+            for (int u = 0; u < kInFlight; ++u)
+              if (on[u]) store_out4(dst[u], a[u]);
+          }
+        } else {
+          for (int j = split; j < 32; j += s.splits) {
+            const int r = row0 + j;
+            if (r >= s.M) break;
+            const float* prow0 = s.partial + ((long long)b * s.M + r) * (long long)s.N;
+            TOut* crow_r = C + (long long)b * s.strideC + (long long)r * s.ldc;
             for (int col = n0 + lane; col < n0 + BN && col < s.N; col += 32) {
-              float a = ld_cg_f1(prow0 + col);
-              for (int sp = 1; sp < s.splits; ++sp) a += ld_cg_f1(prow0 + sp * per_split + col);
+              float a = __ldcg(prow0 + col);
+              for (int sp = 1; sp < s.splits; ++sp) a += __ldcg(prow0 + sp * per_split + col);
               store_out1(crow_r + col, a);
             }
           }
@@ -1082,12 +1087,15 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   }
   const long long work = tiles * splits;
   const int grid_units = (int)(work < units ? work : units);
-  // In-kernel reduction needs every (split, tile) work item on its own resident CTA (pair), so
-  // that waiting for the other splits of a tile cannot deadlock: plan_splits guarantees
-  // work <= units.  B200TF_SPLITK_SEPARATE=1 keeps the second kernel (comparison switch).
+  // In-kernel reduction (B200TF_SPLITK_INKERNEL=1) needs every (split, tile) work item on its own
+  // resident CTA (pair), so that waiting for the other splits of a tile cannot deadlock:
+  // plan_splits guarantees work <= units.  Measured on the MLP's dW GEMM (1024x1024x4096, 4
+  // splits): 26.7 us in-kernel vs 26.6 us with the separate ordered pass, step time unchanged --
+  // the wait for the slowest split plus the L2 round trips of the reduction cost what the second
+  // launch costs -- so the simpler two-kernel form stays the default (profiles/r02_notes.md).
   s.tickets = nullptr;
-  static const bool separate_reduce = getenv("B200TF_SPLITK_SEPARATE") != nullptr;
-  if (splits > 1 && !separate_reduce && work <= units && tiles <= kSplitKMaxTiles) {
+  static const bool inkernel_reduce = getenv("B200TF_SPLITK_INKERNEL") != nullptr;
+  if (splits > 1 && inkernel_reduce && work <= units && tiles <= kSplitKMaxTiles) {
     static unsigned int* ticket_base[64] = {nullptr};
     static std::atomic<unsigned> next_slot{0};
     int dev = 0;

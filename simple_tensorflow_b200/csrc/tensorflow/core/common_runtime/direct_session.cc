@@ -521,7 +521,14 @@ Status DirectSession::FuseMatMulChains(ExecutorsAndKeys* ek) {
   };
   for (size_t i = 0; i < ek->order.size(); ++i) {
     PlanNode& mm = ek->order[i];
-    if (mm.dead || mm.node < 0 || mm.item->def.op != "MatMul") continue;
+    if (mm.dead || mm.node < 0) continue;
+    const bool is_conv = mm.item->def.op == "Conv2D";
+    if (!is_conv && mm.item->def.op != "MatMul") continue;
+    if (is_conv) {  // NHWC only: the fused kernels are NHWC-native
+      std::string cfmt = "NHWC";
+      GetNodeAttr(mm.item->def, "data_format", &cfmt);
+      if (cfmt != "NHWC") continue;
+    }
     const DataType dt = mm.item->kernel->input_type(0);
     if (dt != DT_FLOAT && dt != DT_BFLOAT16) continue;
     if (!single_use(entry_of(mm, 0))) continue;
@@ -545,7 +552,7 @@ Status DirectSession::FuseMatMulChains(ExecutorsAndKeys* ek) {
           last = k;
         }
       }
-    } else if (next.item->def.op == "ReluGrad") {
+    } else if (!is_conv && next.item->def.op == "ReluGrad") {
       fused_ops = {"ReluGrad"};
       extra = next.inputs[1];
       // features must not be the matmul output itself
@@ -555,12 +562,18 @@ Status DirectSession::FuseMatMulChains(ExecutorsAndKeys* ek) {
     }
     std::unique_ptr<NodeItem> fused(new NodeItem);
     PlanNode& tail = ek->order[last];
-    fused->def.name = tail.item->def.name + "/_fused_matmul";
-    fused->def.op = "_FusedMatMul";
+    fused->def.name = tail.item->def.name + (is_conv ? "/_fused_conv2d" : "/_fused_matmul");
+    fused->def.op = is_conv ? "_FusedConv2D" : "_FusedMatMul";
     fused->def.attr["T"] = AttrValue::Type(dt);
     fused->def.attr["num_args"] = AttrValue::I(1);
-    fused->def.attr["transpose_a"] = mm.item->def.attr.at("transpose_a");
-    fused->def.attr["transpose_b"] = mm.item->def.attr.at("transpose_b");
+    if (is_conv) {
+      fused->def.attr["strides"] = mm.item->def.attr.at("strides");
+      fused->def.attr["padding"] = mm.item->def.attr.at("padding");
+      fused->def.attr["data_format"] = AttrValue::S("NHWC");
+    } else {
+      fused->def.attr["transpose_a"] = mm.item->def.attr.at("transpose_a");
+      fused->def.attr["transpose_b"] = mm.item->def.attr.at("transpose_b");
+    }
     fused->def.attr["fused_ops"] = AttrValue::ListS(fused_ops);
     fused->def.input = {mm.item->def.input[0], mm.item->def.input[1], "<fused>"};
     TF_RETURN_IF_ERROR(EnsureKernel(fused.get()));

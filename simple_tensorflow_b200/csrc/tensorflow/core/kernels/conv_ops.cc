@@ -144,6 +144,59 @@ class Conv2DOp : public OpKernel {
   ConvAttrs attrs_;
 };
 
+// Conv2D + BiasAdd (+ Relu) in one launch: created only by DirectSession::FuseConvChains for
+// NHWC graphs; validation = Conv2DOp's plus BiasOp's (bias_op.cc:62-82).
+template <typename T>
+class FusedConv2DOp : public OpKernel {
+ public:
+  explicit FusedConv2DOp(OpKernelConstruction* context) : OpKernel(context) {
+    OP_REQUIRES_OK(context, attrs_.Init(context));
+    OP_REQUIRES(context, !attrs_.nchw,
+                errors::InvalidArgument("_FusedConv2D is NHWC-only"));
+    std::vector<std::string> fused;
+    OP_REQUIRES_OK(context, context->GetAttr("fused_ops", &fused));
+    if (fused == std::vector<std::string>{"BiasAdd"}) relu_ = false;
+    else if (fused == std::vector<std::string>{"BiasAdd", "Relu"}) relu_ = true;
+    else
+      OP_REQUIRES(context, false, errors::InvalidArgument("Unsupported fused_ops for _FusedConv2D"));
+    OP_REQUIRES(context, context->num_inputs() == 3,
+                errors::InvalidArgument("_FusedConv2D expects exactly one extra argument"));
+  }
+  void Compute(OpKernelContext* context) override {
+    const Tensor& input = context->input(0);
+    const Tensor& filter = context->input(1);
+    const Tensor& bias = context->input(2);
+    OP_REQUIRES(context, input.dims() == 4,
+                errors::InvalidArgument("input must be 4-dimensional", input.shape().DebugString()));
+    b200_conv2d_geometry g;
+    TensorShape out_shape;
+    OP_REQUIRES_OK(context, MakeGeometry("Conv2D", input.shape(), filter.shape(), nullptr, attrs_,
+                                         &g, &out_shape));
+    OP_REQUIRES(context, TensorShapeUtils::IsVector(bias.shape()),
+                errors::InvalidArgument("Biases must be 1D: ", bias.shape().DebugString()));
+    OP_REQUIRES(context, bias.dim_size(0) == out_shape.dim_size(3),
+                errors::InvalidArgument("Must provide as many biases as the last dimension of the "
+                                        "input tensor: ", bias.shape().DebugString(), " vs. ",
+                                        out_shape.DebugString()));
+    Tensor* output = nullptr;
+    OP_REQUIRES_OK(context, context->allocate_output(0, out_shape, &output));
+    if (out_shape.num_elements() == 0) return;
+    const size_t ws = b200_conv2d_workspace_bytes(AbiType<T>::v, &g, 0);
+    Tensor scratch;
+    OP_REQUIRES_OK(context, Scratch(context, ws, &scratch));
+    OP_REQUIRES_OK(context,
+                   FromAbi(b200_fused_conv2d(AbiType<T>::v, input.raw_data(), filter.raw_data(),
+                                             bias.raw_data(), relu_ ? 1 : 0, output->raw_data(), &g,
+                                             ws ? scratch.raw_data() : nullptr, ws,
+                                             GetCudaStream(context)),
+                           "_FusedConv2D"));
+  }
+
+ private:
+  ConvAttrs attrs_;
+  bool relu_ = false;
+};
+
 template <typename T>
 class Conv2DBackpropInputOp : public OpKernel {
  public:
@@ -237,6 +290,8 @@ class Conv2DBackpropFilterOp : public OpKernel {
 };
 
 #define REGISTER_GPU(T)                                                                       \
+  REGISTER_KERNEL_BUILDER(Name("_FusedConv2D").Device(DEVICE_GPU).TypeConstraint<T>("T"),     \
+                          FusedConv2DOp<T>);                                                  \
   REGISTER_KERNEL_BUILDER(Name("Conv2D").Device(DEVICE_GPU).TypeConstraint<T>("T"),           \
                           Conv2DOp<T>);                                                       \
   REGISTER_KERNEL_BUILDER(Name("Conv2DBackpropInput")                                         \

@@ -36,6 +36,13 @@ REGISTER_OP("Conv2D")
     .Attr("T: {half, float, double, bfloat16}").Attr("strides: list(int)")
     .Attr("use_cudnn_on_gpu: bool = true").Attr(PADDING_ATTR).Attr(DATA_FORMAT_ATTR);
 
+// Produced only by the executor's rewrite of Conv2D -> BiasAdd (-> Relu) chains (NHWC):
+// args[0] is the bias; fused_ops is {BiasAdd} or {BiasAdd, Relu}.
+REGISTER_OP("_FusedConv2D")
+    .Input("input: T").Input("filter: T").Input("args: num_args * T").Output("output: T")
+    .Attr("T: {float, bfloat16}").Attr("num_args: int >= 0").Attr("strides: list(int)")
+    .Attr(PADDING_ATTR).Attr(DATA_FORMAT_ATTR).Attr("fused_ops: list(string)");
+
 REGISTER_OP("Conv2DBackpropInput")
     .Input("input_sizes: int32").Input("filter: T").Input("out_backprop: T").Output("output: T")
     .Attr("T: {half, float, double, bfloat16}").Attr("strides: list(int)")

@@ -433,6 +433,8 @@ def test_conv_halo_forward_and_input_gradient_vs_oracle(oracle, rng, shape, fsha
         dy = rng.rand(*y_ref.shape).astype(np.float32) - 0.5
         dx = au.conv2d_backprop_input(shape, f, dy, (1, 1), padding, oracle)
         assert au.rel_err(dx, oracle.conv2d_backprop_input(shape, f, dy, (1, 1), padding)) < TOL_TF32
+        dw = au.conv2d_backprop_filter(x, fshape, dy, (1, 1), padding, oracle)
+        assert au.rel_err(dw, oracle.conv2d_backprop_filter(x, fshape, dy, (1, 1), padding)) < TOL_TF32
 
 
 def test_conv_halo_integer_data_is_exact(oracle, rng):
@@ -447,6 +449,21 @@ def test_conv_halo_integer_data_is_exact(oracle, rng):
     np.testing.assert_array_equal(
         au.conv2d_backprop_input(x.shape, f, dy, (1, 1), "SAME", oracle),
         oracle.conv2d_backprop_input(x.shape, f, dy, (1, 1), "SAME"))
+    # filter gradient: every tap group (horizontal, vertical, single) addressed exactly
+    np.testing.assert_array_equal(
+        au.conv2d_backprop_filter(x, f.shape, dy, (1, 1), "SAME", oracle),
+        oracle.conv2d_backprop_filter(x, f.shape, dy, (1, 1), "SAME"))
+    dyv = rng.randint(-3, 4, (4, 10, 10, 64)).astype(np.float32)
+    np.testing.assert_array_equal(
+        au.conv2d_backprop_filter(x, f.shape, dyv, (1, 1), "VALID", oracle),
+        oracle.conv2d_backprop_filter(x, f.shape, dyv, (1, 1), "VALID"))
+    for fs in [(3, 3, 32, 32), (2, 4, 32, 64), (1, 7, 32, 32), (6, 1, 32, 32)]:
+        fz = rng.randint(-3, 4, fs).astype(np.float32)
+        yz = oracle.conv2d(x, fz, (1, 1), "SAME")
+        dz = rng.randint(-2, 3, yz.shape).astype(np.float32)
+        np.testing.assert_array_equal(
+            au.conv2d_backprop_filter(x, fs, dz, (1, 1), "SAME", oracle),
+            oracle.conv2d_backprop_filter(x, fs, dz, (1, 1), "SAME"))
 
 
 def test_conv_halo_bf16(oracle, rng):
@@ -457,6 +474,8 @@ def test_conv_halo_bf16(oracle, rng):
     dy = oracle.truncate_to_bf16(rng.rand(*y_ref.shape).astype(np.float32) - 0.5)
     dx = au.conv2d_backprop_input(x.shape, f, dy, (1, 1), "SAME", oracle, bf16=True)
     assert au.rel_err(dx, oracle.conv2d_backprop_input(x.shape, f, dy, (1, 1), "SAME")) < TOL
+    dw = au.conv2d_backprop_filter(x, f.shape, dy, (1, 1), "SAME", oracle, bf16=True)
+    assert au.rel_err(dw, oracle.conv2d_backprop_filter(x, f.shape, dy, (1, 1), "SAME")) < TOL
 
 
 def test_conv2d_empty_batch(oracle):

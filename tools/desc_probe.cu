@@ -54,7 +54,7 @@ probe_kernel(const __grid_constant__ CUtensorMap mapShift, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tslot;
-  const int fix_rows = test == 0 ? 64 : 128;
+  const int fix_rows = test == 0 ? 64 : (test == 2 ? 32 : 128);
   if (threadIdx.x == 0) {
     mbar_expect_tx(&bar[0], kARows * 128 + fix_rows * 128);
     tma_load_2d(smShift, &mapShift, &bar[0], 0, 0);
@@ -77,6 +77,14 @@ probe_kernel(const __grid_constant__ CUtensorMap mapShift, const __grid_constant
                 make_smem_desc_sw128(smem_u32(smShift) + n * 128 + k * 32, 16, 1024), bo);
             bd = make_smem_desc_sw128(smem_u32(smFix) + k * 32, 16, 1024);
             idesc = make_idesc(2, false, false, 128, 64);
+          } else if (test == 2) {
+            // A: MN-major, M = 4 chunks x 32 channels; chunk j = the shifted tile at rows n + j
+            // (leading byte offset = ONE pixel row: overlapping chunks), K = 32 pixel rows.
+            // B: MN-major [K = 32 pixel rows][N = 32], fixed.
+            ad = with_base_offset(
+                make_smem_desc_sw128(smem_u32(smShift) + n * 128 + k * 8 * 128, 128, 512, 1), bo);
+            bd = make_smem_desc_sw128(smem_u32(smFix) + k * 8 * 128, 32 * 128, 512, 1);
+            idesc = make_idesc(2, true, true, 128, 32);
           } else {
             // B: MN-major (N = 32 channels contiguous), K rows n.., 8 rows per k step
             ad = make_smem_desc_sw128(smem_u32(smFix) + k * 32, 16, 1024);
@@ -136,7 +144,7 @@ int main() {
   cudaMemcpy(dShift, hShift.data(), hShift.size() * 4, cudaMemcpyHostToDevice);
   cudaMemcpy(dFix, hFix.data(), hFix.size() * 4, cudaMemcpyHostToDevice);
   cudaFuncSetAttribute(probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 52 * 1024);
-  for (int test = 0; test < 2; ++test) {
+  for (int test = 0; test < 3; ++test) {
     CUtensorMap mShift, mFix;
     cuuint64_t gdim[2] = {32, (cuuint64_t)kARows};
     cuuint64_t gstr[1] = {128};
@@ -146,11 +154,12 @@ int main() {
                         CU_TENSOR_MAP_INTERLEAVE_NONE,
                         test == 0 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B,
                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    const int fix_rows = test == 0 ? 64 : 128;
+    const int fix_rows = test == 0 ? 64 : (test == 2 ? 32 : 128);
     cuuint64_t gdim2[2] = {32, (cuuint64_t)fix_rows};
     cuuint32_t box2[2] = {32, (cuuint32_t)fix_rows};
     CUresult r2 = encode(&mFix, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dFix, gdim2, gstr, box2, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         test == 2 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
       printf("encode failed %d %d\n", (int)r, (int)r2);
@@ -166,7 +175,9 @@ int main() {
     std::vector<float> hOut(out_elems);
     cudaMemcpy(hOut.data(), dOut, out_elems * 4, cudaMemcpyDeviceToHost);
     printf("== test %s: max abs error per (row shift n, base-offset mode 0 | n&7 | n&3)\n",
-           test == 0 ? "K-major A, SWIZZLE_128B" : "MN-major B, SWIZZLE_128B_ATOM_32B");
+           test == 0 ? "K-major A, SWIZZLE_128B"
+                     : (test == 1 ? "MN-major B, SWIZZLE_128B_ATOM_32B"
+                                  : "MN-major A, M = 4 overlapping chunks (LBO = 128 B), ATOM_32B"));
     for (int n = 0; n < kShifts; ++n) {
       printf("n=%2d:", n);
       for (int mode = 0; mode < kModes; ++mode) {
@@ -179,6 +190,8 @@ int main() {
             for (int k = 0; k < 32; ++k) {
               if (test == 0)
                 ref += (double)hShift[(n + i) * 32 + k] * hFix[j * 32 + k];
+              else if (test == 2)  // row i = (chunk i / 32, channel i % 32); K index = pixel row
+                ref += (double)hShift[(n + i / 32 + k) * 32 + (i % 32)] * hFix[k * 32 + j];
               else
                 ref += (double)hFix[i * 32 + k] * hShift[(n + k) * 32 + j];
             }

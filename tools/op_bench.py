@@ -33,6 +33,10 @@ def peaks():
 
 
 HBM, BF16_TF, PEAK_SRC = peaks()
+try:  # measured cuBLAS TF32 burst (tools/measure_peaks.py on this pool's B200)
+    TF32_TF = json.load(open(os.path.join(ROOT, "profiles", "r02_measured_peaks.json")))["tf32_tflops"]
+except Exception:
+    TF32_TF = 0.5 * BF16_TF
 
 
 def t(*shape, dtype=torch.float32):
@@ -59,11 +63,14 @@ def main():
     ap.add_argument("--once", action="store_true")
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--only", default=None, help="run only ops whose name contains this substring")
     args = ap.parse_args()
     iters = 1 if args.once else args.iters
     rows = []
 
     def add(name, bytes_or_flops, unit, mk, fn, nsets=None):
+        if args.only and args.only not in name:
+            return
         per = max(1, bytes_or_flops if unit == "GB/s" else 64 << 20)
         n = nsets or max(2, min(12, int((300 << 20) // min(per, 300 << 20)) + 1))
         sets = [mk() for _ in range(n)]
@@ -73,7 +80,7 @@ def main():
             peak = HBM
         else:
             ach = bytes_or_flops / (us * 1e-6) / 1e12 if us else 0
-            peak = BF16_TF if "bf16" in name else 0.5 * BF16_TF
+            peak = BF16_TF if "bf16" in name else TF32_TF
         rows.append(dict(op=name, us=us, achieved=ach, unit=unit, peak=peak, frac=ach / peak if peak else 0))
         if not args.once:
             print("%-46s %9.1f us %10.1f %-8s %5.1f%% of %s peak" % (name, us, ach, unit, 100 * ach / peak, PEAK_SRC), flush=True)
@@ -148,7 +155,8 @@ def main():
         add("%s tf32 LeNet conv2 batch 512" % nm, flops, "TFLOP/s", mk, run, nsets=2)
     if args.json and not args.once:
         json.dump({"peaks": {"hbm_gbs": HBM, "bf16_tflops": BF16_TF, "source": PEAK_SRC,
-                             "tf32_peak": "0.5 x bf16 (no measured TF32 figure)"}, "rows": rows},
+                             "tf32_tflops": TF32_TF,
+                             "tf32_peak": "measured cuBLAS TF32 burst (profiles/r02_measured_peaks.json)"}, "rows": rows},
                   open(args.json, "w"), indent=1)
 
 
