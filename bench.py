@@ -181,7 +181,12 @@ def run_reference(args):
 
 # =================================================================================== GPU arm
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled during the timed region.
+
+    ONE long-lived `nvidia-smi -lms 100` child, started before the warm-up: forking a process
+    that holds a CUDA context costs tens of milliseconds, and a fork per sample inside the timed
+    region stalled the launch loop (a 100-step LeNet pass read 1.19 ms/step with a per-sample
+    subprocess, 0.60 without).  Only the samples between mark_begin() and mark_end() count."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -189,35 +194,53 @@ class ClockSampler(threading.Thread):
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.rows = []
-        self.stop_flag = threading.Event()
+        self.rows = []          # (wall time, fields)
+        self.t_begin = self.t_end = None
+        self.proc = None
 
     def run(self):
-        while not self.stop_flag.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True,
-                                     text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            self.stop_flag.wait(0.1)
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                line = line.strip()
+                if line:
+                    self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+        except Exception:
+            pass
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def summary(self):
-        self.stop_flag.set()
-        self.join(timeout=6)
-        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        if self.t_end is None:
+            self.mark_end()
+        time.sleep(0.15)  # let the sample that covers the end of the region arrive
+        try:
+            if self.proc is not None:
+                self.proc.terminate()
+        except Exception:
+            pass
+        self.join(timeout=3)
+        lo = (self.t_begin or 0.0) - 0.05
+        hi = self.t_end + 0.15
+        rows = [r for t, r in self.rows if lo <= t <= hi] or [r for _, r in self.rows[-2:]]
+        sm = [float(r[1]) for r in rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(names, r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None,
                 "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(self.rows)}
+                "samples": len(rows)}
 
 
 def load_peaks():
@@ -378,6 +401,9 @@ class Bench:
         feed = {B.xp: hx, B.lp: hl}
         # second pinned buffer pair: the input pipeline fills one while the other is in flight
         buffers = [(hx, hl), (w.host_tensor(B.x), w.host_tensor(B.labels))]
+        sampler = ClockSampler(self.local_rank)
+        if rank == 0:
+            sampler.start()  # before the warm-up: its one fork stays outside the timed region
         warm = max(args.warmup, 3, MIN_WARMUP)
         for _ in range(warm):
             sess.run(res_fetch)
@@ -387,9 +413,7 @@ class Bench:
         for _ in range(3):
             sess.run(res_fetch)
 
-        sampler = ClockSampler(self.local_rank)
-        if rank == 0:
-            sampler.start()
+        sampler.mark_begin()
         c0 = self.collective_counts()
         ms_res, launches, loss_res = timed(res_fetch, None, args.steps)
         c1 = self.collective_counts()
@@ -400,6 +424,7 @@ class Bench:
         ms_sync, _, _ = timed(fed_fetch, feed, args.steps)  # feed pinned buffers, copy inside Run()
         h2d = sess.last_run_stats()["h2d_bytes"]
         ms_e2e, _, loss_e2e = timed(fed_fetch, None, args.steps, prefetch=buffers)
+        sampler.mark_end()
         clocks = sampler.summary() if rank == 0 else None
         assert sum(client.HostTensor.numpy(t).nbytes for t in buffers[0]) == h2d
         d2h = sess.last_run_stats()["d2h_bytes"]
@@ -430,6 +455,7 @@ class Bench:
             peer, nccl = c1[0] - c0[0], c1[1] - c0[1]
             collective = {"kind": "peer" if peer and not nccl else ("nccl" if nccl and not peer
                                                                     else "mixed" if peer else "none"),
+                          "peer_backend": (L.b200_peer_arena_backend() or b"").decode(),
                           "peer_kernel_launches": peer, "nccl_calls": nccl,
                           "per_step": (peer + nccl) / max(1, args.steps)}
         else:

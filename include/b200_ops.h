@@ -133,6 +133,12 @@ B200_API int b200_fused_matmul(int dtype, const void* a, const void* b, void* c,
                                int64_t n, int64_t k, int transpose_a, int transpose_b,
                                const void* bias, int relu, const void* relu_grad_features,
                                void* stream);
+/* The same with optional scratch (b200_matmul_workspace_bytes): lets a bias / relu-tailed product
+ * with few output tiles split K; the tail is then applied by the ordered reduction pass. */
+B200_API int b200_fused_matmul_ws(int dtype, const void* a, const void* b, void* c, int64_t m,
+                                  int64_t n, int64_t k, int transpose_a, int transpose_b,
+                                  const void* bias, int relu, const void* relu_grad_features,
+                                  void* workspace, size_t workspace_bytes, void* stream);
 /* Replaces LaunchBatchMatMul<GPUDevice,Scalar>::Launch -> ThenBlasGemmBatchedWithScratch
  * (core/kernels/batch_matmul_op_impl.h:297-363).  x is [batch,m,k] (or [batch,k,m] when adj_x),
  * y is [batch,k,n] (or [batch,n,k] when adj_y); strided, no pointer arrays, no scratch. */
@@ -160,6 +166,15 @@ B200_API int b200_relu(int dtype, const void* features, void* activations, int64
                        void* stream);
 B200_API int b200_relu_grad(int dtype, const void* gradients, const void* features,
                             void* backprops, int64_t n, void* stream);
+/* backprops = ReluGrad(gradients, features) and bias_grad = BiasAddGrad(backprops) in ONE pass over
+ * [rows, channels]: the pair a convolution / dense layer's backward pass runs back to back
+ * (relu_op.h:62-94 then bias_op.cc:171-227); `backprops` may alias `gradients`.  Created by the
+ * executor's rewrite (`_ReluGradBiasAddGrad`); workspace from the _workspace_bytes call. */
+B200_API size_t b200_relu_grad_bias_grad_workspace_bytes(int dtype, int64_t rows, int64_t channels);
+B200_API int b200_relu_grad_bias_grad(int dtype, const void* gradients, const void* features,
+                                      void* backprops, void* bias_grad, int64_t rows,
+                                      int64_t channels, void* workspace, size_t workspace_bytes,
+                                      void* stream);
 
 /* ------------------------------------------------------------------ Softmax / LogSoftmax
  * SoftmaxEigenImpl (core/kernels/softmax_op_functor.h:43-99): rank-2 [rows, cols];
@@ -314,6 +329,9 @@ B200_API int b200_nccl_all_gather_bytes(const void* sendbuf, void* recvbuf, int6
  * on SMs next to resident GEMM CTAs). */
 B200_API int b200_peer_arena_create(void* nccl_comm, int rank, int nranks, size_t data_bytes,
                                     void** arena);
+/* What the last arena created in this process runs on: "nvls" (NVSwitch multicast memory, in-switch
+ * reduction: nvls_allreduce.cu), "peer-ipc" (peer-mapped buffers, peer_allreduce.cu) or "none". */
+B200_API const char* b200_peer_arena_backend(void);
 B200_API int b200_peer_arena_destroy(void* arena);
 B200_API void* b200_peer_arena_data(void* arena);
 B200_API size_t b200_peer_arena_bytes(void* arena);

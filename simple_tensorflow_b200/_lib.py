@@ -66,6 +66,8 @@ SIGNATURES = {
                             c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "b200_fused_matmul": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                   c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
+    "b200_fused_matmul_ws": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                  c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "b200_batch_matmul": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
                                   c_int64, c_int, c_int, c_void_p]),
     "b200_bias_add": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]),
@@ -74,6 +76,9 @@ SIGNATURES = {
                                    c_size_t, c_void_p]),
     "b200_relu": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "b200_relu_grad": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "b200_relu_grad_bias_grad_workspace_bytes": (c_size_t, [c_int, c_int64, c_int64]),
+    "b200_relu_grad_bias_grad": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
+                                         c_int64, c_void_p, c_size_t, c_void_p]),
     "b200_softmax": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),
     "b200_softmax_xent": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                   c_int64, c_void_p]),
@@ -117,6 +122,7 @@ SIGNATURES = {
     "b200_nccl_comm_user_rank": (c_int, [c_void_p, ctypes.POINTER(c_int)]),
     "b200_nccl_all_gather_bytes": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "b200_peer_arena_create": (c_int, [c_void_p, c_int, c_int, c_size_t, ctypes.POINTER(c_void_p)]),
+    "b200_peer_arena_backend": (ctypes.c_char_p, []),
     "b200_peer_arena_destroy": (c_int, [c_void_p]),
     "b200_peer_arena_data": (c_void_p, [c_void_p]),
     "b200_peer_arena_bytes": (c_size_t, [c_void_p]),

@@ -192,6 +192,40 @@ __device__ __forceinline__ void umma_f16_elect_lohi(uint32_t d_tmem, uint32_t a_
       "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// CTA-pair (cta_group::2) forms of the elected-lane MMA / commit: issued by the leader CTA only.
+__device__ __forceinline__ void umma_tf32_elect_lohi_2cta(uint32_t d_tmem, uint32_t a_lo,
+                                                          uint32_t a_hi, uint32_t b_lo,
+                                                          uint32_t b_hi, uint32_t idesc,
+                                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "elect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_elect_lohi_2cta(uint32_t d_tmem, uint32_t a_lo,
+                                                         uint32_t a_hi, uint32_t b_lo,
+                                                         uint32_t b_hi, uint32_t idesc,
+                                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "elect.sync _|e, 0xffffffff;\n\tsetp.ne.b32 p, %6, 0;\n\t"
+      "@e tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the barrier at this smem offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_elect_2cta(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+      " [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
   asm volatile(
       "{\n\t.reg .pred e;\n\telect.sync _|e, 0xffffffff;\n\t"

@@ -128,7 +128,12 @@ __device__ __forceinline__ WorkItem decode_work(const HaloShape& s, long long w)
   return it;
 }
 
-template <typename TIn, typename TOut, int BN>
+// kPair: the two CTAs of a cluster form a tcgen05 CTA pair (cta_group::2).  A tcgen05.mma occupies
+// the tensor pipe ~160 cycles whatever its N (tools/mma_rate_probe.cu: M128 x N32..256 all retire in
+// 160 cycles), so with N = K_out <= 64 the only way to more work per instruction is M: the leader
+// issues M = 256 MMAs over both CTAs' halo tiles (each CTA its own image, same smem offsets) and
+// each CTA stages half of the filter tile's columns.  Halves the MMA count per SM.
+template <typename TIn, typename TOut, int BN, bool kPair>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constant__ CUtensorMap tmapW,
                  TOut* __restrict__ out, const HaloShape s) {
@@ -136,8 +141,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
   using Tr = HaloTraits<TIn>;
   constexpr int kChunk = Tr::kChunk;               // channels per block = B rows per stage
   constexpr int kNChunks = BN / kChunk;            // 128-byte column chunks of a filter tile
-  constexpr int kBStageBytes = kNChunks * kChunk * kRowBytes;
-  constexpr uint32_t kIdesc = make_idesc(Tr::kFormat, false, true, 128, BN);
+  constexpr int kMyChunks = kPair ? kNChunks / 2 : kNChunks;  // filter chunks staged by this CTA
+  constexpr int kBStageBytes = kMyChunks * kChunk * kRowBytes;
+  constexpr uint32_t kIdesc = make_idesc(Tr::kFormat, false, true, kPair ? 256 : 128, BN);
+  static_assert(!kPair || kNChunks % 2 == 0, "pair mode splits the filter chunks between the CTAs");
   constexpr int kEpiCols = kRowBytes / (int)sizeof(TOut);  // output columns per staged 128-B row
   constexpr int kLdPerIter = kEpiCols / 32;
   static_assert(BN % kChunk == 0 && BN <= kAccCols, "BN");
@@ -165,6 +172,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
   const long long stride = (long long)gridDim.x;  // clusters * cl
   const uint16_t mask = (uint16_t)((1u << cl) - 1u);
   const int taps = s.R * s.S;
+  const bool leader = !kPair || rank == 0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmapX);
@@ -173,19 +181,23 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
   if (warp == 1) {
     if (lane == 0) {
       for (int i = 0; i < 2; ++i) {
-        mbar_init(&halo_full[i], 1);
+        mbar_init(&halo_full[i], kPair ? 2 : 1);  // pair: one producer arrive per CTA (leader's is used)
         mbar_init(&halo_empty[i], kIssueWarps);
         mbar_init(&tfull[i], kIssueWarps);
-        mbar_init(&tempty[i], 4);
+        mbar_init(&tempty[i], kPair ? 8 : 4);     // pair: both CTAs' epilogue warps (leader's is used)
       }
       for (int i = 0; i < kMaxBStages; ++i) {
-        mbar_init(&b_full[i], 1);
-        mbar_init(&b_empty[i], cl * kIssueWarps);  // one commit per issuing warp of every CTA
+        mbar_init(&b_full[i], kPair ? 2 : 1);
+        // one commit per issuing warp: of every CTA (multicast filter tiles) or of the leader (pair)
+        mbar_init(&b_empty[i], (kPair ? 1 : cl) * kIssueWarps);
       }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc<512>(tmem_slot);
+    if (kPair)
+      tmem_alloc_2cta<512>(tmem_slot);
+    else
+      tmem_alloc<512>(tmem_slot);
   }
   tc_fence_before();
   if (cl > 1)
@@ -209,43 +221,79 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
       // The halo tile of item i + 1 is requested BEFORE the filter tiles of item i: the filter
       // ring throttles the producer to a few taps ahead of the MMAs, so a halo load issued after
       // it would start only when item i is almost finished and its latency would be exposed.
-      auto issue_halo = [&](const WorkItem& h) {
+      // pair mode: `h` is this CTA's item, `peer_active` whether the other CTA of the pair loads too
+      auto issue_halo = [&](const WorkItem& h, bool peer_active) {
         mbar_wait(&halo_empty[hb], hphase ^ 1);
-        mbar_expect_tx(&halo_full[hb], (uint32_t)(s.cblocks * s.HP * s.WP * kRowBytes));
-        for (int cb = 0; cb < s.cblocks; ++cb)
-          tma_load_4d(smHalo + hb * halo_bytes + cb * s.halo_rows * kRowBytes, &tmapX,
-                      &halo_full[hb], cb * kChunk, h.ow0 - s.pl, h.oh0 - s.pt, h.n);
+        const uint32_t bytes = (uint32_t)(s.cblocks * s.HP * s.WP * kRowBytes);
+        if (!kPair) {
+          mbar_expect_tx(&halo_full[hb], bytes);
+        } else if (leader) {
+          mbar_expect_tx(&halo_full[hb], (h.active ? bytes : 0u) + (peer_active ? bytes : 0u));
+        } else {
+          mbar_arrive_remote(&halo_full[hb], 0);
+        }
+        if (h.active) {
+          for (int cb = 0; cb < s.cblocks; ++cb) {
+            uint8_t* dst = smHalo + hb * halo_bytes + cb * s.halo_rows * kRowBytes;
+            if (kPair)
+              tma_load_4d_2cta(dst, &tmapX, &halo_full[hb], cb * kChunk, h.ow0 - s.pl,
+                               h.oh0 - s.pt, h.n);
+            else
+              tma_load_4d(dst, &tmapX, &halo_full[hb], cb * kChunk, h.ow0 - s.pl, h.oh0 - s.pt,
+                          h.n);
+          }
+        }
         if (++hb == 2) {
           hb = 0;
           hphase ^= 1;
         }
       };
-      if (first < s.work_padded) {
-        const WorkItem it0 = decode_work(s, first);
-        if (it0.active) issue_halo(it0);
-      }
+      // the pair advances in lockstep: the leader's item is w, the peer's w + 1 (both or neither
+      // of a pair may be padding, never the leader alone)
+      auto pair_active = [&](long long w) {
+        const long long base_w = kPair ? w - (long long)rank : w;
+        return decode_work(s, base_w).active;  // the leader's item is active <=> the halo is needed
+      };
+      auto request_halo = [&](long long w) {
+        const WorkItem h = decode_work(s, w);
+        if (!kPair) {
+          if (h.active) issue_halo(h, false);
+        } else if (pair_active(w)) {
+          const long long peer_w = rank == 0 ? w + 1 : w - 1;
+          issue_halo(h, decode_work(s, peer_w).active);
+        }
+      };
+      if (first < s.work_padded) request_halo(first);
       for (long long w = first; w < s.work_padded; w += stride) {
         const WorkItem it = decode_work(s, w);
-        if (w + stride < s.work_padded) {
-          const WorkItem nx = decode_work(s, w + stride);
-          if (nx.active) issue_halo(nx);
-        }
+        if (w + stride < s.work_padded) request_halo(w + stride);
         for (int cb = 0; cb < s.cblocks; ++cb) {
           for (int tap = 0; tap < taps; ++tap) {
             mbar_wait(&b_empty[stage], phase ^ 1);
-            mbar_expect_tx(&b_full[stage], kBStageBytes);  // the whole tile lands here (multicast)
             const int krow = tap * s.C + cb * kChunk;      // HWIO row of this (tap, channel block)
             uint8_t* dst = smB + stage * kBStageBytes;
-            for (int p = 0; p < per_cta; ++p) {
-              const int piece = (int)rank * per_cta + p;
-              const int chunk = piece / row_parts, part = piece - chunk * row_parts;
-              uint8_t* d = dst + chunk * (kChunk * kRowBytes) + part * rows_per_piece * kRowBytes;
-              const int r0 = krow + part * rows_per_piece;
-              const int nchunk = it.nb * kNChunks + chunk;
-              if (cl > 1)
-                tma_load_3d_mc(d, &tmapW, &b_full[stage], 0, r0, nchunk, mask);
+            if (kPair) {
+              // each CTA stages its half of the tile's column chunks; bytes credit the leader
+              if (leader)
+                mbar_expect_tx(&b_full[stage], 2 * kBStageBytes);
               else
-                tma_load_3d(d, &tmapW, &b_full[stage], 0, r0, nchunk);
+                mbar_arrive_remote(&b_full[stage], 0);
+              for (int c = 0; c < kMyChunks; ++c)
+                tma_load_3d_2cta(dst + c * (kChunk * kRowBytes), &tmapW, &b_full[stage], 0, krow,
+                                 it.nb * kNChunks + (int)rank * kMyChunks + c);
+            } else {
+              mbar_expect_tx(&b_full[stage], kBStageBytes);  // the whole tile lands here (multicast)
+              for (int p = 0; p < per_cta; ++p) {
+                const int piece = (int)rank * per_cta + p;
+                const int chunk = piece / row_parts, part = piece - chunk * row_parts;
+                uint8_t* d = dst + chunk * (kChunk * kRowBytes) + part * rows_per_piece * kRowBytes;
+                const int r0 = krow + part * rows_per_piece;
+                const int nchunk = it.nb * kNChunks + chunk;
+                if (cl > 1)
+                  tma_load_3d_mc(d, &tmapW, &b_full[stage], 0, r0, nchunk, mask);
+                else
+                  tma_load_3d(d, &tmapW, &b_full[stage], 0, r0, nchunk);
+              }
             }
             if (++stage == (uint32_t)s.b_stages) {
               stage = 0;
@@ -259,7 +307,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
     // ===================== MMA issuers =====================
     // the whole warp runs this loop; one elected lane issues each tcgen05 instruction
     const int iw = warp == 1 ? 0 : warp - 5;  // issuer index: owns M tiles iw, iw + kIssueWarps, ...
-    {
+    if (leader) {  // pair mode: the leader CTA issues for both CTAs
       uint32_t stage = 0, phase = 0, hb = 0, hphase = 0, acc = 0, acc_phase = 0;
       for (long long w = first; w < s.work_padded; w += stride) {
         const WorkItem it = decode_work(s, w);
@@ -300,10 +348,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
                 const uint32_t accum = k == 0 ? acc_first : 1u;
                 for (int mt = iw; mt < s.n_mtiles; mt += kIssueWarps) {
                   const uint32_t a_lo = a_lo0 + mt * kAStepMt + k * kAStepK;
-                  if (sizeof(TIn) == 4)
+                  if (kPair) {
+                    if (sizeof(TIn) == 4)
+                      umma_tf32_elect_lohi_2cta(d0 + mt * BN, a_lo, a_hi, b_lo, b_hi, kIdesc, accum);
+                    else
+                      umma_f16_elect_lohi_2cta(d0 + mt * BN, a_lo, a_hi, b_lo, b_hi, kIdesc, accum);
+                  } else if (sizeof(TIn) == 4) {
                     umma_tf32_elect_lohi(d0 + mt * BN, a_lo, a_hi, b_lo, b_hi, kIdesc, accum);
-                  else
+                  } else {
                     umma_f16_elect_lohi(d0 + mt * BN, a_lo, a_hi, b_lo, b_hi, kIdesc, accum);
+                  }
                 }
               }
             }
@@ -312,7 +366,9 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
               ++r;
             }
             // the filter slot is free (in every CTA of the cluster) once these MMAs retire
-            if (cl > 1)
+            if (kPair)
+              umma_commit_elect_2cta(&b_empty[stage]);
+            else if (cl > 1)
               umma_commit_mc_elect(&b_empty[stage], mask);
             else
               umma_commit_elect(&b_empty[stage]);
@@ -323,8 +379,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
           }
         }
         if (it.active) {
-          umma_commit_elect(&tfull[acc]);        // accumulators complete -> epilogue
-          umma_commit_elect(&halo_empty[hb]);    // halo tile consumed -> producer may refill it
+          if (kPair) {
+            umma_commit_elect_2cta(&tfull[acc]);      // accumulators complete -> both epilogues
+            umma_commit_elect_2cta(&halo_empty[hb]);  // halo tiles consumed -> both producers
+          } else {
+            umma_commit_elect(&tfull[acc]);        // accumulators complete -> epilogue
+            umma_commit_elect(&halo_empty[hb]);    // halo tile consumed -> producer may refill it
+          }
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
@@ -344,9 +405,22 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
     const int sub = lane >> 3, c16 = lane & 7;  // copy-out: 4 rows x 8 x 16 B per instruction
     for (long long w = first; w < s.work_padded; w += stride) {
       const WorkItem it = decode_work(s, w);
-      if (!it.active) continue;
+      // pair mode: the peer of an active leader takes part in the TMEM hand-shake even when its
+      // own item is padding (the leader counts both CTAs' epilogue warps)
+      const bool engaged = kPair ? decode_work(s, w - (long long)rank).active : it.active;
+      if (!engaged) continue;
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
+      if (!it.active) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(&tempty[acc], 0);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+        continue;
+      }
       const int vh = min(s.bh, s.OH - it.oh0), vw = min(s.bw, s.OW - it.ow0);  // valid extent
       const int n0 = it.nb * BN;
       for (int mt = 0; mt < s.n_mtiles; ++mt) {
@@ -462,7 +536,12 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[acc]);
+      if (lane == 0) {
+        if (kPair && !leader)
+          mbar_arrive_remote(&tempty[acc], 0);  // the leader's MMA warps wait on it
+        else
+          mbar_arrive(&tempty[acc]);
+      }
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
@@ -477,7 +556,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmapX, const __grid_constan
     __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if (kPair)
+      tmem_dealloc_2cta<512>(tmem_base);
+    else
+      tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -513,6 +595,10 @@ static HaloPlan plan_halo(int dtype, int N, int H, int W, int C, int K, int R, i
     bn = K % 128 == 0 ? 128 : (K % 64 == 0 ? 64 : chunk);
   }
   if (bn < chunk) return best;
+  // A tcgen05.mma costs the same ~160 cycles for N = 32 as for N = 256, so a one-chunk N is padded
+  // to two chunks (the filter map zero-fills the missing columns, the epilogue never stores them):
+  // CTA pairs then split the chunks and issue M = 256 MMAs.
+  if (bn == chunk && 2 * chunk <= 256) bn = 2 * chunk;
   const int max_mt = kAccCols / bn;
   double best_score = -1.0;
   const int bw_cands[6] = {OW, 126, 62, 30, 14, 6};
@@ -547,6 +633,7 @@ static HaloPlan plan_halo(int dtype, int N, int H, int W, int C, int K, int R, i
   s.N = N; s.H = H; s.W = W; s.C = C; s.K = K; s.R = R; s.S = S; s.pt = pt; s.pl = pl;
   s.OH = OH; s.OW = OW;
   s.nblocks = (K + bn - 1) / bn;
+  best.bn = bn;
   s.items_per_nb = (long long)N * s.tiles_h * s.tiles_w;
   // cluster: multicast the filter tiles when there is enough work for whole clusters
   static const int force_cl = [] {
@@ -569,7 +656,7 @@ static HaloPlan plan_halo(int dtype, int N, int H, int W, int C, int K, int R, i
   return best;
 }
 
-template <typename TIn, int BN>
+template <typename TIn, int BN, bool kPair>
 static int launch_halo(const HaloPlan& p, const void* input, const void* filter, void* output,
                        cudaStream_t stream) {
   using Tr = HaloTraits<TIn>;
@@ -593,7 +680,7 @@ static int launch_halo(const HaloPlan& p, const void* input, const void* filter,
   }
   {
     // filter [R*S*C, K] row-major viewed as (128-B column chunk, row, chunk index)
-    const int row_parts = s.cl > BN / Tr::kChunk ? s.cl / (BN / Tr::kChunk) : 1;
+    const int row_parts = (!kPair && s.cl > BN / Tr::kChunk) ? s.cl / (BN / Tr::kChunk) : 1;
     cuuint64_t gdim[3] = {(cuuint64_t)Tr::kChunk, (cuuint64_t)s.R * s.S * s.C,
                           (cuuint64_t)(s.K / Tr::kChunk)};
     cuuint64_t gstr[2] = {(cuuint64_t)s.K * es, (cuuint64_t)Tr::kChunk * es};
@@ -609,7 +696,7 @@ static int launch_halo(const HaloPlan& p, const void* input, const void* filter,
       return B200_INTERNAL;
     }
   }
-  auto kern = conv_halo_kernel<TIn, TIn, BN>;
+  auto kern = conv_halo_kernel<TIn, TIn, BN, kPair>;
   static size_t attr_smem = 0;  // per instantiation
   if (attr_smem < p.smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -697,19 +784,29 @@ int conv_halo(int dtype, const ConvHaloArgs& a, cudaStream_t stream) {
   }
   p.s.bias = a.bias;
   p.s.relu = a.relu ? 1 : 0;
-#define HALO_CASE(T, BN_)                                                                 \
-  if (p.bn == BN_) return launch_halo<T, BN_>(p, a.input, a.filter, a.output, stream)
+  // CTA pairs (cta_group::2) whenever the cluster is a pair and the filter tile has an even number
+  // of 128-byte column chunks; B200TF_CONV_HALO_NO_PAIR=1 keeps independent CTAs (comparison).
+  static const bool no_pair = getenv("B200TF_CONV_HALO_NO_PAIR") != nullptr;
+  const int chunk = dtype == B200_DT_FLOAT ? 32 : 64;
+  const bool pair = !no_pair && p.s.cl == 2 && (p.bn / chunk) % 2 == 0;
+#define HALO_CASE(T, BN_)                                                                    \
+  if (p.bn == BN_)                                                                           \
+    return pair ? launch_halo<T, BN_, true>(p, a.input, a.filter, a.output, stream)          \
+                : launch_halo<T, BN_, false>(p, a.input, a.filter, a.output, stream)
+#define HALO_CASE_SINGLE(T, BN_) \
+  if (p.bn == BN_) return launch_halo<T, BN_, false>(p, a.input, a.filter, a.output, stream)
   if (dtype == B200_DT_FLOAT) {
-    HALO_CASE(float, 32);
+    HALO_CASE_SINGLE(float, 32);
     HALO_CASE(float, 64);
     HALO_CASE(float, 128);
     HALO_CASE(float, 256);
   } else {
-    HALO_CASE(__nv_bfloat16, 64);
+    HALO_CASE_SINGLE(__nv_bfloat16, 64);
     HALO_CASE(__nv_bfloat16, 128);
     HALO_CASE(__nv_bfloat16, 256);
   }
 #undef HALO_CASE
+#undef HALO_CASE_SINGLE
   set_last_error("conv_halo: no kernel for BN = %d", p.bn);
   return B200_UNIMPLEMENTED;
 }

@@ -821,7 +821,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
 template <typename TOut>
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, TOut* __restrict__ C, int splits,
-                     long long batch, int M, int N, int ldc, long long strideC) {
+                     long long batch, int M, int N, int ldc, long long strideC,
+                     const TOut* __restrict__ bias, int relu) {
   pdl_launch_dependents();
   pdl_wait();  // launched programmatically behind the GEMM that writes `partial`
   const long long per_split = batch * (long long)M * N;
@@ -850,6 +851,12 @@ splitk_reduce_kernel(const float* __restrict__ partial, TOut* __restrict__ C, in
     }
   }
   TOut* dst = C + b * strideC + (long long)row * ldc + col;
+  if (bias != nullptr) {  // fused tail of a split GEMM: + bias[col], then relu (full-precision sum)
+    for (int j = 0; j < nc; ++j) {
+      acc[j] += ld_as_float(bias + col + j);
+      if (relu) acc[j] = acc[j] > 0.f ? acc[j] : 0.f;
+    }
+  }
   for (int j = 0; j < nc; ++j) {
     if (sizeof(TOut) == 4)
       reinterpret_cast<float*>(dst)[j] = acc[j];
@@ -1029,8 +1036,11 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   // split-K when the output tiles alone cannot fill the SMs and scratch was provided
   const int num_kb = (int)((g.K + Tr::kBK - 1) / Tr::kBK);
   int splits = 1;
-  const bool fused = g.bias || g.relu || g.relu_grad_features;
-  if (g.workspace && !fused) {  // a fused tail needs the complete sum in one epilogue
+  // A ReluGrad tail needs the complete sum in the GEMM's own epilogue; a bias (+ relu) tail can
+  // ride on the ordered reduction pass of a split GEMM (LeNet fc1: 512 x 1024 x 3136 has 8 pair
+  // tiles for 74 pairs -- 43 us unsplit).
+  const bool fused = g.relu_grad_features != nullptr;
+  if (g.workspace && !fused) {
     splits = plan_splits(tiles, num_kb, units);
     while (splits > 1 &&
            (size_t)splits * g.batch * g.M * g.N * sizeof(float) > g.workspace_bytes)
@@ -1095,7 +1105,7 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   // launch costs -- so the simpler two-kernel form stays the default (profiles/r02_notes.md).
   s.tickets = nullptr;
   static const bool inkernel_reduce = getenv("B200TF_SPLITK_INKERNEL") != nullptr;
-  if (splits > 1 && inkernel_reduce && work <= units && tiles <= kSplitKMaxTiles) {
+  if (splits > 1 && inkernel_reduce && !g.bias && work <= units && tiles <= kSplitKMaxTiles) {
     static unsigned int* ticket_base[64] = {nullptr};
     static std::atomic<unsigned> next_slot{0};
     int dev = 0;
@@ -1175,7 +1185,8 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     cudaError_t e = cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<TOut>,
                                        static_cast<const float*>(s.partial), static_cast<TOut*>(g.c),
                                        splits, (long long)g.batch, s.M, s.N, s.ldc,
-                                       (long long)s.strideC);
+                                       (long long)s.strideC, static_cast<const TOut*>(g.bias),
+                                       g.relu ? 1 : 0);
     if (e != cudaSuccess) {
       set_last_error("splitk_reduce launch: %s", cudaGetErrorString(e));
       cudaGetLastError();

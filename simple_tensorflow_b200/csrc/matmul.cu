@@ -256,6 +256,14 @@ int b200_matmul(int dtype, const void* a, const void* b, void* c, int64_t m, int
 int b200_fused_matmul(int dtype, const void* a, const void* b, void* c, int64_t m, int64_t n,
                       int64_t k, int transpose_a, int transpose_b, const void* bias, int relu,
                       const void* relu_grad_features, void* stream) {
+  return b200_fused_matmul_ws(dtype, a, b, c, m, n, k, transpose_a, transpose_b, bias, relu,
+                              relu_grad_features, nullptr, 0, stream);
+}
+
+int b200_fused_matmul_ws(int dtype, const void* a, const void* b, void* c, int64_t m, int64_t n,
+                         int64_t k, int transpose_a, int transpose_b, const void* bias, int relu,
+                         const void* relu_grad_features, void* workspace, size_t workspace_bytes,
+                         void* stream) {
   int rc = validate_gemm("b200_fused_matmul", dtype, a, b, c, m, n, k, 1);
   if (rc) return rc;
   if (relu && relu_grad_features) {
@@ -283,6 +291,10 @@ int b200_fused_matmul(int dtype, const void* a, const void* b, void* c, int64_t 
   g.relu = relu != 0;
   g.relu_grad_features = relu_grad_features;
   g.ld_features = n;
+  if (workspace != nullptr && workspace_bytes > 0 && relu_grad_features == nullptr) {
+    g.workspace = workspace;  // enables split-K; the bias / relu tail moves to the reduction pass
+    g.workspace_bytes = workspace_bytes;
+  }
   const bool want_exact = dtype == B200_DT_FLOAT && b200_get_matmul_precision() == 1;
   if (!want_exact && gemm_tcgen05_supported(g) && driver().cuTensorMapEncodeTiled)
     return gemm_tcgen05(g, as_stream(stream));

@@ -19,6 +19,14 @@
 #include "b200_internal.h"
 
 namespace b200 {
+// nvls_allreduce.cu
+struct NvlsArena;
+int nvls_arena_create(void* nccl_comm, int rank, int nranks, size_t data_bytes, NvlsArena** out);
+void nvls_arena_destroy(NvlsArena* a);
+void* nvls_arena_data(NvlsArena* a);
+size_t nvls_arena_bytes(NvlsArena* a);
+int nvls_all_reduce(NvlsArena* a, size_t offset_bytes, long long count, int average, int max_ctas,
+                    cudaStream_t stream);
 namespace {
 
 constexpr int kMaxRanks = 8;
@@ -35,7 +43,10 @@ struct PeerTable {
   int rank, nranks;
 };
 
+const char* g_backend = "none";  // what the last arena created in this process runs on
+
 struct PeerArena {
+  NvlsArena* nvls = nullptr;  // non-null: the arena lives in NVSwitch multicast memory instead
   PeerTable table;
   size_t data_bytes = 0;
   uint32_t epoch = 0;  // barrier values used so far (all ranks issue the same call sequence)
@@ -188,6 +199,27 @@ int b200_peer_arena_create(void* nccl_comm, int rank, int nranks, size_t data_by
   }
   int rc = require_device("b200_peer_arena_create");
   if (rc) return rc;
+  {
+    // First choice: NVSwitch multicast memory (in-switch reduction).  The attempt is collective and
+    // ends in a vote, so either every rank gets an NVLS arena or every rank falls through to the
+    // peer-mapped arena below.  B200TF_NVLS=0 skips it.
+    const char* nv = getenv("B200TF_NVLS");
+    if (nv == nullptr || strcmp(nv, "0") != 0) {
+      NvlsArena* n = nullptr;
+      if (nvls_arena_create(nccl_comm, rank, nranks, data_bytes, &n) == B200_OK) {
+        PeerArena* a = new PeerArena();
+        memset(&a->table, 0, sizeof(a->table));
+        cudaGetDevice(&a->device);
+        a->nvls = n;
+        a->data_bytes = nvls_arena_bytes(n);
+        a->table.rank = rank;
+        a->table.nranks = nranks;
+        *out = a;
+        g_backend = "nvls";
+        return B200_OK;
+      }
+    }
+  }
   // owns the arena record, this rank's buffer and the handle scratch until creation succeeded
   struct Guard {
     PeerArena* a = nullptr;
@@ -282,6 +314,7 @@ int b200_peer_arena_create(void* nccl_comm, int rank, int nranks, size_t data_by
     set_last_error("b200_peer_arena_create: peer mapping unavailable on at least one rank");
     return B200_UNAVAILABLE;  // the guard releases everything
   }
+  g_backend = "peer-ipc";
   guard.a = nullptr;      // success: the caller owns the arena (and through it the buffer)
   guard.local = nullptr;
   *out = a;
@@ -291,6 +324,11 @@ int b200_peer_arena_create(void* nccl_comm, int rank, int nranks, size_t data_by
 int b200_peer_arena_destroy(void* arena) {
   PeerArena* a = static_cast<PeerArena*>(arena);
   if (!a) return B200_OK;
+  if (a->nvls) {
+    nvls_arena_destroy(a->nvls);
+    delete a;
+    return B200_OK;
+  }
   cudaSetDevice(a->device);
   cudaDeviceSynchronize();
   for (int p = 0; p < a->table.nranks; ++p)
@@ -301,8 +339,11 @@ int b200_peer_arena_destroy(void* arena) {
   return B200_OK;
 }
 
+const char* b200_peer_arena_backend(void) { return g_backend; }
+
 void* b200_peer_arena_data(void* arena) {
   PeerArena* a = static_cast<PeerArena*>(arena);
+  if (a && a->nvls) return nvls_arena_data(a->nvls);
   return a ? a->table.base[a->table.rank] + kHeaderBytes : nullptr;
 }
 
@@ -321,6 +362,7 @@ int b200_peer_all_reduce(void* arena, int dtype, size_t offset_bytes, int64_t co
     return B200_INVALID_ARGUMENT;
   }
   if (count == 0) return B200_OK;
+  if (a->nvls) return nvls_all_reduce(a->nvls, offset_bytes, count, average, max_ctas, as_stream(stream));
   const int nr = a->table.nranks;
   const long long nvec = (count + 3) / 4;  // the arena is padded to 256 bytes: whole vectors
   const long long slice = (nvec + nr - 1) / nr;

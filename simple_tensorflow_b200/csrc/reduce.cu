@@ -11,6 +11,7 @@
 #include <atomic>
 #include <cfloat>
 #include <cuda_bf16.h>
+#include <algorithm>
 
 #include "b200_internal.h"
 
@@ -221,6 +222,176 @@ static BiasGradPlan plan_bias_grad(int dtype, long long rows, long long channels
   p.rows_per_chunk = (int)((rows + want - 1) / want);
   p.nchunks = (int)((rows + p.rows_per_chunk - 1) / p.rows_per_chunk);
   return p;
+}
+
+// ================================================================== flat BiasAddGrad (+ ReluGrad)
+// For channel counts whose 16-byte vector columns divide a warp (G = C / VEC in {1, 2, .., 32}:
+// the conv layers' 32 / 64 channels): the [rows, C] matrix is streamed as ONE flat array of
+// 16-byte vectors.  The grid stride is a multiple of G, so a thread always meets the same column
+// group (lane % G) and simply accumulates -- fully coalesced loads, several in flight, no index
+// arithmetic.  Lanes of a column group are folded with shuffles, warps through shared memory, CTAs
+// through an ordered last-ticket pass (fixed order: deterministic, no atomics on the data).
+// kFused: the matrix is produced on the fly as ReluGrad(g, features) = g * (features > 0)
+// (relu_op_functor.h:44-60) and written to `dy`: the ReluGrad -> BiasAddGrad pair of a conv layer's
+// backward pass reads g and features once and writes dy once instead of re-reading dy.
+__device__ unsigned int g_flat_bias_grad_tickets[kBiasGradSlots];
+
+template <typename T, bool kFused>
+__global__ void __launch_bounds__(256)
+flat_bias_grad_kernel(const T* __restrict__ g, const T* __restrict__ features, T* __restrict__ dy,
+                      float* __restrict__ partial, T* __restrict__ out, long long nvec, int G,
+                      unsigned int* __restrict__ ticket) {
+  pdl_prologue();
+  constexpr int VEC = 16 / (int)sizeof(T);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long stride = (long long)gridDim.x * 256;
+  float acc[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  const uint4* gv = reinterpret_cast<const uint4*>(g);
+  const uint4* fv = reinterpret_cast<const uint4*>(features);
+  uint4* dv = reinterpret_cast<uint4*>(dy);
+  auto consume = [&](uint4 x, uint4 f, long long v) {
+    uint32_t xs[4] = {x.x, x.y, x.z, x.w};
+    if (kFused) {
+      const uint32_t fs[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (sizeof(T) == 4) {
+          xs[i] = __uint_as_float(fs[i]) > 0.f ? xs[i] : __float_as_uint(__uint_as_float(xs[i]) * 0.f);
+        } else {  // two bf16 per word: the mask is taken per element
+          const float lo = __uint_as_float(xs[i] << 16), hi = __uint_as_float(xs[i] & 0xFFFF0000u);
+          const bool klo = __uint_as_float(fs[i] << 16) > 0.f;
+          const bool khi = __uint_as_float(fs[i] & 0xFFFF0000u) > 0.f;
+          const uint32_t wlo = klo ? (xs[i] & 0xFFFFu) : (__float_as_uint(lo * 0.f) >> 16);
+          const uint32_t whi = khi ? (xs[i] & 0xFFFF0000u) : (__float_as_uint(hi * 0.f) & 0xFFFF0000u);
+          xs[i] = wlo | whi;
+        }
+      }
+      dv[v] = make_uint4(xs[0], xs[1], xs[2], xs[3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (sizeof(T) == 4) {
+        acc[i % VEC] += __uint_as_float(xs[i]);
+      } else {
+        acc[(2 * i) % VEC] += __uint_as_float(xs[i] << 16);
+        acc[(2 * i + 1) % VEC] += __uint_as_float(xs[i] & 0xFFFF0000u);
+      }
+    }
+  };
+  long long v = (long long)blockIdx.x * 256 + threadIdx.x;
+  for (; v + 3 * stride < nvec; v += 4 * stride) {  // four independent 16-byte loads in flight
+    uint4 x[4], f[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      x[u] = __ldg(gv + v + u * stride);
+      if (kFused) f[u] = __ldg(fv + v + u * stride);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) consume(x[u], kFused ? f[u] : x[u], v + u * stride);
+  }
+  for (; v < nvec; v += stride) {
+    const uint4 x = __ldg(gv + v);
+    consume(x, kFused ? __ldg(fv + v) : x, v);
+  }
+  // lanes with the same lane % G hold the same column group
+  for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+  }
+  __shared__ float sm[8][32][VEC];
+  if (lane < G) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) sm[warp][lane][j] = acc[j];
+  }
+  __syncthreads();
+  const int C = G * VEC;
+  if ((int)threadIdx.x < C) {
+    const int cg = threadIdx.x / VEC, j = threadIdx.x % VEC;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][cg][j];
+    partial[(long long)blockIdx.x * C + threadIdx.x] = t;
+    __threadfence();
+  }
+  __shared__ bool is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // ordered final pass: thread (c, part) adds blocks part, part + P, ...; parts combined in order
+  const int P = 256 / C;  // >= 1 (C <= 256)
+  const int c = threadIdx.x % C, part = threadIdx.x / C;
+  float t = 0.f;
+  if (part < P) {
+    // eight independent loads in flight, added in ascending block order (an `t += load` loop
+    // would serialise one L2 round trip per block: 74 x 0.5 us for a conv layer)
+    const int nb = (int)gridDim.x;
+    for (int b0 = part; b0 < nb; b0 += 8 * P) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int b = b0 + u * P;
+        v[u] = b < nb ? __ldcg(partial + (long long)b * C + c) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t += v[u];
+    }
+  }
+  float* flat = &sm[0][0][0];  // 8 * 32 * VEC >= 256 floats
+  __syncthreads();
+  flat[threadIdx.x] = part < P ? t : 0.f;
+  __syncthreads();
+  if ((int)threadIdx.x < C) {
+    float tot = 0.f;
+    for (int q = 0; q < P; ++q) tot += flat[q * C + threadIdx.x];
+    stf<T>(out + threadIdx.x, tot);
+  }
+  if (threadIdx.x == 0) *ticket = 0;  // ready for the next launch that uses this slot
+}
+
+struct FlatBiasGradPlan {
+  bool ok;
+  int G, blocks;
+  long long nvec;
+};
+static FlatBiasGradPlan plan_flat_bias_grad(int dtype, long long rows, long long channels) {
+  FlatBiasGradPlan p{false, 0, 0, 0};
+  const int vec = dtype == B200_DT_FLOAT ? 4 : 8;
+  if (channels % vec != 0) return p;
+  const long long G = channels / vec;
+  if (G < 1 || G > 32 || (G & (G - 1)) != 0) return p;
+  p.G = (int)G;
+  p.nvec = rows * G;
+  long long blocks = (p.nvec + 256 * 8 - 1) / (256 * 8);  // >= 8 vectors per thread
+  const long long cap = 4LL * sm_count();
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  p.blocks = (int)blocks;
+  p.ok = true;
+  return p;
+}
+template <typename T>
+static int launch_flat_bias_grad(const FlatBiasGradPlan& p, const void* g, const void* features,
+                                 void* dy, void* out, void* workspace, cudaStream_t s) {
+  static std::atomic<unsigned> next_slot{0};
+  unsigned int* base = nullptr;
+  if (cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_flat_bias_grad_tickets) != cudaSuccess)
+    return check_launch("flat_bias_grad");
+  unsigned int* ticket = base + next_slot.fetch_add(1) % kBiasGradSlots;
+  float* partial = static_cast<float*>(workspace);
+  if (features != nullptr)
+    launch_pdl(flat_bias_grad_kernel<T, true>, dim3(p.blocks), dim3(256), 0, s,
+               static_cast<const T*>(g), static_cast<const T*>(features), static_cast<T*>(dy), partial,
+               static_cast<T*>(out), p.nvec, p.G, ticket);
+  else
+    launch_pdl(flat_bias_grad_kernel<T, false>, dim3(p.blocks), dim3(256), 0, s,
+               static_cast<const T*>(g), static_cast<const T*>(nullptr), static_cast<T*>(nullptr),
+               partial, static_cast<T*>(out), p.nvec, p.G, ticket);
+  note_launch();
+  return check_launch("flat_bias_grad");
 }
 
 // ================================================================== Softmax family
@@ -676,7 +847,46 @@ size_t b200_bias_add_grad_workspace_bytes(int dtype, int64_t rows, int64_t chann
   BiasGradPlan a = plan_bias_grad(dtype, rows, channels, true);
   BiasGradPlan b = plan_bias_grad(dtype, rows, channels, false);
   const int n = a.nchunks > b.nchunks ? a.nchunks : b.nchunks;
-  return (size_t)n * (size_t)channels * sizeof(float);
+  size_t need = (size_t)n * (size_t)channels * sizeof(float);
+  const FlatBiasGradPlan f = plan_flat_bias_grad(dtype, rows, channels);
+  if (f.ok) need = std::max(need, (size_t)f.blocks * (size_t)channels * sizeof(float));
+  return need;
+}
+
+size_t b200_relu_grad_bias_grad_workspace_bytes(int dtype, int64_t rows, int64_t channels) {
+  return b200_bias_add_grad_workspace_bytes(dtype, rows, channels);
+}
+
+int b200_relu_grad_bias_grad(int dtype, const void* gradients, const void* features,
+                             void* backprops, void* bias_grad, int64_t rows, int64_t channels,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  if (rows < 0 || channels < 0) {
+    set_last_error("b200_relu_grad_bias_grad: negative size");
+    return B200_INVALID_ARGUMENT;
+  }
+  if (dtype != B200_DT_FLOAT && dtype != B200_DT_BFLOAT16) {
+    set_last_error("b200_relu_grad_bias_grad: unsupported dtype %d", dtype);
+    return B200_UNIMPLEMENTED;
+  }
+  if (channels == 0) return B200_OK;
+  const FlatBiasGradPlan f = plan_flat_bias_grad(dtype, rows, channels);
+  const size_t need = f.ok ? (size_t)f.blocks * (size_t)channels * sizeof(float) : 0;
+  static const bool off = getenv("B200TF_NO_FLAT_BIAS_GRAD") != nullptr;
+  if (rows > 0 && f.ok && !off && workspace && workspace_bytes >= need && aligned16(gradients) &&
+      aligned16(features) && aligned16(backprops)) {
+    int rc = require_device("b200_relu_grad_bias_grad");
+    if (rc) return rc;
+    return dtype == B200_DT_FLOAT
+               ? launch_flat_bias_grad<float>(f, gradients, features, backprops, bias_grad, workspace,
+                                              as_stream(stream))
+               : launch_flat_bias_grad<__nv_bfloat16>(f, gradients, features, backprops, bias_grad,
+                                                      workspace, as_stream(stream));
+  }
+  // any other shape: the two library kernels back to back (same arithmetic)
+  int rc = b200_relu_grad(dtype, gradients, features, backprops, rows * channels, stream);
+  if (rc) return rc;
+  return b200_bias_add_grad(dtype, backprops, bias_grad, rows, channels, workspace, workspace_bytes,
+                            stream);
 }
 
 int b200_bias_add_grad(int dtype, const void* out_backprop, void* out, int64_t rows,
@@ -698,6 +908,16 @@ int b200_bias_add_grad(int dtype, const void* out_backprop, void* out, int64_t r
   if (channels > INT32_MAX) {
     set_last_error("b200_bias_add_grad: channels exceeds int32");
     return B200_INVALID_ARGUMENT;
+  }
+  {
+    const FlatBiasGradPlan f = plan_flat_bias_grad(dtype, rows, channels);
+    static const bool flat_off = getenv("B200TF_NO_FLAT_BIAS_GRAD") != nullptr;
+    if (f.ok && !flat_off && aligned16(out_backprop) && workspace &&
+        workspace_bytes >= (size_t)f.blocks * (size_t)channels * sizeof(float))
+      return dtype == B200_DT_FLOAT
+                 ? launch_flat_bias_grad<float>(f, out_backprop, nullptr, nullptr, out, workspace, s)
+                 : launch_flat_bias_grad<__nv_bfloat16>(f, out_backprop, nullptr, nullptr, out,
+                                                        workspace, s);
   }
   const BiasGradPlan p = plan_bias_grad(dtype, rows, channels, aligned16(out_backprop));
   const size_t need = (size_t)p.nchunks * (size_t)channels * sizeof(float);

@@ -333,6 +333,7 @@ Status DirectSession::GetOrCreateExecutors(const std::vector<std::string>& feeds
   ek->node_first_entry = first_entry;
   if (getenv("B200TF_DISABLE_FUSION") == nullptr) {
     TF_RETURN_IF_ERROR(FuseMatMulChains(ek.get()));
+    TF_RETURN_IF_ERROR(FuseReluGradBiasGrad(ek.get()));
     TF_RETURN_IF_ERROR(FuseXentScale(ek.get()));
     TF_RETURN_IF_ERROR(FuseApplyGradientDescent(ek.get()));
   }
@@ -378,6 +379,55 @@ void DirectSession::PlanGradientArenas(ExecutorsAndKeys* ek) {
       producer.arena_slots[prod.second] = {a, static_cast<int>(i)};
     }
   }
+}
+
+// ReluGrad whose result feeds an NHWC BiasAddGrad (the backward pass of every conv / dense layer
+// that FuseMatMulChains has not already folded into a GEMM epilogue): one node with two outputs
+// that reads the gradient and the features once (`_ReluGradBiasAddGrad`).
+Status DirectSession::FuseReluGradBiasGrad(ExecutorsAndKeys* ek) {
+  for (size_t i = 0; i < ek->order.size(); ++i) {
+    PlanNode& rg = ek->order[i];
+    if (rg.dead || rg.node < 0 || rg.item->def.op != "ReluGrad") continue;
+    const DataType dt = rg.item->kernel->input_type(0);
+    if (dt != DT_FLOAT && dt != DT_BFLOAT16) continue;
+    if (rg.inputs[0].feed >= 0 || rg.inputs[1].feed >= 0) continue;
+    // the BiasAddGrad reading ReluGrad:0
+    int j = -1;
+    for (size_t k = i + 1; k < ek->order.size() && j < 0; ++k) {
+      const PlanNode& c = ek->order[k];
+      if (c.dead || c.node < 0 || c.item->def.op != "BiasAddGrad") continue;
+      if (c.inputs.size() == 1 && c.inputs[0].feed < 0 && c.inputs[0].id.node == rg.node &&
+          c.inputs[0].id.slot == 0)
+        j = static_cast<int>(k);
+    }
+    if (j < 0) continue;
+    PlanNode& bg = ek->order[j];
+    std::string fmt = "NHWC";
+    GetNodeAttr(bg.item->def, "data_format", &fmt);
+    if (fmt != "NHWC") continue;
+    std::unique_ptr<NodeItem> fused(new NodeItem);
+    fused->def.name = bg.item->def.name + "/_relu_grad_bias_grad";
+    fused->def.op = "_ReluGradBiasAddGrad";
+    fused->def.attr["T"] = AttrValue::Type(dt);
+    fused->def.input = {rg.item->def.input[0], rg.item->def.input[1]};
+    TF_RETURN_IF_ERROR(EnsureKernel(fused.get()));
+    PlanNode repl;
+    repl.node = -1;
+    repl.item = fused.get();
+    repl.first_entry = rg.first_entry;
+    repl.inputs = {rg.inputs[0], rg.inputs[1]};
+    repl.output_entries = {rg.out_entry(0), bg.out_entry(0)};
+    // ReluGrad:0 loses the BiasAddGrad as a consumer
+    --ek->entry_consumers[rg.out_entry(0)];
+    bg.dead = true;
+    ek->order[i] = std::move(repl);  // at the ReluGrad's position: every consumer comes later
+    ek->rewritten.push_back(std::move(fused));
+  }
+  std::vector<PlanNode> alive;
+  for (PlanNode& pn : ek->order)
+    if (!pn.dead) alive.push_back(std::move(pn));
+  ek->order.swap(alive);
+  return Status::OK();
 }
 
 Status DirectSession::FuseApplyGradientDescent(ExecutorsAndKeys* ek) {

@@ -143,6 +143,7 @@ class DirectSession : public Session {
   // Runs of ApplyGradientDescent nodes separated only by Const nodes (what an optimizer emits)
   // become one _MultiApplyGradientDescent: one launch instead of one per variable.
   Status FuseApplyGradientDescent(ExecutorsAndKeys* ek);
+  Status FuseReluGradBiasGrad(ExecutorsAndKeys* ek);
   void PlanGradientArenas(ExecutorsAndKeys* ek);
   Status RunPlan(ExecutorsAndKeys* ek, const std::vector<std::pair<std::string, Tensor>>& inputs,
                  std::vector<Tensor>* outputs);

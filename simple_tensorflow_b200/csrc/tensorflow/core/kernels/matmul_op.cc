@@ -173,12 +173,20 @@ class FusedMatMulOp : public OpKernel {
                                               m * n, stream), "Relu"));
       return;
     }
-    OP_REQUIRES_OK(ctx, FromAbi(b200_fused_matmul(
+    // scratch lets a bias / relu-tailed product with few output tiles split K (the tail then
+    // rides on the ordered reduction pass); allocate_temp like the plain MatMul does
+    const size_t ws_bytes =
+        mode_ == kReluGrad ? 0 : b200_matmul_workspace_bytes(AbiType<T>::v, m, n, k);
+    Tensor scratch;
+    if (ws_bytes > 0)
+      OP_REQUIRES_OK(ctx, ctx->allocate_temp(DT_UINT8, TensorShape({static_cast<int64>(ws_bytes)}),
+                                             &scratch));
+    OP_REQUIRES_OK(ctx, FromAbi(b200_fused_matmul_ws(
                                     AbiType<T>::v, a.raw_data(), b.raw_data(), out->raw_data(), m,
                                     n, k, transpose_a_, transpose_b_,
                                     mode_ == kReluGrad ? nullptr : arg.raw_data(),
                                     mode_ == kBiasRelu, mode_ == kReluGrad ? arg.raw_data() : nullptr,
-                                    stream),
+                                    ws_bytes ? scratch.raw_data() : nullptr, ws_bytes, stream),
                                 "Blas GEMM launch failed"));
   }
 

@@ -36,7 +36,47 @@ class ReluGradOp : public OpKernel {
   }
 };
 
+// ReluGrad + BiasAddGrad(NHWC) of its result in one pass (created only by the executor's rewrite):
+// outputs (backprops, bias_grad); validation = ReluGradOp's plus BiasGradOp's (bias_op.cc:185-199).
+template <typename T>
+class ReluGradBiasAddGradOp : public OpKernel {
+ public:
+  explicit ReluGradBiasAddGradOp(OpKernelConstruction* ctx) : OpKernel(ctx) {}
+  void Compute(OpKernelContext* ctx) override {
+    const Tensor& g = ctx->input(0);
+    const Tensor& a = ctx->input(1);
+    OP_REQUIRES(ctx, a.IsSameSize(g), errors::InvalidArgument("Inputs must have the same size"));
+    OP_REQUIRES(ctx, TensorShapeUtils::IsMatrixOrHigher(g.shape()),
+                errors::InvalidArgument("Input tensor must be at least 2D: ",
+                                        g.shape().DebugString()));
+    Tensor* out = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->forward_input_or_allocate_output({0}, 0, g.shape(), &out));
+    const int64 channels = g.dim_size(g.dims() - 1);
+    Tensor* db = nullptr;
+    OP_REQUIRES_OK(ctx, ctx->allocate_output(1, TensorShape({channels}), &db));
+    if (channels == 0) return;
+    const int64 rows = g.NumElements() / channels;
+    if (rows == 0) {  // sum over nothing (bias_op.cc:206-209 zero-fills)
+      OP_REQUIRES_OK(ctx, FromAbi(b200_memset_async(db->raw_data(), 0, db->TotalBytes(),
+                                                    GetCudaStream(ctx)),
+                                  "BiasAddGrad"));
+      return;
+    }
+    const size_t ws = b200_relu_grad_bias_grad_workspace_bytes(AbiType<T>::v, rows, channels);
+    Tensor scratch;
+    if (ws > 0)
+      OP_REQUIRES_OK(ctx, ctx->allocate_temp(DT_UINT8, TensorShape({static_cast<int64>(ws)}), &scratch));
+    OP_REQUIRES_OK(ctx, FromAbi(b200_relu_grad_bias_grad(
+                                    AbiType<T>::v, g.raw_data(), a.raw_data(), out->raw_data(),
+                                    db->raw_data(), rows, channels,
+                                    ws ? scratch.raw_data() : nullptr, ws, GetCudaStream(ctx)),
+                                "_ReluGradBiasAddGrad"));
+  }
+};
+
 #define REGISTER_GPU(T)                                                                      \
+  REGISTER_KERNEL_BUILDER(Name("_ReluGradBiasAddGrad").Device(DEVICE_GPU).TypeConstraint<T>("T"), \
+                          ReluGradBiasAddGradOp<T>);                                         \
   REGISTER_KERNEL_BUILDER(Name("Relu").Device(DEVICE_GPU).TypeConstraint<T>("T"), ReluOp<T>); \
   REGISTER_KERNEL_BUILDER(Name("ReluGrad").Device(DEVICE_GPU).TypeConstraint<T>("T"),        \
                           ReluGradOp<T>);

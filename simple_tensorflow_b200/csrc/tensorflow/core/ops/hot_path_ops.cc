@@ -112,6 +112,12 @@ REGISTER_OP("Mean")
     .Attr("keep_dims: bool = false").Attr("T: numbertype")
     .Attr("Tidx: {int32, int64} = DT_INT32");
 
+// Executor-internal (DirectSession::FuseReluGradBiasGrad): ReluGrad followed by an NHWC BiasAddGrad
+// of its result, one pass over the tensor.
+REGISTER_OP("_ReluGradBiasAddGrad")
+    .Input("gradients: T").Input("features: T").Output("backprops: T").Output("bias_grad: T")
+    .Attr("T: {float, bfloat16}");
+
 // math_ops.cc:1330-1343 ("Sum": same signature as "Mean")
 REGISTER_OP("Sum")
     .Input("input: T").Input("reduction_indices: Tidx").Output("output: T")

@@ -546,3 +546,26 @@ def test_add_n_more_than_eight_inputs(rng):
     for a in xs[1:]:
         ref = ref + a          # left to right in fp32, like the kernel
     np.testing.assert_array_equal(got, ref)
+
+
+@pytest.mark.parametrize("relu", [False, True])
+def test_fused_matmul_with_few_tiles_splits_k(oracle, rng, relu):
+    # LeNet fc1's shape (512 x 1024 x 3136): 8 pair tiles for 74 pairs -> the fused MatMul+BiasAdd
+    # (+Relu) splits K and its tail rides on the ordered reduction pass; same result as op by op
+    x = rng.uniform(-1, 1, (512, 3136)).astype(np.float32)
+    w = (rng.randn(3136, 1024) / 56.0).astype(np.float32)
+    b = rng.uniform(-0.5, 0.5, 1024).astype(np.float32)
+    tf.reset_default_graph()
+    xp = tf.placeholder(tf.float32, [512, 3136], "x")
+    y = tf.bias_add(tf.matmul(xp, tf.constant(w)), tf.constant(b))
+    if relu:
+        y = tf.relu(y)
+    with client.Session(tf.get_default_graph()) as sess:
+        got = sess.run(y, {xp: x})
+        assert sess.last_run_stats()["kernels_launched"] == 2  # split GEMM + reduction with the tail
+    ref = oracle.bias_add(oracle.matmul(x, w), b)
+    if relu:
+        ref = oracle.relu(ref)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-3
+    if relu:
+        assert got.min() >= 0.0
