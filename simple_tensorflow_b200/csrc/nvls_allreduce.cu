@@ -24,6 +24,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <cuda_bf16.h>
+
 #include "b200_internal.h"
 
 namespace b200 {
@@ -181,8 +183,31 @@ __device__ __forceinline__ void nvls_barrier(uint32_t* mc_flags, const uint32_t*
   __syncthreads();
 }
 
+// 16 bytes of bf16 (8 values) reduced in the switch with fp32 accumulation
+__device__ __forceinline__ uint4 multimem_ld_reduce_add_bf16(const void* mc_addr) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc_addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_b32x4(void* mc_addr, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc_addr),
+               "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+               "f"(__uint_as_float(v.w))
+               : "memory");
+}
+__device__ __forceinline__ uint32_t scale_bf16x2(uint32_t w, float scale) {
+  const float lo = __uint_as_float(w << 16) * scale, hi = __uint_as_float(w & 0xFFFF0000u) * scale;
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// data: 16-byte vectors (4 x fp32 or 8 x bf16) of the window, in place
+template <bool kBf16>
 __global__ void __launch_bounds__(kNvlsThreads, 4)
-nvls_all_reduce_kernel(float* __restrict__ mc_data, uint32_t* mc_flags, const uint32_t* uc_flags,
+nvls_all_reduce_kernel(char* __restrict__ mc_data, uint32_t* mc_flags, const uint32_t* uc_flags,
                        long long nvec, long long slice_vecs, int rank, float scale,
                        uint32_t target_begin, uint32_t target_end) {
   pdl_prologue();
@@ -194,21 +219,36 @@ nvls_all_reduce_kernel(float* __restrict__ mc_data, uint32_t* mc_flags, const ui
   constexpr int U = 4;  // reductions in flight per thread (a switch round trip each)
   for (long long v0 = lo + (long long)blockIdx.x * kNvlsThreads + threadIdx.x; v0 < hi;
        v0 += stride * U) {
-    float4 x[U];
+    uint4 x[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long v = v0 + u * stride;
-      if (v < hi) x[u] = multimem_ld_reduce_add(mc_data + 4 * v);
+      if (v < hi) {
+        if (kBf16) {
+          x[u] = multimem_ld_reduce_add_bf16(mc_data + 16 * v);
+        } else {
+          const float4 f = multimem_ld_reduce_add(reinterpret_cast<const float*>(mc_data + 16 * v));
+          x[u] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.y), __float_as_uint(f.z),
+                            __float_as_uint(f.w));
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long v = v0 + u * stride;
       if (v < hi) {
-        x[u].x *= scale;
-        x[u].y *= scale;
-        x[u].z *= scale;
-        x[u].w *= scale;
-        multimem_st(mc_data + 4 * v, x[u]);
+        if (kBf16) {
+          x[u].x = scale_bf16x2(x[u].x, scale);
+          x[u].y = scale_bf16x2(x[u].y, scale);
+          x[u].z = scale_bf16x2(x[u].z, scale);
+          x[u].w = scale_bf16x2(x[u].w, scale);
+        } else {
+          x[u].x = __float_as_uint(__uint_as_float(x[u].x) * scale);
+          x[u].y = __float_as_uint(__uint_as_float(x[u].y) * scale);
+          x[u].z = __float_as_uint(__uint_as_float(x[u].z) * scale);
+          x[u].w = __float_as_uint(__uint_as_float(x[u].w) * scale);
+        }
+        multimem_st_b32x4(mc_data + 16 * v, x[u]);
       }
     }
   }
@@ -421,10 +461,11 @@ void* nvls_arena_data(NvlsArena* a) {
 }
 size_t nvls_arena_bytes(NvlsArena* a) { return a->data_bytes; }
 
-int nvls_all_reduce(NvlsArena* a, size_t offset_bytes, long long count, int average, int max_ctas,
-                    cudaStream_t stream) {
+int nvls_all_reduce(NvlsArena* a, int dtype, size_t offset_bytes, long long count, int average,
+                    int max_ctas, cudaStream_t stream) {
   if (count == 0) return B200_OK;
-  const long long nvec = (count + 3) / 4;  // the arena is padded to 256 bytes: whole vectors
+  const int per_vec = dtype == B200_DT_FLOAT ? 4 : 8;
+  const long long nvec = (count + per_vec - 1) / per_vec;  // the arena is padded to 256 bytes
   const long long slice = (nvec + a->nranks - 1) / a->nranks;
   int ctas = max_ctas > 0 ? max_ctas : 96;
   if (ctas > kNvlsMaxCtas) ctas = kNvlsMaxCtas;
@@ -438,10 +479,17 @@ int nvls_all_reduce(NvlsArena* a, size_t offset_bytes, long long count, int aver
   const uint32_t target_end = (a->barriers + 2) * (uint32_t)a->nranks;
   a->barriers += 2;
   const float scale = average ? 1.0f / (float)a->nranks : 1.0f;
-  cudaError_t e = launch_pdl(nvls_all_reduce_kernel, dim3(ctas), dim3(kNvlsThreads), 0, stream,
-                             reinterpret_cast<float*>(mc + kNvlsHeaderBytes + offset_bytes),
-                             reinterpret_cast<uint32_t*>(mc), reinterpret_cast<const uint32_t*>(uc),
-                             nvec, slice, a->rank, scale, target_begin, target_end);
+  cudaError_t e;
+  if (dtype == B200_DT_FLOAT)
+    e = launch_pdl(nvls_all_reduce_kernel<false>, dim3(ctas), dim3(kNvlsThreads), 0, stream,
+                   mc + kNvlsHeaderBytes + offset_bytes, reinterpret_cast<uint32_t*>(mc),
+                   reinterpret_cast<const uint32_t*>(uc), nvec, slice, a->rank, scale,
+                   target_begin, target_end);
+  else
+    e = launch_pdl(nvls_all_reduce_kernel<true>, dim3(ctas), dim3(kNvlsThreads), 0, stream,
+                   mc + kNvlsHeaderBytes + offset_bytes, reinterpret_cast<uint32_t*>(mc),
+                   reinterpret_cast<const uint32_t*>(uc), nvec, slice, a->rank, scale,
+                   target_begin, target_end);
   if (e != cudaSuccess) {
     set_last_error("nvls_all_reduce launch: %s", cudaGetErrorString(e));
     cudaGetLastError();

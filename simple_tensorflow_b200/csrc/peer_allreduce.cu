@@ -25,8 +25,8 @@ int nvls_arena_create(void* nccl_comm, int rank, int nranks, size_t data_bytes, 
 void nvls_arena_destroy(NvlsArena* a);
 void* nvls_arena_data(NvlsArena* a);
 size_t nvls_arena_bytes(NvlsArena* a);
-int nvls_all_reduce(NvlsArena* a, size_t offset_bytes, long long count, int average, int max_ctas,
-                    cudaStream_t stream);
+int nvls_all_reduce(NvlsArena* a, int dtype, size_t offset_bytes, long long count, int average,
+                    int max_ctas, cudaStream_t stream);
 namespace {
 
 constexpr int kMaxRanks = 8;
@@ -355,14 +355,18 @@ size_t b200_peer_arena_bytes(void* arena) {
 int b200_peer_all_reduce(void* arena, int dtype, size_t offset_bytes, int64_t count, int average,
                          int max_ctas, void* stream) {
   PeerArena* a = static_cast<PeerArena*>(arena);
-  if (!a || dtype != B200_DT_FLOAT || count < 0 || offset_bytes % 16 != 0 ||
-      offset_bytes + (size_t)count * 4 > a->data_bytes) {
-    set_last_error("b200_peer_all_reduce: bad arguments (fp32 only, 16-byte aligned offset, "
-                   "range inside the arena)");
+  // fp32 on both backends; bfloat16 only through the switch (multimem.ld_reduce accumulates in fp32)
+  const bool dtype_ok = dtype == B200_DT_FLOAT || (a && a->nvls && dtype == B200_DT_BFLOAT16);
+  const size_t es = dtype == B200_DT_FLOAT ? 4 : 2;
+  if (!a || !dtype_ok || count < 0 || offset_bytes % 16 != 0 ||
+      offset_bytes + (size_t)count * es > a->data_bytes) {
+    set_last_error("b200_peer_all_reduce: bad arguments (fp32, or bf16 on the NVLS backend; "
+                   "16-byte aligned offset, range inside the arena)");
     return B200_INVALID_ARGUMENT;
   }
   if (count == 0) return B200_OK;
-  if (a->nvls) return nvls_all_reduce(a->nvls, offset_bytes, count, average, max_ctas, as_stream(stream));
+  if (a->nvls)
+    return nvls_all_reduce(a->nvls, dtype, offset_bytes, count, average, max_ctas, as_stream(stream));
   const int nr = a->table.nranks;
   const long long nvec = (count + 3) / 4;  // the arena is padded to 256 bytes: whole vectors
   const long long slice = (nvec + nr - 1) / nr;

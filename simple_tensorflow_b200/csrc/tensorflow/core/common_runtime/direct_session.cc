@@ -801,7 +801,10 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
         if (arena_root[a].buffer() == nullptr) {
           // replicas: carve the arena from the NVLink peer arena, so that its all-reduce is one
           // kernel of peer loads (b200_peer_all_reduce); otherwise (or when it is full) the BFC arena
-          void* peer = ga.dtype == DT_FLOAT ? device_->AllocatePeerArena(ga.total) : nullptr;
+          const bool peer_dtype =
+              ga.dtype == DT_FLOAT ||
+              (ga.dtype == DT_BFLOAT16 && std::strcmp(b200_peer_arena_backend(), "nvls") == 0);
+          void* peer = peer_dtype ? device_->AllocatePeerArena(ga.total) : nullptr;
           if (peer != nullptr) {
             TensorBuffer* wrap = new TensorBuffer(peer, ga.total);  // not owned
             arena_root[a] = Tensor(ga.dtype, TensorShape({static_cast<int64>(ga.total / esize)}), wrap);

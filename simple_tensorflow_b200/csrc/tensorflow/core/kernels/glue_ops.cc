@@ -522,7 +522,10 @@ class B200AllReduceNOp : public OpKernel {
       void* base = ctx->input(0).raw_data();
       const int64 total = static_cast<int64>(span / sizeof(T));  // padding included: inside the arena
       const long long peer_offset = dev->PeerArenaOffset(base);
-      if (peer_offset >= 0 && average && std::is_same<T, float>::value) {
+      // fp32 on either peer backend; bfloat16 when the arena lives in NVSwitch multicast memory
+      const bool peer_dtype = std::is_same<T, float>::value ||
+                              std::strcmp(b200_peer_arena_backend(), "nvls") == 0;
+      if (peer_offset >= 0 && average && peer_dtype) {
         // the arena lives in NVLink peer memory: one kernel of peer loads instead of NCCL (its
         // CTAs fit beside resident GEMM CTAs, so it also runs well on the collective stream)
         static const int ctas = [] {

@@ -373,6 +373,12 @@ def check_parity(w, B, sess, o, world=1, rank=0, seeds=None, tol=1e-2):
     sess.run([B.fed[0], B.fed[1]], feed)
     got_w = {n: w.to_f32(a) for n, a in zip(B.V, sess.run([v.ref for v in B.V.values()]))}
 
+    if rank != 0 and world > 1:
+        # The GPU runs above are collective (every rank takes part); the CPU oracle of the global
+        # batch is evaluated on rank 0 only -- N ranks x all host threads each would oversubscribe
+        # the box's CPU quota N-fold (8 ranks: minutes instead of seconds).
+        return None
+
     def global_reference(oracle_like):
         loss_local, grads = None, None
         for r, seed in enumerate(seeds):
