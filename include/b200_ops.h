@@ -50,7 +50,8 @@ enum {
   B200_DT_FLOAT = 1,
   B200_DT_INT32 = 3,
   B200_DT_INT64 = 9,
-  B200_DT_BFLOAT16 = 14
+  B200_DT_BFLOAT16 = 14,
+  B200_DT_HALF = 19      /* IEEE fp16: b200_cast only; the ops take it through fp32 (half_ops.cc) */
 };
 
 /* ------------------------------------------------------------------ library / device */
@@ -89,7 +90,10 @@ B200_API int b200_stream_create(void** stream);
 B200_API int b200_stream_create_with_priority(void** stream, int high_priority);
 B200_API int b200_stream_destroy(void* stream);
 B200_API int b200_stream_synchronize(void* stream);          /* BlockHostUntilDone */
-B200_API int b200_stream_wait_event(void* stream, void* event); /* ThenWaitFor */
+B200_API int b200_stream_wait_event(void* stream, void* event);
+/* Run fn(arg) on a driver thread once everything enqueued on `stream` so far has completed
+ * (Stream::ThenDoHostCallback, stream_executor/stream.h:1624).  fn must not call CUDA. */
+B200_API int b200_stream_add_host_callback(void* stream, void (*fn)(void*), void* arg); /* ThenWaitFor */
 B200_API int b200_event_create(void** event);
 B200_API int b200_event_destroy(void* event);
 B200_API int b200_event_record(void* event, void* stream);   /* ThenRecordEvent */

@@ -46,6 +46,7 @@ SIGNATURES = {
     "b200_stream_destroy": (c_int, [c_void_p]),
     "b200_stream_synchronize": (c_int, [c_void_p]),
     "b200_stream_wait_event": (c_int, [c_void_p, c_void_p]),
+    "b200_stream_add_host_callback": (c_int, [c_void_p, c_void_p, c_void_p]),
     "b200_event_create": (c_int, [ctypes.POINTER(c_void_p)]),
     "b200_event_destroy": (c_int, [c_void_p]),
     "b200_event_record": (c_int, [c_void_p, c_void_p]),

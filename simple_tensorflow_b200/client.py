@@ -18,11 +18,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 FRAMEWORK_PATH = os.path.join(_HERE, "lib", "libb200tf_framework.so")
 
 # TF_DataType <-> numpy.  bfloat16 has no numpy dtype: it travels as uint16 bit patterns.
-TF_FLOAT, TF_INT32, TF_INT64, TF_BFLOAT16 = 1, 3, 9, 14
-_NP_OF = {TF_FLOAT: np.float32, TF_INT32: np.int32, TF_INT64: np.int64, TF_BFLOAT16: np.uint16}
+TF_FLOAT, TF_INT32, TF_INT64, TF_BFLOAT16, TF_HALF = 1, 3, 9, 14, 19
+_NP_OF = {TF_FLOAT: np.float32, TF_INT32: np.int32, TF_INT64: np.int64, TF_BFLOAT16: np.uint16,
+          TF_HALF: np.float16}
 _TF_OF = {np.dtype(np.float32): TF_FLOAT, np.dtype(np.int32): TF_INT32,
-          np.dtype(np.int64): TF_INT64}
-float32, int32, int64, bfloat16 = TF_FLOAT, TF_INT32, TF_INT64, TF_BFLOAT16
+          np.dtype(np.int64): TF_INT64, np.dtype(np.float16): TF_HALF}
+float32, int32, int64, bfloat16, float16 = TF_FLOAT, TF_INT32, TF_INT64, TF_BFLOAT16, TF_HALF
 
 c_void_p, c_int, c_int64, c_size_t, c_char_p = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64,
                                                  ctypes.c_size_t, ctypes.c_char_p)

@@ -10,6 +10,7 @@
 //   ApplyGradientDescent training_ops_gpu.cu.cc / training_ops.cc:410-412
 //   AddN      aggregate_ops_gpu.cu.cc / aggregate_ops.cc:153-176
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "b200_internal.h"
 
@@ -268,6 +269,14 @@ struct CastOne<float, uint16_t> {  // float -> bfloat16: keep the upper 16 bits 
 template <>
 struct CastOne<uint16_t, float> {  // bfloat16 -> float (bfloat16.cc:33-50)
   __device__ static float run(uint16_t v) { return __uint_as_float(((uint32_t)v) << 16); }
+};
+template <>
+struct CastOne<float, __half> {  // float -> half: round to nearest even (Eigen::half, cast_op.h)
+  __device__ static __half run(float v) { return __float2half_rn(v); }
+};
+template <>
+struct CastOne<__half, float> {
+  __device__ static float run(__half v) { return __half2float(v); }
 };
 template <typename S, typename D>
 struct CastOne {
@@ -661,7 +670,8 @@ int b200_cast(int src_dtype, int dst_dtype, const void* in, void* out, int64_t n
   if (rc) return rc;
   cudaStream_t s = as_stream(stream);
   if (src_dtype == dst_dtype) {  // CastOpBase::Compute aliases the input (cast_op.cc:63-66)
-    size_t es = src_dtype == B200_DT_BFLOAT16 ? 2 : (src_dtype == B200_DT_INT64 ? 8 : 4);
+    size_t es = (src_dtype == B200_DT_BFLOAT16 || src_dtype == B200_DT_HALF)
+                    ? 2 : (src_dtype == B200_DT_INT64 ? 8 : 4);
     if (in != out) return b200_memcpy_d2d_async(out, in, (size_t)n * es, stream);
     return B200_OK;
   }
@@ -684,6 +694,8 @@ int b200_cast(int src_dtype, int dst_dtype, const void* in, void* out, int64_t n
     }
     return launch_cast<uint16_t, float>(in, out, n, s);
   }
+  if (PAIR(B200_DT_FLOAT, B200_DT_HALF)) return launch_cast<float, __half>(in, out, n, s);
+  if (PAIR(B200_DT_HALF, B200_DT_FLOAT)) return launch_cast<__half, float>(in, out, n, s);
   if (PAIR(B200_DT_FLOAT, B200_DT_INT32)) return launch_cast<float, int32_t>(in, out, n, s);
   if (PAIR(B200_DT_FLOAT, B200_DT_INT64)) return launch_cast<float, int64_t>(in, out, n, s);
   if (PAIR(B200_DT_INT32, B200_DT_FLOAT)) return launch_cast<int32_t, float>(in, out, n, s);

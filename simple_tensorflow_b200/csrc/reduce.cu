@@ -213,7 +213,12 @@ static BiasGradPlan plan_bias_grad(int dtype, long long rows, long long channels
   // Enough CTAs to keep several MB of loads in flight (HBM latency x bandwidth) without making the
   // ordered second stage long (it reads one partial row per chunk): ~4 CTAs per SM, each
   // thread issuing one batch of four independent 16-byte loads.
-  long long want = (4LL * 148 + p.col_tiles - 1) / p.col_tiles;
+  static const int ctas_per_sm = [] {  // tuning knob (tools/op_bench.py sweeps it)
+    const char* v = getenv("B200TF_BIAS_GRAD_CTAS_PER_SM");
+    const int n = v ? atoi(v) : 0;
+    return n > 0 ? n : 4;
+  }();
+  long long want = ((long long)ctas_per_sm * sm_count() + p.col_tiles - 1) / p.col_tiles;
   long long max_chunks = (rows + 8LL * fold * 4 - 1) / (8LL * fold * 4);  // >= 4 rows per thread
   if (max_chunks < 1) max_chunks = 1;
   if (want > max_chunks) want = max_chunks;

@@ -280,6 +280,14 @@ int b200_stream_create(void** stream) {
   *stream = s;
   return B200_OK;
 }
+int b200_stream_add_host_callback(void* stream, void (*fn)(void*), void* arg) {
+  if (fn == nullptr) {
+    set_last_error("b200_stream_add_host_callback: null callback");
+    return B200_INVALID_ARGUMENT;
+  }
+  CUDA_RC(cudaLaunchHostFunc(as_stream(stream), fn, arg), "b200_stream_add_host_callback");
+  return B200_OK;
+}
 int b200_stream_create_with_priority(void** stream, int high_priority) {
   int least = 0, greatest = 0;
   CUDA_RC(cudaDeviceGetStreamPriorityRange(&least, &greatest), "b200_stream_create_with_priority");

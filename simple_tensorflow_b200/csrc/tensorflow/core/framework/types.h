@@ -49,6 +49,13 @@ struct bfloat16 {
   uint16_t value;
 };
 
+// IEEE binary16 storage (the reference's Eigen::half, framework/numeric_types.h): the GPU ops take
+// it through fp32 (core/kernels/half_ops.cc); the struct only carries the bits.
+struct half {
+  half() : value(0) {}
+  uint16_t value;
+};
+
 inline size_t DataTypeSize(DataType dt) {
   switch (dt) {
     case DT_FLOAT: case DT_INT32: return 4;
@@ -99,6 +106,7 @@ B200TF_MATCH_TYPE(double, DT_DOUBLE);
 B200TF_MATCH_TYPE(int32, DT_INT32);
 B200TF_MATCH_TYPE(int64, DT_INT64);
 B200TF_MATCH_TYPE(bfloat16, DT_BFLOAT16);
+B200TF_MATCH_TYPE(half, DT_HALF);
 B200TF_MATCH_TYPE(bool, DT_BOOL);
 B200TF_MATCH_TYPE(uint8, DT_UINT8);
 #undef B200TF_MATCH_TYPE

@@ -15,7 +15,9 @@ class GpuCastOp : public OpKernel {
     auto ok = [](DataType t) {
       return t == DT_FLOAT || t == DT_BFLOAT16 || t == DT_INT32 || t == DT_INT64;
     };
-    OP_REQUIRES(ctx, ok(src_dtype_) && ok(dst_dtype_),
+    const bool half_pair = (src_dtype_ == DT_HALF && (dst_dtype_ == DT_FLOAT || dst_dtype_ == DT_HALF)) ||
+                           (dst_dtype_ == DT_HALF && src_dtype_ == DT_FLOAT);
+    OP_REQUIRES(ctx, half_pair || (ok(src_dtype_) && ok(dst_dtype_)),
                 errors::Unimplemented("Cast ", DataTypeString(src_dtype_), " to ",
                                       DataTypeString(dst_dtype_), " is not supported"));
   }

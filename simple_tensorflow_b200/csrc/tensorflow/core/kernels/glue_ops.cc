@@ -45,6 +45,7 @@ class ConstantOp : public OpKernel {
 REGISTER_KERNEL_BUILDER(Name("Const").Device(DEVICE_GPU).TypeConstraint<float>("dtype"), ConstantOp);
 REGISTER_KERNEL_BUILDER(Name("Const").Device(DEVICE_GPU).TypeConstraint<bfloat16>("dtype"),
                         ConstantOp);
+REGISTER_KERNEL_BUILDER(Name("Const").Device(DEVICE_GPU).TypeConstraint<half>("dtype"), ConstantOp);
 REGISTER_KERNEL_BUILDER(Name("Const").Device(DEVICE_GPU).TypeConstraint<int64>("dtype"), ConstantOp);
 REGISTER_KERNEL_BUILDER(
     Name("Const").Device(DEVICE_GPU).HostMemory("output").TypeConstraint<int32>("dtype"),

@@ -27,6 +27,7 @@ inline Status FromAbi(int rc, const char* what) {
 template <typename T> struct AbiType;
 template <> struct AbiType<float> { static constexpr int v = B200_DT_FLOAT; };
 template <> struct AbiType<bfloat16> { static constexpr int v = B200_DT_BFLOAT16; };
+template <> struct AbiType<half> { static constexpr int v = B200_DT_HALF; };
 template <> struct AbiType<int32> { static constexpr int v = B200_DT_INT32; };
 template <> struct AbiType<int64> { static constexpr int v = B200_DT_INT64; };
 

@@ -7,6 +7,7 @@
 
 #include <cstddef>
 #include <cstdint>
+#include <functional>
 
 #include "b200_ops.h"
 
@@ -75,6 +76,26 @@ class Stream {
                         uint64_t size) {
     return Latch(b200_memcpy_d2d_async(gpu_dst->opaque(), gpu_src.opaque(), size, handle_));
   }
+  // The reference's overload set (stream_executor/stream.h:1482-1529): direction from the types.
+  Stream& ThenMemcpy(void* host_dst, const DeviceMemoryBase& gpu_src, uint64_t size) {
+    return ThenMemcpyD2H(host_dst, gpu_src, size);
+  }
+  Stream& ThenMemcpy(DeviceMemoryBase* gpu_dst, const void* host_src, uint64_t size) {
+    return ThenMemcpyH2D(gpu_dst, host_src, size);
+  }
+  Stream& ThenMemcpy(DeviceMemoryBase* gpu_dst, const DeviceMemoryBase& gpu_src, uint64_t size) {
+    return ThenMemcpyD2D(gpu_dst, gpu_src, size);
+  }
+  // stream_executor/stream.h:1624: run `callback` on a driver thread once the work enqueued so
+  // far has completed (the callback must not call into the stream).
+  Stream& ThenDoHostCallback(std::function<void()> callback) {
+    auto* heap = new std::function<void()>(std::move(callback));
+    const int rc = b200_stream_add_host_callback(handle_, &Stream::RunHostCallback, heap);
+    if (rc != 0) delete heap;
+    return Latch(rc);
+  }
+  // (ThenLaunch has no counterpart: kernels are enqueued through the b200_* entry points, which
+  // take this stream's handle -- cuda_stream() -- as their last argument.)
   Stream& ThenMemZero(DeviceMemoryBase* location, uint64_t size) {
     return Latch(b200_memset_async(location->opaque(), 0, size, handle_));
   }
@@ -90,6 +111,11 @@ class Stream {
   }
 
  private:
+  static void RunHostCallback(void* arg) {
+    auto* fn = static_cast<std::function<void()>*>(arg);
+    (*fn)();
+    delete fn;
+  }
   Stream& Latch(int rc) {
     if (rc != 0) ok_ = false;
     return *this;

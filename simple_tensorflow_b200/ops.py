@@ -11,7 +11,8 @@ Shapes are tracked statically here (the C layer checks them again at run time).
 import numpy as np
 
 from . import client
-from .client import Graph, HostTensor, Operation, Output, Session, float32, int32, int64, bfloat16
+from .client import (Graph, HostTensor, Operation, Output, Session, float32, int32, int64, bfloat16,
+                     float16)
 
 _default_graph = None
 

@@ -99,7 +99,7 @@ def test_registries_hold_the_hot_path():
                  "ApplyGradientDescent", "AddN", "VariableV2", "Assign"]:
         assert name in ops_
     kernels = client.registered_kernels()
-    assert kernels.count("MatMul:GPU:") == 2  # float + bfloat16 registrations
+    assert kernels.count("MatMul:GPU:") == 3  # float + bfloat16 + half (fp32 adaptor) registrations
     assert all(k.split(":")[1] == "GPU" for k in kernels), "a CPU kernel would be a fallback"
 
 

@@ -569,3 +569,90 @@ def test_fused_matmul_with_few_tiles_splits_k(oracle, rng, relu):
     assert np.abs(got - ref).max() / np.abs(ref).max() < 3e-3
     if relu:
         assert got.min() >= 0.0
+
+
+def _h(a):
+    """fp32 values that survive a float -> half -> float round trip (the half parity inputs)."""
+    return np.asarray(a, np.float32).astype(np.float16)
+
+
+def test_half_hot_path_ops_vs_oracle(oracle, rng):
+    # DT_HALF for the ops the reference registers half GPU kernels for (matmul_op.cc:301-332,
+    # conv_ops.cc:758-763, maxpooling_op.cc:646-651, bias_op.cc:242-299): oracle on the fp16-rounded
+    # inputs, reference tolerance for half 1e-3 (python/framework/test_util.py:515-523) relative to
+    # the output scale
+    x = _h(rng.uniform(-1, 1, (64, 96)))
+    w = _h(rng.randn(96, 48) / 10.0)
+    b = _h(rng.uniform(-0.5, 0.5, 48))
+    img = _h(rng.uniform(-1, 1, (3, 12, 12, 32)))
+    flt = _h(rng.randn(3, 3, 32, 32) / 17.0)
+    cb = _h(rng.uniform(-0.5, 0.5, 32))
+    tf.reset_default_graph()
+    xp = tf.placeholder(tf.float16, [64, 96], "x")
+    ip = tf.placeholder(tf.float16, [3, 12, 12, 32], "img")
+    dense = tf.relu(tf.bias_add(tf.matmul(xp, tf.constant(w, tf.float16)), tf.constant(b, tf.float16)))
+    conv = tf.bias_add(tf.conv2d(ip, tf.constant(flt, tf.float16), [1, 1, 1, 1], "SAME"),
+                       tf.constant(cb, tf.float16))
+    pool = tf.max_pool(conv, [1, 2, 2, 1], [1, 2, 2, 1], "VALID")
+    sm = tf.softmax(tf.matmul(xp, tf.constant(w, tf.float16)))
+    back = tf.cast(dense, tf.float32)
+    with client.Session(tf.get_default_graph()) as sess:
+        got_dense, got_conv, got_pool, got_sm, got_back = sess.run(
+            [dense, conv, pool, sm, back], {xp: x, ip: img})
+    assert got_dense.dtype == np.float16 and got_pool.dtype == np.float16
+    f = lambda a: np.asarray(a, np.float32)
+    ref_dense = oracle.relu(oracle.bias_add(oracle.matmul(f(x), f(w)), f(b)))
+    ref_conv = oracle.bias_add(oracle.conv2d(f(img), f(flt), (1, 1), "SAME"), f(cb))
+    ref_pool = oracle.max_pool(_h(ref_conv).astype(np.float32), (2, 2), (2, 2), "VALID")
+    ref_sm = oracle.softmax(_h(oracle.matmul(f(x), f(w))).astype(np.float32))
+    for got, ref in ((got_dense, ref_dense), (got_conv, ref_conv), (got_sm, ref_sm)):
+        assert np.abs(f(got) - ref).max() <= 2e-3 * max(np.abs(ref).max(), 1.0)
+    # pooling a half tensor is exact given the same conv output bits
+    np.testing.assert_array_equal(got_pool, oracle.max_pool(f(got_conv), (2, 2), (2, 2), "VALID").astype(np.float16))
+    assert np.abs(f(got_pool) - ref_pool).max() <= 2e-3 * np.abs(ref_pool).max()
+    np.testing.assert_array_equal(got_back, f(got_dense))  # Cast half -> float is exact
+
+
+def test_half_conv_gradients_vs_oracle(oracle, rng):
+    x = _h(rng.uniform(-1, 1, (2, 10, 10, 32)))
+    flt = _h(rng.randn(3, 3, 32, 32) / 17.0)
+    dy = _h(rng.uniform(-1, 1, (2, 10, 10, 32)))
+    tf.reset_default_graph()
+    xp = tf.placeholder(tf.float16, list(x.shape), "x")
+    dp = tf.placeholder(tf.float16, list(dy.shape), "dy")
+    fc = tf.constant(flt, tf.float16)
+    g = tf.get_default_graph()
+    attrs = {"T": ("type", tf.float16), "strides": ("list(int)", [1, 1, 1, 1]),
+             "padding": ("string", "SAME"), "data_format": ("string", "NHWC")}
+    y = tf.conv2d(xp, fc, [1, 1, 1, 1], "SAME")
+    conv_op = y.op
+    dx, dw = tf._GRAD["Conv2D"](conv_op, dp)
+    with client.Session(g) as sess:
+        got_dx, got_dw = sess.run([dx, dw], {xp: x, dp: dy})
+    f = lambda a: np.asarray(a, np.float32)
+    ref_dx = oracle.conv2d_backprop_input(x.shape, f(flt), f(dy), (1, 1), "SAME")
+    ref_dw = oracle.conv2d_backprop_filter(f(x), flt.shape, f(dy), (1, 1), "SAME")
+    assert got_dx.dtype == np.float16 and got_dw.dtype == np.float16
+    assert np.abs(f(got_dx) - ref_dx).max() <= 2e-3 * np.abs(ref_dx).max()
+    assert np.abs(f(got_dw) - ref_dw).max() <= 2e-3 * np.abs(ref_dw).max()
+
+
+def test_stream_host_callback_runs_after_enqueued_work():
+    # Stream::ThenDoHostCallback (stream_executor/stream.h:1624) -> b200_stream_add_host_callback
+    import ctypes
+    from simple_tensorflow_b200 import _lib
+    L = _lib.load()
+    stream = ctypes.c_void_p()
+    assert L.b200_stream_create(ctypes.byref(stream)) == 0
+    dev = ctypes.c_void_p()
+    assert L.b200_malloc(ctypes.byref(dev), 1 << 20) == 0
+    seen = []
+    CB = ctypes.CFUNCTYPE(None, ctypes.c_void_p)
+    cb = CB(lambda arg: seen.append(arg))
+    assert L.b200_memset_async(dev, 0, 1 << 20, stream) == 0
+    assert L.b200_stream_add_host_callback(stream, ctypes.cast(cb, ctypes.c_void_p), ctypes.c_void_p(42)) == 0
+    assert L.b200_stream_synchronize(stream) == 0
+    assert seen == [42]
+    assert L.b200_stream_add_host_callback(stream, None, None) != 0  # null callback is rejected
+    L.b200_free(dev)
+    L.b200_stream_destroy(stream)
