@@ -71,6 +71,20 @@ B200_API void b200_collective_counts(uint64_t* peer_launches, uint64_t* nccl_cal
 /* Measurement hook for bench.py's roofline: between begin and end every tensor-core GEMM launch
  * (MatMul, BatchMatMul, the conv GEMMs) is bracketed by CUDA events on its own stream;
  * end() waits for them and returns the summed device time, launch count and 2*M*N*K FLOPs. */
+/* 1 while a b200_profile_begin/end pass is active (the executor then bypasses captured graphs, whose
+ * launches carry no per-launch events). */
+B200_API int b200_profile_active(void);
+/* Adds n to the launch counter: a replayed CUDA graph launches the kernels of the captured step
+ * without passing through the b200_* entry points that count them. */
+B200_API void b200_note_launches(uint64_t n);
+/* Step-level CUDA graphs (the executor captures one Session.Run plan, keyed like the reference's
+ * executor cache, direct_session.cc:918-936): capture everything the b200_* calls enqueue on
+ * `stream` between begin and end (relaxed mode), instantiate, replay.  end returns the executable
+ * graph or, on failure, B200_INTERNAL with the stream back in normal mode. */
+B200_API int b200_stream_begin_capture(void* stream);
+B200_API int b200_stream_end_capture(void* stream, void** graph_exec);
+B200_API int b200_graph_launch(void* graph_exec, void* stream);
+B200_API int b200_graph_destroy(void* graph_exec);
 B200_API int b200_profile_begin(void);
 B200_API int b200_profile_end(double* gemm_ms_total, uint64_t* gemm_launches,
                               double* gemm_flops_total);

@@ -36,6 +36,12 @@ SIGNATURES = {
     "b200_set_device": (c_int, [c_int]),
     "b200_launch_count": (ctypes.c_uint64, []),
     "b200_collective_counts": (None, [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
+    "b200_profile_active": (c_int, []),
+    "b200_note_launches": (None, [ctypes.c_uint64]),
+    "b200_stream_begin_capture": (c_int, [c_void_p]),
+    "b200_stream_end_capture": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
+    "b200_graph_launch": (c_int, [c_void_p, c_void_p]),
+    "b200_graph_destroy": (c_int, [c_void_p]),
     "b200_profile_begin": (c_int, []),
     "b200_profile_end": (c_int, [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64),
                                  ctypes.POINTER(ctypes.c_double)]),

@@ -234,7 +234,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
   uint64_t* feat_bar = bars + 2 * kStages + 4;    // [4 warps][kFeatBufs]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4 + 4 * kFeatBufs);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = uniform_warp_idx();  // provably warp-uniform: see the MMA issuer below
   const int lane = threadIdx.x & 31;
   const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0;
   const bool leader = cta_rank == 0;
@@ -280,7 +280,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
   else
     __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);  // warp-uniform value
   // Everything above overlapped the previous kernel's tail (programmatic dependent launch);
   // from here on this grid reads and writes global memory.
   if (threadIdx.x == 0) trace_mark(s, 1);
@@ -398,66 +398,73 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA,
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only when paired) =====================
-    if (lane == 0 && leader) {
+    // The WHOLE warp runs this loop and one elected lane issues each tcgen05 instruction
+    // (predication inside the asm block).  Issuing from an `if (lane == 0)` region made ptxas
+    // wrap every MMA in an ELECT + 5 x R2UR.BROADCAST waterfall loop: ~160 cycles of issue per
+    // MMA against the MMA's own 128 -- the main loop ran at the issue rate (profiles/r02_notes.md).
+    if (leader) {
       uint32_t stage = 0, phase = 0;
       uint32_t acc = 0, acc_phase = 0;
+      // MN-major tf32 must use the 32-byte-atom 128B swizzle: 4-row (512 B) K groups.
+      constexpr bool kMn32 = sizeof(TIn) == 4;
+      // descriptors of stage 0, k step 0: later ones differ only in the start-address field
+      const uint64_t adesc0 = kAMN ? make_smem_desc_sw128(smem_u32(smA), BK * kSwizzleBytes,
+                                                          kMn32 ? 512 : 1024, kMn32 ? 1 : 2)
+                                   : make_smem_desc_sw128(smem_u32(smA), 16, 1024);
+      const uint64_t bdesc0 = kBMN ? make_smem_desc_sw128(smem_u32(smB), BK * kSwizzleBytes,
+                                                          kMn32 ? 512 : 1024, kMn32 ? 1 : 2)
+                                   : make_smem_desc_sw128(smem_u32(smB), 16, 1024);
+      const uint32_t a_hi = (uint32_t)(adesc0 >> 32), b_hi = (uint32_t)(bdesc0 >> 32);
+      // K-major: advance 32 B inside the 128-B swizzle row; MN-major: advance kUmmaK rows.
+      constexpr uint32_t kAStep = (kAMN ? Tr::kUmmaK * kSwizzleBytes : Tr::kUmmaK * (int)sizeof(TIn)) >> 4;
+      constexpr uint32_t kBStep = (kBMN ? Tr::kUmmaK * kSwizzleBytes : Tr::kUmmaK * (int)sizeof(TIn)) >> 4;
       for (int work = unit; work < num_work; work += num_units) {
         const int split = work / num_tiles;
         const int kb0 = split * s.kb_per_split;
         const int kb1 = min(kb0 + s.kb_per_split, num_kb);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        __syncwarp();
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          __syncwarp();
           tc_fence_after();
-          if (kb == kb0 && work == unit) trace_mark(s, 3);
-          const uint32_t a_addr = smem_u32(smA + stage * kABytes);
-          const uint32_t b_addr = smem_u32(smB + stage * kBBytes);
+          if (lane == 0 && kb == kb0 && work == unit) trace_mark(s, 3);
+          const uint32_t a_lo0 = (uint32_t)adesc0 + ((stage * kABytes) >> 4);
+          const uint32_t b_lo0 = (uint32_t)bdesc0 + ((stage * kBBytes) >> 4);
 #pragma unroll
           for (int k = 0; k < BK / Tr::kUmmaK; ++k) {
-            // K-major: advance 32 B inside the 128-B swizzle row; MN-major: advance kUmmaK rows.
-            const uint32_t a_off = kAMN ? k * Tr::kUmmaK * kSwizzleBytes
-                                        : k * Tr::kUmmaK * (int)sizeof(TIn);
-            const uint32_t b_off = kBMN ? k * Tr::kUmmaK * kSwizzleBytes
-                                        : k * Tr::kUmmaK * (int)sizeof(TIn);
-            // MN-major tf32 must use the 32-byte-atom 128B swizzle: 4-row (512 B) K groups.
-            constexpr bool kMn32 = sizeof(TIn) == 4;
-            const uint64_t adesc = kAMN ? make_smem_desc_sw128(a_addr + a_off, BK * kSwizzleBytes,
-                                                               kMn32 ? 512 : 1024, kMn32 ? 1 : 2)
-                                        : make_smem_desc_sw128(a_addr + a_off, 16, 1024);
-            const uint64_t bdesc = kBMN ? make_smem_desc_sw128(b_addr + b_off, BK * kSwizzleBytes,
-                                                               kMn32 ? 512 : 1024, kMn32 ? 1 : 2)
-                                        : make_smem_desc_sw128(b_addr + b_off, 16, 1024);
             const uint32_t accum = ((kb - kb0) | k) != 0;
+            const uint32_t a_lo = a_lo0 + k * kAStep, b_lo = b_lo0 + k * kBStep;
             if (kCtas == 2) {
               if (sizeof(TIn) == 4)
-                umma_tf32_2cta(d_tmem, adesc, bdesc, kIdesc, accum);
+                umma_tf32_elect_lohi_2cta(d_tmem, a_lo, a_hi, b_lo, b_hi, kIdesc, accum);
               else
-                umma_f16_2cta(d_tmem, adesc, bdesc, kIdesc, accum);
+                umma_f16_elect_lohi_2cta(d_tmem, a_lo, a_hi, b_lo, b_hi, kIdesc, accum);
             } else {
               if (sizeof(TIn) == 4)
-                umma_tf32(d_tmem, adesc, bdesc, kIdesc, accum);
+                umma_tf32_elect_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, kIdesc, accum);
               else
-                umma_f16(d_tmem, adesc, bdesc, kIdesc, accum);
+                umma_f16_elect_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, kIdesc, accum);
             }
           }
           // frees the smem slot (in both CTAs) once these MMAs retire
           if (kCtas == 2)
-            umma_commit_2cta(&empty_bar[stage]);
+            umma_commit_elect_2cta(&empty_bar[stage]);
           else
-            umma_commit(&empty_bar[stage]);
+            umma_commit_elect(&empty_bar[stage]);
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
         }
         // accumulator ready for the epilogue warps (of both CTAs)
-        if (work == unit) trace_mark(s, 4);
+        if (lane == 0 && work == unit) trace_mark(s, 4);
         if (kCtas == 2)
-          umma_commit_2cta(&tfull_bar[acc]);
+          umma_commit_elect_2cta(&tfull_bar[acc]);
         else
-          umma_commit(&tfull_bar[acc]);
+          umma_commit_elect(&tfull_bar[acc]);
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;

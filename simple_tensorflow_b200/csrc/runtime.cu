@@ -242,6 +242,45 @@ int b200_set_matmul_precision(int mode) {
 }
 int b200_get_matmul_precision(void) { return g_matmul_precision.load(); }
 
+int b200_profile_active(void) { return g_prof_on.load() ? 1 : 0; }
+void b200_note_launches(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int b200_stream_begin_capture(void* stream) {
+  CUDA_RC(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeRelaxed),
+          "b200_stream_begin_capture");
+  return B200_OK;
+}
+int b200_stream_end_capture(void* stream, void** graph_exec) {
+  *graph_exec = nullptr;
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(as_stream(stream), &graph);
+  if (e != cudaSuccess || graph == nullptr) {
+    set_last_error("b200_stream_end_capture: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return B200_INTERNAL;
+  }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    set_last_error("cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    cudaGetLastError();
+    return B200_INTERNAL;
+  }
+  *graph_exec = exec;
+  return B200_OK;
+}
+int b200_graph_launch(void* graph_exec, void* stream) {
+  CUDA_RC(cudaGraphLaunch(static_cast<cudaGraphExec_t>(graph_exec), as_stream(stream)),
+          "b200_graph_launch");
+  return B200_OK;
+}
+int b200_graph_destroy(void* graph_exec) {
+  if (graph_exec) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(graph_exec));
+  cudaGetLastError();
+  return B200_OK;
+}
+
 int b200_profile_begin(void) {
   std::lock_guard<std::mutex> l(g_prof.mu);
   g_prof.starts.clear();

@@ -30,6 +30,7 @@ DirectSession::DirectSession(const SessionOptions& options) : options_(options) 
 
 DirectSession::~DirectSession() {
   if (device_) device_->Sync();
+  if (device_) DropAllGraphs();  // graphs and the memory they pin go before the plans
   executors_.clear();
   nodes_.clear();  // kernels (and the variables they own) go before the device's allocator
 }
@@ -670,9 +671,134 @@ Status DirectSession::Run(const std::vector<std::pair<std::string, Tensor>>& inp
   return s;
 }
 
+static Status FromAbiStatus(int rc, const char* what) {
+  if (rc == 0) return Status::OK();
+  return Status(static_cast<error::Code>(rc), strings::StrCat(what, ": ", b200_last_error()));
+}
+
+// ---------------------------------------------------------------- step-level CUDA graphs
+// A plan is captured when nothing in it needs the host between its first and last launch: no
+// feeds (their buffers change from run to run), a single replica (the peer all-reduce kernels carry
+// a per-call epoch), every kernel on the compute stream, and no input that must be moved between
+// host and device memory mid-plan.  B200TF_CUDA_GRAPH=0 switches it off.
+bool DirectSession::GraphEligible(ExecutorsAndKeys* ek, size_t num_feeds) {
+  if (ek->graph_state != 0) return ek->graph_state > 0;
+  ek->graph_state = -1;
+  for (const PlanNode& pn : ek->order)
+    if (pn.item->def.op == "Assign") ek->has_assign = true;
+  if (ek->has_assign) return false;  // an Assign may replace a buffer other plans have captured
+  const char* env = getenv("B200TF_CUDA_GRAPH");
+  if (env != nullptr && std::strcmp(env, "0") == 0) return false;
+  if (num_feeds != 0 || device_->num_replicas() > 1 || ek->order.empty()) return false;
+  // producer memory space of every entry
+  std::vector<int> entry_host(ek->num_entries, 0);
+  for (const PlanNode& pn : ek->order) {
+    if (pn.collective >= 0) return false;
+    for (int o = 0; o < pn.item->kernel->num_outputs(); ++o)
+      entry_host[pn.out_entry(o)] = pn.item->kernel->output_memory_types()[o] == HOST_MEMORY;
+  }
+  for (const PlanNode& pn : ek->order) {
+    for (size_t i = 0; i < pn.inputs.size(); ++i) {
+      const InputSource& src = pn.inputs[i];
+      if (src.feed >= 0) return false;
+      const bool want_host = pn.item->kernel->input_memory_types()[i] == HOST_MEMORY;
+      if (want_host != (entry_host[entry_index_of(ek, src.id)] != 0)) return false;
+    }
+  }
+  ek->graph_state = 1;
+  return true;
+}
+
+void DirectSession::DropGraph(ExecutorsAndKeys* ek) {
+  if (ek->graph_exec != nullptr) {
+    device_->Sync();
+    b200_graph_destroy(ek->graph_exec);
+    ek->graph_exec = nullptr;
+  }
+  ek->graph_fetches.clear();
+  ek->graph_keepalive.clear();
+  Allocator* a = device_->GetAllocator(AllocatorAttributes());
+  for (void* p : ek->graph_pinned) a->DeallocateRaw(p);
+  ek->graph_pinned.clear();
+  if (ek->graph_state == 2) {
+    ek->graph_state = 1;
+    ek->warm_runs = 0;
+  }
+}
+
+void DirectSession::DropAllGraphs() {
+  for (auto& kv : executors_) DropGraph(kv.second.get());
+}
+
+Status DirectSession::ReplayGraph(ExecutorsAndKeys* ek, std::vector<Tensor>* outputs) {
+  gpu::Stream* compute = device_->compute_stream();
+  TF_RETURN_IF_ERROR(FromAbiStatus(b200_graph_launch(ek->graph_exec, compute->cuda_stream()),
+                                   "cudaGraphLaunch"));
+  b200_note_launches(static_cast<uint64_t>(ek->graph_launches));
+  stats_.nodes_executed += static_cast<long long>(ek->order.size());
+  outputs->clear();
+  outputs->resize(ek->graph_fetches.size());
+  for (size_t i = 0; i < ek->graph_fetches.size(); ++i) {
+    const ExecutorsAndKeys::CapturedFetch& f = ek->graph_fetches[i];
+    Tensor t = f.value;
+    if (f.ref != nullptr) {
+      std::lock_guard<std::mutex> rl(*f.ref_mu);
+      t = *f.ref;
+    }
+    if (f.on_host) {
+      (*outputs)[i] = t;
+    } else {
+      TF_RETURN_IF_ERROR(device_->CopyTensorToHost(t, &(*outputs)[i]));
+      stats_.d2h_bytes += static_cast<long long>(t.TotalBytes());
+    }
+  }
+  stats_.host_enqueue_us = std::chrono::duration_cast<std::chrono::microseconds>(
+                               std::chrono::steady_clock::now() - run_start_).count();
+  return device_->Sync();
+}
+
 Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
                               const std::vector<std::pair<std::string, Tensor>>& inputs,
                               std::vector<Tensor>* outputs) {
+  // ---- step-level CUDA graph: replay, or capture this walk
+  bool capturing = false;
+  if (GraphEligible(ek, inputs.size()) && b200_profile_active() == 0) {
+    if (ek->graph_state == 2) return ReplayGraph(ek, outputs);
+    capturing = ++ek->warm_runs >= 3;  // arenas learned, allocator and lazy inits warm
+  } else if (ek->has_assign) {
+    DropAllGraphs();  // this plan may give a variable a new buffer
+  }
+  GPUBFCAllocator* bfc = nullptr;
+  unsigned long long launches_at_begin = 0;
+  if (capturing) {
+    bfc = dynamic_cast<GPUBFCAllocator*>(device_->GetAllocator(AllocatorAttributes()));
+    if (bfc == nullptr ||
+        b200_stream_begin_capture(device_->compute_stream()->cuda_stream()) != 0) {
+      capturing = false;
+      ek->graph_state = -1;
+    } else {
+      bfc->BeginPin();
+      launches_at_begin = b200_launch_count();
+    }
+  }
+  // leaves capture mode on every early return of the walk below
+  struct CaptureGuard {
+    DirectSession* self;
+    ExecutorsAndKeys* ek;
+    GPUBFCAllocator* bfc;
+    bool* active;
+    ~CaptureGuard() {
+      if (!*active) return;
+      void* exec = nullptr;
+      b200_stream_end_capture(self->device_->compute_stream()->cuda_stream(), &exec);
+      if (exec) b200_graph_destroy(exec);
+      std::vector<void*> pinned;
+      bfc->EndPin(&pinned);
+      for (void* p : pinned) bfc->DeallocateRaw(p);
+      ek->graph_state = -1;  // a plan whose walk failed under capture is not tried again
+    }
+  } capture_guard{this, ek, bfc, &capturing};
+
   // ---- SendInputs: stage feeds where their consumers need them
   std::vector<Tensor> feed_dev(inputs.size()), feed_host(inputs.size());
   std::vector<StagedFeed> consumed_stages;  // released after the step's sync
@@ -910,6 +1036,42 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
       compute->ThenWaitFor(en.pending);
       en.pending = nullptr;
     }
+
+  if (capturing) {
+    // the walk above was recorded, not executed: instantiate, remember what the fetches read,
+    // keep every buffer the recorded kernels address, then run the step by launching the graph
+    capturing = false;  // the guard must not tear the capture down any more
+    void* exec = nullptr;
+    const int rc = b200_stream_end_capture(compute->cuda_stream(), &exec);
+    std::vector<void*> pinned;
+    bfc->EndPin(&pinned);
+    if (rc != 0 || exec == nullptr) {
+      for (void* p : pinned) bfc->DeallocateRaw(p);
+      ek->graph_state = -1;
+      return errors::Internal("CUDA graph capture of the step failed: ", b200_last_error());
+    }
+    ek->graph_exec = exec;
+    ek->graph_pinned.swap(pinned);
+    ek->graph_launches = static_cast<long long>(b200_launch_count() - launches_at_begin);
+    ek->graph_fetches.clear();
+    for (size_t i = 0; i < ek->fetches.size(); ++i) {
+      const InputSource& src = ek->fetches[i];
+      Entry& en = entries[entry_index_of(ek, src.id)];
+      ExecutorsAndKeys::CapturedFetch f;
+      f.value = en.val;
+      f.ref = en.ref;
+      f.ref_mu = en.ref_mu;
+      f.on_host = en.on_host;
+      ek->graph_fetches.push_back(f);
+    }
+    for (Entry& en : entries)
+      if (en.val.buffer() != nullptr) ek->graph_keepalive.push_back(en.val);
+    for (Tensor& t : arena_root)
+      if (t.buffer() != nullptr) ek->graph_keepalive.push_back(t);
+    ek->graph_state = 2;
+    TF_RETURN_IF_ERROR(FromAbiStatus(b200_graph_launch(exec, compute->cuda_stream()),
+                                     "cudaGraphLaunch"));
+  }
 
   // ---- RecvOutputs: device -> pinned host, then the single sync of the step
   outputs->clear();

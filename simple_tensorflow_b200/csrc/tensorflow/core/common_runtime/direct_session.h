@@ -109,6 +109,23 @@ class DirectSession : public Session {
     int num_entries = 0;
     // per collective-stream node: [2k] inputs-ready (recorded on compute), [2k+1] done
     std::vector<std::unique_ptr<gpu::Event>> collective_events;
+    // ---- step-level CUDA graph of this plan (the executor cache entry of
+    // direct_session.cc:918-936 holding its whole launch sequence).  Eligible plans (no feeds, one
+    // stream, no host round trips) are captured on their third run and replayed afterwards.
+    struct CapturedFetch {
+      Tensor value;             // a plain value: the tensor the captured kernels write
+      Tensor* ref = nullptr;    // a variable: read at fetch time (its buffer is stable)
+      std::mutex* ref_mu = nullptr;
+      bool on_host = false;
+    };
+    int graph_state = 0;        // 0 unknown, 1 eligible (counting warm runs), 2 captured, -1 never
+    int warm_runs = 0;
+    void* graph_exec = nullptr;
+    long long graph_launches = 0;             // kernels per replay (for the launch counter)
+    std::vector<void*> graph_pinned;          // device memory the captured kernels address
+    std::vector<Tensor> graph_keepalive;      // entries alive at the end of the captured walk
+    std::vector<CapturedFetch> graph_fetches;
+    bool has_assign = false;                  // running this plan may move a variable's buffer
   };
   struct Entry {
     Tensor val;
@@ -143,6 +160,11 @@ class DirectSession : public Session {
   // Runs of ApplyGradientDescent nodes separated only by Const nodes (what an optimizer emits)
   // become one _MultiApplyGradientDescent: one launch instead of one per variable.
   Status FuseApplyGradientDescent(ExecutorsAndKeys* ek);
+  // CUDA-graph capture / replay of a whole step (direct_session.cc, "step-level CUDA graphs")
+  bool GraphEligible(ExecutorsAndKeys* ek, size_t num_feeds);
+  Status ReplayGraph(ExecutorsAndKeys* ek, std::vector<Tensor>* outputs);
+  void DropGraph(ExecutorsAndKeys* ek);
+  void DropAllGraphs();
   Status FuseReluGradBiasGrad(ExecutorsAndKeys* ek);
   void PlanGradientArenas(ExecutorsAndKeys* ek);
   Status RunPlan(ExecutorsAndKeys* ek, const std::vector<std::pair<std::string, Tensor>>& inputs,

@@ -79,8 +79,27 @@ void* GPUBFCAllocator::AllocateLocked(size_t /*alignment*/, size_t num_bytes) {
   return ptr;
 }
 
+void GPUBFCAllocator::BeginPin() {
+  std::lock_guard<std::mutex> l(mu_);
+  pin_mode_ = true;
+  pinned_.clear();
+}
+void GPUBFCAllocator::EndPin(std::vector<void*>* pinned) {
+  std::lock_guard<std::mutex> l(mu_);
+  pin_mode_ = false;
+  pinned->swap(pinned_);
+  pinned_.clear();
+}
+
 void GPUBFCAllocator::DeallocateRaw(void* p) {
   if (p == nullptr) return;
+  {
+    std::lock_guard<std::mutex> l(mu_);
+    if (pin_mode_) {
+      pinned_.push_back(p);  // stays allocated until the captured graph is destroyed
+      return;
+    }
+  }
   if (DeallocateLocked(p)) Unref();  // may delete this: the lock is already released
 }
 

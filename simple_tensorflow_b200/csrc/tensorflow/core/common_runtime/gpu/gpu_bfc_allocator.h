@@ -31,6 +31,11 @@ class GPUBFCAllocator : public Allocator {
   // legal in the reference's C API) still deallocates into a live allocator; the regions are
   // returned to the driver when the last of them goes.  The device calls Unref() instead of delete.
   void Unref();
+  // Pin mode (step-level CUDA graphs): while a step is being captured, nothing it frees may be
+  // handed out again -- the captured kernels keep the addresses -- so DeallocateRaw parks the
+  // pointers; EndPin returns them and the graph's owner frees them when the graph dies.
+  void BeginPin();
+  void EndPin(std::vector<void*>* pinned);
   std::string Name() override { return name_; }
   void* AllocateRaw(size_t alignment, size_t num_bytes) override;
   void DeallocateRaw(void* ptr) override;
@@ -60,6 +65,8 @@ class GPUBFCAllocator : public Allocator {
   size_t next_region_bytes_;
   AllocatorStats stats_;
   std::atomic<long long> refs_{1};
+  bool pin_mode_ = false;
+  std::vector<void*> pinned_;
 };
 
 // Pinned host memory for feeds/fetches (the role of PoolAllocator + CUDAHostAllocator,

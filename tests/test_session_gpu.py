@@ -656,3 +656,47 @@ def test_stream_host_callback_runs_after_enqueued_work():
     assert L.b200_stream_add_host_callback(stream, None, None) != 0  # null callback is rejected
     L.b200_free(dev)
     L.b200_stream_destroy(stream)
+
+
+def _resident_training_losses(steps, graph_env, monkeypatch):
+    """Train the small resident-input MLP for `steps` Session.Run calls; -> (losses, W after)."""
+    import importlib
+    if graph_env is None:
+        monkeypatch.delenv("B200TF_CUDA_GRAPH", raising=False)
+    else:
+        monkeypatch.setenv("B200TF_CUDA_GRAPH", graph_env)
+    r = np.random.RandomState(5)
+    B, D = 256, 128
+    x = r.uniform(-1, 1, (B, D)).astype(np.float32)
+    labels = np.eye(D, dtype=np.float32)[r.randint(0, D, B)]
+    w = (r.randn(D, D) / np.sqrt(D)).astype(np.float32)
+    tf.reset_default_graph()
+    X, L_ = tf.Variable(x, name="x"), tf.Variable(labels, name="l")
+    W1, W2 = tf.Variable(w, name="w1"), tf.Variable(w.T.copy(), name="w2")
+    b1 = tf.Variable(np.full(D, 0.1, np.float32), name="b1")
+    h = tf.relu(tf.bias_add(tf.matmul(X.ref, W1), b1))
+    loss = tf.reduce_mean(tf.softmax_cross_entropy_with_logits(tf.matmul(h, W2), L_.ref))
+    train = tf.GradientDescentOptimizer(0.5).minimize(loss, [W1, W2, b1])
+    losses, launches = [], []
+    with client.Session(tf.get_default_graph()) as sess:
+        sess.run(tf.global_variables_initializer())
+        for _ in range(steps):
+            losses.append(float(sess.run([loss, train])[0]))
+            launches.append(sess.last_run_stats()["kernels_launched"])
+        w_after = sess.run(W1.ref)
+        # a different plan (fetch only) after the captured one still sees the trained variable
+        loss_only = float(sess.run(loss))
+    return losses, w_after, launches, loss_only
+
+
+def test_step_level_cuda_graph_replays_the_step_bit_exactly(monkeypatch):
+    # SURVEY 8f rank 3: a plan without feeds is captured into a CUDA graph on its third run and
+    # replayed; results and the reported launch count must be those of the un-captured executor
+    plain = _resident_training_losses(8, "0", monkeypatch)
+    graph = _resident_training_losses(8, None, monkeypatch)
+    assert plain[0] == graph[0], (plain[0], graph[0])
+    np.testing.assert_array_equal(plain[1], graph[1])
+    assert graph[2][0] == graph[2][-1] > 0          # replays report the captured launch count
+    assert plain[2] == graph[2]
+    assert plain[3] == graph[3]
+    assert graph[0][-1] < graph[0][0]                # and the model did train
