@@ -77,6 +77,8 @@ B200_API int b200_profile_active(void);
 /* Adds n to the launch counter: a replayed CUDA graph launches the kernels of the captured step
  * without passing through the b200_* entry points that count them. */
 B200_API void b200_note_launches(uint64_t n);
+/* The same for the gradient-exchange counters of b200_collective_counts. */
+B200_API void b200_note_collectives(uint64_t peer_launches, uint64_t nccl_calls);
 /* Step-level CUDA graphs (the executor captures one Session.Run plan, keyed like the reference's
  * executor cache, direct_session.cc:918-936): capture everything the b200_* calls enqueue on
  * `stream` between begin and end (relaxed mode), instantiate, replay.  end returns the executable

@@ -38,6 +38,7 @@ SIGNATURES = {
     "b200_collective_counts": (None, [ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]),
     "b200_profile_active": (c_int, []),
     "b200_note_launches": (None, [ctypes.c_uint64]),
+    "b200_note_collectives": (None, [ctypes.c_uint64, ctypes.c_uint64]),
     "b200_stream_begin_capture": (c_int, [c_void_p]),
     "b200_stream_end_capture": (c_int, [c_void_p, ctypes.POINTER(c_void_p)]),
     "b200_graph_launch": (c_int, [c_void_p, c_void_p]),

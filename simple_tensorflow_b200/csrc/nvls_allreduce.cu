@@ -33,6 +33,7 @@ namespace b200 {
 namespace {
 
 constexpr size_t kNvlsHeaderBytes = 64 << 10;  // flag words live in the first 64 KB
+constexpr size_t kNvlsCallsOffset = 32 << 10;  // per-CTA barrier counters (this rank's view only)
 constexpr int kNvlsMaxCtas = 256;
 constexpr int kNvlsThreads = 256;
 
@@ -208,15 +209,26 @@ __device__ __forceinline__ uint32_t scale_bf16x2(uint32_t w, float scale) {
 template <bool kBf16>
 __global__ void __launch_bounds__(kNvlsThreads, 4)
 nvls_all_reduce_kernel(char* __restrict__ mc_data, uint32_t* mc_flags, const uint32_t* uc_flags,
-                       long long nvec, long long slice_vecs, int rank, float scale,
-                       uint32_t target_begin, uint32_t target_end) {
+                       uint32_t* uc_calls, long long nvec, long long slice_vecs, int rank,
+                       int nranks, float scale) {
   pdl_prologue();
+  // Barrier targets come from a per-CTA counter in this rank's own header (unicast view only): a
+  // kernel argument would be frozen into a captured CUDA graph.  Flag word b only ever grows by
+  // nranks per barrier CTA b takes part in, on every rank alike.
+  __shared__ uint32_t calls_sm;
+  if (threadIdx.x == 0) {
+    calls_sm = uc_calls[blockIdx.x];
+    uc_calls[blockIdx.x] = calls_sm + 2;
+  }
+  __syncthreads();
+  const uint32_t target_begin = (calls_sm + 1) * (uint32_t)nranks;
+  const uint32_t target_end = (calls_sm + 2) * (uint32_t)nranks;
   nvls_barrier(mc_flags, uc_flags, target_begin);  // every rank's producers are done
   const long long lo = (long long)rank * slice_vecs;
   long long hi = lo + slice_vecs;
   if (hi > nvec) hi = nvec;
   const long long stride = (long long)gridDim.x * kNvlsThreads;
-  constexpr int U = 4;  // reductions in flight per thread (a switch round trip each)
+  constexpr int U = 8;  // reductions in flight per thread (a switch round trip each)
   for (long long v0 = lo + (long long)blockIdx.x * kNvlsThreads + threadIdx.x; v0 < hi;
        v0 += stride * U) {
     uint4 x[U];
@@ -467,29 +479,27 @@ int nvls_all_reduce(NvlsArena* a, int dtype, size_t offset_bytes, long long coun
   const int per_vec = dtype == B200_DT_FLOAT ? 4 : 8;
   const long long nvec = (count + per_vec - 1) / per_vec;  // the arena is padded to 256 bytes
   const long long slice = (nvec + a->nranks - 1) / a->nranks;
-  int ctas = max_ctas > 0 ? max_ctas : 96;
+  int ctas = max_ctas > 0 ? max_ctas : 128;
   if (ctas > kNvlsMaxCtas) ctas = kNvlsMaxCtas;
   long long useful = (slice + kNvlsThreads - 1) / kNvlsThreads;
   if (useful < 1) useful = 1;
   if (ctas > useful) ctas = (int)useful;
   char* mc = reinterpret_cast<char*>(a->mc_va);
   char* uc = reinterpret_cast<char*>(a->uc_va);
-  // flag words only grow: barrier k completes when a replica's word reaches k * nranks
-  const uint32_t target_begin = (a->barriers + 1) * (uint32_t)a->nranks;
-  const uint32_t target_end = (a->barriers + 2) * (uint32_t)a->nranks;
-  a->barriers += 2;
   const float scale = average ? 1.0f / (float)a->nranks : 1.0f;
   cudaError_t e;
   if (dtype == B200_DT_FLOAT)
     e = launch_pdl(nvls_all_reduce_kernel<false>, dim3(ctas), dim3(kNvlsThreads), 0, stream,
                    mc + kNvlsHeaderBytes + offset_bytes, reinterpret_cast<uint32_t*>(mc),
-                   reinterpret_cast<const uint32_t*>(uc), nvec, slice, a->rank, scale,
-                   target_begin, target_end);
+                   reinterpret_cast<const uint32_t*>(uc),
+                   reinterpret_cast<uint32_t*>(uc + kNvlsCallsOffset), nvec, slice, a->rank,
+                   a->nranks, scale);
   else
     e = launch_pdl(nvls_all_reduce_kernel<true>, dim3(ctas), dim3(kNvlsThreads), 0, stream,
                    mc + kNvlsHeaderBytes + offset_bytes, reinterpret_cast<uint32_t*>(mc),
-                   reinterpret_cast<const uint32_t*>(uc), nvec, slice, a->rank, scale,
-                   target_begin, target_end);
+                   reinterpret_cast<const uint32_t*>(uc),
+                   reinterpret_cast<uint32_t*>(uc + kNvlsCallsOffset), nvec, slice, a->rank,
+                   a->nranks, scale);
   if (e != cudaSuccess) {
     set_last_error("nvls_all_reduce launch: %s", cudaGetErrorString(e));
     cudaGetLastError();

@@ -33,6 +33,7 @@ constexpr int kMaxRanks = 8;
 constexpr int kMaxCtas = 512;
 constexpr size_t kFlagBytes = (size_t)kMaxRanks * kMaxCtas * sizeof(uint32_t);  // 16 KB
 constexpr size_t kHeaderBytes = 64 << 10;  // flags live in the first 64 KB of every rank's buffer
+constexpr size_t kEpochOffset = 32 << 10;  // per-CTA call counters of the owning rank (local only)
 // 256 threads x <= 64 registers: a CTA of this kernel fits on an SM BESIDE a resident tcgen05 GEMM
 // CTA (192 threads x <= 192 registers, ~220 KB smem), so on the collective stream it needs no
 // free SMs and takes none from the GEMMs -- it only shares their issue slots.
@@ -95,8 +96,20 @@ __device__ __forceinline__ void peer_barrier(const PeerTable& t, uint32_t value)
 template <int NR>
 __global__ void __launch_bounds__(kThreads, 4)
 peer_all_reduce_kernel(const __grid_constant__ PeerTable t, size_t offset, long long nvec, long long slice_vecs,
-                       float scale, uint32_t epoch) {
+                       float scale) {
   pdl_prologue();
+  // The barrier epoch lives in device memory (one word per CTA in this rank's header, never
+  // touched by peers): a kernel argument would be frozen into a captured CUDA graph, and every
+  // replay must use fresh, growing flag values.  All ranks issue the same call sequence with the
+  // same grid, so CTA b's counter agrees across ranks.
+  __shared__ uint32_t epoch_sm;
+  if (threadIdx.x == 0) {
+    uint32_t* calls = reinterpret_cast<uint32_t*>(t.base[t.rank] + kEpochOffset) + blockIdx.x;
+    epoch_sm = *calls;
+    *calls = epoch_sm + 3;
+  }
+  __syncthreads();
+  const uint32_t epoch = epoch_sm;
   const int rank = t.rank;
   // (pointers are re-derived from the parameter table: indexing a local array by rank would
   // put it on the stack)
@@ -382,13 +395,11 @@ int b200_peer_all_reduce(void* arena, int dtype, size_t offset_bytes, int64_t co
   cfg.gridDim = dim3(ctas);
   cfg.blockDim = dim3(kThreads);
   cfg.stream = as_stream(stream);
-  const uint32_t epoch = a->epoch;
-  a->epoch += 3;
   cudaError_t e = cudaSuccess;
 #define PEER_LAUNCH(NR)                                                                      \
   case NR:                                                                                   \
     e = cudaLaunchKernelEx(&cfg, peer_all_reduce_kernel<NR>, a->table, offset_bytes, nvec,   \
-                           slice, scale, epoch);                                             \
+                           slice, scale);                                                    \
     break;
   switch (nr) {
     PEER_LAUNCH(2)

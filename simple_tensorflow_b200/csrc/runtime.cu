@@ -244,6 +244,10 @@ int b200_get_matmul_precision(void) { return g_matmul_precision.load(); }
 
 int b200_profile_active(void) { return g_prof_on.load() ? 1 : 0; }
 void b200_note_launches(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void b200_note_collectives(uint64_t peer_launches, uint64_t nccl_calls) {
+  g_peer_collectives.fetch_add(peer_launches, std::memory_order_relaxed);
+  g_nccl_collectives.fetch_add(nccl_calls, std::memory_order_relaxed);
+}
 
 int b200_stream_begin_capture(void* stream) {
   CUDA_RC(cudaStreamBeginCapture(as_stream(stream), cudaStreamCaptureModeRelaxed),

@@ -689,7 +689,19 @@ bool DirectSession::GraphEligible(ExecutorsAndKeys* ek, size_t num_feeds) {
   if (ek->has_assign) return false;  // an Assign may replace a buffer other plans have captured
   const char* env = getenv("B200TF_CUDA_GRAPH");
   if (env != nullptr && std::strcmp(env, "0") == 0) return false;
-  if (num_feeds != 0 || device_->num_replicas() > 1 || ek->order.empty()) return false;
+  if (num_feeds != 0 || ek->order.empty()) return false;
+  // Replicas: the gradient exchange must be one of our own kernels (their barrier epochs live in
+  // device memory, so a replay is a fresh exchange); an NCCL call is not captured.
+  const bool replicas = device_->num_replicas() > 1;
+  const std::string backend = b200_peer_arena_backend();
+  if (replicas && (backend == "none" || device_->peer_arena() == nullptr)) return false;
+  for (const PlanNode& pn : ek->order) {
+    const std::string& op = pn.item->def.op;
+    if (!replicas || (op != "B200AllReduce" && op != "B200AllReduceN")) continue;
+    if (op == "B200AllReduce") return false;  // the single-tensor form always goes through NCCL
+    const DataType dt = pn.item->kernel->input_type(0);
+    if (pn.arena < 0 || !(dt == DT_FLOAT || (dt == DT_BFLOAT16 && backend == "nvls"))) return false;
+  }
   // producer memory space of every entry
   std::vector<int> entry_host(ek->num_entries, 0);
   for (const PlanNode& pn : ek->order) {
@@ -735,6 +747,7 @@ Status DirectSession::ReplayGraph(ExecutorsAndKeys* ek, std::vector<Tensor>* out
   TF_RETURN_IF_ERROR(FromAbiStatus(b200_graph_launch(ek->graph_exec, compute->cuda_stream()),
                                    "cudaGraphLaunch"));
   b200_note_launches(static_cast<uint64_t>(ek->graph_launches));
+  b200_note_collectives(ek->graph_peer_collectives, ek->graph_nccl_collectives);
   stats_.nodes_executed += static_cast<long long>(ek->order.size());
   outputs->clear();
   outputs->resize(ek->graph_fetches.size());
@@ -770,6 +783,7 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
   }
   GPUBFCAllocator* bfc = nullptr;
   unsigned long long launches_at_begin = 0;
+  uint64_t peer_at_begin = 0, nccl_at_begin = 0;
   if (capturing) {
     bfc = dynamic_cast<GPUBFCAllocator*>(device_->GetAllocator(AllocatorAttributes()));
     if (bfc == nullptr ||
@@ -779,6 +793,7 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
     } else {
       bfc->BeginPin();
       launches_at_begin = b200_launch_count();
+      b200_collective_counts(&peer_at_begin, &nccl_at_begin);
     }
   }
   // leaves capture mode on every early return of the walk below
@@ -1053,6 +1068,10 @@ Status DirectSession::RunPlan(ExecutorsAndKeys* ek,
     ek->graph_exec = exec;
     ek->graph_pinned.swap(pinned);
     ek->graph_launches = static_cast<long long>(b200_launch_count() - launches_at_begin);
+    uint64_t peer_now = 0, nccl_now = 0;
+    b200_collective_counts(&peer_now, &nccl_now);
+    ek->graph_peer_collectives = peer_now - peer_at_begin;
+    ek->graph_nccl_collectives = nccl_now - nccl_at_begin;
     ek->graph_fetches.clear();
     for (size_t i = 0; i < ek->fetches.size(); ++i) {
       const InputSource& src = ek->fetches[i];

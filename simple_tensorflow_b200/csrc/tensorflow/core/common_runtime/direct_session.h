@@ -122,6 +122,7 @@ class DirectSession : public Session {
     int warm_runs = 0;
     void* graph_exec = nullptr;
     long long graph_launches = 0;             // kernels per replay (for the launch counter)
+    unsigned long long graph_peer_collectives = 0, graph_nccl_collectives = 0;
     std::vector<void*> graph_pinned;          // device memory the captured kernels address
     std::vector<Tensor> graph_keepalive;      // entries alive at the end of the captured walk
     std::vector<CapturedFetch> graph_fetches;
