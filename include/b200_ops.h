@@ -178,6 +178,19 @@ B200_API size_t b200_bias_add_grad_workspace_bytes(int dtype, int64_t rows, int6
 B200_API int b200_bias_add_grad(int dtype, const void* out_backprop, void* out, int64_t rows,
                                 int64_t channels, void* workspace, size_t workspace_bytes,
                                 void* stream);
+/* data_format = NCHW, native (no layout change): BiasGPU<T>::compute's BiasNCHWKernel
+ * (bias_op_gpu.cu.cc:56-63,80-86) and BiasGradGPU's BiasGradNCHW_SharedAtomics (:140-188,225-233).
+ * The tensor is [batch, channels, image] with image = prod(dims after the channel dimension), so
+ * 3-D, 4-D and 5-D NCHW inputs (bias_op.cc:75-107) are one call.  out may alias in.  The
+ * gradient is a two-stage ordered reduction (no atomics, bit-reproducible); workspace:
+ * b200_bias_add_grad_nchw_workspace_bytes() bytes of device scratch. */
+B200_API int b200_bias_add_nchw(int dtype, const void* in, const void* bias, void* out,
+                                int64_t batch, int64_t channels, int64_t image, void* stream);
+B200_API size_t b200_bias_add_grad_nchw_workspace_bytes(int dtype, int64_t batch,
+                                                        int64_t channels, int64_t image);
+B200_API int b200_bias_add_grad_nchw(int dtype, const void* out_backprop, void* out,
+                                     int64_t batch, int64_t channels, int64_t image,
+                                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------ Relu / ReluGrad
  * functor::Relu / functor::ReluGrad (core/kernels/relu_op_functor.h:28-60):

@@ -82,6 +82,11 @@ SIGNATURES = {
     "b200_bias_add_grad_workspace_bytes": (c_size_t, [c_int, c_int64, c_int64]),
     "b200_bias_add_grad": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
                                    c_size_t, c_void_p]),
+    "b200_bias_add_nchw": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                   c_void_p]),
+    "b200_bias_add_grad_nchw_workspace_bytes": (c_size_t, [c_int, c_int64, c_int64, c_int64]),
+    "b200_bias_add_grad_nchw": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64,
+                                        c_void_p, c_size_t, c_void_p]),
     "b200_relu": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "b200_relu_grad": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b200_relu_grad_bias_grad_workspace_bytes": (c_size_t, [c_int, c_int64, c_int64]),

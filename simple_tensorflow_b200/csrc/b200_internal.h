@@ -114,6 +114,12 @@ __device__ __forceinline__ void pdl_prologue() {
 }
 void note_collective(bool peer);  // runtime.cu: b200_collective_counts()
 bool pdl_enabled();  // runtime.cu: on unless B200TF_NO_PDL is set
+// B200TF_KERNEL_TIMES=1 (measurement aid, runtime.cu): every launch is bracketed by CUDA events on
+// its stream and the per-kernel totals are printed to stderr at exit (warm caches, in stream
+// order; the brackets serialise the launches, so PDL overlap and CUDA graphs are off in this mode).
+bool kernel_times_enabled();
+void* kernel_times_begin(cudaStream_t stream);
+void kernel_times_end(void* token, cudaStream_t stream, const void* kernel);
 // kernel<<<grid, block, smem, stream>>>(args...) with programmatic stream serialization allowed:
 // the grid may be scheduled while its predecessor in the stream drains (every kernel begins with
 // pdl_prologue(), so nothing is read or written before the predecessor has completed).
@@ -130,6 +136,13 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  if (kernel_times_enabled()) {
+    cfg.numAttrs = 0;
+    void* tok = kernel_times_begin(stream);
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+    kernel_times_end(tok, stream, reinterpret_cast<const void*>(kernel));
+    return e;
+  }
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif

@@ -418,26 +418,247 @@ conv_small_cin_wgrad_kernel(const float* __restrict__ x, const float* __restrict
     }
   }
 }
-// dW[i] = sum over CTAs (fixed order) of partial[cta][i]: 32 elements x 8 strands per CTA, each
-// strand adds every 8th partial in ascending order, the strands are merged in strand order.
-__global__ void __launch_bounds__(256)
+// dW[i] = sum over CTAs (fixed order) of partial[cta][i]: a CTA of (32, strands) threads owns 32
+// elements; strand q adds every strands-th partial in ascending order (four loads in flight), the
+// strands are merged in strand order.  blockDim.y = 8 or 32 strands.
+__global__ void __launch_bounds__(1024)
 conv_small_cin_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw,
                                    int blocks, int elems) {
   pdl_prologue();
-  __shared__ float strands[8][33];
-  const int e = blockIdx.x * 32 + (threadIdx.x & 31), st = threadIdx.x >> 5;
+  __shared__ float strands[32][33];
+  const int x = threadIdx.x & 31;
+  const int st = blockDim.y == 1 ? (int)(threadIdx.x >> 5) : (int)threadIdx.y;
+  const int nst = blockDim.y == 1 ? (int)(blockDim.x >> 5) : (int)blockDim.y;
+  const int e = blockIdx.x * 32 + x;
   float sum = 0.f;
-  if (e < elems)
-    for (int b = st; b < blocks; b += 8) sum += partial[(long long)b * elems + e];
-  strands[st][threadIdx.x & 31] = sum;
+  if (e < elems) {
+    int b = st;
+    for (; b + 3 * nst < blocks; b += 4 * nst) {
+      const float v0 = __ldcg(partial + (long long)b * elems + e);
+      const float v1 = __ldcg(partial + (long long)(b + nst) * elems + e);
+      const float v2 = __ldcg(partial + (long long)(b + 2 * nst) * elems + e);
+      const float v3 = __ldcg(partial + (long long)(b + 3 * nst) * elems + e);
+      sum += v0;
+      sum += v1;
+      sum += v2;
+      sum += v3;
+    }
+    for (; b < blocks; b += nst) sum += __ldcg(partial + (long long)b * elems + e);
+  }
+  strands[st][x] = sum;
   __syncthreads();
   if (st == 0 && e < elems) {
     float t = 0.f;
-    for (int q = 0; q < 8; ++q) t += strands[q][threadIdx.x];
+    for (int q = 0; q < nst; ++q) t += strands[q][x];
     dw[e] = t;
   }
 }
 static int small_cin_wgrad_blocks() { return 8 * sm_count(); }
+
+// ------------------------------------------------------------------ one input channel, unit stride
+// LeNet conv1 (28x28x1 * 5x5x1x32, batch 512: 1.6 MB in, 51 MB out / dY, 0.64 GFLOP) is an HBM
+// streaming problem; the generic small-C_in kernels above were bound by shared-memory loads instead
+// (16-byte filter / dY broadcasts: 4 LDS.128 per 16 FMAs).  Here the lane IS the filter: a lane
+// keeps its filter's R*S taps (forward) or its R*S accumulators (filter gradient) in registers, a
+// warp walks one output row, and the R x S input window -- the same for every lane -- slides over
+// a zero-padded copy of the image in shared memory: S..R new broadcast 4-byte loads per pixel, the
+// window rotates through registers (pixel loop unrolled by S so every index is static).
+// Per pixel and warp: R loads + R*S FMAs + one coalesced 128-byte store (forward) or one
+// conflict-free shared load of the staged dY row (gradient).  Same tap order and fp32 FMAs as the
+// generic kernels (bit-identical forward).
+constexpr int kC1Threads = 256, kC1Warps = 8;
+
+// Tile row stride (floats): OW + S - 1 columns rounded up to a multiple of 4; everything outside
+// the image is zero.
+__host__ __device__ inline int c1_row_stride(int OW) { return (OW + 4 + 3) / 4 * 4; }
+
+template <int R, int S>
+__device__ __forceinline__ void c1_stage_image(float* xs, const float* __restrict__ xn,
+                                               const ConvG& g, int HP, int WPs) {
+  for (int i = threadIdx.x; i < HP * WPs; i += kC1Threads) {
+    const int ih = i / WPs - g.pt, iw = i % WPs - g.pl;
+    xs[i] = (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W) ? __ldg(xn + ih * g.W + iw) : 0.f;
+  }
+}
+
+template <int R, int S>
+__global__ void __launch_bounds__(kC1Threads)
+conv_c1_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y,
+                   ConvG g, const float* __restrict__ bias, int relu, int parts) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float c1_smem[];
+  float* xs = c1_smem;  // [HP][WP], zero padded
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int HP = g.OH + R - 1, WPs = c1_row_stride(g.OW);
+  // work item = (image, band of output rows): `parts` bands per image keep the last wave of CTAs
+  // short when the batch is only a few images per SM
+  for (int item = blockIdx.x; item < g.N * parts; item += gridDim.x) {
+    const int n = item / parts, part = item - n * parts;
+    const int oh_begin = g.OH * part / parts, oh_end = g.OH * (part + 1) / parts;
+    __syncthreads();  // the previous item's readers are done
+    c1_stage_image<R, S>(xs, x + (long long)n * g.H * g.W, g, HP, WPs);
+    __syncthreads();
+    for (int kb = 0; kb < g.K; kb += 32) {
+      float wr[R * S];
+#pragma unroll
+      for (int t = 0; t < R * S; ++t) wr[t] = __ldg(w + t * g.K + kb + lane);
+      const float bv = bias != nullptr ? __ldg(bias + kb + lane) : 0.f;
+      for (int oh = oh_begin + warp; oh < oh_end; oh += kC1Warps) {
+        // rp[r]: the window's NEW column (tile column ow + S - 1) in row r; one increment per row
+        // and group of S pixels, everything else is an immediate offset
+        const float* rp[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) rp[r] = xs + (oh + r) * WPs + (S - 1);
+        float win[R][S];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < S - 1; ++c) win[r][c] = rp[r][c - (S - 1)];
+        float* yp = y + (((long long)n * g.OH + oh) * g.OW) * g.K + kb + lane;
+        const int Kst = g.K;
+        auto pixel = [&](int j) {  // j = ow % S, a compile-time constant at every call site
+#pragma unroll
+          for (int r = 0; r < R; ++r) win[r][(j + S - 1) % S] = rp[r][j];
+          float acc = 0.f;
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int sx = 0; sx < S; ++sx) acc = fmaf(win[r][(j + sx) % S], wr[r * S + sx], acc);
+          if (bias != nullptr) {  // fused BiasAdd (+ Relu), as in conv_small_cin_fwd_kernel
+            acc += bv;
+            if (relu) acc = acc > 0.f ? acc : 0.f;
+          }
+          yp[j * Kst] = acc;
+        };
+        int ow0 = 0;
+        for (; ow0 + S <= g.OW; ow0 += S) {  // whole groups: no per-pixel predicate
+#pragma unroll
+          for (int j = 0; j < S; ++j) pixel(j);
+#pragma unroll
+          for (int r = 0; r < R; ++r) rp[r] += S;
+          yp += S * Kst;
+        }
+#pragma unroll
+        for (int j = 0; j < S - 1; ++j)
+          if (ow0 + j < g.OW) pixel(j);
+      }
+    }
+  }
+}
+
+// Filter gradient: dW[r, s, k] = sum over pixels of x[oh + r - pt, ow + s - pl] * dY[pixel, k].
+// Every warp stages the dY rows it walks through its own double-buffered cp.async ring (a whole
+// output row of 32 filters in flight per warp), accumulates R*S taps per lane over all its rows and
+// images, the warps are merged in warp order and each CTA writes one partial [R*S][K] tile that
+// conv_small_cin_wgrad_reduce_kernel adds in CTA order.  No atomics; reproducible.
+template <int R, int S>
+__global__ void __launch_bounds__(kC1Threads)
+conv_c1_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                     float* __restrict__ partial, ConvG g, int parts) {
+  pdl_prologue();
+  extern __shared__ __align__(16) float c1_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int HP = g.OH + R - 1, WPs = c1_row_stride(g.OW);
+  const int xs_floats = HP * WPs;
+  const int row_floats = g.OW * 32;
+  float* xs = c1_smem;
+  float* my = c1_smem + xs_floats + warp * 2 * row_floats;  // this warp's ring: 2 dY rows
+  for (int kb = 0; kb < g.K; kb += 32) {
+    float acc[R * S];
+#pragma unroll
+    for (int t = 0; t < R * S; ++t) acc[t] = 0.f;
+    for (int item = blockIdx.x; item < g.N * parts; item += gridDim.x) {
+      const int n = item / parts, part = item - n * parts;
+      const int oh_begin = g.OH * part / parts, oh_end = g.OH * (part + 1) / parts;
+      __syncthreads();
+      c1_stage_image<R, S>(xs, x + (long long)n * g.H * g.W, g, HP, WPs);
+      __syncthreads();
+      const float* dyn = dy + (long long)n * g.OH * g.OW * g.K + kb;
+      auto fetch = [&](int oh, int st) {
+        float* dst = my + st * row_floats;
+        const float* src = dyn + (long long)oh * g.OW * g.K;
+        for (int i = lane; i < g.OW * 8; i += 32)
+          cp_async16(dst + (i >> 3) * 32 + (i & 7) * 4, src + (long long)(i >> 3) * g.K + (i & 7) * 4);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      };
+      int st = 0;
+      if (oh_begin + warp < oh_end) fetch(oh_begin + warp, 0);
+      for (int oh = oh_begin + warp; oh < oh_end; oh += kC1Warps) {
+        if (oh + kC1Warps < oh_end) {
+          fetch(oh + kC1Warps, st ^ 1);
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else {
+          asm volatile("cp.async.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
+        const float* d = my + st * row_floats + lane;
+        const float* rp[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) rp[r] = xs + (oh + r) * WPs + (S - 1);
+        float win[R][S];
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int c = 0; c < S - 1; ++c) win[r][c] = rp[r][c - (S - 1)];
+        auto pixel = [&](int j) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) win[r][(j + S - 1) % S] = rp[r][j];
+          const float dv = d[j * 32];
+#pragma unroll
+          for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int sx = 0; sx < S; ++sx)
+              acc[r * S + sx] = fmaf(win[r][(j + sx) % S], dv, acc[r * S + sx]);
+        };
+        int ow0 = 0;
+        for (; ow0 + S <= g.OW; ow0 += S) {
+#pragma unroll
+          for (int j = 0; j < S; ++j) pixel(j);
+#pragma unroll
+          for (int r = 0; r < R; ++r) rp[r] += S;
+          d += S * 32;
+        }
+#pragma unroll
+        for (int j = 0; j < S - 1; ++j)
+          if (ow0 + j < g.OW) pixel(j);
+        __syncwarp();  // row consumed: the next trip's prefetch may overwrite this stage
+        st ^= 1;
+      }
+    }
+    __syncthreads();
+    float* red = c1_smem;  // [warps][R*S][32] over the (now idle) image and rings
+#pragma unroll
+    for (int t = 0; t < R * S; ++t) red[(warp * R * S + t) * 32 + lane] = acc[t];
+    __syncthreads();
+    for (int i = threadIdx.x; i < R * S * 32; i += kC1Threads) {
+      float sum = 0.f;
+#pragma unroll
+      for (int q = 0; q < kC1Warps; ++q) sum += red[q * R * S * 32 + i];
+      partial[((long long)blockIdx.x * R * S + (i >> 5)) * g.K + kb + (i & 31)] = sum;
+    }
+    __syncthreads();
+  }
+}
+
+struct C1Fit {
+  bool fwd, wgrad;
+  size_t smem_fwd, smem_wgrad;
+};
+static C1Fit c1_fit(int dtype, const ConvG& g) {
+  C1Fit f{false, false, 0, 0};
+  if (dtype != B200_DT_FLOAT || g.C != 1 || g.sh != 1 || g.sw != 1 || g.K % 32 != 0 || g.K <= 0)
+    return f;
+  if (!((g.R == 5 && g.S == 5) || (g.R == 3 && g.S == 3))) return f;
+  if (g.OH < 1 || g.OW < 1 || (long long)g.N * g.OH * g.OW * g.K >= (1LL << 40)) return f;
+  const size_t image = (size_t)(g.OH + g.R - 1) * c1_row_stride(g.OW);
+  f.smem_fwd = image * sizeof(float);
+  f.fwd = f.smem_fwd <= 64 * 1024;
+  const size_t red = (size_t)kC1Warps * g.R * g.S * 32 * sizeof(float);
+  f.smem_wgrad = std::max(image * sizeof(float) +
+                              (size_t)kC1Warps * 2 * g.OW * 32 * sizeof(float), red);
+  f.wgrad = f.smem_wgrad <= 100 * 1024;
+  return f;
+}
 
 static GemmArgs base_gemm(int dtype) {
   GemmArgs a{};
@@ -563,7 +784,33 @@ static int conv2d_impl(int dtype, const void* input, const void* filter, void* o
     return B200_INVALID_ARGUMENT;
   }
   static const bool no_direct = getenv("B200TF_CONV_NO_DIRECT") != nullptr;
+  static const bool no_c1 = getenv("B200TF_CONV_NO_C1") != nullptr;
   const SmallCinFit small = small_cin_fit(dtype, g);
+  const C1Fit c1 = c1_fit(dtype, g);
+  if (c1.fwd && !no_direct && !no_c1) {
+    // one image per CTA trip; 3 CTAs per SM by registers
+    const int parts = (g.N < 8 * sm_count() && g.OH >= 2 * kC1Warps) ? 2 : 1;
+    const int blocks = std::min(g.N * parts, 8 * sm_count());
+    const float* xin = static_cast<const float*>(input);
+    const float* win = static_cast<const float*>(filter);
+    float* yout = static_cast<float*>(output);
+#define C1_FWD(R_, S_)                                                                          \
+  do {                                                                                          \
+    static const cudaError_t attr = cudaFuncSetAttribute(                                       \
+        conv_c1_fwd_kernel<R_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);    \
+    (void)attr;                                                                                 \
+    launch_pdl(conv_c1_fwd_kernel<R_, S_>, dim3((unsigned)blocks), dim3(kC1Threads),            \
+               c1.smem_fwd, s, xin, win, yout, g, static_cast<const float*>(bias),              \
+               relu ? 1 : 0, parts);                                                            \
+  } while (0)
+    if (g.R == 5)
+      C1_FWD(5, 5);
+    else
+      C1_FWD(3, 3);
+#undef C1_FWD
+    note_launch();
+    return check_launch("b200_conv2d");
+  }
   if (small.ok && !no_direct && !is_pointwise(g) && aligned16(output)) {
     // 16 filters per thread when K allows it (one input load feeds 16 FMAs), else 4
     const int kp = g.K % 16 == 0 ? 16 : 4;
@@ -667,6 +914,34 @@ int b200_conv2d_backprop_filter(int dtype, const void* input, const void* out_ba
   }
   static const bool no_direct = getenv("B200TF_CONV_NO_DIRECT") != nullptr;
   const SmallCinFit small = small_cin_fit(dtype, g);
+  static const bool no_c1 = getenv("B200TF_CONV_NO_C1") != nullptr;
+  const C1Fit c1 = c1_fit(dtype, g);
+  if (c1.wgrad && small.ok && !no_direct && !no_c1 && aligned16(out_backprop)) {
+    const int parts = (g.N < 8 * sm_count() && g.OH >= 2 * kC1Warps) ? 2 : 1;
+    const int blocks = std::min(g.N * parts, small_cin_wgrad_blocks());  // the workspace holds that many
+    float* partial = static_cast<float*>(workspace);
+    const float* xin = static_cast<const float*>(input);
+    const float* dyin = static_cast<const float*>(out_backprop);
+#define C1_WGRAD(R_, S_)                                                                        \
+  do {                                                                                          \
+    static const cudaError_t attr = cudaFuncSetAttribute(                                       \
+        conv_c1_wgrad_kernel<R_, S_>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024); \
+    (void)attr;                                                                                 \
+    launch_pdl(conv_c1_wgrad_kernel<R_, S_>, dim3((unsigned)blocks), dim3(kC1Threads),          \
+               c1.smem_wgrad, s, xin, dyin, partial, g, parts);                                 \
+  } while (0)
+    if (g.R == 5)
+      C1_WGRAD(5, 5);
+    else
+      C1_WGRAD(3, 3);
+#undef C1_WGRAD
+    const int elems = small.taps * g.K;
+    launch_pdl(conv_small_cin_wgrad_reduce_kernel, dim3((elems + 31) / 32), dim3(32, 32), 0, s,
+               static_cast<const float*>(partial), static_cast<float*>(filter_backprop), blocks,
+               elems);
+    note_launch(2);
+    return check_launch("b200_conv2d_backprop_filter");
+  }
   if (small.ok && g.K % 32 == 0 && !no_direct && !is_pointwise(g) && aligned16(out_backprop)) {
     const int blocks = small_cin_wgrad_blocks();
     float* partial = static_cast<float*>(workspace);

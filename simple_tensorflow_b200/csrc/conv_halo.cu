@@ -598,7 +598,8 @@ static HaloPlan plan_halo(int dtype, int N, int H, int W, int C, int K, int R, i
   // A tcgen05.mma costs the same ~160 cycles for N = 32 as for N = 256, so a one-chunk N is padded
   // to two chunks (the filter map zero-fills the missing columns, the epilogue never stores them):
   // CTA pairs then split the chunks and issue M = 256 MMAs.
-  if (bn == chunk && 2 * chunk <= 256) bn = 2 * chunk;
+  static const bool no_pad_n = getenv("B200TF_CONV_HALO_NO_PAD_N") != nullptr;  // comparison knob
+  if (bn == chunk && 2 * chunk <= 256 && !no_pad_n) bn = 2 * chunk;
   const int max_mt = kAccCols / bn;
   double best_score = -1.0;
   const int bw_cands[6] = {OW, 126, 62, 30, 14, 6};
@@ -748,7 +749,9 @@ static int launch_halo(const HaloPlan& p, const void* input, const void* filter,
   cfg.numAttrs = na;
   const bool prof = profile_enabled();
   if (prof) profile_gemm_launch_begin(stream);
+  void* ktok = kernel_times_enabled() ? kernel_times_begin(stream) : nullptr;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, mx, mw, static_cast<TIn*>(output), s);
+  if (ktok) kernel_times_end(ktok, stream, reinterpret_cast<const void*>(kern));
   if (e != cudaSuccess) {
     set_last_error("conv_halo launch: %s", cudaGetErrorString(e));
     cudaGetLastError();

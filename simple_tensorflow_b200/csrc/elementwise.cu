@@ -258,6 +258,59 @@ static int launch_bias_add(const void* in, const void* bias, void* out, long lon
   return check_launch("b200_bias_add");
 }
 
+// NCHW (channel = dimension 1): the tensor is [planes = batch * channels][image] and plane p takes
+// bias[p % channels] (BiasNCHWKernel, bias_op_gpu.cu.cc:56-63, without its per-element div / mod):
+// blockIdx.y walks planes, blockIdx.x and the thread walk the image in 16-byte vectors.
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(kThreads)
+bias_add_nchw_kernel(const T* in, const T* __restrict__ bias, T* out, long long planes,
+                     int channels, long long image) {
+  pdl_prologue();
+  constexpr int N = Lanes<T>::kN;
+  for (long long p = blockIdx.y; p < planes; p += gridDim.y) {
+    const float b = Lanes<T>::load1(bias + p % channels);
+    const T* src = in + p * image;
+    T* dst = out + p * image;
+    if (kVec) {
+      const long long nvec = image / N;
+      for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nvec;
+           i += (long long)gridDim.x * kThreads) {
+        float x[N];
+        Lanes<T>::unpack(ld16_rw(src + i * N), x);
+#pragma unroll
+        for (int j = 0; j < N; ++j) x[j] += b;
+        st16(dst + i * N, Lanes<T>::pack(x));
+      }
+    } else {
+      for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < image;
+           i += (long long)gridDim.x * kThreads)
+        Lanes<T>::store1(dst + i, Lanes<T>::load1(src + i) + b);
+    }
+  }
+}
+
+template <typename T>
+static int launch_bias_add_nchw(const void* in, const void* bias, void* out, long long batch,
+                                long long channels, long long image, cudaStream_t stream) {
+  constexpr int N = Lanes<T>::kN;
+  const long long planes = batch * channels;
+  const bool vec = image % N == 0 && aligned16(in) && aligned16(out);
+  const long long per_plane = vec ? image / N : image;
+  long long bx = (per_plane + kThreads - 1) / kThreads;
+  if (bx > 64) bx = 64;  // grid-stride inside the plane beyond 64 CTAs
+  const dim3 grid((unsigned)bx, (unsigned)(planes < 65535 ? planes : 65535));
+  if (vec)
+    launch_pdl(bias_add_nchw_kernel<T, true>, grid, dim3(kThreads), 0, stream,
+               static_cast<const T*>(in), static_cast<const T*>(bias), static_cast<T*>(out), planes,
+               (int)channels, image);
+  else
+    launch_pdl(bias_add_nchw_kernel<T, false>, grid, dim3(kThreads), 0, stream,
+               static_cast<const T*>(in), static_cast<const T*>(bias), static_cast<T*>(out), planes,
+               (int)channels, image);
+  note_launch();
+  return check_launch("b200_bias_add_nchw");
+}
+
 // ------------------------------------------------------------------ Cast
 // One generic scalar-converting kernel (4 elements per thread); float<->bfloat16 are bit moves.
 template <typename S, typename D>
@@ -480,6 +533,21 @@ int b200_bias_add(int dtype, const void* in, const void* bias, void* out, int64_
   if (dtype == B200_DT_BFLOAT16)
     return launch_bias_add<__nv_bfloat16>(in, bias, out, rows, channels, as_stream(stream));
   return bad_dtype("b200_bias_add", dtype);
+}
+
+int b200_bias_add_nchw(int dtype, const void* in, const void* bias, void* out, int64_t batch,
+                       int64_t channels, int64_t image, void* stream) {
+  if (batch < 0 || channels < 0 || image < 0 || channels > INT32_MAX)
+    return bad_n("b200_bias_add_nchw", batch < 0 ? batch : (image < 0 ? image : channels));
+  if (batch * channels * image == 0) return B200_OK;
+  int rc = require_device("b200_bias_add_nchw");
+  if (rc) return rc;
+  if (dtype == B200_DT_FLOAT)
+    return launch_bias_add_nchw<float>(in, bias, out, batch, channels, image, as_stream(stream));
+  if (dtype == B200_DT_BFLOAT16)
+    return launch_bias_add_nchw<__nv_bfloat16>(in, bias, out, batch, channels, image,
+                                               as_stream(stream));
+  return bad_dtype("b200_bias_add_nchw", dtype);
 }
 
 int b200_relu(int dtype, const void* features, void* activations, int64_t n, void* stream) {

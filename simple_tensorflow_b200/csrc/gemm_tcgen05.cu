@@ -873,6 +873,49 @@ splitk_reduce_kernel(const float* __restrict__ partial, TOut* __restrict__ C, in
   }  // group loop
 }
 
+// Contiguous fast path (C is [batch * M, N] with ldc == N, N % 4 == 0): one 16-byte column group per
+// thread and no index arithmetic beyond the bias column.  All S partial loads are issued before the
+// first add (S is a template parameter, so they sit in registers); the adds keep the ascending
+// split order of the generic kernel, i.e. the result is bit-identical.
+template <typename TOut, int S>
+__global__ void __launch_bounds__(256)
+splitk_reduce_flat_kernel(const float4* __restrict__ partial, TOut* __restrict__ C,
+                          long long per_split4, long long total4, int n4,
+                          const TOut* __restrict__ bias, int relu) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total4;
+       i += (long long)gridDim.x * 256) {
+    float4 v[S];
+#pragma unroll
+    for (int s = 0; s < S; ++s) v[s] = __ldcg(partial + i + s * per_split4);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      acc[0] += v[s].x;
+      acc[1] += v[s].y;
+      acc[2] += v[s].z;
+      acc[3] += v[s].w;
+    }
+    if (bias != nullptr) {
+      const int col = (int)(i % n4) * 4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[j] += ld_as_float(bias + col + j);
+        if (relu) acc[j] = acc[j] > 0.f ? acc[j] : 0.f;
+      }
+    }
+    if (sizeof(TOut) == 4) {
+      reinterpret_cast<float4*>(C)[i] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    } else {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(acc[0], acc[1]);
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(acc[2], acc[3]);
+      reinterpret_cast<uint2*>(C)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo),
+                                                  *reinterpret_cast<const uint32_t*>(&hi));
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host side
 
 // Operand description: row-major matrix [rows, cols] per batch, leading dimension ld (elements).
@@ -1155,7 +1198,9 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     }
     cfg.attrs = attr;
     cfg.numAttrs = na;
+    void* ktok = kernel_times_enabled() ? kernel_times_begin(stream) : nullptr;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ma, mb, mc, mf, static_cast<TOut*>(g.c), s);
+    if (ktok) kernel_times_end(ktok, stream, reinterpret_cast<const void*>(kern));
     if (e != cudaSuccess) {
       set_last_error("gemm_tcgen05 launch: %s", cudaGetErrorString(e));
       cudaGetLastError();
@@ -1189,11 +1234,48 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl && !prof ? 1 : 0;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<TOut>,
-                                       static_cast<const float*>(s.partial), static_cast<TOut*>(g.c),
-                                       splits, (long long)g.batch, s.M, s.N, s.ldc,
-                                       (long long)s.strideC, static_cast<const TOut*>(g.bias),
-                                       g.relu ? 1 : 0);
+    static const bool generic_only = getenv("B200TF_SPLITK_REDUCE_GENERIC") != nullptr;
+    const bool flat = !generic_only && (s.N & 3) == 0 && s.ldc == s.N &&
+                      (g.batch == 1 || (long long)s.strideC == (long long)s.M * s.N) &&
+                      splits >= 2 && splits <= 8 &&
+                      (reinterpret_cast<uintptr_t>(s.partial) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(g.c) & 15) == 0;
+    cudaError_t e;
+    void* ktok = kernel_times_enabled() ? kernel_times_begin(stream) : nullptr;
+    if (ktok) cfg.numAttrs = 0;
+    if (flat) {
+      const long long total4 = g.batch * (long long)s.M * (s.N / 4);
+      const float4* p4 = reinterpret_cast<const float4*>(s.partial);
+      TOut* c = static_cast<TOut*>(g.c);
+      const TOut* bias = static_cast<const TOut*>(g.bias);
+      const int relu = g.relu ? 1 : 0, n4 = s.N / 4;
+      switch (splits) {
+#define B200_SPLITK_FLAT(S_)                                                                   \
+  case S_:                                                                                     \
+    e = cudaLaunchKernelEx(&cfg, splitk_reduce_flat_kernel<TOut, S_>, p4, c, total4, total4, \
+                           n4, bias, relu);                                                    \
+    break;
+        B200_SPLITK_FLAT(2)
+        B200_SPLITK_FLAT(3)
+        B200_SPLITK_FLAT(4)
+        B200_SPLITK_FLAT(5)
+        B200_SPLITK_FLAT(6)
+        B200_SPLITK_FLAT(7)
+        default:
+        B200_SPLITK_FLAT(8)
+#undef B200_SPLITK_FLAT
+      }
+    } else {
+      e = cudaLaunchKernelEx(&cfg, splitk_reduce_kernel<TOut>,
+                             static_cast<const float*>(s.partial), static_cast<TOut*>(g.c),
+                             splits, (long long)g.batch, s.M, s.N, s.ldc,
+                             (long long)s.strideC, static_cast<const TOut*>(g.bias),
+                             g.relu ? 1 : 0);
+    }
+    if (ktok)
+      kernel_times_end(ktok, stream,
+                       flat ? reinterpret_cast<const void*>(splitk_reduce_flat_kernel<TOut, 4>)
+                            : reinterpret_cast<const void*>(splitk_reduce_kernel<TOut>));
     if (e != cudaSuccess) {
       set_last_error("splitk_reduce launch: %s", cudaGetErrorString(e));
       cudaGetLastError();

@@ -110,40 +110,128 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict
   }
 }
 
-// Skinny GEMM for N <= 32 (e.g. the 10-class logits layer and its weight gradient): one warp per
-// output row, lanes stride over K, N accumulators per lane, shuffle reduction at the end.  The
-// 64x64-tile kernel above would put such a problem on a handful of CTAs.
+// Skinny GEMM for N <= 32 (the 10-class logits layer, its weight gradient): the problem is a few MB
+// and a few MFLOP, so what matters is how many independent loads are in flight, not FLOPs.  Two
+// thread maps, both with the K range of a row split over several warps of the CTA, four k steps
+// unrolled (independent loads) and a fixed-order merge through shared memory (reproducible):
+//   A stored [M, K] (K contiguous):  lanes stride over k (coalesced), 2 rows x 4 K-splits per CTA,
+//                                    lanes folded by shuffles;
+//   A stored [K, M] (M contiguous):  lanes are 32 consecutive rows (coalesced), 8 K-splits per CTA,
+//                                    B[k, :] is the same address for the whole warp (broadcast).
+// The 64x64-tile kernel above would put such a problem on a handful of CTAs.
 template <typename T, int NMAX>
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int M, int N,
                    int K, long long lda, long long ldb, long long ldc, bool a_mn, bool b_mn) {
   pdl_prologue();
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (row >= M) return;
+  // B is staged per K chunk as Bs[k][NMAX (+4 pad)] fp32, zero filled past N / K: the inner loops
+  // are 16-byte shared loads (broadcast, or conflict-free thanks to the pad) and plain FMAs, with
+  // no layout or bounds predicate left in them.
+  constexpr int KC = NMAX <= 16 ? 512 : 256;
+  constexpr int LDB = NMAX + 4;
+  constexpr int kRed = 8 * NMAX * 33;
+  __shared__ __align__(16) float sm[KC * LDB > kRed ? KC * LDB : kRed];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float acc[NMAX];
 #pragma unroll
   for (int j = 0; j < NMAX; ++j) acc[j] = 0.f;
-  for (int k = lane; k < K; k += 32) {
-    const float a = to_f32<T>(a_mn ? A[(long long)k * lda + row] : A[(long long)row * lda + k]);
+  const int wr = warp >> 2, wq = warp & 3;  // K-major A: 2 rows x 4 K-splits
+  const int row = a_mn ? blockIdx.x * 32 + lane : blockIdx.x * 2 + wr;
+  const bool ok = row < M;
+  for (int kc = 0; kc < K; kc += KC) {
+    __syncthreads();  // the previous chunk's readers are done
+    for (int i = threadIdx.x; i < KC * NMAX; i += 256) {
+      const int k = b_mn ? i / NMAX : i % KC, j = b_mn ? i % NMAX : i / KC;
+      float v = 0.f;
+      if (kc + k < K && j < N)
+        v = to_f32<T>(b_mn ? B[(long long)(kc + k) * ldb + j] : B[(long long)j * ldb + kc + k]);
+      sm[k * LDB + j] = v;
+    }
+    __syncthreads();
+    if (!a_mn) {
+      // lane owns k = kc + wq * (KC / 4) + lane + 32 u: coalesced, KC / 128 loads in flight
+      constexpr int U = KC / 128;
+      const int kb = wq * (KC / 4) + lane;
+      float a[U];
 #pragma unroll
-    for (int j = 0; j < NMAX; ++j)
-      if (j < N)
-        acc[j] = fmaf(a, to_f32<T>(b_mn ? B[(long long)k * ldb + j] : B[(long long)j * ldb + k]),
-                      acc[j]);
+      for (int u = 0; u < U; ++u)
+        a[u] = ok && kc + kb + 32 * u < K ? to_f32<T>(A[(long long)row * lda + kc + kb + 32 * u]) : 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float4* bp = reinterpret_cast<const float4*>(sm + (kb + 32 * u) * LDB);
+#pragma unroll
+        for (int q = 0; q < NMAX / 4; ++q) {
+          const float4 bv = bp[q];
+          acc[4 * q] = fmaf(a[u], bv.x, acc[4 * q]);
+          acc[4 * q + 1] = fmaf(a[u], bv.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(a[u], bv.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(a[u], bv.w, acc[4 * q + 3]);
+        }
+      }
+    } else {
+      // lane = row (coalesced along M), warp w owns k = kc + w + 8 i; 8 A loads in flight
+      constexpr int U = 8;
+      for (int k0 = warp; k0 < KC; k0 += 8 * U) {
+        float a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          a[u] = ok && kc + k0 + 8 * u < K ? to_f32<T>(A[(long long)(kc + k0 + 8 * u) * lda + row]) : 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float4* bp = reinterpret_cast<const float4*>(sm + (k0 + 8 * u) * LDB);
+#pragma unroll
+          for (int q = 0; q < NMAX / 4; ++q) {
+            const float4 bv = bp[q];
+            acc[4 * q] = fmaf(a[u], bv.x, acc[4 * q]);
+            acc[4 * q + 1] = fmaf(a[u], bv.y, acc[4 * q + 1]);
+            acc[4 * q + 2] = fmaf(a[u], bv.z, acc[4 * q + 2]);
+            acc[4 * q + 3] = fmaf(a[u], bv.w, acc[4 * q + 3]);
+          }
+        }
+      }
+    }
   }
+  __syncthreads();  // Bs is dead: the merge buffer red[8][NMAX][33] lives in the same bytes
+  float* red = sm;
+  if (!a_mn) {
 #pragma unroll
-  for (int j = 0; j < NMAX; ++j) {
-    float v = acc[j];
+    for (int j = 0; j < NMAX; ++j) {
+      float v = acc[j];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    if (lane == 0 && j < N) C[(long long)row * ldc + j] = from_f32<T>(v);
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[(warp * NMAX + j) * 33] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * NMAX) {
+      const int r = threadIdx.x / NMAX, j = threadIdx.x % NMAX;
+      const int orow = blockIdx.x * 2 + r;
+      if (orow < M && j < N) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v += red[((r * 4 + q) * NMAX + j) * 33];
+        C[(long long)orow * ldc + j] = from_f32<T>(v);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) red[(warp * NMAX + j) * 33 + lane] = acc[j];
+    __syncthreads();
+    for (int i = threadIdx.x; i < 32 * NMAX; i += 256) {
+      const int r = i / NMAX, j = i % NMAX;  // consecutive threads -> consecutive C elements
+      const int orow = blockIdx.x * 32 + r;
+      if (orow < M && j < N) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v += red[(q * NMAX + j) * 33 + r];
+        C[(long long)orow * ldc + j] = from_f32<T>(v);
+      }
+    }
   }
 }
 
 int gemm_simt(const GemmArgs& g, cudaStream_t stream) {
   if (g.batch == 1 && g.N <= 32 && g.K >= 64 && g.M >= 64) {
-    const unsigned grid = (unsigned)((g.M + 7) / 8);
+    const unsigned grid = g.a_mn_major ? (unsigned)((g.M + 31) / 32) : (unsigned)((g.M + 1) / 2);
 #define SKINNY(T, NMAX)                                                                      \
   launch_pdl(gemm_skinny_kernel<T, NMAX>, dim3(grid), dim3(256), 0, stream,                                      \
       static_cast<const T*>(g.a), static_cast<const T*>(g.b), static_cast<T*>(g.c), (int)g.M, \

@@ -49,6 +49,21 @@ __device__ __forceinline__ void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) {
   *p = __float2bfloat16_rn(v);
 }
 
+// Load batching.  ptxas schedules for register pressure and interleaves the adds with a batch of
+// independent 16-byte loads so that only ~3 stay in flight per thread (checked in SASS; neither
+// unrolling nor volatile asm changes it).  cp.async has no destination registers: a thread issues
+// its whole batch into a private shared-memory slot per load and waits once, i.e. one memory
+// latency per batch.  src_bytes = 0 zero-fills the slot (rows past the end contribute +0).
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                   static_cast<uint32_t>(__cvta_generic_to_shared(smem_dst))),
+               "l"(gsrc), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 // ================================================================== BiasAddGrad
 // Stage 1: block (32, 8).  Columns are processed in vectors of VEC elements (16 bytes when the
 // channel count allows).  W = channels / VEC vector-columns.  If W >= 32 a CTA owns 32
@@ -80,43 +95,49 @@ bias_grad_stage1(const T* __restrict__ g, float* __restrict__ partial, long long
   float acc[VEC];
 #pragma unroll
   for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+  __shared__ uint4 stage[VEC > 1 ? 8 : 1][256];
+  const int tid = y * 32 + x;
   if (active) {
-    long long r = r0 + y * fold + sub;
+    // Up to eight independent row loads in flight per thread (rows r, r + step, ...): with the
+    // plan's 8 rows per thread the whole chunk is ONE batch, i.e. one HBM latency.  Rows past the
+    // chunk contribute +0; the adds run in ascending row order whatever the batch size.
+    constexpr int U = 8;
     const long long step = 8 * fold;
-    if (VEC == 4 && sizeof(T) == 4) {
-      // four independent 16-byte row loads in flight per thread (rows r, r+step, r+2step, r+3step)
-      for (; r + 3 * step < r1; r += 4 * step) {
-        float4 v[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          v[u] = __ldg(reinterpret_cast<const float4*>(g + (r + u * step) * channels +
-                                                       (long long)cv * VEC));
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {  // same summation order as the scalar tail below
-          acc[0] += v[u].x;
-          acc[1 % VEC] += v[u].y;
-          acc[2 % VEC] += v[u].z;
-          acc[3 % VEC] += v[u].w;
-        }
-      }
-    }
-    for (; r < r1; r += step) {
-      const T* p = g + r * channels + (long long)cv * VEC;
+    for (long long r = r0 + y * fold + sub; r < r1; r += U * step) {
       if (VEC == 1) {
-        acc[0] += ldf<T>(p);
-      } else if (sizeof(T) == 4) {
-        const float4 v = __ldg(reinterpret_cast<const float4*>(p));
-        acc[0] += v.x;
-        acc[1 % VEC] += v.y;
-        acc[2 % VEC] += v.z;
-        acc[3 % VEC] += v.w;
-      } else {
-        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p));
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        float v[U];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          acc[2 * i] += __uint_as_float(w[i] << 16);
-          acc[2 * i + 1] += __uint_as_float(w[i] & 0xFFFF0000u);
+        for (int u = 0; u < U; ++u) {
+          const long long rr = r + u * step;
+          v[u] = rr < r1 ? ldf<T>(g + rr * channels + cv) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) acc[0] += v[u];
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long rr = r + u * step;
+          cp_async16_zfill(&stage[u][tid],
+                           g + (rr < r1 ? rr : r1 - 1) * channels + (long long)cv * VEC,
+                           rr < r1 ? 16 : 0);
+        }
+        cp_async_wait_all();
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[u] = stage[u][tid];  // own slots only: no CTA barrier
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          if (sizeof(T) == 4) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i % VEC] += __uint_as_float(w[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              acc[(2 * i) % VEC] += __uint_as_float(w[i] << 16);
+              acc[(2 * i + 1) % VEC] += __uint_as_float(w[i] & 0xFFFF0000u);
+            }
+          }
         }
       }
     }
@@ -150,20 +171,43 @@ bias_grad_stage1(const T* __restrict__ g, float* __restrict__ partial, long long
 #pragma unroll
   for (int j = 0; j < VEC; ++j) tot[j] = 0.f;
   if (sub == 0 && cv < W) {
-    // up to four partial rows in flight per thread (the loads are independent; only the adds
-    // are ordered), 16-byte loads when the row is vectorised
-#pragma unroll 4
-    for (int k = y; k < nchunks; k += 8) {
-      const float* src = partial + (long long)k * channels + (long long)cv * VEC;
-      if (VEC == 4) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(src));
-        tot[0] += v.x;
-        tot[1 % VEC] += v.y;
-        tot[2 % VEC] += v.z;
-        tot[3 % VEC] += v.w;
+    // eight partial rows in flight per thread (independent loads, ordered adds), 16-byte loads
+    // when the row is vectorised
+    constexpr int U2 = 8;
+    for (int k0 = y; k0 < nchunks; k0 += 8 * (VEC % 4 == 0 ? U2 / (VEC / 4 > 0 ? VEC / 4 : 1) : U2)) {
+      if (VEC % 4 == 0) {
+        constexpr int Q = VEC % 4 == 0 ? VEC / 4 : 1;  // 16-byte loads per partial row
+        constexpr int RB = U2 / Q;                       // partial rows per batch (8 slots)
+#pragma unroll
+        for (int u = 0; u < RB; ++u) {
+          const int k = k0 + 8 * u;
+          const float* src =
+              partial + (long long)(k < nchunks ? k : nchunks - 1) * channels + (long long)cv * VEC;
+#pragma unroll
+          for (int q = 0; q < Q; ++q)
+            cp_async16_zfill(&stage[u * Q + q][tid], src + 4 * q, k < nchunks ? 16 : 0);
+        }
+        cp_async_wait_all();
+#pragma unroll
+        for (int u = 0; u < RB; ++u)
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            const uint4 t = stage[u * Q + q][tid];
+            tot[(4 * q) % VEC] += __uint_as_float(t.x);
+            tot[(4 * q + 1) % VEC] += __uint_as_float(t.y);
+            tot[(4 * q + 2) % VEC] += __uint_as_float(t.z);
+            tot[(4 * q + 3) % VEC] += __uint_as_float(t.w);
+          }
       } else {
 #pragma unroll
-        for (int j = 0; j < VEC; ++j) tot[j] += __ldcg(src + j);
+        for (int u = 0; u < U2; ++u) {
+          const int k = k0 + 8 * u;
+          if (k < nchunks) {
+            const float* src = partial + (long long)k * channels + (long long)cv * VEC;
+#pragma unroll
+            for (int j = 0; j < VEC; ++j) tot[j] += __ldcg(src + j);
+          }
+        }
       }
     }
   }
@@ -210,23 +254,87 @@ static BiasGradPlan plan_bias_grad(int dtype, long long rows, long long channels
   const long long W = channels / p.vec;
   p.col_tiles = (int)((W + 31) / 32);
   const int fold = W < 32 ? (int)(32 / W) : 1;
-  // Enough CTAs to keep several MB of loads in flight (HBM latency x bandwidth) without making the
-  // ordered second stage long (it reads one partial row per chunk): ~4 CTAs per SM, each
-  // thread issuing one batch of four independent 16-byte loads.
-  static const int ctas_per_sm = [] {  // tuning knob (tools/op_bench.py sweeps it)
-    const char* v = getenv("B200TF_BIAS_GRAD_CTAS_PER_SM");
+  // Eight rows per thread = one batch of independent 16-byte loads (one HBM latency) per chunk,
+  // and a second stage of nchunks / 8 partial rows per thread, again one batch for <= 64 chunks.
+  // More rows than 256 such chunks: the chunks grow instead (the ordered second stage stays short).
+  // B200TF_BIAS_GRAD_ROWS_PER_THREAD is a tuning knob for tools/op_bench.py.
+  static const int rows_per_thread = [] {
+    const char* v = getenv("B200TF_BIAS_GRAD_ROWS_PER_THREAD");
     const int n = v ? atoi(v) : 0;
-    return n > 0 ? n : 4;
+    return n > 0 ? n : 8;
   }();
-  long long want = ((long long)ctas_per_sm * sm_count() + p.col_tiles - 1) / p.col_tiles;
-  long long max_chunks = (rows + 8LL * fold * 4 - 1) / (8LL * fold * 4);  // >= 4 rows per thread
-  if (max_chunks < 1) max_chunks = 1;
-  if (want > max_chunks) want = max_chunks;
-  if (want > 4096) want = 4096;
+  const long long chunk_rows = 8LL * fold * rows_per_thread;
+  long long want = (rows + chunk_rows - 1) / chunk_rows;
+  if (want > 256) want = 256;
   if (want < 1) want = 1;
   p.rows_per_chunk = (int)((rows + want - 1) / want);
   p.nchunks = (int)((rows + p.rows_per_chunk - 1) / p.rows_per_chunk);
   return p;
+}
+
+// ================================================================== BiasAddGrad, NCHW
+// The tensor is [batch][channels][image]; out[c] = sum over batch and image (BiasGradNCHW_SharedAtomics,
+// bias_op_gpu.cu.cc:140-188, which accumulates with atomics).  Here: one warp per (plane, chunk of
+// <= kNchwChunk contiguous elements) -- 16-byte loads when the image allows, lane-strided so a warp
+// reads 512 contiguous bytes per step -- folds with shuffles and writes one fp32 partial at
+// [c][n * chunks + k]; one CTA per channel then adds that channel's partials in index order.
+// Fixed association everywhere: bit-reproducible.
+constexpr int kNchwChunk = 4096;
+
+template <typename T, bool kVec>
+__global__ void __launch_bounds__(256)
+bias_grad_nchw_stage1(const T* __restrict__ g, float* __restrict__ partial, long long items,
+                      int channels, long long image, int chunks, long long per_channel) {
+  pdl_prologue();
+  constexpr int VEC = 16 / (int)sizeof(T);
+  const int lane = threadIdx.x & 31;
+  const long long item = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (item >= items) return;
+  const long long plane = item / chunks;
+  const int k = (int)(item - plane * chunks);
+  const long long n = plane / channels;
+  const int c = (int)(plane - n * channels);
+  const long long e0 = (long long)k * kNchwChunk;
+  long long e1 = e0 + kNchwChunk;
+  if (e1 > image) e1 = image;
+  const T* src = g + plane * image;
+  float acc = 0.f;
+  if (kVec) {
+    for (long long e = e0 + (long long)lane * VEC; e < e1; e += 32 * VEC) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + e));
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (sizeof(T) == 4) {
+          acc += __uint_as_float(w[i]);
+        } else {
+          acc += __uint_as_float(w[i] << 16);
+          acc += __uint_as_float(w[i] & 0xFFFF0000u);
+        }
+      }
+    }
+  } else {
+    for (long long e = e0 + lane; e < e1; e += 32) acc += ldf<T>(src + e);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) partial[(long long)c * per_channel + n * chunks + k] = acc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_grad_nchw_stage2(const float* __restrict__ partial, T* __restrict__ out, long long per_channel) {
+  pdl_prologue();
+  const float* src = partial + (long long)blockIdx.x * per_channel;
+  float acc = 0.f;
+  for (long long i = threadIdx.x; i < per_channel; i += 256) acc += src[i];
+  __shared__ float sm[256];
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) sm[threadIdx.x] += sm[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) stf<T>(out + blockIdx.x, sm[0]);
 }
 
 // ================================================================== flat BiasAddGrad (+ ReluGrad)
@@ -648,6 +756,75 @@ xent_warp_vec_kernel(const float* __restrict__ logits, const float* __restrict__
   }  // row loop
 }
 
+// bf16, cols % 8 == 0, cols <= 256 * NV: 16-byte loads (8 elements), the row of logits and labels in
+// registers as fp32; same arithmetic as xent_warp_kernel<bf16> (fp32 math, one rounding per output).
+template <int NV>
+__global__ void __launch_bounds__(256)
+xent_warp_vec_bf16_kernel(const __nv_bfloat16* __restrict__ logits,
+                          const __nv_bfloat16* __restrict__ labels, __nv_bfloat16* __restrict__ loss,
+                          __nv_bfloat16* __restrict__ backprop, long long rows, int cols) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31;
+  const int nvec = cols >> 3;
+  for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows;
+       row += (long long)gridDim.x * 8) {
+    const uint4* x = reinterpret_cast<const uint4*>(logits + row * cols);
+    const uint4* l = reinterpret_cast<const uint4*>(labels + row * cols);
+    uint4* bp = reinterpret_cast<uint4*>(backprop + row * cols);
+    float v[NV][8], lab[NV][8];
+    float mx = -FLT_MAX;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        const uint4 a = __ldg(x + i), b = __ldg(l + i);
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          v[j][2 * q] = __uint_as_float(aw[q] << 16);
+          v[j][2 * q + 1] = __uint_as_float(aw[q] & 0xFFFF0000u);
+          lab[j][2 * q] = __uint_as_float(bw[q] << 16);
+          lab[j][2 * q + 1] = __uint_as_float(bw[q] & 0xFFFF0000u);
+          mx = fmaxf(mx, fmaxf(v[j][2 * q], v[j][2 * q + 1]));
+        }
+      }
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      if (lane + 32 * j < nvec) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          v[j][q] -= mx;
+          sum += expf(v[j][q]);
+        }
+      }
+    sum = warp_sum(sum);
+    const float ls = logf(sum);
+    float acc = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int i = lane + 32 * j;
+      if (i < nvec) {
+        uint32_t ow[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          acc += lab[j][2 * q] * (ls - v[j][2 * q]);
+          acc += lab[j][2 * q + 1] * (ls - v[j][2 * q + 1]);
+          const __nv_bfloat16 lo = __float2bfloat16_rn(expf(v[j][2 * q]) / sum - lab[j][2 * q]);
+          const __nv_bfloat16 hi =
+              __float2bfloat16_rn(expf(v[j][2 * q + 1]) / sum - lab[j][2 * q + 1]);
+          ow[q] = (uint32_t)__bfloat16_as_ushort(lo) | ((uint32_t)__bfloat16_as_ushort(hi) << 16);
+        }
+        bp[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) loss[row] = __float2bfloat16_rn(acc);
+  }
+}
+
 // ================================================================== ArgMax
 template <typename T>
 __device__ __forceinline__ T arg_lowest();
@@ -858,6 +1035,76 @@ size_t b200_bias_add_grad_workspace_bytes(int dtype, int64_t rows, int64_t chann
   return need;
 }
 
+size_t b200_bias_add_grad_nchw_workspace_bytes(int dtype, int64_t batch, int64_t channels,
+                                               int64_t image) {
+  (void)dtype;
+  if (batch <= 0 || channels <= 0 || image <= 0) return 0;
+  const int64_t chunks = (image + kNchwChunk - 1) / kNchwChunk;
+  return (size_t)batch * (size_t)channels * (size_t)chunks * sizeof(float);
+}
+
+int b200_bias_add_grad_nchw(int dtype, const void* out_backprop, void* out, int64_t batch,
+                            int64_t channels, int64_t image, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  if (batch < 0 || channels < 0 || image < 0 || channels > INT32_MAX) {
+    set_last_error("b200_bias_add_grad_nchw: bad shape [%lld, %lld, %lld]", (long long)batch,
+                   (long long)channels, (long long)image);
+    return B200_INVALID_ARGUMENT;
+  }
+  if (dtype != B200_DT_FLOAT && dtype != B200_DT_BFLOAT16) {
+    set_last_error("b200_bias_add_grad_nchw: unsupported dtype %d", dtype);
+    return B200_UNIMPLEMENTED;
+  }
+  if (channels == 0) return B200_OK;
+  const size_t esize = dtype == B200_DT_FLOAT ? 4 : 2;
+  if (batch == 0 || image == 0)  // sum over nothing = 0 (bias_op.cc:206-209 zero-fills)
+    return b200_memset_async(out, 0, (size_t)channels * esize, stream);
+  int rc = require_device("b200_bias_add_grad_nchw");
+  if (rc) return rc;
+  const size_t need = b200_bias_add_grad_nchw_workspace_bytes(dtype, batch, channels, image);
+  if (!workspace || workspace_bytes < need) {
+    set_last_error("b200_bias_add_grad_nchw: workspace too small (%zu < %zu bytes)",
+                   workspace_bytes, need);
+    return B200_INVALID_ARGUMENT;
+  }
+  cudaStream_t s = as_stream(stream);
+  const int chunks = (int)((image + kNchwChunk - 1) / kNchwChunk);
+  const long long items = (long long)batch * channels * chunks;
+  const long long blocks = (items + 7) / 8;
+  if (blocks > INT32_MAX) {
+    set_last_error("b200_bias_add_grad_nchw: too many planes");
+    return B200_INVALID_ARGUMENT;
+  }
+  float* partial = static_cast<float*>(workspace);
+  const int vec_elems = 16 / (int)esize;
+  // kNchwChunk is a multiple of the vector width, so chunk starts stay 16-byte aligned
+  const bool vec = image % vec_elems == 0 && aligned16(out_backprop);
+  const long long per_channel = (long long)batch * chunks;
+  if (dtype == B200_DT_FLOAT) {
+    const float* gp = static_cast<const float*>(out_backprop);
+    if (vec)
+      launch_pdl(bias_grad_nchw_stage1<float, true>, dim3((unsigned)blocks), dim3(256), 0, s, gp,
+                 partial, items, (int)channels, (long long)image, chunks, per_channel);
+    else
+      launch_pdl(bias_grad_nchw_stage1<float, false>, dim3((unsigned)blocks), dim3(256), 0, s, gp,
+                 partial, items, (int)channels, (long long)image, chunks, per_channel);
+    launch_pdl(bias_grad_nchw_stage2<float>, dim3((unsigned)channels), dim3(256), 0, s,
+               (const float*)partial, static_cast<float*>(out), per_channel);
+  } else {
+    const __nv_bfloat16* gp = static_cast<const __nv_bfloat16*>(out_backprop);
+    if (vec)
+      launch_pdl(bias_grad_nchw_stage1<__nv_bfloat16, true>, dim3((unsigned)blocks), dim3(256), 0,
+                 s, gp, partial, items, (int)channels, (long long)image, chunks, per_channel);
+    else
+      launch_pdl(bias_grad_nchw_stage1<__nv_bfloat16, false>, dim3((unsigned)blocks), dim3(256), 0,
+                 s, gp, partial, items, (int)channels, (long long)image, chunks, per_channel);
+    launch_pdl(bias_grad_nchw_stage2<__nv_bfloat16>, dim3((unsigned)channels), dim3(256), 0, s,
+               (const float*)partial, static_cast<__nv_bfloat16*>(out), per_channel);
+  }
+  note_launch(2);
+  return check_launch("b200_bias_add_grad_nchw");
+}
+
 size_t b200_relu_grad_bias_grad_workspace_bytes(int dtype, int64_t rows, int64_t channels) {
   return b200_bias_add_grad_workspace_bytes(dtype, rows, channels);
 }
@@ -1058,7 +1305,21 @@ int b200_softmax_xent_scaled(int dtype, const void* logits, const void* labels, 
           static_cast<const float*>(logits), static_cast<const float*>(labels),
           static_cast<float*>(loss), static_cast<float*>(backprop), (int)cols, sc);
   } else if (dtype == B200_DT_BFLOAT16) {
-    if (cols <= 1024)
+    const bool vec = cols % 8 == 0 && cols <= 1024 && aligned16(logits) && aligned16(labels) &&
+                     aligned16(backprop);
+    const __nv_bfloat16* xl = static_cast<const __nv_bfloat16*>(logits);
+    const __nv_bfloat16* ll = static_cast<const __nv_bfloat16*>(labels);
+    __nv_bfloat16* lo = static_cast<__nv_bfloat16*>(loss);
+    __nv_bfloat16* bo = static_cast<__nv_bfloat16*>(backprop);
+    unsigned wg = (unsigned)((rows + 7) / 8);
+    if (wg > 8u * (unsigned)sm_count()) wg = 8u * (unsigned)sm_count();
+    if (vec && cols <= 256)
+      launch_pdl(xent_warp_vec_bf16_kernel<1>, dim3(wg), dim3(256), 0, s, xl, ll, lo, bo, rows, (int)cols);
+    else if (vec && cols <= 512)
+      launch_pdl(xent_warp_vec_bf16_kernel<2>, dim3(wg), dim3(256), 0, s, xl, ll, lo, bo, rows, (int)cols);
+    else if (vec)
+      launch_pdl(xent_warp_vec_bf16_kernel<4>, dim3(wg), dim3(256), 0, s, xl, ll, lo, bo, rows, (int)cols);
+    else if (cols <= 1024)
       launch_pdl(xent_warp_kernel<__nv_bfloat16>, dim3((unsigned)((rows + 7) / 8)), dim3(256), 0, s, 
           static_cast<const __nv_bfloat16*>(logits), static_cast<const __nv_bfloat16*>(labels),
           static_cast<__nv_bfloat16*>(loss), static_cast<__nv_bfloat16*>(backprop), rows,

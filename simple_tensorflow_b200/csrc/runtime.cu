@@ -3,7 +3,9 @@
 // Mirrors the members of perftools::gputools::Stream / StreamExecutor that the reference's GPU
 // device and kernels use (tensorflow/stream_executor/stream.h:116,189,214,1482-1531,1591;
 // stream_executor_pimpl.h:110,191,226-268).
+#include <algorithm>
 #include <atomic>
+#include <map>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -126,6 +128,72 @@ void profile_gemm_launch_begin(cudaStream_t stream) {
   g_prof.pending_start = prof_event();
   cudaEventRecord(g_prof.pending_start, stream);
 }
+// ---- B200TF_KERNEL_TIMES=1: per-kernel in-stream times (see b200_internal.h)
+namespace {
+struct KernelTimes {
+  std::mutex mu;
+  std::vector<cudaEvent_t> pool;
+  struct Rec { cudaEvent_t a, b; const void* fn; };
+  std::vector<Rec> recs;
+  void dump() {
+    std::lock_guard<std::mutex> l(mu);
+    if (recs.empty()) return;
+    cudaDeviceSynchronize();
+    struct Tot { double us = 0; long n = 0; };
+    std::map<const void*, Tot> tot;
+    double all = 0;
+    for (auto& r : recs) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+        tot[r.fn].us += ms * 1e3;
+        tot[r.fn].n += 1;
+        all += ms * 1e3;
+      }
+    }
+    std::vector<std::pair<double, const void*>> order;
+    for (auto& kv : tot) order.push_back({kv.second.us, kv.first});
+    std::sort(order.begin(), order.end(), [](auto& x, auto& y) { return x.first > y.first; });
+    fprintf(stderr, "[b200 kernel times] %zu launches, %.1f us bracketed in total\n", recs.size(), all);
+    for (auto& o : order) {
+      const char* name = nullptr;
+      if (cudaFuncGetName(&name, o.second) != cudaSuccess || !name) name = "?";
+      const Tot& t = tot[o.second];
+      fprintf(stderr, "  %10.1f us  %6ld x %8.2f us  %5.1f%%  %.110s\n", t.us, t.n, t.us / t.n,
+              100.0 * t.us / all, name);
+    }
+    cudaGetLastError();
+    recs.clear();
+  }
+};
+KernelTimes& kernel_times() {
+  static KernelTimes* k = [] {
+    KernelTimes* p = new KernelTimes();
+    atexit([] { kernel_times().dump(); });
+    return p;
+  }();
+  return *k;
+}
+}  // namespace
+bool kernel_times_enabled() {
+  static const bool on = getenv("B200TF_KERNEL_TIMES") != nullptr;
+  return on;
+}
+void* kernel_times_begin(cudaStream_t stream) {
+  (void)kernel_times();
+  cudaEvent_t a = nullptr;
+  cudaEventCreate(&a);
+  cudaEventRecord(a, stream);
+  return a;
+}
+void kernel_times_end(void* token, cudaStream_t stream, const void* kernel) {
+  KernelTimes& k = kernel_times();
+  cudaEvent_t b = nullptr;
+  cudaEventCreate(&b);
+  cudaEventRecord(b, stream);
+  std::lock_guard<std::mutex> l(k.mu);
+  if (k.recs.size() < (1u << 20)) k.recs.push_back({static_cast<cudaEvent_t>(token), b, kernel});
+}
+
 bool pdl_enabled() {
   static const bool on = getenv("B200TF_NO_PDL") == nullptr;
   return on;
@@ -242,7 +310,9 @@ int b200_set_matmul_precision(int mode) {
 }
 int b200_get_matmul_precision(void) { return g_matmul_precision.load(); }
 
-int b200_profile_active(void) { return g_prof_on.load() ? 1 : 0; }
+int b200_profile_active(void) {
+  return (g_prof_on.load() || b200::kernel_times_enabled()) ? 1 : 0;
+}
 void b200_note_launches(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 void b200_note_collectives(uint64_t peer_launches, uint64_t nccl_calls) {
   g_peer_collectives.fetch_add(peer_launches, std::memory_order_relaxed);

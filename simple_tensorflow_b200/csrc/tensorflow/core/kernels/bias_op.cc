@@ -1,5 +1,7 @@
-// BiasAdd / BiasAddGrad for DEVICE_GPU on B200 (NHWC-native; data_format NCHW -- GPU-only in the
-// reference too, bias_op.cc:242-299 -- transposes 4-D activations in and out).
+// BiasAdd / BiasAddGrad for DEVICE_GPU on B200.  Both layouts are native: NHWC streams [rows, C];
+// data_format NCHW (GPU-only in the reference too, bias_op.cc:242-299) streams [batch, C, H * W]
+// planes through b200_bias_add_nchw / b200_bias_add_grad_nchw, with the reference's dimension
+// rule (GetBiasValueDims, bias_op.cc:127-151: channel = dims - 3, batch = everything before).
 // Validation follows BiasOp::Compute (core/kernels/bias_op.cc:62-117) and BiasGradOp::Compute
 // (:185-227); launches replace BiasGPU / BiasGradGPU (bias_op_gpu.cu.cc:69-88,189-242).
 #include "tensorflow/core/kernels/gpu_kernel_util.h"
@@ -18,6 +20,15 @@ static Status ReadFormat(OpKernelConstruction* ctx, bool* nchw) {
   return Status::OK();
 }
 
+// GetBiasValueDims for FORMAT_NCHW (bias_op.cc:140-150): [batch dims..., C, H, W]
+static void NchwDims(const Tensor& t, int64* batch, int64* channels, int64* image) {
+  const int cd = t.dims() - 3;
+  *batch = 1;
+  for (int i = 0; i < cd; ++i) *batch *= t.dim_size(i);
+  *channels = t.dim_size(cd);
+  *image = t.dim_size(cd + 1) * t.dim_size(cd + 2);
+}
+
 template <typename T>
 class BiasOp : public OpKernel {
  public:
@@ -32,24 +43,20 @@ class BiasOp : public OpKernel {
                                         input.shape().DebugString()));
     OP_REQUIRES(ctx, TensorShapeUtils::IsVector(bias.shape()),
                 errors::InvalidArgument("Biases must be 1D: ", bias.shape().DebugString()));
-    if (nchw_ && input.dims() > 2) {  // channel = dimension 1
-      OP_REQUIRES(ctx, input.dims() == 4,
-                  errors::Unimplemented("NCHW BiasAdd on B200 takes 2-D or 4-D inputs"));
-      OP_REQUIRES(ctx, bias.dim_size(0) == input.dim_size(1),
+    if (nchw_ && input.dims() > 2) {
+      int64 batch, channels, image;
+      NchwDims(input, &batch, &channels, &image);
+      OP_REQUIRES(ctx, bias.dim_size(0) == channels,
                   errors::InvalidArgument("Must provide as many biases as the channel dimension "
                                           "of the input tensor: ", bias.shape().DebugString(),
-                                          " vs. ", input.shape().DebugString()));
+                                          " vs. ", channels, " in ", input.shape().DebugString()));
       Tensor* output = nullptr;
-      OP_REQUIRES_OK(ctx, ctx->allocate_output(0, input.shape(), &output));
+      OP_REQUIRES_OK(ctx, ctx->forward_input_or_allocate_output({0}, 0, input.shape(), &output));
       if (input.NumElements() == 0) return;
-      Tensor nhwc;
-      OP_REQUIRES_OK(ctx, NchwToNhwc<T>(ctx, input, &nhwc));
-      const int64 channels = input.dim_size(1);
-      OP_REQUIRES_OK(ctx, FromAbi(b200_bias_add(AbiType<T>::v, nhwc.raw_data(), bias.raw_data(),
-                                                nhwc.raw_data(), nhwc.NumElements() / channels,
-                                                channels, GetCudaStream(ctx)),
+      OP_REQUIRES_OK(ctx, FromAbi(b200_bias_add_nchw(AbiType<T>::v, input.raw_data(),
+                                                     bias.raw_data(), output->raw_data(), batch,
+                                                     channels, image, GetCudaStream(ctx)),
                                   "BiasAdd"));
-      OP_REQUIRES_OK(ctx, NhwcToNchw<T>(ctx, nhwc, output));
       return;
     }
     const int64 channels = input.dim_size(input.dims() - 1);
@@ -82,19 +89,21 @@ class BiasGradOp : public OpKernel {
                 errors::InvalidArgument("Input tensor must be at least 2D: ",
                                         g.shape().DebugString()));
     if (nchw_ && g.dims() > 2) {
-      OP_REQUIRES(ctx, g.dims() == 4,
-                  errors::Unimplemented("NCHW BiasAddGrad on B200 takes 2-D or 4-D inputs"));
-      if (g.NumElements() > 0) {
-        OP_REQUIRES_OK(ctx, NchwToNhwc<T>(ctx, ctx->input(0), &g));
-      } else {
-        Tensor* output = nullptr;
-        OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({g.dim_size(1)}), &output));
-        if (output->NumElements() > 0)
-          OP_REQUIRES_OK(ctx, FromAbi(b200_memset_async(output->raw_data(), 0, output->TotalBytes(),
-                                                        GetCudaStream(ctx)),
-                                      "BiasAddGrad"));
-        return;
-      }
+      int64 batch, channels, image;
+      NchwDims(g, &batch, &channels, &image);
+      Tensor* output = nullptr;
+      OP_REQUIRES_OK(ctx, ctx->allocate_output(0, TensorShape({channels}), &output));
+      if (channels == 0) return;
+      const size_t ws = b200_bias_add_grad_nchw_workspace_bytes(AbiType<T>::v, batch, channels, image);
+      Tensor scratch;
+      if (ws > 0)
+        OP_REQUIRES_OK(ctx, ctx->allocate_temp(DT_UINT8, TensorShape({(int64)ws}), &scratch));
+      OP_REQUIRES_OK(ctx, FromAbi(b200_bias_add_grad_nchw(AbiType<T>::v, g.raw_data(),
+                                                          output->raw_data(), batch, channels,
+                                                          image, ws ? scratch.raw_data() : nullptr,
+                                                          ws, GetCudaStream(ctx)),
+                                  "BiasAddGrad"));
+      return;
     }
     const int64 channels = g.dim_size(g.dims() - 1);
     Tensor* output = nullptr;

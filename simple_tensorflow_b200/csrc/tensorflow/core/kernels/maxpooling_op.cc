@@ -1,5 +1,7 @@
-// MaxPool / MaxPoolGrad for DEVICE_GPU on B200 (NHWC-native, spatial pooling; data_format NCHW
-// -- which the reference registers for GPU only, maxpooling_op.cc:341-404 -- transposes in and out).
+// MaxPool / MaxPoolGrad for DEVICE_GPU on B200 (spatial pooling).  Both layouts are native: an NCHW
+// tensor [N, C, H, W] (GPU-only in the reference, maxpooling_op.cc:341-404) IS the NHWC tensor
+// [N * C, H, W, 1], so data_format NCHW runs the same kernels with batch = N * C and depth 1 --
+// no layout change, loads coalesced along W.
 // Parameter checks follow MaxPoolingOp / PoolParameters (core/kernels/pooling_ops_common.h:73-130,
 // pooling_ops_common.cc:31-90) and MaxPoolingGradOp (core/kernels/maxpooling_op.cc:230-306).
 #include "tensorflow/core/kernels/gpu_kernel_util.h"
@@ -33,8 +35,9 @@ struct PoolAttrs {
     if (ksize[0] != 1 || stride[0] != 1)
       return errors::Unimplemented("Pooling is not yet supported on the batch dimension.");
     if (ksize[3] != 1 || stride[3] != 1)
-      return errors::Unimplemented("Depthwise max pooling is outside the B200 hot path "
-                                   "(pooling_ops_common.cc:54-57 allows spatial OR depth pooling)");
+      // same answer as the reference on a GPU device (pooling_ops_common.cc:80-86)
+      return errors::Unimplemented("Depthwise max pooling is currently only implemented for CPU "
+                                   "devices.");
     return Status::OK();
   }
 };
@@ -75,21 +78,15 @@ class MaxPoolingOp : public OpKernel {
     OP_REQUIRES_OK(context, context->allocate_output(
                                 0, attrs_.nchw ? NhwcToNchwShape(out_nhwc) : out_nhwc, &result));
     if (result->NumElements() == 0) return;
-    Tensor pooled_nhwc;
-    Tensor* output = result;
-    if (attrs_.nchw) {
-      OP_REQUIRES_OK(context, NchwToNhwc<T>(context, context->input(0), &tensor_in));
-      OP_REQUIRES_OK(context, context->allocate_temp(result->dtype(), out_nhwc, &pooled_nhwc));
-      output = &pooled_nhwc;
-    }
+    const int64 batch = attrs_.nchw ? d.batch * d.depth : d.batch;
+    const int64 depth = attrs_.nchw ? 1 : d.depth;
     OP_REQUIRES_OK(context,
-                   FromAbi(b200_max_pool(AbiType<T>::v, tensor_in.raw_data(), output->raw_data(),
-                                         d.batch, d.rows, d.cols, d.depth, d.out_rows, d.out_cols,
+                   FromAbi(b200_max_pool(AbiType<T>::v, tensor_in.raw_data(), result->raw_data(),
+                                         batch, d.rows, d.cols, depth, d.out_rows, d.out_cols,
                                          attrs_.ksize[1], attrs_.ksize[2], attrs_.stride[1],
                                          attrs_.stride[2], (int)d.pad_rows, (int)d.pad_cols,
                                          GetCudaStream(context)),
                            "MaxPool"));
-    if (attrs_.nchw) OP_REQUIRES_OK(context, NhwcToNchw<T>(context, pooled_nhwc, result));
   }
 
  private:
@@ -125,25 +122,15 @@ class MaxPoolingGradOp : public OpKernel {
     Tensor* result = nullptr;
     OP_REQUIRES_OK(context, context->allocate_output(0, tensor_in.shape(), &result));
     if (result->NumElements() == 0) return;
-    Tensor dx_nhwc;
-    Tensor* output = result;
-    if (attrs_.nchw) {
-      OP_REQUIRES_OK(context, NchwToNhwc<T>(context, context->input(0), &tensor_in));
-      OP_REQUIRES_OK(context, NchwToNhwc<T>(context, context->input(2), &out_backprop));
-      OP_REQUIRES_OK(context, context->allocate_temp(result->dtype(), in_nhwc, &dx_nhwc));
-      output = &dx_nhwc;
-    }
+    const int64 batch = attrs_.nchw ? d.batch * d.depth : d.batch;
+    const int64 depth = attrs_.nchw ? 1 : d.depth;
     OP_REQUIRES_OK(context, FromAbi(b200_max_pool_grad(
-                                        AbiType<T>::v, tensor_in.raw_data(),
-                                        attrs_.nchw ? nullptr : tensor_out.raw_data(),  // unused by the kernel
-                                       
-                                        out_backprop.raw_data(), output->raw_data(), d.batch,
-                                        d.rows, d.cols, d.depth, d.out_rows, d.out_cols,
-                                        attrs_.ksize[1], attrs_.ksize[2], attrs_.stride[1],
-                                        attrs_.stride[2], (int)d.pad_rows, (int)d.pad_cols,
-                                        GetCudaStream(context)),
+                                        AbiType<T>::v, tensor_in.raw_data(), tensor_out.raw_data(),
+                                        out_backprop.raw_data(), result->raw_data(), batch, d.rows,
+                                        d.cols, depth, d.out_rows, d.out_cols, attrs_.ksize[1],
+                                        attrs_.ksize[2], attrs_.stride[1], attrs_.stride[2],
+                                        (int)d.pad_rows, (int)d.pad_cols, GetCudaStream(context)),
                                     "MaxPoolGrad"));
-    if (attrs_.nchw) OP_REQUIRES_OK(context, NhwcToNchw<T>(context, dx_nhwc, result));
   }
 
  private:

@@ -425,7 +425,8 @@ def _bias_add_grad(op, grad):
     fmt = op.attrs.get("data_format", "NHWC")
     g = op.graph.create_op("BiasAddGrad", [grad], {"T": ("type", grad.dtype), "data_format": fmt},
                            "BiasAddGrad")
-    cdim = 1 if fmt == "NCHW" and _shape(grad) and len(_shape(grad)) > 2 else -1
+    # GetBiasValueDims (bias_op.cc:140-150): NCHW puts the channel third from last
+    cdim = -3 if fmt == "NCHW" and _shape(grad) and len(_shape(grad)) > 2 else -1
     return grad, _set_shape(g.outputs[0], (_shape(grad)[cdim],) if _shape(grad) else None)
 
 

@@ -128,6 +128,30 @@ def bias_add_grad(g, bf16=False):
     return host(out)
 
 
+def bias_add_nchw(x, b, bf16=False):
+    """x: [batch dims..., C, H, W] (GetBiasValueDims, bias_op.cc:140-150)."""
+    c, image = x.shape[-3], x.shape[-2] * x.shape[-1]
+    batch = x.size // max(c * image, 1)
+    dx, db = dev(x, bf16), dev(b, bf16)
+    out = torch.empty_like(dx)
+    call(lib().b200_bias_add_nchw, cdt(bf16), dx.data_ptr(), db.data_ptr(), out.data_ptr(), batch,
+         c, image, stream())
+    return host(out)
+
+
+def bias_add_grad_nchw(g, bf16=False):
+    L = lib()
+    c, image = g.shape[-3], g.shape[-2] * g.shape[-1]
+    batch = g.size // max(c * image, 1)
+    dg = dev(g, bf16)
+    out = empty((c,), tdt(bf16), fill=float("nan"))
+    nb = L.b200_bias_add_grad_nchw_workspace_bytes(cdt(bf16), batch, c, image)
+    w = ws(nb)
+    call(L.b200_bias_add_grad_nchw, cdt(bf16), dg.data_ptr(), out.data_ptr(), batch, c, image,
+         w.data_ptr(), nb, stream())
+    return host(out)
+
+
 def relu(x, bf16=False):
     dx = dev(x, bf16)
     out = torch.empty_like(dx)

@@ -56,6 +56,23 @@ def test_matmul_small_unaligned_exact_fp32(oracle, rng, m, n, k, ta, tb):
                                atol=1e-3)
 
 
+@pytest.mark.parametrize("m,n,k", [(512, 10, 1024), (1024, 10, 512), (100, 7, 65), (64, 30, 64),
+                                   (333, 17, 1000), (65, 1, 130)])
+@pytest.mark.parametrize("ta", [False, True])
+@pytest.mark.parametrize("tb", [False, True])
+def test_matmul_skinny_n(oracle, rng, m, n, k, ta, tb):
+    # N <= 32 (LeNet's 10-class layer and its weight gradient): the K-split CUDA-core kernel, both
+    # thread maps (A stored [M, K] / [K, M]); IEEE fp32 FMAs, so the bar is summation order only
+    a = rng.uniform(-1, 1, (k, m) if ta else (m, k)).astype(np.float32)
+    b = rng.uniform(-1, 1, (n, k) if tb else (k, n)).astype(np.float32)
+    got = au.matmul(a, b, ta, tb)
+    ref = oracle.matmul(a, b, ta, tb)
+    # B stored [K, N] with N % 4 != 0 cannot be a TMA operand: that is the CUDA-core path (exact
+    # fp32); B stored [N, K] may take the tensor path (TF32 tolerance)
+    assert au.rel_err(got, ref) < (TOL_TF32 if tb else 1e-5)
+    np.testing.assert_array_equal(got, au.matmul(a, b, ta, tb))
+
+
 def test_matmul_integer_inputs_exact(oracle, rng):
     # integers <= 2048 are exact in tf32 and their sums are exact in the fp32 accumulator
     a = rng.randint(-8, 9, (256, 192)).astype(np.float32)
@@ -181,6 +198,38 @@ def test_bias_add_bf16(oracle, rng):
     assert au.rel_err(au.bias_add_grad(x, bf16=True), oracle.bias_add_grad(x)) < TOL
 
 
+NCHW_SHAPES = [(4, 8, 5, 7), (3, 16, 8, 8), (2, 3, 80, 80), (5, 6, 4), (2, 3, 4, 12, 20),
+               (512, 64, 14, 14), (1, 1, 1, 1)]
+
+
+@pytest.mark.parametrize("shape", NCHW_SHAPES)
+def test_bias_add_nchw_native(rng, shape):
+    # bias_op_gpu.cu.cc:56-63: out[.., c, h, w] = in + bias[c]; channel = dims - 3
+    x = rng.uniform(-1, 1, shape).astype(np.float32)
+    b = rng.uniform(-1, 1, shape[-3]).astype(np.float32)
+    np.testing.assert_array_equal(au.bias_add_nchw(x, b), x + b[:, None, None])
+
+
+@pytest.mark.parametrize("shape", NCHW_SHAPES)
+def test_bias_add_grad_nchw_native(rng, shape):
+    g = rng.uniform(-1, 1, shape).astype(np.float32)
+    got = au.bias_add_grad_nchw(g)
+    axes = tuple(i for i in range(len(shape)) if i != len(shape) - 3)
+    ref = g.astype(np.float64).sum(axes)
+    assert got.shape == (shape[-3],)
+    assert au.rel_err(got, ref) < 1e-5
+    np.testing.assert_array_equal(got, au.bias_add_grad_nchw(g))  # ordered, no atomics
+
+
+def test_bias_nchw_bf16(oracle, rng):
+    x = oracle.truncate_to_bf16(rng.uniform(-1, 1, (6, 24, 9, 16)).astype(np.float32))
+    b = oracle.truncate_to_bf16(rng.uniform(-1, 1, 24).astype(np.float32))
+    assert au.rel_err(au.bias_add_nchw(x, b, bf16=True), x + b[:, None, None]) < TOL
+    assert au.rel_err(au.bias_add_grad_nchw(x, bf16=True), x.astype(np.float64).sum((0, 2, 3))) < TOL
+    y = oracle.truncate_to_bf16(rng.uniform(-1, 1, (2, 3, 5, 7)).astype(np.float32))  # scalar path
+    assert au.rel_err(au.bias_add_grad_nchw(y, bf16=True), y.astype(np.float64).sum((0, 2, 3))) < TOL
+
+
 # =============================================================================== Relu(+Grad)
 @pytest.mark.parametrize("n", [1, 3, 4, 1023, 4096 * 1024 + 3])
 def test_relu_and_grad(oracle, rng, n):
@@ -249,6 +298,20 @@ def test_xent_known_answers():
     np.testing.assert_allclose(bp, [[0.25, 0.25, 0.25, -0.75], [0.0321, -0.4129, -0.2632, 0.6439]],
                                rtol=1e-3, atol=1e-3)
     np.testing.assert_allclose(loss, [1.3862, 1.9401], rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("shape", [(4096, 1024), (33, 264), (17, 512), (64, 8), (9, 1000), (5, 1030),
+                                   (3, 2048)])
+def test_softmax_xent_bf16(oracle, rng, shape):
+    # vectorised (cols % 8 == 0, <= 1024), row-per-warp scalar and block kernels: fp32 math, one
+    # rounding to bf16 per output
+    x = oracle.truncate_to_bf16((rng.randn(*shape) * 2).astype(np.float32))
+    labels = np.zeros(shape, np.float32)
+    labels[np.arange(shape[0]), rng.randint(0, shape[1], shape[0])] = 1.0
+    loss, bp = au.softmax_xent(x, labels, bf16=True)
+    rloss, rbp = oracle.softmax_xent(x, labels)
+    assert au.rel_err(loss, rloss) < TOL
+    assert np.max(np.abs(bp - rbp)) < 1e-2  # |backprop| <= 1; bf16 keeps 8 bits
 
 
 def test_softmax_bf16(oracle, rng):
@@ -392,6 +455,11 @@ CONV_SHAPES = [
     ((3, 11, 9, 1), (5, 5, 1, 32), (2, 2), "SAME"),
     ((2, 8, 8, 4), (3, 3, 4, 96), (1, 1), "VALID"),     # 36 taps: two tap blocks
     ((2, 6, 7, 2), (7, 5, 2, 32), (1, 2), "SAME"),      # 70 taps: three tap blocks
+    # one input channel, unit stride: the lane-per-filter sliding-window kernels (conv_c1_*)
+    ((5, 13, 11, 1), (5, 5, 1, 64), (1, 1), "SAME"),    # two filter blocks, widths not multiples of S
+    ((3, 9, 16, 1), (3, 3, 1, 32), (1, 1), "VALID"),
+    ((2, 6, 5, 1), (5, 5, 1, 32), (1, 1), "VALID"),     # 2 x 1 output pixels
+    ((9, 7, 30, 1), (3, 3, 1, 96), (1, 1), "SAME"),     # fewer rows than warps
 ]
 
 
@@ -541,6 +609,26 @@ def test_conv2d_full_size_vs_oracle(oracle, rng):
     scale = float(np.sqrt(np.sum(dy.astype(np.float64) ** 2) * np.sum(y.astype(np.float64) ** 2)))
     assert abs(lhs - float(np.sum(dx.astype(np.float64) * x))) < 2e-3 * scale
     assert abs(lhs - float(np.sum(dw.astype(np.float64) * f))) < 2e-3 * scale
+
+
+def test_conv_c1_forward_matches_the_generic_first_layer_kernel_bit_for_bit(oracle, rng, monkeypatch):
+    # same taps in the same order with fp32 FMAs: the specialised kernel changes the schedule only
+    shape, fshape = (7, 28, 28, 1), (5, 5, 1, 32)
+    x = rng.rand(*shape).astype(np.float32) - 0.5
+    f = (rng.rand(*fshape).astype(np.float32) - 0.5) * 0.2
+    got = au.conv2d(x, f, (1, 1), "SAME", oracle)
+    monkeypatch.setenv("B200TF_CONV_NO_C1", "1")
+    # the knob is read once per process: the generic kernel runs in a child
+    import os, subprocess, sys, tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        np.save(os.path.join(tmp, "x.npy"), x)
+        np.save(os.path.join(tmp, "f.npy"), f)
+        code = ("import numpy as np, sys; sys.path.insert(0, 'tests'); import abi_util as au;"
+                "x = np.load(r'%s/x.npy'); f = np.load(r'%s/f.npy');"
+                "np.save(r'%s/y.npy', au.conv2d(x, f, (1, 1), 'SAME', None))" % (tmp, tmp, tmp))
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        subprocess.run([sys.executable, "-c", code], check=True, cwd=root)
+        np.testing.assert_array_equal(got, np.load(os.path.join(tmp, "y.npy")))
 
 
 def test_conv1_full_size_vs_oracle(oracle, rng):

@@ -343,8 +343,10 @@ def test_batch_matmul_gradients(oracle, rng, adj_x, adj_y):
 
 def test_nchw_graph_matches_nhwc_graph(rng):
     # data_format="NCHW" (GPU-only in the reference: conv_ops.cc:758-763, bias_op.cc:242-299,
-    # maxpooling_op.cc:341-404) transposes in and out of the NHWC-native kernels, so a NCHW
-    # conv -> bias -> relu -> pool block and its gradients are bit-identical to the NHWC ones
+    # maxpooling_op.cc:341-404): the convolution transposes in and out of the NHWC kernels, BiasAdd /
+    # BiasAddGrad / MaxPool(+Grad) run natively on the NCHW planes.  Same arithmetic per element, so
+    # a NCHW conv -> bias -> relu -> pool block matches the NHWC one bit for bit; only the bias
+    # gradient is summed in another (fixed) order
     B, H, W, C, K = 3, 12, 10, 32, 64
     x = rng.uniform(-1, 1, (B, H, W, C)).astype(np.float32)
     w = (rng.randn(3, 3, C, K) * 0.1).astype(np.float32)
@@ -373,8 +375,30 @@ def test_nchw_graph_matches_nhwc_graph(rng):
 
     ref, got = run("NHWC"), run("NCHW")
     assert ref[0].shape == (B, 3, 5, K)  # conv stride 2 along H, then the 2x2 pool
-    for r, g in zip(ref, got):
+    for r, g in zip(ref[:3], got[:3]):
         np.testing.assert_array_equal(r, g)
+    np.testing.assert_allclose(got[3], ref[3], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("shape", [(6, 5, 4), (2, 3, 4, 6, 10), (3, 8, 7, 9)])
+def test_nchw_bias_add_any_rank(rng, shape):
+    # GetBiasValueDims (bias_op.cc:140-150): channel = dims - 3, every dimension before it is batch
+    x = rng.uniform(-1, 1, shape).astype(np.float32)
+    b = rng.uniform(-1, 1, shape[-3]).astype(np.float32)
+    tf.reset_default_graph()
+    xp = tf.placeholder(tf.float32, list(shape))
+    bv = tf.Variable(b, name="b")
+    y = tf.bias_add(xp, bv, data_format="NCHW")
+    loss = tf.reduce_sum(tf.multiply(y, y))
+    gx, gb = tf.gradients(loss, [xp, bv])
+    with client.Session(tf.get_default_graph()) as sess:
+        sess.run(tf.global_variables_initializer())
+        yv, gxv, gbv = sess.run([y, gx, gb], {xp: x})
+    ref = x + b[:, None, None]
+    np.testing.assert_array_equal(yv, ref)
+    np.testing.assert_allclose(gxv, 2 * ref, rtol=1e-6)
+    axes = tuple(i for i in range(len(shape)) if i != len(shape) - 3)
+    np.testing.assert_allclose(gbv, (2 * ref.astype(np.float64)).sum(axes), rtol=1e-5, atol=1e-5)
 
 
 def test_reference_style_script_runs():

@@ -128,6 +128,23 @@ def main():
                 lambda s, st, m=m, nn=nn, k=k, ta=ta, tb=tb, dt=dt, ws=ws: L.b200_matmul(
                     dt, s[0].data_ptr(), s[1].data_ptr(), s[2].data_ptr(), m, nn, k, ta, tb,
                     s[3].data_ptr() if ws else None, ws, st), nsets=6)
+    # ---- BatchMatMul on the reference's own benchmark shapes (batch_matmul_op_test.cc:62-132:
+    # BM_BatchMatmul(B, M, K, N, adj_x, adj_y)), fp32 graph on the TF32 tensor path
+    for b, m, k, nn in ((1, 128, 1024, 1024), (8, 128, 1024, 1024), (32, 128, 1024, 1024),
+                        (8, 256, 256, 256), (32, 256, 256, 256), (8, 1024, 1024, 1024),
+                        (32, 1024, 1024, 1024), (8, 2048, 2048, 2048), (32, 10000, 200, 1),
+                        (32, 1, 200, 10000)):
+        add("BatchMatMul tf32 B%d %dx%dx%d (MxKxN)" % (b, m, k, nn), 2.0 * b * m * nn * k, "TFLOP/s",
+            lambda b=b, m=m, k=k, nn=nn: (t(b, m, k), t(b, k, nn), t(b, m, nn)),
+            lambda s, st, b=b, m=m, k=k, nn=nn: L.b200_batch_matmul(
+                F32, s[0].data_ptr(), s[1].data_ptr(), s[2].data_ptr(), b, m, nn, k, 0, 0, st), nsets=4)
+    wsb16 = L.b200_bias_add_grad_workspace_bytes(BF16, R, C)
+    add("BiasAddGrad bf16 [4096,1024]", n * 2 + C * 2, "GB/s",
+        lambda: (t(R, C, dtype=torch.bfloat16), t(C, dtype=torch.bfloat16), torch.empty(wsb16, device=dev, dtype=torch.uint8)),
+        lambda s, st: L.b200_bias_add_grad(BF16, s[0].data_ptr(), s[1].data_ptr(), R, C, s[2].data_ptr(), wsb16, st))
+    add("SoftmaxXent bf16 [4096,1024]", 3 * n * 2 + R * 2, "GB/s",
+        lambda: (t(R, C, dtype=torch.bfloat16), t(R, C, dtype=torch.bfloat16), t(R, dtype=torch.bfloat16), t(R, C, dtype=torch.bfloat16)),
+        lambda s, st: L.b200_softmax_xent(BF16, s[0].data_ptr(), s[1].data_ptr(), s[2].data_ptr(), s[3].data_ptr(), R, C, st))
     add("FusedMatMul tf32 fwd+bias+relu 4096x1024x1024", 2.0 * 4096 * 1024 * 1024, "TFLOP/s",
         lambda: (t(4096, 1024), t(1024, 1024), t(4096, 1024), t(1024)),
         lambda s, st: L.b200_fused_matmul(F32, s[0].data_ptr(), s[1].data_ptr(), s[2].data_ptr(), 4096, 1024, 1024, 0, 0,
