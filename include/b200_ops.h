@@ -240,6 +240,22 @@ B200_API int b200_max_pool_grad(int dtype, const void* orig_in, const void* orig
                                 int64_t in_w, int64_t channels, int64_t out_h, int64_t out_w,
                                 int window_h, int window_w, int stride_h, int stride_w,
                                 int pad_top, int pad_left, void* stream);
+/* MaxPoolGrad -> ReluGrad -> BiasAddGrad of a conv / bias / relu / pool block in one pass
+ * (maxpooling_op.cc:230-306 + relu_op.h:70-98 + bias_op.cc:171-227; the executor's
+ * `_MaxPoolGradReluGradBiasAddGrad` rewrite).  orig_in is the pool's input = the Relu output = the
+ * ReluGrad's features.  backprops = ReluGrad(MaxPoolGrad(orig_in, ., grad), orig_in), bias_grad =
+ * its sum over N, H, W (ordered, no atomics).  Returns B200_UNIMPLEMENTED when the windows do not
+ * tile the input or the channel count has no flat 16-byte mapping (workspace_bytes() == 0): the
+ * caller then runs b200_max_pool_grad and b200_relu_grad_bias_grad. */
+B200_API size_t b200_max_pool_grad_relu_bias_grad_workspace_bytes(
+    int dtype, int64_t batch, int64_t in_h, int64_t in_w, int64_t channels, int64_t out_h,
+    int64_t out_w, int window_h, int window_w, int stride_h, int stride_w, int pad_top, int pad_left);
+B200_API int b200_max_pool_grad_relu_bias_grad(
+    int dtype, const void* orig_in, const void* grad, void* backprops, void* bias_grad,
+    int64_t batch, int64_t in_h, int64_t in_w, int64_t channels, int64_t out_h, int64_t out_w,
+    int window_h, int window_w, int stride_h, int stride_w, int pad_top, int pad_left,
+    void* workspace, size_t workspace_bytes, void* stream);
+
 
 /* ------------------------------------------------------------------ Cast / ArgMax (bit-exact)
  * CastOp (core/kernels/cast_op.cc, cast_op.h:93-141): float->bfloat16 TRUNCATES the low 16 bits

@@ -101,6 +101,10 @@ SIGNATURES = {
                       + [c_void_p]),
     "b200_max_pool_grad": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p] + [c_int64] * 6
                            + [c_int] * 6 + [c_void_p]),
+    "b200_max_pool_grad_relu_bias_grad_workspace_bytes": (c_size_t, [c_int] + [c_int64] * 6 + [c_int] * 6),
+    "b200_max_pool_grad_relu_bias_grad": (c_int, [c_int, c_void_p, c_void_p, c_void_p, c_void_p] +
+                                          [c_int64] * 6 + [c_int] * 6 +
+                                          [c_void_p, c_size_t, c_void_p]),
     "b200_cast": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int64, c_void_p]),
     "b200_argmax": (c_int, [c_int, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "b200_conv2d_workspace_bytes": (c_size_t, [c_int, ctypes.POINTER(ConvGeometry), c_int]),

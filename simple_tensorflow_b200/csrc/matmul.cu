@@ -122,8 +122,14 @@ gemm_simt_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict
 template <typename T, int NMAX>
 __global__ void __launch_bounds__(256)
 gemm_skinny_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int M, int N,
-                   int K, long long lda, long long ldb, long long ldc, bool a_mn, bool b_mn) {
+                   int K, long long lda, long long ldb, long long ldc, bool a_mn, bool b_mn,
+                   long long strideA, long long strideB, long long strideC, bool c_t) {
   pdl_prologue();
+  // batch = blockIdx.y.  c_t: C is written transposed (element (row, j) at C[j * ldc + row]) --
+  // how a skinny-M product runs here as its transpose (C^T = B^T A^T).
+  A += (long long)blockIdx.y * strideA;
+  B += (long long)blockIdx.y * strideB;
+  C += (long long)blockIdx.y * strideC;
   // B is staged per K chunk as Bs[k][NMAX (+4 pad)] fp32, zero filled past N / K: the inner loops
   // are 16-byte shared loads (broadcast, or conflict-free thanks to the pad) and plain FMAs, with
   // no layout or bounds predicate left in them.
@@ -209,7 +215,7 @@ gemm_skinny_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restri
         float v = 0.f;
 #pragma unroll
         for (int q = 0; q < 4; ++q) v += red[((r * 4 + q) * NMAX + j) * 33];
-        C[(long long)orow * ldc + j] = from_f32<T>(v);
+        C[c_t ? (long long)j * ldc + orow : (long long)orow * ldc + j] = from_f32<T>(v);
       }
     }
   } else {
@@ -217,29 +223,139 @@ gemm_skinny_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restri
     for (int j = 0; j < NMAX; ++j) red[(warp * NMAX + j) * 33 + lane] = acc[j];
     __syncthreads();
     for (int i = threadIdx.x; i < 32 * NMAX; i += 256) {
-      const int r = i / NMAX, j = i % NMAX;  // consecutive threads -> consecutive C elements
+      // consecutive threads -> consecutive C elements in either orientation
+      const int r = c_t ? i % 32 : i / NMAX, j = c_t ? i / 32 : i % NMAX;
       const int orow = blockIdx.x * 32 + r;
       if (orow < M && j < N) {
         float v = 0.f;
 #pragma unroll
         for (int q = 0; q < 8; ++q) v += red[(q * NMAX + j) * 33 + r];
-        C[(long long)orow * ldc + j] = from_f32<T>(v);
+        C[c_t ? (long long)j * ldc + orow : (long long)orow * ldc + j] = from_f32<T>(v);
       }
     }
   }
 }
 
+// Matrix-vector products (N <= 4; vector-matrix ones run transposed): pure bandwidth, no staging.
+//   A stored [M, K]: one warp per row, lanes stride over K (coalesced), shuffle fold;
+//   A stored [K, M]: one thread per row (a warp reads 32 consecutive rows of every k), B[k, :] is a
+//                    broadcast load; eight k in flight.
+// Rows are grid-strided; blockIdx.y is the batch.  Fixed summation order (reproducible).
+template <typename T, int NV>
+__global__ void __launch_bounds__(256)
+gemv_kernel(const T* __restrict__ A, const T* __restrict__ B, T* __restrict__ C, int M, int N, int K,
+            long long lda, long long ldb, long long ldc, bool a_mn, bool b_mn, long long strideA,
+            long long strideB, long long strideC, bool c_t) {
+  pdl_prologue();
+  A += (long long)blockIdx.y * strideA;
+  B += (long long)blockIdx.y * strideB;
+  C += (long long)blockIdx.y * strideC;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  auto bval = [&](int k, int j) {
+    return to_f32<T>(b_mn ? B[(long long)k * ldb + j] : B[(long long)j * ldb + k]);
+  };
+  if (!a_mn) {
+    for (long long row = (long long)blockIdx.x * 8 + warp; row < M; row += (long long)gridDim.x * 8) {
+      const T* arow = A + row * lda;
+      float acc[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) acc[j] = 0.f;
+      constexpr int U = 8;
+      for (int k0 = lane; k0 < K; k0 += 32 * U) {
+        float a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = k0 + 32 * u < K ? to_f32<T>(arow[k0 + 32 * u]) : 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (k0 + 32 * u < K) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j)
+              if (j < N) acc[j] = fmaf(a[u], bval(k0 + 32 * u, j), acc[j]);
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        float v = acc[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0 && j < N)
+          C[c_t ? (long long)j * ldc + row : row * ldc + j] = from_f32<T>(v);
+      }
+    }
+  } else {
+    for (long long row = (long long)blockIdx.x * 256 + threadIdx.x; row < M;
+         row += (long long)gridDim.x * 256) {
+      float acc[NV];
+#pragma unroll
+      for (int j = 0; j < NV; ++j) acc[j] = 0.f;
+      constexpr int U = 8;
+      for (int k0 = 0; k0 < K; k0 += U) {
+        float a[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) a[u] = k0 + u < K ? to_f32<T>(A[(long long)(k0 + u) * lda + row]) : 0.f;
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (k0 + u < K) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j)
+              if (j < N) acc[j] = fmaf(a[u], bval(k0 + u, j), acc[j]);
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (j < N) C[c_t ? (long long)j * ldc + row : row * ldc + j] = from_f32<T>(acc[j]);
+    }
+  }
+}
+
 int gemm_simt(const GemmArgs& g, cudaStream_t stream) {
-  if (g.batch == 1 && g.N <= 32 && g.K >= 64 && g.M >= 64) {
-    const unsigned grid = g.a_mn_major ? (unsigned)((g.M + 31) / 32) : (unsigned)((g.M + 1) / 2);
-#define SKINNY(T, NMAX)                                                                      \
-  launch_pdl(gemm_skinny_kernel<T, NMAX>, dim3(grid), dim3(256), 0, stream,                                      \
-      static_cast<const T*>(g.a), static_cast<const T*>(g.b), static_cast<T*>(g.c), (int)g.M, \
-      (int)g.N, (int)g.K, g.lda, g.ldb, g.ldc, g.a_mn_major, g.b_mn_major)
+  // N <= 4 / M <= 4: matrix-vector and vector-matrix products (batch_matmul_op_test.cc:107-132);
+  // N <= 32: the skinny kernel (the 10-class layer).  A skinny-M problem runs as its transpose
+  // C^T[N, M] = B^T[N, K] A^T[K, M].
+  const bool gemv_n = g.N <= 4 && g.M >= 64;
+  const bool gemv_m = !gemv_n && g.M <= 4 && g.N >= 64;
+  const bool skinny_n = !gemv_n && !gemv_m && g.batch == 1 && g.N <= 32 && g.K >= 64 && g.M >= 64;
+  if ((gemv_n || gemv_m || skinny_n) && g.batch <= 65535) {
+    const void *pa = g.a, *pb = g.b;
+    long long M = g.M, N = g.N, lda = g.lda, ldb = g.ldb, sA = g.strideA, sB = g.strideB;
+    bool a_mn = g.a_mn_major, b_mn = g.b_mn_major;
+    if (gemv_m) {  // A' = B^T (stored as B), B' = A^T (stored as A)
+      pa = g.b; pb = g.a;
+      M = g.N; N = g.M;
+      lda = g.ldb; ldb = g.lda;
+      sA = g.strideB; sB = g.strideA;
+      a_mn = g.b_mn_major;   // B stored [K, N] = A' stored [K, M']
+      b_mn = g.a_mn_major;   // A stored [K, M] = B' stored [K, N']
+    }
+    if (gemv_n || gemv_m) {
+      const long long units = a_mn ? (M + 255) / 256 : (M + 7) / 8;
+      const long long cap = std::max<long long>(1, 16LL * sm_count() / g.batch);
+      const dim3 grid((unsigned)std::min(units, cap), (unsigned)g.batch);
+#define GEMV(T)                                                                                   \
+  launch_pdl(gemv_kernel<T, 4>, grid, dim3(256), 0, stream, static_cast<const T*>(pa),            \
+             static_cast<const T*>(pb), static_cast<T*>(g.c), (int)M, (int)N, (int)g.K, lda, ldb, \
+             g.ldc, a_mn, b_mn, sA, sB, g.strideC, gemv_m)
+      if (g.dtype == B200_DT_FLOAT) {
+        GEMV(float);
+      } else if (g.dtype == B200_DT_BFLOAT16) {
+        GEMV(__nv_bfloat16);
+      } else {
+        set_last_error("gemm_simt: unsupported dtype %d", g.dtype);
+        return B200_UNIMPLEMENTED;
+      }
+#undef GEMV
+      note_launch();
+      return check_launch("gemv");
+    }
+    const dim3 grid(a_mn ? (unsigned)((M + 31) / 32) : (unsigned)((M + 1) / 2), 1);
+#define SKINNY(T, NMAX)                                                                          \
+  launch_pdl(gemm_skinny_kernel<T, NMAX>, grid, dim3(256), 0, stream, static_cast<const T*>(pa), \
+             static_cast<const T*>(pb), static_cast<T*>(g.c), (int)M, (int)N, (int)g.K, lda,     \
+             ldb, g.ldc, a_mn, b_mn, sA, sB, g.strideC, false)
     if (g.dtype == B200_DT_FLOAT) {
-      if (g.N <= 16) SKINNY(float, 16); else SKINNY(float, 32);
+      if (N <= 16) SKINNY(float, 16); else SKINNY(float, 32);
     } else if (g.dtype == B200_DT_BFLOAT16) {
-      if (g.N <= 16) SKINNY(__nv_bfloat16, 16); else SKINNY(__nv_bfloat16, 32);
+      if (N <= 16) SKINNY(__nv_bfloat16, 16); else SKINNY(__nv_bfloat16, 32);
     } else {
       set_last_error("gemm_simt: unsupported dtype %d", g.dtype);
       return B200_UNIMPLEMENTED;
@@ -276,7 +392,11 @@ int gemm_dispatch(const GemmArgs& g, cudaStream_t stream) {
   const bool want_exact = g.dtype == B200_DT_FLOAT && b200_get_matmul_precision() == 1;
   // Tiny problems: a 128-row MMA tile would be mostly padding and launch-bound anyway.
   const bool tiny = g.M * g.N * g.K < 32LL * 32 * 32;
-  if (!want_exact && !tiny && gemm_tcgen05_supported(g) && driver().cuTensorMapEncodeTiled)
+  // matrix-vector / vector-matrix products: a 128-row MMA tile would be > 96 % padding; they are
+  // bandwidth problems for the K-split CUDA-core kernel (exact fp32)
+  const bool gemv_like = (g.N <= 4 && g.M >= 64) || (g.M <= 4 && g.N >= 64);
+  if (!want_exact && !tiny && !gemv_like && gemm_tcgen05_supported(g) &&
+      driver().cuTensorMapEncodeTiled)
     return gemm_tcgen05(g, stream);
   return gemm_simt(g, stream);
 }

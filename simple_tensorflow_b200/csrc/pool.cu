@@ -13,6 +13,7 @@
 // element the window's argmax is recomputed and the gradient added when it is this element.
 // No atomics, no zero-fill pass, deterministic order (ascending output index, as the reference's
 // `in_backprop[argmax] += grad` loop, maxpooling_op.cc:165-178).
+#include <atomic>
 #include <cfloat>
 #include <cuda_bf16.h>
 
@@ -218,6 +219,161 @@ max_pool_grad_disjoint_kernel(const T* __restrict__ in, const T* __restrict__ gr
     }
 }
 
+// MaxPoolGrad -> ReluGrad -> BiasAddGrad in one pass (the backward tail of a conv -> bias -> relu ->
+// pool block: LeNet's two, VGG's five).  The pool's input IS the Relu output, i.e. the `features`
+// of the ReluGrad, so one read of it decides both the window's winner and the relu mask:
+//   dx[cell]  = (cell is the window's first maximum) ? grad[window] : 0     (maxpooling_op.cc:124-144)
+//   dy[cell]  = features[cell] > 0 ? dx[cell] : dx[cell] * 0                (relu_op_functor.h:54-55)
+//   db[c]    += dy[cell]                                                     (bias_op.cc:210-226)
+// Unfused this is 115 + 154 MB of traffic for LeNet's pool1 (dx written, then read again with the
+// features); fused it is 115 MB.  Windows must tile the input (stride == window, no padding) and
+// the 16-byte channel vectors of a pixel must divide a warp (G = C / V in {1, 2, .., 32}), so a
+// thread meets one channel group only: the partial sums fold like flat_bias_grad_kernel's (shuffles,
+// shared memory, one partial row per CTA, ordered last-ticket pass; no atomics on the data).
+constexpr int kPoolFusedSlots = 32;
+__device__ unsigned int g_pool_fused_tickets[kPoolFusedSlots];
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+max_pool_grad_relu_bias_kernel(const T* __restrict__ in, const T* __restrict__ grad,
+                               T* __restrict__ dy, float* __restrict__ partial,
+                               T* __restrict__ bias_grad, PoolGeom g, long long total, int G,
+                               unsigned int* __restrict__ ticket) {
+  pdl_prologue();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float bsum[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) bsum[j] = 0.f;
+  // the grid stride is a multiple of G (256 is), so idx % G -- the channel group -- never changes
+  for (long long idx = (long long)blockIdx.x * 256 + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * 256) {
+    const int cv = (int)(idx % G);
+    long long r = idx / G;
+    const int ow = (int)(r % g.OW);
+    r /= g.OW;
+    const int oh = (int)(r % g.OH);
+    const int n = (int)(r / g.OH);
+    const int h0 = oh * g.sh, w0 = ow * g.sw;
+    const int h1 = min(h0 + g.wh, g.H), w1 = min(w0 + g.ww, g.W);
+    const long long ibase = ((long long)n * g.H * g.W) * g.C + (long long)cv * V;
+    float best[V], feat[V], gv[V];
+    int arg[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      best[j] = -FLT_MAX;
+      arg[j] = -1;
+    }
+    for (int h = h0; h < h1; ++h)
+      for (int w = w0; w < w1; ++w) {
+        float v[V];
+        PoolVec<T, V>::load(in + ibase + ((long long)h * g.W + w) * g.C, v);
+#pragma unroll
+        for (int j = 0; j < V; ++j)
+          if (best[j] < v[j] || arg[j] == -1) {  // first maximum wins
+            best[j] = v[j];
+            arg[j] = h * g.W + w;
+          }
+      }
+    PoolVec<T, V>::load(grad + idx * V, gv);
+    // the winner's feature value is `best`: only the winner can carry a non-zero gradient
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      feat[j] = best[j];
+      gv[j] = feat[j] > 0.f ? gv[j] : gv[j] * 0.f;
+      bsum[j] += gv[j];
+    }
+    for (int h = h0; h < h1; ++h)
+      for (int w = w0; w < w1; ++w) {
+        float o[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) o[j] = (arg[j] == h * g.W + w) ? gv[j] : 0.f;
+        PoolVec<T, V>::store(dy + ibase + ((long long)h * g.W + w) * g.C, o);
+      }
+  }
+  // ---- bias gradient: lanes with the same lane % G hold the same channel group
+  for (int off = G; off < 32; off <<= 1) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) bsum[j] += __shfl_xor_sync(0xffffffffu, bsum[j], off);
+  }
+  __shared__ float sm[8][32][V];
+  if (lane < G) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) sm[warp][lane][j] = bsum[j];
+  }
+  __syncthreads();
+  const int C = G * V;
+  if ((int)threadIdx.x < C) {
+    const int cg = threadIdx.x / V, j = threadIdx.x % V;
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += sm[w][cg][j];
+    partial[(long long)blockIdx.x * C + threadIdx.x] = t;
+    __threadfence();
+  }
+  __shared__ bool is_last;
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  // ordered final pass: thread (c, part) adds blocks part, part + P, ...; parts combined in order
+  const int P = 256 / C;  // >= 1 (C <= 256)
+  const int c = threadIdx.x % C, part = threadIdx.x / C;
+  float t = 0.f;
+  if (part < P) {
+    const int nb = (int)gridDim.x;
+    for (int b0 = part; b0 < nb; b0 += 8 * P) {
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int b = b0 + u * P;
+        v[u] = b < nb ? __ldcg(partial + (long long)b * C + c) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) t += v[u];
+    }
+  }
+  float* flat = &sm[0][0][0];  // 8 * 32 * V >= 256 floats
+  __syncthreads();
+  flat[threadIdx.x] = part < P ? t : 0.f;
+  __syncthreads();
+  if ((int)threadIdx.x < C) {
+    float tot = 0.f;
+    for (int q = 0; q < P; ++q) tot += flat[q * C + threadIdx.x];
+    if (sizeof(T) == 4)
+      reinterpret_cast<float*>(bias_grad)[threadIdx.x] = tot;
+    else
+      reinterpret_cast<__nv_bfloat16*>(bias_grad)[threadIdx.x] = __float2bfloat16_rn(tot);
+  }
+  if (threadIdx.x == 0) *ticket = 0;  // ready for the next launch that uses this slot
+}
+
+struct PoolFusedPlan {
+  bool ok;
+  int G, V, blocks;
+  long long total;
+};
+static PoolFusedPlan plan_pool_fused(int dtype, const PoolGeom& g, int64_t batch) {
+  PoolFusedPlan p{false, 0, 0, 0, 0};
+  p.V = dtype == B200_DT_FLOAT ? 4 : 8;
+  if (g.C % p.V != 0) return p;
+  const int G = g.C / p.V;
+  if (G < 1 || G > 32 || (G & (G - 1)) != 0) return p;
+  // the windows tile the input exactly: every input cell belongs to exactly one window
+  if (g.sh != g.wh || g.sw != g.ww || g.pt != 0 || g.pl != 0 || g.OH <= 0 || g.OW <= 0 ||
+      (long long)g.OH * g.sh < g.H || (long long)g.OW * g.sw < g.W)
+    return p;
+  p.G = G;
+  p.total = (long long)batch * g.OH * g.OW * G;
+  long long blocks = (p.total + 255) / 256;
+  const long long cap = 8LL * sm_count();
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  p.blocks = (int)blocks;
+  p.ok = true;
+  return p;
+}
+
 static int check_pool_args(const char* what, int dtype, int64_t batch, int64_t in_h, int64_t in_w,
                            int64_t channels, int64_t out_h, int64_t out_w, int window_h,
                            int window_w, int stride_h, int stride_w, int pad_top, int pad_left,
@@ -360,6 +516,69 @@ int b200_max_pool_grad(int dtype, const void* orig_in, const void* orig_out, con
   }
   note_launch();
   return check_launch("b200_max_pool_grad");
+}
+
+size_t b200_max_pool_grad_relu_bias_grad_workspace_bytes(int dtype, int64_t batch, int64_t in_h,
+                                                         int64_t in_w, int64_t channels,
+                                                         int64_t out_h, int64_t out_w, int window_h,
+                                                         int window_w, int stride_h, int stride_w,
+                                                         int pad_top, int pad_left) {
+  PoolGeom g;
+  if (check_pool_args("b200_max_pool_grad_relu_bias_grad_workspace_bytes", dtype, batch, in_h, in_w,
+                      channels, out_h, out_w, window_h, window_w, stride_h, stride_w, pad_top,
+                      pad_left, &g) != B200_OK)
+    return 0;
+  const PoolFusedPlan p = plan_pool_fused(dtype, g, batch);
+  return p.ok ? (size_t)p.blocks * (size_t)channels * sizeof(float) : 0;
+}
+
+int b200_max_pool_grad_relu_bias_grad(int dtype, const void* orig_in, const void* grad,
+                                      void* backprops, void* bias_grad, int64_t batch,
+                                      int64_t in_h, int64_t in_w, int64_t channels, int64_t out_h,
+                                      int64_t out_w, int window_h, int window_w, int stride_h,
+                                      int stride_w, int pad_top, int pad_left, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  PoolGeom g;
+  int rc = check_pool_args("b200_max_pool_grad_relu_bias_grad", dtype, batch, in_h, in_w, channels,
+                           out_h, out_w, window_h, window_w, stride_h, stride_w, pad_top, pad_left,
+                           &g);
+  if (rc) return rc;
+  const PoolFusedPlan p = plan_pool_fused(dtype, g, batch);
+  static const bool off = getenv("B200TF_NO_POOL_GRAD_FUSION") != nullptr;
+  if (!p.ok || off || batch == 0 || !aligned16(orig_in) || !aligned16(grad) ||
+      !aligned16(backprops)) {
+    // the caller composes b200_max_pool_grad + b200_relu_grad_bias_grad instead
+    set_last_error("b200_max_pool_grad_relu_bias_grad: geometry outside the fused kernel (windows "
+                   "must tile the input, C / (16 B) a power of two <= 32)");
+    return B200_UNIMPLEMENTED;
+  }
+  const size_t need = (size_t)p.blocks * (size_t)channels * sizeof(float);
+  if (!workspace || workspace_bytes < need) {
+    set_last_error("b200_max_pool_grad_relu_bias_grad: workspace too small (%zu < %zu bytes)",
+                   workspace_bytes, need);
+    return B200_INVALID_ARGUMENT;
+  }
+  rc = require_device("b200_max_pool_grad_relu_bias_grad");
+  if (rc) return rc;
+  cudaStream_t s = as_stream(stream);
+  static std::atomic<unsigned> next_slot{0};
+  unsigned int* base = nullptr;
+  if (cudaGetSymbolAddress(reinterpret_cast<void**>(&base), g_pool_fused_tickets) != cudaSuccess)
+    return check_launch("b200_max_pool_grad_relu_bias_grad");
+  unsigned int* ticket = base + next_slot.fetch_add(1) % kPoolFusedSlots;
+  float* partial = static_cast<float*>(workspace);
+  if (dtype == B200_DT_FLOAT)
+    launch_pdl(max_pool_grad_relu_bias_kernel<float, 4>, dim3(p.blocks), dim3(256), 0, s,
+               static_cast<const float*>(orig_in), static_cast<const float*>(grad),
+               static_cast<float*>(backprops), partial, static_cast<float*>(bias_grad), g, p.total,
+               p.G, ticket);
+  else
+    launch_pdl(max_pool_grad_relu_bias_kernel<__nv_bfloat16, 8>, dim3(p.blocks), dim3(256), 0, s,
+               static_cast<const __nv_bfloat16*>(orig_in), static_cast<const __nv_bfloat16*>(grad),
+               static_cast<__nv_bfloat16*>(backprops), partial,
+               static_cast<__nv_bfloat16*>(bias_grad), g, p.total, p.G, ticket);
+  note_launch();
+  return check_launch("b200_max_pool_grad_relu_bias_grad");
 }
 
 }  // extern "C"

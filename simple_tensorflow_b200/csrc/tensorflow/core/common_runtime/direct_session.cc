@@ -335,6 +335,7 @@ Status DirectSession::GetOrCreateExecutors(const std::vector<std::string>& feeds
   if (getenv("B200TF_DISABLE_FUSION") == nullptr) {
     TF_RETURN_IF_ERROR(FuseMatMulChains(ek.get()));
     TF_RETURN_IF_ERROR(FuseReluGradBiasGrad(ek.get()));
+    TF_RETURN_IF_ERROR(FusePoolGradReluGradBiasGrad(ek.get()));
     TF_RETURN_IF_ERROR(FuseXentScale(ek.get()));
     TF_RETURN_IF_ERROR(FuseApplyGradientDescent(ek.get()));
   }
@@ -422,6 +423,61 @@ Status DirectSession::FuseReluGradBiasGrad(ExecutorsAndKeys* ek) {
     --ek->entry_consumers[rg.out_entry(0)];
     bg.dead = true;
     ek->order[i] = std::move(repl);  // at the ReluGrad's position: every consumer comes later
+    ek->rewritten.push_back(std::move(fused));
+  }
+  std::vector<PlanNode> alive;
+  for (PlanNode& pn : ek->order)
+    if (!pn.dead) alive.push_back(std::move(pn));
+  ek->order.swap(alive);
+  return Status::OK();
+}
+
+// MaxPoolGrad whose only reader is a `_ReluGradBiasAddGrad` masking with the pool's own input (the
+// backward tail of conv -> bias -> relu -> max_pool: the pool's orig_input IS the Relu output):
+// `_MaxPoolGradReluGradBiasAddGrad` reads that tensor once for both the window winner and the mask
+// and never materialises the pool gradient.
+Status DirectSession::FusePoolGradReluGradBiasGrad(ExecutorsAndKeys* ek) {
+  for (size_t i = 0; i < ek->order.size(); ++i) {
+    PlanNode& pg = ek->order[i];
+    if (pg.dead || pg.node < 0 || pg.item->def.op != "MaxPoolGrad" || pg.inputs.size() != 3) continue;
+    const DataType dt = pg.item->kernel->input_type(0);
+    if (dt != DT_FLOAT && dt != DT_BFLOAT16) continue;
+    if (pg.inputs[0].feed >= 0 || pg.inputs[1].feed >= 0 || pg.inputs[2].feed >= 0) continue;
+    std::string fmt = "NHWC";
+    GetNodeAttr(pg.item->def, "data_format", &fmt);
+    if (fmt != "NHWC") continue;
+    const int dx_entry = pg.out_entry(0);
+    if (ek->entry_consumers[dx_entry] != 1 || ek->entry_is_fetch[dx_entry]) continue;
+    // the fused ReluGrad + BiasAddGrad reading MaxPoolGrad:0 with features == the pool's input
+    int j = -1;
+    for (size_t k = i + 1; k < ek->order.size() && j < 0; ++k) {
+      const PlanNode& c = ek->order[k];
+      if (c.dead || c.item->def.op != "_ReluGradBiasAddGrad" || c.inputs.size() != 2) continue;
+      if (c.inputs[0].feed < 0 && c.inputs[0].id.node == pg.node && c.inputs[0].id.slot == 0)
+        j = static_cast<int>(k);
+    }
+    if (j < 0) continue;
+    PlanNode& rb = ek->order[j];
+    if (rb.inputs[1].feed >= 0 || rb.inputs[1].id.node != pg.inputs[0].id.node ||
+        rb.inputs[1].id.slot != pg.inputs[0].id.slot)
+      continue;
+    std::unique_ptr<NodeItem> fused(new NodeItem);
+    fused->def.name = rb.item->def.name + "/_pool_grad";
+    fused->def.op = "_MaxPoolGradReluGradBiasAddGrad";
+    fused->def.attr = pg.item->def.attr;  // T, ksize, strides, padding, data_format
+    fused->def.input = pg.item->def.input;
+    TF_RETURN_IF_ERROR(EnsureKernel(fused.get()));
+    PlanNode repl;
+    repl.node = -1;
+    repl.item = fused.get();
+    repl.first_entry = rb.first_entry;
+    repl.inputs = pg.inputs;
+    repl.output_entries = {rb.out_entry(0), rb.out_entry(1)};
+    // the pool's input loses one reader (the ReluGrad's features), the pool gradient its only one
+    --ek->entry_consumers[entry_index_of(ek, pg.inputs[0].id)];
+    ek->entry_consumers[dx_entry] = 0;
+    pg.dead = true;
+    ek->order[j] = std::move(repl);  // at the ReluGrad's position: its consumers come later
     ek->rewritten.push_back(std::move(fused));
   }
   std::vector<PlanNode> alive;

@@ -167,6 +167,7 @@ class DirectSession : public Session {
   void DropGraph(ExecutorsAndKeys* ek);
   void DropAllGraphs();
   Status FuseReluGradBiasGrad(ExecutorsAndKeys* ek);
+  Status FusePoolGradReluGradBiasGrad(ExecutorsAndKeys* ek);
   void PlanGradientArenas(ExecutorsAndKeys* ek);
   Status RunPlan(ExecutorsAndKeys* ek, const std::vector<std::pair<std::string, Tensor>>& inputs,
                  std::vector<Tensor>* outputs);

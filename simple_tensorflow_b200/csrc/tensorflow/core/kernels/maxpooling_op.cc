@@ -137,10 +137,92 @@ class MaxPoolingGradOp : public OpKernel {
   PoolAttrs attrs_;
 };
 
-#define REGISTER_GPU(T)                                                                      \
-  REGISTER_KERNEL_BUILDER(Name("MaxPool").Device(DEVICE_GPU).TypeConstraint<T>("T"),         \
-                          MaxPoolingOp<T>);                                                  \
-  REGISTER_KERNEL_BUILDER(Name("MaxPoolGrad").Device(DEVICE_GPU).TypeConstraint<T>("T"),     \
+// `_MaxPoolGradReluGradBiasAddGrad` (NHWC only; the rewrite checks the format): one kernel when the
+// windows tile the input, else MaxPoolGrad into a temporary followed by the fused
+// ReluGrad + BiasAddGrad -- the same arithmetic as the three graph nodes.
+template <typename T>
+class MaxPoolGradReluGradBiasAddGradOp : public OpKernel {
+ public:
+  explicit MaxPoolGradReluGradBiasAddGradOp(OpKernelConstruction* context) : OpKernel(context) {
+    OP_REQUIRES_OK(context, attrs_.Init(context));
+    OP_REQUIRES(context, !attrs_.nchw,
+                errors::InvalidArgument("_MaxPoolGradReluGradBiasAddGrad is NHWC-only"));
+  }
+  void Compute(OpKernelContext* context) override {
+    const Tensor& tensor_in = context->input(0);
+    const Tensor& out_backprop = context->input(2);
+    OP_REQUIRES(context, tensor_in.dims() == 4,
+                errors::InvalidArgument("tensor_in must be 4-dimensional"));
+    OP_REQUIRES(context, out_backprop.dims() == 4,
+                errors::InvalidArgument("out_backprop must be 4-dimensional"));
+    PoolDims d;
+    OP_REQUIRES_OK(context, ComputePoolDims(tensor_in.shape(), attrs_, &d));
+    const TensorShape expect({d.batch, d.out_rows, d.out_cols, d.depth});
+    OP_REQUIRES(context, out_backprop.shape() == expect,
+                errors::InvalidArgument("out_backprop shape ", out_backprop.shape().DebugString(),
+                                        " does not match the pooled shape ", expect.DebugString()));
+    Tensor* backprops = nullptr;
+    OP_REQUIRES_OK(context, context->allocate_output(0, tensor_in.shape(), &backprops));
+    Tensor* bias_grad = nullptr;
+    OP_REQUIRES_OK(context, context->allocate_output(1, TensorShape({d.depth}), &bias_grad));
+    if (d.depth == 0) return;
+    void* stream = GetCudaStream(context);
+    if (backprops->NumElements() == 0) {
+      OP_REQUIRES_OK(context, FromAbi(b200_memset_async(bias_grad->raw_data(), 0,
+                                                        bias_grad->TotalBytes(), stream),
+                                      "BiasAddGrad"));
+      return;
+    }
+    const int dt = AbiType<T>::v;
+    const size_t ws = b200_max_pool_grad_relu_bias_grad_workspace_bytes(
+        dt, d.batch, d.rows, d.cols, d.depth, d.out_rows, d.out_cols, attrs_.ksize[1],
+        attrs_.ksize[2], attrs_.stride[1], attrs_.stride[2], (int)d.pad_rows, (int)d.pad_cols);
+    if (ws > 0) {
+      Tensor scratch;
+      OP_REQUIRES_OK(context, context->allocate_temp(DT_UINT8, TensorShape({(int64)ws}), &scratch));
+      const int rc = b200_max_pool_grad_relu_bias_grad(
+          dt, tensor_in.raw_data(), out_backprop.raw_data(), backprops->raw_data(),
+          bias_grad->raw_data(), d.batch, d.rows, d.cols, d.depth, d.out_rows, d.out_cols,
+          attrs_.ksize[1], attrs_.ksize[2], attrs_.stride[1], attrs_.stride[2], (int)d.pad_rows,
+          (int)d.pad_cols, scratch.raw_data(), ws, stream);
+      if (rc != B200_UNIMPLEMENTED) {
+        OP_REQUIRES_OK(context, FromAbi(rc, "_MaxPoolGradReluGradBiasAddGrad"));
+        return;
+      }
+    }
+    Tensor dx;
+    OP_REQUIRES_OK(context, context->allocate_temp(backprops->dtype(), tensor_in.shape(), &dx));
+    OP_REQUIRES_OK(context,
+                   FromAbi(b200_max_pool_grad(dt, tensor_in.raw_data(), nullptr,
+                                              out_backprop.raw_data(), dx.raw_data(), d.batch,
+                                              d.rows, d.cols, d.depth, d.out_rows, d.out_cols,
+                                              attrs_.ksize[1], attrs_.ksize[2], attrs_.stride[1],
+                                              attrs_.stride[2], (int)d.pad_rows, (int)d.pad_cols,
+                                              stream),
+                           "MaxPoolGrad"));
+    const int64 rows = dx.NumElements() / d.depth;
+    const size_t ws2 = b200_relu_grad_bias_grad_workspace_bytes(dt, rows, d.depth);
+    Tensor scratch2;
+    if (ws2 > 0)
+      OP_REQUIRES_OK(context, context->allocate_temp(DT_UINT8, TensorShape({(int64)ws2}), &scratch2));
+    OP_REQUIRES_OK(context, FromAbi(b200_relu_grad_bias_grad(
+                                        dt, dx.raw_data(), tensor_in.raw_data(),
+                                        backprops->raw_data(), bias_grad->raw_data(), rows, d.depth,
+                                        ws2 ? scratch2.raw_data() : nullptr, ws2, stream),
+                                    "_ReluGradBiasAddGrad"));
+  }
+
+ private:
+  PoolAttrs attrs_;
+};
+
+#define REGISTER_GPU(T)                                                                             \
+  REGISTER_KERNEL_BUILDER(                                                                          \
+      Name("_MaxPoolGradReluGradBiasAddGrad").Device(DEVICE_GPU).TypeConstraint<T>("T"),            \
+      MaxPoolGradReluGradBiasAddGradOp<T>);                                                         \
+  REGISTER_KERNEL_BUILDER(Name("MaxPool").Device(DEVICE_GPU).TypeConstraint<T>("T"),                \
+                          MaxPoolingOp<T>);                                                         \
+  REGISTER_KERNEL_BUILDER(Name("MaxPoolGrad").Device(DEVICE_GPU).TypeConstraint<T>("T"),            \
                           MaxPoolingGradOp<T>);
 REGISTER_B200_FLOAT_TYPES(REGISTER_GPU)
 #undef REGISTER_GPU

@@ -118,6 +118,14 @@ REGISTER_OP("_ReluGradBiasAddGrad")
     .Input("gradients: T").Input("features: T").Output("backprops: T").Output("bias_grad: T")
     .Attr("T: {float, bfloat16}");
 
+// Executor-internal (DirectSession::FusePoolGradReluGradBiasGrad): MaxPoolGrad whose only reader
+// is a `_ReluGradBiasAddGrad` that masks with the pool's own input (the Relu output).
+REGISTER_OP("_MaxPoolGradReluGradBiasAddGrad")
+    .Input("orig_input: T").Input("orig_output: T").Input("grad: T")
+    .Output("backprops: T").Output("bias_grad: T")
+    .Attr("ksize: list(int) >= 4").Attr("strides: list(int) >= 4")
+    .Attr("padding: {'SAME', 'VALID'}").Attr(DATA_FORMAT_ATTR).Attr("T: {float, bfloat16}");
+
 // math_ops.cc:1330-1343 ("Sum": same signature as "Mean")
 REGISTER_OP("Sum")
     .Input("input: T").Input("reduction_indices: Tidx").Output("output: T")

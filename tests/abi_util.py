@@ -204,6 +204,24 @@ def max_pool_grad(x, grad, ksize, strides, padding, oracle, bf16=False):
     return host(out)
 
 
+def max_pool_grad_relu_bias_grad(x, grad, ksize, strides, padding, bf16=False):
+    """Returns (backprops, bias_grad), or None when the geometry is outside the fused kernel."""
+    L = lib()
+    n, h, w, c = x.shape
+    oh, ow, pt, pl = pool_geometry(x.shape, ksize, strides, padding)
+    geo = (n, h, w, c, oh, ow, ksize[0], ksize[1], strides[0], strides[1], pt, pl)
+    nb = L.b200_max_pool_grad_relu_bias_grad_workspace_bytes(cdt(bf16), *geo)
+    if nb == 0:
+        return None
+    dx, dg = dev(x, bf16), dev(grad, bf16)
+    out = empty(x.shape, tdt(bf16), fill=float("nan"))
+    db = empty((c,), tdt(bf16), fill=float("nan"))
+    wk = ws(nb)
+    call(L.b200_max_pool_grad_relu_bias_grad, cdt(bf16), dx.data_ptr(), dg.data_ptr(), out.data_ptr(),
+         db.data_ptr(), *geo, wk.data_ptr(), nb, stream())
+    return host(out), host(db)
+
+
 def cast(x, src, dst):
     """src/dst: numpy dtypes or the string 'bf16' (bf16 travels as uint16 bit patterns)."""
     L = lib()

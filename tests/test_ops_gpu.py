@@ -73,6 +73,20 @@ def test_matmul_skinny_n(oracle, rng, m, n, k, ta, tb):
     np.testing.assert_array_equal(got, au.matmul(a, b, ta, tb))
 
 
+@pytest.mark.parametrize("shape", [(3, 1000, 200, 1), (5, 1, 200, 1000), (2, 70, 64, 3), (4, 2, 100, 333),
+                                   (1, 9, 129, 640)])
+@pytest.mark.parametrize("adj_x", [False, True])
+@pytest.mark.parametrize("adj_y", [False, True])
+def test_batch_matmul_vector_shapes(oracle, rng, shape, adj_x, adj_y):
+    # matrix-vector / vector-matrix products (batch_matmul_op_test.cc:107-132): the K-split kernel,
+    # batched; skinny-M runs as the transposed problem
+    batch, m, k, n = shape
+    x = rng.uniform(-1, 1, (batch, k, m) if adj_x else (batch, m, k)).astype(np.float32)
+    y = rng.uniform(-1, 1, (batch, n, k) if adj_y else (batch, k, n)).astype(np.float32)
+    got = au.batch_matmul(x, y, adj_x, adj_y)
+    assert au.rel_err(got, oracle.batch_matmul(x, y, adj_x, adj_y)) < TOL_TF32
+
+
 def test_matmul_integer_inputs_exact(oracle, rng):
     # integers <= 2048 are exact in tf32 and their sums are exact in the fp32 accumulator
     a = rng.randint(-8, 9, (256, 192)).astype(np.float32)
@@ -641,6 +655,46 @@ def test_conv1_full_size_vs_oracle(oracle, rng):
     dy = rng.rand(*y_ref.shape).astype(np.float32) - 0.5
     dw = au.conv2d_backprop_filter(x, fshape, dy, (1, 1), "SAME", oracle)
     assert au.rel_err(dw, oracle.conv2d_backprop_filter(x, fshape, dy, (1, 1), "SAME")) < TOL_TF32
+
+
+# =============================================================================== fused pool backward
+@pytest.mark.parametrize("shape,ksize,padding", [((8, 28, 28, 32), (2, 2), "VALID"),
+                                                 ((4, 14, 14, 64), (2, 2), "SAME"),
+                                                 ((3, 9, 7, 32), (2, 2), "SAME"),   # clipped last windows
+                                                 ((2, 12, 9, 128), (3, 3), "VALID"),
+                                                 ((5, 6, 6, 4), (2, 3), "VALID")])
+def test_max_pool_grad_relu_bias_grad_fused(oracle, rng, shape, ksize, padding):
+    # = MaxPoolGrad -> ReluGrad(features = the pool input) -> BiasAddGrad, three oracle calls
+    x = rng.uniform(-1, 1, shape).astype(np.float32)
+    x[rng.rand(*shape) < 0.3] = 0.0               # exact zeros: relu mask is strict (f > 0)
+    x[0, :2, :2, :] = 0.25                         # ties: the first maximum wins
+    oh, ow, _, _ = au.pool_geometry(shape, ksize, ksize, padding)
+    g = rng.uniform(-1, 1, (shape[0], oh, ow, shape[3])).astype(np.float32)
+    got = au.max_pool_grad_relu_bias_grad(x, g, ksize, ksize, padding)
+    assert got is not None
+    dx = oracle.max_pool_grad(x, g, ksize, ksize, padding)
+    dy = oracle.relu_grad(dx, x)
+    np.testing.assert_array_equal(got[0], dy)
+    ref_db = dy.reshape(-1, shape[3]).astype(np.float64).sum(0)
+    assert au.rel_err(got[1], ref_db) < 1e-5
+    again = au.max_pool_grad_relu_bias_grad(x, g, ksize, ksize, padding)
+    np.testing.assert_array_equal(got[1], again[1])  # ordered reduction
+
+
+def test_max_pool_grad_relu_bias_grad_fused_bf16_and_limits(oracle, rng):
+    shape = (4, 8, 8, 64)
+    x = oracle.truncate_to_bf16(rng.uniform(-1, 1, shape).astype(np.float32))
+    g = oracle.truncate_to_bf16(rng.uniform(-1, 1, (4, 4, 4, 64)).astype(np.float32))
+    got = au.max_pool_grad_relu_bias_grad(x, g, (2, 2), (2, 2), "VALID", bf16=True)
+    dy = oracle.relu_grad(oracle.max_pool_grad(x, g, (2, 2), (2, 2), "VALID"), x)
+    np.testing.assert_array_equal(got[0], dy)
+    assert au.rel_err(got[1], dy.reshape(-1, 64).astype(np.float64).sum(0)) < TOL
+    # overlapping windows / windows that leave cells uncovered / odd channel counts: not fused
+    xf = rng.uniform(-1, 1, (2, 9, 9, 32)).astype(np.float32)
+    assert au.max_pool_grad_relu_bias_grad(xf, np.zeros((2, 4, 4, 32), np.float32), (3, 3), (2, 2), "VALID") is None
+    assert au.max_pool_grad_relu_bias_grad(xf, np.zeros((2, 4, 4, 32), np.float32), (2, 2), (2, 2), "VALID") is None
+    xo = rng.uniform(-1, 1, (2, 8, 8, 12)).astype(np.float32)
+    assert au.max_pool_grad_relu_bias_grad(xo, np.zeros((2, 4, 4, 12), np.float32), (2, 2), (2, 2), "VALID") is None
 
 
 # =============================================================================== glue ops

@@ -282,6 +282,43 @@ def test_fusion_rewrite_matches_unfused(oracle, rng, monkeypatch):
         np.testing.assert_allclose(a, b, rtol=1e-4, atol=5e-5)
 
 
+@pytest.mark.parametrize("hw,ksize", [((12, 12), 2), ((9, 9), 2)])
+def test_pool_grad_relu_grad_bias_grad_rewrite(rng, monkeypatch, hw, ksize):
+    # conv -> bias -> relu -> max_pool: the backward tail MaxPoolGrad -> ReluGrad -> BiasAddGrad
+    # runs as one `_MaxPoolGradReluGradBiasAddGrad` node (one kernel when the windows tile the
+    # input -- 12x12 -- and the two-kernel composition when they do not -- 9x9 VALID); same values
+    # as the op-by-op execution, the bias gradient up to its summation order
+    B, C, K = 6, 32, 64
+    x = rng.uniform(-1, 1, (B, hw[0], hw[1], C)).astype(np.float32)
+    w = (rng.randn(3, 3, C, K) * 0.1).astype(np.float32)
+    b = (rng.randn(K) * 0.1).astype(np.float32)
+
+    def run(disable):
+        if disable:
+            monkeypatch.setenv("B200TF_DISABLE_FUSION", "1")
+        else:
+            monkeypatch.delenv("B200TF_DISABLE_FUSION", raising=False)
+        tf.reset_default_graph()
+        xp = tf.placeholder(tf.float32, list(x.shape))
+        wv, bv = tf.Variable(w, name="w"), tf.Variable(b, name="b")
+        a = tf.relu(tf.bias_add(tf.conv2d(xp, wv, [1, 1, 1, 1], "SAME"), bv))
+        p = tf.max_pool(a, [1, ksize, ksize, 1], [1, ksize, ksize, 1], "VALID")
+        loss = tf.reduce_sum(tf.multiply(p, p))
+        gx, gw, gb = tf.gradients(loss, [xp, wv, bv])
+        with client.Session(tf.get_default_graph()) as sess:
+            sess.run(tf.global_variables_initializer())
+            out = sess.run([gx, gw, gb], {xp: x})
+            return out, sess.last_run_stats()
+
+    ref, s0 = run(disable=True)
+    got, s1 = run(disable=False)
+    assert s1["nodes_executed"] < s0["nodes_executed"]
+    np.testing.assert_allclose(got[2], ref[2], rtol=1e-5, atol=1e-5)
+    # dY is bit-identical, so the convolution gradients are too
+    np.testing.assert_array_equal(got[0], ref[0])
+    np.testing.assert_array_equal(got[1], ref[1])
+
+
 def test_xent_scale_rewrite_is_bit_exact(rng, monkeypatch):
     # xent -> Mul(backprop, 1/N) (the gradient of a mean loss) runs as one scaled xent kernel:
     # (softmax - labels) is rounded to fp32 and then multiplied, exactly like the two-op form
