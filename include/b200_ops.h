@@ -381,6 +381,10 @@ B200_API int b200_peer_arena_create(void* nccl_comm, int rank, int nranks, size_
 /* What the last arena created in this process runs on: "nvls" (NVSwitch multicast memory, in-switch
  * reduction: nvls_allreduce.cu), "peer-ipc" (peer-mapped buffers, peer_allreduce.cu) or "none". */
 B200_API const char* b200_peer_arena_backend(void);
+/* 1 when the current device / driver can back an arena with NVSwitch multicast memory (and
+ * B200TF_NVLS is not 0): what a front-end asks before it decides to bucket the gradient exchange
+ * for overlap (simple_tensorflow_b200/ops.py apply_gradients).  No reference counterpart. */
+B200_API int b200_nvls_supported(void);
 B200_API int b200_peer_arena_destroy(void* arena);
 B200_API void* b200_peer_arena_data(void* arena);
 B200_API size_t b200_peer_arena_bytes(void* arena);

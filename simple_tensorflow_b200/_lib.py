@@ -140,6 +140,7 @@ SIGNATURES = {
     "b200_nccl_all_gather_bytes": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "b200_peer_arena_create": (c_int, [c_void_p, c_int, c_int, c_size_t, ctypes.POINTER(c_void_p)]),
     "b200_peer_arena_backend": (ctypes.c_char_p, []),
+    "b200_nvls_supported": (c_int, []),
     "b200_peer_arena_destroy": (c_int, [c_void_p]),
     "b200_peer_arena_data": (c_void_p, [c_void_p]),
     "b200_peer_arena_bytes": (c_size_t, [c_void_p]),

@@ -511,3 +511,24 @@ int nvls_all_reduce(NvlsArena* a, int dtype, size_t offset_bytes, long long coun
 }
 
 }  // namespace b200
+
+extern "C" int b200_nvls_supported(void) {
+  // 1: the current device and driver can put memory behind an NVSwitch multicast object (the
+  // per-device half of nvls_arena_create's first vote); B200TF_NVLS=0 answers 0 as well.
+  const char* nv = getenv("B200TF_NVLS");
+  if (nv != nullptr && std::strcmp(nv, "0") == 0) return 0;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count < 1) {
+    cudaGetLastError();
+    return 0;
+  }
+  const b200::VmmApi& v = b200::vmm();
+  if (!v.ok) return 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaFree(nullptr);  // a context for the driver API
+  int mc = 0;
+  if (v.DeviceGetAttribute(&mc, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev) != CUDA_SUCCESS)
+    return 0;
+  return mc ? 1 : 0;
+}

@@ -220,11 +220,18 @@ Status DirectSession::GetOrCreateExecutors(const std::vector<std::string>& feeds
   // Measured on 4 and 8 B200 (profiles/r01_notes.md): NCCL's 24-32 CTAs land on as many TPCs
   // and break up the CTA pairs of the persistent GEMMs running beside them, so the side-stream
   // exchange costs more than it hides; the default is one in-place all-reduce of the whole
-  // gradient arena on the compute stream.  B200TF_COLLECTIVE_OVERLAP=1 turns the overlap on.
+  // gradient arena on the compute stream for the NCCL and peer-IPC exchanges.
+  // Round 2: with the gradient arena in NVSwitch multicast memory the exchange is a 16-CTA kernel
+  // whose reduction happens in the switch; it no longer disturbs the GEMMs, so on that backend the
+  // overlap is the default (and captured into the step's CUDA graph).  B200TF_COLLECTIVE_OVERLAP=0 / 1
+  // forces either behaviour.
   const char* ov = getenv("B200TF_COLLECTIVE_OVERLAP");
-  const bool overlap_collectives = device_->num_replicas() > 1 &&
-                                   device_->collective_comm() != nullptr && ov != nullptr &&
-                                   std::strcmp(ov, "1") == 0;
+  const bool overlap_default = std::strcmp(b200_peer_arena_backend(), "nvls") == 0;
+  // A plan with feeds is not graph-captured; there the side stream costs more host time than the
+  // overlap returns (measured at N = 2), so it keeps the single exposed exchange.
+  const bool overlap_collectives =
+      device_->num_replicas() > 1 && device_->collective_comm() != nullptr &&
+      (ov != nullptr ? std::strcmp(ov, "1") == 0 : (overlap_default && feeds.empty()));
   auto is_collective = [&](int n) {
     return overlap_collectives && nodes_[n]->def.op.rfind("B200AllReduce", 0) == 0 &&
            nodes_[n]->def.op != "B200AllReduce";  // the ref-variable form stays on compute
@@ -338,6 +345,9 @@ Status DirectSession::GetOrCreateExecutors(const std::vector<std::string>& feeds
     TF_RETURN_IF_ERROR(FusePoolGradReluGradBiasGrad(ek.get()));
     TF_RETURN_IF_ERROR(FuseXentScale(ek.get()));
     TF_RETURN_IF_ERROR(FuseApplyGradientDescent(ek.get()));
+    // gradient buckets exist to be overlapped; exposed on the compute stream, one exchange is
+    // cheaper than several (each pays the ~12 us barrier latency)
+    if (!overlap_collectives) TF_RETURN_IF_ERROR(MergeAllReduceBuckets(ek.get()));
   }
   if (!EnvFlagOff("B200TF_GRADIENT_ARENA")) PlanGradientArenas(ek.get());
   *out = ek.get();
@@ -480,6 +490,68 @@ Status DirectSession::FusePoolGradReluGradBiasGrad(ExecutorsAndKeys* ek) {
     ek->order[j] = std::move(repl);  // at the ReluGrad's position: its consumers come later
     ek->rewritten.push_back(std::move(fused));
   }
+  std::vector<PlanNode> alive;
+  for (PlanNode& pn : ek->order)
+    if (!pn.dead) alive.push_back(std::move(pn));
+  ek->order.swap(alive);
+  return Status::OK();
+}
+
+// Several B200AllReduceN buckets of one dtype and scale, all on the compute stream: one node that
+// reduces every gradient in a single exchange, placed where the last bucket was (all inputs exist
+// there; the merge is skipped if a consumer of an earlier bucket would then run too early).
+Status DirectSession::MergeAllReduceBuckets(ExecutorsAndKeys* ek) {
+  std::vector<size_t> buckets;
+  for (size_t i = 0; i < ek->order.size(); ++i) {
+    const PlanNode& pn = ek->order[i];
+    if (pn.dead || pn.node < 0 || pn.collective >= 0 || pn.item->def.op != "B200AllReduceN") continue;
+    bool fed = false;
+    for (const InputSource& in : pn.inputs) fed = fed || in.feed >= 0;
+    if (fed) continue;
+    if (!buckets.empty()) {
+      const NodeDef& first = ek->order[buckets.front()].item->def;
+      DataType t0 = DT_INVALID, t1 = DT_INVALID;
+      float s0 = 1.f, s1 = 1.f;
+      GetNodeAttr(first, "T", &t0);
+      GetNodeAttr(pn.item->def, "T", &t1);
+      GetNodeAttr(first, "scale", &s0);
+      GetNodeAttr(pn.item->def, "scale", &s1);
+      if (t0 != t1 || s0 != s1) continue;
+    }
+    buckets.push_back(i);
+  }
+  if (buckets.size() < 2) return Status::OK();
+  const size_t last = buckets.back();
+  // no reader of an earlier bucket may sit before the merged node
+  for (size_t b = 0; b + 1 < buckets.size(); ++b) {
+    const int producer = ek->order[buckets[b]].node;
+    for (size_t k = buckets[b] + 1; k < last; ++k) {
+      if (ek->order[k].dead) continue;
+      for (const InputSource& in : ek->order[k].inputs)
+        if (in.feed < 0 && in.id.node == producer) return Status::OK();
+    }
+  }
+  std::unique_ptr<NodeItem> fused(new NodeItem);
+  fused->def.name = ek->order[last].item->def.name + "/_merged";
+  fused->def.op = "B200AllReduceN";
+  fused->def.attr = ek->order[last].item->def.attr;
+  PlanNode repl;
+  repl.node = -1;
+  repl.first_entry = ek->order[buckets.front()].first_entry;
+  for (size_t b : buckets) {
+    const PlanNode& pn = ek->order[b];
+    for (size_t i = 0; i < pn.inputs.size(); ++i) {
+      repl.inputs.push_back(pn.inputs[i]);
+      fused->def.input.push_back(pn.item->def.input[i]);
+      repl.output_entries.push_back(pn.out_entry(static_cast<int>(i)));
+    }
+  }
+  fused->def.attr["N"] = AttrValue::I(static_cast<int64>(repl.inputs.size()));
+  TF_RETURN_IF_ERROR(EnsureKernel(fused.get()));
+  repl.item = fused.get();
+  for (size_t b = 0; b + 1 < buckets.size(); ++b) ek->order[buckets[b]].dead = true;
+  ek->order[last] = std::move(repl);
+  ek->rewritten.push_back(std::move(fused));
   std::vector<PlanNode> alive;
   for (PlanNode& pn : ek->order)
     if (!pn.dead) alive.push_back(std::move(pn));
@@ -761,7 +833,10 @@ bool DirectSession::GraphEligible(ExecutorsAndKeys* ek, size_t num_feeds) {
   // producer memory space of every entry
   std::vector<int> entry_host(ek->num_entries, 0);
   for (const PlanNode& pn : ek->order) {
-    if (pn.collective >= 0) return false;
+    // A node on the collective stream is captured too (the event edges fork and join the second
+    // stream inside the capture) as long as it is one of the arena exchanges checked above.
+    if (pn.collective >= 0 && !(replicas && pn.arena >= 0 && pn.item->def.op == "B200AllReduceN"))
+      return false;
     for (int o = 0; o < pn.item->kernel->num_outputs(); ++o)
       entry_host[pn.out_entry(o)] = pn.item->kernel->output_memory_types()[o] == HOST_MEMORY;
   }

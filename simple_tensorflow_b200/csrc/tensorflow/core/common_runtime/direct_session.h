@@ -168,6 +168,7 @@ class DirectSession : public Session {
   void DropAllGraphs();
   Status FuseReluGradBiasGrad(ExecutorsAndKeys* ek);
   Status FusePoolGradReluGradBiasGrad(ExecutorsAndKeys* ek);
+  Status MergeAllReduceBuckets(ExecutorsAndKeys* ek);
   void PlanGradientArenas(ExecutorsAndKeys* ek);
   Status RunPlan(ExecutorsAndKeys* ek, const std::vector<std::pair<std::string, Tensor>>& inputs,
                  std::vector<Tensor>* outputs);

@@ -529,9 +529,12 @@ class B200AllReduceNOp : public OpKernel {
       if (peer_offset >= 0 && average && peer_dtype) {
         // the arena lives in NVLink peer memory: one kernel of peer loads instead of NCCL (its
         // CTAs fit beside resident GEMM CTAs, so it also runs well on the collective stream)
+        // NVLS: 16 CTAs move 4 MB as fast as 128 do (the switch reduces; tools/arena_probe.py)
+        // and leave the SMs to the backward pass they run beside.  0 = the kernel's own default.
         static const int ctas = [] {
           const char* v = getenv("B200TF_PEER_CTAS");
-          return v ? std::atoi(v) : 0;
+          if (v) return std::atoi(v);
+          return std::strcmp(b200_peer_arena_backend(), "nvls") == 0 ? 16 : 0;
         }();
         OP_REQUIRES_OK(ctx, FromAbi(b200_peer_all_reduce(dev->peer_arena(), AbiType<T>::v,
                                                          static_cast<size_t>(peer_offset), total, 1,

@@ -580,6 +580,20 @@ def gradients(ys, xs):
     return [result.get(t.name) for t in targets]
 
 
+def _default_bucket_bytes():
+    """Bucket size that matches how the session will run the exchange (see apply_gradients)."""
+    import os
+    if os.environ.get("B200TF_COLLECTIVE_OVERLAP") == "0":
+        return None
+    try:
+        from . import _lib
+        if _lib.load().b200_nvls_supported() == 1:
+            return 4 << 20
+    except Exception:
+        pass
+    return None
+
+
 class GradientDescentOptimizer:
     """python/training/gradient_descent.py: one ApplyGradientDescent per variable."""
 
@@ -591,18 +605,23 @@ class GradientDescentOptimizer:
         grads = gradients(loss, var_list)
         return list(zip(grads, var_list))
 
-    def apply_gradients(self, grads_and_vars, name=None, num_replicas=1, bucket_bytes=None):
+    def apply_gradients(self, grads_and_vars, name=None, num_replicas=1, bucket_bytes="auto"):
         g = get_default_graph()
         updates = []
         grads_and_vars = [(gr, v) for gr, v in grads_and_vars if gr is not None]
+        if bucket_bytes == "auto":
+            bucket_bytes = _default_bucket_bytes() if num_replicas > 1 else None
         if num_replicas > 1:
             # Replica data-parallel: gradients are averaged across replicas in buckets, filled
             # in the order backprop emits them (graph-construction order) and closed once they
             # hold `bucket_bytes`; each bucket is one collective that the executor starts as
             # soon as its gradients exist (under the rest of the backward pass when the session
             # runs collectives on their own stream, B200TF_COLLECTIVE_OVERLAP=1).
-            # bucket_bytes=None (default, fastest measured on 2-8 B200): a single all-reduce of
-            # one contiguous gradient arena after the whole backward pass.
+            # bucket_bytes=None: a single all-reduce of one contiguous gradient arena after the
+            # whole backward pass.  "auto" (default): 4 MB buckets when the exchange will run as
+            # the 16-CTA NVSwitch multicast kernel, which the session overlaps with the rest of the
+            # backward pass inside the step's CUDA graph; one bucket otherwise (peer-IPC / NCCL
+            # exchanges are faster exposed than overlapped: profiles/r01_notes.md, r02_notes.md).
             reduced = {}
             bucket, held = [], 0
             position = {id(op): i for i, op in enumerate(g.operations)}
@@ -635,6 +654,6 @@ class GradientDescentOptimizer:
                                        "GradientDescent/update_" + var.op.name))
         return group(*updates, name=name or "GradientDescent")
 
-    def minimize(self, loss, var_list=None, name=None, num_replicas=1, bucket_bytes=None):
+    def minimize(self, loss, var_list=None, name=None, num_replicas=1, bucket_bytes="auto"):
         return self.apply_gradients(self.compute_gradients(loss, var_list), name, num_replicas,
                                     bucket_bytes)
