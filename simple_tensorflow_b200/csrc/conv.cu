@@ -15,9 +15,10 @@
 // filter needs no reshuffle: HWIO is already the row-major [R*S*C, K] GEMM operand.  1x1/stride-1
 // convolutions skip the patch matrix entirely (same shortcut as conv_ops.cc:454-480).
 // Data paths, fastest first: unit-stride convolutions whose channel counts are whole 128-byte
-// blocks run the halo-tile kernel (conv_halo.cu: forward and, with the flipped filter, dInput);
-// other strides / the filter gradient use TMA im2col-mode loads on the tcgen05 GEMM (no patch
-// matrix either); first layers (C <= 4) use direct CUDA-core kernels; everything else
+// blocks run the halo-tile kernels (conv_halo.cu: forward and, with the flipped filter, dInput;
+// conv_halo_wgrad.cu: the filter gradient); other strides use TMA im2col-mode loads on the
+// tcgen05 GEMM (no patch matrix either); first layers use CUDA-core kernels (C = 1, unit stride:
+// the lane-per-filter conv_c1_* kernels below; other C <= 4: conv_small_cin_*); everything else
 // materialises the patch matrix in the caller-provided workspace.
 #include <cuda_bf16.h>
 #include <cstdlib>

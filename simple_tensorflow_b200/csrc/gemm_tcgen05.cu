@@ -1237,7 +1237,7 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     static const bool generic_only = getenv("B200TF_SPLITK_REDUCE_GENERIC") != nullptr;
     const bool flat = !generic_only && (s.N & 3) == 0 && s.ldc == s.N &&
                       (g.batch == 1 || (long long)s.strideC == (long long)s.M * s.N) &&
-                      splits >= 2 && splits <= 8 &&
+                      splits >= 2 && splits <= 16 &&
                       (reinterpret_cast<uintptr_t>(s.partial) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(g.c) & 15) == 0;
     cudaError_t e;
@@ -1261,8 +1261,16 @@ static int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
         B200_SPLITK_FLAT(5)
         B200_SPLITK_FLAT(6)
         B200_SPLITK_FLAT(7)
-        default:
         B200_SPLITK_FLAT(8)
+        B200_SPLITK_FLAT(9)
+        B200_SPLITK_FLAT(10)
+        B200_SPLITK_FLAT(11)
+        B200_SPLITK_FLAT(12)
+        B200_SPLITK_FLAT(13)
+        B200_SPLITK_FLAT(14)
+        B200_SPLITK_FLAT(15)
+        default:
+        B200_SPLITK_FLAT(16)
 #undef B200_SPLITK_FLAT
       }
     } else {

@@ -526,7 +526,6 @@ extern "C" int b200_nvls_supported(void) {
   if (!v.ok) return 0;
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-  cudaFree(nullptr);  // a context for the driver API
   int mc = 0;
   if (v.DeviceGetAttribute(&mc, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, dev) != CUDA_SUCCESS)
     return 0;

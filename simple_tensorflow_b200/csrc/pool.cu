@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 
 #include "b200_internal.h"
+#include "ordered_reduce.cuh"
 
 namespace b200 {
 
@@ -316,30 +317,11 @@ max_pool_grad_relu_bias_kernel(const T* __restrict__ in, const T* __restrict__ g
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // ordered final pass: thread (c, part) adds blocks part, part + P, ...; parts combined in order
-  const int P = 256 / C;  // >= 1 (C <= 256)
-  const int c = threadIdx.x % C, part = threadIdx.x / C;
-  float t = 0.f;
-  if (part < P) {
-    const int nb = (int)gridDim.x;
-    for (int b0 = part; b0 < nb; b0 += 8 * P) {
-      float v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int b = b0 + u * P;
-        v[u] = b < nb ? __ldcg(partial + (long long)b * C + c) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) t += v[u];
-    }
-  }
-  float* flat = &sm[0][0][0];  // 8 * 32 * V >= 256 floats
-  __syncthreads();
-  flat[threadIdx.x] = part < P ? t : 0.f;
-  __syncthreads();
+  // ordered final pass over the per-CTA partial rows (ordered_reduce.cuh)
+  __shared__ uint4 slots[8 * 256];
+  __shared__ float flat[256 * 4];
+  const float tot = ordered_partial_sum(partial, (int)gridDim.x, C, slots, flat);
   if ((int)threadIdx.x < C) {
-    float tot = 0.f;
-    for (int q = 0; q < P; ++q) tot += flat[q * C + threadIdx.x];
     if (sizeof(T) == 4)
       reinterpret_cast<float*>(bias_grad)[threadIdx.x] = tot;
     else
@@ -366,7 +348,7 @@ static PoolFusedPlan plan_pool_fused(int dtype, const PoolGeom& g, int64_t batch
   p.G = G;
   p.total = (long long)batch * g.OH * g.OW * G;
   long long blocks = (p.total + 255) / 256;
-  const long long cap = 8LL * sm_count();
+  const long long cap = 4LL * sm_count();  // the ordered tail reads one partial row per CTA
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   p.blocks = (int)blocks;

@@ -14,6 +14,7 @@
 #include <algorithm>
 
 #include "b200_internal.h"
+#include "ordered_reduce.cuh"
 
 namespace b200 {
 
@@ -434,34 +435,11 @@ flat_bias_grad_kernel(const T* __restrict__ g, const T* __restrict__ features, T
   __syncthreads();
   if (!is_last) return;
   __threadfence();
-  // ordered final pass: thread (c, part) adds blocks part, part + P, ...; parts combined in order
-  const int P = 256 / C;  // >= 1 (C <= 256)
-  const int c = threadIdx.x % C, part = threadIdx.x / C;
-  float t = 0.f;
-  if (part < P) {
-    // eight independent loads in flight, added in ascending block order (an `t += load` loop
-    // would serialise one L2 round trip per block: 74 x 0.5 us for a conv layer)
-    const int nb = (int)gridDim.x;
-    for (int b0 = part; b0 < nb; b0 += 8 * P) {
-      float v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int b = b0 + u * P;
-        v[u] = b < nb ? __ldcg(partial + (long long)b * C + c) : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) t += v[u];
-    }
-  }
-  float* flat = &sm[0][0][0];  // 8 * 32 * VEC >= 256 floats
-  __syncthreads();
-  flat[threadIdx.x] = part < P ? t : 0.f;
-  __syncthreads();
-  if ((int)threadIdx.x < C) {
-    float tot = 0.f;
-    for (int q = 0; q < P; ++q) tot += flat[q * C + threadIdx.x];
-    stf<T>(out + threadIdx.x, tot);
-  }
+  // ordered final pass over the per-CTA partial rows (ordered_reduce.cuh)
+  __shared__ uint4 slots[8 * 256];
+  __shared__ float flat[256 * 4];
+  const float tot = ordered_partial_sum(partial, (int)gridDim.x, C, slots, flat);
+  if ((int)threadIdx.x < C) stf<T>(out + threadIdx.x, tot);
   if (threadIdx.x == 0) *ticket = 0;  // ready for the next launch that uses this slot
 }
 
